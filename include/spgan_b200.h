@@ -1,0 +1,173 @@
+/*
+ * spgan_b200.h — C ABI of the B200-native SP-GAN conv hot path (libspgan_b200.so).
+ *
+ * The reference (chronos123/SP-GAN-TIP2025) has no FFI of its own for this path: its boundary is two
+ * pybind11 ops plus PyTorch library calls.  Each entry point below names the reference interface it
+ * replaces (paths relative to the reference root).  Conventions, matching
+ * models/custom_ops/fused_bias_act_kernel.cu:52-99 and upfirdn2d_kernel.cu:209-369:
+ *   - every pointer is a DEVICE pointer to contiguous fp32 (int32 where stated); NULL = "absent tensor"
+ *     (the reference passes an empty tensor for that);
+ *   - outputs are caller-allocated and fully overwritten;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*), nothing synchronises;
+ *   - return value 0 = success, non-zero = failure with a message in spgan_last_error() (the Python host
+ *     raises RuntimeError, as the reference's TORCH_CHECK / CUDA errors do);
+ *   - thread-safe as far as streams are: no global mutable state besides the per-thread error string.
+ * There is no CPU fallback anywhere behind this ABI.
+ */
+#ifndef SPGAN_B200_H
+#define SPGAN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPGAN_ABI_VERSION 1
+#define SPGAN_MAX_TAPS 49
+
+int spgan_abi_version(void);
+const char* spgan_last_error(void);
+/* 1 when a CUDA device with compute capability 10.x is current, else 0 (message in spgan_last_error). */
+int spgan_device_ok(void);
+
+/* ---- K1: fused bias + activation -------------------------------------------------------------------
+ * Replaces fused.fused_bias_act(input, bias, refer, act, grad, alpha, scale)
+ *   (models/custom_ops/fused_bias_act.cpp:11-20, fused_bias_act_kernel.cu:18-49).
+ * out[i] = f(x[i] + bias[(i / step_b) % size_b]) * scale ; act*10+grad: 10/11 linear, 30 lrelu,
+ * 31 lrelu gradient gated by sign of ref[i], 12/32 zero.  bias/ref may be NULL. */
+int spgan_bias_act(float* out, const float* x, const float* bias, const float* ref, int64_t n, int64_t step_b,
+                   int64_t size_b, int act, int grad, float alpha, float scale, void* stream);
+/* Fused first-order backward of fused_leaky_relu (models/custom_ops/fused_act.py:24-44): grad_in = K1(act 3, grad 1)
+ * and grad_bias[c] = sum over batch and pixels of grad_in.  x is (batch, channels, inner). grad_bias is overwritten. */
+int spgan_bias_act_bwd(float* grad_in, float* grad_bias, const float* grad_out, const float* out_ref, int64_t batch,
+                       int64_t channels, int64_t inner, float alpha, float scale, void* stream);
+/* NoiseInjection + FusedLeakyReLU in one pass (models/ops.py:784 then models/custom_ops/fused_act.py:56-64):
+ * out[b,c,p] = lrelu(x[b,c,p] + noise_w[0] * noise[b,p] + bias[c], alpha) * scale.  noise (batch, inner) and noise_w (1)
+ * may be NULL together, bias (channels) may be NULL. */
+int spgan_noise_bias_act(float* out, const float* x, const float* noise, const float* noise_w, const float* bias,
+                         int64_t batch, int64_t channels, int64_t inner, float alpha, float scale, void* stream);
+
+/* ---- K2/K3: upfirdn2d ---------------------------------------------------------------------------------
+ * Replaces upfirdn2d_op.upfirdn2d(input[N,H,W,1], kernel[kh,kw], up_x, up_y, down_x, down_y, pad_x0..pad_y1)
+ *   (models/custom_ops/upfirdn2d.cpp:12-22, upfirdn2d_kernel.cu:209-369) with minor == 1, i.e. `planes` = B*C
+ *   independent (in_h, in_w) images.  out is (planes, out_h, out_w) with
+ *   out_h = (in_h*up_y + pad_y0 + pad_y1 - kh) / down_y + 1 (same for w).  kernel is a DEVICE pointer. */
+int spgan_upfirdn2d(float* out, const float* x, const float* kernel, int64_t planes, int in_h, int in_w, int kh, int kw,
+                    int up_x, int up_y, int down_x, int down_y, int pad_x0, int pad_x1, int pad_y0, int pad_y1,
+                    void* stream);
+
+/* ---- L1: spherical bilinear gather ----------------------------------------------------------------------
+ * Replaces F.grid_sample(z, grid, mode='bilinear', padding_mode='border', align_corners=True) as called by
+ *   GridSamplerFuncNoGrad.forward (models/spherenet/grid_generator.py:610-613) for 3x3 tap grids.
+ * z (B, C, H, W); grid (Bg, 3H, 3W, 2) fp32 with Bg == B or Bg == 1 (test mode: one grid shared by the batch);
+ * out plane (b, c) is written at out + ((b * out_bstride) + out_coff + c) * 9*H*W, which lets the caller lay
+ * the result out exactly like the reference's flat (1, B*C + B*3, 3H, 3W) concatenation
+ * (models/spgan_ops_gs.py:791-813).  encode != 0 applies the coordinate encoding of :799-802 to channels
+ * 0/1/2 (tanh, cos(pi x), sin(pi x)) after sampling. */
+int spgan_sphere_gather(float* out, const float* z, const float* grid, int B, int C, int H, int W, int grid_batch,
+                        int64_t out_bstride, int64_t out_coff, int encode, void* stream);
+/* Corner indices and weights exactly as ATen computes them (GridSampler.h:27-36, 58-60); used by the
+ * bit-exactness tests.  grid (n, 2); x0,y0 int32 (n); wx,wy fp32 (n) = weight of the +1 corner. */
+int spgan_sphere_gather_indices(int32_t* x0, int32_t* y0, float* wx, float* wy, const float* grid, int64_t n, int H,
+                                int W, void* stream);
+/* Surrogate backward of the gather (grid_generator.py:615-623): grad_in = mean over each 3x3 block * 0.1.
+ * grad_out (planes, 3H, 3W) → grad_in (planes, H, W).  The guarded all_reduce of :621-622 is deliberately absent. */
+int spgan_sphere_gather_bwd(float* grad_in, const float* grad_out, int64_t planes, int H, int W, void* stream);
+
+/* ---- L7: EqualLinear ------------------------------------------------------------------------------------
+ * Replaces F.linear(x, W * w_scale, bias * b_scale) [+ fused_leaky_relu] (models/ops.py:213-218).
+ * x (M, K), w (N, K), bias (N) or NULL, y (M, N).  act: 0 none, 1 = leaky-relu(alpha) * gain applied after bias. */
+int spgan_linear(float* y, const float* x, const float* w, const float* bias, int M, int N, int K, float w_scale,
+                 float b_scale, int act, float alpha, float gain, void* stream);
+
+/* ---- L2-L6: convolution passes ---------------------------------------------------------------------------
+ * One "pass" computes, for every sample b, output channel o and lattice point (i, j), 0<=i<My, 0<=j<Mx:
+ *   acc = sum_c sum_t  w[o*ws_o + c*ws_c + tap_w[t]] * in_mul[b,c] * x[b, c, i*in_stride + tap_dy[t], j*in_stride + tap_dx[t]]
+ *         (taps falling outside [0,H)x[0,W) contribute zero)
+ *   v   = acc * out_scale * out_mul[b,o]  + noise_w[0]*noise[b, Y, X] + bias[o]
+ *   v   = act ? (v > 0 ? v : v*alpha) * gain : v
+ *   y[b, o, Y, X] = v + residual[b, o, Y, X],      Y = i*out_stride + out_off_y,  X = j*out_stride + out_off_x.
+ * With tap lists this covers F.conv2d(groups=batch) k in {1,3,7} / stride {1,2,3} (models/ops.py:634,175;
+ * models/spgan_ops_gs.py:814), F.conv_transpose2d(stride=2, groups=batch) as four parity passes
+ * (models/ops.py:617), their data gradients, and the non-modulated convs of the discriminator.
+ * in_mul (B, Cin) carries the style modulation, out_mul (B, Cout) the demodulation (models/ops.py:598-607):
+ * the per-sample weight tensor is never materialised.  NULL pointers switch a term off. */
+typedef struct SpganConvPass {
+  int32_t B, Cin, H, W;           /* input tensor (B, Cin, H, W) */
+  int32_t Cout, out_H, out_W;     /* output tensor (B, Cout, out_H, out_W) */
+  int32_t My, Mx;                 /* lattice extent of this pass */
+  int32_t in_stride;              /* input step per lattice step */
+  int32_t out_stride, out_off_y, out_off_x;
+  int32_t ntaps;
+  int32_t tap_dy[SPGAN_MAX_TAPS], tap_dx[SPGAN_MAX_TAPS], tap_w[SPGAN_MAX_TAPS];
+  int64_t ws_o, ws_c;             /* weight strides (elements) for output / input channel */
+  float out_scale;
+  int32_t act;                    /* 0 = none, 1 = leaky relu */
+  float act_alpha, act_gain;
+  int32_t precision;              /* 0 = fp32 SIMT, 1 = bf16x3 split on tcgen05 (fp32-equivalent), 2 = bf16 on tcgen05 */
+} SpganConvPass;
+
+int spgan_conv_pass(const SpganConvPass* p, float* y, const float* x, const float* w, const float* in_mul,
+                    const float* out_mul, const float* noise, const float* noise_w, const float* bias,
+                    const float* residual, void* stream);
+
+/* Demodulation coefficients (models/ops.py:603-604): d[b,o] = rsqrt(scale^2 * sum_c s[b,c]^2 * sum_t w[o,c,t]^2 + eps).
+ * w (Cout, Cin, taps), s (B, Cin), d (B, Cout). */
+int spgan_demod(float* d, const float* s, const float* w, int B, int Cin, int Cout, int taps, float scale, float eps,
+                void* stream);
+
+/* Weight gradient of a conv pass: dw[o*ws_o + c*ws_c + tap_w[t]] (+)= sum_b sum_ij
+ *   g[b,o,Y,X] * out_mul[b,o] * out_scale * in_mul[b,c] * x[b,c,i*in_stride+dy_t, j*in_stride+dx_t].
+ * Replaces cuDNN wgrad of the same F.conv2d / F.conv_transpose2d calls.  accumulate != 0 adds into dw. */
+int spgan_conv_wgrad(const SpganConvPass* p, float* dw, const float* g, const float* x, const float* in_mul,
+                     const float* out_mul, int accumulate, void* stream);
+
+/* ---- tcgen05 / TMEM implicit-GEMM path (precision 1 = bf16x3 split, fp32-equivalent; 2 = plain bf16) ---------
+ * The dense contractions run as  Y[p, o] = sum_t sum_k A[p + off_t, k] * Wp[t][o][k]  over the FLATTENED pixel index
+ * p = (b*Hl + i)*Wl + j of a channels-last bf16 copy of the input ("packed activation"), off_t = dy_t*Wl + dx_t:
+ * a tap shift is a constant row offset, so every A tile is one TMA box and the conv is a plain K-major GEMM on
+ * tcgen05.mma with the accumulator in TMEM.  Lattice points whose window would wrap a row are computed and dropped
+ * in the epilogue (the pass's My/Mx bounds).  Operands are stored as two bf16 planes, hi = bf16(v) and
+ * lo = bf16(v - hi); precision 1 issues hi*hi + hi*lo + lo*hi (relative error ~2^-16), precision 2 only hi*hi.
+ *
+ * spgan_pack_act: x (B, C, H, W) fp32 [* in_mul (B, C)] -> out [2][B*Hl*Wl][Cp] bf16; image pixel (y, x) lands on
+ *   lattice point (y + pad_y0, x + pad_x0) of the (Hl, Wl) lattice, everything else (borders, channels C..Cp-1,
+ *   Cp a multiple of 64) is zero.  Carries the style modulation of models/ops.py:598-600 (applied to the
+ *   activations instead of the weights). */
+int spgan_pack_act(uint16_t* out, const float* x, const float* in_mul, int B, int C, int H, int W, int Cp, int pad_y0,
+                   int pad_x0, int Hl, int Wl, void* stream);
+/* spgan_pack_weight: w[o*ws_o + c*ws_c + tap_w[t]] fp32 -> out [2][ntaps][Cout][Cp] bf16 (merged == 0) or
+ *   [2][1][Cout][ntaps*Cp] (merged != 0, k = t*Cp + c: the layout that pairs with spgan_sphere_pack). */
+int spgan_pack_weight(uint16_t* out, const float* w, int Cout, int Cin, int64_t ws_o, int64_t ws_c, int ntaps,
+                      const int32_t* tap_w, int Cp, int merged, void* stream);
+/* spgan_nchw_to_nhwc: (B, C, H, W) fp32 -> (B, H, W, C) fp32; staging copy that makes the spherical gather coalesced. */
+int spgan_nchw_to_nhwc(float* out, const float* x, int B, int C, int H, int W, void* stream);
+/* spgan_sphere_pack: the fused A-operand producer of the spherical modulated conv
+ *   (models/spgan_ops_gs.py:791-813 + grid_generator.py:610-613): bilinear border gather of the features
+ *   (x_nhwc, (B, H, W, C) fp32) and of the raw coords ((B, 3, H, W) fp32, may be NULL) at the 3x3 tap grid
+ *   ((Bg, 3H, 3W, 2), Bg in {1, B}), coordinate encoding tanh / cos(pi.) / sin(pi.), style modulation
+ *   in_mul (B, C + nc) (may be NULL), bf16 hi/lo split -> out [2][B*H*W][9*Cp], k = tap*Cp + channel.
+ *   The reference concatenates the gathered tensors as flat (1, B*C) ++ (1, B*nc) channel lists and then convolves
+ *   with groups = B, so group g reads flat channels [g*(C+nc), (g+1)*(C+nc)) (for B > 1 that mixes samples);
+ *   flat_concat != 0 reproduces exactly that mapping, 0 gives the per-sample concatenation. */
+int spgan_sphere_pack(uint16_t* out, const float* x_nhwc, const float* coords, const float* grid, const float* in_mul,
+                      int B, int C, int H, int W, int grid_batch, int Cp, int flat_concat, void* stream);
+/* spgan_conv_gemm: the tcgen05 kernel.  `p` is a conv pass whose (H, W) are the LATTICE dims (Hl, Wl) of the packed
+ *   activation, Cin is ignored (K per tap = kp, a multiple of 64), in_stride must be 1, tap_w is ignored (the packed
+ *   weight is already in tap order) and precision must be 1 or 2.  a_packed [2][a_rows][kp], w_packed
+ *   [2][ntaps][Cout][kp].  Epilogue terms as in spgan_conv_pass. */
+int spgan_conv_gemm(const SpganConvPass* p, float* y, const uint16_t* a_packed, int64_t a_rows, int kp,
+                    const uint16_t* w_packed, const float* out_mul, const float* noise, const float* noise_w,
+                    const float* bias, const float* residual, void* stream);
+/* Number of tcgen05 GEMM launches since load (the bench's gpu_launches evidence for the tensor path). */
+int64_t spgan_gemm_launch_count(void);
+
+/* Per-plane dot products: out[p] = sum_k a[p,k] * b[p,k]; planes x inner.  Used for the style / demodulation
+ * gradients (d s[b,c] = <x[b,c], dxs[b,c]>). */
+int spgan_plane_dot(float* out, const float* a, const float* b, int64_t planes, int64_t inner, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPGAN_B200_H */

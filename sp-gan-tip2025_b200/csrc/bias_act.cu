@@ -1,0 +1,180 @@
+// K1: fused bias + activation (forward, gradient, second gradient) and its fused first-order backward.
+// HBM-bound: 8 B/element forward, 12 B/element backward.  128-bit accesses whenever a float4 cannot
+// straddle a bias channel; otherwise 4 independent scalar accesses in flight per thread.
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ float act_fn(float v, float r, int code, float alpha) {
+  switch (code) {
+    case 30: return v > 0.f ? v : v * alpha;
+    case 31: return r > 0.f ? v : v * alpha;
+    case 12:
+    case 32: return 0.f;
+    default: return v;  // 10, 11 and the reference kernel's `default:` label
+  }
+}
+
+__global__ void __launch_bounds__(256) bias_act_vec4(float4* __restrict__ out, const float4* __restrict__ x,
+                                                    const float* __restrict__ bias, const float4* __restrict__ ref,
+                                                    int64_t n4, int64_t step_b4, int64_t size_b, int code, float alpha,
+                                                    float scale) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = __ldcs(x + i);
+    float b = bias ? __ldg(bias + (i / step_b4) % size_b) : 0.f;
+    float4 r = ref ? __ldcs(ref + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 o;
+    o.x = act_fn(v.x + b, r.x, code, alpha) * scale;
+    o.y = act_fn(v.y + b, r.y, code, alpha) * scale;
+    o.z = act_fn(v.z + b, r.z, code, alpha) * scale;
+    o.w = act_fn(v.w + b, r.w, code, alpha) * scale;
+    __stcs(out + i, o);
+  }
+}
+
+__global__ void __launch_bounds__(256) bias_act_scalar(float* __restrict__ out, const float* __restrict__ x,
+                                                      const float* __restrict__ bias, const float* __restrict__ ref,
+                                                      int64_t n, int64_t step_b, int64_t size_b, int code, float alpha,
+                                                      float scale) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n; i += 4 * stride) {
+    float v[4], r[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      v[u] = __ldcs(x + i + u * stride);
+      r[u] = ref ? __ldcs(ref + i + u * stride) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      int64_t j = i + u * stride;
+      float b = bias ? __ldg(bias + (j / step_b) % size_b) : 0.f;
+      __stcs(out + j, act_fn(v[u] + b, r[u], code, alpha) * scale);
+    }
+  }
+  for (; i < n; i += stride) {
+    float b = bias ? __ldg(bias + (i / step_b) % size_b) : 0.f;
+    float r = ref ? ref[i] : 0.f;
+    out[i] = act_fn(x[i] + b, r, code, alpha) * scale;
+  }
+}
+
+// Backward: blockIdx.x = channel, blockIdx.y = slice of that channel's batch*inner elements.
+// Writes grad_in and reduces grad_bias with one atomicAdd per CTA.
+__global__ void __launch_bounds__(256) bias_act_bwd_kernel(float* __restrict__ gi, float* __restrict__ gb,
+                                                          const float* __restrict__ go, const float* __restrict__ ref,
+                                                          int64_t batch, int64_t channels, int64_t inner, float alpha,
+                                                          float scale) {
+  const int64_t c = blockIdx.x;
+  const int64_t total = batch * inner;
+  const int64_t per = (total + gridDim.y - 1) / gridDim.y;
+  const int64_t begin = (int64_t)blockIdx.y * per;
+  const int64_t end = begin + per < total ? begin + per : total;
+  float acc = 0.f;
+  for (int64_t e = begin + threadIdx.x; e < end; e += blockDim.x) {
+    const int64_t b = e / inner;
+    const int64_t k = e - b * inner;
+    const int64_t idx = (b * channels + c) * inner + k;
+    const float g = __ldcs(go + idx);
+    const float r = __ldcs(ref + idx);
+    const float v = (r > 0.f ? g : g * alpha) * scale;
+    __stcs(gi + idx, v);
+    acc += v;
+  }
+  __shared__ float warp_sums[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float s = warp_sums[threadIdx.x];
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(0xffu, s, o);
+    if (threadIdx.x == 0) atomicAdd(gb + c, s);
+  }
+}
+
+// NoiseInjection + bias + leaky-ReLU: plane0 + blockIdx.y = (b, c) plane, threads stride over the plane's pixels.
+__global__ void __launch_bounds__(256) noise_bias_act_kernel(float* __restrict__ out, const float* __restrict__ x,
+                                                            const float* __restrict__ noise,
+                                                            const float* __restrict__ noise_w,
+                                                            const float* __restrict__ bias, int64_t plane0,
+                                                            int64_t channels, int64_t inner, float alpha, float scale) {
+  const int64_t plane = plane0 + blockIdx.y;
+  const int64_t b = plane / channels, c = plane - b * channels;
+  const float nw = noise ? __ldg(noise_w) : 0.f;
+  const float bv = bias ? __ldg(bias + c) : 0.f;
+  const float* xp = x + plane * inner;
+  const float* np = noise ? noise + b * inner : nullptr;
+  float* op = out + plane * inner;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < inner; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = __ldcs(xp + i) + bv;
+    if (np) v += nw * __ldg(np + i);
+    __stcs(op + i, (v > 0.f ? v : v * alpha) * scale);
+  }
+}
+
+}  // namespace
+
+extern "C" int spgan_noise_bias_act(float* out, const float* x, const float* noise, const float* noise_w,
+                                    const float* bias, int64_t batch, int64_t channels, int64_t inner, float alpha,
+                                    float scale, void* stream) {
+  SPGAN_CHECK_ARG(batch >= 0 && channels >= 0 && inner >= 0, "spgan_noise_bias_act: negative size");
+  if (batch * channels * inner == 0) return 0;
+  SPGAN_CHECK_ARG(out && x, "spgan_noise_bias_act: null pointer");
+  SPGAN_CHECK_ARG((noise == nullptr) == (noise_w == nullptr), "spgan_noise_bias_act: noise and noise_w go together");
+  int64_t gx = ceil_div64(inner, 1024);
+  if (gx > 64) gx = 64;
+  const int64_t planes = batch * channels;
+  for (int64_t p0 = 0; p0 < planes; p0 += 65535) {  // gridDim.y <= 65535
+    const int64_t np = planes - p0 < 65535 ? planes - p0 : 65535;
+    dim3 grid((unsigned)gx, (unsigned)np);
+    noise_bias_act_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(out, x, noise, noise_w, bias, p0, channels, inner,
+                                                                  alpha, scale);
+  }
+  SPGAN_CHECK_LAUNCH("spgan_noise_bias_act");
+  return 0;
+}
+
+extern "C" int spgan_bias_act(float* out, const float* x, const float* bias, const float* ref, int64_t n,
+                              int64_t step_b, int64_t size_b, int act, int grad, float alpha, float scale,
+                              void* stream) {
+  SPGAN_CHECK_ARG(n >= 0, "spgan_bias_act: negative size");
+  if (n == 0) return 0;
+  SPGAN_CHECK_ARG(out && x, "spgan_bias_act: input must be a CUDA tensor (null pointer)");
+  SPGAN_CHECK_ARG(!bias || (step_b > 0 && size_b > 0), "spgan_bias_act: bad bias geometry");
+  const int code = act * 10 + grad;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool aligned = ((((uintptr_t)out) | ((uintptr_t)x) | ((uintptr_t)ref)) & 15) == 0;
+  if (aligned && n % 4 == 0 && (!bias || step_b % 4 == 0)) {
+    const int64_t n4 = n / 4;
+    bias_act_vec4<<<grid_for(n4, 256, 8), 256, 0, st>>>((float4*)out, (const float4*)x, bias, (const float4*)ref, n4,
+                                                        bias ? step_b / 4 : 1, bias ? size_b : 1, code, alpha, scale);
+  } else {
+    bias_act_scalar<<<grid_for(n, 1024, 8), 256, 0, st>>>(out, x, bias, ref, n, bias ? step_b : 1, bias ? size_b : 1,
+                                                          code, alpha, scale);
+  }
+  SPGAN_CHECK_LAUNCH("spgan_bias_act");
+  return 0;
+}
+
+extern "C" int spgan_bias_act_bwd(float* grad_in, float* grad_bias, const float* grad_out, const float* out_ref,
+                                  int64_t batch, int64_t channels, int64_t inner, float alpha, float scale,
+                                  void* stream) {
+  SPGAN_CHECK_ARG(batch >= 0 && channels >= 0 && inner >= 0, "spgan_bias_act_bwd: negative size");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (channels > 0) SPGAN_CUDA(cudaMemsetAsync(grad_bias, 0, sizeof(float) * channels, st), "spgan_bias_act_bwd memset");
+  if (batch * channels * inner == 0) return 0;
+  SPGAN_CHECK_ARG(grad_in && grad_bias && grad_out && out_ref, "spgan_bias_act_bwd: null pointer");
+  SPGAN_CHECK_ARG(channels <= 2147483647, "spgan_bias_act_bwd: too many channels");
+  // enough slices that channels*slices covers >= 4 waves of 148 SMs x 8 CTAs, each slice >= 2048 elements
+  int64_t slices = ceil_div64((int64_t)SPGAN_NUM_SMS * 8 * 4, channels);
+  const int64_t max_slices = ceil_div64(batch * inner, 2048);
+  if (slices > max_slices) slices = max_slices;
+  if (slices > 65535) slices = 65535;
+  if (slices < 1) slices = 1;
+  dim3 grid((unsigned)channels, (unsigned)slices);
+  bias_act_bwd_kernel<<<grid, 256, 0, st>>>(grad_in, grad_bias, grad_out, out_ref, batch, channels, inner, alpha, scale);
+  SPGAN_CHECK_LAUNCH("spgan_bias_act_bwd");
+  return 0;
+}

@@ -1,0 +1,48 @@
+// Shared helpers for libspgan_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "../../include/spgan_b200.h"
+
+#define SPGAN_NUM_SMS 148  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+
+void spgan_set_error(const char* fmt, ...);
+
+#define SPGAN_CHECK_ARG(cond, ...)          \
+  do {                                      \
+    if (!(cond)) {                          \
+      spgan_set_error(__VA_ARGS__);         \
+      return 1;                             \
+    }                                       \
+  } while (0)
+
+#define SPGAN_CHECK_LAUNCH(name)                                                   \
+  do {                                                                             \
+    cudaError_t e__ = cudaGetLastError();                                          \
+    if (e__ != cudaSuccess) {                                                      \
+      spgan_set_error("%s: CUDA launch failed: %s", name, cudaGetErrorString(e__)); \
+      return 2;                                                                    \
+    }                                                                              \
+  } while (0)
+
+#define SPGAN_CUDA(call, name)                                            \
+  do {                                                                    \
+    cudaError_t e__ = (call);                                             \
+    if (e__ != cudaSuccess) {                                             \
+      spgan_set_error("%s: %s", name, cudaGetErrorString(e__));           \
+      return 2;                                                           \
+    }                                                                     \
+  } while (0)
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// Grid size for a grid-stride kernel: enough CTAs for `work` items at `per_block` each, capped at
+// `waves` full waves of the 148 SMs x `ctas_per_sm` resident CTAs.
+static inline int grid_for(int64_t work, int64_t per_block, int ctas_per_sm, int waves = 4) {
+  int64_t need = ceil_div64(work, per_block);
+  int64_t cap = (int64_t)SPGAN_NUM_SMS * ctas_per_sm * waves;
+  if (need < 1) need = 1;
+  return (int)(need < cap ? need : cap);
+}

@@ -1,0 +1,709 @@
+// tcgen05 / TMEM implicit-GEMM convolution for sm_100a and its operand packers.
+//
+//   Y[p, o] = sum_t sum_k A[p + off_t, k] * Wp[t][o][k]          (see include/spgan_b200.h)
+//
+// A is a channels-last bf16 copy of the (modulated) activation, flattened over (sample, row, column); a conv tap is a
+// constant row offset, so every operand tile is one TMA box (128B-swizzled, K-major) and the contraction is issued as
+// tcgen05.mma.cta_group::1.kind::f16 (M = 128, N <= 256, K = 16) with the fp32 accumulator in TMEM.
+//
+// Kernel anatomy (one persistent CTA per SM, 192 threads):
+//   warp 0      TMA producer: one elected lane streams {A_hi, A_lo, B_hi, B_lo} boxes through a ring of smem stages
+//   warp 1      TMEM allocator + MMA issuer: one lane issues 4 (K=16 steps) x {hi*hi, hi*lo, lo*hi} MMAs per stage,
+//               tcgen05.commit releases the stage / publishes the accumulator
+//   warps 2..5  epilogue: tcgen05.ld their 32-lane TMEM quarter, apply demodulation, noise, bias, leaky-ReLU, residual,
+//               scatter to the NCHW fp32 output.  Two accumulator stages (2 x 256 TMEM columns) overlap the epilogue of
+//               tile i with the mainloop of tile i+1.
+// Roofline: tensor pipe.  FLOPs per launch = 2 * rows * Cout * ntaps * kp (x3 issued MMAs in bf16x3 mode).
+#include "common.cuh"
+
+#include <atomic>
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+namespace {
+
+constexpr int GEMM_BLOCK_M = 128;
+constexpr int GEMM_BLOCK_N = 256;
+constexpr int GEMM_BLOCK_K = 64;  // bf16 elements = one 128-byte swizzle row
+constexpr int GEMM_UMMA_K = 16;
+constexpr int GEMM_THREADS = 192;
+constexpr int A_TILE_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;  // 16 KiB
+constexpr int B_TILE_BYTES = GEMM_BLOCK_N * GEMM_BLOCK_K * 2;  // 32 KiB
+
+struct GemmParams {
+  int32_t rows;        // B * Hl * Wl lattice points
+  int32_t Hl, Wl;      // lattice dims
+  int32_t My, Mx;      // valid lattice extent
+  int32_t Cout, out_H, out_W;
+  int32_t out_stride, out_off_y, out_off_x;
+  int32_t ntaps, kblocks;  // kblocks = kp / 64
+  int32_t tap_off[SPGAN_MAX_TAPS];
+  int32_t m_tiles, n_tiles;
+  float out_scale;
+  int32_t act;
+  float act_alpha, act_gain;
+};
+
+// ------------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a trapped kernel (an error code at the C ABI), never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  unsigned long long t0 = 0;
+  for (uint32_t it = 1;; ++it) {
+    if (mbar_try_wait(bar, parity)) return;
+    if ((it & 0x3ff) == 0) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      if (now - t0 > 4000000000ull) {  // 4 s
+        printf("spgan conv_gemm: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x,
+               threadIdx.x, bar, parity);
+        __trap();
+      }
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, 128-byte swizzle, 8-row core-matrix groups 1024 bytes apart (cute::UMMA::SmemDescriptor, version 1).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);  // start address, bits [0,14)
+  d |= (uint64_t)1 << 16;                       // leading byte offset (unused for swizzled K-major), bits [16,30)
+  d |= (uint64_t)(1024 >> 4) << 32;             // stride byte offset, bits [32,46)
+  d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ uint32_t umma_idesc_bf16(int n) {
+  return (1u << 4)                  // D format f32
+         | (1u << 7)                // A format bf16
+         | (1u << 10)               // B format bf16
+         | ((uint32_t)(n >> 3) << 17)
+         | ((uint32_t)(GEMM_BLOCK_M >> 4) << 24);  // A, B K-major: bits 15, 16 stay 0
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------------------ GEMM kernel
+template <int kPasses>
+struct GemmSmem {
+  static constexpr int kStageBytes = (kPasses == 3 ? 2 : 1) * (A_TILE_BYTES + B_TILE_BYTES);
+  static constexpr int kStages = (kPasses == 3) ? 2 : 4;
+  static constexpr int kTileBytes = kStageBytes * kStages;
+  static constexpr int kBarrierBytes = 256;
+  static constexpr int kTotal = kTileBytes + kBarrierBytes + 1024;  // + alignment slack
+};
+
+template <int kPasses>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams gp,
+                 float* __restrict__ y, const float* __restrict__ out_mul, const float* __restrict__ noise,
+                 const float* __restrict__ noise_w, const float* __restrict__ bias, const float* __restrict__ residual) {
+  using S = GemmSmem<kPasses>;
+  constexpr int kStages = S::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + S::kTileBytes;
+  // barrier slots (8 bytes each): full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], then the TMEM base word
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = gp.m_tiles * gp.n_tiles;
+  const int kiters = gp.ntaps * gp.kblocks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / gp.n_tiles) * GEMM_BLOCK_M;
+        const int n0 = (tile % gp.n_tiles) * GEMM_BLOCK_N;
+        for (int t = 0; t < gp.ntaps; ++t) {
+          const int row = m0 + gp.tap_off[t];
+          for (int kb = 0; kb < gp.kblocks; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            const uint32_t sa = smem_base + stage * S::kStageBytes;
+            mbar_arrive_expect_tx(full_bar(stage), S::kStageBytes);
+            if (kPasses == 3) {
+              tma_load_3d(sa, &tmA, full_bar(stage), kb * GEMM_BLOCK_K, row, 0);
+              tma_load_3d(sa + A_TILE_BYTES, &tmA, full_bar(stage), kb * GEMM_BLOCK_K, row, 1);
+              tma_load_4d(sa + 2 * A_TILE_BYTES, &tmB, full_bar(stage), kb * GEMM_BLOCK_K, n0, t, 0);
+              tma_load_4d(sa + 2 * A_TILE_BYTES + B_TILE_BYTES, &tmB, full_bar(stage), kb * GEMM_BLOCK_K, n0, t, 1);
+            } else {
+              tma_load_3d(sa, &tmA, full_bar(stage), kb * GEMM_BLOCK_K, row, 0);
+              tma_load_4d(sa + A_TILE_BYTES, &tmB, full_bar(stage), kb * GEMM_BLOCK_K, n0, t, 0);
+            }
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int titer = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++titer) {
+        const int n0 = (tile % gp.n_tiles) * GEMM_BLOCK_N;
+        int n_eff = gp.Cout - n0;
+        n_eff = n_eff > GEMM_BLOCK_N ? GEMM_BLOCK_N : ((n_eff + 15) & ~15);
+        const uint32_t idesc = umma_idesc_bf16(n_eff);
+        const int as = titer & 1;
+        const uint32_t aphase = (uint32_t)(titer >> 1) & 1u;
+        mbar_wait(tempty_bar(as), aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * GEMM_BLOCK_N);
+        for (int it = 0; it < kiters; ++it) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * S::kStageBytes;
+          const uint32_t a_hi = sa;
+          const uint32_t a_lo = sa + A_TILE_BYTES;
+          const uint32_t b_hi = sa + (kPasses == 3 ? 2 : 1) * A_TILE_BYTES;
+          const uint32_t b_lo = b_hi + B_TILE_BYTES;
+#pragma unroll
+          for (int k = 0; k < GEMM_BLOCK_K / GEMM_UMMA_K; ++k) {
+            const uint32_t koff = k * GEMM_UMMA_K * 2;  // bytes inside the 128-byte swizzle row
+            const uint64_t da_hi = umma_desc_sw128(a_hi + koff);
+            const uint64_t db_hi = umma_desc_sw128(b_hi + koff);
+            tc_mma_f16(d_tmem, da_hi, db_hi, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            if (kPasses == 3) {
+              const uint64_t da_lo = umma_desc_sw128(a_lo + koff);
+              const uint64_t db_lo = umma_desc_sw128(b_lo + koff);
+              tc_mma_f16(d_tmem, da_hi, db_lo, idesc, 1u);
+              tc_mma_f16(d_tmem, da_lo, db_hi, idesc, 1u);
+            }
+          }
+          tc_commit(empty_bar(stage));  // frees the smem stage once these MMAs have read it
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        tc_commit(tfull_bar(as));  // accumulator complete
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================================================================== epilogue (warps 2..5)
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int plane = gp.Hl * gp.Wl;
+    const int64_t ostride_c = (int64_t)gp.out_H * gp.out_W;
+    const float nw = (noise != nullptr && noise_w != nullptr) ? __ldg(noise_w) : 0.f;
+    int titer = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++titer) {
+      const int m0 = (tile / gp.n_tiles) * GEMM_BLOCK_M;
+      const int n0 = (tile % gp.n_tiles) * GEMM_BLOCK_N;
+      int n_eff = gp.Cout - n0;
+      n_eff = n_eff > GEMM_BLOCK_N ? GEMM_BLOCK_N : ((n_eff + 15) & ~15);
+      const int as = titer & 1;
+      const uint32_t aphase = (uint32_t)(titer >> 1) & 1u;
+      // decode this thread's lattice point
+      const int p = m0 + quarter * 32 + lane;
+      bool valid = p < gp.rows;
+      int b = 0, Y = 0, X = 0;
+      if (valid) {
+        b = p / plane;
+        const int r = p - b * plane;
+        const int i = r / gp.Wl;
+        const int j = r - i * gp.Wl;
+        Y = i * gp.out_stride + gp.out_off_y;
+        X = j * gp.out_stride + gp.out_off_x;
+        valid = i < gp.My && j < gp.Mx && Y >= 0 && Y < gp.out_H && X >= 0 && X < gp.out_W;
+      }
+      const int64_t pix = (int64_t)Y * gp.out_W + X;
+      const int64_t ybase = (int64_t)b * gp.Cout * ostride_c + pix;
+      const float nz = (valid && noise != nullptr && noise_w != nullptr) ? nw * __ldg(noise + (int64_t)b * ostride_c + pix) : 0.f;
+      const float* om = out_mul ? out_mul + (int64_t)b * gp.Cout : nullptr;
+
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * GEMM_BLOCK_N);
+      for (int c0 = 0; c0 < n_eff; c0 += 32) {
+        float v[32];
+        tmem_ld32(taddr + (uint32_t)c0, v);
+        if (valid) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            const int o = n0 + c0 + k;
+            if (o < gp.Cout) {
+              float r = v[k] * gp.out_scale;
+              if (om) r *= __ldg(om + o);
+              r += nz;
+              if (bias) r += __ldg(bias + o);
+              if (gp.act) r = (r > 0.f ? r : r * gp.act_alpha) * gp.act_gain;
+              const int64_t idx = ybase + (int64_t)o * ostride_c;
+              if (residual) r += __ldg(residual + idx);
+              y[idx] = r;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ operand packers
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(v);
+  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+// One CTA: 64 channels x 64 consecutive lattice points of one sample.  Reads coalesced along pixels, writes
+// coalesced along channels (bf16x2 per lane, 128 bytes per warp).
+__global__ void __launch_bounds__(256) pack_act_kernel(__nv_bfloat16* __restrict__ out, const float* __restrict__ x,
+                                                      const float* __restrict__ in_mul, int B, int C, int H, int W,
+                                                      int Cp, int pad_y, int pad_x, int Hl, int Wl) {
+  // (pad_y, pad_x) = top/left offset of the image inside the (Hl, Wl) lattice
+  __shared__ float tile[64][65];
+  const int plane_l = Hl * Wl;
+  const int q0 = blockIdx.x * 64;  // lattice point within the sample
+  const int c0 = blockIdx.y * 64;
+  const int b = blockIdx.z;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  {
+    const int q = q0 + tx;
+    int sy = -1, sx = -1;
+    if (q < plane_l) {
+      const int i = q / Wl, j = q - i * Wl;
+      sy = i - pad_y;
+      sx = j - pad_x;
+    }
+    const bool inside = sy >= 0 && sy < H && sx >= 0 && sx < W;
+#pragma unroll 4
+    for (int cc = ty; cc < 64; cc += 4) {
+      const int c = c0 + cc;
+      float v = 0.f;
+      if (inside && c < C) {
+        v = __ldg(x + (((int64_t)b * C + c) * H + sy) * W + sx);
+        if (in_mul) v *= __ldg(in_mul + (int64_t)b * C + c);
+      }
+      tile[cc][tx] = v;
+    }
+  }
+  __syncthreads();
+  const int cpair = threadIdx.x & 31, prow = threadIdx.x >> 5;
+  const int64_t rows_total = (int64_t)B * plane_l;
+  __nv_bfloat16* out_lo = out + rows_total * Cp;
+#pragma unroll
+  for (int pp = prow; pp < 64; pp += 8) {
+    const int q = q0 + pp;
+    if (q >= plane_l) break;
+    const float v0 = tile[2 * cpair][pp], v1 = tile[2 * cpair + 1][pp];
+    __nv_bfloat16 h0, l0, h1, l1;
+    split_bf16(v0, h0, l0);
+    split_bf16(v1, h1, l1);
+    const int64_t off = ((int64_t)b * plane_l + q) * Cp + c0 + 2 * cpair;
+    *reinterpret_cast<__nv_bfloat162*>(out + off) = __halves2bfloat162(h0, h1);
+    *reinterpret_cast<__nv_bfloat162*>(out_lo + off) = __halves2bfloat162(l0, l1);
+  }
+}
+
+struct TapList {
+  int32_t w[SPGAN_MAX_TAPS];
+};
+
+// out[plane][t][o][c] (or [plane][o][t*Cp + c] when merged); one thread per (t, o, c) element, c fastest.
+__global__ void __launch_bounds__(256) pack_weight_kernel(__nv_bfloat16* __restrict__ out, const float* __restrict__ w,
+                                                         int Cout, int Cin, int64_t ws_o, int64_t ws_c, int ntaps,
+                                                         TapList taps, int Cp, int merged) {
+  const int64_t total = (int64_t)ntaps * Cout * Cp;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % Cp);
+    const int64_t r = idx / Cp;
+    const int o = (int)(r % Cout);
+    const int t = (int)(r / Cout);
+    float v = 0.f;
+    if (c < Cin) v = __ldg(w + (int64_t)o * ws_o + (int64_t)c * ws_c + taps.w[t]);
+    __nv_bfloat16 hi, lo;
+    split_bf16(v, hi, lo);
+    const int64_t dst = merged ? ((int64_t)o * ntaps + t) * Cp + c : idx;
+    out[dst] = hi;
+    out[total + dst] = lo;
+  }
+}
+
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(float* __restrict__ out, const float* __restrict__ x, int C,
+                                                          int HW) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int cc = ty; cc < 32; cc += 8) {
+    const int c = c0 + cc, p = p0 + tx;
+    tile[cc][tx] = (c < C && p < HW) ? __ldg(x + ((int64_t)b * C + c) * HW + p) : 0.f;
+  }
+  __syncthreads();
+  for (int pp = ty; pp < 32; pp += 8) {
+    const int p = p0 + pp, c = c0 + tx;
+    if (p < HW && c < C) out[((int64_t)b * HW + p) * C + c] = tile[tx][pp];
+  }
+}
+
+// ATen's fp32 index sequence (GridSampler.h:27-36, 58-60) with explicit round-to-nearest ops (no FMA contraction).
+__device__ __forceinline__ float unnorm_clip(float g, int size) {
+  float v = __fmul_rn(__fdiv_rn(__fadd_rn(g, 1.f), 2.f), (float)(size - 1));
+  return fminf((float)(size - 1), fmaxf(v, 0.f));
+}
+
+// One thread per (group g, pixel p, tap t, channel k), k fastest: corner reads are coalesced over channels in the
+// NHWC staging copy, bf16 writes are coalesced over k.
+__global__ void __launch_bounds__(256) sphere_pack_kernel(__nv_bfloat16* __restrict__ out, const float* __restrict__ xh,
+                                                         const float* __restrict__ coords, const float* __restrict__ grid,
+                                                         const float* __restrict__ in_mul, int B, int C, int nc, int H,
+                                                         int W, int grid_batch, int Cp, int flat_concat) {
+  const int Ct = C + nc;
+  const int HW = H * W;
+  const int64_t plane_elems = (int64_t)B * HW * 9 * Cp;
+  const int64_t total = plane_elems;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(idx % Cp);
+    int64_t r = idx / Cp;
+    const int t = (int)(r % 9);
+    r /= 9;
+    const int p = (int)(r % HW);
+    const int g = (int)(r / HW);
+    float v = 0.f;
+    if (k < Ct) {
+      // which gathered plane feeds channel k of group g
+      int bs, cs;
+      bool is_coord;
+      if (flat_concat) {
+        const int64_t flat = (int64_t)g * Ct + k;
+        if (flat < (int64_t)B * C) {
+          bs = (int)(flat / C);
+          cs = (int)(flat - (int64_t)bs * C);
+          is_coord = false;
+        } else {
+          const int64_t f2 = flat - (int64_t)B * C;
+          bs = (int)(f2 / nc);
+          cs = (int)(f2 - (int64_t)bs * nc);
+          is_coord = true;
+        }
+      } else {
+        bs = g;
+        is_coord = k >= C;
+        cs = is_coord ? k - C : k;
+      }
+      const int py = p / W, px = p - py * W;
+      const int ty = t / 3, tx = t - ty * 3;
+      const int bg = grid_batch == 1 ? 0 : bs;
+      const float2 gxy =
+          __ldg(reinterpret_cast<const float2*>(grid) + ((int64_t)bg * 3 * H + (3 * py + ty)) * (3 * W) + 3 * px + tx);
+      const float ix = unnorm_clip(gxy.x, W), iy = unnorm_clip(gxy.y, H);
+      const float fx = floorf(ix), fy = floorf(iy);
+      const int x0 = (int)fx, y0 = (int)fy;
+      const int x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
+      const float ex = __fsub_rn(__fadd_rn(fx, 1.f), ix), ey = __fsub_rn(__fadd_rn(fy, 1.f), iy);
+      const float wx = __fsub_rn(ix, fx), wy = __fsub_rn(iy, fy);
+      float nwv, nev, swv, sev;
+      if (!is_coord) {
+        const float* src = xh + (int64_t)bs * HW * C + cs;
+        nwv = __ldg(src + (int64_t)(y0 * W + x0) * C);
+        nev = __ldg(src + (int64_t)(y0 * W + x1) * C);
+        swv = __ldg(src + (int64_t)(y1 * W + x0) * C);
+        sev = __ldg(src + (int64_t)(y1 * W + x1) * C);
+      } else {
+        const float* src = coords + ((int64_t)bs * nc + cs) * HW;
+        nwv = __ldg(src + y0 * W + x0);
+        nev = __ldg(src + y0 * W + x1);
+        swv = __ldg(src + y1 * W + x0);
+        sev = __ldg(src + y1 * W + x1);
+      }
+      v = nwv * (ex * ey) + nev * (wx * ey) + swv * (ex * wy) + sev * (wx * wy);
+      if (is_coord) {
+        if (cs == 0) v = tanhf(v);
+        else if (cs == 1) v = cosf(v * 3.14159274101257324f);
+        else if (cs == 2) v = sinf(v * 3.14159274101257324f);
+      }
+      if (in_mul) v *= __ldg(in_mul + (int64_t)g * Ct + k);
+    }
+    __nv_bfloat16 hi, lo;
+    split_bf16(v, hi, lo);
+    out[idx] = hi;
+    out[plane_elems + idx] = lo;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* sym = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess || sym == nullptr)
+    return nullptr;
+  fn = (EncodeTiledFn)sym;
+  return fn;
+}
+
+int encode_bf16_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                    const cuuint32_t* box, const char* who) {
+  EncodeTiledFn fn = get_encode_fn();
+  SPGAN_CHECK_ARG(fn != nullptr, "%s: cuTensorMapEncodeTiled is not available from the CUDA driver", who);
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SPGAN_CHECK_ARG(r == CUDA_SUCCESS, "%s: cuTensorMapEncodeTiled failed with CUresult %d", who, (int)r);
+  return 0;
+}
+
+std::atomic<long long>* launch_counter() {
+  static std::atomic<long long> c{0};
+  return &c;
+}
+
+template <int kPasses>
+int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& gp, float* y, const float* out_mul,
+                const float* noise, const float* noise_w, const float* bias, const float* residual, cudaStream_t st) {
+  using S = GemmSmem<kPasses>;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  SPGAN_CUDA(cudaGetDevice(&dev), "spgan_conv_gemm");
+  if (dev < 64 && !attr_set[dev]) {
+    SPGAN_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<kPasses>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal),
+               "spgan_conv_gemm (shared memory opt-in)");
+    attr_set[dev] = true;
+  }
+  const int tiles = gp.m_tiles * gp.n_tiles;
+  const int grid = tiles < SPGAN_NUM_SMS ? tiles : SPGAN_NUM_SMS;
+  conv_gemm_kernel<kPasses><<<grid, GEMM_THREADS, S::kTotal, st>>>(tmA, tmB, gp, y, out_mul, noise, noise_w, bias, residual);
+  SPGAN_CHECK_LAUNCH("spgan_conv_gemm");
+  launch_counter()->fetch_add(1);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int64_t spgan_gemm_launch_count(void) { return (int64_t)launch_counter()->load(); }
+
+extern "C" int spgan_pack_act(uint16_t* out, const float* x, const float* in_mul, int B, int C, int H, int W, int Cp,
+                              int pad_y, int pad_x, int Hl, int Wl, void* stream) {
+  SPGAN_CHECK_ARG(B >= 0 && C >= 0 && H >= 0 && W >= 0 && pad_y >= 0 && pad_x >= 0, "spgan_pack_act: negative size");
+  SPGAN_CHECK_ARG(Hl >= H + pad_y && Wl >= W + pad_x, "spgan_pack_act: lattice %dx%d smaller than the padded image", Hl, Wl);
+  SPGAN_CHECK_ARG(Cp >= C && Cp % 64 == 0, "spgan_pack_act: Cp=%d must be a multiple of 64 and >= C=%d", Cp, C);
+  if (B == 0 || Cp == 0 || H == 0 || W == 0) return 0;
+  SPGAN_CHECK_ARG(out && x, "spgan_pack_act: null pointer");
+  SPGAN_CHECK_ARG(B <= 65535, "spgan_pack_act: batch %d > 65535", B);
+  dim3 grid((Hl * Wl + 63) / 64, Cp / 64, B);
+  pack_act_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)out, x, in_mul, B, C, H, W, Cp, pad_y, pad_x,
+                                                          Hl, Wl);
+  SPGAN_CHECK_LAUNCH("spgan_pack_act");
+  return 0;
+}
+
+extern "C" int spgan_pack_weight(uint16_t* out, const float* w, int Cout, int Cin, int64_t ws_o, int64_t ws_c, int ntaps,
+                                 const int32_t* tap_w, int Cp, int merged, void* stream) {
+  SPGAN_CHECK_ARG(Cout >= 0 && Cin >= 0, "spgan_pack_weight: negative size");
+  SPGAN_CHECK_ARG(ntaps >= 1 && ntaps <= SPGAN_MAX_TAPS, "spgan_pack_weight: %d taps unsupported", ntaps);
+  SPGAN_CHECK_ARG(Cp >= Cin && Cp % 64 == 0, "spgan_pack_weight: Cp=%d must be a multiple of 64 and >= Cin=%d", Cp, Cin);
+  if (Cout == 0 || Cp == 0) return 0;
+  SPGAN_CHECK_ARG(out && w && tap_w, "spgan_pack_weight: null pointer");
+  TapList taps;
+  for (int t = 0; t < ntaps; ++t) taps.w[t] = tap_w[t];
+  const int64_t total = (int64_t)ntaps * Cout * Cp;
+  pack_weight_kernel<<<grid_for(total, 256, 8), 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)out, w, Cout, Cin, ws_o,
+                                                                                ws_c, ntaps, taps, Cp, merged);
+  SPGAN_CHECK_LAUNCH("spgan_pack_weight");
+  return 0;
+}
+
+extern "C" int spgan_nchw_to_nhwc(float* out, const float* x, int B, int C, int H, int W, void* stream) {
+  SPGAN_CHECK_ARG(B >= 0 && C >= 0 && H >= 0 && W >= 0, "spgan_nchw_to_nhwc: negative size");
+  if (B == 0 || C == 0 || H == 0 || W == 0) return 0;
+  SPGAN_CHECK_ARG(out && x, "spgan_nchw_to_nhwc: null pointer");
+  SPGAN_CHECK_ARG(B <= 65535, "spgan_nchw_to_nhwc: batch %d > 65535", B);
+  dim3 grid((H * W + 31) / 32, (C + 31) / 32, B);
+  nchw_to_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(out, x, C, H * W);
+  SPGAN_CHECK_LAUNCH("spgan_nchw_to_nhwc");
+  return 0;
+}
+
+extern "C" int spgan_sphere_pack(uint16_t* out, const float* x_nhwc, const float* coords, const float* grid,
+                                 const float* in_mul, int B, int C, int H, int W, int grid_batch, int Cp,
+                                 int flat_concat, void* stream) {
+  SPGAN_CHECK_ARG(B >= 0 && C >= 0 && H >= 0 && W >= 0, "spgan_sphere_pack: negative size");
+  const int nc = coords ? 3 : 0;
+  SPGAN_CHECK_ARG(Cp >= C + nc && Cp % 64 == 0, "spgan_sphere_pack: Cp=%d must be a multiple of 64 and >= %d", Cp, C + nc);
+  if (B == 0 || H == 0 || W == 0) return 0;
+  SPGAN_CHECK_ARG(out && x_nhwc && grid, "spgan_sphere_pack: null pointer");
+  SPGAN_CHECK_ARG(grid_batch == 1 || grid_batch == B, "spgan_sphere_pack: grid batch %d must be 1 or %d", grid_batch, B);
+  SPGAN_CHECK_ARG((((uintptr_t)grid) & 7) == 0, "spgan_sphere_pack: grid must be 8-byte aligned");
+  const int64_t total = (int64_t)B * H * W * 9 * Cp;
+  sphere_pack_kernel<<<grid_for(total, 256, 8, 8), 256, 0, (cudaStream_t)stream>>>(
+      (__nv_bfloat16*)out, x_nhwc, coords, grid, in_mul, B, C, nc, H, W, grid_batch, Cp, flat_concat);
+  SPGAN_CHECK_LAUNCH("spgan_sphere_pack");
+  return 0;
+}
+
+extern "C" int spgan_conv_gemm(const SpganConvPass* p, float* y, const uint16_t* a_packed, int64_t a_rows, int kp,
+                               const uint16_t* w_packed, const float* out_mul, const float* noise, const float* noise_w,
+                               const float* bias, const float* residual, void* stream) {
+  SPGAN_CHECK_ARG(p != nullptr, "spgan_conv_gemm: null pass descriptor");
+  SPGAN_CHECK_ARG(p->precision == 1 || p->precision == 2, "spgan_conv_gemm: precision must be 1 (bf16x3) or 2 (bf16), got %d",
+                  p->precision);
+  SPGAN_CHECK_ARG(p->ntaps >= 1 && p->ntaps <= SPGAN_MAX_TAPS, "spgan_conv_gemm: %d taps unsupported", p->ntaps);
+  SPGAN_CHECK_ARG(p->in_stride == 1, "spgan_conv_gemm: in_stride %d unsupported on the tcgen05 path", p->in_stride);
+  SPGAN_CHECK_ARG(kp > 0 && kp % GEMM_BLOCK_K == 0, "spgan_conv_gemm: kp=%d must be a positive multiple of 64", kp);
+  SPGAN_CHECK_ARG(p->B >= 0 && p->H >= 0 && p->W >= 0 && p->Cout >= 0, "spgan_conv_gemm: negative size");
+  SPGAN_CHECK_ARG(p->out_stride >= 1, "spgan_conv_gemm: out_stride must be >= 1");
+  const int64_t rows = (int64_t)p->B * p->H * p->W;
+  SPGAN_CHECK_ARG(rows == a_rows, "spgan_conv_gemm: a_rows=%lld does not match B*H*W=%lld", (long long)a_rows, (long long)rows);
+  SPGAN_CHECK_ARG(rows < 2147483647LL - 65536, "spgan_conv_gemm: too many lattice points");
+  if (rows == 0 || p->Cout == 0 || p->My == 0 || p->Mx == 0) return 0;
+  SPGAN_CHECK_ARG(p->Cout >= 16, "spgan_conv_gemm: Cout=%d < 16 belongs on the SIMT path", p->Cout);
+  SPGAN_CHECK_ARG(y && a_packed && w_packed, "spgan_conv_gemm: null pointer");
+  SPGAN_CHECK_ARG(((((uintptr_t)a_packed) | ((uintptr_t)w_packed)) & 15) == 0, "spgan_conv_gemm: packed operands must be 16-byte aligned");
+
+  GemmParams gp;
+  gp.rows = (int32_t)rows;
+  gp.Hl = p->H;
+  gp.Wl = p->W;
+  gp.My = p->My;
+  gp.Mx = p->Mx;
+  gp.Cout = p->Cout;
+  gp.out_H = p->out_H;
+  gp.out_W = p->out_W;
+  gp.out_stride = p->out_stride;
+  gp.out_off_y = p->out_off_y;
+  gp.out_off_x = p->out_off_x;
+  gp.ntaps = p->ntaps;
+  gp.kblocks = kp / GEMM_BLOCK_K;
+  for (int t = 0; t < p->ntaps; ++t) gp.tap_off[t] = p->tap_dy[t] * p->W + p->tap_dx[t];
+  for (int t = p->ntaps; t < SPGAN_MAX_TAPS; ++t) gp.tap_off[t] = 0;
+  gp.m_tiles = (int32_t)((rows + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M);
+  gp.n_tiles = (p->Cout + GEMM_BLOCK_N - 1) / GEMM_BLOCK_N;
+  gp.out_scale = p->out_scale;
+  gp.act = p->act;
+  gp.act_alpha = p->act_alpha;
+  gp.act_gain = p->act_gain;
+
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)kp, (cuuint64_t)rows, 2};
+    cuuint64_t strides[2] = {(cuuint64_t)kp * 2, (cuuint64_t)rows * kp * 2};
+    cuuint32_t box[3] = {GEMM_BLOCK_K, GEMM_BLOCK_M, 1};
+    if (int e = encode_bf16_map(&tmA, a_packed, 3, dims, strides, box, "spgan_conv_gemm (A map)")) return e;
+  }
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)kp, (cuuint64_t)p->Cout, (cuuint64_t)p->ntaps, 2};
+    cuuint64_t strides[3] = {(cuuint64_t)kp * 2, (cuuint64_t)p->Cout * kp * 2, (cuuint64_t)p->ntaps * p->Cout * kp * 2};
+    cuuint32_t box[4] = {GEMM_BLOCK_K, GEMM_BLOCK_N, 1, 1};
+    if (int e = encode_bf16_map(&tmB, w_packed, 4, dims, strides, box, "spgan_conv_gemm (B map)")) return e;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p->precision == 1) return launch_gemm<3>(tmA, tmB, gp, y, out_mul, noise, noise_w, bias, residual, st);
+  return launch_gemm<1>(tmA, tmB, gp, y, out_mul, noise, noise_w, bias, residual, st);
+}

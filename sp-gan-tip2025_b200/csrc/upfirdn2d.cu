@@ -1,0 +1,131 @@
+// K2/K3: upfirdn2d over (planes, H, W) fp32 images — pad, zero-stuff by `up`, FIR with the flipped kernel,
+// keep every `down`-th sample.  HBM-bound stencil: algorithmic traffic 4*(in_h*in_w + out_h*out_w) bytes per plane.
+//   * tiled kernel (up = down = 1, K x K with K <= 4): the shapes the generator's Blur (3x3, pad 0) and the
+//     discriminator's Blur (4x4, pad 2/1) use; one 32x32 output tile per CTA, input tile staged in shared memory
+//     with coalesced row loads and zero fill for the padding.
+//   * generic kernel: any up/down/pad/kernel up to 16x16 (reads through L1/L2).
+#include "common.cuh"
+
+namespace {
+
+struct UfdParams {
+  int in_h, in_w, out_h, out_w;
+  int kh, kw;
+  int up_x, up_y, down_x, down_y;
+  int pad_x0, pad_y0;
+};
+
+__global__ void __launch_bounds__(256) upfirdn2d_generic(float* __restrict__ out, const float* __restrict__ x,
+                                                        const float* __restrict__ kernel, int64_t planes, UfdParams p) {
+  __shared__ float kf[256];  // flipped kernel
+  for (int i = threadIdx.x; i < p.kh * p.kw; i += blockDim.x) {
+    int ky = i / p.kw, kx = i - ky * p.kw;
+    kf[i] = kernel[(p.kh - 1 - ky) * p.kw + (p.kw - 1 - kx)];
+  }
+  __syncthreads();
+  const int64_t per_plane = (int64_t)p.out_h * p.out_w;
+  const int64_t total = planes * per_plane;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t plane = idx / per_plane;
+    const int rem = (int)(idx - plane * per_plane);
+    const int oy = rem / p.out_w, ox = rem - oy * p.out_w;
+    const float* xp = x + plane * (int64_t)p.in_h * p.in_w;
+    float acc = 0.f;
+    for (int ky = 0; ky < p.kh; ++ky) {
+      const int Y = oy * p.down_y + ky - p.pad_y0;
+      if (Y < 0 || Y % p.up_y != 0) continue;
+      const int iy = Y / p.up_y;
+      if (iy >= p.in_h) continue;
+      for (int kx = 0; kx < p.kw; ++kx) {
+        const int X = ox * p.down_x + kx - p.pad_x0;
+        if (X < 0 || X % p.up_x != 0) continue;
+        const int ix = X / p.up_x;
+        if (ix >= p.in_w) continue;
+        acc += kf[ky * p.kw + kx] * __ldg(xp + (int64_t)iy * p.in_w + ix);
+      }
+    }
+    out[idx] = acc;
+  }
+}
+
+constexpr int TILE = 32;
+
+template <int K>
+__global__ void __launch_bounds__(256) upfirdn2d_tiled(float* __restrict__ out, const float* __restrict__ x,
+                                                      const float* __restrict__ kernel, int tiles_x, int tiles_y,
+                                                      UfdParams p) {
+  constexpr int IN = TILE + K - 1;
+  __shared__ float tile[IN][IN + 1];
+  __shared__ float kf[K * K];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  if (threadIdx.x < K * K) {
+    int ky = threadIdx.x / K, kx = threadIdx.x - ky * K;
+    kf[threadIdx.x] = kernel[(K - 1 - ky) * K + (K - 1 - kx)];
+  }
+  const int tiles_per_plane = tiles_x * tiles_y;
+  const int64_t plane = blockIdx.x / tiles_per_plane;
+  const int t = blockIdx.x - (int)(plane * tiles_per_plane);
+  const int oy0 = (t / tiles_x) * TILE, ox0 = (t % tiles_x) * TILE;
+  const float* xp = x + plane * (int64_t)p.in_h * p.in_w;
+  const int iy0 = oy0 - p.pad_y0, ix0 = ox0 - p.pad_x0;
+  for (int r = ty; r < IN; r += 8) {
+    const int iy = iy0 + r;
+    const bool row_ok = iy >= 0 && iy < p.in_h;
+    for (int c = tx; c < IN; c += 32) {
+      const int ix = ix0 + c;
+      tile[r][c] = (row_ok && ix >= 0 && ix < p.in_w) ? __ldg(xp + (int64_t)iy * p.in_w + ix) : 0.f;
+    }
+  }
+  __syncthreads();
+  float w[K * K];
+#pragma unroll
+  for (int i = 0; i < K * K; ++i) w[i] = kf[i];
+  float* op = out + plane * (int64_t)p.out_h * p.out_w;
+  const int ox = ox0 + tx;
+#pragma unroll
+  for (int r = 0; r < TILE / 8; ++r) {
+    const int ly = ty + r * 8;
+    const int oy = oy0 + ly;
+    float acc = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < K; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < K; ++kx) acc += w[ky * K + kx] * tile[ly + ky][tx + kx];
+    if (oy < p.out_h && ox < p.out_w) op[(int64_t)oy * p.out_w + ox] = acc;
+  }
+}
+
+}  // namespace
+
+extern "C" int spgan_upfirdn2d(float* out, const float* x, const float* kernel, int64_t planes, int in_h, int in_w,
+                               int kh, int kw, int up_x, int up_y, int down_x, int down_y, int pad_x0, int pad_x1,
+                               int pad_y0, int pad_y1, void* stream) {
+  SPGAN_CHECK_ARG(planes >= 0 && in_h >= 0 && in_w >= 0, "spgan_upfirdn2d: negative size");
+  SPGAN_CHECK_ARG(kh >= 1 && kw >= 1 && kh * kw <= 256, "spgan_upfirdn2d: kernel %dx%d unsupported (max 256 taps)", kh, kw);
+  SPGAN_CHECK_ARG(up_x >= 1 && up_y >= 1 && down_x >= 1 && down_y >= 1, "spgan_upfirdn2d: up/down must be >= 1");
+  UfdParams p;
+  p.in_h = in_h; p.in_w = in_w; p.kh = kh; p.kw = kw;
+  p.up_x = up_x; p.up_y = up_y; p.down_x = down_x; p.down_y = down_y;
+  p.pad_x0 = pad_x0; p.pad_y0 = pad_y0;
+  const int full_h = in_h * up_y + pad_y0 + pad_y1 - kh;
+  const int full_w = in_w * up_x + pad_x0 + pad_x1 - kw;
+  p.out_h = full_h >= 0 ? full_h / down_y + 1 : 0;
+  p.out_w = full_w >= 0 ? full_w / down_x + 1 : 0;
+  if (planes == 0 || p.out_h <= 0 || p.out_w <= 0) return 0;
+  SPGAN_CHECK_ARG(out && x && kernel, "spgan_upfirdn2d: input and kernel must be CUDA tensors (null pointer)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool unit = up_x == 1 && up_y == 1 && down_x == 1 && down_y == 1 && kh == kw && pad_x0 >= 0 && pad_y0 >= 0;
+  const int tiles_x = (p.out_w + TILE - 1) / TILE, tiles_y = (p.out_h + TILE - 1) / TILE;
+  const int64_t blocks = planes * tiles_x * tiles_y;
+  if (unit && kh >= 2 && kh <= 4 && blocks <= 2147483647LL) {
+    if (kh == 2) upfirdn2d_tiled<2><<<(unsigned)blocks, 256, 0, st>>>(out, x, kernel, tiles_x, tiles_y, p);
+    if (kh == 3) upfirdn2d_tiled<3><<<(unsigned)blocks, 256, 0, st>>>(out, x, kernel, tiles_x, tiles_y, p);
+    if (kh == 4) upfirdn2d_tiled<4><<<(unsigned)blocks, 256, 0, st>>>(out, x, kernel, tiles_x, tiles_y, p);
+  } else {
+    const int64_t total = planes * p.out_h * p.out_w;
+    upfirdn2d_generic<<<grid_for(total, 256, 8, 8), 256, 0, st>>>(out, x, kernel, planes, p);
+  }
+  SPGAN_CHECK_LAUNCH("spgan_upfirdn2d");
+  return 0;
+}

@@ -1,0 +1,699 @@
+"""Autograd-level operators over the C ABI (include/spgan_b200.h).
+
+Every function here launches kernels of libspgan_b200.so on the current CUDA stream of the input tensors' device.
+torch supplies device memory, streams and the autograd graph; none of the arithmetic of the path is done by torch
+kernels in the forward direction.  The conv operator is written as a (bi)linear map with its adjoint so that
+first- and second-order gradients (R1 through D, path-length regularisation through G; reference
+models/losses.py:36-41, 60-78) compose out of the same three kernels, the way the reference composes them out of
+cuDNN fwd / dgrad / wgrad.
+"""
+import ctypes
+import math
+from collections import OrderedDict
+from dataclasses import dataclass
+
+import torch
+
+from . import lib
+from .lib import ConvPass
+
+# 0 = exact fp32 SIMT, 1 = bf16x3 split on tcgen05 (fp32-equivalent, default), 2 = plain bf16 on tcgen05
+_PRECISION = 1
+
+
+def set_precision(p):
+    global _PRECISION
+    if p not in (0, 1, 2):
+        raise ValueError("precision must be 0 (fp32 SIMT), 1 (bf16x3 tcgen05) or 2 (bf16 tcgen05)")
+    _PRECISION = p
+
+
+def get_precision():
+    return _PRECISION
+
+
+def _stream(t):
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _check_cuda(t, who):
+    if not t.is_cuda:
+        raise RuntimeError("%s: input must be a CUDA tensor (this package has no CPU path)" % who)
+    if t.dtype != torch.float32:
+        raise RuntimeError("%s: only float32 tensors are supported, got %s" % (who, t.dtype))
+
+
+def _f32c(t, who):
+    _check_cuda(t, who)
+    return t.contiguous()
+
+
+# =================================================================================================== K1 bias-act
+def bias_act(x, bias=None, ref=None, act=3, grad=0, alpha=0.2, scale=2 ** 0.5):
+    """fused.fused_bias_act(input, bias, refer, act, grad, alpha, scale) — models/custom_ops/fused_bias_act.cpp:11-20.
+    Empty tensors / None mean "absent", as in the reference."""
+    x = _f32c(x, "fused_bias_act")
+    out = torch.empty_like(x)
+    b = bias if (bias is not None and bias.numel() > 0) else None
+    r = ref if (ref is not None and ref.numel() > 0) else None
+    step_b = 1
+    if b is not None:
+        b = _f32c(b, "fused_bias_act")
+        for d in x.shape[2:]:
+            step_b *= d
+    if r is not None:
+        r = _f32c(r, "fused_bias_act")
+    with torch.cuda.device(x.device):
+        lib.call("spgan_bias_act", _ptr(out), _ptr(x), _ptr(b), _ptr(r), x.numel(), step_b,
+                 b.numel() if b is not None else 1, int(act), int(grad), float(alpha), float(scale), _stream(x))
+    return out
+
+
+class FusedLeakyReLUFunctionBackward(torch.autograd.Function):
+    """models/custom_ops/fused_act.py:24-53 (grad_input and grad_bias in one kernel)."""
+
+    @staticmethod
+    def forward(ctx, grad_output, out, negative_slope, scale):
+        ctx.save_for_backward(out)
+        ctx.negative_slope = negative_slope
+        ctx.scale = scale
+        go = _f32c(grad_output, "fused_leaky_relu backward")
+        outc = _f32c(out, "fused_leaky_relu backward")
+        grad_input = torch.empty_like(go)
+        B, C = go.shape[0], go.shape[1]
+        inner = go.numel() // max(B * C, 1)
+        grad_bias = torch.empty(C, device=go.device, dtype=torch.float32)
+        with torch.cuda.device(go.device):
+            lib.call("spgan_bias_act_bwd", _ptr(grad_input), _ptr(grad_bias), _ptr(go), _ptr(outc), B, C, inner,
+                     float(negative_slope), float(scale), _stream(go))
+        return grad_input, grad_bias
+
+    @staticmethod
+    def backward(ctx, gradgrad_input, gradgrad_bias):
+        out, = ctx.saved_tensors
+        gradgrad_out = bias_act(gradgrad_input, gradgrad_bias, out, 3, 1, ctx.negative_slope, ctx.scale)
+        return gradgrad_out, None, None, None
+
+
+class FusedLeakyReLUFunction(torch.autograd.Function):
+    """models/custom_ops/fused_act.py:56-75."""
+
+    @staticmethod
+    def forward(ctx, input, bias, negative_slope, scale):
+        out = bias_act(input, bias, None, 3, 0, negative_slope, scale)
+        ctx.save_for_backward(out)
+        ctx.negative_slope = negative_slope
+        ctx.scale = scale
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        out, = ctx.saved_tensors
+        grad_input, grad_bias = FusedLeakyReLUFunctionBackward.apply(grad_output, out, ctx.negative_slope, ctx.scale)
+        return grad_input, grad_bias, None, None
+
+
+def fused_leaky_relu(input, bias, negative_slope=0.2, scale=2 ** 0.5):
+    """models/custom_ops/fused_act.py:91-101 (CUDA branch)."""
+    _check_cuda(input, "fused_leaky_relu")
+    return FusedLeakyReLUFunction.apply(input, bias, negative_slope, scale)
+
+
+def noise_bias_act(x, noise, noise_weight, bias, negative_slope=0.2, scale=2 ** 0.5):
+    """NoiseInjection (models/ops.py:784) + FusedLeakyReLU in one pass; inference-only fusion (no autograd)."""
+    x = _f32c(x, "noise_bias_act")
+    B, C = x.shape[0], x.shape[1]
+    inner = x.numel() // max(B * C, 1)
+    out = torch.empty_like(x)
+    nz = _f32c(noise, "noise_bias_act") if noise is not None else None
+    if nz is not None and nz.numel() != B * inner:
+        raise RuntimeError("noise_bias_act: noise must have shape (B, 1, H, W) matching the input")
+    with torch.cuda.device(x.device):
+        lib.call("spgan_noise_bias_act", _ptr(out), _ptr(x), _ptr(nz), _ptr(noise_weight) if nz is not None else _ptr(None),
+                 _ptr(bias), B, C, inner, float(negative_slope), float(scale), _stream(x))
+    return out
+
+
+# =================================================================================================== K2/K3 upfirdn2d
+def _upfirdn2d_raw(x4, kernel, up_x, up_y, down_x, down_y, px0, px1, py0, py1):
+    """x4: (planes..., H, W) contiguous; returns (planes, out_h, out_w)."""
+    in_h, in_w = x4.shape[-2], x4.shape[-1]
+    planes = x4.numel() // max(in_h * in_w, 1)
+    kh, kw = kernel.shape
+    out_h = (in_h * up_y + py0 + py1 - kh) // down_y + 1
+    out_w = (in_w * up_x + px0 + px1 - kw) // down_x + 1
+    out = torch.empty((planes, max(out_h, 0), max(out_w, 0)), device=x4.device, dtype=torch.float32)
+    with torch.cuda.device(x4.device):
+        lib.call("spgan_upfirdn2d", _ptr(out), _ptr(x4), _ptr(kernel), planes, in_h, in_w, kh, kw, up_x, up_y, down_x,
+                 down_y, px0, px1, py0, py1, _stream(x4))
+    return out
+
+
+class UpFirDn2dBackward(torch.autograd.Function):
+    """models/custom_ops/upfirdn2d.py:24-90."""
+
+    @staticmethod
+    def forward(ctx, grad_output, kernel, grad_kernel, up, down, pad, g_pad, in_size, out_size):
+        up_x, up_y = up
+        down_x, down_y = down
+        g_pad_x0, g_pad_x1, g_pad_y0, g_pad_y1 = g_pad
+        go = _f32c(grad_output, "upfirdn2d backward").reshape(-1, out_size[0], out_size[1])
+        grad_input = _upfirdn2d_raw(go, grad_kernel, down_x, down_y, up_x, up_y, g_pad_x0, g_pad_x1, g_pad_y0, g_pad_y1)
+        grad_input = grad_input.view(in_size[0], in_size[1], in_size[2], in_size[3])
+        ctx.save_for_backward(kernel)
+        ctx.up, ctx.down, ctx.pad = up, down, pad
+        ctx.in_size, ctx.out_size = in_size, out_size
+        return grad_input
+
+    @staticmethod
+    def backward(ctx, gradgrad_input):
+        kernel, = ctx.saved_tensors
+        up_x, up_y = ctx.up
+        down_x, down_y = ctx.down
+        px0, px1, py0, py1 = ctx.pad
+        ggi = _f32c(gradgrad_input, "upfirdn2d grad-grad").reshape(-1, ctx.in_size[2], ctx.in_size[3])
+        ggo = _upfirdn2d_raw(ggi, kernel, up_x, up_y, down_x, down_y, px0, px1, py0, py1)
+        ggo = ggo.view(ctx.in_size[0], ctx.in_size[1], ctx.out_size[0], ctx.out_size[1])
+        return ggo, None, None, None, None, None, None, None, None
+
+
+class UpFirDn2d(torch.autograd.Function):
+    """models/custom_ops/upfirdn2d.py:93-147."""
+
+    @staticmethod
+    def forward(ctx, input, kernel, up, down, pad):
+        up_x, up_y = up
+        down_x, down_y = down
+        pad_x0, pad_x1, pad_y0, pad_y1 = pad
+        kernel_h, kernel_w = kernel.shape
+        batch, channel, in_h, in_w = input.shape
+        ctx.in_size = input.shape
+        x = _f32c(input, "upfirdn2d").reshape(-1, in_h, in_w)
+        kernel = _f32c(kernel, "upfirdn2d")
+        ctx.save_for_backward(kernel, torch.flip(kernel, [0, 1]))
+        out_h = (in_h * up_y + pad_y0 + pad_y1 - kernel_h) // down_y + 1
+        out_w = (in_w * up_x + pad_x0 + pad_x1 - kernel_w) // down_x + 1
+        ctx.out_size = (out_h, out_w)
+        ctx.up, ctx.down, ctx.pad = (up_x, up_y), (down_x, down_y), (pad_x0, pad_x1, pad_y0, pad_y1)
+        g_pad_x0 = kernel_w - pad_x0 - 1
+        g_pad_y0 = kernel_h - pad_y0 - 1
+        g_pad_x1 = in_w * up_x - out_w * down_x + pad_x0 - up_x + 1
+        g_pad_y1 = in_h * up_y - out_h * down_y + pad_y0 - up_y + 1
+        ctx.g_pad = (g_pad_x0, g_pad_x1, g_pad_y0, g_pad_y1)
+        out = _upfirdn2d_raw(x, kernel, up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1)
+        return out.view(-1, channel, out_h, out_w)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        kernel, grad_kernel = ctx.saved_tensors
+        grad_input = UpFirDn2dBackward.apply(grad_output, kernel, grad_kernel, ctx.up, ctx.down, ctx.pad, ctx.g_pad,
+                                             ctx.in_size, ctx.out_size)
+        return grad_input, None, None, None, None
+
+
+def upfirdn2d(input, kernel, up=1, down=1, pad=(0, 0)):
+    """models/custom_ops/upfirdn2d.py:150-161 (CUDA branch)."""
+    _check_cuda(input, "upfirdn2d")
+    return UpFirDn2d.apply(input, kernel, (up, up), (down, down), (pad[0], pad[1], pad[0], pad[1]))
+
+
+# =================================================================================================== L7 linear
+class _LinearFn(torch.autograd.Function):
+    """y = x (W * w_scale)^T + bias * b_scale  (models/ops.py:213-218 without the activation)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, w_scale, b_scale):
+        xc, wc = _f32c(x, "equal_linear"), _f32c(weight, "equal_linear")
+        ctx.save_for_backward(xc, wc)
+        ctx.w_scale, ctx.b_scale, ctx.has_bias = w_scale, b_scale, bias is not None
+        return _linear_raw(xc, wc, bias, w_scale, b_scale, 0, 0.0, 1.0)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = _LinearFn.apply(g, w.t(), None, ctx.w_scale, 1.0)
+        if ctx.needs_input_grad[1]:
+            gw = _LinearFn.apply(g.t(), x.t(), None, ctx.w_scale, 1.0)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = g.sum(0) * ctx.b_scale
+        return gx, gw, gb, None, None
+
+
+def _linear_raw(x, w, bias, w_scale, b_scale, act, alpha, gain):
+    M, K = x.shape
+    N = w.shape[0]
+    y = torch.empty((M, N), device=x.device, dtype=torch.float32)
+    b = _f32c(bias, "equal_linear") if bias is not None else None
+    with torch.cuda.device(x.device):
+        lib.call("spgan_linear", _ptr(y), _ptr(x), _ptr(w), _ptr(b), M, N, K, float(w_scale), float(b_scale), int(act),
+                 float(alpha), float(gain), _stream(x))
+    return y
+
+
+def equal_linear(x, weight, bias, scale, lr_mul=1.0, activation=False):
+    """EqualLinear.forward (models/ops.py:213-218).  Under no_grad the bias + leaky-ReLU epilogue is fused."""
+    _check_cuda(x, "equal_linear")
+    lead = x.shape[:-1]
+    x2 = x.reshape(-1, x.shape[-1])
+    if not torch.is_grad_enabled() or not (x.requires_grad or weight.requires_grad or (bias is not None and bias.requires_grad)):
+        y = _linear_raw(_f32c(x2, "equal_linear"), _f32c(weight, "equal_linear"), bias, scale, lr_mul,
+                        1 if activation else 0, 0.2, 2 ** 0.5)
+    elif activation:
+        y = _LinearFn.apply(x2, weight, None, scale, 1.0)
+        y = fused_leaky_relu(y, bias * lr_mul)
+    else:
+        y = _LinearFn.apply(x2, weight, bias, scale, lr_mul)
+    return y.reshape(*lead, weight.shape[0])
+
+
+# =================================================================================================== conv geometry
+@dataclass(frozen=True)
+class ConvGeom:
+    """A 2-D convolution family member: F.conv2d(stride, padding) or F.conv_transpose2d(stride) followed by a crop of
+    `crop` pixels per side (models/ops.py:617-619).  Weights are always indexed (O, C, kh, kw)."""
+    kh: int
+    kw: int
+    stride: int = 1
+    pad: int = 0
+    transposed: bool = False
+    crop: int = 0
+
+    def out_size(self, H, W):
+        if self.transposed:
+            return (H - 1) * self.stride + self.kh - 2 * self.crop, (W - 1) * self.stride + self.kw - 2 * self.crop
+        return (H + 2 * self.pad - self.kh) // self.stride + 1, (W + 2 * self.pad - self.kw) // self.stride + 1
+
+
+def _ceil_div(a, b):
+    return -(-a // b)
+
+
+def plan_passes(geom, adjoint, in_hw, out_hw):
+    """Decompose the linear map (base conv, or its adjoint = data gradient) into lattice passes.
+    Returns a list of dicts {My, Mx, in_stride, out_stride, off_y, off_x, taps=[(dy, dx, widx)]}; `covers` tells
+    whether the passes write every output element (otherwise the caller zero-fills first)."""
+    s = geom.stride
+    kh, kw = geom.kh, geom.kw
+    H_out, W_out = out_hw
+    passes = []
+    covers = True
+    if not adjoint and not geom.transposed:
+        taps = [(ky - geom.pad, kx - geom.pad, ky * kw + kx) for ky in range(kh) for kx in range(kw)]
+        passes.append(dict(My=H_out, Mx=W_out, in_stride=s, out_stride=1, off_y=0, off_x=0, taps=taps))
+    elif adjoint and geom.transposed:
+        taps = [(ky - geom.crop, kx - geom.crop, ky * kw + kx) for ky in range(kh) for kx in range(kw)]
+        passes.append(dict(My=H_out, Mx=W_out, in_stride=s, out_stride=1, off_y=0, off_x=0, taps=taps))
+    else:
+        for ay in range(s):
+            for ax in range(s):
+                if not adjoint:  # transposed conv forward: Y = s*i + ky - crop
+                    ys = [(-(ky - geom.crop - ay) // s, ky) for ky in range(kh) if (ky - geom.crop - ay) % s == 0]
+                    xs = [(-(kx - geom.crop - ax) // s, kx) for kx in range(kw) if (kx - geom.crop - ax) % s == 0]
+                else:  # data gradient of a strided conv: Y = s*i + ky - pad
+                    ys = [((ay - ky + geom.pad) // s, ky) for ky in range(kh) if (ay - ky + geom.pad) % s == 0]
+                    xs = [((ax - kx + geom.pad) // s, kx) for kx in range(kw) if (ax - kx + geom.pad) % s == 0]
+                My, Mx = _ceil_div(H_out - ay, s), _ceil_div(W_out - ax, s)
+                if My <= 0 or Mx <= 0:
+                    continue
+                if not ys or not xs:
+                    covers = False
+                    continue
+                taps = [(dy, dx, ky * kw + kx) for dy, ky in ys for dx, kx in xs]
+                passes.append(dict(My=My, Mx=Mx, in_stride=1, out_stride=s, off_y=ay, off_x=ax, taps=taps))
+    return passes, covers
+
+
+def _fill_pass(p, B, Cin, H, W, Cout, out_H, out_W, ws_o, ws_c, out_scale, act, alpha, gain, precision):
+    cp = ConvPass()
+    cp.B, cp.Cin, cp.H, cp.W = B, Cin, H, W
+    cp.Cout, cp.out_H, cp.out_W = Cout, out_H, out_W
+    cp.My, cp.Mx = p["My"], p["Mx"]
+    cp.in_stride, cp.out_stride = p["in_stride"], p["out_stride"]
+    cp.out_off_y, cp.out_off_x = p["off_y"], p["off_x"]
+    taps = p["taps"]
+    if len(taps) > lib.MAX_TAPS:
+        raise RuntimeError("conv: %d taps exceed the supported %d" % (len(taps), lib.MAX_TAPS))
+    cp.ntaps = len(taps)
+    for t, (dy, dx, wi) in enumerate(taps):
+        cp.tap_dy[t], cp.tap_dx[t], cp.tap_w[t] = dy, dx, wi
+    cp.ws_o, cp.ws_c = ws_o, ws_c
+    cp.out_scale = out_scale
+    cp.act, cp.act_alpha, cp.act_gain = act, alpha, gain
+    cp.precision = precision
+    return cp
+
+
+# --------------------------------------------------------------------------------------------------- weight packing
+_WEIGHT_CACHE = OrderedDict()
+_WEIGHT_CACHE_MAX = 512
+
+
+def _round_up(a, b):
+    return _ceil_div(a, b) * b
+
+
+def _packed_weight(w, Cout, Cin, ws_o, ws_c, tap_w, Cp, merged):
+    """bf16 hi/lo copy of the weight in [2][ntaps][Cout][Cp] (or merged-K) order, cached per weight version."""
+    key = (w.data_ptr(), w._version, tuple(w.shape), Cout, Cin, ws_o, ws_c, tuple(tap_w), Cp, merged, w.device.index)
+    hit = _WEIGHT_CACHE.get(key)
+    if hit is not None:
+        _WEIGHT_CACHE.move_to_end(key)
+        return hit[0]
+    ntaps = len(tap_w)
+    out = torch.empty((2, ntaps, Cout, Cp), device=w.device, dtype=torch.bfloat16)
+    arr = (ctypes.c_int32 * ntaps)(*tap_w)
+    with torch.cuda.device(w.device):
+        lib.call("spgan_pack_weight", _ptr(out), _ptr(w), Cout, Cin, ws_o, ws_c, ntaps, arr, Cp, int(merged), _stream(w))
+    _WEIGHT_CACHE[key] = (out, w)  # keep `w` alive so the data_ptr cannot be recycled while the entry exists
+    if len(_WEIGHT_CACHE) > _WEIGHT_CACHE_MAX:
+        _WEIGHT_CACHE.popitem(last=False)
+    return out
+
+
+def clear_weight_cache():
+    _WEIGHT_CACHE.clear()
+
+
+# --------------------------------------------------------------------------------------------------- conv driver
+def _tensor_path_ok(passes, Cin, Cout, precision):
+    return precision != 0 and Cin >= 16 and Cout >= 16 and all(p["in_stride"] == 1 for p in passes)
+
+
+def conv_apply(x, w, geom, adjoint=False, out_hw=None, in_mul=None, out_mul=None, out_scale=1.0, noise=None,
+               noise_w=None, bias=None, act=None, residual=None, precision=None):
+    """y = [act]( out_scale * out_mul[b,o] * L_w(in_mul[b,c] * x) + noise_w*noise + bias ) + residual, no autograd.
+
+    L_w is the conv described by `geom` (adjoint=False) or its adjoint / data gradient (adjoint=True, `out_hw`
+    required).  w is (O, C, kh, kw).  act = (alpha, gain) or None."""
+    x = _f32c(x, "conv")
+    w = _f32c(w, "conv")
+    B, Cx, H, W = x.shape
+    O, C = w.shape[0], w.shape[1]
+    kk = geom.kh * geom.kw
+    if tuple(w.shape[2:]) != (geom.kh, geom.kw):
+        raise RuntimeError("conv: weight %s does not match a %dx%d kernel" % (tuple(w.shape), geom.kh, geom.kw))
+    if not adjoint:
+        if Cx != C:
+            raise RuntimeError("conv: input has %d channels, weight expects %d" % (Cx, C))
+        Cin, Cout, ws_o, ws_c = C, O, C * kk, kk
+        oh, ow = geom.out_size(H, W)
+    else:
+        if Cx != O:
+            raise RuntimeError("conv adjoint: input has %d channels, weight expects %d" % (Cx, O))
+        Cin, Cout, ws_o, ws_c = O, C, kk, C * kk
+        oh, ow = out_hw
+    precision = _PRECISION if precision is None else precision
+    passes, covers = plan_passes(geom, adjoint, (H, W), (oh, ow))
+    y = (torch.empty if covers else torch.zeros)((B, Cout, max(oh, 0), max(ow, 0)), device=x.device, dtype=torch.float32)
+    if y.numel() == 0 or not passes:
+        return y
+    a, g = (act if act is not None else (0.0, 1.0))
+    act_on = 1 if act is not None else 0
+    im = _f32c(in_mul, "conv") if in_mul is not None else None
+    om = _f32c(out_mul, "conv") if out_mul is not None else None
+    nz = _f32c(noise, "conv") if noise is not None else None
+    nwt = _f32c(noise_w, "conv") if (noise is not None) else None
+    bs = _f32c(bias, "conv") if bias is not None else None
+    rs = _f32c(residual, "conv") if residual is not None else None
+    if rs is not None and rs.shape != y.shape:
+        raise RuntimeError("conv: residual shape %s != output shape %s" % (tuple(rs.shape), tuple(y.shape)))
+    st = _stream(x)
+    with torch.cuda.device(x.device):
+        if _tensor_path_ok(passes, Cin, Cout, precision):
+            # one packed activation shared by all passes: pads cover every pass's tap reach
+            dy_all = [t[0] for p in passes for t in p["taps"]]
+            dx_all = [t[1] for p in passes for t in p["taps"]]
+            pt, pl = max(0, -min(dy_all)), max(0, -min(dx_all))
+            reach_y = max(p["My"] - 1 + max(t[0] for t in p["taps"]) for p in passes)
+            reach_x = max(p["Mx"] - 1 + max(t[1] for t in p["taps"]) for p in passes)
+            Hl = pt + max(H, reach_y + 1)
+            Wl = pl + max(W, reach_x + 1)
+            Cp = _round_up(Cin, 64)
+            rows = B * Hl * Wl
+            a_packed = torch.empty((2, rows, Cp), device=x.device, dtype=torch.bfloat16)
+            lib.call("spgan_pack_act", _ptr(a_packed), _ptr(x), _ptr(im), B, Cin, H, W, Cp, pt, pl, Hl, Wl, st)
+            for p in passes:
+                shifted = dict(p, taps=[(dy + pt, dx + pl, wi) for dy, dx, wi in p["taps"]])
+                cp = _fill_pass(shifted, B, Cin, Hl, Wl, Cout, oh, ow, ws_o, ws_c, out_scale, act_on, a, g, precision)
+                wp = _packed_weight(w, Cout, Cin, ws_o, ws_c, [t[2] for t in p["taps"]], Cp, False)
+                lib.call("spgan_conv_gemm", ctypes.byref(cp), _ptr(y), _ptr(a_packed), rows, Cp, _ptr(wp), _ptr(om),
+                         _ptr(nz), _ptr(nwt), _ptr(bs), _ptr(rs), st)
+        else:
+            for p in passes:
+                cp = _fill_pass(p, B, Cin, H, W, Cout, oh, ow, ws_o, ws_c, out_scale, act_on, a, g, 0)
+                lib.call("spgan_conv_pass", ctypes.byref(cp), _ptr(y), _ptr(x), _ptr(w), _ptr(im), _ptr(om), _ptr(nz),
+                         _ptr(nwt), _ptr(bs), _ptr(rs), st)
+    return y
+
+
+def conv_wgrad(g, x, w_shape, geom, in_mul=None, out_mul=None, out_scale=1.0):
+    """dw[o,c,ky,kx] = out_scale * sum_b <out_mul*g, L_{e(o,c,ky,kx)}(in_mul*x)> for the BASE conv of `geom`
+    (x = base input (B, C, H, W), g = base output gradient (B, O, oh, ow))."""
+    g = _f32c(g, "conv wgrad")
+    x = _f32c(x, "conv wgrad")
+    O, C, kh, kw = w_shape
+    B, _, H, W = x.shape
+    oh, ow = g.shape[2], g.shape[3]
+    kk = kh * kw
+    dw = torch.zeros(w_shape, device=x.device, dtype=torch.float32)
+    if g.numel() == 0 or x.numel() == 0:
+        return dw
+    passes, _ = plan_passes(geom, False, (H, W), (oh, ow))
+    im = _f32c(in_mul, "conv wgrad") if in_mul is not None else None
+    om = _f32c(out_mul, "conv wgrad") if out_mul is not None else None
+    with torch.cuda.device(x.device):
+        for p in passes:
+            cp = _fill_pass(p, B, C, H, W, O, oh, ow, C * kk, kk, out_scale, 0, 0.0, 1.0, 0)
+            lib.call("spgan_conv_wgrad", ctypes.byref(cp), _ptr(dw), _ptr(g), _ptr(x), _ptr(im), _ptr(om), 1, _stream(x))
+    return dw
+
+
+class _ConvFn(torch.autograd.Function):
+    """y = out_scale * D(out_mul) L_w( D(in_mul) x ), differentiable to any order in x, w, in_mul, out_mul
+    (the weight-gradient node itself is first-order only, which is all R1 / path-length need)."""
+
+    @staticmethod
+    def forward(ctx, x, w, in_mul, out_mul, geom, adjoint, out_hw, out_scale):
+        y = conv_apply(x, w, geom, adjoint, out_hw, in_mul, out_mul, out_scale)
+        ctx.geom, ctx.adjoint, ctx.out_scale = geom, adjoint, out_scale
+        ctx.in_hw = (x.shape[2], x.shape[3])
+        ctx.has_im, ctx.has_om = in_mul is not None, out_mul is not None
+        ctx.save_for_backward(x, w, in_mul, out_mul, y if out_mul is not None else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w, in_mul, out_mul, y = ctx.saved_tensors
+        need_x, need_w, need_im, need_om = ctx.needs_input_grad[:4]
+        gx = gw = gim = gom = None
+        if need_x or need_im:
+            # D(in_mul)^-1 applied lazily: the un-modulated data gradient serves both dx and d(in_mul)
+            gx_un = _ConvFn.apply(g, w, out_mul, None, ctx.geom, not ctx.adjoint, ctx.in_hw, ctx.out_scale)
+            if need_im:
+                gim = (x * gx_un).sum(dim=(2, 3))
+            if need_x:
+                gx = gx_un * in_mul[:, :, None, None] if ctx.has_im else gx_un
+        if need_w:
+            if not ctx.adjoint:
+                gw = _WgradFn.apply(g, x, in_mul, out_mul, tuple(w.shape), ctx.geom, ctx.out_scale)
+            else:  # z = L^T(g'): <z, gz> = <L(gz), g'>, so the base input is the incoming gradient
+                gw = _WgradFn.apply(x, g, out_mul, in_mul, tuple(w.shape), ctx.geom, ctx.out_scale)
+        if need_om:
+            gom = (g * y).sum(dim=(2, 3)) / out_mul
+        return gx, gw, gim, gom, None, None, None, None
+
+
+class _WgradFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, g, x, in_mul, out_mul, w_shape, geom, out_scale):
+        return conv_wgrad(g, x, w_shape, geom, in_mul, out_mul, out_scale)
+
+    @staticmethod
+    def backward(ctx, ggw):
+        raise NotImplementedError("spgan_b200: third-order derivative through the conv weight gradient is not implemented")
+
+
+def conv2d(x, w, geom, in_mul=None, out_mul=None, out_scale=1.0):
+    """Differentiable modulated / plain convolution (forward of models/ops.py:617, 634; 175)."""
+    _check_cuda(x, "conv2d")
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (x, w, in_mul, out_mul)):
+        return _ConvFn.apply(x, w, in_mul, out_mul, geom, False, None, out_scale)
+    return conv_apply(x, w, geom, False, None, in_mul, out_mul, out_scale)
+
+
+def demod_coefficients(w, s, scale, eps=1e-8):
+    """d[b,o] = rsqrt(scale^2 * sum_c s[b,c]^2 sum_t w[o,c,t]^2 + eps)  (models/ops.py:603-604), no autograd."""
+    w = _f32c(w, "demod")
+    s = _f32c(s, "demod")
+    O, C = w.shape[0], w.shape[1]
+    taps = w.numel() // max(O * C, 1)
+    B = s.shape[0]
+    d = torch.empty((B, O), device=w.device, dtype=torch.float32)
+    with torch.cuda.device(w.device):
+        lib.call("spgan_demod", _ptr(d), _ptr(s), _ptr(w), B, C, O, taps, float(scale), float(eps), _stream(w))
+    return d
+
+
+# =================================================================================================== spherical gather
+def sphere_gather_raw(z, grid, out=None, out_bstride=None, out_coff=0, encode=False):
+    """F.grid_sample(z, grid, bilinear, border, align_corners=True) for a (Bg, 3H, 3W, 2) tap grid."""
+    z = _f32c(z, "sphere_gather")
+    grid = _f32c(grid, "sphere_gather")
+    B, C, H, W = z.shape
+    if grid.dim() != 4 or grid.shape[1] != 3 * H or grid.shape[2] != 3 * W or grid.shape[3] != 2 or grid.shape[0] not in (1, B):
+        raise RuntimeError("sphere_gather: grid %s does not match input %s" % (tuple(grid.shape), tuple(z.shape)))
+    if out is None:
+        out = torch.empty((B, C, 3 * H, 3 * W), device=z.device, dtype=torch.float32)
+        out_bstride = C
+    with torch.cuda.device(z.device):
+        lib.call("spgan_sphere_gather", _ptr(out), _ptr(z), _ptr(grid), B, C, H, W, grid.shape[0], out_bstride, out_coff,
+                 1 if encode else 0, _stream(z))
+    return out
+
+
+def sphere_gather_indices(grid, H, W):
+    """(x0, y0, wx, wy) exactly as the gather kernels compute them (bit-exactness tests)."""
+    grid = _f32c(grid, "sphere_gather_indices")
+    n = grid.numel() // 2
+    x0 = torch.empty(n, device=grid.device, dtype=torch.int32)
+    y0 = torch.empty_like(x0)
+    wx = torch.empty(n, device=grid.device, dtype=torch.float32)
+    wy = torch.empty_like(wx)
+    with torch.cuda.device(grid.device):
+        lib.call("spgan_sphere_gather_indices", _ptr(x0), _ptr(y0), _ptr(wx), _ptr(wy), _ptr(grid), n, H, W, _stream(grid))
+    shp = grid.shape[:-1]
+    return x0.view(shp), y0.view(shp), wx.view(shp), wy.view(shp)
+
+
+class _BlockMeanFn(torch.autograd.Function):
+    """grad_in = mean over each 3x3 block * 0.1 (grid_generator.py:615-623); linear, so its own backward is the
+    adjoint (each block cell receives g * 0.1 / 9)."""
+
+    @staticmethod
+    def forward(ctx, go):
+        go = _f32c(go, "sphere_gather backward")
+        B, C, H3, W3 = go.shape
+        H, W = H3 // 3, W3 // 3
+        gi = torch.empty((B, C, H, W), device=go.device, dtype=torch.float32)
+        with torch.cuda.device(go.device):
+            lib.call("spgan_sphere_gather_bwd", _ptr(gi), _ptr(go), B * C, H, W, _stream(go))
+        return gi
+
+    @staticmethod
+    def backward(ctx, gg):
+        return (gg * (0.1 / 9.0)).repeat_interleave(3, dim=2).repeat_interleave(3, dim=3)
+
+
+class GridSamplerFuncNoGrad(torch.autograd.Function):
+    """models/spherenet/grid_generator.py:602-623: bilinear border gather with the SURROGATE backward.
+    The guarded all_reduce of :621-622 is deliberately not reproduced."""
+
+    @staticmethod
+    def forward(ctx, z, grid):
+        return sphere_gather_raw(z, grid)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        return _BlockMeanFn.apply(grad_output), None
+
+
+def sphere_gather(z, grid):
+    _check_cuda(z, "sphere_gather")
+    return GridSamplerFuncNoGrad.apply(z, grid)
+
+
+# =================================================================================================== spherical conv
+def sphere_modconv_fused(x, coords, grid, w, in_mul, out_mul, out_scale, act=None, flat_concat=True, precision=None,
+                         residual=None, bias=None):
+    """Inference path of spgan_ops_gs.ModulatedConv2d (models/spgan_ops_gs.py:791-816): the gather, coordinate
+    encoding, concat, modulation and bf16 split happen in one producer kernel (`spgan_sphere_pack`) whose output
+    feeds the tcgen05 GEMM; the 9x gathered fp32 tensor of the reference never exists."""
+    x = _f32c(x, "sphere_modconv")
+    w = _f32c(w, "sphere_modconv")
+    grid = _f32c(grid, "sphere_modconv")
+    B, C, H, W = x.shape
+    O, Ct = w.shape[0], w.shape[1]
+    nc = 0 if coords is None else coords.shape[1]
+    if Ct != C + nc or tuple(w.shape[2:]) != (3, 3):
+        raise RuntimeError("sphere_modconv: weight %s does not match %d + %d channels, 3x3" % (tuple(w.shape), C, nc))
+    precision = _PRECISION if precision is None else precision
+    if precision == 0 or O < 16:
+        return _sphere_modconv_simt(x, coords, grid, w, in_mul, out_mul, out_scale, act, flat_concat, residual, bias)
+    Cp = _round_up(Ct, 64)
+    rows = B * H * W
+    st = _stream(x)
+    a, g = (act if act is not None else (0.0, 1.0))
+    y = torch.empty((B, O, H, W), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        xh = torch.empty((B, H, W, C), device=x.device, dtype=torch.float32)
+        lib.call("spgan_nchw_to_nhwc", _ptr(xh), _ptr(x), B, C, H, W, st)
+        a_packed = torch.empty((2, rows, 9 * Cp), device=x.device, dtype=torch.bfloat16)
+        cc = _f32c(coords, "sphere_modconv") if coords is not None else None
+        im = _f32c(in_mul, "sphere_modconv") if in_mul is not None else None
+        lib.call("spgan_sphere_pack", _ptr(a_packed), _ptr(xh), _ptr(cc), _ptr(grid), _ptr(im), B, C, H, W, grid.shape[0],
+                 Cp, 1 if flat_concat else 0, st)
+        wp = _packed_weight(w, O, Ct, Ct * 9, 9, list(range(9)), Cp, True)
+        p = dict(My=H, Mx=W, in_stride=1, out_stride=1, off_y=0, off_x=0, taps=[(0, 0, 0)])
+        cp = _fill_pass(p, B, Ct, H, W, O, H, W, Ct * 9, 9, out_scale, 1 if act is not None else 0, a, g, precision)
+        om = _f32c(out_mul, "sphere_modconv") if out_mul is not None else None
+        lib.call("spgan_conv_gemm", ctypes.byref(cp), _ptr(y), _ptr(a_packed), rows, 9 * Cp, _ptr(wp), _ptr(om),
+                 _ptr(None), _ptr(None), _ptr(bias), _ptr(residual), st)
+    return y
+
+
+def sphere_concat_gather(x, coords, grid):
+    """The reference's gathered + concatenated conv input, (1, B*C + B*nc, 3H, 3W) flat (models/spgan_ops_gs.py:791-813),
+    coordinate channels encoded.  No autograd."""
+    B, C, H, W = x.shape
+    nc = 0 if coords is None else coords.shape[1]
+    flat = torch.empty((1, B * (C + nc), 3 * H, 3 * W), device=x.device, dtype=torch.float32)
+    sphere_gather_raw(x, grid, out=flat, out_bstride=C, out_coff=0)
+    if nc:
+        sphere_gather_raw(coords, grid, out=flat, out_bstride=nc, out_coff=B * C, encode=True)
+    return flat
+
+
+_SPHERE_GEOM = ConvGeom(3, 3, stride=3, pad=0)
+
+
+def _sphere_modconv_simt(x, coords, grid, w, in_mul, out_mul, out_scale, act, flat_concat, residual, bias):
+    B, C, H, W = x.shape
+    Ct = w.shape[1]
+    if flat_concat:
+        inp = sphere_concat_gather(x, coords, grid).view(B, Ct, 3 * H, 3 * W)
+    else:
+        gx = sphere_gather_raw(x, grid)
+        inp = gx if coords is None else torch.cat([gx, sphere_gather_raw(coords, grid, encode=True)], 1)
+    return conv_apply(inp, w, _SPHERE_GEOM, False, None, in_mul, out_mul, out_scale, None, None, bias, act, residual, 0)
+
+
+def encode_coords(c):
+    """tanh / cos(pi.) / sin(pi.) on channels 0/1/2 (models/spgan_ops_gs.py:799-802); differentiable torch glue used
+    only on the 3-channel coordinate planes of the training path."""
+    return torch.stack([torch.tanh(c[:, 0]), torch.cos(c[:, 1] * math.pi), torch.sin(c[:, 2] * math.pi)], 1)
+
+
+def sphere_modconv(x, coords, grid, w, in_mul, out_mul, out_scale, flat_concat=True):
+    """Differentiable spherical modulated conv: gather (surrogate backward) -> flat concat -> stride-3 conv."""
+    needs = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (x, w, in_mul, out_mul))
+    if not needs:
+        return sphere_modconv_fused(x, coords, grid, w, in_mul, out_mul, out_scale, None, flat_concat)
+    B, C, H, W = x.shape
+    Ct = w.shape[1]
+    gx = sphere_gather(x, grid)
+    if coords is not None:
+        gc = encode_coords(sphere_gather(coords, grid))
+        if flat_concat:
+            inp = torch.cat([gx.reshape(1, B * C, 3 * H, 3 * W), gc.reshape(1, B * coords.shape[1], 3 * H, 3 * W)], 1)
+            inp = inp.view(B, Ct, 3 * H, 3 * W)
+        else:
+            inp = torch.cat([gx, gc], 1)
+    else:
+        inp = gx
+    return _ConvFn.apply(inp, w, in_mul, out_mul, _SPHERE_GEOM, False, None, out_scale)

@@ -1,0 +1,260 @@
+"""Generator composition over the mirrored op modules, with the reference's parameter names.
+
+The reference's `models/spgan/spgan.py` is a *caller* of the hot path: it only wires op modules.
+bench.py and the parity tests cannot import it on the GPU box (the reference tree is not there, and it needs
+easydict / CUDA-at-import), so this file wires the same graph for `configs/model/spgan.yaml`
+(patch 101, ts_input 11, 4 structure blocks, coords on every layer) out of `spgan_b200.models.*`.
+State-dict keys equal the reference's `InfinityGanGenerator` keys, so checkpoints load either way.
+"""
+import random
+from types import SimpleNamespace
+
+import torch
+from torch import nn
+
+from . import functional as SF
+from .models import ops
+from .models import spgan_ops as sp_ops
+from .models import spgan_ops_gs as sp_ops_gs
+from .models.spherenet import SphereConvBatchDiffFixBorderGNoGrad
+
+
+def default_config():
+    """The fields of configs/model/spgan.yaml that the hot path reads."""
+    tp = SimpleNamespace(
+        patch_size=101, full_size=197, training_modality="patch", batch_size=16, partial=0.6667,
+        global_latent_dim=512, local_latent_dim=256, n_mlp=8, channel_multiplier=2, mixing=0.9,
+        use_ss=True, ss_n_layers=4, ss_unfold_radius=3, ss_coord_all_layers="each_layer", ss_disable_noise=True,
+        ts_input_size=11, ts_no_zero_pad=True, coord_num_dir=3, coord_vert_cut_pt=3, coord_vert_sample_size=10,
+        coord_hori_occupy_ratio=0.25, r1=10, path_regularize=2, path_batch_shrink=2, d_reg_every=16, g_reg_every=4,
+        lr=0.002, coord_use_ac=True, coord_ac_w=1, coord_ac_vert_only=True, diversity_z_w=1, diversity_angular=True)
+    return SimpleNamespace(train_params=tp, var=SimpleNamespace(dataparallel=False))
+
+
+def encode_coords(c):
+    """convert_idx_to_input_coords_ori (coord_handler.py:696-711) for coord_num_dir == 3."""
+    return SF.encode_coords(c)
+
+
+def center_crop(src, h, w):
+    ph, pw = (src.shape[2] - h) // 2, (src.shape[3] - w) // 2
+    if ph == 0 and pw == 0:
+        return src
+    return src[:, :, ph:ph + h, pw:pw + w]
+
+
+class ShortcutConv(nn.Conv2d):
+    """`self.sc = nn.Conv2d(256, 256, 1)` of SphereConditionalBlock (models/spgan/spgan.py:141), run through the conv
+    kernels of this package; same parameter names (`weight`, `bias`) and default init as nn.Conv2d."""
+
+    _GEOM = SF.ConvGeom(1, 1)
+
+    def forward(self, x, residual=None):
+        if ops._grad_needed(x, self.weight, self.bias):
+            y = SF.conv2d(x, self.weight, self._GEOM) + self.bias.view(1, -1, 1, 1)
+            return y if residual is None else y + residual
+        return SF.conv_apply(x, self.weight, self._GEOM, bias=self.bias, residual=residual)
+
+
+class SphereConditionalBlock(nn.Module):
+    """models/spgan/spgan.py:122-169: spherical StyledConv (LeakyReLU 0.01, no noise) + 1x1 shortcut."""
+
+    def __init__(self, idx, config):
+        super().__init__()
+        tp = config.train_params
+        self.config = config
+        self.deal_coords = tp.ss_coord_all_layers == "each_layer"
+        in_channel = tp.local_latent_dim
+        if tp.ss_coord_all_layers or idx == 0:
+            in_channel += tp.coord_num_dir
+        self.sc = ShortcutConv(tp.local_latent_dim, tp.local_latent_dim, kernel_size=1)
+        self.conv = sp_ops_gs.StyledConv(in_channel=in_channel, out_channel=tp.local_latent_dim, kernel_size=3,
+                                         disable_noise=True, style_dim=tp.global_latent_dim, no_zero_pad=True,
+                                         config=config, activation="LeakyReLU_n", side="ss",
+                                         deal_coords=self.deal_coords)
+
+    def forward(self, x, cond, coords, coords_partial, noise=None, test_ids=None, calc_flops=False):
+        if not self.deal_coords and self.config.train_params.ss_coord_all_layers:
+            x = torch.cat([x, coords], 1)
+        out, flops = self.conv(x, cond, noise=noise, coords=coords, coords_partial=coords_partial, test_ids=test_ids,
+                               calc_flops=calc_flops)
+        return self.sc(x, residual=out), flops
+
+
+class ConditionalBlock(nn.Module):
+    """models/spgan/spgan.py:79-119: concat encoded coords, 7x7 StyledConv (no padding, fused leaky-ReLU)."""
+
+    def __init__(self, idx, config):
+        super().__init__()
+        tp = config.train_params
+        self.config = config
+        in_channel = tp.local_latent_dim
+        if tp.ss_coord_all_layers or idx == 0:
+            in_channel += tp.coord_num_dir
+        self.conv = ops.StyledConv(in_channel=in_channel, out_channel=tp.local_latent_dim,
+                                   kernel_size=tp.ss_unfold_radius * 2 + 1, style_dim=tp.global_latent_dim,
+                                   no_zero_pad=True, disable_noise=tp.ss_disable_noise, config=config, side="ss")
+
+    def forward(self, x, cond, coords, coords_partial, noise=None, test_ids=None, calc_flops=False):
+        if self.config.train_params.ss_coord_all_layers:
+            x = torch.cat([x, encode_coords(coords)], 1)
+        return self.conv(x, cond, noise=noise, coords=coords, test_ids=test_ids, calc_flops=calc_flops)
+
+
+class ImplicitFunction(nn.Module):
+    """models/spgan/spgan.py:172-254."""
+
+    def __init__(self, config):
+        super().__init__()
+        convs = []
+        for i in range(config.train_params.ss_n_layers):
+            convs.append(SphereConditionalBlock(idx=i, config=config))
+            convs.append(ConditionalBlock(idx=i, config=config))
+        self.conv_stack = nn.Sequential(*convs)
+        self.global_mapping = None  # spgan.yaml has no ss_mapping
+
+    def forward(self, global_latent, local_latent, coords, coords_partial, noises=None, test_ids=None, calc_flops=False):
+        h = local_latent
+        flops = 0
+        for conv in self.conv_stack:
+            coords = center_crop(coords, h.shape[2], h.shape[3])  # coords_partial is NOT re-cut (:199-206)
+            h, cur = conv(h, global_latent, coords, coords_partial, noise=noises, test_ids=test_ids, calc_flops=calc_flops)
+            flops += cur
+        return h, flops
+
+
+class StructureSynthesizer(nn.Module):
+    """models/spgan/spgan.py:257-389, for inputs whose coords / coords_partial are supplied by the caller (the test
+    managers' `override_coords` path, or the synthetic training sampler of bench.py)."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.implicit_model = ImplicitFunction(config)
+
+    def calc_out_spatial_size(self, in_spatial_size, return_list=False):
+        tp = self.config.train_params
+        return in_spatial_size - tp.ss_n_layers * tp.ss_unfold_radius * 2
+
+    def forward(self, global_latent, local_latent, coords, coords_partial, noises=None, test_ids=None, calc_flops=False):
+        return self.implicit_model(global_latent, local_latent, coords=coords, coords_partial=coords_partial,
+                                   noises=noises, test_ids=test_ids, calc_flops=calc_flops)
+
+
+class TextureSynthesizer(nn.Module):
+    """models/spgan/spgan.py:392-978 for patch_size 101 / ts_input_size 11."""
+
+    CONVS = [(512, True), (512, False), (512, True), (512, False), (512, True), (512, False), (None, True), (None, False)]
+    TO_RGBS = [(1, 3), (3, 5), (5, 7), (7, 8)]
+    I2J = {3: 0, 5: 1, 7: 2}
+
+    def __init__(self, config):
+        super().__init__()
+        tp = config.train_params
+        if tp.patch_size != 101 or tp.ts_input_size != 11:
+            raise NotImplementedError("only patch_size 101 / ts_input_size 11 (configs/model/spgan.yaml) is wired")
+        self.config = config
+        self.global_latent_dim = tp.global_latent_dim
+        self.local_latent_dim = tp.local_latent_dim
+        blur_kernel = [1, 2, 1]
+        layers = [ops.PixelNorm()]
+        for _ in range(tp.n_mlp):
+            layers.append(ops.EqualLinear(self.global_latent_dim, self.global_latent_dim, lr_mul=0.01,
+                                          activation='fused_lrelu'))
+        self.mapping = nn.Sequential(*layers)
+        self.const_z = ops.ConstantInput(self.local_latent_dim)
+        self.convs = nn.ModuleList()
+        self.to_rgbs = nn.ModuleList()
+        self.sp_convs = nn.ModuleList()
+        self.noises = nn.Module()
+        self.num_layers = len(self.CONVS)
+        self.n_latent = self.num_layers + 1
+        for layer_idx in range(self.num_layers):
+            res = (layer_idx + 5) // 2
+            self.noises.register_buffer(f'noise_{layer_idx}', torch.randn(1, 1, 2 ** res, 2 ** res))
+        in_ch = self.local_latent_dim
+        specs = [(c if c is not None else 256 * tp.channel_multiplier, up) for c, up in self.CONVS]
+        for i, (out_ch, up) in enumerate(specs):
+            self.convs.append(ops.StyledConv(in_ch, out_ch, 3, self.global_latent_dim, upsample=up,
+                                             blur_kernel=blur_kernel, no_zero_pad=tp.ts_no_zero_pad, config=config,
+                                             side="ts"))
+            if i in self.I2J:
+                self.sp_convs.append(SphereConvBatchDiffFixBorderGNoGrad(3, 3))
+            in_ch = out_ch
+        for src, _ in self.TO_RGBS:
+            self.to_rgbs.append(sp_ops.ToRGB(specs[src][0], self.global_latent_dim, upsample=True,
+                                             no_zero_pad=tp.ts_no_zero_pad, blur_kernel=blur_kernel, config=config,
+                                             side="ts"))
+
+    def calc_in_spatial_size(self, out_spatial_size, return_list=False):
+        sizes = []
+        for conv in self.convs[::-1]:
+            out_spatial_size = conv.calc_in_spatial_size(out_spatial_size)
+            sizes.append(out_spatial_size)
+        return sizes[::-1] if return_list else sizes[-1]
+
+    def calc_out_spatial_size(self, in_spatial_size, return_list=False):
+        sizes = []
+        for conv in self.convs:
+            in_spatial_size = conv.calc_out_spatial_size(in_spatial_size)
+            sizes.append(in_spatial_size)
+        return sizes if return_list else sizes[-1]
+
+    def get_style(self, global_latent):
+        return self.mapping(global_latent)
+
+    def styles_for(self, global_latent, inject_index=None):
+        """global_latent (B, 2, 512) -> (B, n_latent, 512) w-space styles with style mixing at `inject_index`
+        (models/spgan/spgan.py:843-876)."""
+        w0 = self.mapping(global_latent[:, 0])
+        if inject_index is None or inject_index >= self.n_latent:
+            return w0.unsqueeze(1).repeat(1, self.n_latent, 1)
+        w1 = self.mapping(global_latent[:, 1])
+        return torch.cat([w0.unsqueeze(1).repeat(1, inject_index, 1),
+                          w1.unsqueeze(1).repeat(1, self.n_latent - inject_index, 1)], 1)
+
+    def forward(self, styles, structure_latent, coords_partial, noises=None, test_ids=None, calc_flops=False):
+        """Synthesis loop (models/spgan/spgan.py:924-978).  styles (B, 9, 512); noises: list of 8 (B, 1, h, w) or None."""
+        h = structure_latent
+        skip = None
+        flops = 0
+        rgb_idx = 0
+        for i, conv in enumerate(self.convs):
+            nz = noises[i] if noises is not None else None
+            h, cur = conv(h, styles[:, i], noise=nz, test_ids=test_ids, calc_flops=calc_flops)
+            flops += cur
+            if rgb_idx < len(self.TO_RGBS) and i == self.TO_RGBS[rgb_idx][0]:
+                if i in self.I2J:
+                    skip = self.sp_convs[self.I2J[i]](skip, coords_partial)
+                skip, cur = self.to_rgbs[rgb_idx](h, styles[:, self.TO_RGBS[rgb_idx][1]], skip=skip, calc_flops=calc_flops)
+                flops += cur
+                rgb_idx += 1
+        return skip, flops
+
+
+class Generator(nn.Module):
+    """InfinityGanGenerator (models/spgan/spgan.py:1180-1420) restricted to the generation / training data flow:
+    forward(global_latent (B,2,512), local_latent (B,256,35,35), coords (B,3,35,35) raw meta coords,
+    coords_partial (dict for test mode, list of B dicts for training), noises, inject_index) -> image (B,3,101,101)."""
+
+    def __init__(self, config=None):
+        super().__init__()
+        self.config = config if config is not None else default_config()
+        self.structure_synthesizer = StructureSynthesizer(self.config)
+        self.texture_synthesizer = TextureSynthesizer(self.config)
+
+    def forward(self, global_latent, local_latent, coords, coords_partial, noises=None, inject_index=None,
+                test_ids=None, return_latents=False):
+        if global_latent.dim() == 2:
+            global_latent = torch.stack([global_latent, global_latent], 1)
+        ts = self.texture_synthesizer
+        if inject_index is None and self.training and self.config.train_params.mixing > 0:
+            if random.random() < self.config.train_params.mixing:  # models/spgan/spgan.py:865-869
+                inject_index = random.randint(1, ts.n_latent - 1)
+        structure, _ = self.structure_synthesizer(global_latent[:, 0], local_latent, coords, coords_partial,
+                                                  test_ids=test_ids)
+        styles = ts.styles_for(global_latent, inject_index)
+        img, _ = ts(styles, structure, coords_partial, noises=noises, test_ids=test_ids)
+        if return_latents:
+            return img, styles, structure
+        return img

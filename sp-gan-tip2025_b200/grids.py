@@ -1,0 +1,162 @@
+"""Host-side spherical sampling tables.
+
+The reference rebuilds every (1, 3H, 3W, 2) tap grid in numpy float64, per sample, per layer, on every forward
+(models/spgan_ops_gs.py:767-781 -> models/spherenet/grid_generator.py:137-283; its `lru_cache` never hits because
+the generator object is new each time).  Bit-exact sampling indices are decided by the last ulp of that float64
+arithmetic, so the tables stay on the host, in numpy, with the reference's own operation order —
+but vectorised over rows, computed once per distinct (size, coords_partial) and kept resident on the device.
+"""
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+_KEYS = ("p_x_st", "p_x_ed", "p_y_st", "p_y_ed", "circular_flag", "x_total", "y_total", "test_flag", "partial")
+
+
+def _norm(v):
+    """min_max_norm (grid_generator.py:349-352) with start = -1."""
+    return (v - np.min(v)) / (np.max(v) - np.min(v)) * 2 + (-1)
+
+
+def angular_ranges(h, w, cp):
+    """Centre latitudes / longitudes of the patch rows / columns: grid_generator.py:164-241, plain branch
+    (`full_shape` / `pre_sample_mode` are never set by spgan.yaml or the close-loop manager)."""
+    if cp.get("full_shape", None) is not None or cp.get("pre_sample_mode", False):
+        raise NotImplementedError("coords_partial['full_shape'/'pre_sample_mode'] is not used by spgan.yaml and is not supported")
+    partial = 0.8  # training hard-codes 0.8 (grid_generator.py:164-167)
+    if cp.get("test_flag", False):
+        partial = cp.get("partial", partial)
+    x_st = cp["p_x_st"] * np.pi * partial
+    x_ed = cp["p_x_ed"] * np.pi * partial
+    y_st = cp["p_y_st"] * np.pi * 2
+    y_ed = cp["p_y_ed"] * np.pi * 2
+    if y_ed != 2 * np.pi:
+        y_ed = y_ed % (np.pi * 2)
+    lat = np.linspace(x_st, x_ed, h) - (np.pi / 2 * partial)
+    if cp["circular_flag"]:
+        y_ed = y_ed + 2 * np.pi
+    lon = np.linspace(y_st, y_ed, w) - np.pi
+    return lat, lon
+
+
+def sampling_pattern(h, w, cp):
+    """float64 (lat, lon) tap positions in grid units: lat (h, 3, 3) shared by every column, lon (h, w, 3, 3).
+    createSamplingPattern of GridGeneratorPatchCoordsFixBorder (grid_generator.py:137-283), stride 1, 3x3."""
+    x_total, y_total = cp["x_total"], cp["y_total"]
+    # createKernel (grid_generator.py:303-323)
+    d_lat = np.pi / x_total
+    d_lon = 2 * np.pi / y_total
+    r = np.arange(-1, 2)
+    ker_x, ker_y = np.meshgrid(np.tan(r * d_lon), np.tan(r * d_lat) / np.cos(r * d_lon))
+    rho = np.sqrt(ker_x ** 2 + ker_y ** 2)
+    rho[1][1] = 1e-8
+    nu = np.arctan(rho)
+    cos_nu, sin_nu = np.cos(nu), np.sin(nu)
+    lat_c, lon_c = angular_ranges(h, w, cp)
+    t = lat_c[:, None, None]  # rows broadcast against the 3x3 kernel: same elementwise sequence as the row loop (:249-262)
+    lat = np.arcsin(cos_nu * np.sin(t) + ker_y * sin_nu * np.cos(t) / rho)
+    lon = np.arctan(ker_x * sin_nu / (rho * np.cos(t) * cos_nu - ker_y * np.sin(t) * sin_nu))
+    lat_off = lat - lat[:, 1:2, 1:2]                            # get_pattern (:325-335)
+    lat_rows = _norm(lat_c)[:, None, None] + lat_off            # add_pattern_to_lat (:337-346)
+    lon_cols = lon[:, None, :, :] + _norm(lon_c)[None, :, None, None]  # (h, w, 3, 3)
+    lat_g = (lat_rows / 2 + 0.5) * x_total
+    lon_g = (lon_cols / 2 + 0.5) * y_total
+    return lat_g, lon_g
+
+
+def sampling_pattern_dense(h, w, cp):
+    """The reference's return layout: (1, 3h, 3w, 2) float64, last dim (lat, lon)."""
+    lat_g, lon_g = sampling_pattern(h, w, cp)
+    out = np.empty((h, 3, w, 3, 2), dtype=np.float64)
+    out[..., 0] = lat_g[:, :, None, :]
+    out[..., 1] = lon_g.transpose(0, 2, 1, 3)
+    return out.reshape(1, 3 * h, 3 * w, 2)
+
+
+def sampling_grid(h, w, cp):
+    """(1, 3h, 3w, 2) float32 grid in F.grid_sample convention (x = lon, y = lat), equal bit for bit to
+    ModulatedConv2d.genSamplingPattern (models/spgan_ops_gs.py:410-428) /
+    SphereConvBatchDiffFixBorderGNoGrad.genSamplingPattern (models/spherenet/sphere_conv2d.py:147-165)."""
+    lat_g, lon_g = sampling_pattern(h, w, cp)
+    lat_n = ((lat_g / cp["x_total"]) * 2 - 1).astype(np.float32)
+    lon_n = ((lon_g / cp["y_total"]) * 2 - 1).astype(np.float32)
+    out = np.empty((h, 3, w, 3, 2), dtype=np.float32)
+    out[..., 0] = lon_n.transpose(0, 2, 1, 3)
+    out[..., 1] = lat_n[:, :, None, :]
+    return out.reshape(1, 3 * h, 3 * w, 2)
+
+
+def full_sphere_pattern(height, width, kernel_size=(3, 3), stride=(1, 1)):
+    """SphereNet's original full-panorama pattern, GridGenerator.createSamplingPattern (grid_generator.py:28-84):
+    (1, H*Kh, W*Kw, 2) float64 (lat, lon) pixel positions, longitude wrapped modulo the width."""
+    kh, kw = kernel_size
+    d_lat = np.pi / height
+    d_lon = 2 * np.pi / width
+    rx = np.arange(-(kw // 2), kw // 2 + 1)
+    if not kw % 2:
+        rx = np.delete(rx, kw // 2)
+    ry = np.arange(-(kh // 2), kh // 2 + 1)
+    if not kh % 2:
+        ry = np.delete(ry, kh // 2)
+    ker_x, ker_y = np.meshgrid(np.tan(rx * d_lon), np.tan(ry * d_lat) / np.cos(ry * d_lon))
+    rho = np.sqrt(ker_x ** 2 + ker_y ** 2)
+    if kh % 2 and kw % 2:
+        rho[kh // 2][kw // 2] = 1e-8
+    nu = np.arctan(rho)
+    cos_nu, sin_nu = np.cos(nu), np.sin(nu)
+    lat_c = ((np.arange(0, height, stride[0]) / height) - 0.5) * np.pi
+    lon_c = ((np.arange(0, width, stride[1]) / width) - 0.5) * (2 * np.pi)
+    t = lat_c[:, None, None]
+    lat = np.arcsin(cos_nu * np.sin(t) + ker_y * sin_nu * np.cos(t) / rho)
+    lon = np.arctan(ker_x * sin_nu / (rho * np.cos(t) * cos_nu - ker_y * np.sin(t) * sin_nu))
+    lon = lon[:, None, :, :] + lon_c[None, :, None, None]
+    lat = (lat / np.pi + 0.5) * height
+    lon = ((lon / (2 * np.pi) + 0.5) * width) % width
+    H, W = len(lat_c), len(lon_c)
+    out = np.empty((H, kh, W, kw, 2), dtype=np.float64)
+    out[..., 0] = lat[:, :, None, :]
+    out[..., 1] = lon.transpose(0, 2, 1, 3)
+    return out.reshape(1, H * kh, W * kw, 2)
+
+
+class GridCache:
+    """Device-resident sampling grids keyed by (size, coords_partial); an LRU bounded in entries."""
+
+    def __init__(self, max_entries=8192):
+        self.max_entries = max_entries
+        self._store = OrderedDict()
+        self.hits = 0
+        self.misses = 0
+
+    @staticmethod
+    def _key(h, w, cp, device):
+        return (h, w, str(device)) + tuple((k, cp.get(k, None)) for k in _KEYS)
+
+    def get(self, h, w, cp, device):
+        key = self._key(h, w, cp, device)
+        g = self._store.get(key)
+        if g is not None:
+            self._store.move_to_end(key)
+            self.hits += 1
+            return g
+        self.misses += 1
+        g = torch.from_numpy(sampling_grid(h, w, cp)).to(device)
+        self._store[key] = g
+        if len(self._store) > self.max_entries:
+            self._store.popitem(last=False)
+        return g
+
+    def batch(self, h, w, coords_partial, batch, device):
+        """Training: a list of per-sample dicts -> (B, 3h, 3w, 2); test: one dict -> (1, 3h, 3w, 2) shared by the
+        batch (models/spgan_ops_gs.py:760-789)."""
+        if isinstance(coords_partial, (list, tuple)):
+            if len(coords_partial) != batch:
+                raise RuntimeError("coords_partial has %d entries for a batch of %d" % (len(coords_partial), batch))
+            if batch == 1:
+                return self.get(h, w, coords_partial[0], device)
+            return torch.cat([self.get(h, w, cp, device) for cp in coords_partial], 0)
+        return self.get(h, w, coords_partial, device)
+
+
+GRID_CACHE = GridCache()

@@ -1,0 +1,111 @@
+"""ctypes binding of libspgan_b200.so (the C ABI declared in include/spgan_b200.h).
+
+The library is built in-tree by `csrc/build.py` (nvcc, sm_100a).  Nothing here falls back to PyTorch: if the
+library is missing, or a call returns non-zero, a RuntimeError is raised — the same failure mode as the
+reference's `TORCH_CHECK`s in models/custom_ops/fused_bias_act_kernel.cu:52-99.
+"""
+import ctypes
+import os
+import threading
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "libspgan_b200.so")
+MAX_TAPS = 49
+
+c_int, c_i64, c_f32, c_vp = ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
+
+
+class ConvPass(ctypes.Structure):
+    """Mirror of `SpganConvPass` (include/spgan_b200.h)."""
+    _fields_ = [
+        ("B", ctypes.c_int32), ("Cin", ctypes.c_int32), ("H", ctypes.c_int32), ("W", ctypes.c_int32),
+        ("Cout", ctypes.c_int32), ("out_H", ctypes.c_int32), ("out_W", ctypes.c_int32),
+        ("My", ctypes.c_int32), ("Mx", ctypes.c_int32),
+        ("in_stride", ctypes.c_int32),
+        ("out_stride", ctypes.c_int32), ("out_off_y", ctypes.c_int32), ("out_off_x", ctypes.c_int32),
+        ("ntaps", ctypes.c_int32),
+        ("tap_dy", ctypes.c_int32 * MAX_TAPS), ("tap_dx", ctypes.c_int32 * MAX_TAPS), ("tap_w", ctypes.c_int32 * MAX_TAPS),
+        ("ws_o", ctypes.c_int64), ("ws_c", ctypes.c_int64),
+        ("out_scale", ctypes.c_float),
+        ("act", ctypes.c_int32),
+        ("act_alpha", ctypes.c_float), ("act_gain", ctypes.c_float),
+        ("precision", ctypes.c_int32),
+    ]
+
+
+_PASS_P = ctypes.POINTER(ConvPass)
+
+# name -> (restype, argtypes).  tests/test_abi.py checks this table against the header, symbol by symbol.
+SIGNATURES = {
+    "spgan_abi_version": (c_int, []),
+    "spgan_last_error": (ctypes.c_char_p, []),
+    "spgan_device_ok": (c_int, []),
+    "spgan_bias_act": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_f32, c_f32, c_vp]),
+    "spgan_bias_act_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_f32, c_f32, c_vp]),
+    "spgan_noise_bias_act": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_f32, c_f32, c_vp]),
+    "spgan_upfirdn2d": (c_int, [c_vp, c_vp, c_vp, c_i64] + [c_int] * 12 + [c_vp]),
+    "spgan_sphere_gather": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_i64, c_i64, c_int, c_vp]),
+    "spgan_sphere_gather_indices": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_vp]),
+    "spgan_sphere_gather_bwd": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_vp]),
+    "spgan_linear": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_f32, c_f32, c_int, c_f32, c_f32, c_vp]),
+    "spgan_conv_pass": (c_int, [_PASS_P] + [c_vp] * 10),
+    "spgan_demod": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_f32, c_f32, c_vp]),
+    "spgan_conv_wgrad": (c_int, [_PASS_P, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp]),
+    "spgan_plane_dot": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp]),
+    "spgan_pack_act": (c_int, [c_vp, c_vp, c_vp] + [c_int] * 9 + [c_vp]),
+    "spgan_pack_weight": (c_int, [c_vp, c_vp, c_int, c_int, c_i64, c_i64, c_int, ctypes.POINTER(ctypes.c_int32), c_int, c_int, c_vp]),
+    "spgan_nchw_to_nhwc": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp]),
+    "spgan_sphere_pack": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
+    "spgan_conv_gemm": (c_int, [_PASS_P, c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "spgan_gemm_launch_count": (c_i64, []),
+}
+
+_lib = None
+_lock = threading.Lock()
+_launches = 0  # kernel launches issued through this binding (bench.py reports it as `gpu_launches`)
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built: there is no fallback path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "libspgan_b200.so is missing (%s). Build it with `python __graft_entry__.py build` or "
+                "`python sp-gan-tip2025_b200/csrc/build.py`; this package has no CPU/PyTorch fallback." % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError here = header/library mismatch
+            fn.restype = res
+            fn.argtypes = args
+        if lib.spgan_abi_version() != 1:
+            raise RuntimeError("libspgan_b200.so ABI version %d, expected 1" % lib.spgan_abi_version())
+        _lib = lib
+    return _lib
+
+
+def last_error():
+    return load().spgan_last_error().decode("utf-8", "replace")
+
+
+def call(name, *args):
+    """Invoke an int-returning entry point; non-zero -> RuntimeError carrying spgan_last_error()."""
+    global _launches
+    rc = getattr(load(), name)(*args)
+    if rc != 0:
+        raise RuntimeError("%s failed (code %d): %s" % (name, rc, last_error()))
+    _launches += 1
+
+
+def launches():
+    return _launches
+
+
+def require_device():
+    """Fail loudly unless the current CUDA device is a B200-class (sm_100) GPU."""
+    if load().spgan_device_ok() != 1:
+        raise RuntimeError("spgan_b200 needs an sm_100a GPU: " + last_error())

@@ -1,0 +1,157 @@
+"""Close-loop panorama generation: the patch lattice, per-patch inputs and on-device assembly.
+
+Restates the data flow of the reference's close-loop test manager
+(test_managers/base_test_manager.py:86-121, 219-325; test_managers/close_loop_infinite_generation.py:84-305, 428-472)
+with everything resident on the GPU: the latent / coordinate / noise canvases are sliced on the device, the generator
+runs one batch of patches per lattice position, and the patch is written into the meta image on the device (the
+reference copies every patch to the CPU, base_test_manager.py:282-290).  Patch positions are independent, so
+`positions=` lets several ranks shard the lattice; assembling in row-major order keeps the
+reference's "later patch overwrites the 5-pixel overlap" rule.
+"""
+import math
+
+import torch
+
+TS_UPSAMPLE = [True, False, True, False, True, False, True, False]
+TEST_META_EXTRA_PAD = 3  # test_managers/global_config.py:1
+
+
+def _ts_out_sizes(n):
+    out = []
+    for up in TS_UPSAMPLE:
+        n = n * 2 - 3 if up else n - 2
+        out.append(n)
+    return out
+
+
+def _ts_in_sizes(n):
+    out = []
+    for up in TS_UPSAMPLE[::-1]:
+        if up:
+            v = n + 3
+            n = (v if v % 2 == 0 else v + 1) // 2
+        else:
+            n = n + 2
+        out.append(n)
+    return out[::-1]
+
+
+def plan(target_h, target_w, ts_input=11, ss_unfold=12, patch=101):
+    """Lattice geometry (base_test_manager.py:86-121; close_loop_infinite_generation.py:428-460, 46-48)."""
+    out1, out2 = _ts_out_sizes(ts_input), _ts_out_sizes(ts_input * 2)
+    in1, in2 = _ts_in_sizes(out1[-1]), _ts_in_sizes(out2[-1])
+    unit = (out2[-1] - out1[-1]) // ts_input
+    pix_step = (out1[-1] // unit) * unit
+    lat_step = pix_step // unit
+    infeat_step = [lat_step * ((b - a) // ts_input) for a, b in zip(in1, in2)]
+    outfeat_step = [lat_step * ((b - a) // ts_input) for a, b in zip(out1, out2)]
+    steps_h = math.ceil((target_h - out1[-1]) / pix_step) + TEST_META_EXTRA_PAD
+    if target_w % pix_step != 0:
+        raise ValueError("close-loop width %d must be a multiple of the pixel step %d" % (target_w, pix_step))
+    steps_w_min = math.ceil(target_w / pix_step)
+    meta_h = pix_step * (steps_h - 1) + out1[-1]
+    meta_w = steps_w_min * pix_step
+    return dict(pix_step=pix_step, lat_step=lat_step, outfeat_step=outfeat_step, out_sizes=out1, steps_h=steps_h,
+                steps_w=steps_w_min + 2, steps_w_min=steps_w_min, meta_h=meta_h, meta_w=meta_w,
+                noise_h=[s * (steps_h - 1) + o for s, o in zip(outfeat_step, out1)],
+                noise_w=[s * steps_w_min for s in outfeat_step],
+                lat_h=_ts_in_sizes(meta_h)[0] + 2 * ss_unfold, lat_w=meta_w // infeat_step[-1] * 6,
+                ts_input=ts_input, ss_unfold=ss_unfold, patch=patch, target_h=target_h, target_w=target_w)
+
+
+def positions(pl):
+    """Row-major lattice positions, as generate() visits them (close_loop_infinite_generation.py:185)."""
+    return [(a, b) for a in range(pl["steps_h"]) for b in range(pl["steps_w"])]
+
+
+def meta_coords(height, width, device, cut_pt=3.0, const_x=45, const_y=140):
+    """Test-time coordinate canvas (coord_handler.py:575-607, 620-627): channels (x, y, y)."""
+    x = torch.arange(height, dtype=torch.float32) / (const_x - 1)
+    y = torch.arange(width, dtype=torch.float32) / (const_y - 1)
+    x = x - (x[-1] - 1) / 2
+    x = (x * 2 - 1) * cut_pt
+    y = y * 2 - 1
+    xt = x.view(-1, 1).repeat(1, width)
+    yt = y.view(1, -1).repeat(height, 1)
+    return torch.stack([xt, yt, yt], 0).to(device)
+
+
+def patch_inputs(pl, ix, iy, iiter, lat_h, lat_w, partial=0.6667):
+    """coords_partial dict and canvas cursors of one lattice position (close_loop_infinite_generation.py:204-261,
+    462-472)."""
+    ss = pl["ss_unfold"]
+    zx_st = ix * pl["lat_step"]
+    zy_st = iy * pl["lat_step"]
+    zx_ed = zx_st + pl["ts_input"] + 2 * ss
+    zy_ed = zy_st + pl["ts_input"] + 2 * ss
+    x_size, y_size = zx_ed - zx_st + 1, zy_ed - zy_st + 1
+    if zy_ed > lat_w:
+        circ, zy = (True, zy_st) if zy_st < lat_w else (False, zy_st % lat_w)
+    else:
+        circ, zy = False, zy_st
+    cp = {"p_x_st": zx_st / lat_h, "p_x_ed": (zx_st + x_size) / lat_h, "p_y_st": zy / lat_w,
+          "p_y_ed": (zy + y_size) / lat_w, "circular_flag": circ, "x_total": lat_h, "y_total": lat_w,
+          "test_flag": True, "start_flag": iiter == 0, "h_step": zx_st // 6, "w_step": zy // 6, "y_st": zy,
+          "y_ed": zy_ed, "partial": partial}
+    return cp, (zx_st, zx_ed, zy_st, zy_ed)
+
+
+def circular_slice(t, width, x_st, x_ed, y_st, y_ed):
+    """circular_sample_width (close_loop_infinite_generation.py:307-331)."""
+    while y_ed > 2 * width:
+        y_st, y_ed = y_st - width, y_ed - width
+    if y_ed <= width:
+        return t[:, :, x_st:x_ed, y_st:y_ed]
+    if y_st < width:
+        return torch.cat((t[:, :, x_st:x_ed, y_st:], t[:, :, x_st:x_ed, :y_ed % width]), dim=3)
+    return t[:, :, x_st:x_ed, y_st % width:y_ed % width]
+
+
+def circular_assign(t, width, x_st, x_ed, y_st, y_ed, v):
+    """_circular_assign_value_width (base_test_manager.py:305-325)."""
+    while y_ed > 2 * width:
+        y_st, y_ed = y_st - width, y_ed - width
+    if y_ed <= width:
+        t[:, :, x_st:x_ed, y_st:y_ed] = v
+    elif y_st < width:
+        d = width - y_st
+        t[:, :, x_st:x_ed, y_st:] = v[:, :, :, :d]
+        t[:, :, x_st:x_ed, :y_ed % width] = v[:, :, :, d:]
+    else:
+        t[:, :, x_st:x_ed, y_st % width:y_ed % width] = v
+
+
+@torch.no_grad()
+def generate(gen, pl, global_latent, local_latent, noises, meta=None, only=None):
+    """Generate (a shard of) a batch of panoramas.  global_latent (B, 2, 512) or (B, 512); local_latent
+    (B, 256, lat_h, lat_w) circular canvas; noises: 8 canvases (B, 1, noise_h[l], noise_w[l]).
+    `only`: optional set of lattice positions to run (rank sharding); returns the (B, 3, meta_h, meta_w) meta image."""
+    B = local_latent.shape[0]
+    dev = local_latent.device
+    lat_h, lat_w = local_latent.shape[2], local_latent.shape[3]
+    if meta is None:
+        meta = torch.zeros(B, 3, pl["meta_h"], pl["meta_w"], device=dev)
+    coords_full = meta_coords(lat_h, lat_w, dev).unsqueeze(0).expand(B, -1, -1, -1)
+    P = pl["patch"]
+    for it, (ix, iy) in enumerate(positions(pl)):
+        if only is not None and (ix, iy) not in only:
+            continue
+        cp, (zx_st, zx_ed, zy_st, zy_ed) = patch_inputs(pl, ix, iy, it, lat_h, lat_w)
+        cur_lat = circular_slice(local_latent, lat_w, zx_st, zx_ed, zy_st, zy_ed).contiguous()
+        cur_coords = circular_slice(coords_full, lat_w, zx_st, zx_ed, zy_st, zy_ed).contiguous()
+        cur_noises = []
+        for l in range(8):
+            fx, fy = ix * pl["outfeat_step"][l], iy * pl["outfeat_step"][l]
+            s = pl["out_sizes"][l]
+            cur_noises.append(circular_slice(noises[l], pl["noise_w"][l], fx, fx + s, fy, fy + s).contiguous())
+        patch = gen(global_latent, cur_lat, cur_coords, cp, noises=cur_noises)
+        px, py = ix * pl["pix_step"], iy * pl["pix_step"]
+        circular_assign(meta, pl["meta_w"], px, px + P, py, py + P, patch)
+    return meta
+
+
+def crop_to_target(meta, pl):
+    """Centre crop of the meta image to the requested size (close_loop_infinite_generation.py:363-382)."""
+    ph = (meta.shape[2] - pl["target_h"]) // 2
+    pw = (meta.shape[3] - pl["target_w"]) // 2
+    return meta[:, :, ph:ph + pl["target_h"], pw:pw + pl["target_w"]]

@@ -1,0 +1,105 @@
+"""Shared case tables for the parity tests (must stay in step with oracle/make_golden.py, which wrote the fixtures)."""
+import json
+import os
+
+import numpy as np
+import torch
+
+import spgan_oracle as O
+import synth
+
+SEED = 9000
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+STYLE_DIM = 8
+
+UPFIRDN_CASES = [
+    ("g_blur3", (2, 3, 13, 13), [1, 2, 1], 4.0, 1, 1, (0, 0)),
+    ("d_blur4_main", (2, 3, 13, 13), [1, 3, 3, 1], 1.0, 1, 1, (2, 2)),
+    ("d_blur4_skip", (2, 3, 12, 12), [1, 3, 3, 1], 1.0, 1, 1, (1, 1)),
+    ("up2_4", (1, 2, 7, 9), [1, 3, 3, 1], 4.0, 2, 1, (2, 1)),
+    ("down2_4", (1, 2, 10, 8), [1, 3, 3, 1], 1.0, 1, 2, (1, 1)),
+    ("up2_3", (1, 2, 6, 5), [1, 2, 1], 4.0, 2, 1, (1, 1)),
+    ("negpad", (1, 2, 9, 9), [1, 2, 1], 1.0, 1, 1, (-1, 0)),
+]
+
+MODCONV_CASES = [
+    # name, cin, cout, k, demod, upsample, B, H
+    ("k3", 6, 5, 3, True, False, 2, 9),
+    ("k7", 7, 4, 7, True, False, 2, 11),
+    ("k1_nodemod", 8, 3, 1, False, False, 2, 6),
+    ("k3_up", 6, 5, 3, True, True, 2, 5),
+]
+
+
+def train_cp(x_st, y_st, size=35, gx=45, gy=140, circular=None):
+    if circular is None:
+        circular = y_st + size > gy
+    return {"p_x_st": x_st / gx, "p_x_ed": (x_st + size - 1) / gx, "p_y_st": y_st / gy,
+            "p_y_ed": (y_st + size - 1) / gy, "circular_flag": bool(circular), "x_total": gx, "y_total": gy,
+            "y_st": y_st, "y_ed": y_st + size, "partial": 0.6667}
+
+
+def test_cp(ix, iy, it):
+    plan = O.close_loop_plan(384, 768)
+    cp, _ = O.patch_coords_partial(plan, ix, iy, plan["lat_h"], plan["lat_w"], it)
+    return cp
+
+
+SPHERE_CASES = [
+    # name, B, C, cout, h, coords_partial
+    ("train_b2", 2, 4, 5, 17, [train_cp(7, 139, 17), train_cp(1, 20, 17)]),
+    ("test_b3", 3, 4, 5, 11, test_cp(2, 7, 27)),
+    ("train_b1", 1, 5, 4, 23, [train_cp(3, 60, 23)]),
+]
+
+
+def load(name):
+    return np.load(os.path.join(GOLDEN, name))
+
+
+def load_json(name):
+    with open(os.path.join(GOLDEN, name)) as f:
+        return json.load(f)
+
+
+def module_params(tag, shapes):
+    """Parameters as make_golden.fill_module wrote them: randn(seed, tag + name), modulation.bias shifted by 1."""
+    return {n: synth.randn_t(SEED, tag + n, s, 1.0, 1.0 if n.endswith("modulation.bias") else 0.0) for n, s in shapes.items()}
+
+
+def modconv_params(name, cin, cout, k):
+    return module_params("mc_" + name + "_", {"weight": (1, cout, cin, k, k), "modulation.weight": (cin, STYLE_DIM),
+                                               "modulation.bias": (cin,)})
+
+
+def sphere_params(name, cin_total, cout):
+    return module_params("smc_" + name + "_", {"weight": (1, cout, cin_total, 3, 3), "modulation.weight": (cin_total, STYLE_DIM),
+                                                "modulation.bias": (cin_total,)})
+
+
+def rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def t2n(t):
+    return t.detach().cpu().numpy()
+
+
+def generator_case(name, B, ix, iy):
+    """Inputs of the golden generator cases (make_golden.golden_generator)."""
+    plan = O.close_loop_plan(384, 768)
+    cp, (zx_st, zx_ed, zy_st, zy_ed) = O.patch_coords_partial(plan, ix, iy, plan["lat_h"], plan["lat_w"], 5)
+    gl = synth.randn_t(SEED, "gen_gl_" + name, (B, 512))
+    gl = torch.stack([gl, gl], 1)
+    canvas = synth.randn_t(SEED, "gen_canvas_" + name, (B, 256, plan["lat_h"], plan["lat_w"]))
+    coords_full = O.meta_coord_grid(plan["lat_h"], plan["lat_w"]).unsqueeze(0).repeat(B, 1, 1, 1)
+    lat = O.circular_slice(canvas, plan["lat_w"], zx_st, zx_ed, zy_st, zy_ed).contiguous()
+    coords = O.circular_slice(coords_full, plan["lat_w"], zx_st, zx_ed, zy_st, zy_ed).contiguous()
+    noises = [synth.randn_t(SEED, "gen_noise%d_%s" % (l, name), (B, 1, s, s)) for l, s in enumerate(plan["out_sizes"])]
+    return gl, lat, coords, cp, noises
+
+
+def generator_state_dict():
+    return synth.synthetic_state_dict(load_json("generator_manifest.json"), SEED)

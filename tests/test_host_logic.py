@@ -1,0 +1,115 @@
+"""CPU: host-side product logic (sampling tables, panorama lattice, module bookkeeping) against the oracle and the
+golden fixtures."""
+import json
+
+import numpy as np
+import torch
+
+import cases as K
+import spgan_oracle as O
+from spgan_b200 import generator, grids, panorama
+from spgan_b200.models import ops, spgan_ops, spgan_ops_gs, spherenet
+
+
+def test_product_grids_bit_exact_vs_golden():
+    g = K.load("grids.npz")
+    for name, c in K.load_json("grid_cases.json").items():
+        grid = grids.sampling_grid(c["h"], c["h"], c["cp"])
+        assert grid.dtype == np.float32 and grid.shape == (1, 3 * c["h"], 3 * c["h"], 2)
+        assert np.array_equal(grid.view(np.uint32), g[name].view(np.uint32)), name
+
+
+def test_product_grids_bit_exact_vs_oracle_sweep():
+    for x_st in (0, 4, 9):
+        for y_st in range(0, 140, 11):
+            cp = K.train_cp(x_st, y_st)
+            for h in (35, 29, 23, 17, 53):
+                a = grids.sampling_grid(h, h, cp)
+                b = O.gen_sampling_grid(h, h, cp)
+                assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (x_st, y_st, h)
+
+
+def test_dense_pattern_matches_oracle():
+    cp = K.train_cp(3, 130)
+    assert np.array_equal(grids.sampling_pattern_dense(17, 17, cp), O.create_sampling_pattern(17, 17, cp))
+
+
+def test_grid_cache_hits_and_batches():
+    cache = grids.GridCache(max_entries=4)
+    cps = [K.train_cp(1, 2), K.train_cp(3, 4)]
+    g = cache.batch(17, 17, cps, 2, "cpu")
+    assert g.shape == (2, 51, 51, 2) and cache.misses == 2
+    cache.batch(17, 17, cps, 2, "cpu")
+    assert cache.hits == 2
+    one = cache.batch(17, 17, K.test_cp(2, 7, 27), 5, "cpu")
+    assert one.shape[0] == 1  # test mode: one grid shared by the batch
+    for i in range(6):
+        cache.get(11, 11, K.train_cp(i, i), "cpu")
+    assert len(cache._store) == 4
+
+
+def test_panorama_plan_and_cursors_match_oracle_and_golden():
+    ref = K.load_json("lattice.json")
+    for key, hw in (("384x768", (384, 768)), ("768x1536", (768, 1536))):
+        pl = panorama.plan(*hw)
+        for k, v in ref[key].items():
+            assert pl[k] == v, (key, k)
+        po = O.close_loop_plan(*hw)
+        for it, (ix, iy) in enumerate(panorama.positions(pl)):
+            a = panorama.patch_inputs(pl, ix, iy, it, pl["lat_h"], pl["lat_w"])
+            b = O.patch_coords_partial(po, ix, iy, po["lat_h"], po["lat_w"], it)
+            assert a == b
+    assert len(panorama.positions(panorama.plan(384, 768))) == 60
+    assert len(panorama.positions(panorama.plan(768, 1536))) == 180
+
+
+def test_circular_slice_and_assign_match_oracle():
+    t = torch.arange(2 * 3 * 7 * 10, dtype=torch.float32).view(2, 3, 7, 10)
+    for (ys, ye) in ((0, 4), (7, 12), (10, 14), (12, 16), (21, 25)):
+        a = panorama.circular_slice(t, 10, 1, 5, ys, ye)
+        b = O.circular_slice(t, 10, 1, 5, ys, ye)
+        assert torch.equal(a, b)
+        m1, m2 = torch.zeros_like(t), torch.zeros_like(t)
+        v = torch.randn(2, 3, 4, ye - ys)
+        panorama.circular_assign(m1, 10, 1, 5, ys, ye, v)
+        O.circular_assign(m2, 10, 1, 5, ys, ye, v)
+        assert torch.equal(m1, m2)
+
+
+def test_generator_state_dict_matches_reference_manifest():
+    g = generator.Generator()
+    manifest = K.load_json("generator_manifest.json")
+    sd = g.state_dict()
+    assert set(sd) == set(manifest)
+    for k, shape in manifest.items():
+        assert list(sd[k].shape) == shape, k
+    g.load_state_dict(K.generator_state_dict())  # strict
+
+
+def test_spatial_size_bookkeeping():
+    ts = generator.Generator().texture_synthesizer
+    assert ts.calc_out_spatial_size(11, return_list=True) == [19, 17, 31, 29, 55, 53, 103, 101]
+    assert ts.calc_in_spatial_size(101, return_list=True) == O.ts_in_sizes(101)
+    assert generator.Generator().structure_synthesizer.calc_out_spatial_size(35) == 11
+
+
+def test_spherical_conv_initialises_to_centre_delta():
+    cfg = generator.default_config()
+    m = spgan_ops_gs.ModulatedConv2d(7, 4, 3, 8, no_zero_pad=True, config=cfg, side="ss", deal_coords=True)
+    w = m.weight.detach()
+    assert w.shape == (1, 4, 7, 3, 3)
+    assert torch.all(w[..., 1, 1] == 1) and w.sum() == 4 * 7
+    s = spherenet.SphereConvBatchDiffFixBorderGNoGrad(3, 3)
+    assert s.weight.shape == (3, 3, 3, 3) and s.weight.sum() == 9 and abs(s.scale - 1 / np.sqrt(27)) < 1e-12
+
+
+def test_module_surface_matches_reference_names():
+    for mod, names in ((ops, ["PixelNorm", "make_kernel", "Upsample", "Downsample", "Blur", "EqualConv2d", "EqualLinear",
+                             "ScaledLeakyReLU", "ModulatedConv2d", "NoiseInjection", "ConstantInput", "StyledConv", "ToRGB"]),
+                       (spgan_ops, ["ToRGB", "Upsample", "ModulatedConv2d", "SphereModulatedConv2d", "StyledConv"]),
+                       (spgan_ops_gs, ["ModulatedConv2d", "StyledConv", "Blur", "EqualConv2d", "EqualLinear"]),
+                       (spherenet, ["GridGenerator", "GridSamplerNewTextureNoGrad", "GridGeneratorPatchCoordsFixBorder",
+                                    "GridSamplerNewTexture", "SphereConv2d", "IncreIntervalSphereConv2d",
+                                    "SphereConvBatchDiffFixBorderGNoGrad"])):
+        for n in names:
+            assert hasattr(mod, n), (mod.__name__, n)
