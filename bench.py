@@ -1,0 +1,281 @@
+"""bench.py — SP-GAN generator forward: 384x768 close-loop panoramas per second (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch 32] [--precision 1]
+
+A step = one batch of B = 32 panoramas = 60 lattice positions x 32 patches = 1920 generator patch forwards through
+the public API (`spgan_b200.panorama.generate` over `spgan_b200.generator.Generator`), random-init weights of
+configs/model/spgan.yaml, synthetic latents/noise.  `value` times the steps with all inputs resident in HBM; `e2e`
+repeats them with the inputs in pinned host memory (H2D inside the timed region) and the finished panoramas copied
+back (D2H).  Under torchrun every rank generates its own 32 panoramas (weak scaling, no data-path collective).
+`--impl reference` times the CPU restatement of the reference (oracle/, all host threads) on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "panoramas_per_sec_384x768_generator_forward"
+UNIT = "panoramas/s"
+PATCH_GFLOP = 101.0  # algorithmic GFLOP per 101x101 patch forward (50.51 GMAC)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--precision", type=int, default=1, choices=[0, 1, 2])
+    ap.add_argument("--cpu-sample-patches", type=int, default=24)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm (oracle)
+def cpu_reference_rate(n_patches, threads=None):
+    """panoramas/s of the CPU restatement of the reference (oracle/spgan_oracle.py), B = 1, on the first
+    `n_patches` lattice positions of a 384x768 panorama (every position costs the same)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import spgan_oracle as O
+    import synth
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    plan = O.close_loop_plan(384, 768)
+    with open(os.path.join(ROOT, "tests", "golden", "generator_manifest.json")) as f:
+        sd = synth.synthetic_state_dict(json.load(f), 9000)
+    gl = synth.randn_t(9000, "bench_gl", (1, 512))
+    gl = torch.stack([gl, gl], 1)
+    canvas = synth.randn_t(9000, "bench_canvas", (1, 256, plan["lat_h"], plan["lat_w"]))
+    noises = [synth.randn_t(9000, "bench_noise%d" % l, (1, 1, plan["noise_h"][l], plan["noise_w"][l])) for l in range(8)]
+    pos = [(a, b) for a in range(plan["steps_h"]) for b in range(plan["steps_w"])]
+    with torch.no_grad():
+        O.generate_panorama(sd, plan, gl, canvas, noises, positions=set(pos[:1]))  # warm-up patch
+        t0 = time.perf_counter()
+        O.generate_panorama(sd, plan, gl, canvas, noises, positions=set(pos[:n_patches]))
+        dt = time.perf_counter() - t0
+    total = len(pos)
+    return (n_patches / total) / dt, threads, dt, total
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    per_step = max(2, min(args.cpu_sample_patches, 12))
+    rates, dts = [], []
+    for i in range(args.warmup + args.steps):
+        r, threads, dt, total = cpu_reference_rate(per_step)
+        if i >= args.warmup:
+            rates.append(r)
+            dts.append(dt)
+    ms = 1000.0 * sum(dts) / len(dts)
+    value = (per_step / total) * len(dts) / sum(dts)
+    sample = "B=1, %d of %d patch positions of one 384x768 panorama per step, oracle port of the reference on CPU" % (per_step, total)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": "SP-GAN generator forward, 384x768 close-loop panorama, random-init configs/model/spgan.yaml",
+                   "batch": 1, "patches_per_panorama": total},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import spgan_b200.functional as SF
+    import spgan_b200.lib as lib
+    from spgan_b200 import panorama
+    from spgan_b200.generator import Generator
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    lib.require_device()  # no fallback: fail loudly if the extension or a B200 is missing
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    SF.set_precision(args.precision)
+
+    torch.manual_seed(9000)
+    gen = Generator().to(dev).eval()
+    B = args.batch
+    pl = panorama.plan(384, 768)
+    n_pos = len(panorama.positions(pl))
+
+    g = torch.Generator(device="cpu").manual_seed(9000 + rank)
+    host = {
+        "gl": torch.randn(B, 2, 512, generator=g).pin_memory(),
+        "canvas": torch.randn(B, 256, pl["lat_h"], pl["lat_w"], generator=g).pin_memory(),
+        "noises": [torch.randn(B, 1, pl["noise_h"][l], pl["noise_w"][l], generator=g).pin_memory() for l in range(8)],
+    }
+    host["gl"][:, 1] = host["gl"][:, 0]  # the managers use mixing=False: both columns equal
+    host_out = torch.empty(B, 3, pl["meta_h"], pl["meta_w"]).pin_memory()
+    h2d = host["gl"].numel() * 4 + host["canvas"].numel() * 4 + sum(n.numel() * 4 for n in host["noises"])
+    d2h = host_out.numel() * 4
+
+    def upload():
+        return (host["gl"].to(dev, non_blocking=True), host["canvas"].to(dev, non_blocking=True),
+                [n.to(dev, non_blocking=True) for n in host["noises"]])
+
+    resident = upload()
+    meta = torch.zeros(B, 3, pl["meta_h"], pl["meta_w"], device=dev)
+
+    def step_resident():
+        gl, canvas, noises = resident
+        return panorama.generate(gen, pl, gl, canvas, noises, meta=meta)
+
+    def step_e2e():
+        gl, canvas, noises = upload()
+        out = panorama.generate(gen, pl, gl, canvas, noises, meta=meta)
+        host_out.copy_(out, non_blocking=True)
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    SF.profile_gemm(True)
+    l0, g0 = lib.launches(), lib.load().spgan_gemm_launch_count()
+    ms_total = timed(step_resident, args.steps)
+    l1, g1 = lib.launches(), lib.load().spgan_gemm_launch_count()
+    gemm_stats = SF.profile_gemm(False)
+    clocks = sampler.stop() if sampler else None
+    ms_step = ms_total / args.steps
+    value = world * B / (ms_step / 1000.0)
+
+    step_e2e()
+    ms_e2e = timed(step_e2e, args.steps) / args.steps
+    e2e_value = world * B / (ms_e2e / 1000.0)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)"
+    ach = gemm_stats["flops"] / (gemm_stats["ms"] / 1000.0) / 1e12 if gemm_stats["ms"] > 0 else 0.0
+    issued = {1: 3, 2: 1, 0: 0}[args.precision]
+    roofline = {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit-GEMM modulated conv)", "achieved": ach,
+                "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf if peak_tf else None, "traffic": None,
+                "peak_source": peak_src, "launches_timed": gemm_stats["launches"], "avg_launch_ms": gemm_stats["ms"] / max(gemm_stats["launches"], 1),
+                "share_of_step": gemm_stats["ms"] / (ms_total if ms_total else 1.0),
+                "note": "achieved = algorithmic conv FLOPs (2*B*Ho*Wo*Cout*Cin*k^2, valid outputs, real channels) / CUDA-event "
+                        "time of the launches; bf16x3 mode issues %dx that many tensor-core FLOPs" % issued}
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": {0: "fp32 (SIMT)", 1: "fp32-equivalent (bf16x3 split on tcgen05, fp32 accumulate)", 2: "bf16 (tcgen05, fp32 accumulate)"}[args.precision],
+        "data": "synthetic",
+        "config": {"workload": "SP-GAN generator forward batch %d at 384x768 (close-loop, %d patch positions x %d patches of 101x101 per step), "
+                               "random-init configs/model/spgan.yaml, synthetic latents" % (B, n_pos, B),
+                   "batch_per_gpu": B, "patches_per_step_per_gpu": B * n_pos, "l2": "inputs and activations larger than L2 (latent canvas %d MB, activations > 1 GB per patch batch)" % (host["canvas"].numel() * 4 // 2 ** 20),
+                   "precision_mode": args.precision, "algorithmic_tflop_per_step_per_gpu": B * n_pos * PATCH_GFLOP / 1000.0},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
+        "gpu_launches": l1 - l0, "tcgen05_gemm_launches": int(g1 - g0),
+        "achieved_model_tflops": world * B * n_pos * PATCH_GFLOP / 1000.0 / (ms_step / 1000.0),
+        "clocks": clocks, "roofline": roofline,
+    }
+    if not args.no_cpu_baseline and world >= 1:
+        rate, threads, dt, total = cpu_reference_rate(args.cpu_sample_patches)
+        out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                               "sample": "B=1, first %d of %d patch positions of one 384x768 panorama (%.1f s), oracle port of the reference's PyTorch CPU path" % (args.cpu_sample_patches, total, dt)}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

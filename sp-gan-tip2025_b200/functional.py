@@ -32,6 +32,33 @@ def get_precision():
     return _PRECISION
 
 
+_PROFILE = None  # list of (start event, end event, algorithmic flops) while bench.py profiles the tcgen05 launches
+
+
+def profile_gemm(on):
+    """bench.py: bracket every tcgen05 GEMM launch with CUDA events on the launching stream.  profile_gemm(True) starts
+    recording; profile_gemm(False) returns {"ms", "flops", "launches"} summed over the recorded launches."""
+    global _PROFILE
+    if on:
+        _PROFILE = []
+        return None
+    rec, _PROFILE = _PROFILE or [], None
+    torch.cuda.synchronize()
+    return {"ms": float(sum(a.elapsed_time(b) for a, b, _ in rec)), "flops": float(sum(f for _, _, f in rec)),
+            "launches": len(rec)}
+
+
+def _gemm_call(flops, *args):
+    if _PROFILE is None:
+        lib.call("spgan_conv_gemm", *args)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    lib.call("spgan_conv_gemm", *args)
+    e1.record()
+    _PROFILE.append((e0, e1, flops))
+
+
 def _stream(t):
     return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
 
@@ -442,8 +469,9 @@ def conv_apply(x, w, geom, adjoint=False, out_hw=None, in_mul=None, out_mul=None
                 shifted = dict(p, taps=[(dy + pt, dx + pl, wi) for dy, dx, wi in p["taps"]])
                 cp = _fill_pass(shifted, B, Cin, Hl, Wl, Cout, oh, ow, ws_o, ws_c, out_scale, act_on, a, g, precision)
                 wp = _packed_weight(w, Cout, Cin, ws_o, ws_c, [t[2] for t in p["taps"]], Cp, False)
-                lib.call("spgan_conv_gemm", ctypes.byref(cp), _ptr(y), _ptr(a_packed), rows, Cp, _ptr(wp), _ptr(om),
-                         _ptr(nz), _ptr(nwt), _ptr(bs), _ptr(rs), st)
+                valid = min(p["My"], _ceil_div(oh - p["off_y"], p["out_stride"])) * min(p["Mx"], _ceil_div(ow - p["off_x"], p["out_stride"]))
+                _gemm_call(2.0 * B * valid * Cout * Cin * len(p["taps"]), ctypes.byref(cp), _ptr(y), _ptr(a_packed), rows,
+                           Cp, _ptr(wp), _ptr(om), _ptr(nz), _ptr(nwt), _ptr(bs), _ptr(rs), st)
         else:
             for p in passes:
                 cp = _fill_pass(p, B, Cin, H, W, Cout, oh, ow, ws_o, ws_c, out_scale, act_on, a, g, 0)
@@ -642,8 +670,8 @@ def sphere_modconv_fused(x, coords, grid, w, in_mul, out_mul, out_scale, act=Non
         p = dict(My=H, Mx=W, in_stride=1, out_stride=1, off_y=0, off_x=0, taps=[(0, 0, 0)])
         cp = _fill_pass(p, B, Ct, H, W, O, H, W, Ct * 9, 9, out_scale, 1 if act is not None else 0, a, g, precision)
         om = _f32c(out_mul, "sphere_modconv") if out_mul is not None else None
-        lib.call("spgan_conv_gemm", ctypes.byref(cp), _ptr(y), _ptr(a_packed), rows, 9 * Cp, _ptr(wp), _ptr(om),
-                 _ptr(None), _ptr(None), _ptr(bias), _ptr(residual), st)
+        _gemm_call(2.0 * B * H * W * O * Ct * 9, ctypes.byref(cp), _ptr(y), _ptr(a_packed), rows, 9 * Cp, _ptr(wp),
+                   _ptr(om), _ptr(None), _ptr(None), _ptr(bias), _ptr(residual), st)
     return y
 
 

@@ -1,0 +1,405 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the golden fixtures, same seeded inputs.
+
+Tolerances: bit-exact for sampling indices; <= 1e-5 relative-to-peak for the HBM-bound fp32 kernels and the exact
+fp32 SIMT conv; <= 1e-4 for the bf16x3 tcgen05 conv (fp32-equivalent, north_star bound 1e-3); <= 3e-2 for the
+plain-bf16 tcgen05 mode (the stated looser bound for bf16 paths)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import cases as K
+import spgan_oracle as O
+import synth
+
+pytestmark = pytest.mark.gpu
+
+TOL = {0: 1e-5, 1: 1e-4, 2: 3e-2}
+
+
+@pytest.fixture(scope="module")
+def dev():
+    import spgan_b200.lib as lib
+    torch.cuda.set_device(0)
+    lib.require_device()
+    return torch.device("cuda:0")
+
+
+def SF():
+    import spgan_b200.functional as f
+    return f
+
+
+# ---------------------------------------------------------------------------------------------- K1
+def test_bias_act_golden_forward_backward(dev):
+    g = K.load("bias_act.npz")
+    for name, shape in (("4d", (2, 5, 7, 3)), ("2d", (3, 6))):
+        x = synth.randn_t(K.SEED, "ba_x_" + name, shape).to(dev).requires_grad_(True)
+        b = synth.randn_t(K.SEED, "ba_b_" + name, (shape[1],)).to(dev).requires_grad_(True)
+        go = synth.randn_t(K.SEED, "ba_go_" + name, shape).to(dev)
+        y = SF().fused_leaky_relu(x, b)
+        gx, gb = torch.autograd.grad(y, [x, b], go)
+        assert K.rel_err(K.t2n(y), g["y_" + name]) < 1e-6
+        assert K.rel_err(K.t2n(gx), g["gx_" + name]) < 1e-6
+        assert K.rel_err(K.t2n(gb), g["gb_" + name]) < 1e-5
+
+
+@pytest.mark.parametrize("shape", [(3, 7, 5, 9), (2, 8, 16, 16), (1, 3, 1, 1), (4, 512), (2, 6, 33, 35)])
+@pytest.mark.parametrize("code", [(3, 0), (3, 1), (1, 0), (1, 1), (3, 2)])
+def test_bias_act_all_codes_vs_oracle(dev, shape, code):
+    act, grad = code
+    x = synth.randn(1, "bx", shape)
+    b = synth.randn(1, "bb", (shape[1],))
+    r = synth.randn(1, "br", shape)
+    want = O.fused_bias_act(x, b, r, act, grad, 0.2, 2 ** 0.5)
+    got = SF().bias_act(torch.from_numpy(x).to(dev), torch.from_numpy(b).to(dev), torch.from_numpy(r).to(dev), act, grad, 0.2, 2 ** 0.5)
+    assert np.array_equal(K.t2n(got), want) or K.rel_err(K.t2n(got), want) < 1e-7
+    got = SF().bias_act(torch.from_numpy(x).to(dev), None, torch.from_numpy(r).to(dev), act, grad, 0.1, 1.0)
+    assert K.rel_err(K.t2n(got), O.fused_bias_act(x, None, r, act, grad, 0.1, 1.0)) < 1e-7
+
+
+def test_bias_act_empty_and_double_backward(dev):
+    e = SF().bias_act(torch.zeros(0, 4, 3, 3, device=dev), torch.zeros(4, device=dev))
+    assert e.shape == (0, 4, 3, 3)
+    x = torch.randn(2, 3, 5, 5, device=dev, requires_grad=True)
+    b = torch.randn(3, device=dev, requires_grad=True)
+    y = SF().fused_leaky_relu(x, b)
+    go = torch.randn_like(y).requires_grad_(True)
+    gx, = torch.autograd.grad(y, x, go, create_graph=True)
+    # d(gx)/d(go) applied to v = K1(grad=1) with the same gate
+    v = torch.randn_like(gx)
+    ggo, = torch.autograd.grad(gx, go, v)
+    want = O.fused_bias_act(K.t2n(v), None, K.t2n(y), 3, 1, 0.2, 2 ** 0.5)
+    assert K.rel_err(K.t2n(ggo), want) < 1e-6
+
+
+def test_noise_bias_act_vs_oracle(dev):
+    x = synth.randn_t(2, "nx", (3, 6, 19, 19))
+    nz = synth.randn_t(2, "nn", (3, 1, 19, 19))
+    b = synth.randn_t(2, "nb", (6,))
+    nw = torch.tensor([0.37])
+    want = O.fused_leaky_relu(K.t2n(x + nw * nz), K.t2n(b))
+    got = SF().noise_bias_act(x.to(dev), nz.to(dev), nw.to(dev), b.to(dev))
+    assert K.rel_err(K.t2n(got), want) < 1e-6
+
+
+# ---------------------------------------------------------------------------------------------- K2/K3
+@pytest.mark.parametrize("case", K.UPFIRDN_CASES, ids=[c[0] for c in K.UPFIRDN_CASES])
+def test_upfirdn2d_golden(dev, case):
+    name, shape, taps, gain, up, down, pad = case
+    g = K.load("upfirdn2d.npz")
+    k = torch.from_numpy(O.make_kernel(taps) * np.float32(gain)).to(dev)
+    x = synth.randn_t(K.SEED, "ufd_x_" + name, shape).to(dev).requires_grad_(True)
+    y = SF().upfirdn2d(x, k, up=up, down=down, pad=pad)
+    assert y.shape == g["y_" + name].shape
+    go = synth.randn_t(K.SEED, "ufd_go_" + name, y.shape).to(dev)
+    gx, = torch.autograd.grad(y, x, go)
+    assert K.rel_err(K.t2n(y), g["y_" + name]) < 1e-6
+    assert K.rel_err(K.t2n(gx), g["gx_" + name]) < 1e-6
+
+
+def test_upfirdn2d_large_and_double_backward(dev):
+    k = torch.from_numpy(O.make_kernel([1, 3, 3, 1])).to(dev)
+    x = synth.randn_t(3, "ufl", (2, 7, 101, 101))
+    y = SF().upfirdn2d(x.to(dev), k, pad=(2, 2))
+    assert K.rel_err(K.t2n(y), O.upfirdn2d(K.t2n(x), K.t2n(k), pad=(2, 2, 2, 2))) < 1e-6
+    xg = x.to(dev).requires_grad_(True)
+    y = SF().upfirdn2d(xg, k, pad=(1, 1))
+    go = torch.randn_like(y).requires_grad_(True)
+    gx, = torch.autograd.grad(y, xg, go, create_graph=True)
+    v = torch.randn_like(gx)
+    ggo, = torch.autograd.grad(gx, go, v)  # adjoint of the adjoint = the forward op
+    assert K.rel_err(K.t2n(ggo), O.upfirdn2d(K.t2n(v), K.t2n(k), pad=(1, 1, 1, 1))) < 1e-6
+    # a delta kernel with no padding is the identity
+    d = torch.ones(1, 1, device=dev)
+    assert torch.equal(SF().upfirdn2d(x.to(dev), d), x.to(dev))
+
+
+# ---------------------------------------------------------------------------------------------- gather
+def test_gather_indices_bit_exact(dev):
+    g = K.load("grids.npz")
+    for name, c in K.load_json("grid_cases.json").items():
+        h = c["h"]
+        grid = torch.from_numpy(g[name]).to(dev)
+        x0, y0, wx, wy = SF().sphere_gather_indices(grid, h, h)
+        ox0, oy0, owx, owy = O.gather_indices(g[name], h, h)
+        assert np.array_equal(K.t2n(x0), ox0) and np.array_equal(K.t2n(y0), oy0), name
+        assert np.array_equal(K.t2n(x0).astype(np.int16), g[name + "_x0"]), name
+        assert np.array_equal(K.t2n(wx), owx) and np.array_equal(K.t2n(wy), owy), name
+
+
+def test_gather_golden_forward_and_surrogate_backward(dev):
+    g = K.load("gather.npz")
+    for name, (B, C, h) in (("train", (2, 5, 17)), ("border", (1, 3, 11))):
+        z = synth.randn_t(K.SEED, "gather_z_" + name, (B, C, h, h)).to(dev).requires_grad_(True)
+        grid = torch.from_numpy(g["grid_" + name]).to(dev)
+        y = SF().sphere_gather(z, grid)
+        go = synth.randn_t(K.SEED, "gather_go_" + name, y.shape).to(dev)
+        gz, = torch.autograd.grad(y, z, go)
+        assert K.rel_err(K.t2n(y), g["y_" + name]) < 2e-6
+        assert K.rel_err(K.t2n(gz), g["gz_" + name]) < 1e-6
+
+
+def test_gather_shared_grid_and_channel_chunks(dev):
+    cp = K.test_cp(2, 7, 27)
+    grid = O.gen_sampling_grid(23, 23, cp)
+    z = synth.randn(4, "gz", (3, 37, 23, 23))
+    want = O.grid_sample_border(z, np.repeat(grid, 3, 0))
+    got = SF().sphere_gather_raw(torch.from_numpy(z).to(dev), torch.from_numpy(grid).to(dev))
+    assert K.rel_err(K.t2n(got), want) < 2e-6
+
+
+# ---------------------------------------------------------------------------------------------- conv passes
+def _ref_conv(x, w, geom, adjoint, out_hw, in_mul, out_mul, out_scale):
+    x = x.double()
+    w = w.double()
+    if in_mul is not None:
+        x = x * in_mul.double()[:, :, None, None]
+    if not adjoint:
+        if geom.transposed:
+            y = F.conv_transpose2d(x, w.transpose(0, 1), stride=geom.stride)
+            c = geom.crop
+            y = y[:, :, c:y.shape[2] - c, c:y.shape[3] - c] if c else y
+        else:
+            y = F.conv2d(x, w, stride=geom.stride, padding=geom.pad)
+    else:
+        B = x.shape[0]
+        probe = torch.zeros(B, w.shape[1], out_hw[0], out_hw[1], dtype=torch.float64, requires_grad=True)
+        if geom.transposed:
+            base = F.conv_transpose2d(probe, w.transpose(0, 1), stride=geom.stride)
+            c = geom.crop
+            base = base[:, :, c:base.shape[2] - c, c:base.shape[3] - c] if c else base
+        else:
+            base = F.conv2d(probe, w, stride=geom.stride, padding=geom.pad)
+        y, = torch.autograd.grad(base, probe, x)
+    if out_mul is not None:
+        y = y * out_mul.double()[:, :, None, None]
+    return y * out_scale
+
+
+def _geoms():
+    from spgan_b200.functional import ConvGeom
+    return [
+        ("k3", ConvGeom(3, 3), 19),
+        ("k3_pad1", ConvGeom(3, 3, pad=1), 12),
+        ("k7", ConvGeom(7, 7), 17),
+        ("k1", ConvGeom(1, 1), 9),
+        ("k3_s2", ConvGeom(3, 3, stride=2), 13),
+        ("k1_s2", ConvGeom(1, 1, stride=2), 12),
+        ("k3_s3", ConvGeom(3, 3, stride=3), 15),
+        ("convT_crop1", ConvGeom(3, 3, stride=2, transposed=True, crop=1), 11),
+        ("convT_crop0", ConvGeom(3, 3, stride=2, transposed=True, crop=0), 6),
+    ]
+
+
+@pytest.mark.parametrize("gi", range(9))
+def test_conv_simt_forward_adjoint_wgrad_vs_torch(dev, gi):
+    _conv_case(dev, gi, 0)
+
+
+@pytest.mark.parametrize("gi", range(9))
+@pytest.mark.parametrize("precision", [1, 2])
+def test_conv_tcgen05_forward_adjoint_vs_torch(dev, gi, precision):
+    _conv_case(dev, gi, precision)
+
+
+def _conv_case(dev, gi, precision):
+    name, geom, H = _geoms()[gi]
+    B, C, Oc = 3, 70, 40  # C pads to 128 channels on the tensor path, Cout is not a multiple of 16
+    x = synth.randn_t(7, "cx" + name, (B, C, H, H))
+    w = synth.randn_t(7, "cw" + name, (Oc, C, geom.kh, geom.kw), 0.2)
+    im = synth.randn_t(7, "cim" + name, (B, C), 0.3, 1.0)
+    om = synth.randn_t(7, "com" + name, (B, Oc), 0.3, 1.0)
+    want = _ref_conv(x, w, geom, False, None, im, om, 0.37)
+    got = SF().conv_apply(x.to(dev), w.to(dev), geom, False, None, im.to(dev), om.to(dev), 0.37, precision=precision)
+    assert got.shape == want.shape
+    assert K.rel_err(K.t2n(got), want.numpy()) < TOL[precision], "forward"
+    oh, ow = want.shape[2:]
+    g = synth.randn_t(7, "cg" + name, (B, Oc, oh, ow))
+    want = _ref_conv(g, w, geom, True, (H, H), om, im, 0.37)
+    got = SF().conv_apply(g.to(dev), w.to(dev), geom, True, (H, H), om.to(dev), im.to(dev), 0.37, precision=precision)
+    assert K.rel_err(K.t2n(got), want.numpy()) < TOL[precision], "adjoint"
+    if precision == 0:
+        wd = w.double().requires_grad_(True)
+        base = _ref_conv(x, wd, geom, False, None, im, om, 0.37)
+        want_w, = torch.autograd.grad(base, wd, g.double())
+        got_w = SF().conv_wgrad(g.to(dev), x.to(dev), tuple(w.shape), geom, im.to(dev), om.to(dev), 0.37)
+        assert K.rel_err(K.t2n(got_w), want_w.numpy()) < 1e-5, "wgrad"
+
+
+@pytest.mark.parametrize("precision", [1, 2])
+def test_conv_tcgen05_tiles_and_epilogue(dev, precision):
+    """Two N tiles with a ragged second tile, several M tiles, K padding, and every epilogue term at once."""
+    from spgan_b200.functional import ConvGeom
+    B, C, Oc, H = 5, 130, 300, 23
+    geom = ConvGeom(3, 3)
+    x = synth.randn_t(8, "tx", (B, C, H, H))
+    w = synth.randn_t(8, "tw", (Oc, C, 3, 3), 0.1)
+    im = synth.randn_t(8, "tim", (B, C), 0.3, 1.0)
+    om = synth.randn_t(8, "tom", (B, Oc), 0.3, 1.0)
+    nz = synth.randn_t(8, "tnz", (B, 1, H - 2, H - 2))
+    nw = torch.tensor([0.41])
+    bias = synth.randn_t(8, "tb", (Oc,))
+    res = synth.randn_t(8, "tr", (B, Oc, H - 2, H - 2))
+    y = _ref_conv(x, w, geom, False, None, im, om, 0.05) + (nw * nz).double() + bias.double()[None, :, None, None]
+    y = F.leaky_relu(y, 0.2) * 2 ** 0.5 + res.double()
+    got = SF().conv_apply(x.to(dev), w.to(dev), geom, False, None, im.to(dev), om.to(dev), 0.05, nz.to(dev), nw.to(dev),
+                          bias.to(dev), (0.2, 2 ** 0.5), res.to(dev), precision)
+    assert K.rel_err(K.t2n(got), y.numpy()) < TOL[precision]
+    import spgan_b200.lib as lib
+    assert lib.load().spgan_gemm_launch_count() > 0
+
+
+def test_conv_tcgen05_matches_simt_at_layer_size_and_is_linear(dev):
+    """Full-size property check (TS layer 7 shape, batch 4): tcgen05 bf16x3 == exact SIMT, and the op is linear in x."""
+    from spgan_b200.functional import ConvGeom
+    B, C, Oc, H = 4, 512, 512, 103
+    geom = ConvGeom(3, 3)
+    gen = torch.Generator(device="cpu").manual_seed(5)
+    x1 = torch.randn(B, C, H, H, generator=gen).to(dev)
+    x2 = torch.randn(B, C, H, H, generator=gen).to(dev)
+    w = (torch.randn(Oc, C, 3, 3, generator=gen) * 0.05).to(dev)
+    im = (torch.randn(B, C, generator=gen) * 0.3 + 1).to(dev)
+    om = (torch.randn(B, Oc, generator=gen) * 0.3 + 1).to(dev)
+    y1 = SF().conv_apply(x1, w, geom, in_mul=im, out_mul=om, out_scale=0.02, precision=1)
+    y2 = SF().conv_apply(x2, w, geom, in_mul=im, out_mul=om, out_scale=0.02, precision=1)
+    y12 = SF().conv_apply(2.5 * x1 + x2, w, geom, in_mul=im, out_mul=om, out_scale=0.02, precision=1)
+    assert K.rel_err(K.t2n(y12), K.t2n(2.5 * y1 + y2)) < 1e-4
+    ys = SF().conv_apply(x1[:1], w, geom, in_mul=im[:1], out_mul=om[:1], out_scale=0.02, precision=0)
+    assert K.rel_err(K.t2n(y1[:1]), K.t2n(ys)) < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------- modulated conv modules
+def _modconv_module(name, cin, cout, k, demod, up, dev):
+    from spgan_b200.models import ops
+    from spgan_b200.generator import default_config
+    m = ops.ModulatedConv2d(cin, cout, k, K.STYLE_DIM, demodulate=demod, upsample=up, no_zero_pad=True,
+                            blur_kernel=[1, 2, 1], config=default_config(), side="ts")
+    p = K.modconv_params(name, cin, cout, k)
+    with torch.no_grad():
+        m.weight.copy_(p["weight"])
+        m.modulation.weight.copy_(p["modulation.weight"])
+        m.modulation.bias.copy_(p["modulation.bias"])
+    return m.to(dev)
+
+
+@pytest.mark.parametrize("case", K.MODCONV_CASES, ids=[c[0] for c in K.MODCONV_CASES])
+def test_modconv_module_golden_forward_and_grads(dev, case):
+    name, cin, cout, k, demod, up, B, H = case
+    g = K.load("modconv.npz")
+    m = _modconv_module(name, cin, cout, k, demod, up, dev)
+    x = synth.randn_t(K.SEED, "mc_x_" + name, (B, cin, H, H)).to(dev)
+    s = synth.randn_t(K.SEED, "mc_s_" + name, (B, K.STYLE_DIM)).to(dev)
+    with torch.no_grad():
+        y0, _ = m(x, s)
+    assert K.rel_err(K.t2n(y0), g["y_" + name]) < 1e-5
+    x.requires_grad_(True)
+    s.requires_grad_(True)
+    y, _ = m(x, s)
+    assert K.rel_err(K.t2n(y), g["y_" + name]) < 1e-5
+    go = synth.randn_t(K.SEED, "mc_go_" + name, y.shape).to(dev)
+    grads = torch.autograd.grad(y, [x, s, m.weight, m.modulation.weight, m.modulation.bias], go)
+    for gname, got in zip(("gx", "gs", "gw", "gmw", "gmb"), grads):
+        assert K.rel_err(K.t2n(got), g[gname + "_" + name]) < 2e-5, gname
+
+
+@pytest.mark.parametrize("case", K.SPHERE_CASES, ids=[c[0] for c in K.SPHERE_CASES])
+def test_sphere_modconv_module_golden_forward_and_grads(dev, case):
+    name, B, C, cout, h, cps = case
+    from spgan_b200.models import spgan_ops_gs
+    from spgan_b200.generator import default_config
+    g = K.load("sphere_modconv.npz")
+    m = spgan_ops_gs.ModulatedConv2d(C + 3, cout, 3, K.STYLE_DIM, no_zero_pad=True, config=default_config(), side="ss",
+                                     deal_coords=True)
+    p = K.sphere_params(name, C + 3, cout)
+    with torch.no_grad():
+        m.weight.copy_(p["weight"])
+        m.modulation.weight.copy_(p["modulation.weight"])
+        m.modulation.bias.copy_(p["modulation.bias"])
+    m = m.to(dev)
+    x = synth.randn_t(K.SEED, "smc_x_" + name, (B, C, h, h)).to(dev)
+    c = synth.randn_t(K.SEED, "smc_c_" + name, (B, 3, h, h)).to(dev)
+    s = synth.randn_t(K.SEED, "smc_s_" + name, (B, K.STYLE_DIM)).to(dev)
+    with torch.no_grad():
+        y0, _ = m(x, s, coords=c.clone(), coords_partial=cps)
+    assert K.rel_err(K.t2n(y0), g["y_" + name]) < 1e-5
+    x.requires_grad_(True)
+    s.requires_grad_(True)
+    y, _ = m(x, s, coords=c.clone(), coords_partial=cps)
+    assert K.rel_err(K.t2n(y), g["y_" + name]) < 1e-5
+    go = synth.randn_t(K.SEED, "smc_go_" + name, y.shape).to(dev)
+    gx, gs, gw = torch.autograd.grad(y, [x, s, m.weight], go)
+    assert K.rel_err(K.t2n(gx), g["gx_" + name]) < 2e-5
+    assert K.rel_err(K.t2n(gs), g["gs_" + name]) < 2e-5
+    assert K.rel_err(K.t2n(gw), g["gw_" + name]) < 2e-5
+
+
+@pytest.mark.parametrize("precision", [1, 2])
+def test_sphere_tcgen05_fused_vs_oracle(dev, precision):
+    """The fused producer + tcgen05 GEMM at tensor-path channel counts, train (per-sample grids) and test (shared)."""
+    for B, C, Oc, h, cps in ((2, 61, 32, 17, [K.train_cp(7, 139, 17), K.train_cp(1, 20, 17)]),
+                             (3, 125, 64, 23, K.test_cp(2, 7, 27))):
+        x = synth.randn_t(9, "sfx%d" % B, (B, C, h, h))
+        c = synth.randn_t(9, "sfc%d" % B, (B, 3, h, h))
+        w = synth.randn_t(9, "sfw%d" % B, (1, Oc, C + 3, 3, 3))
+        s = synth.randn_t(9, "sfs%d" % B, (B, C + 3), 0.3, 1.0)
+        wm = O.modulated_weight(w, s, True)
+        grid = torch.from_numpy(O.batch_sampling_grid(h, h, cps, B))
+        xs = O.gather_t(x, grid)
+        cs = O.encode_coords(O.gather_t(c, grid))
+        inp = torch.cat([xs.reshape(1, B * C, 3 * h, 3 * h), cs.reshape(1, B * 3, 3 * h, 3 * h)], 1)
+        want = F.leaky_relu(F.conv2d(inp, wm.reshape(B * Oc, C + 3, 3, 3), groups=B, stride=3).reshape(B, Oc, h, h), 0.01)
+        scale = 1 / np.sqrt((C + 3) * 9)
+        d = SF().demod_coefficients(w[0].to(dev), s.to(dev), scale)
+        g1 = grid[:1] if isinstance(cps, dict) else grid
+        got = SF().sphere_modconv_fused(x.to(dev), c.to(dev), g1.to(dev), w[0].to(dev), s.to(dev), d, scale,
+                                        act=(0.01, 1.0), precision=precision)
+        assert K.rel_err(K.t2n(got), want.numpy()) < TOL[precision]
+
+
+def test_sphere_rgb_conv_golden(dev):
+    from spgan_b200.models.spherenet import SphereConvBatchDiffFixBorderGNoGrad
+    g = K.load("sphere_modconv.npz")
+    m = SphereConvBatchDiffFixBorderGNoGrad(3, 3)
+    p = K.module_params("srgb_", {"weight": (3, 3, 3, 3), "bias": (3,)})
+    with torch.no_grad():
+        m.weight.copy_(p["weight"])
+        m.bias.copy_(p["bias"])
+    m = m.to(dev)
+    x = synth.randn_t(K.SEED, "srgb_x", (2, 3, 17, 17)).to(dev)
+    cps = [K.train_cp(7, 139, 17), K.train_cp(1, 20, 17)]
+    with torch.no_grad():
+        y0 = m(x, cps)
+    assert K.rel_err(K.t2n(y0), g["y_srgb"]) < 1e-5
+    x.requires_grad_(True)
+    y = m(x, cps)
+    go = synth.randn_t(K.SEED, "srgb_go", y.shape).to(dev)
+    gx, gw, gb = torch.autograd.grad(y, [x, m.weight, m.bias], go)
+    assert K.rel_err(K.t2n(y), g["y_srgb"]) < 1e-5
+    assert K.rel_err(K.t2n(gx), g["gx_srgb"]) < 2e-5
+    assert K.rel_err(K.t2n(gw), g["gw_srgb"]) < 2e-5
+    assert K.rel_err(K.t2n(gb), g["gb_srgb"]) < 2e-5
+
+
+def test_equal_linear_vs_oracle(dev):
+    x = synth.randn_t(3, "lx", (5, 512))
+    w = synth.randn_t(3, "lw", (259, 512))
+    b = synth.randn_t(3, "lb", (259,))
+    want = O.equal_linear(x, w, b, lr_mul=1.0)
+    got = SF().equal_linear(x.to(dev), w.to(dev), b.to(dev), 1 / np.sqrt(512), 1.0, False)
+    assert K.rel_err(K.t2n(got), K.t2n(want)) < 1e-5
+    w2 = synth.randn_t(3, "lw2", (512, 512), 100.0)
+    b2 = synth.randn_t(3, "lb2", (512,))
+    want = O.equal_linear(x, w2, b2, lr_mul=0.01, activation=True)
+    got = SF().equal_linear(x.to(dev), w2.to(dev), b2.to(dev), 0.01 / np.sqrt(512), 0.01, True)
+    assert K.rel_err(K.t2n(got), K.t2n(want)) < 1e-5
+    xg = x.to(dev).requires_grad_(True)
+    wg = w2.to(dev).requires_grad_(True)
+    bg = b2.to(dev).requires_grad_(True)
+    y = SF().equal_linear(xg, wg, bg, 0.01 / np.sqrt(512), 0.01, True)
+    go = synth.randn_t(3, "lgo", (5, 512))
+    gx, gw, gb = torch.autograd.grad(y, [xg, wg, bg], go.to(dev))
+    xr, wr, br = x.clone().requires_grad_(True), w2.clone().requires_grad_(True), b2.clone().requires_grad_(True)
+    rx, rw, rb = torch.autograd.grad(O.equal_linear(xr, wr, br, lr_mul=0.01, activation=True), [xr, wr, br], go)
+    assert K.rel_err(K.t2n(gx), K.t2n(rx)) < 1e-5 and K.rel_err(K.t2n(gw), K.t2n(rw)) < 1e-5
+    assert K.rel_err(K.t2n(gb), K.t2n(rb)) < 1e-5
