@@ -349,7 +349,7 @@ def golden_panorama(gen):
     img = t2n(tv.meta_img)
     np.savez_compressed(os.path.join(OUT, "panorama_384.npz"),
                         strip=img[:, :, 250:290, :].astype(np.float32),
-                        col_seam=img[:, :, :, 740:768].astype(np.float16),
+                        col_seam=img[:, :, :, 740:768].astype(np.float32),
                         mean=np.float64(img.mean()), std=np.float64(img.std()))
 
 

@@ -64,7 +64,7 @@ def test_panorama_384_golden_strip(gen):
     img = K.t2n(meta)
     assert img.shape == (1, 3, pl["meta_h"], pl["meta_w"])
     assert K.rel_err(img[:, :, 250:290, :], ref["strip"]) < 5e-4
-    assert K.rel_err(img[:, :, :, 740:768], ref["col_seam"].astype(np.float32)) < 2e-3  # fixture stored as fp16
+    assert K.rel_err(img[:, :, :, 740:768], ref["col_seam"]) < 5e-4  # longitude seam columns
     assert abs(img.mean() - float(ref["mean"])) < 1e-3 and abs(img.std() - float(ref["std"])) < 1e-3
 
 
