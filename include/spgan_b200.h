@@ -57,6 +57,15 @@ int spgan_upfirdn2d(float* out, const float* x, const float* kernel, int64_t pla
                     int up_x, int up_y, int down_x, int down_y, int pad_x0, int pad_x1, int pad_y0, int pad_y1,
                     void* stream);
 
+/* Fused tail of the upsampling StyledConv (models/ops.py:617-622 + 784 + fused_act.py:56-64): the cropped
+ * conv_transpose2d(stride 2) output is held as four polyphase planes pp (planes, 4, Hq, Wq), plane index
+ * (Y & 1) * 2 + (X & 1), element (Y >> 1, X >> 1); this kernel applies the 3x3 FIR of Blur (upfirdn2d, pad 0; `kernel`
+ * is the un-flipped 3x3 buffer on the device), adds noise_w * noise (batch, out_h, out_w) and bias (channels), and the
+ * leaky-ReLU * scale:  out (batch*channels, zh - 2, zw - 2) where (zh, zw) is the interleaved size. */
+int spgan_upblur_act(float* out, const float* pp, const float* kernel, const float* noise, const float* noise_w,
+                     const float* bias, int64_t batch, int64_t channels, int zh, int zw, int Hq, int Wq, float alpha,
+                     float scale, void* stream);
+
 /* ---- L1: spherical bilinear gather ----------------------------------------------------------------------
  * Replaces F.grid_sample(z, grid, mode='bilinear', padding_mode='border', align_corners=True) as called by
  *   GridSamplerFuncNoGrad.forward (models/spherenet/grid_generator.py:610-613) for 3x3 tap grids.
@@ -106,6 +115,9 @@ typedef struct SpganConvPass {
   int32_t act;                    /* 0 = none, 1 = leaky relu */
   float act_alpha, act_gain;
   int32_t precision;              /* 0 = fp32 SIMT, 1 = bf16x3 split on tcgen05 (fp32-equivalent), 2 = bf16 on tcgen05 */
+  int64_t out_cstride;            /* elements between output channels; 0 = out_H*out_W (dense NCHW).  A larger stride
+                                     lets the parity passes of a transposed conv write polyphase planes
+                                     (B, Cout, s*s, Hq, Wq) instead of scattering with stride s (see spgan_upblur_act) */
 } SpganConvPass;
 
 int spgan_conv_pass(const SpganConvPass* p, float* y, const float* x, const float* w, const float* in_mul,

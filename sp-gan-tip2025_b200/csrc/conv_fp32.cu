@@ -113,10 +113,102 @@ __global__ void __launch_bounds__(256) conv_pass_fp32(SpganConvPass p, float* __
       r += nz;
       if (bias) r += __ldg(bias + o);
       if (p.act) r = (r > 0.f ? r : r * p.act_alpha) * p.act_gain;
-      const int64_t idx = (((int64_t)b * p.Cout + o) * p.out_H + Y) * p.out_W + X;
+      const int64_t cst = p.out_cstride ? p.out_cstride : (int64_t)p.out_H * p.out_W;
+      const int64_t idx = ((int64_t)b * p.Cout + o) * cst + (int64_t)Y * p.out_W + X;
       if (residual) r += __ldg(residual + idx);
       y[idx] = r;
     }
+  }
+}
+
+// Few output channels (ToRGB: 512 -> 3, the 3 -> 3 spherical RGB convs): HBM-bound, not GEMM-shaped.  One thread per
+// lattice point accumulates all (<= 4) outputs; the per-sample modulated weights w * in_mul live in shared memory
+// as [c][tap][4], so each input element is read exactly once, coalesced along x, and costs one LDS.128 + 4 FMAs.
+constexpr int SMALL_COUT = 4;
+
+__global__ void __launch_bounds__(256) conv_small_cout(SpganConvPass p, float* __restrict__ y, const float* __restrict__ x,
+                                                      const float* __restrict__ w, const float* __restrict__ in_mul,
+                                                      const float* __restrict__ out_mul, const float* __restrict__ noise,
+                                                      const float* __restrict__ noise_w, const float* __restrict__ bias,
+                                                      const float* __restrict__ residual) {
+  extern __shared__ float4 wsm[];  // [Cin][ntaps]
+  const int b = blockIdx.y;
+  const int nt = p.ntaps;
+  for (int i = threadIdx.x; i < p.Cin * nt; i += blockDim.x) {
+    const int c = i / nt, t = i - c * nt;
+    const float m = in_mul ? __ldg(in_mul + (int64_t)b * p.Cin + c) : 1.f;
+    float v[SMALL_COUT];
+#pragma unroll
+    for (int o = 0; o < SMALL_COUT; ++o)
+      v[o] = o < p.Cout ? m * __ldg(w + (int64_t)o * p.ws_o + (int64_t)c * p.ws_c + p.tap_w[t]) : 0.f;
+    wsm[i] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+  __syncthreads();
+  const int Mtot = p.My * p.Mx;
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= Mtot) return;
+  const int i = m / p.Mx, j = m - i * p.Mx;
+  const int Y = i * p.out_stride + p.out_off_y, X = j * p.out_stride + p.out_off_x;
+  if (Y < 0 || Y >= p.out_H || X < 0 || X >= p.out_W) return;
+  const float* xb = x + (int64_t)b * p.Cin * p.H * p.W;
+  const int64_t plane = (int64_t)p.H * p.W;
+  float acc[SMALL_COUT] = {0.f, 0.f, 0.f, 0.f};
+  if (nt == 1) {
+    const int yy = i * p.in_stride + p.tap_dy[0], xx = j * p.in_stride + p.tap_dx[0];
+    if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) {
+      const float* xp = xb + (int64_t)yy * p.W + xx;
+      int c = 0;
+      for (; c + 8 <= p.Cin; c += 8) {
+        float xv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) xv[u] = __ldcs(xp + (int64_t)(c + u) * plane);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float4 wv = wsm[c + u];
+          acc[0] += xv[u] * wv.x;
+          acc[1] += xv[u] * wv.y;
+          acc[2] += xv[u] * wv.z;
+          acc[3] += xv[u] * wv.w;
+        }
+      }
+      for (; c < p.Cin; ++c) {
+        const float xv = __ldcs(xp + (int64_t)c * plane);
+        const float4 wv = wsm[c];
+        acc[0] += xv * wv.x;
+        acc[1] += xv * wv.y;
+        acc[2] += xv * wv.z;
+        acc[3] += xv * wv.w;
+      }
+    }
+  } else {
+    for (int c = 0; c < p.Cin; ++c) {
+      const float* xc = xb + (int64_t)c * plane;
+      for (int t = 0; t < nt; ++t) {
+        const int yy = i * p.in_stride + p.tap_dy[t], xx = j * p.in_stride + p.tap_dx[t];
+        if (yy < 0 || yy >= p.H || xx < 0 || xx >= p.W) continue;
+        const float xv = __ldg(xc + (int64_t)yy * p.W + xx);
+        const float4 wv = wsm[c * nt + t];
+        acc[0] += xv * wv.x;
+        acc[1] += xv * wv.y;
+        acc[2] += xv * wv.z;
+        acc[3] += xv * wv.w;
+      }
+    }
+  }
+  const int64_t opix = (int64_t)Y * p.out_W + X;
+  const int64_t oplane = p.out_cstride ? p.out_cstride : (int64_t)p.out_H * p.out_W;
+  const float nz = (noise && noise_w) ? __ldg(noise_w) * __ldg(noise + (int64_t)b * p.out_H * p.out_W + opix) : 0.f;
+#pragma unroll
+  for (int o = 0; o < SMALL_COUT; ++o) {
+    if (o >= p.Cout) break;
+    float r = acc[o] * p.out_scale;
+    if (out_mul) r *= __ldg(out_mul + (int64_t)b * p.Cout + o);
+    r += nz;
+    if (bias) r += __ldg(bias + o);
+    if (p.act) r = (r > 0.f ? r : r * p.act_alpha) * p.act_gain;
+    const int64_t idx = ((int64_t)b * p.Cout + o) * oplane + opix;
+    if (residual) r += __ldg(residual + idx);
+    y[idx] = r;
   }
 }
 
@@ -294,6 +386,14 @@ extern "C" int spgan_conv_pass(const SpganConvPass* p, float* y, const float* x,
                   "spgan_conv_pass: precision %d runs on the tcgen05 path: pack the operands (spgan_pack_act / "
                   "spgan_pack_weight) and call spgan_conv_gemm",
                   p->precision);
+  const size_t small_smem = sizeof(float4) * (size_t)p->Cin * p->ntaps;
+  if (p->Cout <= SMALL_COUT && small_smem <= 48 * 1024) {
+    dim3 grid((p->My * p->Mx + 255) / 256, p->B);
+    conv_small_cout<<<grid, 256, small_smem, (cudaStream_t)stream>>>(*p, y, x, w, in_mul, out_mul, noise, noise_w, bias,
+                                                                     residual);
+    SPGAN_CHECK_LAUNCH("spgan_conv_pass");
+    return 0;
+  }
   dim3 grid((p->My * p->Mx + BM - 1) / BM, (p->Cout + BN - 1) / BN, p->B);
   conv_pass_fp32<<<grid, 256, 0, (cudaStream_t)stream>>>(*p, y, x, w, in_mul, out_mul, noise, noise_w, bias, residual);
   SPGAN_CHECK_LAUNCH("spgan_conv_pass");

@@ -37,6 +37,7 @@ struct GemmParams {
   int32_t My, Mx;      // valid lattice extent
   int32_t Cout, out_H, out_W;
   int32_t out_stride, out_off_y, out_off_x;
+  int64_t out_cstride;     // elements between output channels
   int32_t ntaps, kblocks;  // kblocks = kp / 64
   int32_t tap_off[SPGAN_MAX_TAPS];
   int32_t m_tiles, n_tiles;
@@ -282,7 +283,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ===================================================================== epilogue (warps 2..5)
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
     const int plane = gp.Hl * gp.Wl;
-    const int64_t ostride_c = (int64_t)gp.out_H * gp.out_W;
+    const int64_t ostride_c = gp.out_cstride;
+    const int64_t oplane = (int64_t)gp.out_H * gp.out_W;
     const float nw = (noise != nullptr && noise_w != nullptr) ? __ldg(noise_w) : 0.f;
     int titer = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++titer) {
@@ -307,7 +309,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       const int64_t pix = (int64_t)Y * gp.out_W + X;
       const int64_t ybase = (int64_t)b * gp.Cout * ostride_c + pix;
-      const float nz = (valid && noise != nullptr && noise_w != nullptr) ? nw * __ldg(noise + (int64_t)b * ostride_c + pix) : 0.f;
+      const float nz = (valid && noise != nullptr && noise_w != nullptr) ? nw * __ldg(noise + (int64_t)b * oplane + pix) : 0.f;
       const float* om = out_mul ? out_mul + (int64_t)b * gp.Cout : nullptr;
 
       mbar_wait(tfull_bar(as), aphase);
@@ -317,18 +319,26 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         float v[32];
         tmem_ld32(taddr + (uint32_t)c0, v);
         if (valid) {
+          // Two halves of 16 columns: all global loads of a half are issued before the first dependent use, so the
+          // epilogue pays one memory latency per half instead of one per column (the issue order is in-order).
 #pragma unroll
-          for (int k = 0; k < 32; ++k) {
-            const int o = n0 + c0 + k;
-            if (o < gp.Cout) {
-              float r = v[k] * gp.out_scale;
-              if (om) r *= __ldg(om + o);
-              r += nz;
-              if (bias) r += __ldg(bias + o);
+          for (int h0 = 0; h0 < 32; h0 += 16) {
+            float omv[16], bv[16], rv[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              const int o = n0 + c0 + h0 + k;
+              const int oc = o < gp.Cout ? o : gp.Cout - 1;
+              omv[k] = om ? __ldg(om + oc) : 1.f;
+              bv[k] = bias ? __ldg(bias + oc) : 0.f;
+              rv[k] = residual ? __ldg(residual + ybase + (int64_t)oc * ostride_c) : 0.f;
+            }
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              const int o = n0 + c0 + h0 + k;
+              float r = v[h0 + k] * gp.out_scale * omv[k] + nz + bv[k];
               if (gp.act) r = (r > 0.f ? r : r * gp.act_alpha) * gp.act_gain;
-              const int64_t idx = ybase + (int64_t)o * ostride_c;
-              if (residual) r += __ldg(residual + idx);
-              y[idx] = r;
+              r += rv[k];
+              if (o < gp.Cout) y[ybase + (int64_t)o * ostride_c] = r;
             }
           }
         }
@@ -451,8 +461,37 @@ __device__ __forceinline__ float unnorm_clip(float g, int size) {
   return fminf((float)(size - 1), fmaxf(v, 0.f));
 }
 
-// One thread per (group g, pixel p, tap t, channel k), k fastest: corner reads are coalesced over channels in the
-// NHWC staging copy, bf16 writes are coalesced over k.
+struct TapCorners {
+  int o_nw, o_ne, o_sw, o_se;  // pixel offsets y*W + x of the four corners
+  float w_nw, w_ne, w_sw, w_se;
+};
+
+__device__ __forceinline__ TapCorners tap_corners(const float* __restrict__ grid, int bg, int H, int W, int py, int px,
+                                                  int ty, int tx) {
+  const float2 gxy =
+      __ldg(reinterpret_cast<const float2*>(grid) + ((int64_t)bg * 3 * H + (3 * py + ty)) * (3 * W) + 3 * px + tx);
+  const float ix = unnorm_clip(gxy.x, W), iy = unnorm_clip(gxy.y, H);
+  const float fx = floorf(ix), fy = floorf(iy);
+  const int x0 = (int)fx, y0 = (int)fy;
+  const int x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
+  const float ex = __fsub_rn(__fadd_rn(fx, 1.f), ix), ey = __fsub_rn(__fadd_rn(fy, 1.f), iy);
+  const float wx = __fsub_rn(ix, fx), wy = __fsub_rn(iy, fy);
+  TapCorners c;
+  c.o_nw = y0 * W + x0;
+  c.o_ne = y0 * W + x1;
+  c.o_sw = y1 * W + x0;
+  c.o_se = y1 * W + x1;
+  c.w_nw = ex * ey;
+  c.w_ne = wx * ey;
+  c.w_sw = ex * wy;
+  c.w_se = wx * wy;
+  return c;
+}
+
+// One warp per (group g, pixel p, tap t); lanes sweep the channel pairs (2*lane, 2*lane + 1) + 64*j.  The corner
+// indices and weights are computed once per source sample and reused for every channel (they only change when the
+// flat-concat mapping crosses into another sample's planes); corner reads are coalesced over channels in the NHWC
+// staging copy and each lane writes one bf16x2 to the hi plane and one to the lo plane (128 B per warp and plane).
 __global__ void __launch_bounds__(256) sphere_pack_kernel(__nv_bfloat16* __restrict__ out, const float* __restrict__ xh,
                                                          const float* __restrict__ coords, const float* __restrict__ grid,
                                                          const float* __restrict__ in_mul, int B, int C, int nc, int H,
@@ -460,74 +499,82 @@ __global__ void __launch_bounds__(256) sphere_pack_kernel(__nv_bfloat16* __restr
   const int Ct = C + nc;
   const int HW = H * W;
   const int64_t plane_elems = (int64_t)B * HW * 9 * Cp;
-  const int64_t total = plane_elems;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    const int k = (int)(idx % Cp);
-    int64_t r = idx / Cp;
-    const int t = (int)(r % 9);
-    r /= 9;
+  const int64_t warps_total = (int64_t)B * HW * 9;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t warp_stride = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t wid = warp0; wid < warps_total; wid += warp_stride) {
+    const int t = (int)(wid % 9);
+    const int64_t r = wid / 9;
     const int p = (int)(r % HW);
     const int g = (int)(r / HW);
-    float v = 0.f;
-    if (k < Ct) {
-      // which gathered plane feeds channel k of group g
-      int bs, cs;
-      bool is_coord;
-      if (flat_concat) {
-        const int64_t flat = (int64_t)g * Ct + k;
-        if (flat < (int64_t)B * C) {
-          bs = (int)(flat / C);
-          cs = (int)(flat - (int64_t)bs * C);
-          is_coord = false;
-        } else {
-          const int64_t f2 = flat - (int64_t)B * C;
-          bs = (int)(f2 / nc);
-          cs = (int)(f2 - (int64_t)bs * nc);
-          is_coord = true;
+    const int py = p / W, px = p - py * W;
+    const int ty = t / 3, tx = t - ty * 3;
+    int cur_bs = -1;
+    TapCorners cn;
+    cn.o_nw = cn.o_ne = cn.o_sw = cn.o_se = 0;
+    cn.w_nw = cn.w_ne = cn.w_sw = cn.w_se = 0.f;
+    __nv_bfloat16* orow = out + wid * Cp;  // row (g, p), columns [t*Cp, (t+1)*Cp): wid = (g*HW + p)*9 + t
+    for (int k0 = 2 * lane; k0 < Cp; k0 += 64) {
+      float v[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int k = k0 + u;
+        float val = 0.f;
+        if (k < Ct) {
+          int bs, cs;
+          bool is_coord;
+          if (flat_concat) {
+            const int64_t flat = (int64_t)g * Ct + k;
+            if (flat < (int64_t)B * C) {
+              bs = (int)(flat / C);
+              cs = (int)(flat - (int64_t)bs * C);
+              is_coord = false;
+            } else {
+              const int64_t f2 = flat - (int64_t)B * C;
+              bs = (int)(f2 / nc);
+              cs = (int)(f2 - (int64_t)bs * nc);
+              is_coord = true;
+            }
+          } else {
+            bs = g;
+            is_coord = k >= C;
+            cs = is_coord ? k - C : k;
+          }
+          if (bs != cur_bs) {
+            cur_bs = bs;
+            cn = tap_corners(grid, grid_batch == 1 ? 0 : bs, H, W, py, px, ty, tx);
+          }
+          float a, b2, c2, d2;
+          if (!is_coord) {
+            const float* src = xh + (int64_t)bs * HW * C + cs;
+            a = __ldg(src + (int64_t)cn.o_nw * C);
+            b2 = __ldg(src + (int64_t)cn.o_ne * C);
+            c2 = __ldg(src + (int64_t)cn.o_sw * C);
+            d2 = __ldg(src + (int64_t)cn.o_se * C);
+          } else {
+            const float* src = coords + ((int64_t)bs * nc + cs) * HW;
+            a = __ldg(src + cn.o_nw);
+            b2 = __ldg(src + cn.o_ne);
+            c2 = __ldg(src + cn.o_sw);
+            d2 = __ldg(src + cn.o_se);
+          }
+          val = a * cn.w_nw + b2 * cn.w_ne + c2 * cn.w_sw + d2 * cn.w_se;
+          if (is_coord) {
+            if (cs == 0) val = tanhf(val);
+            else if (cs == 1) val = cosf(val * 3.14159274101257324f);
+            else if (cs == 2) val = sinf(val * 3.14159274101257324f);
+          }
+          if (in_mul) val *= __ldg(in_mul + (int64_t)g * Ct + k);
         }
-      } else {
-        bs = g;
-        is_coord = k >= C;
-        cs = is_coord ? k - C : k;
+        v[u] = val;
       }
-      const int py = p / W, px = p - py * W;
-      const int ty = t / 3, tx = t - ty * 3;
-      const int bg = grid_batch == 1 ? 0 : bs;
-      const float2 gxy =
-          __ldg(reinterpret_cast<const float2*>(grid) + ((int64_t)bg * 3 * H + (3 * py + ty)) * (3 * W) + 3 * px + tx);
-      const float ix = unnorm_clip(gxy.x, W), iy = unnorm_clip(gxy.y, H);
-      const float fx = floorf(ix), fy = floorf(iy);
-      const int x0 = (int)fx, y0 = (int)fy;
-      const int x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
-      const float ex = __fsub_rn(__fadd_rn(fx, 1.f), ix), ey = __fsub_rn(__fadd_rn(fy, 1.f), iy);
-      const float wx = __fsub_rn(ix, fx), wy = __fsub_rn(iy, fy);
-      float nwv, nev, swv, sev;
-      if (!is_coord) {
-        const float* src = xh + (int64_t)bs * HW * C + cs;
-        nwv = __ldg(src + (int64_t)(y0 * W + x0) * C);
-        nev = __ldg(src + (int64_t)(y0 * W + x1) * C);
-        swv = __ldg(src + (int64_t)(y1 * W + x0) * C);
-        sev = __ldg(src + (int64_t)(y1 * W + x1) * C);
-      } else {
-        const float* src = coords + ((int64_t)bs * nc + cs) * HW;
-        nwv = __ldg(src + y0 * W + x0);
-        nev = __ldg(src + y0 * W + x1);
-        swv = __ldg(src + y1 * W + x0);
-        sev = __ldg(src + y1 * W + x1);
-      }
-      v = nwv * (ex * ey) + nev * (wx * ey) + swv * (ex * wy) + sev * (wx * wy);
-      if (is_coord) {
-        if (cs == 0) v = tanhf(v);
-        else if (cs == 1) v = cosf(v * 3.14159274101257324f);
-        else if (cs == 2) v = sinf(v * 3.14159274101257324f);
-      }
-      if (in_mul) v *= __ldg(in_mul + (int64_t)g * Ct + k);
+      __nv_bfloat16 h0, l0, h1, l1;
+      split_bf16(v[0], h0, l0);
+      split_bf16(v[1], h1, l1);
+      *reinterpret_cast<__nv_bfloat162*>(orow + k0) = __halves2bfloat162(h0, h1);
+      *reinterpret_cast<__nv_bfloat162*>(orow + plane_elems + k0) = __halves2bfloat162(l0, l1);
     }
-    __nv_bfloat16 hi, lo;
-    split_bf16(v, hi, lo);
-    out[idx] = hi;
-    out[plane_elems + idx] = lo;
   }
 }
 
@@ -641,8 +688,8 @@ extern "C" int spgan_sphere_pack(uint16_t* out, const float* x_nhwc, const float
   SPGAN_CHECK_ARG(out && x_nhwc && grid, "spgan_sphere_pack: null pointer");
   SPGAN_CHECK_ARG(grid_batch == 1 || grid_batch == B, "spgan_sphere_pack: grid batch %d must be 1 or %d", grid_batch, B);
   SPGAN_CHECK_ARG((((uintptr_t)grid) & 7) == 0, "spgan_sphere_pack: grid must be 8-byte aligned");
-  const int64_t total = (int64_t)B * H * W * 9 * Cp;
-  sphere_pack_kernel<<<grid_for(total, 256, 8, 8), 256, 0, (cudaStream_t)stream>>>(
+  const int64_t warps = (int64_t)B * H * W * 9;
+  sphere_pack_kernel<<<grid_for(warps, 8, 8, 8), 256, 0, (cudaStream_t)stream>>>(
       (__nv_bfloat16*)out, x_nhwc, coords, grid, in_mul, B, C, nc, H, W, grid_batch, Cp, flat_concat);
   SPGAN_CHECK_LAUNCH("spgan_sphere_pack");
   return 0;
@@ -679,6 +726,7 @@ extern "C" int spgan_conv_gemm(const SpganConvPass* p, float* y, const uint16_t*
   gp.out_stride = p->out_stride;
   gp.out_off_y = p->out_off_y;
   gp.out_off_x = p->out_off_x;
+  gp.out_cstride = p->out_cstride ? p->out_cstride : (int64_t)p->out_H * p->out_W;
   gp.ntaps = p->ntaps;
   gp.kblocks = kp / GEMM_BLOCK_K;
   for (int t = 0; t < p->ntaps; ++t) gp.tap_off[t] = p->tap_dy[t] * p->W + p->tap_dx[t];

@@ -96,7 +96,82 @@ __global__ void __launch_bounds__(256) upfirdn2d_tiled(float* __restrict__ out, 
   }
 }
 
+// Fused tail of the upsampling StyledConv: interleave the four polyphase planes of the transposed conv on the fly,
+// 3x3 FIR, + noise + bias, leaky-ReLU * scale.  One 32x32 output tile per CTA; HBM traffic = one read of the planes
+// (+ halo) and one write of the result, instead of scatter-write + FIR read/write + activation read/write.
+__global__ void __launch_bounds__(256) upblur_act_kernel(float* __restrict__ out, const float* __restrict__ pp,
+                                                        const float* __restrict__ kernel, const float* __restrict__ noise,
+                                                        const float* __restrict__ noise_w, const float* __restrict__ bias,
+                                                        int64_t channels, int zh, int zw, int Hq, int Wq, int oh, int ow,
+                                                        int tiles_x, int tiles_y, float alpha, float scale) {
+  constexpr int K = 3, IN = TILE + K - 1;
+  __shared__ float tile[IN][IN + 1];
+  __shared__ float kf[K * K];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  if (threadIdx.x < K * K) {
+    int ky = threadIdx.x / K, kx = threadIdx.x - ky * K;
+    kf[threadIdx.x] = kernel[(K - 1 - ky) * K + (K - 1 - kx)];
+  }
+  const int tiles_per_plane = tiles_x * tiles_y;
+  const int64_t plane = blockIdx.x / tiles_per_plane;
+  const int t = blockIdx.x - (int)(plane * tiles_per_plane);
+  const int oy0 = (t / tiles_x) * TILE, ox0 = (t % tiles_x) * TILE;
+  const int64_t q = (int64_t)Hq * Wq;
+  const float* pb = pp + plane * 4 * q;
+  for (int r = ty; r < IN; r += 8) {
+    const int Yz = oy0 + r;
+    const bool row_ok = Yz < zh;
+    const float* prow = pb + (int64_t)((Yz & 1) * 2) * q + (int64_t)(Yz >> 1) * Wq;
+    for (int c = tx; c < IN; c += 32) {
+      const int Xz = ox0 + c;
+      tile[r][c] = (row_ok && Xz < zw) ? __ldcs(prow + (int64_t)(Xz & 1) * q + (Xz >> 1)) : 0.f;
+    }
+  }
+  __syncthreads();
+  float w[K * K];
+#pragma unroll
+  for (int i = 0; i < K * K; ++i) w[i] = kf[i];
+  const int64_t b = plane / channels, c = plane - b * channels;
+  const float nw = noise ? __ldg(noise_w) : 0.f;
+  const float bv = bias ? __ldg(bias + c) : 0.f;
+  const int64_t opl = (int64_t)oh * ow;
+  const int ox = ox0 + tx;
+#pragma unroll
+  for (int r = 0; r < TILE / 8; ++r) {
+    const int ly = ty + r * 8;
+    const int oy = oy0 + ly;
+    float acc = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < K; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < K; ++kx) acc += w[ky * K + kx] * tile[ly + ky][tx + kx];
+    if (oy < oh && ox < ow) {
+      float v = acc + bv;
+      if (noise) v += nw * __ldg(noise + b * opl + (int64_t)oy * ow + ox);
+      __stcs(out + plane * opl + (int64_t)oy * ow + ox, (v > 0.f ? v : v * alpha) * scale);
+    }
+  }
+}
+
 }  // namespace
+
+extern "C" int spgan_upblur_act(float* out, const float* pp, const float* kernel, const float* noise,
+                                const float* noise_w, const float* bias, int64_t batch, int64_t channels, int zh, int zw,
+                                int Hq, int Wq, float alpha, float scale, void* stream) {
+  SPGAN_CHECK_ARG(batch >= 0 && channels >= 0 && zh >= 0 && zw >= 0, "spgan_upblur_act: negative size");
+  SPGAN_CHECK_ARG(Hq * 2 >= zh && Wq * 2 >= zw, "spgan_upblur_act: polyphase planes %dx%d too small for %dx%d", Hq, Wq, zh, zw);
+  const int oh = zh - 2, ow = zw - 2;
+  if (batch * channels == 0 || oh <= 0 || ow <= 0) return 0;
+  SPGAN_CHECK_ARG(out && pp && kernel, "spgan_upblur_act: null pointer");
+  SPGAN_CHECK_ARG((noise == nullptr) == (noise_w == nullptr), "spgan_upblur_act: noise and noise_w go together");
+  const int tiles_x = (ow + TILE - 1) / TILE, tiles_y = (oh + TILE - 1) / TILE;
+  const int64_t blocks = batch * channels * tiles_x * tiles_y;
+  SPGAN_CHECK_ARG(blocks <= 2147483647LL, "spgan_upblur_act: too many tiles");
+  upblur_act_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(out, pp, kernel, noise, noise_w, bias, channels, zh,
+                                                                       zw, Hq, Wq, oh, ow, tiles_x, tiles_y, alpha, scale);
+  SPGAN_CHECK_LAUNCH("spgan_upblur_act");
+  return 0;
+}
 
 extern "C" int spgan_upfirdn2d(float* out, const float* x, const float* kernel, int64_t planes, int in_h, int in_w,
                                int kh, int kw, int up_x, int up_y, int down_x, int down_y, int pad_x0, int pad_x1,

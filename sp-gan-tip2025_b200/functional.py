@@ -165,6 +165,24 @@ def noise_bias_act(x, noise, noise_weight, bias, negative_slope=0.2, scale=2 ** 
     return out
 
 
+def upblur_act(pp, kernel, out_hw, noise, noise_weight, bias, negative_slope=0.2, scale=2 ** 0.5):
+    """Fused tail of the upsampling StyledConv on polyphase planes pp (B, C, 4, Hq, Wq) -> (B, C, zh-2, zw-2):
+    interleave + 3x3 FIR (Blur, pad 0) + noise + bias + leaky-ReLU (see spgan_upblur_act).  (zh, zw) = out_hw."""
+    B, C, _, Hq, Wq = pp.shape
+    zh, zw = out_hw
+    out = torch.empty((B, C, zh - 2, zw - 2), device=pp.device, dtype=torch.float32)
+    nz = _f32c(noise, "upblur_act") if noise is not None else None
+    if nz is not None and nz.numel() != B * (zh - 2) * (zw - 2):
+        raise RuntimeError("upblur_act: noise must have shape (B, 1, %d, %d)" % (zh - 2, zw - 2))
+    if tuple(kernel.shape) != (3, 3):
+        raise RuntimeError("upblur_act: only the 3x3 blur kernel is fused")
+    with torch.cuda.device(pp.device):
+        lib.call("spgan_upblur_act", _ptr(out), _ptr(pp), _ptr(_f32c(kernel, "upblur_act")), _ptr(nz),
+                 _ptr(noise_weight) if nz is not None else _ptr(None), _ptr(bias), B, C, zh, zw, Hq, Wq,
+                 float(negative_slope), float(scale), _stream(pp))
+    return out
+
+
 # =================================================================================================== K2/K3 upfirdn2d
 def _upfirdn2d_raw(x4, kernel, up_x, up_y, down_x, down_y, px0, px1, py0, py1):
     """x4: (planes..., H, W) contiguous; returns (planes, out_h, out_w)."""
@@ -356,8 +374,9 @@ def plan_passes(geom, adjoint, in_hw, out_hw):
     return passes, covers
 
 
-def _fill_pass(p, B, Cin, H, W, Cout, out_H, out_W, ws_o, ws_c, out_scale, act, alpha, gain, precision):
+def _fill_pass(p, B, Cin, H, W, Cout, out_H, out_W, ws_o, ws_c, out_scale, act, alpha, gain, precision, cstride=0):
     cp = ConvPass()
+    cp.out_cstride = cstride
     cp.B, cp.Cin, cp.H, cp.W = B, Cin, H, W
     cp.Cout, cp.out_H, cp.out_W = Cout, out_H, out_W
     cp.My, cp.Mx = p["My"], p["Mx"]
@@ -413,7 +432,7 @@ def _tensor_path_ok(passes, Cin, Cout, precision):
 
 
 def conv_apply(x, w, geom, adjoint=False, out_hw=None, in_mul=None, out_mul=None, out_scale=1.0, noise=None,
-               noise_w=None, bias=None, act=None, residual=None, precision=None):
+               noise_w=None, bias=None, act=None, residual=None, precision=None, polyphase=False):
     """y = [act]( out_scale * out_mul[b,o] * L_w(in_mul[b,c] * x) + noise_w*noise + bias ) + residual, no autograd.
 
     L_w is the conv described by `geom` (adjoint=False) or its adjoint / data gradient (adjoint=True, `out_hw`
@@ -437,9 +456,20 @@ def conv_apply(x, w, geom, adjoint=False, out_hw=None, in_mul=None, out_mul=None
         oh, ow = out_hw
     precision = _PRECISION if precision is None else precision
     passes, covers = plan_passes(geom, adjoint, (H, W), (oh, ow))
-    y = (torch.empty if covers else torch.zeros)((B, Cout, max(oh, 0), max(ow, 0)), device=x.device, dtype=torch.float32)
-    if y.numel() == 0 or not passes:
-        return y
+    if polyphase:
+        # parity passes write dense planes (B, Cout, s*s, Hq, Wq), plane (off_y * s + off_x), instead of scattering
+        # with stride s into the interleaved image: coalesced epilogue stores; the consumer interleaves on the fly
+        sp = geom.stride
+        if not (geom.transposed and not adjoint and sp == 2) or any(t is not None for t in (noise, bias, act, residual)):
+            raise RuntimeError("conv: polyphase output is for the bare stride-2 transposed conv only")
+        Hq, Wq = _ceil_div(oh, sp), _ceil_div(ow, sp)
+        y = (torch.empty if covers else torch.zeros)((B, Cout, sp * sp, Hq, Wq), device=x.device, dtype=torch.float32)
+        if y.numel() == 0 or not passes:
+            return y
+    else:
+        y = (torch.empty if covers else torch.zeros)((B, Cout, max(oh, 0), max(ow, 0)), device=x.device, dtype=torch.float32)
+        if y.numel() == 0 or not passes:
+            return y
     a, g = (act if act is not None else (0.0, 1.0))
     act_on = 1 if act is not None else 0
     im = _f32c(in_mul, "conv") if in_mul is not None else None
@@ -451,6 +481,15 @@ def conv_apply(x, w, geom, adjoint=False, out_hw=None, in_mul=None, out_mul=None
     if rs is not None and rs.shape != y.shape:
         raise RuntimeError("conv: residual shape %s != output shape %s" % (tuple(rs.shape), tuple(y.shape)))
     st = _stream(x)
+
+    def target(p):
+        """(pass geometry, output pointer, out_H, out_W, channel stride) for the dense or the polyphase layout."""
+        if not polyphase:
+            return p, _ptr(y), oh, ow, 0
+        plane = (p["off_y"] * geom.stride + p["off_x"]) * Hq * Wq
+        q = dict(p, out_stride=1, off_y=0, off_x=0)
+        return q, ctypes.c_void_p(y.data_ptr() + 4 * plane), Hq, Wq, geom.stride * geom.stride * Hq * Wq
+
     with torch.cuda.device(x.device):
         if _tensor_path_ok(passes, Cin, Cout, precision):
             # one packed activation shared by all passes: pads cover every pass's tap reach
@@ -466,16 +505,18 @@ def conv_apply(x, w, geom, adjoint=False, out_hw=None, in_mul=None, out_mul=None
             a_packed = torch.empty((2, rows, Cp), device=x.device, dtype=torch.bfloat16)
             lib.call("spgan_pack_act", _ptr(a_packed), _ptr(x), _ptr(im), B, Cin, H, W, Cp, pt, pl, Hl, Wl, st)
             for p in passes:
-                shifted = dict(p, taps=[(dy + pt, dx + pl, wi) for dy, dx, wi in p["taps"]])
-                cp = _fill_pass(shifted, B, Cin, Hl, Wl, Cout, oh, ow, ws_o, ws_c, out_scale, act_on, a, g, precision)
+                q, yptr, o_h, o_w, cst = target(p)
+                shifted = dict(q, taps=[(dy + pt, dx + pl, wi) for dy, dx, wi in p["taps"]])
+                cp = _fill_pass(shifted, B, Cin, Hl, Wl, Cout, o_h, o_w, ws_o, ws_c, out_scale, act_on, a, g, precision, cst)
                 wp = _packed_weight(w, Cout, Cin, ws_o, ws_c, [t[2] for t in p["taps"]], Cp, False)
                 valid = min(p["My"], _ceil_div(oh - p["off_y"], p["out_stride"])) * min(p["Mx"], _ceil_div(ow - p["off_x"], p["out_stride"]))
-                _gemm_call(2.0 * B * valid * Cout * Cin * len(p["taps"]), ctypes.byref(cp), _ptr(y), _ptr(a_packed), rows,
+                _gemm_call(2.0 * B * valid * Cout * Cin * len(p["taps"]), ctypes.byref(cp), yptr, _ptr(a_packed), rows,
                            Cp, _ptr(wp), _ptr(om), _ptr(nz), _ptr(nwt), _ptr(bs), _ptr(rs), st)
         else:
             for p in passes:
-                cp = _fill_pass(p, B, Cin, H, W, Cout, oh, ow, ws_o, ws_c, out_scale, act_on, a, g, 0)
-                lib.call("spgan_conv_pass", ctypes.byref(cp), _ptr(y), _ptr(x), _ptr(w), _ptr(im), _ptr(om), _ptr(nz),
+                q, yptr, o_h, o_w, cst = target(p)
+                cp = _fill_pass(q, B, Cin, H, W, Cout, o_h, o_w, ws_o, ws_c, out_scale, act_on, a, g, 0, cst)
+                lib.call("spgan_conv_pass", ctypes.byref(cp), yptr, _ptr(x), _ptr(w), _ptr(im), _ptr(om), _ptr(nz),
                          _ptr(nwt), _ptr(bs), _ptr(rs), st)
     return y
 

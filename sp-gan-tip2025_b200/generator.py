@@ -244,7 +244,9 @@ class Generator(nn.Module):
         self.texture_synthesizer = TextureSynthesizer(self.config)
 
     def forward(self, global_latent, local_latent, coords, coords_partial, noises=None, inject_index=None,
-                test_ids=None, return_latents=False):
+                test_ids=None, return_latents=False, styles=None):
+        """`styles` (B, 9, 512): optional precomputed w-space styles (`texture_synthesizer.styles_for`); the panorama
+        loop maps the global latent once per panorama batch instead of once per patch."""
         if global_latent.dim() == 2:
             global_latent = torch.stack([global_latent, global_latent], 1)
         ts = self.texture_synthesizer
@@ -253,7 +255,8 @@ class Generator(nn.Module):
                 inject_index = random.randint(1, ts.n_latent - 1)
         structure, _ = self.structure_synthesizer(global_latent[:, 0], local_latent, coords, coords_partial,
                                                   test_ids=test_ids)
-        styles = ts.styles_for(global_latent, inject_index)
+        if styles is None:
+            styles = ts.styles_for(global_latent, inject_index)
         img, _ = ts(styles, structure, coords_partial, noises=noises, test_ids=test_ids)
         if return_latents:
             return img, styles, structure

@@ -30,6 +30,7 @@ class ConvPass(ctypes.Structure):
         ("act", ctypes.c_int32),
         ("act_alpha", ctypes.c_float), ("act_gain", ctypes.c_float),
         ("precision", ctypes.c_int32),
+        ("out_cstride", ctypes.c_int64),
     ]
 
 
@@ -43,6 +44,7 @@ SIGNATURES = {
     "spgan_bias_act": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_f32, c_f32, c_vp]),
     "spgan_bias_act_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_f32, c_f32, c_vp]),
     "spgan_noise_bias_act": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_f32, c_f32, c_vp]),
+    "spgan_upblur_act": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_int, c_int, c_int, c_int, c_f32, c_f32, c_vp]),
     "spgan_upfirdn2d": (c_int, [c_vp, c_vp, c_vp, c_i64] + [c_int] * 12 + [c_vp]),
     "spgan_sphere_gather": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_i64, c_i64, c_int, c_vp]),
     "spgan_sphere_gather_indices": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_vp]),

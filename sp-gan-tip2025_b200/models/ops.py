@@ -373,16 +373,29 @@ class ModulatedConv2d(nn.Module):
 
     def _mod_demod(self, style, batch):
         """s = modulation(style) (B, Cin); d = rsqrt(scale^2 sum_c s^2 sum_t w^2 + eps) (B, Cout) or None
-        (models/ops.py:598-604), with autograd when needed."""
-        s = self.modulation(style).view(batch, self.in_channel)
+        (models/ops.py:598-604), with autograd when needed.
+
+        Under no_grad the pair is memoised per module for as long as the SAME style storage (kept alive by the cache,
+        so its address cannot be recycled) and the same parameter versions are presented: a panorama runs 60 patch
+        calls with one global latent, and the reference recomputes these 20 small GEMMs in every call."""
         w = self.weight[0]
-        d = None
-        if self.demodulate:
-            if _grad_needed(s, self.weight):
+        if _grad_needed(style, self.weight, self.modulation.weight, self.modulation.bias):
+            s = self.modulation(style).view(batch, self.in_channel)
+            d = None
+            if self.demodulate:
                 wsq = (w * w).sum(dim=(2, 3))
                 d = torch.rsqrt(SF._LinearFn.apply(s * s, wsq, None, self.scale * self.scale, 1.0) + 1e-8)
-            else:
-                d = SF.demod_coefficients(w, s, self.scale, 1e-8)
+            return s, w, d
+        key = (style.data_ptr(), style._version, tuple(style.shape), tuple(style.stride()), str(style.device),
+               self.weight._version, self.modulation.weight._version,
+               self.modulation.bias._version if self.modulation.bias is not None else -1,
+               self.weight.data_ptr(), self.modulation.weight.data_ptr())
+        cached = getattr(self, "_md_cache", None)
+        if cached is not None and cached[0] == key:
+            return cached[2], w, cached[3]
+        s = self.modulation(style).view(batch, self.in_channel)
+        d = SF.demod_coefficients(w, s, self.scale, 1e-8) if self.demodulate else None
+        object.__setattr__(self, "_md_cache", (key, style, s, d))
         return s, w, d
 
     def forward(self, input, style, coords=None, calc_flops=False):
@@ -407,7 +420,13 @@ class ModulatedConv2d(nn.Module):
         batch = input.shape[0]
         s, w, d = self._mod_demod(style, batch)
         if self.upsample:
-            out = SF.conv_apply(input, w, self._geom(), in_mul=s, out_mul=d, out_scale=self.scale)
+            geom = self._geom()
+            if tuple(self.blur.kernel.shape) == (3, 3) and self.blur.zero_pad == (0, 0) and not self.blur.use_replicate_pad:
+                # polyphase transposed conv -> one fused interleave + FIR + noise + bias + leaky-ReLU kernel
+                pp = SF.conv_apply(input, w, geom, in_mul=s, out_mul=d, out_scale=self.scale, polyphase=True)
+                return SF.upblur_act(pp, self.blur.kernel, geom.out_size(input.shape[2], input.shape[3]), noise,
+                                     noise_weight, act_bias, act[0], act[1])
+            out = SF.conv_apply(input, w, geom, in_mul=s, out_mul=d, out_scale=self.scale)
             out = self.blur(out)
             return SF.noise_bias_act(out, noise, noise_weight, act_bias, act[0], act[1])
         return SF.conv_apply(input, w, self._geom(), in_mul=s, out_mul=d, out_scale=self.scale, noise=noise,

@@ -133,6 +133,11 @@ def generate(gen, pl, global_latent, local_latent, noises, meta=None, only=None)
         meta = torch.zeros(B, 3, pl["meta_h"], pl["meta_w"], device=dev)
     coords_full = meta_coords(lat_h, lat_w, dev).unsqueeze(0).expand(B, -1, -1, -1)
     P = pl["patch"]
+    if global_latent.dim() == 2:
+        global_latent = torch.stack([global_latent, global_latent], 1)
+    # the mapping network and every layer's modulation / demodulation depend only on the global latent: computed once
+    # per panorama batch (the per-layer (s, d) pairs are memoised inside ModulatedConv2d as long as `styles` lives)
+    styles = gen.texture_synthesizer.styles_for(global_latent)
     for it, (ix, iy) in enumerate(positions(pl)):
         if only is not None and (ix, iy) not in only:
             continue
@@ -144,7 +149,7 @@ def generate(gen, pl, global_latent, local_latent, noises, meta=None, only=None)
             fx, fy = ix * pl["outfeat_step"][l], iy * pl["outfeat_step"][l]
             s = pl["out_sizes"][l]
             cur_noises.append(circular_slice(noises[l], pl["noise_w"][l], fx, fx + s, fy, fy + s).contiguous())
-        patch = gen(global_latent, cur_lat, cur_coords, cp, noises=cur_noises)
+        patch = gen(global_latent, cur_lat, cur_coords, cp, noises=cur_noises, styles=styles)
         px, py = ix * pl["pix_step"], iy * pl["pix_step"]
         circular_assign(meta, pl["meta_w"], px, px + P, py, py + P, patch)
     return meta

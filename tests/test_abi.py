@@ -41,7 +41,7 @@ def test_conv_pass_struct_layout():
     n = lib.MAX_TAPS
     expect = 4 * 14 + 4 * 3 * n  # 14 leading int32 + three tap arrays
     expect = (expect + 7) // 8 * 8 + 16 + 4 * 5  # two int64 strides (8-aligned), out_scale, act, alpha, gain, precision
-    expect = (expect + 7) // 8 * 8
+    expect = (expect + 7) // 8 * 8 + 8  # out_cstride (8-aligned)
     assert ctypes.sizeof(lib.ConvPass) == expect
 
 

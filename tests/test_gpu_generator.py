@@ -65,7 +65,8 @@ def test_panorama_384_golden_strip(gen):
     assert img.shape == (1, 3, pl["meta_h"], pl["meta_w"])
     assert K.rel_err(img[:, :, 250:290, :], ref["strip"]) < 5e-4
     assert K.rel_err(img[:, :, :, 740:768], ref["col_seam"]) < 5e-4  # longitude seam columns
-    assert abs(img.mean() - float(ref["mean"])) < 1e-3 and abs(img.std() - float(ref["std"])) < 1e-3
+    assert abs(img.mean() - float(ref["mean"])) < 1e-3 * float(ref["std"])
+    assert abs(img.std() - float(ref["std"])) < 1e-3 * float(ref["std"])
 
 
 def test_panorama_sharded_positions_assemble_identically(gen):
@@ -89,3 +90,21 @@ def test_panorama_sharded_positions_assemble_identically(gen):
         patch = panorama.circular_slice(src, pl["meta_w"], px, px + 101, py, py + 101)
         panorama.circular_assign(merged, pl["meta_w"], px, px + 101, py, py + 101, patch)
     assert torch.equal(merged, full)
+
+
+def test_style_memoisation_tracks_latent_updates(gen):
+    """The per-layer (modulation, demodulation) memo must not survive an in-place change of the global latent."""
+    gl, lat, coords, cp, noises = K.generator_case("b1_p27", 1, 2, 7)
+    gl, lat, coords = gl.cuda(), lat.cuda(), coords.cuda()
+    noises = [n.cuda() for n in noises]
+    with torch.no_grad():
+        styles = gen.texture_synthesizer.styles_for(gl)
+        a1 = gen(gl, lat, coords, cp, noises=noises, styles=styles)
+        a2 = gen(gl, lat, coords, cp, noises=noises, styles=styles)  # memo hit
+        assert torch.equal(a1, a2)
+        gl.mul_(0.5)
+        styles.copy_(gen.texture_synthesizer.styles_for(gl))  # same storage, new contents
+        b1 = gen(gl, lat, coords, cp, noises=noises, styles=styles)
+        b2 = gen(gl.clone(), lat, coords, cp, noises=noises)  # fresh tensors, no memo
+    assert K.rel_err(K.t2n(b1), K.t2n(b2)) < 1e-6
+    assert K.rel_err(K.t2n(b1), K.t2n(a1)) > 1e-3

@@ -269,6 +269,56 @@ def test_conv_tcgen05_matches_simt_at_layer_size_and_is_linear(dev):
     assert K.rel_err(K.t2n(y1[:1]), K.t2n(ys)) < 1e-4
 
 
+@pytest.mark.parametrize("precision", [0, 1])
+def test_polyphase_transposed_conv_and_fused_upblur(dev, precision):
+    """Upsampling StyledConv tail: polyphase convT + fused interleave/FIR/noise/bias/act == convT -> Blur -> noise -> act."""
+    from spgan_b200.functional import ConvGeom
+    geom = ConvGeom(3, 3, stride=2, transposed=True, crop=1)
+    B, C, Oc, H = 3, 70, 40, 11
+    x = synth.randn_t(11, "px", (B, C, H, H))
+    w = synth.randn_t(11, "pw", (Oc, C, 3, 3), 0.2)
+    im = synth.randn_t(11, "pim", (B, C), 0.3, 1.0)
+    om = synth.randn_t(11, "pom", (B, Oc), 0.3, 1.0)
+    nz = synth.randn_t(11, "pnz", (B, 1, 2 * H - 3, 2 * H - 3))
+    nw = torch.tensor([0.3])
+    bias = synth.randn_t(11, "pb", (Oc,))
+    k = torch.from_numpy(O.make_kernel([1, 2, 1]) * 4)
+    z = _ref_conv(x, w, geom, False, None, im, om, 0.11).float()
+    want = O.fused_leaky_relu(O.upfirdn2d(z.numpy(), k.numpy()) + (nw * nz).numpy(), bias.numpy())
+    pp = SF().conv_apply(x.to(dev), w.to(dev), geom, in_mul=im.to(dev), out_mul=om.to(dev), out_scale=0.11,
+                         precision=precision, polyphase=True)
+    assert pp.shape == (B, Oc, 4, H, H)
+    zz = torch.zeros(B, Oc, 2 * H - 1, 2 * H - 1, device=dev)
+    for a in range(2):
+        for b in range(2):
+            sub = zz[:, :, a::2, b::2]
+            sub.copy_(pp[:, :, a * 2 + b, :sub.shape[2], :sub.shape[3]])
+    assert K.rel_err(K.t2n(zz), z.numpy()) < TOL[precision]
+    got = SF().upblur_act(pp, k.to(dev), (2 * H - 1, 2 * H - 1), nz.to(dev), nw.to(dev), bias.to(dev))
+    assert K.rel_err(K.t2n(got), want) < TOL[precision]
+
+
+def test_conv_small_cout_paths(dev):
+    """ToRGB-shaped (512 -> 3, 1x1, every epilogue term) and RGB-sphere-shaped (3 -> 3, 3x3 stride 3) convs."""
+    from spgan_b200.functional import ConvGeom
+    B, C, H = 3, 512, 29
+    x = synth.randn_t(12, "sx", (B, C, H, H))
+    w = synth.randn_t(12, "sw", (3, C, 1, 1))
+    im = synth.randn_t(12, "sim", (B, C), 0.3, 1.0)
+    bias = synth.randn_t(12, "sb", (3,))
+    res = synth.randn_t(12, "sr", (B, 3, H, H))
+    want = _ref_conv(x, w, ConvGeom(1, 1), False, None, im, None, 0.044) + bias.double()[None, :, None, None] + res.double()
+    got = SF().conv_apply(x.to(dev), w.to(dev), ConvGeom(1, 1), in_mul=im.to(dev), out_scale=0.044, bias=bias.to(dev),
+                          residual=res.to(dev))
+    assert K.rel_err(K.t2n(got), want.numpy()) < 1e-5
+    x2 = synth.randn_t(12, "sx2", (2, 3, 51, 51))
+    w2 = synth.randn_t(12, "sw2", (3, 3, 3, 3))
+    g3 = ConvGeom(3, 3, stride=3)
+    want = F.leaky_relu(_ref_conv(x2, w2, g3, False, None, None, None, 0.19) + bias.double()[None, :, None, None], 0.01)
+    got = SF().conv_apply(x2.to(dev), w2.to(dev), g3, out_scale=0.19, bias=bias.to(dev), act=(0.01, 1.0))
+    assert K.rel_err(K.t2n(got), want.numpy()) < 1e-5
+
+
 # ---------------------------------------------------------------------------------------------- modulated conv modules
 def _modconv_module(name, cin, cout, k, demod, up, dev):
     from spgan_b200.models import ops
