@@ -160,11 +160,13 @@ int spgan_nchw_to_nhwc(float* out, const float* x, int B, int C, int H, int W, v
  *   (x_nhwc, (B, H, W, C) fp32) and of the raw coords ((B, 3, H, W) fp32, may be NULL) at the 3x3 tap grid
  *   ((Bg, 3H, 3W, 2), Bg in {1, B}), coordinate encoding tanh / cos(pi.) / sin(pi.), style modulation
  *   in_mul (B, C + nc) (may be NULL), bf16 hi/lo split -> out [2][B*H*W][9*Cp], k = tap*Cp + channel.
+ *   chan_map (B, Cp) uint32 on the device says which gathered plane feeds channel k of group g:
+ *   bit 31 = coordinate plane, bits [15,31) = source sample, bits [0,15) = source channel, 0xFFFFFFFF = zero padding.
  *   The reference concatenates the gathered tensors as flat (1, B*C) ++ (1, B*nc) channel lists and then convolves
- *   with groups = B, so group g reads flat channels [g*(C+nc), (g+1)*(C+nc)) (for B > 1 that mixes samples);
- *   flat_concat != 0 reproduces exactly that mapping, 0 gives the per-sample concatenation. */
+ *   with groups = B, so group g reads flat channels [g*(C+nc), (g+1)*(C+nc)) (for B > 1 that mixes samples); the host
+ *   encodes exactly that mapping (or the per-sample concatenation) in the table. */
 int spgan_sphere_pack(uint16_t* out, const float* x_nhwc, const float* coords, const float* grid, const float* in_mul,
-                      int B, int C, int H, int W, int grid_batch, int Cp, int flat_concat, void* stream);
+                      const uint32_t* chan_map, int B, int C, int H, int W, int grid_batch, int Cp, void* stream);
 /* spgan_conv_gemm: the tcgen05 kernel.  `p` is a conv pass whose (H, W) are the LATTICE dims (Hl, Wl) of the packed
  *   activation, Cin is ignored (K per tap = kp, a multiple of 64), in_stride must be 1, tap_w is ignored (the packed
  *   weight is already in tap order) and precision must be 1 or 2.  a_packed [2][a_rows][kp], w_packed

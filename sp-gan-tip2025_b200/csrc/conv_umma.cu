@@ -488,14 +488,16 @@ __device__ __forceinline__ TapCorners tap_corners(const float* __restrict__ grid
   return c;
 }
 
-// One warp per (group g, pixel p, tap t); lanes sweep the channel pairs (2*lane, 2*lane + 1) + 64*j.  The corner
-// indices and weights are computed once per source sample and reused for every channel (they only change when the
-// flat-concat mapping crosses into another sample's planes); corner reads are coalesced over channels in the NHWC
-// staging copy and each lane writes one bf16x2 to the hi plane and one to the lo plane (128 B per warp and plane).
+// One warp per (group g, pixel p, tap t); lanes sweep the channel pairs (2*lane, 2*lane + 1) + 64*j.  Which gathered
+// plane feeds channel k of group g comes from the host-built table chan_map[g][k] (the reference's flat-concat
+// quirk lives there), so the inner loop has no integer divisions.  The corner indices and weights are computed once
+// per source sample; corner reads are coalesced over channels in the NHWC staging copy and each lane writes one bf16x2
+// to the hi plane and one to the lo plane (128 B per warp and plane).
 __global__ void __launch_bounds__(256) sphere_pack_kernel(__nv_bfloat16* __restrict__ out, const float* __restrict__ xh,
                                                          const float* __restrict__ coords, const float* __restrict__ grid,
-                                                         const float* __restrict__ in_mul, int B, int C, int nc, int H,
-                                                         int W, int grid_batch, int Cp, int flat_concat) {
+                                                         const float* __restrict__ in_mul,
+                                                         const uint32_t* __restrict__ chan_map, int B, int C, int nc,
+                                                         int H, int W, int grid_batch, int Cp) {
   const int Ct = C + nc;
   const int HW = H * W;
   const int64_t plane_elems = (int64_t)B * HW * 9 * Cp;
@@ -515,32 +517,19 @@ __global__ void __launch_bounds__(256) sphere_pack_kernel(__nv_bfloat16* __restr
     cn.o_nw = cn.o_ne = cn.o_sw = cn.o_se = 0;
     cn.w_nw = cn.w_ne = cn.w_sw = cn.w_se = 0.f;
     __nv_bfloat16* orow = out + wid * Cp;  // row (g, p), columns [t*Cp, (t+1)*Cp): wid = (g*HW + p)*9 + t
+    const uint32_t* mrow = chan_map + (int64_t)g * Cp;
+    const float* mulrow = in_mul ? in_mul + (int64_t)g * Ct : nullptr;
     for (int k0 = 2 * lane; k0 < Cp; k0 += 64) {
+      const uint2 mm = __ldg(reinterpret_cast<const uint2*>(mrow + k0));
       float v[2];
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
-        const int k = k0 + u;
+        const uint32_t m = u ? mm.y : mm.x;
         float val = 0.f;
-        if (k < Ct) {
-          int bs, cs;
-          bool is_coord;
-          if (flat_concat) {
-            const int64_t flat = (int64_t)g * Ct + k;
-            if (flat < (int64_t)B * C) {
-              bs = (int)(flat / C);
-              cs = (int)(flat - (int64_t)bs * C);
-              is_coord = false;
-            } else {
-              const int64_t f2 = flat - (int64_t)B * C;
-              bs = (int)(f2 / nc);
-              cs = (int)(f2 - (int64_t)bs * nc);
-              is_coord = true;
-            }
-          } else {
-            bs = g;
-            is_coord = k >= C;
-            cs = is_coord ? k - C : k;
-          }
+        if (m != 0xFFFFFFFFu) {
+          const int bs = (int)((m >> 15) & 0xFFFFu);
+          const int cs = (int)(m & 0x7FFFu);
+          const bool is_coord = (m >> 31) != 0;
           if (bs != cur_bs) {
             cur_bs = bs;
             cn = tap_corners(grid, grid_batch == 1 ? 0 : bs, H, W, py, px, ty, tx);
@@ -565,7 +554,7 @@ __global__ void __launch_bounds__(256) sphere_pack_kernel(__nv_bfloat16* __restr
             else if (cs == 1) val = cosf(val * 3.14159274101257324f);
             else if (cs == 2) val = sinf(val * 3.14159274101257324f);
           }
-          if (in_mul) val *= __ldg(in_mul + (int64_t)g * Ct + k);
+          if (mulrow) val *= __ldg(mulrow + k0 + u);
         }
         v[u] = val;
       }
@@ -679,18 +668,20 @@ extern "C" int spgan_nchw_to_nhwc(float* out, const float* x, int B, int C, int 
 }
 
 extern "C" int spgan_sphere_pack(uint16_t* out, const float* x_nhwc, const float* coords, const float* grid,
-                                 const float* in_mul, int B, int C, int H, int W, int grid_batch, int Cp,
-                                 int flat_concat, void* stream) {
+                                 const float* in_mul, const uint32_t* chan_map, int B, int C, int H, int W,
+                                 int grid_batch, int Cp, void* stream) {
   SPGAN_CHECK_ARG(B >= 0 && C >= 0 && H >= 0 && W >= 0, "spgan_sphere_pack: negative size");
   const int nc = coords ? 3 : 0;
   SPGAN_CHECK_ARG(Cp >= C + nc && Cp % 64 == 0, "spgan_sphere_pack: Cp=%d must be a multiple of 64 and >= %d", Cp, C + nc);
   if (B == 0 || H == 0 || W == 0) return 0;
-  SPGAN_CHECK_ARG(out && x_nhwc && grid, "spgan_sphere_pack: null pointer");
+  SPGAN_CHECK_ARG(out && x_nhwc && grid && chan_map, "spgan_sphere_pack: null pointer");
+  SPGAN_CHECK_ARG(B <= 65535 && C <= 32767, "spgan_sphere_pack: B=%d / C=%d exceed the channel-map encoding", B, C);
   SPGAN_CHECK_ARG(grid_batch == 1 || grid_batch == B, "spgan_sphere_pack: grid batch %d must be 1 or %d", grid_batch, B);
-  SPGAN_CHECK_ARG((((uintptr_t)grid) & 7) == 0, "spgan_sphere_pack: grid must be 8-byte aligned");
+  SPGAN_CHECK_ARG((((uintptr_t)grid) & 7) == 0 && (((uintptr_t)chan_map) & 7) == 0,
+                  "spgan_sphere_pack: grid and chan_map must be 8-byte aligned");
   const int64_t warps = (int64_t)B * H * W * 9;
   sphere_pack_kernel<<<grid_for(warps, 8, 8, 8), 256, 0, (cudaStream_t)stream>>>(
-      (__nv_bfloat16*)out, x_nhwc, coords, grid, in_mul, B, C, nc, H, W, grid_batch, Cp, flat_concat);
+      (__nv_bfloat16*)out, x_nhwc, coords, grid, in_mul, chan_map, B, C, nc, H, W, grid_batch, Cp);
   SPGAN_CHECK_LAUNCH("spgan_sphere_pack");
   return 0;
 }

@@ -49,7 +49,11 @@ __global__ void __launch_bounds__(256) upfirdn2d_generic(float* __restrict__ out
   }
 }
 
-constexpr int TILE = 32;
+// Tiled FIR kernels: 64x64 output tile per CTA (256 threads as 64 columns x 4 row groups, 16 rows per thread).
+// A CTA's lifetime is one global-load latency + one store; the tile size is what keeps enough bytes in flight per SM
+// (8 resident CTAs x ~17 KB) for the kernel to sit on the HBM roofline rather than on the load latency.
+constexpr int TILE = 64;
+constexpr int TROWS = 4;  // thread rows
 
 template <int K>
 __global__ void __launch_bounds__(256) upfirdn2d_tiled(float* __restrict__ out, const float* __restrict__ x,
@@ -58,7 +62,7 @@ __global__ void __launch_bounds__(256) upfirdn2d_tiled(float* __restrict__ out, 
   constexpr int IN = TILE + K - 1;
   __shared__ float tile[IN][IN + 1];
   __shared__ float kf[K * K];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 64 x 4
   if (threadIdx.x < K * K) {
     int ky = threadIdx.x / K, kx = threadIdx.x - ky * K;
     kf[threadIdx.x] = kernel[(K - 1 - ky) * K + (K - 1 - kx)];
@@ -69,12 +73,13 @@ __global__ void __launch_bounds__(256) upfirdn2d_tiled(float* __restrict__ out, 
   const int oy0 = (t / tiles_x) * TILE, ox0 = (t % tiles_x) * TILE;
   const float* xp = x + plane * (int64_t)p.in_h * p.in_w;
   const int iy0 = oy0 - p.pad_y0, ix0 = ox0 - p.pad_x0;
-  for (int r = ty; r < IN; r += 8) {
+  const int rows_needed = min(IN, p.out_h - oy0 + K - 1);
+  for (int r = ty; r < rows_needed; r += TROWS) {
     const int iy = iy0 + r;
     const bool row_ok = iy >= 0 && iy < p.in_h;
-    for (int c = tx; c < IN; c += 32) {
+    for (int c = tx; c < IN; c += 64) {
       const int ix = ix0 + c;
-      tile[r][c] = (row_ok && ix >= 0 && ix < p.in_w) ? __ldg(xp + (int64_t)iy * p.in_w + ix) : 0.f;
+      tile[r][c] = (row_ok && ix >= 0 && ix < p.in_w) ? __ldcs(xp + (int64_t)iy * p.in_w + ix) : 0.f;
     }
   }
   __syncthreads();
@@ -83,22 +88,24 @@ __global__ void __launch_bounds__(256) upfirdn2d_tiled(float* __restrict__ out, 
   for (int i = 0; i < K * K; ++i) w[i] = kf[i];
   float* op = out + plane * (int64_t)p.out_h * p.out_w;
   const int ox = ox0 + tx;
-#pragma unroll
-  for (int r = 0; r < TILE / 8; ++r) {
-    const int ly = ty + r * 8;
+  if (ox >= p.out_w) return;
+#pragma unroll 4
+  for (int r = 0; r < TILE / TROWS; ++r) {
+    const int ly = ty + r * TROWS;
     const int oy = oy0 + ly;
+    if (oy >= p.out_h) break;
     float acc = 0.f;
 #pragma unroll
     for (int ky = 0; ky < K; ++ky)
 #pragma unroll
       for (int kx = 0; kx < K; ++kx) acc += w[ky * K + kx] * tile[ly + ky][tx + kx];
-    if (oy < p.out_h && ox < p.out_w) op[(int64_t)oy * p.out_w + ox] = acc;
+    __stcs(op + (int64_t)oy * p.out_w + ox, acc);
   }
 }
 
 // Fused tail of the upsampling StyledConv: interleave the four polyphase planes of the transposed conv on the fly,
-// 3x3 FIR, + noise + bias, leaky-ReLU * scale.  One 32x32 output tile per CTA; HBM traffic = one read of the planes
-// (+ halo) and one write of the result, instead of scatter-write + FIR read/write + activation read/write.
+// 3x3 FIR, + noise + bias, leaky-ReLU * scale.  HBM traffic = one read of the planes (+ halo) and one write of the
+// result, instead of scatter-write + FIR read/write + activation read/write.
 __global__ void __launch_bounds__(256) upblur_act_kernel(float* __restrict__ out, const float* __restrict__ pp,
                                                         const float* __restrict__ kernel, const float* __restrict__ noise,
                                                         const float* __restrict__ noise_w, const float* __restrict__ bias,
@@ -107,7 +114,7 @@ __global__ void __launch_bounds__(256) upblur_act_kernel(float* __restrict__ out
   constexpr int K = 3, IN = TILE + K - 1;
   __shared__ float tile[IN][IN + 1];
   __shared__ float kf[K * K];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
   if (threadIdx.x < K * K) {
     int ky = threadIdx.x / K, kx = threadIdx.x - ky * K;
     kf[threadIdx.x] = kernel[(K - 1 - ky) * K + (K - 1 - kx)];
@@ -118,13 +125,13 @@ __global__ void __launch_bounds__(256) upblur_act_kernel(float* __restrict__ out
   const int oy0 = (t / tiles_x) * TILE, ox0 = (t % tiles_x) * TILE;
   const int64_t q = (int64_t)Hq * Wq;
   const float* pb = pp + plane * 4 * q;
-  for (int r = ty; r < IN; r += 8) {
+  const int rows_needed = min(IN, zh - oy0);
+  for (int r = ty; r < rows_needed; r += TROWS) {
     const int Yz = oy0 + r;
-    const bool row_ok = Yz < zh;
     const float* prow = pb + (int64_t)((Yz & 1) * 2) * q + (int64_t)(Yz >> 1) * Wq;
-    for (int c = tx; c < IN; c += 32) {
+    for (int c = tx; c < IN; c += 64) {
       const int Xz = ox0 + c;
-      tile[r][c] = (row_ok && Xz < zw) ? __ldcs(prow + (int64_t)(Xz & 1) * q + (Xz >> 1)) : 0.f;
+      tile[r][c] = Xz < zw ? __ldcs(prow + (int64_t)(Xz & 1) * q + (Xz >> 1)) : 0.f;
     }
   }
   __syncthreads();
@@ -136,20 +143,22 @@ __global__ void __launch_bounds__(256) upblur_act_kernel(float* __restrict__ out
   const float bv = bias ? __ldg(bias + c) : 0.f;
   const int64_t opl = (int64_t)oh * ow;
   const int ox = ox0 + tx;
-#pragma unroll
-  for (int r = 0; r < TILE / 8; ++r) {
-    const int ly = ty + r * 8;
+  if (ox >= ow) return;
+  const float* np = noise ? noise + b * opl : nullptr;
+  float* op = out + plane * opl;
+#pragma unroll 4
+  for (int r = 0; r < TILE / TROWS; ++r) {
+    const int ly = ty + r * TROWS;
     const int oy = oy0 + ly;
+    if (oy >= oh) break;
     float acc = 0.f;
 #pragma unroll
     for (int ky = 0; ky < K; ++ky)
 #pragma unroll
       for (int kx = 0; kx < K; ++kx) acc += w[ky * K + kx] * tile[ly + ky][tx + kx];
-    if (oy < oh && ox < ow) {
-      float v = acc + bv;
-      if (noise) v += nw * __ldg(noise + b * opl + (int64_t)oy * ow + ox);
-      __stcs(out + plane * opl + (int64_t)oy * ow + ox, (v > 0.f ? v : v * alpha) * scale);
-    }
+    float v = acc + bv;
+    if (np) v += nw * __ldg(np + (int64_t)oy * ow + ox);
+    __stcs(op + (int64_t)oy * ow + ox, (v > 0.f ? v : v * alpha) * scale);
   }
 }
 

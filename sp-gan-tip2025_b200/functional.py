@@ -705,8 +705,9 @@ def sphere_modconv_fused(x, coords, grid, w, in_mul, out_mul, out_scale, act=Non
         a_packed = torch.empty((2, rows, 9 * Cp), device=x.device, dtype=torch.bfloat16)
         cc = _f32c(coords, "sphere_modconv") if coords is not None else None
         im = _f32c(in_mul, "sphere_modconv") if in_mul is not None else None
-        lib.call("spgan_sphere_pack", _ptr(a_packed), _ptr(xh), _ptr(cc), _ptr(grid), _ptr(im), B, C, H, W, grid.shape[0],
-                 Cp, 1 if flat_concat else 0, st)
+        cmap = _sphere_chan_map(B, C, nc, Cp, bool(flat_concat), x.device)
+        lib.call("spgan_sphere_pack", _ptr(a_packed), _ptr(xh), _ptr(cc), _ptr(grid), _ptr(im), _ptr(cmap), B, C, H, W,
+                 grid.shape[0], Cp, st)
         wp = _packed_weight(w, O, Ct, Ct * 9, 9, list(range(9)), Cp, True)
         p = dict(My=H, Mx=W, in_stride=1, out_stride=1, off_y=0, off_x=0, taps=[(0, 0, 0)])
         cp = _fill_pass(p, B, Ct, H, W, O, H, W, Ct * 9, 9, out_scale, 1 if act is not None else 0, a, g, precision)
@@ -714,6 +715,37 @@ def sphere_modconv_fused(x, coords, grid, w, in_mul, out_mul, out_scale, act=Non
         _gemm_call(2.0 * B * H * W * O * Ct * 9, ctypes.byref(cp), _ptr(y), _ptr(a_packed), rows, 9 * Cp, _ptr(wp),
                    _ptr(om), _ptr(None), _ptr(None), _ptr(bias), _ptr(residual), st)
     return y
+
+
+_CHAN_MAPS = {}
+
+
+def _sphere_chan_map(B, C, nc, Cp, flat_concat, device):
+    """(B, Cp) uint32 table for spgan_sphere_pack: which gathered plane feeds channel k of group g.  With flat_concat
+    the reference's (1, B*C) ++ (1, B*nc) concatenation under groups=B is reproduced (models/spgan_ops_gs.py:792-814):
+    group g reads flat channels [g*Ct, (g+1)*Ct)."""
+    key = (B, C, nc, Cp, flat_concat, str(device))
+    t = _CHAN_MAPS.get(key)
+    if t is not None:
+        return t
+    import numpy as np
+    Ct = C + nc
+    m = np.full((B, Cp), 0xFFFFFFFF, dtype=np.uint64)
+    g = np.arange(B)[:, None]
+    k = np.arange(Ct)[None, :]
+    if flat_concat:
+        flat = g * Ct + k
+        feat = flat < B * C
+        bs = np.where(feat, flat // max(C, 1), (flat - B * C) // max(nc, 1))
+        cs = np.where(feat, flat % max(C, 1), (flat - B * C) % max(nc, 1))
+    else:
+        feat = np.broadcast_to(k < C, (B, Ct))
+        bs = np.broadcast_to(g, (B, Ct))
+        cs = np.where(feat, k, k - C)
+    m[:, :Ct] = (np.where(feat, 0, 1).astype(np.uint64) << 31) | (bs.astype(np.uint64) << 15) | cs.astype(np.uint64)
+    t = torch.from_numpy(m.astype(np.uint32).view(np.int32)).to(device)
+    _CHAN_MAPS[key] = t
+    return t
 
 
 def sphere_concat_gather(x, coords, grid):
