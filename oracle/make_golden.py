@@ -353,8 +353,160 @@ def golden_panorama(gen):
                         mean=np.float64(img.mean()), std=np.float64(img.std()))
 
 
+# ------------------------------------------------------------------------------------------ training-path pins
+def compact(res, limit=8192):
+    """Keep the fixtures small: tensors above `limit` elements are stored as a strided sample of the flattened array
+    plus its l2 norm (tests/cases.py:compact_view takes the same sample)."""
+    out = {}
+    for k, v in res.items():
+        v = np.asarray(v)
+        if v.size <= limit:
+            out[k] = v
+        else:
+            stride = -(-v.size // 4096)
+            out[k + "__sample"] = v.reshape(-1)[::stride].copy()
+            out[k + "__norm"] = np.float64(np.sqrt((v.astype(np.float64) ** 2).sum()))
+    return out
+
+
+def synthetic_d_state(disc):
+    sd = {}
+    for k, v in disc.state_dict().items():
+        if k.endswith("kernel"):
+            sd[k] = v.clone()
+        elif k.endswith(".bias"):
+            sd[k] = synth.randn_t(SEED, "d_" + k, v.shape, 0.1)
+        else:
+            sd[k] = synth.randn_t(SEED, "d_" + k, v.shape)
+    return sd
+
+
+def golden_discriminator():
+    """Reference: StyleGan2Discriminator (models/stylegan2discriminator.py) forward, first-order grads and the R1
+    second-order gradient (models/losses.py:36-41) on a B = 2 batch."""
+    from models.stylegan2discriminator import StyleGan2Discriminator
+    torch.manual_seed(SEED)
+    disc = StyleGan2Discriminator(config)
+    manifest = {k: list(v.shape) for k, v in disc.state_dict().items()}
+    with open(os.path.join(OUT, "discriminator_manifest.json"), "w") as f:
+        json.dump(manifest, f, indent=0)
+    sd = synthetic_d_state(disc)
+    disc.load_state_dict(sd)
+    disc.train()
+    res = {}
+    img = synth.randn_t(SEED, "d_img", (2, 3, 101, 101)).clamp(-1, 1).requires_grad_(True)
+    out = disc(img)
+    d, ac = out["d_patch"], out["ac_coords_pred"]
+    res["d"], res["ac"] = t2n(d), t2n(ac)
+    do, ao = O.discriminator_forward(sd, img)
+    close(t2n(do), res["d"], 1e-5, "D forward d_patch")
+    close(t2n(ao), res["ac"], 1e-5, "D forward ac_coords")
+    names = ["convs.0.0.weight", "convs.1.conv1.0.weight", "convs.1.conv2.1.weight", "convs.1.skip.1.weight",
+             "convs.3.conv2.2.bias", "final_conv.0.weight", "final_linear.0.weight", "coord_linear.1.weight"]
+    params = dict(disc.named_parameters())
+    loss = F.softplus(-d).mean() + (ac * synth.randn_t(SEED, "d_acw", ac.shape)).sum()
+    grads = torch.autograd.grad(loss, [img] + [params[n] for n in names], retain_graph=True)
+    res["g_img"] = t2n(grads[0])
+    for n, g in zip(names, grads[1:]):
+        res["g_" + n] = t2n(g)
+    # R1
+    r1 = O.d_r1_penalty(d, img)
+    res["r1"] = t2n(r1)
+    g2 = torch.autograd.grad(r1, [params[n] for n in names[:6]], allow_unused=True)
+    for n, g in zip(names[:6], g2):
+        res["r1g_" + n] = t2n(g)
+    np.savez_compressed(os.path.join(OUT, "discriminator.npz"), **compact(res))
+    print("  discriminator golden: d", res["d"].ravel(), "r1", float(res["r1"]))
+
+
+def golden_second_order_ops():
+    """Path-length style second-order gradients through ONE styled conv of each kind (plain 3x3, upsampling 3x3,
+    spherical 3x3): g = d<y, n>/d style (create_graph) ; L = |g|^2 ; dL/d{weight, modulation.weight, x}."""
+    res = {}
+    for name, up in (("plain", False), ("up", True)):
+        m = ref_ops.StyledConv(6, 5, 3, STYLE_DIM, upsample=up, blur_kernel=[1, 2, 1], no_zero_pad=True, config=config, side="ts")
+        fill_module(m, "so_" + name + "_")
+        with torch.no_grad():
+            m.noise.weight.fill_(0.3)
+        H = 7
+        x = synth.randn_t(SEED, "so_x_" + name, (2, 6, H, H)).requires_grad_(True)
+        s = synth.randn_t(SEED, "so_s_" + name, (2, STYLE_DIM)).requires_grad_(True)
+        oh = m.calc_out_spatial_size(H)
+        nz = synth.randn_t(SEED, "so_nz_" + name, (2, 1, oh, oh))
+        y, _ = m(x, s, noise=nz)
+        n = synth.randn_t(SEED, "so_n_" + name, y.shape)
+        g, = torch.autograd.grad((y * n).sum(), s, create_graph=True)
+        L = g.pow(2).sum()
+        gw, gmw, gx = torch.autograd.grad(L, [m.conv.weight, m.conv.modulation.weight, x])
+        res["y_" + name], res["g_" + name] = t2n(y), t2n(g)
+        res["gw_" + name], res["gmw_" + name], res["gx_" + name] = t2n(gw), t2n(gmw), t2n(gx)
+    # spherical
+    cps = [train_cp(7, 139, 11), train_cp(1, 20, 11)]
+    m = ref_gs.StyledConv(4 + 3, 5, 3, STYLE_DIM, no_zero_pad=True, disable_noise=True, config=config, activation="LeakyReLU_n",
+                          side="ss", deal_coords=True)
+    fill_module(m, "so_sph_")
+    x = synth.randn_t(SEED, "so_x_sph", (2, 4, 11, 11)).requires_grad_(True)
+    c = synth.randn_t(SEED, "so_c_sph", (2, 3, 11, 11))
+    s = synth.randn_t(SEED, "so_s_sph", (2, STYLE_DIM)).requires_grad_(True)
+    y, _ = m(x, s, coords=c.clone(), coords_partial=cps)
+    n = synth.randn_t(SEED, "so_n_sph", y.shape)
+    g, = torch.autograd.grad((y * n).sum(), s, create_graph=True)
+    L = g.pow(2).sum()
+    gw, gmw, gx = torch.autograd.grad(L, [m.conv.weight, m.conv.modulation.weight, x])
+    res["y_sph"], res["g_sph"], res["gw_sph"], res["gmw_sph"], res["gx_sph"] = t2n(y), t2n(g), t2n(gw), t2n(gmw), t2n(gx)
+    np.savez_compressed(os.path.join(OUT, "second_order.npz"), **res)
+    print("  second-order op goldens written")
+
+
+TRAIN_GRAD_KEYS = [
+    "structure_synthesizer.implicit_model.conv_stack.0.conv.conv.weight",
+    "structure_synthesizer.implicit_model.conv_stack.0.sc.weight",
+    "structure_synthesizer.implicit_model.conv_stack.1.conv.conv.weight",
+    "structure_synthesizer.implicit_model.conv_stack.2.conv.conv.modulation.weight",
+    "texture_synthesizer.convs.0.conv.weight",
+    "texture_synthesizer.convs.3.conv.weight",
+    "texture_synthesizer.convs.6.activate.bias",
+    "texture_synthesizer.convs.6.noise.weight",
+    "texture_synthesizer.to_rgbs.1.conv.weight",
+    "texture_synthesizer.sp_convs.0.weight",
+    "texture_synthesizer.mapping.1.weight",
+]
+
+
+def golden_generator_train(gen):
+    """Reference generator in train() mode: per-sample coords_partial list, style mixing at inject_index 5, first-order
+    gradients of <img, go> w.r.t. the local latent and a spread of parameters."""
+    sd = synth.synthetic_state_dict({k: list(v.shape) for k, v in gen.state_dict().items()}, SEED)
+    gen.load_state_dict(sd)
+    gen.train()
+    B = 2
+    cps = [train_cp(3, 17), train_cp(8, 120)]
+    gl = synth.randn_t(SEED, "tr_gl", (B, 2, 512))
+    lat = synth.randn_t(SEED, "tr_lat", (B, 256, 35, 35)).requires_grad_(True)
+    coords_full = O.meta_coord_grid(80, 180)
+    coords = torch.stack([coords_full[:, 3:38, 17:52], coords_full[:, 8:43, 120:155]]).contiguous()
+    noises = [synth.randn_t(SEED, "tr_noise%d" % l, (B, 1, s, s)) for l, s in enumerate(O.TS_FEATURE_SIZES)]
+    out = gen(global_latent=gl, local_latent=lat, override_coords=coords.clone(), coords_partial_override=cps,
+              noises=noises, inject_index=5, disable_dual_latents=True)["gen"]
+    go = synth.randn_t(SEED, "tr_go", out.shape)
+    params = dict(gen.named_parameters())
+    grads = torch.autograd.grad((out * go).sum(), [lat] + [params[k] for k in TRAIN_GRAD_KEYS])
+    res = {"img": t2n(out), "g_lat": t2n(grads[0])}
+    for k, g in zip(TRAIN_GRAD_KEYS, grads[1:]):
+        res["g_" + k] = t2n(g)
+    yo = O.generator_forward(sd, gl, lat, coords, cps, noises, inject_index=5)
+    close(t2n(yo), res["img"], 2e-4, "generator train-mode fwd")
+    np.savez_compressed(os.path.join(OUT, "generator_train.npz"), **compact(res))
+    gen.eval()
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["ops", "gen", "pano"]
+    which = sys.argv[1:] or ["ops", "gen", "pano", "train"]
+    if "train" in which:
+        golden_discriminator()
+        golden_second_order_ops()
+        torch.manual_seed(SEED)
+        golden_generator_train(InfinityGanGenerator(config))
     if "ops" in which:
         golden_bias_act()
         golden_upfirdn2d()

@@ -661,3 +661,68 @@ def generate_panorama(sd, plan, global_latent, local_latent, noises, positions=N
         px, py = ix * plan["pix_step"], iy * plan["pix_step"]
         circular_assign(meta, plan["meta_w"], px, px + 101, py, py + 101, patch.detach())
     return meta
+
+
+# --------------------------------------------------------------------------------------------
+# Discriminator                          models/stylegan2discriminator.py
+# --------------------------------------------------------------------------------------------
+def equal_conv2d(x, weight, bias=None, stride=1, padding=0):
+    """EqualConv2d.forward (models/ops.py:172-182)."""
+    scale = 1 / math.sqrt(weight.shape[1] * weight.shape[2] ** 2)
+    return F.conv2d(x, weight * scale, bias=bias, stride=stride, padding=padding)
+
+
+def d_conv_layer(sd, p, x, kernel_size, downsample=False, activate=True, bias=True):
+    """ConvLayer (stylegan2discriminator.py:9-54): [Blur] -> EqualConv2d -> [FusedLeakyReLU].  `p` = key prefix."""
+    i = 0
+    if downsample:
+        pd = (4 - 2) + (kernel_size - 1)
+        k = sd[p + "0.kernel"]
+        x = upfirdn2d_t(x, k, pad=((pd + 1) // 2, pd // 2))
+        i = 1
+        x = equal_conv2d(x, sd[p + "%d.weight" % i], None if activate or not bias else sd.get(p + "%d.bias" % i), stride=2, padding=0)
+    else:
+        x = equal_conv2d(x, sd[p + "%d.weight" % i], None if activate or not bias else sd.get(p + "%d.bias" % i),
+                         padding=kernel_size // 2)
+    if activate:
+        x = fused_leaky_relu_t(x, sd[p + "%d.bias" % (i + 1)])
+    return x
+
+
+def discriminator_forward(sd, img, stddev_group=16):
+    """StyleGan2Discriminator.forward (stylegan2discriminator.py:185-229) with coord_use_ac (spgan.yaml):
+    returns (d_patch (B, 1), ac_coords_pred (B, 3))."""
+    h = d_conv_layer(sd, "convs.0.", img, 1)
+    for i in range(1, 6):  # ResBlocks 256->512->512->512->512->512 at 101, 50, 25, 12, 6 -> 3
+        p = "convs.%d." % i
+        out = d_conv_layer(sd, p + "conv1.", h, 3)
+        out = d_conv_layer(sd, p + "conv2.", out, 3, downsample=True)
+        skip = d_conv_layer(sd, p + "skip.", h, 1, downsample=True, activate=False, bias=False)
+        h = (out + skip) / math.sqrt(2)
+    batch, channel, height, width = h.shape
+    group = min(batch, stddev_group)
+    stddev = h.view(group, -1, 1, channel, height, width)
+    stddev = torch.sqrt(stddev.var(0, unbiased=False) + 1e-8)
+    stddev = stddev.mean([2, 3, 4], keepdims=True).squeeze(2)
+    stddev = stddev.repeat(group, 1, height, width)
+    h = torch.cat([h, stddev], 1)
+    out = d_conv_layer(sd, "final_conv.", h, 3).view(batch, -1)
+    d = equal_linear(equal_linear(out, sd["final_linear.0.weight"], sd["final_linear.0.bias"], activation=True),
+                     sd["final_linear.1.weight"], sd["final_linear.1.bias"])
+    ac = equal_linear(equal_linear(out, sd["coord_linear.0.weight"], sd["coord_linear.0.bias"], activation=True),
+                      sd["coord_linear.1.weight"], sd["coord_linear.1.bias"])
+    return d, ac
+
+
+def d_r1_penalty(real_pred, real_img):
+    """models/losses.py:36-41."""
+    g, = torch.autograd.grad(real_pred.sum(), real_img, create_graph=True)
+    return g.pow(2).reshape(g.shape[0], -1).sum(1).mean()
+
+
+def styled_conv(x, style, weight, mod_weight, mod_bias, noise, noise_weight, act_bias, upsample=False, blur_kernel=None):
+    """ops.StyledConv.forward (models/ops.py:853-863): modulated conv -> NoiseInjection -> FusedLeakyReLU."""
+    y = modulated_conv2d(x, style, weight, mod_weight, mod_bias, upsample=upsample, blur_kernel=blur_kernel)
+    if noise is not None:
+        y = y + noise_weight * noise
+    return fused_leaky_relu_t(y, act_bias)

@@ -103,3 +103,61 @@ def generator_case(name, B, ix, iy):
 
 def generator_state_dict():
     return synth.synthetic_state_dict(load_json("generator_manifest.json"), SEED)
+
+
+def compact_check(golden, key, got, tol):
+    """Compare `got` with a fixture entry that may be stored compacted (oracle/make_golden.py:compact)."""
+    got = np.asarray(got)
+    if key in golden:
+        return rel_err(got, golden[key]) < tol
+    ref = golden[key + "__sample"]
+    stride = -(-got.size // 4096)
+    sample = got.reshape(-1)[::stride]
+    norm = float(np.sqrt((got.astype(np.float64) ** 2).sum()))
+    ref_norm = float(golden[key + "__norm"])
+    scale = max(np.abs(ref).max(), ref_norm / np.sqrt(got.size), 1e-30)
+    return float(np.abs(sample - ref).max() / scale) < tol and abs(norm - ref_norm) <= tol * ref_norm
+
+
+def discriminator_state_dict():
+    """As oracle/make_golden.py:synthetic_d_state: FIR buffers keep their values, biases ~ 0.1 N(0,1), weights N(0,1)."""
+    sd = {}
+    for k, shape in load_json("discriminator_manifest.json").items():
+        if k.endswith("kernel"):
+            sd[k] = torch.from_numpy(O.make_kernel([1, 3, 3, 1]))
+        elif k.endswith(".bias"):
+            sd[k] = synth.randn_t(SEED, "d_" + k, shape, 0.1)
+        else:
+            sd[k] = synth.randn_t(SEED, "d_" + k, shape)
+    return sd
+
+
+D_GRAD_KEYS = ["convs.0.0.weight", "convs.1.conv1.0.weight", "convs.1.conv2.1.weight", "convs.1.skip.1.weight",
+               "convs.3.conv2.2.bias", "final_conv.0.weight", "final_linear.0.weight", "coord_linear.1.weight"]
+
+TRAIN_GRAD_KEYS = [
+    "structure_synthesizer.implicit_model.conv_stack.0.conv.conv.weight",
+    "structure_synthesizer.implicit_model.conv_stack.0.sc.weight",
+    "structure_synthesizer.implicit_model.conv_stack.1.conv.conv.weight",
+    "structure_synthesizer.implicit_model.conv_stack.2.conv.conv.modulation.weight",
+    "texture_synthesizer.convs.0.conv.weight",
+    "texture_synthesizer.convs.3.conv.weight",
+    "texture_synthesizer.convs.6.activate.bias",
+    "texture_synthesizer.convs.6.noise.weight",
+    "texture_synthesizer.to_rgbs.1.conv.weight",
+    "texture_synthesizer.sp_convs.0.weight",
+    "texture_synthesizer.mapping.1.weight",
+]
+
+
+def generator_train_case():
+    """Inputs of make_golden.golden_generator_train."""
+    B = 2
+    cps = [train_cp(3, 17), train_cp(8, 120)]
+    gl = synth.randn_t(SEED, "tr_gl", (B, 2, 512))
+    lat = synth.randn_t(SEED, "tr_lat", (B, 256, 35, 35))
+    coords_full = O.meta_coord_grid(80, 180)
+    coords = torch.stack([coords_full[:, 3:38, 17:52], coords_full[:, 8:43, 120:155]]).contiguous()
+    noises = [synth.randn_t(SEED, "tr_noise%d" % l, (B, 1, s, s)) for l, s in enumerate(O.TS_FEATURE_SIZES)]
+    go = synth.randn_t(SEED, "tr_go", (B, 3, 101, 101))
+    return gl, lat, coords, cps, noises, go

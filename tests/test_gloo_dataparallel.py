@@ -1,0 +1,50 @@
+"""CPU, world_size 2 over gloo: the gradient exchange of the data-parallel training step and the lattice sharding
+rule used for multi-GPU panorama generation."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from spgan_b200.training import allreduce_gradients
+    from spgan_b200 import panorama
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.zeros(n)) for n in (3, 1000, 70000, 5)]
+    for i, p in enumerate(params):
+        p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
+    params.append(torch.nn.Parameter(torch.zeros(4)))  # no grad: must be skipped
+    n = allreduce_gradients(params, world, bucket_bytes=1 << 12)
+    ok = all(torch.allclose(p.grad, torch.full_like(p, 1.5 * (i + 1))) for i, p in enumerate(params[:4]))
+    # lattice sharding: every position owned by exactly one rank
+    pl = panorama.plan(384, 768)
+    pos = panorama.positions(pl)
+    mine = pos[rank::world]
+    counts = torch.zeros(len(pos))
+    for p_ in mine:
+        counts[pos.index(p_)] += 1
+    dist.all_reduce(counts)
+    ret[rank] = bool(ok and n >= 2 and params[4].grad is None and bool((counts == 1).all()))
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_and_lattice_sharding_world2():
+    ctx = mp.get_context("spawn")
+    mgr = ctx.Manager()
+    ret = mgr.dict()
+    port = 29500 + os.getpid() % 1000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert ret[0] and ret[1]

@@ -1,0 +1,122 @@
+"""GPU parity of the training path: discriminator forward / gradients / R1 second-order, path-length-style second-order
+gradients through one styled conv of each kind, the generator in train() mode with per-sample sampling grids, and one
+full training iteration."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import cases as K
+import spgan_oracle as O
+import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    import spgan_b200.lib as lib
+    torch.cuda.set_device(0)
+    lib.require_device()
+    return torch.device("cuda:0")
+
+
+def test_discriminator_golden_forward_grads_and_r1(dev):
+    from spgan_b200.discriminator import Discriminator
+    g = K.load("discriminator.npz")
+    disc = Discriminator()
+    disc.load_state_dict(K.discriminator_state_dict())
+    disc = disc.to(dev).train()
+    img0 = synth.randn_t(K.SEED, "d_img", (2, 3, 101, 101)).clamp(-1, 1)
+    with torch.no_grad():
+        out = disc(img0.to(dev))
+    assert K.rel_err(K.t2n(out["d_patch"]), g["d"]) < 5e-4 and K.rel_err(K.t2n(out["ac_coords_pred"]), g["ac"]) < 5e-4
+    img = img0.to(dev).requires_grad_(True)
+    out = disc(img)
+    d, ac = out["d_patch"], out["ac_coords_pred"]
+    assert K.rel_err(K.t2n(d), g["d"]) < 5e-4 and K.rel_err(K.t2n(ac), g["ac"]) < 5e-4
+    params = dict(disc.named_parameters())
+    loss = F.softplus(-d).mean() + (ac * synth.randn_t(K.SEED, "d_acw", ac.shape).to(dev)).sum()
+    grads = torch.autograd.grad(loss, [img] + [params[n] for n in K.D_GRAD_KEYS], retain_graph=True)
+    assert K.compact_check(g, "g_img", K.t2n(grads[0]), 1e-3), "g_img"
+    for n, got in zip(K.D_GRAD_KEYS, grads[1:]):
+        assert K.compact_check(g, "g_" + n, K.t2n(got), 1e-3), n
+    from spgan_b200.training import d_r1_loss
+    r1 = d_r1_loss(d, img)
+    assert abs(float(r1) - float(g["r1"])) < 1e-3 * abs(float(g["r1"]))
+    g2 = torch.autograd.grad(r1, [params[n] for n in K.D_GRAD_KEYS[:6]], allow_unused=True)
+    for n, got in zip(K.D_GRAD_KEYS[:6], g2):
+        assert K.compact_check(g, "r1g_" + n, K.t2n(got), 2e-3), "r1 " + n
+
+
+def _styled(kind, dev):
+    from spgan_b200.generator import default_config
+    from spgan_b200.models import ops, spgan_ops_gs
+    cfg = default_config()
+    if kind == "sph":
+        m = spgan_ops_gs.StyledConv(4 + 3, 5, 3, K.STYLE_DIM, no_zero_pad=True, disable_noise=True, config=cfg,
+                                    activation="LeakyReLU_n", side="ss", deal_coords=True)
+    else:
+        m = ops.StyledConv(6, 5, 3, K.STYLE_DIM, upsample=(kind == "up"), blur_kernel=[1, 2, 1], no_zero_pad=True,
+                           config=cfg, side="ts")
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            p.copy_(synth.randn_t(K.SEED, "so_" + kind + "_" + n, p.shape, 1.0, 1.0 if n.endswith("modulation.bias") else 0.0))
+        if kind != "sph":
+            m.noise.weight.fill_(0.3)
+    return m.to(dev)
+
+
+@pytest.mark.parametrize("kind", ["plain", "up", "sph"])
+def test_second_order_through_styled_conv(dev, kind):
+    g = K.load("second_order.npz")
+    m = _styled(kind, dev)
+    s = synth.randn_t(K.SEED, "so_s_" + kind, (2, K.STYLE_DIM)).to(dev).requires_grad_(True)
+    if kind == "sph":
+        x = synth.randn_t(K.SEED, "so_x_sph", (2, 4, 11, 11)).to(dev).requires_grad_(True)
+        c = synth.randn_t(K.SEED, "so_c_sph", (2, 3, 11, 11)).to(dev)
+        y, _ = m(x, s, coords=c.clone(), coords_partial=[K.train_cp(7, 139, 11), K.train_cp(1, 20, 11)])
+    else:
+        x = synth.randn_t(K.SEED, "so_x_" + kind, (2, 6, 7, 7)).to(dev).requires_grad_(True)
+        oh = m.calc_out_spatial_size(7)
+        nz = synth.randn_t(K.SEED, "so_nz_" + kind, (2, 1, oh, oh)).to(dev)
+        y, _ = m(x, s, noise=nz)
+    assert K.rel_err(K.t2n(y), g["y_" + kind]) < 1e-5
+    n = synth.randn_t(K.SEED, "so_n_" + kind, y.shape).to(dev)
+    gs, = torch.autograd.grad((y * n).sum(), s, create_graph=True)
+    assert K.rel_err(K.t2n(gs), g["g_" + kind]) < 2e-5
+    gw, gmw, gx = torch.autograd.grad(gs.pow(2).sum(), [m.conv.weight, m.conv.modulation.weight, x])
+    assert K.rel_err(K.t2n(gw), g["gw_" + kind]) < 1e-4
+    assert K.rel_err(K.t2n(gmw), g["gmw_" + kind]) < 1e-4
+    assert K.rel_err(K.t2n(gx), g["gx_" + kind]) < 1e-4
+
+
+def test_generator_train_mode_golden_forward_and_grads(dev):
+    from spgan_b200.generator import Generator
+    g = K.load("generator_train.npz")
+    gen = Generator()
+    gen.load_state_dict(K.generator_state_dict())
+    gen = gen.to(dev).train()
+    gl, lat, coords, cps, noises, go = K.generator_train_case()
+    lat = lat.to(dev).requires_grad_(True)
+    img = gen(gl.to(dev), lat, coords.to(dev), cps, noises=[n.to(dev) for n in noises], inject_index=5)
+    assert K.compact_check(g, "img", K.t2n(img), 5e-4)
+    params = dict(gen.named_parameters())
+    grads = torch.autograd.grad((img * go.to(dev)).sum(), [lat] + [params[k] for k in K.TRAIN_GRAD_KEYS])
+    assert K.compact_check(g, "g_lat", K.t2n(grads[0]), 1e-3), "g_lat"
+    for k, got in zip(K.TRAIN_GRAD_KEYS, grads[1:]):
+        assert K.compact_check(g, "g_" + k, K.t2n(got), 1e-3), k
+
+
+def test_one_training_iteration_runs_and_updates(dev):
+    from spgan_b200.training import TrainStep
+    ts = TrainStep(batch=2, device=dev, world=1, seed=1)
+    w_g = ts.G.texture_synthesizer.convs[7].conv.weight.detach().clone()
+    w_d = ts.D.convs[1].conv1[0].weight.detach().clone()
+    out = ts.step(lazy="all")
+    assert set(out) == {"d", "r1", "g", "path"}
+    assert all(torch.isfinite(v).all() for v in out.values())
+    assert not torch.equal(w_g, ts.G.texture_synthesizer.convs[7].conv.weight)
+    assert not torch.equal(w_d, ts.D.convs[1].conv1[0].weight)
+    out = ts.step(lazy="none")
+    assert set(out) == {"d", "g"}

@@ -125,3 +125,38 @@ def test_lattice_golden():
             assert plan[k] == v, (key, k)
     mc = O.meta_coord_grid(ref["384x768"]["lat_h"], ref["384x768"]["lat_w"])
     assert hashlib.sha256(K.t2n(mc).tobytes()).hexdigest() == ref["meta_coords_384_sha256"]
+
+
+def test_discriminator_golden():
+    g = K.load("discriminator.npz")
+    sd = K.discriminator_state_dict()
+    img = synth.randn_t(K.SEED, "d_img", (2, 3, 101, 101)).clamp(-1, 1).requires_grad_(True)
+    torch.set_num_threads(8)
+    d, ac = O.discriminator_forward(sd, img)
+    assert K.rel_err(K.t2n(d), g["d"]) < 1e-5 and K.rel_err(K.t2n(ac), g["ac"]) < 1e-5
+    r1 = O.d_r1_penalty(d, img)
+    assert abs(float(r1) - float(g["r1"])) < 1e-5 * abs(float(g["r1"]))
+
+
+def test_second_order_ops_golden():
+    g = K.load("second_order.npz")
+    for name, up in (("plain", False), ("up", True)):
+        p = K.module_params("so_" + name + "_", {"conv.weight": (1, 5, 6, 3, 3), "conv.modulation.weight": (6, K.STYLE_DIM),
+                                                  "conv.modulation.bias": (6,), "activate.bias": (5,)})
+        w = p["conv.weight"].requires_grad_(True)
+        mw = p["conv.modulation.weight"].requires_grad_(True)
+        x = synth.randn_t(K.SEED, "so_x_" + name, (2, 6, 7, 7)).requires_grad_(True)
+        s = synth.randn_t(K.SEED, "so_s_" + name, (2, K.STYLE_DIM)).requires_grad_(True)
+        oh = 11 if up else 5
+        nz = synth.randn_t(K.SEED, "so_nz_" + name, (2, 1, oh, oh))
+        blur = torch.from_numpy(O.make_kernel([1, 2, 1]) * 4) if up else None
+        y = O.styled_conv(x, s, w, mw, p["conv.modulation.bias"], nz, torch.tensor([0.3]), p["activate.bias"], upsample=up,
+                          blur_kernel=blur)
+        assert K.rel_err(K.t2n(y), g["y_" + name]) < 1e-5
+        n = synth.randn_t(K.SEED, "so_n_" + name, y.shape)
+        gs, = torch.autograd.grad((y * n).sum(), s, create_graph=True)
+        gw, gmw, gx = torch.autograd.grad(gs.pow(2).sum(), [w, mw, x])
+        assert K.rel_err(K.t2n(gs), g["g_" + name]) < 1e-5
+        assert K.rel_err(K.t2n(gw), g["gw_" + name]) < 1e-4
+        assert K.rel_err(K.t2n(gmw), g["gmw_" + name]) < 1e-4
+        assert K.rel_err(K.t2n(gx), g["gx_" + name]) < 1e-4
