@@ -35,6 +35,9 @@ def parse():
     ap.add_argument("--precision", type=int, default=1, choices=[0, 1, 2])
     ap.add_argument("--cpu-sample-patches", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="panorama", choices=["panorama", "train"],
+                    help="panorama = BASELINE configs[1] (default, the headline); train = configs[2], full G+D step")
+    ap.add_argument("--train-batch", type=int, default=8)
     return ap.parse_args()
 
 
@@ -273,9 +276,171 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------ train workload
+TRAIN_METRIC = "train_images_per_sec_101x101_full_G+D_step"
+TRAIN_UNIT = "img/s"
+
+
+def cpu_train_rate(batch=2, threads=None):
+    """img/s of one D step + one G step (forward + backward, no regularisers) of the oracle port on the CPU."""
+    import torch
+    import torch.nn.functional as F
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cases as K
+    import spgan_oracle as O
+    import synth
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    gsd = {k: v.clone().requires_grad_(v.dtype.is_floating_point and "kernel" not in k and "noises." not in k)
+           for k, v in K.generator_state_dict().items()}
+    dsd = {k: v.clone().requires_grad_("kernel" not in k) for k, v in K.discriminator_state_dict().items()}
+    gl, lat, coords, cps, noises, _ = K.generator_train_case()
+    t0 = time.perf_counter()
+    # D step
+    with torch.no_grad():
+        fake = O.generator_forward({k: v.detach() for k, v in gsd.items()}, gl, lat, coords, cps, noises, inject_index=5)
+    real = synth.randn_t(9000, "bench_real", fake.shape).clamp(-1, 1)
+    fp, rp = O.discriminator_forward(dsd, fake), O.discriminator_forward(dsd, real)
+    (F.softplus(-rp[0]).mean() + F.softplus(fp[0]).mean()).backward()
+    # G step
+    fake = O.generator_forward(gsd, gl, lat, coords, cps, noises, inject_index=5)
+    fp = O.discriminator_forward({k: v.detach() for k, v in dsd.items()}, fake)
+    F.softplus(-fp[0]).mean().backward()
+    dt = time.perf_counter() - t0
+    return batch / dt, threads, dt
+
+
+def run_train(args):
+    import torch
+    import torch.distributed as dist
+    import spgan_b200.functional as SF
+    import spgan_b200.lib as lib
+    from spgan_b200.training import TrainStep
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    lib.require_device()
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    SF.set_precision(args.precision)
+    B = args.train_batch
+    ts = TrainStep(batch=B, device=dev, world=world, seed=9000 + rank)
+    tp = ts.config.train_params
+    # "real" patches live in pinned host memory for the e2e leg (the dataloader side of train.py:205-215)
+    g = torch.Generator(device="cpu").manual_seed(9000 + rank)
+    host_real = torch.randn(B, 3, 101, 101, generator=g).clamp_(-1, 1).pin_memory()
+    host_ac = (torch.rand(B, 3, generator=g) * 2 - 1).pin_memory()
+    host_loss = torch.empty(4).pin_memory()
+
+    parts = ("d", "r1", "g", "path", "ema")
+
+    def one_iteration(acc, e2e):
+        """Every part of the iteration runs, each bracketed by CUDA events (the schedule weights them afterwards)."""
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(parts) + 1)]
+        ev[0].record()
+        real = (host_real.to(dev, non_blocking=True), host_ac.to(dev, non_blocking=True)) if e2e else None
+        ld = ts.d_step(real=real)
+        ev[1].record()
+        lr = ts.d_r1_step(real=real)
+        ev[2].record()
+        lg = ts.g_step()
+        ev[3].record()
+        lp = ts.g_path_step()
+        ev[4].record()
+        ts.ema_step()
+        if e2e:
+            host_loss.copy_(torch.stack([ld, lr, lg, lp]), non_blocking=True)
+        ev[5].record()
+        acc.append(ev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def measure(steps, e2e):
+        acc = []
+        barrier()
+        for _ in range(steps):
+            one_iteration(acc, e2e)
+        barrier()
+        ms = {k: sum(ev[i].elapsed_time(ev[i + 1]) for ev in acc) / steps for i, k in enumerate(parts)}
+        t = torch.tensor([ms[k] for k in parts], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return dict(zip(parts, [float(v) for v in t.tolist()]))
+
+    def amortised(ms):
+        return ms["d"] + ms["g"] + ms["ema"] + ms["r1"] / tp.d_reg_every + ms["path"] / tp.g_reg_every
+
+    measure(max(args.warmup, 3), False)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    SF.profile_gemm(True)
+    l0, g0 = lib.launches(), lib.load().spgan_gemm_launch_count()
+    ms = measure(args.steps, False)
+    l1, g1 = lib.launches(), lib.load().spgan_gemm_launch_count()
+    gemm_stats = SF.profile_gemm(False)
+    clocks = sampler.stop() if sampler else None
+    ms_e2e = measure(args.steps, True)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    ms_step = amortised(ms)
+    value = world * B / (ms_step / 1000.0)
+    e2e_value = world * B / (amortised(ms_e2e) / 1000.0)
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    ach = gemm_stats["flops"] / (gemm_stats["ms"] / 1000.0) / 1e12 if gemm_stats["ms"] > 0 else 0.0
+    all_ms = sum(ms.values()) * args.steps
+    out = {
+        "metric": TRAIN_METRIC, "value": value, "unit": TRAIN_UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": {0: "fp32 (SIMT)", 1: "fp32-equivalent (bf16x3 split on tcgen05, fp32 accumulate)", 2: "bf16 (tcgen05, fp32 accumulate)"}[args.precision],
+        "data": "synthetic",
+        "config": {"workload": "full G+D training iteration (StyleGAN2 discriminator, R1 every %d, path-length every %d at batch %d), "
+                               "batch %d/GPU data-parallel, 101x101 patches, random-init configs/model/spgan.yaml" % (
+                                   tp.d_reg_every, tp.g_reg_every, max(1, B // tp.path_batch_shrink), B),
+                   "batch_per_gpu": B, "parallelism": "dp%d" % world,
+                   "schedule": "every timed step runs D, R1, G, path-length and EMA; ms_per_step = D + G + EMA + R1/%d + path/%d "
+                               "(the reference's lazy-regularisation cadence, train.py:288,379)" % (tp.d_reg_every, tp.g_reg_every),
+                   "part_ms": ms, "l2": "activations of one iteration exceed L2 (> 1 GB)", "precision_mode": args.precision},
+        "e2e": {"value": e2e_value, "unit": TRAIN_UNIT, "h2d_bytes_per_step": 2 * (host_real.numel() + host_ac.numel()) * 4,
+                "d2h_bytes_per_step": 16, "ms_per_step": amortised(ms_e2e)},
+        "gpu_launches": l1 - l0, "tcgen05_gemm_launches": int(g1 - g0), "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit-GEMM conv, forward and data-gradient passes)",
+                     "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf if peak_tf else None,
+                     "traffic": None, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s",
+                     "launches_timed": gemm_stats["launches"],
+                     "avg_launch_ms": gemm_stats["ms"] / max(gemm_stats["launches"], 1),
+                     "share_of_step": gemm_stats["ms"] / (all_ms if all_ms else 1.0)},
+    }
+    if not args.no_cpu_baseline:
+        rate, threads, dt = cpu_train_rate(2)
+        out["cpu_baseline"] = {"value": rate, "unit": TRAIN_UNIT, "cores": threads, "kind": "port",
+                               "sample": "one D step + one G step (forward + backward, no regularisers) at batch 2 (%.1f s), oracle port on CPU" % dt}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.workload == "train":
+        run_train(a)
     else:
         run_ours(a)

@@ -384,16 +384,17 @@ __global__ void __launch_bounds__(256) pack_act_kernel(__nv_bfloat16* __restrict
       sx = j - pad_x;
     }
     const bool inside = sy >= 0 && sy < H && sx >= 0 && sx < W;
-#pragma unroll 4
-    for (int cc = ty; cc < 64; cc += 4) {
-      const int c = c0 + cc;
-      float v = 0.f;
-      if (inside && c < C) {
-        v = __ldg(x + (((int64_t)b * C + c) * H + sy) * W + sx);
-        if (in_mul) v *= __ldg(in_mul + (int64_t)b * C + c);
-      }
-      tile[cc][tx] = v;
+    // all 16 loads of a thread are in flight before the first shared-memory store (bytes in flight cover the latency)
+    float v[16], m[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int c = c0 + ty + 4 * u;
+      const bool ok = inside && c < C;
+      v[u] = ok ? __ldcs(x + (((int64_t)b * C + c) * H + sy) * W + sx) : 0.f;
+      m[u] = (ok && in_mul) ? __ldg(in_mul + (int64_t)b * C + c) : 1.f;
     }
+#pragma unroll
+    for (int u = 0; u < 16; ++u) tile[ty + 4 * u][tx] = v[u] * m[u];
   }
   __syncthreads();
   const int cpair = threadIdx.x & 31, prow = threadIdx.x >> 5;
@@ -567,6 +568,84 @@ __global__ void __launch_bounds__(256) sphere_pack_kernel(__nv_bfloat16* __restr
   }
 }
 
+// Shared-grid specialisation (test / panorama mode: one sampling grid for the whole batch, grid_batch == 1) with
+// Cp = 64 * KITER known at compile time: the corner set is computed once per warp and all 8 * KITER corner loads of a
+// lane are issued before the first use, so a warp keeps 40 x 128 B of reads in flight instead of one dependent chain per
+// 64 channels (the general kernel above is latency-bound at ~10 % of the HBM write roofline).
+template <int KITER>
+__global__ void __launch_bounds__(256) sphere_pack_shared_kernel(__nv_bfloat16* __restrict__ out,
+                                                                const float* __restrict__ xh,
+                                                                const float* __restrict__ coords,
+                                                                const float* __restrict__ grid,
+                                                                const float* __restrict__ in_mul,
+                                                                const uint32_t* __restrict__ chan_map, int B, int C,
+                                                                int nc, int H, int W) {
+  constexpr int Cp = 64 * KITER;
+  const int Ct = C + nc;
+  const int HW = H * W;
+  const int64_t plane_elems = (int64_t)B * HW * 9 * Cp;
+  const int64_t warps_total = (int64_t)B * HW * 9;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t warp_stride = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t wid = warp0; wid < warps_total; wid += warp_stride) {
+    const int t = (int)(wid % 9);
+    const int64_t r = wid / 9;
+    const int p = (int)(r % HW);
+    const int g = (int)(r / HW);
+    const int py = p / W, px = p - py * W;
+    const int ty = t / 3, tx = t - ty * 3;
+    const TapCorners cn = tap_corners(grid, 0, H, W, py, px, ty, tx);
+    const uint32_t* mrow = chan_map + (int64_t)g * Cp;
+    const float* mulrow = in_mul ? in_mul + (int64_t)g * Ct : nullptr;
+    uint2 mm[KITER];
+#pragma unroll
+    for (int j = 0; j < KITER; ++j) mm[j] = __ldg(reinterpret_cast<const uint2*>(mrow + 2 * lane + 64 * j));
+    float cv[KITER][2][4], mv[KITER][2];
+#pragma unroll
+    for (int j = 0; j < KITER; ++j) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const uint32_t m = u ? mm[j].y : mm[j].x;
+        const bool ok = m != 0xFFFFFFFFu;
+        const int bs = (int)((m >> 15) & 0xFFFFu);
+        const int cs = (int)(m & 0x7FFFu);
+        const bool is_coord = (m >> 31) != 0;
+        const float* src = is_coord ? coords + ((int64_t)bs * nc + cs) * HW : xh + (int64_t)bs * HW * C + cs;
+        const int64_t st = is_coord ? 1 : C;
+        cv[j][u][0] = ok ? __ldg(src + cn.o_nw * st) : 0.f;
+        cv[j][u][1] = ok ? __ldg(src + cn.o_ne * st) : 0.f;
+        cv[j][u][2] = ok ? __ldg(src + cn.o_sw * st) : 0.f;
+        cv[j][u][3] = ok ? __ldg(src + cn.o_se * st) : 0.f;
+        mv[j][u] = (ok && mulrow) ? __ldg(mulrow + 2 * lane + 64 * j + u) : 1.f;
+      }
+    }
+    __nv_bfloat16* orow = out + wid * Cp;
+#pragma unroll
+    for (int j = 0; j < KITER; ++j) {
+      float v[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const uint32_t m = u ? mm[j].y : mm[j].x;
+        float val = cv[j][u][0] * cn.w_nw + cv[j][u][1] * cn.w_ne + cv[j][u][2] * cn.w_sw + cv[j][u][3] * cn.w_se;
+        if (m != 0xFFFFFFFFu && (m >> 31) != 0) {
+          const int cs = (int)(m & 0x7FFFu);
+          if (cs == 0) val = tanhf(val);
+          else if (cs == 1) val = cosf(val * 3.14159274101257324f);
+          else if (cs == 2) val = sinf(val * 3.14159274101257324f);
+        }
+        v[u] = val * mv[j][u];
+      }
+      __nv_bfloat16 h0, l0, h1, l1;
+      split_bf16(v[0], h0, l0);
+      split_bf16(v[1], h1, l1);
+      const int k0 = 2 * lane + 64 * j;
+      *reinterpret_cast<__nv_bfloat162*>(orow + k0) = __halves2bfloat162(h0, h1);
+      *reinterpret_cast<__nv_bfloat162*>(orow + plane_elems + k0) = __halves2bfloat162(l0, l1);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -680,8 +759,20 @@ extern "C" int spgan_sphere_pack(uint16_t* out, const float* x_nhwc, const float
   SPGAN_CHECK_ARG((((uintptr_t)grid) & 7) == 0 && (((uintptr_t)chan_map) & 7) == 0,
                   "spgan_sphere_pack: grid and chan_map must be 8-byte aligned");
   const int64_t warps = (int64_t)B * H * W * 9;
-  sphere_pack_kernel<<<grid_for(warps, 8, 8, 8), 256, 0, (cudaStream_t)stream>>>(
-      (__nv_bfloat16*)out, x_nhwc, coords, grid, in_mul, chan_map, B, C, nc, H, W, grid_batch, Cp);
+  cudaStream_t st = (cudaStream_t)stream;
+  __nv_bfloat16* o = (__nv_bfloat16*)out;
+  const int nblk = grid_for(warps, 8, 2, 16);
+#define SPGAN_SPHERE_SHARED(KI)                                                                                       \
+  sphere_pack_shared_kernel<KI><<<nblk, 256, 0, st>>>(o, x_nhwc, coords, grid, in_mul, chan_map, B, C, nc, H, W)
+  if (grid_batch == 1 && Cp == 64) SPGAN_SPHERE_SHARED(1);
+  else if (grid_batch == 1 && Cp == 128) SPGAN_SPHERE_SHARED(2);
+  else if (grid_batch == 1 && Cp == 192) SPGAN_SPHERE_SHARED(3);
+  else if (grid_batch == 1 && Cp == 256) SPGAN_SPHERE_SHARED(4);
+  else if (grid_batch == 1 && Cp == 320) SPGAN_SPHERE_SHARED(5);
+  else
+    sphere_pack_kernel<<<grid_for(warps, 8, 8, 8), 256, 0, st>>>(o, x_nhwc, coords, grid, in_mul, chan_map, B, C, nc, H, W,
+                                                                grid_batch, Cp);
+#undef SPGAN_SPHERE_SHARED
   SPGAN_CHECK_LAUNCH("spgan_sphere_pack");
   return 0;
 }

@@ -55,14 +55,37 @@ __global__ void __launch_bounds__(256) upfirdn2d_generic(float* __restrict__ out
 constexpr int TILE = 64;
 constexpr int TROWS = 4;  // thread rows
 
+// Exact unsigned division by a runtime-constant divisor (Granlund-Montgomery), so that flat-index kernels can decode
+// (row, column) without the ~25-instruction hardware-emulated integer division.
+struct FastDiv {
+  uint32_t d, m, s1, s2;
+};
+static inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  f.d = d;
+  uint32_t l = 0;
+  while ((1ull << l) < d) ++l;
+  f.m = (uint32_t)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+  f.s1 = l < 1 ? l : 1;
+  f.s2 = l > 0 ? l - 1 : 0;
+  return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) {
+  const uint32_t t = __umulhi(f.m, n);
+  return (t + ((n - t) >> f.s1)) >> f.s2;
+}
+
+// Tiled FIR (up = down = 1, K x K, zero padding): 64x64 output tile per CTA.  All of a thread's ~17 input loads are issued
+// before the first shared-memory store (>= 64 KB in flight per SM: the kernel sits on HBM bandwidth, not on load latency),
+// and each thread filters a vertical strip of 16 rows with a sliding window (K shared-memory reads per output, not K*K).
 template <int K>
 __global__ void __launch_bounds__(256) upfirdn2d_tiled(float* __restrict__ out, const float* __restrict__ x,
                                                       const float* __restrict__ kernel, int tiles_x, int tiles_y,
                                                       UfdParams p) {
   constexpr int IN = TILE + K - 1;
+  constexpr int NLOAD = (IN * IN + 255) / 256;
   __shared__ float tile[IN][IN + 1];
   __shared__ float kf[K * K];
-  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 64 x 4
   if (threadIdx.x < K * K) {
     int ky = threadIdx.x / K, kx = threadIdx.x - ky * K;
     kf[threadIdx.x] = kernel[(K - 1 - ky) * K + (K - 1 - kx)];
@@ -74,31 +97,52 @@ __global__ void __launch_bounds__(256) upfirdn2d_tiled(float* __restrict__ out, 
   const float* xp = x + plane * (int64_t)p.in_h * p.in_w;
   const int iy0 = oy0 - p.pad_y0, ix0 = ox0 - p.pad_x0;
   const int rows_needed = min(IN, p.out_h - oy0 + K - 1);
-  for (int r = ty; r < rows_needed; r += TROWS) {
-    const int iy = iy0 + r;
-    const bool row_ok = iy >= 0 && iy < p.in_h;
-    for (int c = tx; c < IN; c += 64) {
-      const int ix = ix0 + c;
-      tile[r][c] = (row_ok && ix >= 0 && ix < p.in_w) ? __ldcs(xp + (int64_t)iy * p.in_w + ix) : 0.f;
-    }
+  const int cols_needed = min(IN, p.out_w - ox0 + K - 1);
+  float v[NLOAD];
+#pragma unroll
+  for (int u = 0; u < NLOAD; ++u) {
+    const int e = threadIdx.x + u * 256;
+    const int r = e / IN, c = e - r * IN;
+    const int iy = iy0 + r, ix = ix0 + c;
+    const bool ok = r < rows_needed && c < cols_needed && iy >= 0 && iy < p.in_h && ix >= 0 && ix < p.in_w;
+    v[u] = ok ? __ldcs(xp + (int64_t)iy * p.in_w + ix) : 0.f;
+  }
+#pragma unroll
+  for (int u = 0; u < NLOAD; ++u) {
+    const int e = threadIdx.x + u * 256;
+    const int r = e / IN, c = e - r * IN;
+    if (r < IN) tile[r][c] = v[u];
   }
   __syncthreads();
   float w[K * K];
 #pragma unroll
   for (int i = 0; i < K * K; ++i) w[i] = kf[i];
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 64 columns x 4 strips of 16 rows
   float* op = out + plane * (int64_t)p.out_h * p.out_w;
   const int ox = ox0 + tx;
   if (ox >= p.out_w) return;
-#pragma unroll 4
-  for (int r = 0; r < TILE / TROWS; ++r) {
-    const int ly = ty + r * TROWS;
-    const int oy = oy0 + ly;
+  constexpr int STRIP = TILE / TROWS;
+  const int ly0 = ty * STRIP;
+  float win[K][K];
+#pragma unroll
+  for (int ky = 0; ky < K - 1; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < K; ++kx) win[ky + 1][kx] = tile[ly0 + ky][tx + kx];
+#pragma unroll
+  for (int r = 0; r < STRIP; ++r) {
+    const int oy = oy0 + ly0 + r;
     if (oy >= p.out_h) break;
+#pragma unroll
+    for (int ky = 0; ky < K - 1; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < K; ++kx) win[ky][kx] = win[ky + 1][kx];
+#pragma unroll
+    for (int kx = 0; kx < K; ++kx) win[K - 1][kx] = tile[ly0 + r + K - 1][tx + kx];
     float acc = 0.f;
 #pragma unroll
     for (int ky = 0; ky < K; ++ky)
 #pragma unroll
-      for (int kx = 0; kx < K; ++kx) acc += w[ky * K + kx] * tile[ly + ky][tx + kx];
+      for (int kx = 0; kx < K; ++kx) acc += w[ky * K + kx] * win[ky][kx];
     __stcs(op + (int64_t)oy * p.out_w + ox, acc);
   }
 }
@@ -106,59 +150,79 @@ __global__ void __launch_bounds__(256) upfirdn2d_tiled(float* __restrict__ out, 
 // Fused tail of the upsampling StyledConv: interleave the four polyphase planes of the transposed conv on the fly,
 // 3x3 FIR, + noise + bias, leaky-ReLU * scale.  HBM traffic = one read of the planes (+ halo) and one write of the
 // result, instead of scatter-write + FIR read/write + activation read/write.
-__global__ void __launch_bounds__(256) upblur_act_kernel(float* __restrict__ out, const float* __restrict__ pp,
-                                                        const float* __restrict__ kernel, const float* __restrict__ noise,
-                                                        const float* __restrict__ noise_w, const float* __restrict__ bias,
-                                                        int64_t channels, int zh, int zw, int Hq, int Wq, int oh, int ow,
-                                                        int tiles_x, int tiles_y, float alpha, float scale) {
-  constexpr int K = 3, IN = TILE + K - 1;
-  __shared__ float tile[IN][IN + 1];
-  __shared__ float kf[K * K];
-  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
-  if (threadIdx.x < K * K) {
-    int ky = threadIdx.x / K, kx = threadIdx.x - ky * K;
-    kf[threadIdx.x] = kernel[(K - 1 - ky) * K + (K - 1 - kx)];
+//
+// The kernel works on the FLAT index q = Y*zw + X of the interleaved (zh, zw) image: a FIR tap (ky, kx) is the constant
+// offset ky*zw + kx, so a CTA stages one contiguous run of `chunk` + 2*zw + 2 lattice points in shared memory and every
+// lane computes a useful output whatever the image size (2-D tiles waste 20 % of the lanes at 103 and 91 % at 19).
+// Outputs whose X falls in the last two columns of a row are the wrap-around positions and are skipped.  All input loads
+// of a thread are issued before the first shared-memory store (latency is covered by bytes in flight, not occupancy).
+constexpr int UB_THREADS = 256;
+constexpr int UB_MAX_ITER = 8;  // lattice points per thread
+
+__global__ void __launch_bounds__(UB_THREADS) upblur_act_kernel(float* __restrict__ out, const float* __restrict__ pp,
+                                                               const float* __restrict__ kernel,
+                                                               const float* __restrict__ noise,
+                                                               const float* __restrict__ noise_w,
+                                                               const float* __restrict__ bias, int64_t channels, int zh,
+                                                               int zw, int Hq, int Wq, int oh, int ow, int chunk,
+                                                               int chunks_per_plane, FastDiv dzw, float alpha, float scale) {
+  extern __shared__ float stage[];
+  __shared__ float kf[9];
+  if (threadIdx.x < 9) {
+    int ky = threadIdx.x / 3, kx = threadIdx.x - ky * 3;
+    kf[threadIdx.x] = kernel[(2 - ky) * 3 + (2 - kx)];
   }
-  const int tiles_per_plane = tiles_x * tiles_y;
-  const int64_t plane = blockIdx.x / tiles_per_plane;
-  const int t = blockIdx.x - (int)(plane * tiles_per_plane);
-  const int oy0 = (t / tiles_x) * TILE, ox0 = (t % tiles_x) * TILE;
-  const int64_t q = (int64_t)Hq * Wq;
-  const float* pb = pp + plane * 4 * q;
-  const int rows_needed = min(IN, zh - oy0);
-  for (int r = ty; r < rows_needed; r += TROWS) {
-    const int Yz = oy0 + r;
-    const float* prow = pb + (int64_t)((Yz & 1) * 2) * q + (int64_t)(Yz >> 1) * Wq;
-    for (int c = tx; c < IN; c += 64) {
-      const int Xz = ox0 + c;
-      tile[r][c] = Xz < zw ? __ldcs(prow + (int64_t)(Xz & 1) * q + (Xz >> 1)) : 0.f;
+  const int64_t plane = blockIdx.x / chunks_per_plane;
+  const int ck = blockIdx.x - (int)(plane * chunks_per_plane);
+  const int q0 = ck * chunk;
+  const int q_out_end = min(q0 + chunk, oh * zw);          // outputs of this CTA: [q0, q_out_end)
+  const int n_in = min(q_out_end + 2 * zw + 2, zh * zw) - q0;  // staged inputs: [q0, q0 + n_in)
+  const int64_t Q = (int64_t)Hq * Wq;
+  const float* pb = pp + plane * 4 * Q;
+  constexpr int LB = 10;  // loads per batch
+  for (int e0 = 0; e0 < n_in; e0 += LB * UB_THREADS) {
+    float v[LB];
+#pragma unroll
+    for (int u = 0; u < LB; ++u) {
+      const int e = e0 + u * UB_THREADS + threadIdx.x;
+      v[u] = 0.f;
+      if (e < n_in) {
+        const uint32_t q = (uint32_t)(q0 + e);
+        const uint32_t Y = fdiv(q, dzw), X = q - Y * (uint32_t)zw;
+        v[u] = __ldcs(pb + (int64_t)((Y & 1u) * 2u + (X & 1u)) * Q + (int64_t)(Y >> 1) * Wq + (X >> 1));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < LB; ++u) {
+      const int e = e0 + u * UB_THREADS + threadIdx.x;
+      if (e < n_in) stage[e] = v[u];
     }
   }
   __syncthreads();
-  float w[K * K];
+  float w[9];
 #pragma unroll
-  for (int i = 0; i < K * K; ++i) w[i] = kf[i];
+  for (int i = 0; i < 9; ++i) w[i] = kf[i];
   const int64_t b = plane / channels, c = plane - b * channels;
   const float nw = noise ? __ldg(noise_w) : 0.f;
   const float bv = bias ? __ldg(bias + c) : 0.f;
   const int64_t opl = (int64_t)oh * ow;
-  const int ox = ox0 + tx;
-  if (ox >= ow) return;
   const float* np = noise ? noise + b * opl : nullptr;
   float* op = out + plane * opl;
 #pragma unroll 4
-  for (int r = 0; r < TILE / TROWS; ++r) {
-    const int ly = ty + r * TROWS;
-    const int oy = oy0 + ly;
-    if (oy >= oh) break;
+  for (int j = threadIdx.x; j < q_out_end - q0; j += UB_THREADS) {
+    const uint32_t q = (uint32_t)(q0 + j);
+    const uint32_t Y = fdiv(q, dzw), X = q - Y * (uint32_t)zw;
+    if ((int)X >= ow) continue;
+    const int64_t o = (int64_t)Y * ow + X;
+    const float nz = np ? nw * __ldg(np + o) : 0.f;
+    const float* sp = stage + j;
     float acc = 0.f;
 #pragma unroll
-    for (int ky = 0; ky < K; ++ky)
+    for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-      for (int kx = 0; kx < K; ++kx) acc += w[ky * K + kx] * tile[ly + ky][tx + kx];
-    float v = acc + bv;
-    if (np) v += nw * __ldg(np + (int64_t)oy * ow + ox);
-    __stcs(op + (int64_t)oy * ow + ox, (v > 0.f ? v : v * alpha) * scale);
+      for (int kx = 0; kx < 3; ++kx) acc += w[ky * 3 + kx] * sp[ky * zw + kx];
+    const float r = acc + bv + nz;
+    __stcs(op + o, (r > 0.f ? r : r * alpha) * scale);
   }
 }
 
@@ -173,11 +237,19 @@ extern "C" int spgan_upblur_act(float* out, const float* pp, const float* kernel
   if (batch * channels == 0 || oh <= 0 || ow <= 0) return 0;
   SPGAN_CHECK_ARG(out && pp && kernel, "spgan_upblur_act: null pointer");
   SPGAN_CHECK_ARG((noise == nullptr) == (noise_w == nullptr), "spgan_upblur_act: noise and noise_w go together");
-  const int tiles_x = (ow + TILE - 1) / TILE, tiles_y = (oh + TILE - 1) / TILE;
-  const int64_t blocks = batch * channels * tiles_x * tiles_y;
-  SPGAN_CHECK_ARG(blocks <= 2147483647LL, "spgan_upblur_act: too many tiles");
-  upblur_act_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(out, pp, kernel, noise, noise_w, bias, channels, zh,
-                                                                       zw, Hq, Wq, oh, ow, tiles_x, tiles_y, alpha, scale);
+  SPGAN_CHECK_ARG((int64_t)zh * zw < (1LL << 30), "spgan_upblur_act: image %dx%d too large", zh, zw);
+  const int total = oh * zw;  // flat lattice points that can hold an output
+  const int max_chunk = UB_THREADS * UB_MAX_ITER;
+  const int chunks_per_plane = (total + max_chunk - 1) / max_chunk;
+  int chunk = (total + chunks_per_plane - 1) / chunks_per_plane;
+  chunk = (chunk + 31) / 32 * 32;
+  const int64_t blocks = batch * channels * chunks_per_plane;
+  SPGAN_CHECK_ARG(blocks <= 2147483647LL, "spgan_upblur_act: too many chunks");
+  const size_t smem = (size_t)(chunk + 2 * zw + 2) * sizeof(float);
+  SPGAN_CHECK_ARG(smem <= 48 * 1024, "spgan_upblur_act: rows of %d pixels exceed the staging buffer", zw);
+  upblur_act_kernel<<<(unsigned)blocks, UB_THREADS, smem, (cudaStream_t)stream>>>(
+      out, pp, kernel, noise, noise_w, bias, channels, zh, zw, Hq, Wq, oh, ow, chunk, chunks_per_plane,
+      make_fastdiv((uint32_t)zw), alpha, scale);
   SPGAN_CHECK_LAUNCH("spgan_upblur_act");
   return 0;
 }

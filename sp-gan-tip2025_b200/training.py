@@ -175,12 +175,13 @@ class TrainStep:
         img, styles, structure = self.G(gl, lat, coords, cps, noises=noises, return_latents=True)
         return img, ac, styles, structure, lat
 
-    def d_step(self):
+    def d_step(self, real=None):
+        """`real` = (images (B,3,101,101), ac_coords (B,3)) from the caller's data loader, or None for synthetic."""
         requires_grad(self.G, False)
         requires_grad(self.D, True)
         with torch.no_grad():
             fake, fake_ac, _, _, _ = self._fake()
-        real, real_ac = self.sampler.real()
+        real, real_ac = real if real is not None else self.sampler.real()
         fp, rp = self.D(fake), self.D(real)
         loss = d_logistic_loss(rp["d_patch"], fp["d_patch"])
         loss = loss + (coord_ac_loss(rp["ac_coords_pred"], real_ac) + coord_ac_loss(fp["ac_coords_pred"], fake_ac)) * \
@@ -191,9 +192,10 @@ class TrainStep:
         self.d_optim.step()
         return loss.detach()
 
-    def d_r1_step(self):
+    def d_r1_step(self, real=None):
         tp = self.config.train_params
-        real, _ = self.sampler.real()
+        requires_grad(self.D, True)
+        real = real[0].detach().clone() if real is not None else self.sampler.real()[0]
         real.requires_grad_(True)
         rp = self.D(real)
         r1 = d_r1_loss(rp["d_patch"], real)
@@ -220,6 +222,8 @@ class TrainStep:
 
     def g_path_step(self):
         tp = self.config.train_params
+        requires_grad(self.G, True)
+        requires_grad(self.D, False)
         pb = max(1, self.batch // tp.path_batch_shrink)
         gl, lat = self.sampler.latents(pb)
         coords, cps, _ = self.sampler.coords(pb)
@@ -236,6 +240,10 @@ class TrainStep:
         self.g_optim.step()
         return penalty.detach()
 
+    def ema_step(self):
+        if self.G_ema is not None:
+            accumulate(self.G_ema, self.G)
+
     def step(self, lazy="schedule"):
         """One training iteration (train.py:200-415): D step, [R1 every d_reg_every], G step, [path-length every
         g_reg_every], EMA.  lazy="schedule" follows the reference's cadence (g_path_start ignored),
@@ -247,7 +255,6 @@ class TrainStep:
         out["g"] = self.g_step()
         if lazy == "all" or (lazy == "schedule" and self.iter % tp.g_reg_every == 0):
             out["path"] = self.g_path_step()
-        if self.G_ema is not None:
-            accumulate(self.G_ema, self.G)
+        self.ema_step()
         self.iter += 1
         return out
