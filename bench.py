@@ -35,6 +35,7 @@ def parse():
     ap.add_argument("--precision", type=int, default=1, choices=[0, 1, 2])
     ap.add_argument("--cpu-sample-patches", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-calls", action="store_true", help="add per-entry-point CUDA-event times of one extra step")
     ap.add_argument("--workload", default="panorama", choices=["panorama", "train"],
                     help="panorama = BASELINE configs[1] (default, the headline); train = configs[2], full G+D step")
     ap.add_argument("--train-batch", type=int, default=8)
@@ -227,6 +228,13 @@ def run_ours(args):
     ms_step = ms_total / args.steps
     value = world * B / (ms_step / 1000.0)
 
+    call_ms = None
+    if args.profile_calls:
+        SF.profile_calls(True)
+        ms_prof = timed(step_resident, 1)
+        call_ms = {k: [round(v[0], 3), v[1]] for k, v in sorted(SF.profile_calls(False).items(), key=lambda kv: -kv[1][0])}
+        call_ms["_step_total_ms"] = ms_prof
+
     step_e2e()
     ms_e2e = timed(step_e2e, args.steps) / args.steps
     e2e_value = world * B / (ms_e2e / 1000.0)
@@ -267,6 +275,8 @@ def run_ours(args):
         "achieved_model_tflops": world * B * n_pos * PATCH_GFLOP / 1000.0 / (ms_step / 1000.0),
         "clocks": clocks, "roofline": roofline,
     }
+    if call_ms is not None:
+        out["call_ms"] = call_ms
     if not args.no_cpu_baseline and world >= 1:
         rate, threads, dt, total = cpu_reference_rate(args.cpu_sample_patches)
         out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
@@ -388,6 +398,12 @@ def run_train(args):
     gemm_stats = SF.profile_gemm(False)
     clocks = sampler.stop() if sampler else None
     ms_e2e = measure(args.steps, True)
+    call_ms = None
+    if args.profile_calls:
+        SF.profile_calls(True)
+        ms_prof = measure(1, False)
+        call_ms = {k: [round(v[0], 3), v[1]] for k, v in sorted(SF.profile_calls(False).items(), key=lambda kv: -kv[1][0])}
+        call_ms["_all_parts_ms"] = sum(ms_prof.values())
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -427,6 +443,8 @@ def run_train(args):
                      "avg_launch_ms": gemm_stats["ms"] / max(gemm_stats["launches"], 1),
                      "share_of_step": gemm_stats["ms"] / (all_ms if all_ms else 1.0)},
     }
+    if call_ms is not None:
+        out["call_ms"] = call_ms
     if not args.no_cpu_baseline:
         rate, threads, dt = cpu_train_rate(2)
         out["cpu_baseline"] = {"value": rate, "unit": TRAIN_UNIT, "cores": threads, "kind": "port",

@@ -146,9 +146,13 @@ int spgan_conv_wgrad(const SpganConvPass* p, float* dw, const float* g, const fl
  * spgan_pack_act: x (B, C, H, W) fp32 [* in_mul (B, C)] -> out [2][B*Hl*Wl][Cp] bf16; image pixel (y, x) lands on
  *   lattice point (y + pad_y0, x + pad_x0) of the (Hl, Wl) lattice, everything else (borders, channels C..Cp-1,
  *   Cp a multiple of 64) is zero.  Carries the style modulation of models/ops.py:598-600 (applied to the
- *   activations instead of the weights). */
+ *   activations instead of the weights).
+ *   step s > 1 writes s*s polyphase planes, out [2][s*s][B*Hl*Wl][Cp]: lattice point (i, j) of phase py*s + px holds image
+ *   pixel (i*s + py - pad_y0, j*s + px - pad_x0).  A strided conv (the discriminator's stride-2 convs, models/ops.py:175;
+ *   the stride-3 conv behind the spherical gather, models/spgan_ops_gs.py:814) is then a stride-1 conv whose taps pick
+ *   their phase plane. */
 int spgan_pack_act(uint16_t* out, const float* x, const float* in_mul, int B, int C, int H, int W, int Cp, int pad_y0,
-                   int pad_x0, int Hl, int Wl, void* stream);
+                   int pad_x0, int Hl, int Wl, int step, void* stream);
 /* spgan_pack_weight: w[o*ws_o + c*ws_c + tap_w[t]] fp32 -> out [2][ntaps][Cout][Cp] bf16 (merged == 0) or
  *   [2][1][Cout][ntaps*Cp] (merged != 0, k = t*Cp + c: the layout that pairs with spgan_sphere_pack). */
 int spgan_pack_weight(uint16_t* out, const float* w, int Cout, int Cin, int64_t ws_o, int64_t ws_c, int ntaps,
@@ -170,12 +174,33 @@ int spgan_sphere_pack(uint16_t* out, const float* x_nhwc, const float* coords, c
 /* spgan_conv_gemm: the tcgen05 kernel.  `p` is a conv pass whose (H, W) are the LATTICE dims (Hl, Wl) of the packed
  *   activation, Cin is ignored (K per tap = kp, a multiple of 64), in_stride must be 1, tap_w is ignored (the packed
  *   weight is already in tap order) and precision must be 1 or 2.  a_packed [2][a_rows][kp], w_packed
- *   [2][ntaps][Cout][kp].  Epilogue terms as in spgan_conv_pass. */
+ *   [2][ntaps][Cout][kp].  a_rows = phases * B*H*W; a tap reads phase plane f by carrying f * B*H in its tap_dy (the row
+ *   offset of a tap is tap_dy*W + tap_dx).  Epilogue terms as in spgan_conv_pass. */
 int spgan_conv_gemm(const SpganConvPass* p, float* y, const uint16_t* a_packed, int64_t a_rows, int kp,
                     const uint16_t* w_packed, const float* out_mul, const float* noise, const float* noise_w,
                     const float* bias, const float* residual, void* stream);
 /* Number of tcgen05 GEMM launches since load (the bench's gpu_launches evidence for the tensor path). */
 int64_t spgan_gemm_launch_count(void);
+
+/* ---- weight gradient on tcgen05 ---------------------------------------------------------------------------------
+ * dW[t][o][c] = out_scale * sum_q G'[o][q] * X'[phase_t][c][q + off_t] over the flattened lattice q = (b*Hl + i)*Wl + j
+ * (replaces cuDNN wgrad of models/ops.py:617, 634, 175 and models/spgan_ops_gs.py:814 under autograd).
+ *
+ * spgan_pack_kmajor: x (B, C, H, W) fp32 [* mul (B, C)] -> out [2][step*step][C][qstride] bf16 hi/lo, PIXEL-contiguous:
+ *   column b*Hl*Wl + i*Wl + j of phase py*step + px holds pixel (i*step + py - pad_y0, j*step + px - pad_x0), zero
+ *   outside the image.  qstride >= B*Hl*Wl, a multiple of 8.  Used for both operands: the output gradient (mul = the
+ *   demodulation, step = the pass's out_stride) and the input (mul = the style modulation, step = the pass's in_stride). */
+int spgan_pack_kmajor(uint16_t* out, const float* x, const float* mul, int B, int C, int H, int W, int step, int pad_y0,
+                      int pad_x0, int Hl, int Wl, int64_t qstride, void* stream);
+/* spgan_conv_wgrad_gemm: `p` describes the pass on the common lattice: (B, H, W) = (B, Hl, Wl), Cin, Cout, ntaps,
+ *   tap_dy/tap_dx = non-negative lattice offsets of each tap inside ITS phase plane of x_packed (tap_phase[t], NULL = 0),
+ *   tap_w/ws_o/ws_c = where the tap lives in dw, out_scale, precision 1 (bf16x3) or 2 (bf16).  g_packed has g_phases
+ *   planes of which this pass reads g_phase.  workspace: fp32 scratch of at least spgan_conv_wgrad_gemm_workspace(p)
+ *   elements (per-K-chunk partial tiles, summed in a fixed order: results are deterministic).  accumulate != 0 adds to dw. */
+int64_t spgan_conv_wgrad_gemm_workspace(const SpganConvPass* p);
+int spgan_conv_wgrad_gemm(const SpganConvPass* p, float* dw, const uint16_t* g_packed, int g_phases, int g_phase,
+                          const uint16_t* x_packed, int x_phases, const int32_t* tap_phase, int64_t qstride,
+                          float* workspace, int64_t workspace_elems, int accumulate, void* stream);
 
 /* Per-plane dot products: out[p] = sum_k a[p,k] * b[p,k]; planes x inner.  Used for the style / demodulation
  * gradients (d s[b,c] = <x[b,c], dxs[b,c]>). */

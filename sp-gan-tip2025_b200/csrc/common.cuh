@@ -46,3 +46,25 @@ static inline int grid_for(int64_t work, int64_t per_block, int ctas_per_sm, int
   if (need < 1) need = 1;
   return (int)(need < cap ? need : cap);
 }
+
+// Exact unsigned division by a runtime-constant divisor (Granlund-Montgomery), so that flat-index kernels can decode
+// (row, column) without the ~25-instruction hardware-emulated integer division.
+struct FastDiv {
+  uint32_t d, m, s1, s2;
+};
+static inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  f.d = d;
+  uint32_t l = 0;
+  while ((1ull << l) < d) ++l;
+  f.m = (uint32_t)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+  f.s1 = l < 1 ? l : 1;
+  f.s2 = l > 0 ? l - 1 : 0;
+  return f;
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) {
+  const uint32_t t = __umulhi(f.m, n);
+  return (t + ((n - t) >> f.s1)) >> f.s2;
+}
+#endif

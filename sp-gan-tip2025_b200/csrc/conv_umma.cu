@@ -14,22 +14,11 @@
 //               scatter to the NCHW fp32 output.  Two accumulator stages (2 x 256 TMEM columns) overlap the epilogue of
 //               tile i with the mainloop of tile i+1.
 // Roofline: tensor pipe.  FLOPs per launch = 2 * rows * Cout * ntaps * kp (x3 issued MMAs in bf16x3 mode).
-#include "common.cuh"
+#include "umma_common.cuh"
 
 #include <atomic>
 
-#include <cuda.h>
-#include <cuda_bf16.h>
-
 namespace {
-
-constexpr int GEMM_BLOCK_M = 128;
-constexpr int GEMM_BLOCK_N = 256;
-constexpr int GEMM_BLOCK_K = 64;  // bf16 elements = one 128-byte swizzle row
-constexpr int GEMM_UMMA_K = 16;
-constexpr int GEMM_THREADS = 192;
-constexpr int A_TILE_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;  // 16 KiB
-constexpr int B_TILE_BYTES = GEMM_BLOCK_N * GEMM_BLOCK_K * 2;  // 32 KiB
 
 struct GemmParams {
   int32_t rows;        // B * Hl * Wl lattice points
@@ -45,105 +34,6 @@ struct GemmParams {
   int32_t act;
   float act_alpha, act_gain;
 };
-
-// ------------------------------------------------------------------------------------------------ PTX helpers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug must surface as a trapped kernel (an error code at the C ABI), never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  unsigned long long t0 = 0;
-  for (uint32_t it = 1;; ++it) {
-    if (mbar_try_wait(bar, parity)) return;
-    if ((it & 0x3ff) == 0) {
-      unsigned long long now;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-      if (t0 == 0) t0 = now;
-      if (now - t0 > 4000000000ull) {  // 4 s
-        printf("spgan conv_gemm: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x,
-               threadIdx.x, bar, parity);
-        __trap();
-      }
-    }
-  }
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
-      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
-                                            int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
-      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                           uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// K-major, 128-byte swizzle, 8-row core-matrix groups 1024 bytes apart (cute::UMMA::SmemDescriptor, version 1).
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);  // start address, bits [0,14)
-  d |= (uint64_t)1 << 16;                       // leading byte offset (unused for swizzled K-major), bits [16,30)
-  d |= (uint64_t)(1024 >> 4) << 32;             // stride byte offset, bits [32,46)
-  d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
-  return d;
-}
-__device__ __forceinline__ uint32_t umma_idesc_bf16(int n) {
-  return (1u << 4)                  // D format f32
-         | (1u << 7)                // A format bf16
-         | (1u << 10)               // B format bf16
-         | ((uint32_t)(n >> 3) << 17)
-         | ((uint32_t)(GEMM_BLOCK_M >> 4) << 24);  // A, B K-major: bits 15, 16 stay 0
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-  uint32_t* r = reinterpret_cast<uint32_t*>(v);
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 
 // ------------------------------------------------------------------------------------------------ GEMM kernel
 template <int kPasses>
@@ -358,30 +248,29 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------------ operand packers
-__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
-  hi = __float2bfloat16_rn(v);
-  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-}
-
-// One CTA: 64 channels x 64 consecutive lattice points of one sample.  Reads coalesced along pixels, writes
-// coalesced along channels (bf16x2 per lane, 128 bytes per warp).
+// One CTA: 64 channels x 64 consecutive lattice points of one sample (and one polyphase plane).  Reads coalesced along
+// pixels, writes coalesced along channels (bf16x2 per lane, 128 bytes per warp).  With step s > 1 the lattice point
+// (i, j) of phase (py, px) holds source pixel (i*s + py - pad_y, j*s + px - pad_x): a strided conv becomes a stride-1
+// conv whose taps pick their phase plane (rows [ph * B*Hl*Wl, (ph+1) * B*Hl*Wl) of the packed matrix).
 __global__ void __launch_bounds__(256) pack_act_kernel(__nv_bfloat16* __restrict__ out, const float* __restrict__ x,
                                                       const float* __restrict__ in_mul, int B, int C, int H, int W,
-                                                      int Cp, int pad_y, int pad_x, int Hl, int Wl) {
+                                                      int Cp, int pad_y, int pad_x, int Hl, int Wl, int step) {
   // (pad_y, pad_x) = top/left offset of the image inside the (Hl, Wl) lattice
   __shared__ float tile[64][65];
   const int plane_l = Hl * Wl;
   const int q0 = blockIdx.x * 64;  // lattice point within the sample
   const int c0 = blockIdx.y * 64;
-  const int b = blockIdx.z;
+  const int ph = blockIdx.z / B;
+  const int b = blockIdx.z - ph * B;
+  const int py = ph / step, px = ph - py * step;
   const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
   {
     const int q = q0 + tx;
     int sy = -1, sx = -1;
     if (q < plane_l) {
       const int i = q / Wl, j = q - i * Wl;
-      sy = i - pad_y;
-      sx = j - pad_x;
+      sy = i * step + py - pad_y;
+      sx = j * step + px - pad_x;
     }
     const bool inside = sy >= 0 && sy < H && sx >= 0 && sx < W;
     // all 16 loads of a thread are in flight before the first shared-memory store (bytes in flight cover the latency)
@@ -398,7 +287,7 @@ __global__ void __launch_bounds__(256) pack_act_kernel(__nv_bfloat16* __restrict
   }
   __syncthreads();
   const int cpair = threadIdx.x & 31, prow = threadIdx.x >> 5;
-  const int64_t rows_total = (int64_t)B * plane_l;
+  const int64_t rows_total = (int64_t)step * step * B * plane_l;
   __nv_bfloat16* out_lo = out + rows_total * Cp;
 #pragma unroll
   for (int pp = prow; pp < 64; pp += 8) {
@@ -408,7 +297,7 @@ __global__ void __launch_bounds__(256) pack_act_kernel(__nv_bfloat16* __restrict
     __nv_bfloat16 h0, l0, h1, l1;
     split_bf16(v0, h0, l0);
     split_bf16(v1, h1, l1);
-    const int64_t off = ((int64_t)b * plane_l + q) * Cp + c0 + 2 * cpair;
+    const int64_t off = (((int64_t)ph * B + b) * plane_l + q) * Cp + c0 + 2 * cpair;
     *reinterpret_cast<__nv_bfloat162*>(out + off) = __halves2bfloat162(h0, h1);
     *reinterpret_cast<__nv_bfloat162*>(out_lo + off) = __halves2bfloat162(l0, l1);
   }
@@ -647,34 +536,6 @@ __global__ void __launch_bounds__(256) sphere_pack_shared_kernel(__nv_bfloat16* 
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (fn) return fn;
-  void* sym = nullptr;
-  cudaDriverEntryPointQueryResult qres;
-  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
-      qres != cudaDriverEntryPointSuccess || sym == nullptr)
-    return nullptr;
-  fn = (EncodeTiledFn)sym;
-  return fn;
-}
-
-int encode_bf16_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                    const cuuint32_t* box, const char* who) {
-  EncodeTiledFn fn = get_encode_fn();
-  SPGAN_CHECK_ARG(fn != nullptr, "%s: cuTensorMapEncodeTiled is not available from the CUDA driver", who);
-  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
-                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  SPGAN_CHECK_ARG(r == CUDA_SUCCESS, "%s: cuTensorMapEncodeTiled failed with CUresult %d", who, (int)r);
-  return 0;
-}
-
 std::atomic<long long>* launch_counter() {
   static std::atomic<long long> c{0};
   return &c;
@@ -705,16 +566,17 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams
 extern "C" int64_t spgan_gemm_launch_count(void) { return (int64_t)launch_counter()->load(); }
 
 extern "C" int spgan_pack_act(uint16_t* out, const float* x, const float* in_mul, int B, int C, int H, int W, int Cp,
-                              int pad_y, int pad_x, int Hl, int Wl, void* stream) {
+                              int pad_y, int pad_x, int Hl, int Wl, int step, void* stream) {
   SPGAN_CHECK_ARG(B >= 0 && C >= 0 && H >= 0 && W >= 0 && pad_y >= 0 && pad_x >= 0, "spgan_pack_act: negative size");
-  SPGAN_CHECK_ARG(Hl >= H + pad_y && Wl >= W + pad_x, "spgan_pack_act: lattice %dx%d smaller than the padded image", Hl, Wl);
+  SPGAN_CHECK_ARG(step >= 1 && step <= 8, "spgan_pack_act: step %d unsupported", step);
+  SPGAN_CHECK_ARG(step > 1 || (Hl >= H + pad_y && Wl >= W + pad_x), "spgan_pack_act: lattice %dx%d smaller than the padded image", Hl, Wl);
   SPGAN_CHECK_ARG(Cp >= C && Cp % 64 == 0, "spgan_pack_act: Cp=%d must be a multiple of 64 and >= C=%d", Cp, C);
   if (B == 0 || Cp == 0 || H == 0 || W == 0) return 0;
   SPGAN_CHECK_ARG(out && x, "spgan_pack_act: null pointer");
-  SPGAN_CHECK_ARG(B <= 65535, "spgan_pack_act: batch %d > 65535", B);
-  dim3 grid((Hl * Wl + 63) / 64, Cp / 64, B);
+  SPGAN_CHECK_ARG(B * step * step <= 65535, "spgan_pack_act: batch %d x %d phases > 65535", B, step * step);
+  dim3 grid((Hl * Wl + 63) / 64, Cp / 64, B * step * step);
   pack_act_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)out, x, in_mul, B, C, H, W, Cp, pad_y, pad_x,
-                                                          Hl, Wl);
+                                                          Hl, Wl, step);
   SPGAN_CHECK_LAUNCH("spgan_pack_act");
   return 0;
 }
@@ -789,7 +651,9 @@ extern "C" int spgan_conv_gemm(const SpganConvPass* p, float* y, const uint16_t*
   SPGAN_CHECK_ARG(p->B >= 0 && p->H >= 0 && p->W >= 0 && p->Cout >= 0, "spgan_conv_gemm: negative size");
   SPGAN_CHECK_ARG(p->out_stride >= 1, "spgan_conv_gemm: out_stride must be >= 1");
   const int64_t rows = (int64_t)p->B * p->H * p->W;
-  SPGAN_CHECK_ARG(rows == a_rows, "spgan_conv_gemm: a_rows=%lld does not match B*H*W=%lld", (long long)a_rows, (long long)rows);
+  SPGAN_CHECK_ARG(rows > 0 ? (a_rows >= rows && a_rows % rows == 0) : a_rows == 0,
+                  "spgan_conv_gemm: a_rows=%lld is not a multiple (polyphase planes) of B*H*W=%lld", (long long)a_rows, (long long)rows);
+  SPGAN_CHECK_ARG(a_rows < 2147483647LL - 65536, "spgan_conv_gemm: too many packed rows");
   SPGAN_CHECK_ARG(rows < 2147483647LL - 65536, "spgan_conv_gemm: too many lattice points");
   if (rows == 0 || p->Cout == 0 || p->My == 0 || p->Mx == 0) return 0;
   SPGAN_CHECK_ARG(p->Cout >= 16, "spgan_conv_gemm: Cout=%d < 16 belongs on the SIMT path", p->Cout);
@@ -822,8 +686,8 @@ extern "C" int spgan_conv_gemm(const SpganConvPass* p, float* y, const uint16_t*
 
   CUtensorMap tmA, tmB;
   {
-    cuuint64_t dims[3] = {(cuuint64_t)kp, (cuuint64_t)rows, 2};
-    cuuint64_t strides[2] = {(cuuint64_t)kp * 2, (cuuint64_t)rows * kp * 2};
+    cuuint64_t dims[3] = {(cuuint64_t)kp, (cuuint64_t)a_rows, 2};
+    cuuint64_t strides[2] = {(cuuint64_t)kp * 2, (cuuint64_t)a_rows * kp * 2};
     cuuint32_t box[3] = {GEMM_BLOCK_K, GEMM_BLOCK_M, 1};
     if (int e = encode_bf16_map(&tmA, a_packed, 3, dims, strides, box, "spgan_conv_gemm (A map)")) return e;
   }

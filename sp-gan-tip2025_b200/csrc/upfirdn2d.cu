@@ -55,26 +55,6 @@ __global__ void __launch_bounds__(256) upfirdn2d_generic(float* __restrict__ out
 constexpr int TILE = 64;
 constexpr int TROWS = 4;  // thread rows
 
-// Exact unsigned division by a runtime-constant divisor (Granlund-Montgomery), so that flat-index kernels can decode
-// (row, column) without the ~25-instruction hardware-emulated integer division.
-struct FastDiv {
-  uint32_t d, m, s1, s2;
-};
-static inline FastDiv make_fastdiv(uint32_t d) {
-  FastDiv f;
-  f.d = d;
-  uint32_t l = 0;
-  while ((1ull << l) < d) ++l;
-  f.m = (uint32_t)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
-  f.s1 = l < 1 ? l : 1;
-  f.s2 = l > 0 ? l - 1 : 0;
-  return f;
-}
-__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) {
-  const uint32_t t = __umulhi(f.m, n);
-  return (t + ((n - t) >> f.s1)) >> f.s2;
-}
-
 // Tiled FIR (up = down = 1, K x K, zero padding): 64x64 output tile per CTA.  All of a thread's ~17 input loads are issued
 // before the first shared-memory store (>= 64 KB in flight per SM: the kernel sits on HBM bandwidth, not on load latency),
 // and each thread filters a vertical strip of 16 rows with a sliding window (K shared-memory reads per output, not K*K).

@@ -48,15 +48,48 @@ def profile_gemm(on):
             "launches": len(rec)}
 
 
-def _gemm_call(flops, *args):
+def profile_calls(on):
+    """bench.py --profile-calls: bracket EVERY C-ABI call with CUDA events on the launching stream (warm, in-situ
+    durations; ncu's per-launch times are cold-cache and serialised).  profile_calls(False) returns
+    {entry point: (ms, calls)}."""
+    global _CALLS
+    if on:
+        _CALLS = []
+
+        def hook(name, tok):
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            if tok is None:
+                return e
+            _CALLS.append((name, tok, e))
+        lib.set_call_hook(hook)
+        return None
+    lib.set_call_hook(None)
+    rec, _CALLS = _CALLS or [], None
+    torch.cuda.synchronize()
+    out = {}
+    for name, a, b in rec:
+        ms, n = out.get(name, (0.0, 0))
+        out[name] = (ms + a.elapsed_time(b), n + 1)
+    return out
+
+
+_CALLS = None
+
+
+def _timed_call(flops, name, *args):
     if _PROFILE is None:
-        lib.call("spgan_conv_gemm", *args)
+        lib.call(name, *args)
         return
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    lib.call("spgan_conv_gemm", *args)
+    lib.call(name, *args)
     e1.record()
     _PROFILE.append((e0, e1, flops))
+
+
+def _gemm_call(flops, *args):
+    _timed_call(flops, "spgan_conv_gemm", *args)
 
 
 def _stream(t):
@@ -428,7 +461,28 @@ def clear_weight_cache():
 
 # --------------------------------------------------------------------------------------------------- conv driver
 def _tensor_path_ok(passes, Cin, Cout, precision):
-    return precision != 0 and Cin >= 16 and Cout >= 16 and all(p["in_stride"] == 1 for p in passes)
+    return precision != 0 and Cin >= 16 and Cout >= 16 and len({p["in_stride"] for p in passes}) == 1
+
+
+def _phase_taps(passes):
+    """Map every tap of every pass onto the polyphase lattice of the input: with s = in_stride and the taps shifted by
+    (pt, pl) to be non-negative, input row i*s + dy + pt = s*(i + (dy+pt)//s) + (dy+pt)%s.  Returns
+    (s, pt, pl, Hl, Wl, per-pass [(phase, oy, ox, widx)]) where (Hl, Wl) is the smallest lattice on which no tap of a valid
+    lattice point wraps around a row."""
+    s = passes[0]["in_stride"]
+    dy_all = [t[0] for p in passes for t in p["taps"]]
+    dx_all = [t[1] for p in passes for t in p["taps"]]
+    pt, pl = max(0, -min(dy_all)), max(0, -min(dx_all))
+    mapped, Hl, Wl = [], 1, 1
+    for p in passes:
+        cur = []
+        for dy, dx, wi in p["taps"]:
+            vy, vx = dy + pt, dx + pl
+            cur.append(((vy % s) * s + (vx % s), vy // s, vx // s, wi))
+        mapped.append(cur)
+        Hl = max(Hl, p["My"] + max(t[1] for t in cur))
+        Wl = max(Wl, p["Mx"] + max(t[2] for t in cur))
+    return s, pt, pl, Hl, Wl, mapped
 
 
 def conv_apply(x, w, geom, adjoint=False, out_hw=None, in_mul=None, out_mul=None, out_scale=1.0, noise=None,
@@ -492,26 +546,23 @@ def conv_apply(x, w, geom, adjoint=False, out_hw=None, in_mul=None, out_mul=None
 
     with torch.cuda.device(x.device):
         if _tensor_path_ok(passes, Cin, Cout, precision):
-            # one packed activation shared by all passes: pads cover every pass's tap reach
-            dy_all = [t[0] for p in passes for t in p["taps"]]
-            dx_all = [t[1] for p in passes for t in p["taps"]]
-            pt, pl = max(0, -min(dy_all)), max(0, -min(dx_all))
-            reach_y = max(p["My"] - 1 + max(t[0] for t in p["taps"]) for p in passes)
-            reach_x = max(p["Mx"] - 1 + max(t[1] for t in p["taps"]) for p in passes)
-            Hl = pt + max(H, reach_y + 1)
-            Wl = pl + max(W, reach_x + 1)
+            # one packed activation shared by all passes: pads cover every pass's tap reach; a strided conv reads the
+            # polyphase planes of the input (spgan_pack_act with step = stride)
+            step, pt, pl, Hl, Wl, mapped = _phase_taps(passes)
+            if step == 1:
+                Hl, Wl = max(Hl, pt + H), max(Wl, pl + W)
             Cp = _round_up(Cin, 64)
             rows = B * Hl * Wl
-            a_packed = torch.empty((2, rows, Cp), device=x.device, dtype=torch.bfloat16)
-            lib.call("spgan_pack_act", _ptr(a_packed), _ptr(x), _ptr(im), B, Cin, H, W, Cp, pt, pl, Hl, Wl, st)
-            for p in passes:
+            a_packed = torch.empty((2, step * step * rows, Cp), device=x.device, dtype=torch.bfloat16)
+            lib.call("spgan_pack_act", _ptr(a_packed), _ptr(x), _ptr(im), B, Cin, H, W, Cp, pt, pl, Hl, Wl, step, st)
+            for p, taps in zip(passes, mapped):
                 q, yptr, o_h, o_w, cst = target(p)
-                shifted = dict(q, taps=[(dy + pt, dx + pl, wi) for dy, dx, wi in p["taps"]])
+                shifted = dict(q, in_stride=1, taps=[(ph * B * Hl + oy, ox, wi) for ph, oy, ox, wi in taps])
                 cp = _fill_pass(shifted, B, Cin, Hl, Wl, Cout, o_h, o_w, ws_o, ws_c, out_scale, act_on, a, g, precision, cst)
                 wp = _packed_weight(w, Cout, Cin, ws_o, ws_c, [t[2] for t in p["taps"]], Cp, False)
                 valid = min(p["My"], _ceil_div(oh - p["off_y"], p["out_stride"])) * min(p["Mx"], _ceil_div(ow - p["off_x"], p["out_stride"]))
-                _gemm_call(2.0 * B * valid * Cout * Cin * len(p["taps"]), ctypes.byref(cp), yptr, _ptr(a_packed), rows,
-                           Cp, _ptr(wp), _ptr(om), _ptr(nz), _ptr(nwt), _ptr(bs), _ptr(rs), st)
+                _gemm_call(2.0 * B * valid * Cout * Cin * len(p["taps"]), ctypes.byref(cp), yptr, _ptr(a_packed),
+                           step * step * rows, Cp, _ptr(wp), _ptr(om), _ptr(nz), _ptr(nwt), _ptr(bs), _ptr(rs), st)
         else:
             for p in passes:
                 q, yptr, o_h, o_w, cst = target(p)
@@ -521,7 +572,7 @@ def conv_apply(x, w, geom, adjoint=False, out_hw=None, in_mul=None, out_mul=None
     return y
 
 
-def conv_wgrad(g, x, w_shape, geom, in_mul=None, out_mul=None, out_scale=1.0):
+def conv_wgrad(g, x, w_shape, geom, in_mul=None, out_mul=None, out_scale=1.0, precision=None):
     """dw[o,c,ky,kx] = out_scale * sum_b <out_mul*g, L_{e(o,c,ky,kx)}(in_mul*x)> for the BASE conv of `geom`
     (x = base input (B, C, H, W), g = base output gradient (B, O, oh, ow))."""
     g = _f32c(g, "conv wgrad")
@@ -536,6 +587,29 @@ def conv_wgrad(g, x, w_shape, geom, in_mul=None, out_mul=None, out_scale=1.0):
     passes, _ = plan_passes(geom, False, (H, W), (oh, ow))
     im = _f32c(in_mul, "conv wgrad") if in_mul is not None else None
     om = _f32c(out_mul, "conv wgrad") if out_mul is not None else None
+    precision = _PRECISION if precision is None else precision
+    if passes and _tensor_path_ok(passes, C, O, precision) and len({p["out_stride"] for p in passes}) == 1:
+        # tcgen05: contraction over the flattened lattice of pixel-contiguous bf16 hi/lo copies (spgan_pack_kmajor)
+        s_in, pt, pl, Hl, Wl, mapped = _phase_taps(passes)
+        s_out = passes[0]["out_stride"]
+        Q = B * Hl * Wl
+        qstride = _round_up(Q, 8)
+        st = _stream(x)
+        with torch.cuda.device(x.device):
+            gp = torch.empty((2, s_out * s_out, O, qstride), device=x.device, dtype=torch.bfloat16)
+            xp = torch.empty((2, s_in * s_in, C, qstride), device=x.device, dtype=torch.bfloat16)
+            lib.call("spgan_pack_kmajor", _ptr(gp), _ptr(g), _ptr(om), B, O, oh, ow, s_out, 0, 0, Hl, Wl, qstride, st)
+            lib.call("spgan_pack_kmajor", _ptr(xp), _ptr(x), _ptr(im), B, C, H, W, s_in, pt, pl, Hl, Wl, qstride, st)
+            for p, taps in zip(passes, mapped):
+                q = dict(p, in_stride=1, out_stride=1, off_y=0, off_x=0, taps=[(oy, ox, wi) for _, oy, ox, wi in taps])
+                cp = _fill_pass(q, B, C, Hl, Wl, O, Hl, Wl, C * kk, kk, out_scale, 0, 0.0, 1.0, precision)
+                phases = (ctypes.c_int32 * len(taps))(*[t[0] for t in taps])
+                need = lib.load().spgan_conv_wgrad_gemm_workspace(ctypes.byref(cp))
+                ws = torch.empty((max(int(need), 1),), device=x.device, dtype=torch.float32)
+                flops = 2.0 * B * min(p["My"], oh) * min(p["Mx"], ow) * O * C * len(taps)
+                _timed_call(flops, "spgan_conv_wgrad_gemm", ctypes.byref(cp), _ptr(dw), _ptr(gp), s_out * s_out,
+                            p["off_y"] * s_out + p["off_x"], _ptr(xp), s_in * s_in, phases, qstride, _ptr(ws), int(need), 0, st)
+        return dw
     with torch.cuda.device(x.device):
         for p in passes:
             cp = _fill_pass(p, B, C, H, W, O, oh, ow, C * kk, kk, out_scale, 0, 0.0, 1.0, 0)

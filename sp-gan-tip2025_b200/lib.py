@@ -54,7 +54,11 @@ SIGNATURES = {
     "spgan_demod": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_f32, c_f32, c_vp]),
     "spgan_conv_wgrad": (c_int, [_PASS_P, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp]),
     "spgan_plane_dot": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp]),
-    "spgan_pack_act": (c_int, [c_vp, c_vp, c_vp] + [c_int] * 9 + [c_vp]),
+    "spgan_pack_act": (c_int, [c_vp, c_vp, c_vp] + [c_int] * 10 + [c_vp]),
+    "spgan_pack_kmajor": (c_int, [c_vp, c_vp, c_vp] + [c_int] * 9 + [c_i64, c_vp]),
+    "spgan_conv_wgrad_gemm_workspace": (c_i64, [_PASS_P]),
+    "spgan_conv_wgrad_gemm": (c_int, [_PASS_P, c_vp, c_vp, c_int, c_int, c_vp, c_int, ctypes.POINTER(ctypes.c_int32), c_i64,
+                                      c_vp, c_i64, c_int, c_vp]),
     "spgan_pack_weight": (c_int, [c_vp, c_vp, c_int, c_int, c_i64, c_i64, c_int, ctypes.POINTER(ctypes.c_int32), c_int, c_int, c_vp]),
     "spgan_nchw_to_nhwc": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp]),
     "spgan_sphere_pack": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
@@ -94,12 +98,23 @@ def last_error():
     return load().spgan_last_error().decode("utf-8", "replace")
 
 
+_hook = None  # optional profiler: _hook(name, None) -> token before the call, _hook(name, token) after it
+
+
+def set_call_hook(fn):
+    global _hook
+    _hook = fn
+
+
 def call(name, *args):
     """Invoke an int-returning entry point; non-zero -> RuntimeError carrying spgan_last_error()."""
     global _launches
+    tok = _hook(name, None) if _hook is not None else None
     rc = getattr(load(), name)(*args)
     if rc != 0:
         raise RuntimeError("%s failed (code %d): %s" % (name, rc, last_error()))
+    if _hook is not None:
+        _hook(name, tok)
     _launches += 1
 
 
