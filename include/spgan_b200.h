@@ -183,23 +183,19 @@ int spgan_conv_gemm(const SpganConvPass* p, float* y, const uint16_t* a_packed, 
 int64_t spgan_gemm_launch_count(void);
 
 /* ---- weight gradient on tcgen05 ---------------------------------------------------------------------------------
- * dW[t][o][c] = out_scale * sum_q G'[o][q] * X'[phase_t][c][q + off_t] over the flattened lattice q = (b*Hl + i)*Wl + j
- * (replaces cuDNN wgrad of models/ops.py:617, 634, 175 and models/spgan_ops_gs.py:814 under autograd).
- *
- * spgan_pack_kmajor: x (B, C, H, W) fp32 [* mul (B, C)] -> out [2][step*step][C][qstride] bf16 hi/lo, PIXEL-contiguous:
- *   column b*Hl*Wl + i*Wl + j of phase py*step + px holds pixel (i*step + py - pad_y0, j*step + px - pad_x0), zero
- *   outside the image.  qstride >= B*Hl*Wl, a multiple of 8.  Used for both operands: the output gradient (mul = the
- *   demodulation, step = the pass's out_stride) and the input (mul = the style modulation, step = the pass's in_stride). */
-int spgan_pack_kmajor(uint16_t* out, const float* x, const float* mul, int B, int C, int H, int W, int step, int pad_y0,
-                      int pad_x0, int Hl, int Wl, int64_t qstride, void* stream);
-/* spgan_conv_wgrad_gemm: `p` describes the pass on the common lattice: (B, H, W) = (B, Hl, Wl), Cin, Cout, ntaps,
- *   tap_dy/tap_dx = non-negative lattice offsets of each tap inside ITS phase plane of x_packed (tap_phase[t], NULL = 0),
- *   tap_w/ws_o/ws_c = where the tap lives in dw, out_scale, precision 1 (bf16x3) or 2 (bf16).  g_packed has g_phases
- *   planes of which this pass reads g_phase.  workspace: fp32 scratch of at least spgan_conv_wgrad_gemm_workspace(p)
- *   elements (per-K-chunk partial tiles, summed in a fixed order: results are deterministic).  accumulate != 0 adds to dw. */
+ * dW[t][o][c] = out_scale * sum_q G'[q][o] * X'[phase_t][q + off_t][c] over the flattened lattice q = (b*Hl + i)*Wl + j
+ * (replaces cuDNN wgrad of models/ops.py:617, 634, 175 and models/spgan_ops_gs.py:814 under autograd).  Both operands are
+ * spgan_pack_act outputs on one common (Hl, Wl) lattice: g_packed = pack of the output gradient with in_mul = the
+ * demodulation and step = the pass's out_stride ([2][g_phases*Q][gp_cols]); x_packed = pack of the input with in_mul =
+ * the style modulation and step = the pass's in_stride ([2][x_phases*Q][xp_cols]); Q = B*Hl*Wl.
+ * `p` describes the pass on that lattice: (B, H, W) = (B, Hl, Wl), Cin, Cout, ntaps, tap_dy/tap_dx = non-negative lattice
+ * offsets of each tap inside ITS phase plane of x_packed (tap_phase[t], NULL = 0), tap_w/ws_o/ws_c = where the tap lives
+ * in dw, out_scale, precision 1 (bf16x3) or 2 (bf16).  This pass reads phase plane g_phase of g_packed.  workspace: fp32
+ * scratch of at least spgan_conv_wgrad_gemm_workspace(p) elements (per-K-chunk partial tiles, summed in a fixed order:
+ * results are deterministic).  accumulate != 0 adds to dw. */
 int64_t spgan_conv_wgrad_gemm_workspace(const SpganConvPass* p);
 int spgan_conv_wgrad_gemm(const SpganConvPass* p, float* dw, const uint16_t* g_packed, int g_phases, int g_phase,
-                          const uint16_t* x_packed, int x_phases, const int32_t* tap_phase, int64_t qstride,
+                          int gp_cols, const uint16_t* x_packed, int x_phases, const int32_t* tap_phase, int xp_cols,
                           float* workspace, int64_t workspace_elems, int accumulate, void* stream);
 
 /* Per-plane dot products: out[p] = sum_k a[p,k] * b[p,k]; planes x inner.  Used for the style / demodulation

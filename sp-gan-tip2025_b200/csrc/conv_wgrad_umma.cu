@@ -1,13 +1,17 @@
 // Weight gradient of the conv passes on tcgen05 / TMEM (replaces cuDNN wgrad of the reference's F.conv2d /
 // F.conv_transpose2d calls, models/ops.py:617, 634, 175; models/spgan_ops_gs.py:814).
 //
-//   dW[t][o][c] = sum_q G'[o][q] * X'[phase_t][c][q + off_t],       q = (b*Hl + i)*Wl + j   (flattened lattice point)
+//   dW[t][o][c] = sum_q G'[g_phase][q][o] * X'[phase_t][q + off_t][c],     q = (b*Hl + i)*Wl + j  (flattened lattice point)
 //
-// G' = out_mul * g and X' = in_mul * x are PIXEL-contiguous ("K-major" for a contraction over pixels) bf16 hi/lo copies
-// on one common lattice (spgan_pack_kmajor); a conv tap is again a constant offset along the contraction index, so both
-// operand tiles are plain TMA boxes.  G' is zero at lattice points that are not outputs of the pass, which makes the
-// row wrap-around of the flattened index harmless.  Strided convs read X' from its polyphase planes (phase_t), the
-// parity passes of the transposed conv read G' from its polyphase planes (g_phase).
+// G' = out_mul * g and X' = in_mul * x are the SAME channels-last bf16 hi/lo packs the forward GEMM consumes
+// (spgan_pack_act: [2][phases * B*Hl*Wl][Cp]) on one common lattice.  The contraction runs over the ROW index of both
+// packs, so both operands are "MN-major" for tcgen05 (instruction-descriptor bits 15/16): a tile is a stack of TMA boxes
+// of 64 pixel rows x 64 channels (128-byte swizzle), and a conv tap is a shift of the X' row coordinate.  (A
+// pixel-contiguous K-major layout does not work: the tap shift would land on the INNER TMA coordinate, which must be a
+// multiple of 16 bytes — an odd offset raises an illegal-instruction fault, see tools/probes/tma_unaligned.cu.)
+// G' is zero at lattice points that are not outputs of the pass, which makes the row wrap-around of the flattened index
+// harmless.  Strided convs read X' from its polyphase planes (phase_t), the parity passes of the transposed conv read
+// G' from its polyphase planes (g_phase).
 //
 // GEMM shape: M = Cout (128-row tiles), N = Cin (256-column tiles), K = B*Hl*Wl split into `ksplit` chunks so that
 // taps * tiles * ksplit work items fill the 148 SMs; items are ordered K-chunk-major, so the CTAs running at the same
@@ -20,14 +24,34 @@
 
 namespace {
 
+constexpr int CHUNK_BYTES = 64 * GEMM_BLOCK_K * 2;  // one TMA box: 64 pixel rows x 64 channels of bf16 = 8 KiB
+
 struct WgradParams {
-  int32_t Q;  // contraction length
+  int32_t Q;  // contraction length (lattice points per phase plane)
   int32_t O, C, Cs;  // M extent, N extent, padded row stride of the partial tiles
   int32_t ntaps;
-  int32_t tap_off[SPGAN_MAX_TAPS], tap_phase[SPGAN_MAX_TAPS];
-  int32_t g_phase;
+  int32_t tap_row[SPGAN_MAX_TAPS];  // row offset of the tap in the X' pack: phase_t * Q + off_t
+  int32_t g_row0;                   // row offset of this pass's phase plane in the G' pack
   int32_t m_tiles, n_tiles, ksplit, kb_per_split, kblocks;
+  uint32_t lbo, sbo, kstep;  // MN-major shared-memory descriptor: chunk stride, 8-row group stride, bytes per K = 16 step
 };
+
+// MN-major, 128-byte swizzle (canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units): 64 contiguous
+// channels per row, rows 128 bytes apart, 8-row groups SBO = 1024 B apart, 64-channel chunks LBO = one TMA box (8 KiB)
+// apart, and a K = 16 step advances the start address by two 8-row groups (2048 B).  Verified on a B200 against the
+// exact-fp32 kernel (5e-6); the swapped / other encodings give O(1) errors.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ uint32_t umma_idesc_bf16_mn(int n) {
+  return umma_idesc_bf16(n) | (1u << 15) | (1u << 16);  // A and B MN-major
+}
 
 template <int kPasses>
 struct WgSmem {
@@ -101,20 +125,24 @@ conv_wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_con
         decode(item, ks, t, m0, n0);
         const int kb0 = ks * wp.kb_per_split;
         const int kb1 = min(kb0 + wp.kb_per_split, wp.kblocks);
-        const int off = wp.tap_off[t], ph = wp.tap_phase[t];
+        const int xrow0 = wp.tap_row[t];
+        int n_eff = wp.C - n0;
+        n_eff = n_eff > GEMM_BLOCK_N ? GEMM_BLOCK_N : ((n_eff + 15) & ~15);
+        const int nchunks = (n_eff + 63) >> 6;
+        constexpr int kPlanes = kPasses == 3 ? 2 : 1;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_base + stage * S::kStageBytes;
           const int q = kb * GEMM_BLOCK_K;
-          mbar_arrive_expect_tx(full_bar(stage), S::kStageBytes);
-          if (kPasses == 3) {
-            tma_load_4d(sa, &tmG, full_bar(stage), q, m0, wp.g_phase, 0);
-            tma_load_4d(sa + A_TILE_BYTES, &tmG, full_bar(stage), q, m0, wp.g_phase, 1);
-            tma_load_4d(sa + 2 * A_TILE_BYTES, &tmX, full_bar(stage), q + off, n0, ph, 0);
-            tma_load_4d(sa + 2 * A_TILE_BYTES + B_TILE_BYTES, &tmX, full_bar(stage), q + off, n0, ph, 1);
-          } else {
-            tma_load_4d(sa, &tmG, full_bar(stage), q, m0, wp.g_phase, 0);
-            tma_load_4d(sa + A_TILE_BYTES, &tmX, full_bar(stage), q + off, n0, ph, 0);
+          mbar_arrive_expect_tx(full_bar(stage), (uint32_t)(kPlanes * (2 + nchunks) * CHUNK_BYTES));
+#pragma unroll
+          for (int pl = 0; pl < kPlanes; ++pl) {
+            const uint32_t a_dst = sa + pl * A_TILE_BYTES;
+            const uint32_t b_dst = sa + kPlanes * A_TILE_BYTES + pl * B_TILE_BYTES;
+            tma_load_3d(a_dst, &tmG, full_bar(stage), m0, wp.g_row0 + q, pl);
+            tma_load_3d(a_dst + CHUNK_BYTES, &tmG, full_bar(stage), m0 + 64, wp.g_row0 + q, pl);
+            for (int i = 0; i < nchunks; ++i)
+              tma_load_3d(b_dst + i * CHUNK_BYTES, &tmX, full_bar(stage), n0 + 64 * i, xrow0 + q, pl);
           }
           if (++stage == kStages) {
             stage = 0;
@@ -134,7 +162,7 @@ conv_wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_con
         decode(item, ks, t, m0, n0);
         int n_eff = wp.C - n0;
         n_eff = n_eff > GEMM_BLOCK_N ? GEMM_BLOCK_N : ((n_eff + 15) & ~15);
-        const uint32_t idesc = umma_idesc_bf16(n_eff);
+        const uint32_t idesc = umma_idesc_bf16_mn(n_eff);
         const int as = titer & 1;
         const uint32_t aphase = (uint32_t)(titer >> 1) & 1u;
         mbar_wait(tempty_bar(as), aphase ^ 1u);
@@ -152,13 +180,13 @@ conv_wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_con
           const uint32_t b_lo = b_hi + B_TILE_BYTES;
 #pragma unroll
           for (int k = 0; k < GEMM_BLOCK_K / GEMM_UMMA_K; ++k) {
-            const uint32_t koff = k * GEMM_UMMA_K * 2;
-            const uint64_t da_hi = umma_desc_sw128(a_hi + koff);
-            const uint64_t db_hi = umma_desc_sw128(b_hi + koff);
+            const uint32_t koff = k * wp.kstep;  // 16 pixel rows = two 8-row groups further down the tile
+            const uint64_t da_hi = umma_desc_mn_sw128(a_hi + koff, wp.lbo, wp.sbo);
+            const uint64_t db_hi = umma_desc_mn_sw128(b_hi + koff, wp.lbo, wp.sbo);
             tc_mma_f16(d_tmem, da_hi, db_hi, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
             if (kPasses == 3) {
-              const uint64_t da_lo = umma_desc_sw128(a_lo + koff);
-              const uint64_t db_lo = umma_desc_sw128(b_lo + koff);
+              const uint64_t da_lo = umma_desc_mn_sw128(a_lo + koff, wp.lbo, wp.sbo);
+              const uint64_t db_lo = umma_desc_mn_sw128(b_lo + koff, wp.lbo, wp.sbo);
               tc_mma_f16(d_tmem, da_hi, db_lo, idesc, 1u);
               tc_mma_f16(d_tmem, da_lo, db_hi, idesc, 1u);
             }
@@ -237,51 +265,6 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(float* __restrict__ d
   }
 }
 
-// out[plane][ph][c][b*Hl*Wl + i*Wl + j] = mul[b,c] * x[b, c, i*step + py - pad_y, j*step + px - pad_x]   (0 outside x),
-// ph = py*step + px.  One thread per 4 consecutive columns (8-byte bf16 stores to the hi and the lo plane).
-__global__ void __launch_bounds__(256) pack_kmajor_kernel(__nv_bfloat16* __restrict__ out, const float* __restrict__ x,
-                                                         const float* __restrict__ mul, int B, int C, int H, int W,
-                                                         int step, int pad_y, int pad_x, int Hl, int Wl, int64_t qstride,
-                                                         FastDiv dplane, FastDiv dwl) {
-  const int plane_l = Hl * Wl;
-  const int Q = B * plane_l;
-  const int c = blockIdx.y;
-  const int ph = blockIdx.z;
-  const int py = ph / step, px = ph - py * step;
-  const int64_t lo_off = (int64_t)step * step * C * qstride;
-  __nv_bfloat16* orow = out + ((int64_t)ph * C + c) * qstride;
-  for (int q4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4; q4 < Q; q4 += gridDim.x * blockDim.x * 4) {
-    float v[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const uint32_t q = (uint32_t)(q4 + u);
-      v[u] = 0.f;
-      if ((int)q < Q) {
-        const uint32_t b = fdiv(q, dplane);
-        const uint32_t r = q - b * (uint32_t)plane_l;
-        const uint32_t i = fdiv(r, dwl);
-        const uint32_t j = r - i * (uint32_t)Wl;
-        const int sy = (int)i * step + py - pad_y, sx = (int)j * step + px - pad_x;
-        if (sy >= 0 && sy < H && sx >= 0 && sx < W) {
-          v[u] = __ldg(x + (((int64_t)b * C + c) * H + sy) * W + sx);
-          if (mul) v[u] *= __ldg(mul + (int64_t)b * C + c);
-        }
-      }
-    }
-    __nv_bfloat16 h[4], l[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) split_bf16(v[u], h[u], l[u]);
-    // qstride is a multiple of 8 and q4 a multiple of 4: 8-byte aligned, and q4 + 3 < qstride
-    uint2 hv, lv;
-    hv.x = (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16);
-    hv.y = (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16);
-    lv.x = (uint32_t)__bfloat16_as_ushort(l[0]) | ((uint32_t)__bfloat16_as_ushort(l[1]) << 16);
-    lv.y = (uint32_t)__bfloat16_as_ushort(l[2]) | ((uint32_t)__bfloat16_as_ushort(l[3]) << 16);
-    *reinterpret_cast<uint2*>(orow + q4) = hv;
-    *reinterpret_cast<uint2*>(orow + lo_off + q4) = lv;
-  }
-}
-
 template <int kPasses>
 int launch_wgrad(const CUtensorMap& tmG, const CUtensorMap& tmX, const WgradParams& wp, float* partial, cudaStream_t st) {
   using S = WgSmem<kPasses>;
@@ -317,28 +300,6 @@ void plan_split(int Q, int ntaps, int m_tiles, int n_tiles, int* kblocks, int* k
 
 }  // namespace
 
-extern "C" int spgan_pack_kmajor(uint16_t* out, const float* x, const float* mul, int B, int C, int H, int W, int step,
-                                 int pad_y0, int pad_x0, int Hl, int Wl, int64_t qstride, void* stream) {
-  SPGAN_CHECK_ARG(B >= 0 && C >= 0 && H >= 0 && W >= 0 && Hl >= 0 && Wl >= 0, "spgan_pack_kmajor: negative size");
-  SPGAN_CHECK_ARG(step >= 1 && step <= 8, "spgan_pack_kmajor: step %d unsupported", step);
-  const int64_t Q = (int64_t)B * Hl * Wl;
-  SPGAN_CHECK_ARG(qstride >= Q && qstride % 8 == 0, "spgan_pack_kmajor: qstride=%lld must be a multiple of 8 and >= B*Hl*Wl=%lld",
-                  (long long)qstride, (long long)Q);
-  SPGAN_CHECK_ARG(Q < (1LL << 30), "spgan_pack_kmajor: too many lattice points");
-  if (Q == 0 || C == 0) return 0;
-  SPGAN_CHECK_ARG(out && x, "spgan_pack_kmajor: null pointer");
-  SPGAN_CHECK_ARG(C <= 65535, "spgan_pack_kmajor: C=%d > 65535", C);
-  int gx = (int)((Q / 4 + 255) / 256);
-  if (gx > 2048) gx = 2048;
-  if (gx < 1) gx = 1;
-  dim3 grid(gx, C, step * step);
-  pack_kmajor_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)out, x, mul, B, C, H, W, step, pad_y0, pad_x0,
-                                                            Hl, Wl, qstride, make_fastdiv((uint32_t)(Hl * Wl)),
-                                                            make_fastdiv((uint32_t)Wl));
-  SPGAN_CHECK_LAUNCH("spgan_pack_kmajor");
-  return 0;
-}
-
 extern "C" int64_t spgan_conv_wgrad_gemm_workspace(const SpganConvPass* p) {
   if (p == nullptr || p->ntaps < 1 || p->Cout < 1 || p->Cin < 1) return 0;
   const int64_t Q = (int64_t)p->B * p->H * p->W;
@@ -351,9 +312,9 @@ extern "C" int64_t spgan_conv_wgrad_gemm_workspace(const SpganConvPass* p) {
 }
 
 extern "C" int spgan_conv_wgrad_gemm(const SpganConvPass* p, float* dw, const uint16_t* g_packed, int g_phases,
-                                     int g_phase, const uint16_t* x_packed, int x_phases, const int32_t* tap_phase,
-                                     int64_t qstride, float* workspace, int64_t workspace_elems, int accumulate,
-                                     void* stream) {
+                                     int g_phase, int gp_cols, const uint16_t* x_packed, int x_phases,
+                                     const int32_t* tap_phase, int xp_cols, float* workspace, int64_t workspace_elems,
+                                     int accumulate, void* stream) {
   SPGAN_CHECK_ARG(p != nullptr, "spgan_conv_wgrad_gemm: null pass descriptor");
   SPGAN_CHECK_ARG(p->precision == 1 || p->precision == 2, "spgan_conv_wgrad_gemm: precision must be 1 (bf16x3) or 2 (bf16), got %d",
                   p->precision);
@@ -361,10 +322,12 @@ extern "C" int spgan_conv_wgrad_gemm(const SpganConvPass* p, float* dw, const ui
   SPGAN_CHECK_ARG(p->B >= 0 && p->H >= 0 && p->W >= 0 && p->Cout >= 0 && p->Cin >= 0, "spgan_conv_wgrad_gemm: negative size");
   const int64_t Q = (int64_t)p->B * p->H * p->W;
   if (Q == 0 || p->Cout == 0 || p->Cin == 0) return 0;
-  SPGAN_CHECK_ARG(Q < (1LL << 30), "spgan_conv_wgrad_gemm: too many lattice points");
-  SPGAN_CHECK_ARG(qstride >= Q && qstride % 8 == 0, "spgan_conv_wgrad_gemm: qstride must be a multiple of 8 and >= B*H*W");
   SPGAN_CHECK_ARG(p->Cout >= 16 && p->Cin >= 16, "spgan_conv_wgrad_gemm: Cout=%d / Cin=%d < 16 belong on the SIMT path", p->Cout, p->Cin);
   SPGAN_CHECK_ARG(g_phases >= 1 && g_phase >= 0 && g_phase < g_phases && x_phases >= 1, "spgan_conv_wgrad_gemm: bad phase arguments");
+  SPGAN_CHECK_ARG(Q * (g_phases > x_phases ? g_phases : x_phases) < 2147483647LL - 65536, "spgan_conv_wgrad_gemm: too many lattice points");
+  SPGAN_CHECK_ARG(gp_cols >= p->Cout && gp_cols % 64 == 0 && xp_cols >= p->Cin && xp_cols % 64 == 0,
+                  "spgan_conv_wgrad_gemm: packed widths (%d, %d) must be multiples of 64 covering Cout=%d / Cin=%d", gp_cols, xp_cols,
+                  p->Cout, p->Cin);
   SPGAN_CHECK_ARG(dw && g_packed && x_packed && workspace, "spgan_conv_wgrad_gemm: null pointer");
   SPGAN_CHECK_ARG(((((uintptr_t)g_packed) | ((uintptr_t)x_packed) | ((uintptr_t)workspace)) & 15) == 0,
                   "spgan_conv_wgrad_gemm: packed operands and workspace must be 16-byte aligned");
@@ -374,39 +337,41 @@ extern "C" int spgan_conv_wgrad_gemm(const SpganConvPass* p, float* dw, const ui
   wp.C = p->Cin;
   wp.Cs = (p->Cin + 3) / 4 * 4;
   wp.ntaps = p->ntaps;
-  wp.g_phase = g_phase;
-  for (int t = 0; t < SPGAN_MAX_TAPS; ++t) {
-    wp.tap_off[t] = 0;
-    wp.tap_phase[t] = 0;
-  }
+  wp.g_row0 = 0;  // the G map below is a view of this pass's phase plane only: rows >= Q are zero-filled by TMA
+  for (int t = 0; t < SPGAN_MAX_TAPS; ++t) wp.tap_row[t] = 0;
   for (int t = 0; t < p->ntaps; ++t) {
-    wp.tap_off[t] = p->tap_dy[t] * p->W + p->tap_dx[t];
-    wp.tap_phase[t] = tap_phase ? tap_phase[t] : 0;
-    SPGAN_CHECK_ARG(wp.tap_phase[t] >= 0 && wp.tap_phase[t] < x_phases, "spgan_conv_wgrad_gemm: tap %d has phase %d of %d", t,
-                    wp.tap_phase[t], x_phases);
-    SPGAN_CHECK_ARG(wp.tap_off[t] >= 0, "spgan_conv_wgrad_gemm: tap %d has a negative lattice offset (pad the lattice)", t);
+    const int ph = tap_phase ? tap_phase[t] : 0;
+    SPGAN_CHECK_ARG(ph >= 0 && ph < x_phases, "spgan_conv_wgrad_gemm: tap %d has phase %d of %d", t, ph, x_phases);
+    const int off = p->tap_dy[t] * p->W + p->tap_dx[t];
+    SPGAN_CHECK_ARG(off >= 0, "spgan_conv_wgrad_gemm: tap %d has a negative lattice offset (pad the lattice)", t);
+    wp.tap_row[t] = (int32_t)(ph * Q + off);
   }
   wp.m_tiles = (p->Cout + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
   wp.n_tiles = (p->Cin + GEMM_BLOCK_N - 1) / GEMM_BLOCK_N;
   plan_split((int)Q, p->ntaps, wp.m_tiles, wp.n_tiles, &wp.kblocks, &wp.ksplit, &wp.kb_per_split);
+  wp.lbo = CHUNK_BYTES;
+  wp.sbo = 1024;
+  wp.kstep = 2048;
   const int64_t need = (int64_t)wp.ksplit * wp.ntaps * wp.O * wp.Cs;
   SPGAN_CHECK_ARG(workspace_elems >= need, "spgan_conv_wgrad_gemm: workspace holds %lld floats, %lld needed",
                   (long long)workspace_elems, (long long)need);
 
   CUtensorMap tmG, tmX;
   {
-    cuuint64_t dims[4] = {(cuuint64_t)Q, (cuuint64_t)p->Cout, (cuuint64_t)g_phases, 2};
-    cuuint64_t strides[3] = {(cuuint64_t)qstride * 2, (cuuint64_t)p->Cout * qstride * 2,
-                             (cuuint64_t)g_phases * p->Cout * qstride * 2};
-    cuuint32_t box[4] = {GEMM_BLOCK_K, GEMM_BLOCK_M, 1, 1};
-    if (int e = encode_bf16_map(&tmG, g_packed, 4, dims, strides, box, "spgan_conv_wgrad_gemm (G map)")) return e;
+    // the last K block reads up to 63 rows past Q: they must contribute nothing, so the map ends at this phase plane
+    const cuuint64_t rows = (cuuint64_t)g_phases * Q;
+    cuuint64_t dims[3] = {(cuuint64_t)gp_cols, (cuuint64_t)Q, 2};
+    cuuint64_t strides[2] = {(cuuint64_t)gp_cols * 2, rows * gp_cols * 2};
+    cuuint32_t box[3] = {64, GEMM_BLOCK_K, 1};
+    const uint16_t* gbase = g_packed + (int64_t)g_phase * Q * gp_cols;
+    if (int e = encode_bf16_map(&tmG, gbase, 3, dims, strides, box, "spgan_conv_wgrad_gemm (G map)")) return e;
   }
   {
-    cuuint64_t dims[4] = {(cuuint64_t)Q, (cuuint64_t)p->Cin, (cuuint64_t)x_phases, 2};
-    cuuint64_t strides[3] = {(cuuint64_t)qstride * 2, (cuuint64_t)p->Cin * qstride * 2,
-                             (cuuint64_t)x_phases * p->Cin * qstride * 2};
-    cuuint32_t box[4] = {GEMM_BLOCK_K, GEMM_BLOCK_N, 1, 1};
-    if (int e = encode_bf16_map(&tmX, x_packed, 4, dims, strides, box, "spgan_conv_wgrad_gemm (X map)")) return e;
+    const cuuint64_t rows = (cuuint64_t)x_phases * Q;
+    cuuint64_t dims[3] = {(cuuint64_t)xp_cols, rows, 2};
+    cuuint64_t strides[2] = {(cuuint64_t)xp_cols * 2, rows * xp_cols * 2};
+    cuuint32_t box[3] = {64, GEMM_BLOCK_K, 1};
+    if (int e = encode_bf16_map(&tmX, x_packed, 3, dims, strides, box, "spgan_conv_wgrad_gemm (X map)")) return e;
   }
   cudaStream_t st = (cudaStream_t)stream;
   int e = p->precision == 1 ? launch_wgrad<3>(tmG, tmX, wp, workspace, st) : launch_wgrad<1>(tmG, tmX, wp, workspace, st);

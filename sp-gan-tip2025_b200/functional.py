@@ -589,26 +589,28 @@ def conv_wgrad(g, x, w_shape, geom, in_mul=None, out_mul=None, out_scale=1.0, pr
     om = _f32c(out_mul, "conv wgrad") if out_mul is not None else None
     precision = _PRECISION if precision is None else precision
     if passes and _tensor_path_ok(passes, C, O, precision) and len({p["out_stride"] for p in passes}) == 1:
-        # tcgen05: contraction over the flattened lattice of pixel-contiguous bf16 hi/lo copies (spgan_pack_kmajor)
+        # tcgen05: contraction over the flattened lattice rows of the same channels-last packs the forward GEMM reads
         s_in, pt, pl, Hl, Wl, mapped = _phase_taps(passes)
         s_out = passes[0]["out_stride"]
+        if s_in == 1:
+            Hl, Wl = max(Hl, pt + H), max(Wl, pl + W)
         Q = B * Hl * Wl
-        qstride = _round_up(Q, 8)
+        Op, Cp = _round_up(O, 64), _round_up(C, 64)
         st = _stream(x)
         with torch.cuda.device(x.device):
-            gp = torch.empty((2, s_out * s_out, O, qstride), device=x.device, dtype=torch.bfloat16)
-            xp = torch.empty((2, s_in * s_in, C, qstride), device=x.device, dtype=torch.bfloat16)
-            lib.call("spgan_pack_kmajor", _ptr(gp), _ptr(g), _ptr(om), B, O, oh, ow, s_out, 0, 0, Hl, Wl, qstride, st)
-            lib.call("spgan_pack_kmajor", _ptr(xp), _ptr(x), _ptr(im), B, C, H, W, s_in, pt, pl, Hl, Wl, qstride, st)
+            gp = torch.empty((2, s_out * s_out * Q, Op), device=x.device, dtype=torch.bfloat16)
+            xp = torch.empty((2, s_in * s_in * Q, Cp), device=x.device, dtype=torch.bfloat16)
+            lib.call("spgan_pack_act", _ptr(gp), _ptr(g), _ptr(om), B, O, oh, ow, Op, 0, 0, Hl, Wl, s_out, st)
+            lib.call("spgan_pack_act", _ptr(xp), _ptr(x), _ptr(im), B, C, H, W, Cp, pt, pl, Hl, Wl, s_in, st)
             for p, taps in zip(passes, mapped):
                 q = dict(p, in_stride=1, out_stride=1, off_y=0, off_x=0, taps=[(oy, ox, wi) for _, oy, ox, wi in taps])
                 cp = _fill_pass(q, B, C, Hl, Wl, O, Hl, Wl, C * kk, kk, out_scale, 0, 0.0, 1.0, precision)
                 phases = (ctypes.c_int32 * len(taps))(*[t[0] for t in taps])
-                need = lib.load().spgan_conv_wgrad_gemm_workspace(ctypes.byref(cp))
-                ws = torch.empty((max(int(need), 1),), device=x.device, dtype=torch.float32)
+                need = int(lib.load().spgan_conv_wgrad_gemm_workspace(ctypes.byref(cp)))
+                ws = torch.empty((max(need, 1),), device=x.device, dtype=torch.float32)
                 flops = 2.0 * B * min(p["My"], oh) * min(p["Mx"], ow) * O * C * len(taps)
                 _timed_call(flops, "spgan_conv_wgrad_gemm", ctypes.byref(cp), _ptr(dw), _ptr(gp), s_out * s_out,
-                            p["off_y"] * s_out + p["off_x"], _ptr(xp), s_in * s_in, phases, qstride, _ptr(ws), int(need), 0, st)
+                            p["off_y"] * s_out + p["off_x"], Op, _ptr(xp), s_in * s_in, phases, Cp, _ptr(ws), need, 0, st)
         return dw
     with torch.cuda.device(x.device):
         for p in passes:

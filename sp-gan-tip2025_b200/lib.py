@@ -55,10 +55,9 @@ SIGNATURES = {
     "spgan_conv_wgrad": (c_int, [_PASS_P, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp]),
     "spgan_plane_dot": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp]),
     "spgan_pack_act": (c_int, [c_vp, c_vp, c_vp] + [c_int] * 10 + [c_vp]),
-    "spgan_pack_kmajor": (c_int, [c_vp, c_vp, c_vp] + [c_int] * 9 + [c_i64, c_vp]),
     "spgan_conv_wgrad_gemm_workspace": (c_i64, [_PASS_P]),
-    "spgan_conv_wgrad_gemm": (c_int, [_PASS_P, c_vp, c_vp, c_int, c_int, c_vp, c_int, ctypes.POINTER(ctypes.c_int32), c_i64,
-                                      c_vp, c_i64, c_int, c_vp]),
+    "spgan_conv_wgrad_gemm": (c_int, [_PASS_P, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_int, ctypes.POINTER(ctypes.c_int32),
+                                      c_int, c_vp, c_i64, c_int, c_vp]),
     "spgan_pack_weight": (c_int, [c_vp, c_vp, c_int, c_int, c_i64, c_i64, c_int, ctypes.POINTER(ctypes.c_int32), c_int, c_int, c_vp]),
     "spgan_nchw_to_nhwc": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp]),
     "spgan_sphere_pack": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
