@@ -458,11 +458,13 @@ __global__ void __launch_bounds__(256) sphere_pack_kernel(__nv_bfloat16* __restr
 }
 
 // Shared-grid specialisation (test / panorama mode: one sampling grid for the whole batch, grid_batch == 1) with
-// Cp = 64 * KITER known at compile time: the corner set is computed once per warp and all 8 * KITER corner loads of a
-// lane are issued before the first use, so a warp keeps 40 x 128 B of reads in flight instead of one dependent chain per
-// 64 channels (the general kernel above is latency-bound at ~10 % of the HBM write roofline).
+// Cp = 64 * KITER known at compile time.  One warp per (group g, pixel p) walks all 9 taps: lanes 0..8 fetch the nine
+// grid entries and compute the corner sets in parallel (one grid latency per pixel instead of one per tap, broadcast by
+// shuffle), the channel map and the modulation are decoded once per pixel, and per tap all 8 * KITER corner loads of a
+// lane are issued before the first use.  The general kernel above pays three dependent global latencies per
+// (pixel, tap) with 16 warps per SM and sat at ~15 % of the HBM write roofline.
 template <int KITER>
-__global__ void __launch_bounds__(256) sphere_pack_shared_kernel(__nv_bfloat16* __restrict__ out,
+__global__ void __launch_bounds__(256, 2) sphere_pack_shared_kernel(__nv_bfloat16* __restrict__ out,
                                                                 const float* __restrict__ xh,
                                                                 const float* __restrict__ coords,
                                                                 const float* __restrict__ grid,
@@ -473,64 +475,88 @@ __global__ void __launch_bounds__(256) sphere_pack_shared_kernel(__nv_bfloat16* 
   const int Ct = C + nc;
   const int HW = H * W;
   const int64_t plane_elems = (int64_t)B * HW * 9 * Cp;
-  const int64_t warps_total = (int64_t)B * HW * 9;
+  const int64_t warps_total = (int64_t)B * HW;
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t warp_stride = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t wid = warp0; wid < warps_total; wid += warp_stride) {
-    const int t = (int)(wid % 9);
-    const int64_t r = wid / 9;
-    const int p = (int)(r % HW);
-    const int g = (int)(r / HW);
+    const int p = (int)(wid % HW);
+    const int g = (int)(wid / HW);
     const int py = p / W, px = p - py * W;
-    const int ty = t / 3, tx = t - ty * 3;
-    const TapCorners cn = tap_corners(grid, 0, H, W, py, px, ty, tx);
+    TapCorners mine;
+    mine.o_nw = mine.o_ne = mine.o_sw = mine.o_se = 0;
+    mine.w_nw = mine.w_ne = mine.w_sw = mine.w_se = 0.f;
+    if (lane < 9) mine = tap_corners(grid, 0, H, W, py, px, lane / 3, lane % 3);
     const uint32_t* mrow = chan_map + (int64_t)g * Cp;
     const float* mulrow = in_mul ? in_mul + (int64_t)g * Ct : nullptr;
-    uint2 mm[KITER];
-#pragma unroll
-    for (int j = 0; j < KITER; ++j) mm[j] = __ldg(reinterpret_cast<const uint2*>(mrow + 2 * lane + 64 * j));
-    float cv[KITER][2][4], mv[KITER][2];
+    // decode this lane's 2 * KITER channels once: 32-bit element offset of the source plane, the map word (flags) and
+    // the modulation
+    uint32_t mw[KITER][2];
+    uint32_t soff[KITER][2];
+    float mv[KITER][2];
 #pragma unroll
     for (int j = 0; j < KITER; ++j) {
+      const uint2 mm = __ldg(reinterpret_cast<const uint2*>(mrow + 2 * lane + 64 * j));
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
-        const uint32_t m = u ? mm[j].y : mm[j].x;
-        const bool ok = m != 0xFFFFFFFFu;
-        const int bs = (int)((m >> 15) & 0xFFFFu);
-        const int cs = (int)(m & 0x7FFFu);
-        const bool is_coord = (m >> 31) != 0;
-        const float* src = is_coord ? coords + ((int64_t)bs * nc + cs) * HW : xh + (int64_t)bs * HW * C + cs;
-        const int64_t st = is_coord ? 1 : C;
-        cv[j][u][0] = ok ? __ldg(src + cn.o_nw * st) : 0.f;
-        cv[j][u][1] = ok ? __ldg(src + cn.o_ne * st) : 0.f;
-        cv[j][u][2] = ok ? __ldg(src + cn.o_sw * st) : 0.f;
-        cv[j][u][3] = ok ? __ldg(src + cn.o_se * st) : 0.f;
-        mv[j][u] = (ok && mulrow) ? __ldg(mulrow + 2 * lane + 64 * j + u) : 1.f;
+        const uint32_t m = u ? mm.y : mm.x;
+        const bool valid = m != 0xFFFFFFFFu;
+        const uint32_t bs = (m >> 15) & 0xFFFFu, cs = m & 0x7FFFu;
+        mw[j][u] = m;
+        soff[j][u] = !valid ? 0u : ((m >> 31) ? (bs * (uint32_t)nc + cs) * (uint32_t)HW : bs * (uint32_t)HW * (uint32_t)C + cs);
+        mv[j][u] = (valid && mulrow) ? __ldg(mulrow + 2 * lane + 64 * j + u) : 1.f;
       }
     }
-    __nv_bfloat16* orow = out + wid * Cp;
+    __nv_bfloat16* obase = out + wid * 9 * Cp;  // row (g, p): 9 taps x Cp columns
+#pragma unroll 1
+    for (int t = 0; t < 9; ++t) {
+      TapCorners cn;
+      cn.o_nw = __shfl_sync(0xffffffffu, mine.o_nw, t);
+      cn.o_ne = __shfl_sync(0xffffffffu, mine.o_ne, t);
+      cn.o_sw = __shfl_sync(0xffffffffu, mine.o_sw, t);
+      cn.o_se = __shfl_sync(0xffffffffu, mine.o_se, t);
+      cn.w_nw = __shfl_sync(0xffffffffu, mine.w_nw, t);
+      cn.w_ne = __shfl_sync(0xffffffffu, mine.w_ne, t);
+      cn.w_sw = __shfl_sync(0xffffffffu, mine.w_sw, t);
+      cn.w_se = __shfl_sync(0xffffffffu, mine.w_se, t);
+      float cv[KITER][2][4];
 #pragma unroll
-    for (int j = 0; j < KITER; ++j) {
-      float v[2];
+      for (int j = 0; j < KITER; ++j)
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const uint32_t m = u ? mm[j].y : mm[j].x;
-        float val = cv[j][u][0] * cn.w_nw + cv[j][u][1] * cn.w_ne + cv[j][u][2] * cn.w_sw + cv[j][u][3] * cn.w_se;
-        if (m != 0xFFFFFFFFu && (m >> 31) != 0) {
-          const int cs = (int)(m & 0x7FFFu);
-          if (cs == 0) val = tanhf(val);
-          else if (cs == 1) val = cosf(val * 3.14159274101257324f);
-          else if (cs == 2) val = sinf(val * 3.14159274101257324f);
+        for (int u = 0; u < 2; ++u) {
+          const uint32_t m = mw[j][u];
+          const bool valid = m != 0xFFFFFFFFu;
+          const bool is_coord = (m >> 31) != 0;
+          const float* sp = (is_coord ? coords : xh) + soff[j][u];
+          const int st = is_coord ? 1 : C;
+          cv[j][u][0] = valid ? __ldg(sp + cn.o_nw * st) : 0.f;
+          cv[j][u][1] = valid ? __ldg(sp + cn.o_ne * st) : 0.f;
+          cv[j][u][2] = valid ? __ldg(sp + cn.o_sw * st) : 0.f;
+          cv[j][u][3] = valid ? __ldg(sp + cn.o_se * st) : 0.f;
         }
-        v[u] = val * mv[j][u];
+      __nv_bfloat16* orow = obase + t * Cp;
+#pragma unroll
+      for (int j = 0; j < KITER; ++j) {
+        float v[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          float val = cv[j][u][0] * cn.w_nw + cv[j][u][1] * cn.w_ne + cv[j][u][2] * cn.w_sw + cv[j][u][3] * cn.w_se;
+          const uint32_t m = mw[j][u];
+          if (m != 0xFFFFFFFFu && (m >> 31) != 0) {
+            const uint32_t cs = m & 0x7FFFu;
+            if (cs == 0) val = tanhf(val);
+            else if (cs == 1) val = cosf(val * 3.14159274101257324f);
+            else if (cs == 2) val = sinf(val * 3.14159274101257324f);
+          }
+          v[u] = val * mv[j][u];
+        }
+        __nv_bfloat16 h0, l0, h1, l1;
+        split_bf16(v[0], h0, l0);
+        split_bf16(v[1], h1, l1);
+        const int k0 = 2 * lane + 64 * j;
+        *reinterpret_cast<__nv_bfloat162*>(orow + k0) = __halves2bfloat162(h0, h1);
+        *reinterpret_cast<__nv_bfloat162*>(orow + plane_elems + k0) = __halves2bfloat162(l0, l1);
       }
-      __nv_bfloat16 h0, l0, h1, l1;
-      split_bf16(v[0], h0, l0);
-      split_bf16(v[1], h1, l1);
-      const int k0 = 2 * lane + 64 * j;
-      *reinterpret_cast<__nv_bfloat162*>(orow + k0) = __halves2bfloat162(h0, h1);
-      *reinterpret_cast<__nv_bfloat162*>(orow + plane_elems + k0) = __halves2bfloat162(l0, l1);
     }
   }
 }
@@ -618,12 +644,13 @@ extern "C" int spgan_sphere_pack(uint16_t* out, const float* x_nhwc, const float
   SPGAN_CHECK_ARG(out && x_nhwc && grid && chan_map, "spgan_sphere_pack: null pointer");
   SPGAN_CHECK_ARG(B <= 65535 && C <= 32767, "spgan_sphere_pack: B=%d / C=%d exceed the channel-map encoding", B, C);
   SPGAN_CHECK_ARG(grid_batch == 1 || grid_batch == B, "spgan_sphere_pack: grid batch %d must be 1 or %d", grid_batch, B);
+  SPGAN_CHECK_ARG((int64_t)B * H * W * (C > 3 ? C : 3) < (1LL << 31), "spgan_sphere_pack: input too large for 32-bit plane offsets");
   SPGAN_CHECK_ARG((((uintptr_t)grid) & 7) == 0 && (((uintptr_t)chan_map) & 7) == 0,
                   "spgan_sphere_pack: grid and chan_map must be 8-byte aligned");
   const int64_t warps = (int64_t)B * H * W * 9;
   cudaStream_t st = (cudaStream_t)stream;
   __nv_bfloat16* o = (__nv_bfloat16*)out;
-  const int nblk = grid_for(warps, 8, 2, 16);
+  const int nblk = grid_for((int64_t)B * H * W, 8, 2, 16);
 #define SPGAN_SPHERE_SHARED(KI)                                                                                       \
   sphere_pack_shared_kernel<KI><<<nblk, 256, 0, st>>>(o, x_nhwc, coords, grid, in_mul, chan_map, B, C, nc, H, W)
   if (grid_batch == 1 && Cp == 64) SPGAN_SPHERE_SHARED(1);

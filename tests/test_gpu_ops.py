@@ -314,6 +314,29 @@ def test_polyphase_transposed_conv_and_fused_upblur(dev, precision):
     assert K.rel_err(K.t2n(got), want) < TOL[precision]
 
 
+@pytest.mark.parametrize("H,Hq_extra,with_noise", [(53, 0, True), (28, 1, True), (6, 0, False), (2, 0, True), (100, 0, True)])
+def test_upblur_act_bands_and_edges_vs_composition(dev, H, Hq_extra, with_noise):
+    """Fused interleave + FIR + noise + bias + act against interleave -> upfirdn2d -> noise_bias_act, at sizes with
+    several bands per plane, odd and even heights, padded polyphase planes and the single-row edge case."""
+    B, C = 2, 5
+    zh = 2 * H - 1
+    Hq = H + Hq_extra
+    pp = synth.randn_t(13, "ubpp%d" % H, (B, C, 4, Hq, Hq)).to(dev)
+    k = torch.from_numpy(O.make_kernel([1, 2, 1]) * 4).to(dev)
+    nz = synth.randn_t(13, "ubnz%d" % H, (B, 1, zh - 2, zh - 2)).to(dev) if with_noise else None
+    nw = torch.tensor([0.7], device=dev) if with_noise else None
+    bias = synth.randn_t(13, "ubb%d" % H, (C,)).to(dev)
+    zz = torch.zeros(B, C, zh, zh, device=dev)
+    for a in range(2):
+        for b in range(2):
+            sub = zz[:, :, a::2, b::2]
+            sub.copy_(pp[:, :, a * 2 + b, :sub.shape[2], :sub.shape[3]])
+    want = SF().noise_bias_act(SF().upfirdn2d(zz, k, pad=(0, 0)), nz, nw, bias)
+    got = SF().upblur_act(pp, k, (zh, zh), nz, nw, bias)
+    assert got.shape == want.shape
+    assert K.rel_err(K.t2n(got), K.t2n(want)) < 1e-6
+
+
 def test_conv_small_cout_paths(dev):
     """ToRGB-shaped (512 -> 3, 1x1, every epilogue term) and RGB-sphere-shaped (3 -> 3, 3x3 stride 3) convs."""
     from spgan_b200.functional import ConvGeom
