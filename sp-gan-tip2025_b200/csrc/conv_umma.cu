@@ -6,19 +6,21 @@
 // constant row offset, so every operand tile is one TMA box (128B-swizzled, K-major) and the contraction is issued as
 // tcgen05.mma.cta_group::1.kind::f16 (M = 128, N <= 256, K = 16) with the fp32 accumulator in TMEM.
 //
-// Kernel anatomy (one persistent CTA per SM, 192 threads):
+// Kernel anatomy (one persistent CTA per SM, 320 threads):
 //   warp 0      TMA producer: one elected lane streams {A_hi, A_lo, B_hi, B_lo} boxes through a ring of smem stages
 //   warp 1      TMEM allocator + MMA issuer: one lane issues 4 (K=16 steps) x {hi*hi, hi*lo, lo*hi} MMAs per stage,
 //               tcgen05.commit releases the stage / publishes the accumulator
-//   warps 2..5  epilogue: tcgen05.ld their 32-lane TMEM quarter, apply demodulation, noise, bias, leaky-ReLU, residual,
-//               scatter to the NCHW fp32 output.  Two accumulator stages (2 x 256 TMEM columns) overlap the epilogue of
-//               tile i with the mainloop of tile i+1.
+//   warps 2..9  epilogue: tcgen05.ld their 32-lane TMEM quarter (two warps per quarter, alternate 32-column blocks), apply
+//               demodulation, noise, bias, leaky-ReLU, residual, scatter to the NCHW fp32 output.  Two accumulator stages
+//               (2 x 256 TMEM columns) overlap the epilogue of tile i with the mainloop of tile i+1.
 // Roofline: tensor pipe.  FLOPs per launch = 2 * rows * Cout * ntaps * kp (x3 issued MMAs in bf16x3 mode).
 #include "umma_common.cuh"
 
 #include <atomic>
 
 namespace {
+
+constexpr int FWD_THREADS = 320;  // warp 0 producer, warp 1 MMA issuer, warps 2..9 epilogue
 
 struct GemmParams {
   int32_t rows;        // B * Hl * Wl lattice points
@@ -46,7 +48,7 @@ struct GemmSmem {
 };
 
 template <int kPasses>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(FWD_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams gp,
                  float* __restrict__ y, const float* __restrict__ out_mul, const float* __restrict__ noise,
                  const float* __restrict__ noise_w, const float* __restrict__ bias, const float* __restrict__ residual) {
@@ -75,7 +77,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 4);
+      mbar_init(tempty_bar(s), 8);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -170,12 +172,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     __syncwarp();
   } else {
-    // ===================================================================== epilogue (warps 2..5)
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    // ===================================================================== epilogue (warps 2..9)
+    // Eight warps: warp w may touch TMEM lanes 32*(w & 3)..+31; the two warps of a lane quarter take alternate blocks of 32
+    // accumulator columns.  With one warp per scheduler the epilogue of the few-tap passes (parity passes of the
+    // transposed conv, 1x1 shortcuts) was issue-latency bound at ~56 instructions per column; here the per-column work is
+    // a multiply, a pointer bump and a store, the per-channel factors come in as 128-bit loads, and the rare terms (noise,
+    // bias, activation, residual) are behind one warp-uniform branch.
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;  // 0: even 32-column blocks, 1: odd ones
     const int plane = gp.Hl * gp.Wl;
     const int64_t ostride_c = gp.out_cstride;
     const int64_t oplane = (int64_t)gp.out_H * gp.out_W;
-    const float nw = (noise != nullptr && noise_w != nullptr) ? __ldg(noise_w) : 0.f;
+    const bool has_noise = noise != nullptr && noise_w != nullptr;
+    const float nw = has_noise ? __ldg(noise_w) : 0.f;
+    const bool plain = !has_noise && bias == nullptr && residual == nullptr && !gp.act;
+    const bool vec_ok = (gp.Cout & 3) == 0;  // per-channel rows start 16-byte aligned
     int titer = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++titer) {
       const int m0 = (tile / gp.n_tiles) * GEMM_BLOCK_M;
@@ -199,36 +210,56 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       const int64_t pix = (int64_t)Y * gp.out_W + X;
       const int64_t ybase = (int64_t)b * gp.Cout * ostride_c + pix;
-      const float nz = (valid && noise != nullptr && noise_w != nullptr) ? nw * __ldg(noise + (int64_t)b * oplane + pix) : 0.f;
+      const float nz = (valid && has_noise) ? nw * __ldg(noise + (int64_t)b * oplane + pix) : 0.f;
       const float* om = out_mul ? out_mul + (int64_t)b * gp.Cout : nullptr;
 
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * GEMM_BLOCK_N);
-      for (int c0 = 0; c0 < n_eff; c0 += 32) {
+      for (int c0 = half * 32; c0 < n_eff; c0 += 64) {
         float v[32];
         tmem_ld32(taddr + (uint32_t)c0, v);
         if (valid) {
-          // Two halves of 16 columns: all global loads of a half are issued before the first dependent use, so the
-          // epilogue pays one memory latency per half instead of one per column (the issue order is in-order).
+          const int o0 = n0 + c0;
+          const bool full = o0 + 32 <= gp.Cout;
+          // per-channel factor out_scale * out_mul[b, o]
+          float f[32];
+          if (om && full && vec_ok) {
+            const float4* omp = reinterpret_cast<const float4*>(om + o0);
 #pragma unroll
-          for (int h0 = 0; h0 < 32; h0 += 16) {
-            float omv[16], bv[16], rv[16];
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {
-              const int o = n0 + c0 + h0 + k;
-              const int oc = o < gp.Cout ? o : gp.Cout - 1;
-              omv[k] = om ? __ldg(om + oc) : 1.f;
-              bv[k] = bias ? __ldg(bias + oc) : 0.f;
-              rv[k] = residual ? __ldg(residual + ybase + (int64_t)oc * ostride_c) : 0.f;
+            for (int k = 0; k < 8; ++k) {
+              const float4 t4 = __ldg(omp + k);
+              f[4 * k] = t4.x * gp.out_scale;
+              f[4 * k + 1] = t4.y * gp.out_scale;
+              f[4 * k + 2] = t4.z * gp.out_scale;
+              f[4 * k + 3] = t4.w * gp.out_scale;
             }
+          } else {
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
-              const int o = n0 + c0 + h0 + k;
-              float r = v[h0 + k] * gp.out_scale * omv[k] + nz + bv[k];
+            for (int k = 0; k < 32; ++k) {
+              const int oc = o0 + k < gp.Cout ? o0 + k : gp.Cout - 1;
+              f[k] = (om ? __ldg(om + oc) : 1.f) * gp.out_scale;
+            }
+          }
+          float* yp = y + ybase + (int64_t)o0 * ostride_c;
+          if (plain && full) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+              *yp = v[k] * f[k];
+              yp += ostride_c;
+            }
+          } else {
+            const float* rp = residual ? residual + ybase + (int64_t)o0 * ostride_c : nullptr;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+              const int o = o0 + k;
+              const int oc = o < gp.Cout ? o : gp.Cout - 1;
+              float r = v[k] * f[k] + nz + (bias ? __ldg(bias + oc) : 0.f);
               if (gp.act) r = (r > 0.f ? r : r * gp.act_alpha) * gp.act_gain;
-              r += rv[k];
-              if (o < gp.Cout) y[ybase + (int64_t)o * ostride_c] = r;
+              if (o < gp.Cout) {
+                if (rp) r += __ldg(rp + (int64_t)k * ostride_c);
+                yp[(int64_t)k * ostride_c] = r;
+              }
             }
           }
         }
@@ -581,7 +612,7 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams
   }
   const int tiles = gp.m_tiles * gp.n_tiles;
   const int grid = tiles < SPGAN_NUM_SMS ? tiles : SPGAN_NUM_SMS;
-  conv_gemm_kernel<kPasses><<<grid, GEMM_THREADS, S::kTotal, st>>>(tmA, tmB, gp, y, out_mul, noise, noise_w, bias, residual);
+  conv_gemm_kernel<kPasses><<<grid, FWD_THREADS, S::kTotal, st>>>(tmA, tmB, gp, y, out_mul, noise, noise_w, bias, residual);
   SPGAN_CHECK_LAUNCH("spgan_conv_gemm");
   launch_counter()->fetch_add(1);
   return 0;
