@@ -261,6 +261,10 @@ def run_ours(args):
                 "note": "achieved = algorithmic conv FLOPs (2*B*Ho*Wo*Cout*Cin*k^2, valid outputs, real channels) / CUDA-event "
                         "time of the launches; bf16x3 mode issues %dx that many tensor-core FLOPs" % issued}
 
+    shapes = sorted(gemm_stats.get("shapes", {}).items(), key=lambda kv: -kv[1][0])
+    roofline["by_shape"] = [{"shape": k, "ms_per_step": round(v[0] / args.steps, 3), "launches_per_step": v[2] // args.steps,
+                             "algorithmic_tflops": round(v[1] / (v[0] / 1000.0) / 1e12, 1) if v[0] > 0 else None}
+                            for k, v in shapes[:24]]
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

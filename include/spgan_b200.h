@@ -145,7 +145,7 @@ int spgan_conv_wgrad(const SpganConvPass* p, float* dw, const float* g, const fl
  *
  * spgan_pack_act: x (B, C, H, W) fp32 [* in_mul (B, C)] -> out [2][B*Hl*Wl][Cp] bf16; image pixel (y, x) lands on
  *   lattice point (y + pad_y0, x + pad_x0) of the (Hl, Wl) lattice, everything else (borders, channels C..Cp-1,
- *   Cp a multiple of 64) is zero.  Carries the style modulation of models/ops.py:598-600 (applied to the
+ *   Cp a multiple of 16) is zero.  Carries the style modulation of models/ops.py:598-600 (applied to the
  *   activations instead of the weights).
  *   step s > 1 writes s*s polyphase planes, out [2][s*s][B*Hl*Wl][Cp]: lattice point (i, j) of phase py*s + px holds image
  *   pixel (i*s + py - pad_y0, j*s + px - pad_x0).  A strided conv (the discriminator's stride-2 convs, models/ops.py:175;
@@ -172,7 +172,7 @@ int spgan_nchw_to_nhwc(float* out, const float* x, int B, int C, int H, int W, v
 int spgan_sphere_pack(uint16_t* out, const float* x_nhwc, const float* coords, const float* grid, const float* in_mul,
                       const uint32_t* chan_map, int B, int C, int H, int W, int grid_batch, int Cp, void* stream);
 /* spgan_conv_gemm: the tcgen05 kernel.  `p` is a conv pass whose (H, W) are the LATTICE dims (Hl, Wl) of the packed
- *   activation, Cin is ignored (K per tap = kp, a multiple of 64), in_stride must be 1, tap_w is ignored (the packed
+ *   activation, Cin is ignored (K per tap = kp, a multiple of 16), in_stride must be 1, tap_w is ignored (the packed
  *   weight is already in tap order) and precision must be 1 or 2.  a_packed [2][a_rows][kp], w_packed
  *   [2][ntaps][Cout][kp].  a_rows = phases * B*H*W; a tap reads phase plane f by carrying f * B*H in its tap_dy (the row
  *   offset of a tap is tap_dy*W + tap_dx).  Epilogue terms as in spgan_conv_pass. */

@@ -29,7 +29,8 @@ struct GemmParams {
   int32_t Cout, out_H, out_W;
   int32_t out_stride, out_off_y, out_off_x;
   int64_t out_cstride;     // elements between output channels
-  int32_t ntaps, kblocks;  // kblocks = kp / 64
+  int32_t ntaps, kblocks;  // kblocks = ceil(kp / 64)
+  int32_t last_ksteps;     // K = 16 steps in the last block of a tap (1..4)
   int32_t tap_off[SPGAN_MAX_TAPS];
   int32_t m_tiles, n_tiles;
   float out_scale;
@@ -38,22 +39,27 @@ struct GemmParams {
 };
 
 // ------------------------------------------------------------------------------------------------ GEMM kernel
-template <int kPasses>
+// kBlockN = 256 for the large layers; 128 halves the tile so that the small layers (structure synthesiser, first texture
+// layers: 70..300 M tiles of 128 rows) spread over the 148 SMs without a half-empty last wave.  The MMA rate is the same
+// (N = 128 takes half the cycles of N = 256); the A tile is simply fetched once per N tile from L2.
+template <int kPasses, int kBlockN>
 struct GemmSmem {
-  static constexpr int kStageBytes = (kPasses == 3 ? 2 : 1) * (A_TILE_BYTES + B_TILE_BYTES);
-  static constexpr int kStages = (kPasses == 3) ? 2 : 4;
+  static constexpr int kBTileBytes = kBlockN * GEMM_BLOCK_K * 2;
+  static constexpr int kStageBytes = (kPasses == 3 ? 2 : 1) * (A_TILE_BYTES + kBTileBytes);
+  static constexpr int kStages = (196608 / kStageBytes) < 4 ? (196608 / kStageBytes) : 4;
   static constexpr int kTileBytes = kStageBytes * kStages;
   static constexpr int kBarrierBytes = 256;
   static constexpr int kTotal = kTileBytes + kBarrierBytes + 1024;  // + alignment slack
 };
 
-template <int kPasses>
+template <int kPasses, int kBlockN>
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams gp,
                  float* __restrict__ y, const float* __restrict__ out_mul, const float* __restrict__ noise,
                  const float* __restrict__ noise_w, const float* __restrict__ bias, const float* __restrict__ residual) {
-  using S = GemmSmem<kPasses>;
+  using S = GemmSmem<kPasses, kBlockN>;
   constexpr int kStages = S::kStages;
+  constexpr int kBTile = S::kBTileBytes;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + S::kTileBytes;
@@ -99,7 +105,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m0 = (tile / gp.n_tiles) * GEMM_BLOCK_M;
-        const int n0 = (tile % gp.n_tiles) * GEMM_BLOCK_N;
+        const int n0 = (tile % gp.n_tiles) * kBlockN;
         for (int t = 0; t < gp.ntaps; ++t) {
           const int row = m0 + gp.tap_off[t];
           for (int kb = 0; kb < gp.kblocks; ++kb) {
@@ -110,7 +116,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               tma_load_3d(sa, &tmA, full_bar(stage), kb * GEMM_BLOCK_K, row, 0);
               tma_load_3d(sa + A_TILE_BYTES, &tmA, full_bar(stage), kb * GEMM_BLOCK_K, row, 1);
               tma_load_4d(sa + 2 * A_TILE_BYTES, &tmB, full_bar(stage), kb * GEMM_BLOCK_K, n0, t, 0);
-              tma_load_4d(sa + 2 * A_TILE_BYTES + B_TILE_BYTES, &tmB, full_bar(stage), kb * GEMM_BLOCK_K, n0, t, 1);
+              tma_load_4d(sa + 2 * A_TILE_BYTES + kBTile, &tmB, full_bar(stage), kb * GEMM_BLOCK_K, n0, t, 1);
             } else {
               tma_load_3d(sa, &tmA, full_bar(stage), kb * GEMM_BLOCK_K, row, 0);
               tma_load_4d(sa + A_TILE_BYTES, &tmB, full_bar(stage), kb * GEMM_BLOCK_K, n0, t, 0);
@@ -131,15 +137,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t phase = 0;
       int titer = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++titer) {
-        const int n0 = (tile % gp.n_tiles) * GEMM_BLOCK_N;
+        const int n0 = (tile % gp.n_tiles) * kBlockN;
         int n_eff = gp.Cout - n0;
-        n_eff = n_eff > GEMM_BLOCK_N ? GEMM_BLOCK_N : ((n_eff + 15) & ~15);
+        n_eff = n_eff > kBlockN ? kBlockN : ((n_eff + 15) & ~15);
         const uint32_t idesc = umma_idesc_bf16(n_eff);
         const int as = titer & 1;
         const uint32_t aphase = (uint32_t)(titer >> 1) & 1u;
         mbar_wait(tempty_bar(as), aphase ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(as * GEMM_BLOCK_N);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * kBlockN);
         for (int it = 0; it < kiters; ++it) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
@@ -147,9 +153,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t a_hi = sa;
           const uint32_t a_lo = sa + A_TILE_BYTES;
           const uint32_t b_hi = sa + (kPasses == 3 ? 2 : 1) * A_TILE_BYTES;
-          const uint32_t b_lo = b_hi + B_TILE_BYTES;
+          const uint32_t b_lo = b_hi + kBTile;
+          // the last K block of a tap may be partial (kp a multiple of 16, not of 64): TMA zero-fills the box, the MMAs
+          // of the all-zero K steps are simply not issued
+          const int ksteps = ((it + 1) % gp.kblocks == 0) ? gp.last_ksteps : GEMM_BLOCK_K / GEMM_UMMA_K;
 #pragma unroll
           for (int k = 0; k < GEMM_BLOCK_K / GEMM_UMMA_K; ++k) {
+            if (k >= ksteps) break;
             const uint32_t koff = k * GEMM_UMMA_K * 2;  // bytes inside the 128-byte swizzle row
             const uint64_t da_hi = umma_desc_sw128(a_hi + koff);
             const uint64_t db_hi = umma_desc_sw128(b_hi + koff);
@@ -190,9 +200,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int titer = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++titer) {
       const int m0 = (tile / gp.n_tiles) * GEMM_BLOCK_M;
-      const int n0 = (tile % gp.n_tiles) * GEMM_BLOCK_N;
+      const int n0 = (tile % gp.n_tiles) * kBlockN;
       int n_eff = gp.Cout - n0;
-      n_eff = n_eff > GEMM_BLOCK_N ? GEMM_BLOCK_N : ((n_eff + 15) & ~15);
+      n_eff = n_eff > kBlockN ? kBlockN : ((n_eff + 15) & ~15);
       const int as = titer & 1;
       const uint32_t aphase = (uint32_t)(titer >> 1) & 1u;
       // decode this thread's lattice point
@@ -215,7 +225,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * GEMM_BLOCK_N);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * kBlockN);
       for (int c0 = half * 32; c0 < n_eff; c0 += 64) {
         float v[32];
         tmem_ld32(taddr + (uint32_t)c0, v);
@@ -249,16 +259,23 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               yp += ostride_c;
             }
           } else {
+            // rare terms: all loads of a 16-column half are issued before the first dependent use
             const float* rp = residual ? residual + ybase + (int64_t)o0 * ostride_c : nullptr;
 #pragma unroll
-            for (int k = 0; k < 32; ++k) {
-              const int o = o0 + k;
-              const int oc = o < gp.Cout ? o : gp.Cout - 1;
-              float r = v[k] * f[k] + nz + (bias ? __ldg(bias + oc) : 0.f);
-              if (gp.act) r = (r > 0.f ? r : r * gp.act_alpha) * gp.act_gain;
-              if (o < gp.Cout) {
-                if (rp) r += __ldg(rp + (int64_t)k * ostride_c);
-                yp[(int64_t)k * ostride_c] = r;
+            for (int h0 = 0; h0 < 32; h0 += 16) {
+              float bv[16], rv[16];
+#pragma unroll
+              for (int k = 0; k < 16; ++k) {
+                const int o = o0 + h0 + k;
+                const int oc = o < gp.Cout ? o : gp.Cout - 1;
+                bv[k] = bias ? __ldg(bias + oc) : 0.f;
+                rv[k] = (rp && o < gp.Cout) ? __ldg(rp + (int64_t)(h0 + k) * ostride_c) : 0.f;
+              }
+#pragma unroll
+              for (int k = 0; k < 16; ++k) {
+                float r = v[h0 + k] * f[h0 + k] + nz + bv[k];
+                if (gp.act) r = (r > 0.f ? r : r * gp.act_alpha) * gp.act_gain;
+                if (o0 + h0 + k < gp.Cout) yp[(int64_t)(h0 + k) * ostride_c] = r + rv[k];
               }
             }
           }
@@ -328,6 +345,7 @@ __global__ void __launch_bounds__(256) pack_act_kernel(__nv_bfloat16* __restrict
     __nv_bfloat16 h0, l0, h1, l1;
     split_bf16(v0, h0, l0);
     split_bf16(v1, h1, l1);
+    if (c0 + 2 * cpair >= Cp) continue;  // Cp is a multiple of 16: the last channel tile may be partial
     const int64_t off = (((int64_t)ph * B + b) * plane_l + q) * Cp + c0 + 2 * cpair;
     *reinterpret_cast<__nv_bfloat162*>(out + off) = __halves2bfloat162(h0, h1);
     *reinterpret_cast<__nv_bfloat162*>(out_lo + off) = __halves2bfloat162(l0, l1);
@@ -598,24 +616,35 @@ std::atomic<long long>* launch_counter() {
   return &c;
 }
 
-template <int kPasses>
+template <int kPasses, int kBlockN>
 int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& gp, float* y, const float* out_mul,
                 const float* noise, const float* noise_w, const float* bias, const float* residual, cudaStream_t st) {
-  using S = GemmSmem<kPasses>;
+  using S = GemmSmem<kPasses, kBlockN>;
   static bool attr_set[64] = {false};
   int dev = 0;
   SPGAN_CUDA(cudaGetDevice(&dev), "spgan_conv_gemm");
   if (dev < 64 && !attr_set[dev]) {
-    SPGAN_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<kPasses>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal),
+    SPGAN_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<kPasses, kBlockN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal),
                "spgan_conv_gemm (shared memory opt-in)");
     attr_set[dev] = true;
   }
   const int tiles = gp.m_tiles * gp.n_tiles;
   const int grid = tiles < SPGAN_NUM_SMS ? tiles : SPGAN_NUM_SMS;
-  conv_gemm_kernel<kPasses><<<grid, FWD_THREADS, S::kTotal, st>>>(tmA, tmB, gp, y, out_mul, noise, noise_w, bias, residual);
+  conv_gemm_kernel<kPasses, kBlockN><<<grid, FWD_THREADS, S::kTotal, st>>>(tmA, tmB, gp, y, out_mul, noise, noise_w, bias, residual);
   SPGAN_CHECK_LAUNCH("spgan_conv_gemm");
   launch_counter()->fetch_add(1);
   return 0;
+}
+
+// N tile choice: the one whose tiles fill whole waves of the 148 SMs best (ties go to 256: fewer A re-reads).
+int pick_block_n(int64_t m_tiles, int cout) {
+  if (cout <= 128) return 128;
+  auto eff = [&](int bn) {
+    const int64_t tiles = m_tiles * ((cout + bn - 1) / bn);
+    const int64_t waves = (tiles + SPGAN_NUM_SMS - 1) / SPGAN_NUM_SMS;
+    return (double)tiles / (double)(waves * SPGAN_NUM_SMS);
+  };
+  return eff(128) > eff(256) + 0.04 ? 128 : 256;
 }
 
 }  // namespace
@@ -627,11 +656,11 @@ extern "C" int spgan_pack_act(uint16_t* out, const float* x, const float* in_mul
   SPGAN_CHECK_ARG(B >= 0 && C >= 0 && H >= 0 && W >= 0 && pad_y >= 0 && pad_x >= 0, "spgan_pack_act: negative size");
   SPGAN_CHECK_ARG(step >= 1 && step <= 8, "spgan_pack_act: step %d unsupported", step);
   SPGAN_CHECK_ARG(step > 1 || (Hl >= H + pad_y && Wl >= W + pad_x), "spgan_pack_act: lattice %dx%d smaller than the padded image", Hl, Wl);
-  SPGAN_CHECK_ARG(Cp >= C && Cp % 64 == 0, "spgan_pack_act: Cp=%d must be a multiple of 64 and >= C=%d", Cp, C);
+  SPGAN_CHECK_ARG(Cp >= C && Cp % 16 == 0, "spgan_pack_act: Cp=%d must be a multiple of 16 and >= C=%d", Cp, C);
   if (B == 0 || Cp == 0 || H == 0 || W == 0) return 0;
   SPGAN_CHECK_ARG(out && x, "spgan_pack_act: null pointer");
   SPGAN_CHECK_ARG(B * step * step <= 65535, "spgan_pack_act: batch %d x %d phases > 65535", B, step * step);
-  dim3 grid((Hl * Wl + 63) / 64, Cp / 64, B * step * step);
+  dim3 grid((Hl * Wl + 63) / 64, (Cp + 63) / 64, B * step * step);
   pack_act_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)out, x, in_mul, B, C, H, W, Cp, pad_y, pad_x,
                                                           Hl, Wl, step);
   SPGAN_CHECK_LAUNCH("spgan_pack_act");
@@ -642,7 +671,7 @@ extern "C" int spgan_pack_weight(uint16_t* out, const float* w, int Cout, int Ci
                                  const int32_t* tap_w, int Cp, int merged, void* stream) {
   SPGAN_CHECK_ARG(Cout >= 0 && Cin >= 0, "spgan_pack_weight: negative size");
   SPGAN_CHECK_ARG(ntaps >= 1 && ntaps <= SPGAN_MAX_TAPS, "spgan_pack_weight: %d taps unsupported", ntaps);
-  SPGAN_CHECK_ARG(Cp >= Cin && Cp % 64 == 0, "spgan_pack_weight: Cp=%d must be a multiple of 64 and >= Cin=%d", Cp, Cin);
+  SPGAN_CHECK_ARG(Cp >= Cin && Cp % 16 == 0, "spgan_pack_weight: Cp=%d must be a multiple of 16 and >= Cin=%d", Cp, Cin);
   if (Cout == 0 || Cp == 0) return 0;
   SPGAN_CHECK_ARG(out && w && tap_w, "spgan_pack_weight: null pointer");
   TapList taps;
@@ -705,7 +734,7 @@ extern "C" int spgan_conv_gemm(const SpganConvPass* p, float* y, const uint16_t*
                   p->precision);
   SPGAN_CHECK_ARG(p->ntaps >= 1 && p->ntaps <= SPGAN_MAX_TAPS, "spgan_conv_gemm: %d taps unsupported", p->ntaps);
   SPGAN_CHECK_ARG(p->in_stride == 1, "spgan_conv_gemm: in_stride %d unsupported on the tcgen05 path", p->in_stride);
-  SPGAN_CHECK_ARG(kp > 0 && kp % GEMM_BLOCK_K == 0, "spgan_conv_gemm: kp=%d must be a positive multiple of 64", kp);
+  SPGAN_CHECK_ARG(kp > 0 && kp % GEMM_UMMA_K == 0, "spgan_conv_gemm: kp=%d must be a positive multiple of 16", kp);
   SPGAN_CHECK_ARG(p->B >= 0 && p->H >= 0 && p->W >= 0 && p->Cout >= 0, "spgan_conv_gemm: negative size");
   SPGAN_CHECK_ARG(p->out_stride >= 1, "spgan_conv_gemm: out_stride must be >= 1");
   const int64_t rows = (int64_t)p->B * p->H * p->W;
@@ -732,11 +761,13 @@ extern "C" int spgan_conv_gemm(const SpganConvPass* p, float* y, const uint16_t*
   gp.out_off_x = p->out_off_x;
   gp.out_cstride = p->out_cstride ? p->out_cstride : (int64_t)p->out_H * p->out_W;
   gp.ntaps = p->ntaps;
-  gp.kblocks = kp / GEMM_BLOCK_K;
+  gp.kblocks = (kp + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+  gp.last_ksteps = (kp - (gp.kblocks - 1) * GEMM_BLOCK_K) / GEMM_UMMA_K;
   for (int t = 0; t < p->ntaps; ++t) gp.tap_off[t] = p->tap_dy[t] * p->W + p->tap_dx[t];
   for (int t = p->ntaps; t < SPGAN_MAX_TAPS; ++t) gp.tap_off[t] = 0;
   gp.m_tiles = (int32_t)((rows + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M);
-  gp.n_tiles = (p->Cout + GEMM_BLOCK_N - 1) / GEMM_BLOCK_N;
+  const int block_n = pick_block_n(gp.m_tiles, p->Cout);
+  gp.n_tiles = (p->Cout + block_n - 1) / block_n;
   gp.out_scale = p->out_scale;
   gp.act = p->act;
   gp.act_alpha = p->act_alpha;
@@ -752,10 +783,13 @@ extern "C" int spgan_conv_gemm(const SpganConvPass* p, float* y, const uint16_t*
   {
     cuuint64_t dims[4] = {(cuuint64_t)kp, (cuuint64_t)p->Cout, (cuuint64_t)p->ntaps, 2};
     cuuint64_t strides[3] = {(cuuint64_t)kp * 2, (cuuint64_t)p->Cout * kp * 2, (cuuint64_t)p->ntaps * p->Cout * kp * 2};
-    cuuint32_t box[4] = {GEMM_BLOCK_K, GEMM_BLOCK_N, 1, 1};
+    cuuint32_t box[4] = {GEMM_BLOCK_K, (cuuint32_t)block_n, 1, 1};
     if (int e = encode_bf16_map(&tmB, w_packed, 4, dims, strides, box, "spgan_conv_gemm (B map)")) return e;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  if (p->precision == 1) return launch_gemm<3>(tmA, tmB, gp, y, out_mul, noise, noise_w, bias, residual, st);
-  return launch_gemm<1>(tmA, tmB, gp, y, out_mul, noise, noise_w, bias, residual, st);
+  if (p->precision == 1)
+    return block_n == 256 ? launch_gemm<3, 256>(tmA, tmB, gp, y, out_mul, noise, noise_w, bias, residual, st)
+                          : launch_gemm<3, 128>(tmA, tmB, gp, y, out_mul, noise, noise_w, bias, residual, st);
+  return block_n == 256 ? launch_gemm<1, 256>(tmA, tmB, gp, y, out_mul, noise, noise_w, bias, residual, st)
+                        : launch_gemm<1, 128>(tmA, tmB, gp, y, out_mul, noise, noise_w, bias, residual, st);
 }

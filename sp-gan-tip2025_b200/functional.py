@@ -44,8 +44,12 @@ def profile_gemm(on):
         return None
     rec, _PROFILE = _PROFILE or [], None
     torch.cuda.synchronize()
-    return {"ms": float(sum(a.elapsed_time(b) for a, b, _ in rec)), "flops": float(sum(f for _, _, f in rec)),
-            "launches": len(rec)}
+    shapes = {}
+    for a, b, f, key in rec:
+        ms, fl, n = shapes.get(key, (0.0, 0.0, 0))
+        shapes[key] = (ms + a.elapsed_time(b), fl + f, n + 1)
+    return {"ms": float(sum(v[0] for v in shapes.values())), "flops": float(sum(f for _, _, f, _ in rec)),
+            "launches": len(rec), "shapes": shapes}
 
 
 def profile_calls(on):
@@ -85,7 +89,10 @@ def _timed_call(flops, name, *args):
     e0.record()
     lib.call(name, *args)
     e1.record()
-    _PROFILE.append((e0, e1, flops))
+    cp = args[0]._obj  # the SpganConvPass of this launch: label the shape for the per-layer breakdown
+    key = "%s taps%d lattice%dx%dx%d cout%d %s" % (name.replace("spgan_conv_", ""), cp.ntaps, cp.B, cp.H, cp.W, cp.Cout,
+                                                  "act" if cp.act else "plain")
+    _PROFILE.append((e0, e1, flops, key))
 
 
 def _gemm_call(flops, *args):
@@ -551,7 +558,7 @@ def conv_apply(x, w, geom, adjoint=False, out_hw=None, in_mul=None, out_mul=None
             step, pt, pl, Hl, Wl, mapped = _phase_taps(passes)
             if step == 1:
                 Hl, Wl = max(Hl, pt + H), max(Wl, pl + W)
-            Cp = _round_up(Cin, 64)
+            Cp = _round_up(Cin, 16)  # K granularity of the bf16 MMA; the last 64-wide K block may be partial
             rows = B * Hl * Wl
             a_packed = torch.empty((2, step * step * rows, Cp), device=x.device, dtype=torch.bfloat16)
             lib.call("spgan_pack_act", _ptr(a_packed), _ptr(x), _ptr(im), B, Cin, H, W, Cp, pt, pl, Hl, Wl, step, st)
