@@ -36,8 +36,9 @@ def parse():
     ap.add_argument("--cpu-sample-patches", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-calls", action="store_true", help="add per-entry-point CUDA-event times of one extra step")
-    ap.add_argument("--workload", default="panorama", choices=["panorama", "train"],
-                    help="panorama = BASELINE configs[1] (default, the headline); train = configs[2], full G+D step")
+    ap.add_argument("--workload", default="panorama", choices=["panorama", "train", "pano768"],
+                    help="panorama = BASELINE configs[1] (default, the headline); train = configs[2], full G+D step; "
+                         "pano768 = configs[3], one batch of 768x1536 panoramas with the patch lattice sharded over the ranks")
     ap.add_argument("--train-batch", type=int, default=8)
     return ap.parse_args()
 
@@ -163,10 +164,13 @@ def run_ours(args):
     torch.manual_seed(9000)
     gen = Generator().to(dev).eval()
     B = args.batch
-    pl = panorama.plan(384, 768)
+    sharded = args.workload == "pano768"
+    th, tw = (768, 1536) if sharded else (384, 768)
+    pl = panorama.plan(th, tw)
     n_pos = len(panorama.positions(pl))
 
-    g = torch.Generator(device="cpu").manual_seed(9000 + rank)
+    # sharded: every rank holds the SAME canvases (same seed) and runs its share of the lattice (strong scaling)
+    g = torch.Generator(device="cpu").manual_seed(9000 + (0 if sharded else rank))
     host = {
         "gl": torch.randn(B, 2, 512, generator=g).pin_memory(),
         "canvas": torch.randn(B, 256, pl["lat_h"], pl["lat_w"], generator=g).pin_memory(),
@@ -184,13 +188,16 @@ def run_ours(args):
     resident = upload()
     meta = torch.zeros(B, 3, pl["meta_h"], pl["meta_w"], device=dev)
 
-    def step_resident():
-        gl, canvas, noises = resident
+    def run(gl, canvas, noises):
+        if sharded:
+            return panorama.generate_sharded(gen, pl, gl, canvas, noises, rank, world, meta=meta)
         return panorama.generate(gen, pl, gl, canvas, noises, meta=meta)
 
+    def step_resident():
+        return run(*resident)
+
     def step_e2e():
-        gl, canvas, noises = upload()
-        out = panorama.generate(gen, pl, gl, canvas, noises, meta=meta)
+        out = run(*upload())
         host_out.copy_(out, non_blocking=True)
         return out
 
@@ -226,7 +233,8 @@ def run_ours(args):
     gemm_stats = SF.profile_gemm(False)
     clocks = sampler.stop() if sampler else None
     ms_step = ms_total / args.steps
-    value = world * B / (ms_step / 1000.0)
+    jobs = B if sharded else world * B  # sharded: the ranks share ONE batch of panoramas
+    value = jobs / (ms_step / 1000.0)
 
     call_ms = None
     if args.profile_calls:
@@ -237,7 +245,7 @@ def run_ours(args):
 
     step_e2e()
     ms_e2e = timed(step_e2e, args.steps) / args.steps
-    e2e_value = world * B / (ms_e2e / 1000.0)
+    e2e_value = jobs / (ms_e2e / 1000.0)
 
     if rank != 0:
         if world > 1:
@@ -266,22 +274,25 @@ def run_ours(args):
                              "algorithmic_tflops": round(v[1] / (v[0] / 1000.0) / 1e12, 1) if v[0] > 0 else None}
                             for k, v in shapes[:24]]
     out = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "metric": METRIC.replace("384x768", "%dx%d" % (th, tw)) + ("_lattice_sharded" if sharded else ""), "value": value,
+        "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None,
         "dtype": {0: "fp32 (SIMT)", 1: "fp32-equivalent (bf16x3 split on tcgen05, fp32 accumulate)", 2: "bf16 (tcgen05, fp32 accumulate)"}[args.precision],
         "data": "synthetic",
-        "config": {"workload": "SP-GAN generator forward batch %d at 384x768 (close-loop, %d patch positions x %d patches of 101x101 per step), "
-                               "random-init configs/model/spgan.yaml, synthetic latents" % (B, n_pos, B),
-                   "batch_per_gpu": B, "patches_per_step_per_gpu": B * n_pos, "l2": "inputs and activations larger than L2 (latent canvas %d MB, activations > 1 GB per patch batch)" % (host["canvas"].numel() * 4 // 2 ** 20),
-                   "precision_mode": args.precision, "algorithmic_tflop_per_step_per_gpu": B * n_pos * PATCH_GFLOP / 1000.0},
+        "config": {"workload": "SP-GAN generator forward batch %d at %dx%d (close-loop, %d patch positions x %d patches of 101x101 per step%s), "
+                               "random-init configs/model/spgan.yaml, synthetic latents" % (
+                                   B, th, tw, n_pos, B, ", lattice positions sharded over the ranks + one all-gather of the patches" if sharded else ""),
+                   "batch_per_gpu": B, "patches_per_step_per_gpu": B * (-(-n_pos // world) if sharded else n_pos), "l2": "inputs and activations larger than L2 (latent canvas %d MB, activations > 1 GB per patch batch)" % (host["canvas"].numel() * 4 // 2 ** 20),
+                   "precision_mode": args.precision,
+                   "algorithmic_tflop_per_step_per_gpu": B * (-(-n_pos // world) if sharded else n_pos) * PATCH_GFLOP / 1000.0},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
         "gpu_launches": l1 - l0, "tcgen05_gemm_launches": int(g1 - g0),
-        "achieved_model_tflops": world * B * n_pos * PATCH_GFLOP / 1000.0 / (ms_step / 1000.0),
+        "achieved_model_tflops": jobs * n_pos * PATCH_GFLOP / 1000.0 / (ms_step / 1000.0),
         "clocks": clocks, "roofline": roofline,
     }
     if call_ms is not None:
         out["call_ms"] = call_ms
-    if not args.no_cpu_baseline and world >= 1:
+    if not args.no_cpu_baseline and not sharded:
         rate, threads, dt, total = cpu_reference_rate(args.cpu_sample_patches)
         out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                                "sample": "B=1, first %d of %d patch positions of one 384x768 panorama (%.1f s), oracle port of the reference's PyTorch CPU path" % (args.cpu_sample_patches, total, dt)}

@@ -121,37 +121,79 @@ def circular_assign(t, width, x_st, x_ed, y_st, y_ed, v):
         t[:, :, x_st:x_ed, y_st % width:y_ed % width] = v
 
 
+def _run_position(gen, pl, global_latent, local_latent, coords_full, noises, styles, it, ix, iy):
+    """One lattice position: slice the canvases (with longitude wrap), run the generator on the patch batch."""
+    lat_h, lat_w = local_latent.shape[2], local_latent.shape[3]
+    cp, (zx_st, zx_ed, zy_st, zy_ed) = patch_inputs(pl, ix, iy, it, lat_h, lat_w)
+    cur_lat = circular_slice(local_latent, lat_w, zx_st, zx_ed, zy_st, zy_ed).contiguous()
+    cur_coords = circular_slice(coords_full, lat_w, zx_st, zx_ed, zy_st, zy_ed).contiguous()
+    cur_noises = []
+    for l in range(8):
+        fx, fy = ix * pl["outfeat_step"][l], iy * pl["outfeat_step"][l]
+        s = pl["out_sizes"][l]
+        cur_noises.append(circular_slice(noises[l], pl["noise_w"][l], fx, fx + s, fy, fy + s).contiguous())
+    return gen(global_latent, cur_lat, cur_coords, cp, noises=cur_noises, styles=styles)
+
+
+def _prepare(gen, global_latent, local_latent):
+    B = local_latent.shape[0]
+    coords_full = meta_coords(local_latent.shape[2], local_latent.shape[3], local_latent.device).unsqueeze(0).expand(B, -1, -1, -1)
+    if global_latent.dim() == 2:
+        global_latent = torch.stack([global_latent, global_latent], 1)
+    # the mapping network and every layer's modulation / demodulation depend only on the global latent: computed once
+    # per panorama batch (the per-layer (s, d) pairs are memoised inside ModulatedConv2d as long as `styles` lives)
+    styles = gen.texture_synthesizer.styles_for(global_latent) if hasattr(gen, "texture_synthesizer") else None
+    return global_latent, coords_full, styles
+
+
 @torch.no_grad()
 def generate(gen, pl, global_latent, local_latent, noises, meta=None, only=None):
     """Generate (a shard of) a batch of panoramas.  global_latent (B, 2, 512) or (B, 512); local_latent
     (B, 256, lat_h, lat_w) circular canvas; noises: 8 canvases (B, 1, noise_h[l], noise_w[l]).
     `only`: optional set of lattice positions to run (rank sharding); returns the (B, 3, meta_h, meta_w) meta image."""
     B = local_latent.shape[0]
-    dev = local_latent.device
-    lat_h, lat_w = local_latent.shape[2], local_latent.shape[3]
     if meta is None:
-        meta = torch.zeros(B, 3, pl["meta_h"], pl["meta_w"], device=dev)
-    coords_full = meta_coords(lat_h, lat_w, dev).unsqueeze(0).expand(B, -1, -1, -1)
+        meta = torch.zeros(B, 3, pl["meta_h"], pl["meta_w"], device=local_latent.device)
     P = pl["patch"]
-    if global_latent.dim() == 2:
-        global_latent = torch.stack([global_latent, global_latent], 1)
-    # the mapping network and every layer's modulation / demodulation depend only on the global latent: computed once
-    # per panorama batch (the per-layer (s, d) pairs are memoised inside ModulatedConv2d as long as `styles` lives)
-    styles = gen.texture_synthesizer.styles_for(global_latent)
+    global_latent, coords_full, styles = _prepare(gen, global_latent, local_latent)
     for it, (ix, iy) in enumerate(positions(pl)):
         if only is not None and (ix, iy) not in only:
             continue
-        cp, (zx_st, zx_ed, zy_st, zy_ed) = patch_inputs(pl, ix, iy, it, lat_h, lat_w)
-        cur_lat = circular_slice(local_latent, lat_w, zx_st, zx_ed, zy_st, zy_ed).contiguous()
-        cur_coords = circular_slice(coords_full, lat_w, zx_st, zx_ed, zy_st, zy_ed).contiguous()
-        cur_noises = []
-        for l in range(8):
-            fx, fy = ix * pl["outfeat_step"][l], iy * pl["outfeat_step"][l]
-            s = pl["out_sizes"][l]
-            cur_noises.append(circular_slice(noises[l], pl["noise_w"][l], fx, fx + s, fy, fy + s).contiguous())
-        patch = gen(global_latent, cur_lat, cur_coords, cp, noises=cur_noises, styles=styles)
+        patch = _run_position(gen, pl, global_latent, local_latent, coords_full, noises, styles, it, ix, iy)
         px, py = ix * pl["pix_step"], iy * pl["pix_step"]
         circular_assign(meta, pl["meta_w"], px, px + P, py, py + P, patch)
+    return meta
+
+
+@torch.no_grad()
+def generate_sharded(gen, pl, global_latent, local_latent, noises, rank, world, meta=None):
+    """Multi-GPU generation of ONE batch of panoramas (BASELINE configs[3]: 768x1536, lattice sharded over the ranks).
+
+    Every rank holds the same canvases (broadcast once by the caller: 256*lat_h*lat_w*4 bytes per sample), runs the
+    lattice positions rank, rank + world, ... and the finished (B, 3, 101, 101) patches are exchanged with ONE
+    all-gather (122 KB per patch and sample); each rank then writes all patches into the meta image in the reference's
+    row-major order, so the 5-pixel overlaps resolve exactly as in the sequential loop
+    (base_test_manager.py:305-325: later patches overwrite earlier ones)."""
+    import torch.distributed as dist
+    B = local_latent.shape[0]
+    P = pl["patch"]
+    if meta is None:
+        meta = torch.zeros(B, 3, pl["meta_h"], pl["meta_w"], device=local_latent.device)
+    pos = positions(pl)
+    global_latent, coords_full, styles = _prepare(gen, global_latent, local_latent)
+    per_rank = -(-len(pos) // world)
+    mine = torch.zeros(per_rank, B, 3, P, P, device=local_latent.device)
+    for slot, it in enumerate(range(rank, len(pos), world)):
+        ix, iy = pos[it]
+        mine[slot] = _run_position(gen, pl, global_latent, local_latent, coords_full, noises, styles, it, ix, iy)
+    if world > 1:
+        allp = torch.empty(world, per_rank, B, 3, P, P, device=mine.device)
+        dist.all_gather_into_tensor(allp.view(world * per_rank, B, 3, P, P), mine)
+    else:
+        allp = mine.unsqueeze(0)
+    for it, (ix, iy) in enumerate(pos):
+        px, py = ix * pl["pix_step"], iy * pl["pix_step"]
+        circular_assign(meta, pl["meta_w"], px, px + P, py, py + P, allp[it % world, it // world])
     return meta
 
 

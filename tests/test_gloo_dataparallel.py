@@ -32,7 +32,19 @@ def _worker(rank, world, port, ret):
     for p_ in mine:
         counts[pos.index(p_)] += 1
     dist.all_reduce(counts)
-    ret[rank] = bool(ok and n >= 2 and params[4].grad is None and bool((counts == 1).all()))
+    # sharded panorama generation with a stub generator: identical to the sequential loop on every rank
+    def stub_gen(global_latent, lat, coords, cp, noises=None, styles=None):
+        v = lat.mean(dim=(1, 2, 3)) + coords.mean(dim=(1, 2, 3)) + noises[7].mean(dim=(1, 2, 3)) + cp["p_x_st"] + 3 * cp["p_y_st"]
+        base = torch.arange(101 * 101, dtype=torch.float32).view(1, 1, 101, 101) / 1e4
+        return (v.view(-1, 1, 1, 1) + base).expand(-1, 3, -1, -1).contiguous()
+    g = torch.Generator().manual_seed(5)
+    gl = torch.randn(2, 512, generator=g)
+    canvas = torch.randn(2, 256, pl["lat_h"], pl["lat_w"], generator=g)
+    noises = [torch.randn(2, 1, pl["noise_h"][l], pl["noise_w"][l], generator=g) for l in range(8)]
+    seq = panorama.generate(stub_gen, pl, gl, canvas, noises)
+    sh = panorama.generate_sharded(stub_gen, pl, gl, canvas, noises, rank, world)
+    same = bool(torch.equal(seq, sh))
+    ret[rank] = bool(ok and n >= 2 and params[4].grad is None and bool((counts == 1).all()) and same)
     dist.destroy_process_group()
 
 
