@@ -35,6 +35,7 @@ def parse():
     ap.add_argument("--precision", type=int, default=1, choices=[0, 1, 2])
     ap.add_argument("--cpu-sample-patches", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true", help="profiling runs under ncu only: skip the end-to-end leg")
     ap.add_argument("--profile-calls", action="store_true", help="add per-entry-point CUDA-event times of one extra step")
     ap.add_argument("--workload", default="panorama", choices=["panorama", "train", "pano768"],
                     help="panorama = BASELINE configs[1] (default, the headline); train = configs[2], full G+D step; "
@@ -221,7 +222,7 @@ def run_ours(args):
             ms = float(t.item())
         return ms
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(args.warmup if args.skip_e2e else max(args.warmup, 3)):
         step_resident()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
@@ -243,8 +244,11 @@ def run_ours(args):
         call_ms = {k: [round(v[0], 3), v[1]] for k, v in sorted(SF.profile_calls(False).items(), key=lambda kv: -kv[1][0])}
         call_ms["_step_total_ms"] = ms_prof
 
-    step_e2e()
-    ms_e2e = timed(step_e2e, args.steps) / args.steps
+    if args.skip_e2e:
+        ms_e2e = float("nan")
+    else:
+        step_e2e()
+        ms_e2e = timed(step_e2e, args.steps) / args.steps
     e2e_value = jobs / (ms_e2e / 1000.0)
 
     if rank != 0:
@@ -402,7 +406,7 @@ def run_train(args):
     def amortised(ms):
         return ms["d"] + ms["g"] + ms["ema"] + ms["r1"] / tp.d_reg_every + ms["path"] / tp.g_reg_every
 
-    measure(max(args.warmup, 3), False)
+    measure(args.warmup if args.skip_e2e else max(args.warmup, 3), False)
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -412,7 +416,7 @@ def run_train(args):
     l1, g1 = lib.launches(), lib.load().spgan_gemm_launch_count()
     gemm_stats = SF.profile_gemm(False)
     clocks = sampler.stop() if sampler else None
-    ms_e2e = measure(args.steps, True)
+    ms_e2e = measure(args.steps, True) if not args.skip_e2e else {k: float("nan") for k in parts}
     call_ms = None
     if args.profile_calls:
         SF.profile_calls(True)
