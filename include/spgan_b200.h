@@ -84,6 +84,16 @@ int spgan_sphere_gather_indices(int32_t* x0, int32_t* y0, float* wx, float* wy, 
  * grad_out (planes, 3H, 3W) → grad_in (planes, H, W).  The guarded all_reduce of :621-622 is deliberately absent. */
 int spgan_sphere_gather_bwd(float* grad_in, const float* grad_out, int64_t planes, int H, int W, void* stream);
 
+/* Per-sample training grids assembled on the device (replaces the per-sample, per-layer host rebuild of
+ * models/spgan_ops_gs.py:767-781 -> models/spherenet/grid_generator.py:137-283).  The grid separates into a row factor
+ * (lat_n (slots_x, H, 9) fp32 final latitude coordinate; lon (slots_x, H, 9) fp64 tangent-plane longitude offset) and a
+ * column factor (nlon (slots_y, W) fp64 normalised column base); the host computes each factor once per distinct window
+ * edge with numpy float64 and keeps it on the device.  ix / iy (B) int32 pick the slots of each sample.  The kernel redoes
+ * the reference's remaining float64 add / divide / multiply sequence with round-to-nearest intrinsics: out
+ * (B, 3H, 3W, 2) fp32 equals the host-built grid bit for bit. */
+int spgan_sphere_grid_assemble(float* out, const float* lat_n, const double* lon, const double* nlon, const int32_t* ix,
+                               const int32_t* iy, int B, int H, int W, double y_total, void* stream);
+
 /* ---- L7: EqualLinear ------------------------------------------------------------------------------------
  * Replaces F.linear(x, W * w_scale, bias * b_scale) [+ fused_leaky_relu] (models/ops.py:213-218).
  * x (M, K), w (N, K), bias (N) or NULL, y (M, N).  act: 0 none, 1 = leaky-relu(alpha) * gain applied after bias. */

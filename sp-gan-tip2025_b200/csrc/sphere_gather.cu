@@ -103,6 +103,55 @@ __global__ void __launch_bounds__(256) sphere_gather_bwd_kernel(float* __restric
   }
 }
 
+// Assemble per-sample training grids on the device from the two factors the grid separates into:
+// the latitude part and the tangent-plane longitude offsets depend only on the rows of the window (p_x_st / p_x_ed),
+// the normalised column base only on its columns (p_y_st / p_y_ed / circular flag).  The host keeps the float64 factor
+// tables it computed with numpy (bit-exact libm), this kernel redoes the reference's remaining float64 +, /, * sequence
+// (models/spherenet/grid_generator.py:270-283, models/spgan_ops_gs.py:416-423) with explicit round-to-nearest
+// intrinsics, so the result equals the host-built grid bit for bit without a host round trip per sample.
+//   out[b, 3y+ky, 3x+kx, 0] = float(((((lon[ix[b]][y][k] + nlon[iy[b]][x]) / 2 + 0.5) * y_total) / y_total) * 2 - 1)
+//   out[b, 3y+ky, 3x+kx, 1] = lat_n[ix[b]][y][k]
+__global__ void __launch_bounds__(256) grid_assemble_kernel(float* __restrict__ out, const float* __restrict__ lat_n,
+                                                           const double* __restrict__ lon, const double* __restrict__ nlon,
+                                                           const int* __restrict__ ix, const int* __restrict__ iy, int B,
+                                                           int H, int W, double y_total) {
+  const int OW = 3 * W;
+  const int64_t per = (int64_t)9 * H * W;
+  const int64_t total = (int64_t)B * per;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(idx / per);
+    const int r = (int)(idx - (int64_t)b * per);
+    const int oy = r / OW, ox = r - oy * OW;
+    const int y = oy / 3, ky = oy - 3 * y, x = ox / 3, kx = ox - 3 * x;
+    const int sx = __ldg(ix + b), sy = __ldg(iy + b);
+    const int64_t t = ((int64_t)sx * H + y) * 9 + ky * 3 + kx;
+    const double a = __dadd_rn(__ldg(lon + t), __ldg(nlon + (int64_t)sy * W + x));
+    const double g = __dmul_rn(__dadd_rn(__ddiv_rn(a, 2.0), 0.5), y_total);
+    const double n = __dsub_rn(__dmul_rn(__ddiv_rn(g, y_total), 2.0), 1.0);
+    float2 v;
+    v.x = __double2float_rn(n);
+    v.y = __ldg(lat_n + t);
+    reinterpret_cast<float2*>(out)[idx] = v;
+  }
+}
+
+}  // namespace
+
+extern "C" int spgan_sphere_grid_assemble(float* out, const float* lat_n, const double* lon, const double* nlon,
+                                          const int32_t* ix, const int32_t* iy, int B, int H, int W, double y_total,
+                                          void* stream) {
+  SPGAN_CHECK_ARG(B >= 0 && H >= 0 && W >= 0, "spgan_sphere_grid_assemble: negative size");
+  if (B == 0 || H == 0 || W == 0) return 0;
+  SPGAN_CHECK_ARG(out && lat_n && lon && nlon && ix && iy, "spgan_sphere_grid_assemble: null pointer");
+  SPGAN_CHECK_ARG((((uintptr_t)out) & 7) == 0, "spgan_sphere_grid_assemble: out must be 8-byte aligned");
+  const int64_t total = (int64_t)B * 9 * H * W;
+  grid_assemble_kernel<<<grid_for(total, 256, 8), 256, 0, (cudaStream_t)stream>>>(out, lat_n, lon, nlon, ix, iy, B, H, W, y_total);
+  SPGAN_CHECK_LAUNCH("spgan_sphere_grid_assemble");
+  return 0;
+}
+
+namespace {
 }  // namespace
 
 extern "C" int spgan_sphere_gather(float* out, const float* z, const float* grid, int B, int C, int H, int W,

@@ -19,30 +19,44 @@ def _norm(v):
     return (v - np.min(v)) / (np.max(v) - np.min(v)) * 2 + (-1)
 
 
-def angular_ranges(h, w, cp):
-    """Centre latitudes / longitudes of the patch rows / columns: grid_generator.py:164-241, plain branch
-    (`full_shape` / `pre_sample_mode` are never set by spgan.yaml or the close-loop manager)."""
+def _check_plain(cp):
     if cp.get("full_shape", None) is not None or cp.get("pre_sample_mode", False):
         raise NotImplementedError("coords_partial['full_shape'/'pre_sample_mode'] is not used by spgan.yaml and is not supported")
+
+
+def lat_range(h, cp):
+    """Centre latitudes of the patch rows: grid_generator.py:164-241, plain branch (`full_shape` / `pre_sample_mode`
+    are never set by spgan.yaml or the close-loop manager)."""
+    _check_plain(cp)
     partial = 0.8  # training hard-codes 0.8 (grid_generator.py:164-167)
     if cp.get("test_flag", False):
         partial = cp.get("partial", partial)
     x_st = cp["p_x_st"] * np.pi * partial
     x_ed = cp["p_x_ed"] * np.pi * partial
+    return np.linspace(x_st, x_ed, h) - (np.pi / 2 * partial)
+
+
+def lon_range(w, cp):
+    """Centre longitudes of the patch columns (same source lines)."""
+    _check_plain(cp)
     y_st = cp["p_y_st"] * np.pi * 2
     y_ed = cp["p_y_ed"] * np.pi * 2
     if y_ed != 2 * np.pi:
         y_ed = y_ed % (np.pi * 2)
-    lat = np.linspace(x_st, x_ed, h) - (np.pi / 2 * partial)
     if cp["circular_flag"]:
         y_ed = y_ed + 2 * np.pi
-    lon = np.linspace(y_st, y_ed, w) - np.pi
-    return lat, lon
+    return np.linspace(y_st, y_ed, w) - np.pi
 
 
-def sampling_pattern(h, w, cp):
-    """float64 (lat, lon) tap positions in grid units: lat (h, 3, 3) shared by every column, lon (h, w, 3, 3).
-    createSamplingPattern of GridGeneratorPatchCoordsFixBorder (grid_generator.py:137-283), stride 1, 3x3."""
+def angular_ranges(h, w, cp):
+    return lat_range(h, cp), lon_range(w, cp)
+
+
+def row_factor(h, cp):
+    """The part of the sampling pattern that depends only on the ROWS of the window (p_x_st, p_x_ed, x_total, y_total,
+    partial): lat_g (h, 3, 3) float64 latitude tap positions in grid units (shared by every column) and lon (h, 3, 3)
+    float64 tangent-plane longitude offsets.  createSamplingPattern of GridGeneratorPatchCoordsFixBorder
+    (grid_generator.py:137-283), stride 1, 3x3."""
     x_total, y_total = cp["x_total"], cp["y_total"]
     # createKernel (grid_generator.py:303-323)
     d_lat = np.pi / x_total
@@ -53,15 +67,27 @@ def sampling_pattern(h, w, cp):
     rho[1][1] = 1e-8
     nu = np.arctan(rho)
     cos_nu, sin_nu = np.cos(nu), np.sin(nu)
-    lat_c, lon_c = angular_ranges(h, w, cp)
+    lat_c = lat_range(h, cp)
     t = lat_c[:, None, None]  # rows broadcast against the 3x3 kernel: same elementwise sequence as the row loop (:249-262)
     lat = np.arcsin(cos_nu * np.sin(t) + ker_y * sin_nu * np.cos(t) / rho)
     lon = np.arctan(ker_x * sin_nu / (rho * np.cos(t) * cos_nu - ker_y * np.sin(t) * sin_nu))
     lat_off = lat - lat[:, 1:2, 1:2]                            # get_pattern (:325-335)
     lat_rows = _norm(lat_c)[:, None, None] + lat_off            # add_pattern_to_lat (:337-346)
-    lon_cols = lon[:, None, :, :] + _norm(lon_c)[None, :, None, None]  # (h, w, 3, 3)
     lat_g = (lat_rows / 2 + 0.5) * x_total
-    lon_g = (lon_cols / 2 + 0.5) * y_total
+    return lat_g, lon
+
+
+def col_factor(w, cp):
+    """The part that depends only on the COLUMNS of the window (p_y_st, p_y_ed, circular_flag): the min-max normalised
+    column base (w,) float64."""
+    return _norm(lon_range(w, cp))
+
+
+def sampling_pattern(h, w, cp):
+    """float64 (lat, lon) tap positions in grid units: lat (h, 3, 3) shared by every column, lon (h, w, 3, 3)."""
+    lat_g, lon = row_factor(h, cp)
+    lon_cols = lon[:, None, :, :] + col_factor(w, cp)[None, :, None, None]  # (h, w, 3, 3)
+    lon_g = (lon_cols / 2 + 0.5) * cp["y_total"]
     return lat_g, lon_g
 
 
@@ -120,12 +146,50 @@ def full_sphere_pattern(height, width, kernel_size=(3, 3), stride=(1, 1)):
     return out.reshape(1, H * kh, W * kw, 2)
 
 
+_KEYS_ROW = ("p_x_st", "p_x_ed", "x_total", "y_total", "test_flag", "partial")
+_KEYS_COL = ("p_y_st", "p_y_ed", "circular_flag")
+
+
+class _FactorTable:
+    """Growable device table of per-window factors: slot -> row of a (capacity, *shape) tensor."""
+
+    def __init__(self, shape, dtype, device):
+        self.shape, self.dtype, self.device = tuple(shape), dtype, device
+        self.slots = {}
+        self.data = torch.zeros((16,) + self.shape, dtype=dtype, device=device)
+
+    def slot(self, key, build):
+        s = self.slots.get(key)
+        if s is not None:
+            return s
+        s = len(self.slots)
+        if s >= self.data.shape[0]:
+            grown = torch.zeros((2 * self.data.shape[0],) + self.shape, dtype=self.dtype, device=self.device)
+            grown[:self.data.shape[0]] = self.data
+            self.data = grown
+        host = torch.from_numpy(np.ascontiguousarray(build())).to(self.dtype)
+        if self.device.type == "cuda":
+            host = host.pin_memory()  # pinned + non_blocking: the upload does not stall the host behind queued kernels
+        self.data[s].copy_(host.view(self.shape), non_blocking=True)
+        self.slots[key] = s
+        return s
+
+
 class GridCache:
-    """Device-resident sampling grids keyed by (size, coords_partial); an LRU bounded in entries."""
+    """Device-resident sampling grids.
+
+    Test mode (one coords_partial dict shared by the batch): whole (1, 3h, 3w, 2) grids keyed by (size, coords_partial),
+    an LRU bounded in entries.  Training (a list of per-sample dicts): the grid separates into a row factor and a column
+    factor (`row_factor`, `col_factor`); each distinct factor is computed once on the host, kept in a device table, and
+    `spgan_sphere_grid_assemble` builds the (B, 3h, 3w, 2) batch grid from per-sample slot indices — the values are the
+    host-built ones bit for bit, but a training step no longer pays ~0.3 ms of numpy and a blocking upload per sample
+    and layer (the reference's models/spgan_ops_gs.py:767-781)."""
 
     def __init__(self, max_entries=8192):
         self.max_entries = max_entries
         self._store = OrderedDict()
+        self._rows = {}
+        self._cols = {}
         self.hits = 0
         self.misses = 0
 
@@ -147,16 +211,70 @@ class GridCache:
             self._store.popitem(last=False)
         return g
 
+    def assemble(self, h, w, cps, device):
+        """(B, 3h, 3w, 2) grid of a list of per-sample coords_partial dicts, built on the device from factor tables."""
+        from . import lib
+        import ctypes
+        device = torch.device(device)
+        y_total = cps[0]["y_total"]
+        if any(cp["y_total"] != y_total for cp in cps):
+            return torch.cat([self.get(h, w, cp, device) for cp in cps], 0)
+        rows = self._rows.get((h, str(device)))
+        if rows is None:
+            rows = self._rows[(h, str(device))] = (_FactorTable((h, 9), torch.float32, device),
+                                                   _FactorTable((h, 9), torch.float64, device), {})
+        cols = self._cols.get((w, str(device)))
+        if cols is None:
+            cols = self._cols[(w, str(device))] = _FactorTable((w,), torch.float64, device)
+        lat_tab, lon_tab, memo = rows
+        ix, iy = [], []
+        for cp in cps:
+            kr = tuple(cp.get(k, None) for k in _KEYS_ROW)
+            if kr not in lat_tab.slots:
+                lat_g, lon = row_factor(h, cp)
+                memo[kr] = (((lat_g / cp["x_total"]) * 2 - 1).astype(np.float32).reshape(h, 9), lon.reshape(h, 9))
+            s = lat_tab.slot(kr, lambda: memo[kr][0])
+            s2 = lon_tab.slot(kr, lambda: memo[kr][1])
+            assert s == s2
+            memo.pop(kr, None)
+            ix.append(s)
+            kc = tuple(cp.get(k, None) for k in _KEYS_COL)
+            iy.append(cols.slot(kc, lambda: col_factor(w, cp)))
+        B = len(cps)
+        idx = torch.tensor([ix, iy], dtype=torch.int32)
+        if device.type == "cuda":
+            idx = idx.pin_memory()
+        idx = idx.to(device, non_blocking=True)
+        out = torch.empty((B, 3 * h, 3 * w, 2), device=device, dtype=torch.float32)
+        vp = lambda t: ctypes.c_void_p(t.data_ptr())
+        with torch.cuda.device(device):
+            lib.call("spgan_sphere_grid_assemble", vp(out), vp(lat_tab.data), vp(lon_tab.data), vp(cols.data), vp(idx[0]),
+                     vp(idx[1]), B, h, w, float(y_total), ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream))
+        return out
+
     def batch(self, h, w, coords_partial, batch, device):
         """Training: a list of per-sample dicts -> (B, 3h, 3w, 2); test: one dict -> (1, 3h, 3w, 2) shared by the
         batch (models/spgan_ops_gs.py:760-789)."""
         if isinstance(coords_partial, (list, tuple)):
             if len(coords_partial) != batch:
                 raise RuntimeError("coords_partial has %d entries for a batch of %d" % (len(coords_partial), batch))
-            if batch == 1:
-                return self.get(h, w, coords_partial[0], device)
-            return torch.cat([self.get(h, w, cp, device) for cp in coords_partial], 0)
+            if torch.device(device).type != "cuda":
+                return torch.cat([self.get(h, w, cp, device) for cp in coords_partial], 0)
+            return self.assemble(h, w, list(coords_partial), device)
         return self.get(h, w, coords_partial, device)
+
+
+def assemble_reference(h, w, cp):
+    """numpy statement of what spgan_sphere_grid_assemble computes from the factors (tests: equals sampling_grid)."""
+    lat_g, lon = row_factor(h, cp)
+    lat_n = ((lat_g / cp["x_total"]) * 2 - 1).astype(np.float32)
+    y_total = float(cp["y_total"])
+    a = lon[:, None, :, :] + col_factor(w, cp)[None, :, None, None]
+    n = ((((a / 2.0) + 0.5) * y_total) / y_total) * 2.0 - 1.0
+    out = np.empty((h, 3, w, 3, 2), dtype=np.float32)
+    out[..., 0] = n.astype(np.float32).transpose(0, 2, 1, 3)
+    out[..., 1] = lat_n[:, :, None, :]
+    return out.reshape(1, 3 * h, 3 * w, 2)
 
 
 GRID_CACHE = GridCache()

@@ -90,7 +90,10 @@ class SyntheticSampler:
                 "y_total": self.GRID_Y, "y_st": int(y), "y_ed": int(y + S), "partial": 0.6667} for x, y in zip(x_st, y_st)]
         ac = np.stack([(x_st / 9.0) * 2 - 1, np.cos(((y_st / (self.GRID_Y - 1)) * 2 - 1) * np.pi),
                        np.sin(((y_st / (self.GRID_Y - 1)) * 2 - 1) * np.pi)], 1)
-        return coords, cps, torch.from_numpy(ac).float().to(self.device)
+        ac = torch.from_numpy(ac).float()
+        if torch.device(self.device).type == "cuda":
+            ac = ac.pin_memory()  # non-blocking upload: a pageable copy would stall the host behind the queued kernels
+        return coords, cps, ac.to(self.device, non_blocking=True)
 
     def noises(self, batch=None):
         b = batch or self.batch

@@ -128,6 +128,21 @@ def test_gather_indices_bit_exact(dev):
         assert np.array_equal(K.t2n(wx), owx) and np.array_equal(K.t2n(wy), owy), name
 
 
+def test_grid_assembly_on_device_bit_exact(dev):
+    """Per-sample training grids assembled on the device from the factor tables equal the host-built grids bit for
+    bit, across table growth (more than 16 distinct windows) and repeated windows."""
+    from spgan_b200 import grids
+    rng = np.random.RandomState(5)
+    cache = grids.GridCache()
+    for h in (35, 17, 53):
+        for B in (1, 8, 40):
+            cps = [K.train_cp(int(rng.randint(0, 10)), int(rng.randint(0, 140)), 35) for _ in range(B)]
+            got = cache.batch(h, h, cps, B, dev)
+            want = np.concatenate([grids.sampling_grid(h, h, cp) for cp in cps], 0)
+            assert got.shape == want.shape
+            assert np.array_equal(K.t2n(got).view(np.uint32), want.view(np.uint32)), (h, B)
+
+
 def test_gather_golden_forward_and_surrogate_backward(dev):
     g = K.load("gather.npz")
     for name, (B, C, h) in (("train", (2, 5, 17)), ("border", (1, 3, 11))):

@@ -113,3 +113,19 @@ def test_module_surface_matches_reference_names():
                                     "SphereConvBatchDiffFixBorderGNoGrad"])):
         for n in names:
             assert hasattr(mod, n), (mod.__name__, n)
+
+
+def test_grid_factorisation_equals_dense_grid_bitwise():
+    """The row-factor / column-factor decomposition used by the device-side grid assembly reproduces the dense grid
+    (and therefore the golden grids of the reference) bit for bit, for training and test-mode windows."""
+    import numpy as np
+    import cases as K
+    from spgan_b200 import grids
+    rng = np.random.RandomState(3)
+    cps = [K.train_cp(int(rng.randint(0, 10)), int(rng.randint(0, 140)), 35) for _ in range(12)]
+    cps += [K.test_cp(2, 7, 27), K.test_cp(0, 9, 3), K.train_cp(9, 139, 35), K.train_cp(0, 0, 35)]
+    for cp in cps:
+        for h in (35, 29, 23, 17, 53):
+            want = grids.sampling_grid(h, h, cp)
+            got = grids.assemble_reference(h, h, cp)
+            assert np.array_equal(want.view(np.uint32), got.view(np.uint32)), (h, cp)
