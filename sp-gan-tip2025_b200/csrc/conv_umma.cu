@@ -323,12 +323,14 @@ __global__ void __launch_bounds__(256) pack_act_kernel(__nv_bfloat16* __restrict
     const bool inside = sy >= 0 && sy < H && sx >= 0 && sx < W;
     // all 16 loads of a thread are in flight before the first shared-memory store (bytes in flight cover the latency)
     float v[16], m[16];
+    const int64_t cstep = (int64_t)H * W;
+    const float* xp = x + ((int64_t)b * C + c0 + ty) * cstep + (int64_t)sy * W + sx;  // one pointer, bumped per channel
+    const float* mp = in_mul ? in_mul + (int64_t)b * C + c0 + ty : nullptr;
 #pragma unroll
     for (int u = 0; u < 16; ++u) {
-      const int c = c0 + ty + 4 * u;
-      const bool ok = inside && c < C;
-      v[u] = ok ? __ldcs(x + (((int64_t)b * C + c) * H + sy) * W + sx) : 0.f;
-      m[u] = (ok && in_mul) ? __ldg(in_mul + (int64_t)b * C + c) : 1.f;
+      const bool ok = inside && c0 + ty + 4 * u < C;
+      v[u] = ok ? __ldcs(xp + 4 * u * cstep) : 0.f;
+      m[u] = (ok && mp) ? __ldg(mp + 4 * u) : 1.f;
     }
 #pragma unroll
     for (int u = 0; u < 16; ++u) tile[ty + 4 * u][tx] = v[u] * m[u];

@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(256) upfirdn2d_tiled(float* __restrict__ out, 
 // column parities sit 16 banks apart, so the reads are conflict-free).  ~30 instructions per output instead of ~65 for
 // a one-output-per-thread interleaving kernel, which was issue-bound at 27 % of the HBM roofline.
 constexpr int UB_THREADS = 256;
-constexpr int UB_LD = 3;  // staged loads per thread and plane on the fast path
+constexpr int UB_LD = 4;  // staged loads per thread and plane on the fast path ((A + 2) * Wq <= 768)
 
 __global__ void __launch_bounds__(UB_THREADS) upblur_act_kernel(float* __restrict__ out, const float* __restrict__ pp,
                                                                const float* __restrict__ kernel,
@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(UB_THREADS) upblur_act_kernel(float* __restric
   const int64_t plane = blockIdx.x / bands;
   const int band = blockIdx.x - (int)(plane * bands);
   const int a0 = band * A;                       // first output-row pair of the band
-  const int rows = min(A + 1, Hq - a0);          // plane rows to stage
+  const int rows = min(A + 2, Hq - a0);          // plane rows to stage (A pairs + halo; + 1 when A is odd: quads)
   const int n = rows * Wq;
   const int64_t Q = (int64_t)Hq * Wq;
   const float* src = pp + plane * 4 * Q + (int64_t)a0 * Wq;
@@ -190,39 +190,49 @@ __global__ void __launch_bounds__(UB_THREADS) upblur_act_kernel(float* __restric
   const int64_t opl = (int64_t)oh * ow;
   const float* np = noise ? noise + b * opl : nullptr;
   float* op = out + plane * opl;
+  // Each thread produces a vertical QUAD of outputs (rows 4q .. 4q+3 of the band at one column): 18 shared-memory reads
+  // and 36 FMAs per 4 outputs.  Column parity selects the plane pair once per quad; every other address term is a
+  // warp-uniform constant, so a read is one LDS with an immediate-style offset.
   const int pair_rows = min(A, (oh + 1) / 2 - a0);
-  const int npairs = pair_rows * ow;
-#pragma unroll 2
-  for (int j = threadIdx.x; j < npairs; j += UB_THREADS) {
-    const uint32_t a = fdiv((uint32_t)j, dow);
-    const int ox = j - (int)a * ow;
-    const int oy0 = 2 * (a0 + (int)a);
-    const bool two = oy0 + 1 < oh;
-    const int64_t o0 = (int64_t)oy0 * ow + ox;
-    const float nz0 = np ? nw * __ldg(np + o0) : 0.f;
-    const float nz1 = (np && two) ? nw * __ldg(np + o0 + ow) : 0.f;
-    // z[oy0 + dy][ox + dx] = stage[((dy & 1) * 2 + ((ox + dx) & 1)) * pstride + (a + (dy >> 1)) * Wq + ((ox + dx) >> 1)]
-    float r[4][3];
+  const int quad_rows = (pair_rows + 1) >> 1;
+  const int nquads = quad_rows * ow;
+  const int r1o = Wq, r2o = 2 * Wq;          // plane-row offsets
+  const int odd_row = 2 * pstride;           // planes 2, 3 hold the odd interleaved rows
+  for (int j = threadIdx.x; j < nquads; j += UB_THREADS) {
+    const uint32_t qd = fdiv((uint32_t)j, dow);
+    const int ox = j - (int)qd * ow;
+    const int a = 2 * (int)qd;               // first row pair of the quad inside the band
+    const int oy0 = 2 * (a0 + a);
+    const int p0 = ox & 1;
+    // column taps: dx = 0 -> (parity p0, col ox>>1), dx = 1 -> (parity 1-p0, col (ox+1)>>1), dx = 2 -> (p0, (ox>>1)+1)
+    const float* e0 = stage + p0 * pstride + a * Wq + (ox >> 1);
+    const float* e1 = stage + (1 - p0) * pstride + a * Wq + ((ox + 1) >> 1);
+    // interleaved rows oy0 + dy, dy = 0..5: plane row a + (dy >> 1), odd rows in planes 2, 3
+    float r[6][3];
 #pragma unroll
-    for (int dy = 0; dy < 4; ++dy)
-#pragma unroll
-      for (int dx = 0; dx < 3; ++dx) {
-        const int X = ox + dx;
-        r[dy][dx] = stage[((dy & 1) * 2 + (X & 1)) * pstride + ((int)a + (dy >> 1)) * Wq + (X >> 1)];
-      }
-    float acc0 = 0.f, acc1 = 0.f;
+    for (int dy = 0; dy < 6; ++dy) {
+      const int off = (dy & 1) * odd_row + (dy >> 1 == 0 ? 0 : (dy >> 1 == 1 ? r1o : r2o));
+      r[dy][0] = e0[off];
+      r[dy][1] = e1[off];
+      r[dy][2] = e0[off + 1];
+    }
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
-        acc0 += w[ky * 3 + kx] * r[ky][kx];
-        acc1 += w[ky * 3 + kx] * r[ky + 1][kx];
+        const float wv = w[ky * 3 + kx];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i] += wv * r[ky + i][kx];
       }
-    const float r0 = acc0 + bv + nz0;
-    __stcs(op + o0, (r0 > 0.f ? r0 : r0 * alpha) * scale);
-    if (two) {
-      const float r1 = acc1 + bv + nz1;
-      __stcs(op + o0 + ow, (r1 > 0.f ? r1 : r1 * alpha) * scale);
+    const int64_t o0 = (int64_t)oy0 * ow + ox;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (oy0 + i < oh) {
+        const int64_t o = o0 + (int64_t)i * ow;
+        const float v = acc[i] + bv + (np ? nw * __ldg(np + o) : 0.f);
+        __stcs(op + o, (v > 0.f ? v : v * alpha) * scale);
+      }
     }
   }
 }
@@ -240,14 +250,27 @@ extern "C" int spgan_upblur_act(float* out, const float* pp, const float* kernel
   SPGAN_CHECK_ARG((noise == nullptr) == (noise_w == nullptr), "spgan_upblur_act: noise and noise_w go together");
   SPGAN_CHECK_ARG((int64_t)zh * zw < (1LL << 30), "spgan_upblur_act: image %dx%d too large", zh, zw);
   const int pair_rows = (oh + 1) / 2;
-  int A = 1024 / ow;  // ~1024 vertical output pairs per CTA
-  if (A < 1) A = 1;
-  if (A > pair_rows) A = pair_rows;
-  while (A > 1 && (A + 1) * Wq + 50 > 3072) --A;  // keep the 4 staged planes inside 48 KB
-  int bands = (pair_rows + A - 1) / A;
-  A = (pair_rows + bands - 1) / bands;
-  bands = (pair_rows + A - 1) / A;
-  const int pstride = ((A + 1) * Wq + 2 + 31) / 32 * 32 + 16;  // planes 16 banks apart: column parities never collide
+  // band height A (output-row pairs per CTA): the even A that keeps the 256 threads busiest (quads per CTA just below
+  // a multiple of 256, little waste in the last band) among those whose staging fits the fast path and 48 KB
+  int A = 2;
+  double best = -1.0;
+  for (int cand = 2; cand <= 64; cand += 2) {
+    if ((cand + 2) * Wq > UB_LD * UB_THREADS && cand > 2) break;
+    if ((cand + 2) * Wq + 50 > 3072) break;
+    const int quads = (cand / 2) * ow;
+    const double util = (double)quads / (double)(((quads + UB_THREADS - 1) / UB_THREADS) * UB_THREADS);
+    const int nb = (pair_rows + cand - 1) / cand;
+    const double tail = (double)pair_rows / (double)(nb * cand);
+    const double halo = (double)cand / (double)(cand + 2);  // staged rows that are not halo
+    const double score = util * tail * (0.5 + 0.5 * halo);
+    if (score > best) {
+      best = score;
+      A = cand;
+    }
+  }
+  SPGAN_CHECK_ARG((A + 2) * Wq + 50 <= 3072, "spgan_upblur_act: rows of %d pixels exceed the staging buffer", zw);
+  const int bands = (pair_rows + A - 1) / A;
+  const int pstride = ((A + 2) * Wq + 2 + 31) / 32 * 32 + 16;  // planes 16 banks apart: column parities never collide
   const size_t smem = (size_t)4 * pstride * sizeof(float);
   SPGAN_CHECK_ARG(smem <= 48 * 1024, "spgan_upblur_act: rows of %d pixels exceed the staging buffer", zw);
   const int64_t blocks = batch * channels * bands;
