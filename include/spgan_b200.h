@@ -100,6 +100,10 @@ int spgan_sphere_grid_assemble(float* out, const float* lat_n, const double* lon
 int spgan_linear(float* y, const float* x, const float* w, const float* bias, int M, int N, int K, float w_scale,
                  float b_scale, int act, float alpha, float gain, void* stream);
 
+/* Weight gradient of the same layer (autograd of F.linear, models/ops.py:213-218): dw (N, K) = scale * g^T x with
+ * g (M, N) the output gradient and x (M, K) the input, M = batch. */
+int spgan_linear_wgrad(float* dw, const float* g, const float* x, int M, int N, int K, float scale, void* stream);
+
 /* ---- L2-L6: convolution passes ---------------------------------------------------------------------------
  * One "pass" computes, for every sample b, output channel o and lattice point (i, j), 0<=i<My, 0<=j<Mx:
  *   acc = sum_c sum_t  w[o*ws_o + c*ws_c + tap_w[t]] * in_mul[b,c] * x[b, c, i*in_stride + tap_dy[t], j*in_stride + tap_dx[t]]

@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(256) conv_small_cout(SpganConvPass p, float* _
 __global__ void __launch_bounds__(256) conv_wgrad_fp32(SpganConvPass p, float* __restrict__ dw,
                                                       const float* __restrict__ g, const float* __restrict__ x,
                                                       const float* __restrict__ in_mul,
-                                                      const float* __restrict__ out_mul) {
+                                                      const float* __restrict__ out_mul, int nsplit) {
   __shared__ float Gs[BK][BM + 1];  // [pixel][out channel]
   __shared__ float Xs[BK][BN + 1];  // [pixel][(c, tap)]
   __shared__ TapTable taps;
@@ -226,9 +226,14 @@ __global__ void __launch_bounds__(256) conv_wgrad_fp32(SpganConvPass p, float* _
     taps.dx[t] = p.tap_dx[t];
     taps.w[t] = p.tap_w[t];
   }
-  const int b = blockIdx.z;
+  // blockIdx.z = sample * nsplit + pixel chunk: the few-channel layers (ToRGB 512 -> 3, the discriminator's 3 -> 256 stem)
+  // have only a handful of (out, in) tiles, so the pixel range is split to fill the SMs (partial sums meet in atomicAdd)
+  const int b = blockIdx.z / nsplit;
+  const int split = blockIdx.z - b * nsplit;
   const int o0 = blockIdx.x * BM, q0 = blockIdx.y * BN;
   const int Mtot = p.My * p.Mx;
+  const int Mchunk = ((Mtot + nsplit - 1) / nsplit + BK - 1) / BK * BK;
+  const int Mbeg = split * Mchunk, Mend = min(Mtot, Mbeg + Mchunk);
   const int Qtot = p.Cin * p.ntaps;
   const int lp = tid & 15, lc = tid >> 4;  // loader: pixel lp (contiguous), column lc + 16u
   const int tx = tid & 15, ty = tid >> 4;  // compute: out channels tx + 16u, columns ty*4 + v
@@ -259,9 +264,9 @@ __global__ void __launch_bounds__(256) conv_wgrad_fp32(SpganConvPass p, float* _
 #pragma unroll
     for (int v = 0; v < 4; ++v) acc[u][v] = 0.f;
 
-  for (int m0 = 0; m0 < Mtot; m0 += BK) {
+  for (int m0 = Mbeg; m0 < Mend; m0 += BK) {
     const int m = m0 + lp;
-    const bool m_ok = m < Mtot;
+    const bool m_ok = m < Mend;
     const int i = m_ok ? m / p.Mx : 0, j = m_ok ? m - i * p.Mx : 0;
     const int Y = i * p.out_stride + p.out_off_y, X = j * p.out_stride + p.out_off_x;
     const bool out_ok = m_ok && Y >= 0 && Y < p.out_H && X >= 0 && X < p.out_W;
@@ -405,9 +410,15 @@ extern "C" int spgan_conv_wgrad(const SpganConvPass* p, float* dw, const float* 
   if (int e = check_pass(p, "spgan_conv_wgrad")) return e;
   SPGAN_CHECK_ARG(dw && g && x, "spgan_conv_wgrad: null pointer");
   if (p->B == 0 || p->Cout == 0 || p->Cin == 0 || p->My == 0 || p->Mx == 0) return 0;
-  dim3 grid((p->Cout + BM - 1) / BM, (p->Cin * p->ntaps + BN - 1) / BN, p->B);
+  const int gx = (p->Cout + BM - 1) / BM, gy = (p->Cin * p->ntaps + BN - 1) / BN;
+  int nsplit = (2 * SPGAN_NUM_SMS + gx * gy * p->B - 1) / (gx * gy * p->B);
+  const int max_split = (p->My * p->Mx + 8 * BK - 1) / (8 * BK);
+  if (nsplit > max_split) nsplit = max_split;
+  if (nsplit < 1) nsplit = 1;
+  SPGAN_CHECK_ARG((int64_t)p->B * nsplit <= 65535, "spgan_conv_wgrad: batch %d too large", p->B);
+  dim3 grid(gx, gy, p->B * nsplit);
   (void)accumulate;  // the caller zeroes dw when it does not accumulate (the tensor extent is only known to the host)
-  conv_wgrad_fp32<<<grid, 256, 0, (cudaStream_t)stream>>>(*p, dw, g, x, in_mul, out_mul);
+  conv_wgrad_fp32<<<grid, 256, 0, (cudaStream_t)stream>>>(*p, dw, g, x, in_mul, out_mul, nsplit);
   SPGAN_CHECK_LAUNCH("spgan_conv_wgrad");
   return 0;
 }

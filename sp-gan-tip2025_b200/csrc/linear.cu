@@ -57,7 +57,42 @@ __global__ void __launch_bounds__(128) linear_kernel(float* __restrict__ y, cons
   }
 }
 
+// Weight gradient of the linear layer: dw[n][k] = scale * sum_m g[m][n] * x[m][k] with M = batch (<= 64): an outer-product
+// accumulation, HBM-bound on writing dw (the general kernel above would run a K = batch contraction with 8 of 32 lanes).
+__global__ void __launch_bounds__(256) linear_wgrad_kernel(float* __restrict__ dw, const float* __restrict__ g,
+                                                          const float* __restrict__ x, int M, int N, int K, float scale) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n0 = blockIdx.y * 8;
+  if (k >= K) return;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int m = 0; m < M; ++m) {
+    const float xv = __ldg(x + (int64_t)m * K + k);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int n = n0 + i;
+      acc[i] += (n < N ? __ldg(g + (int64_t)m * N + n) : 0.f) * xv;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (n0 + i < N) dw[(int64_t)(n0 + i) * K + k] = acc[i] * scale;
+}
+
 }  // namespace
+
+extern "C" int spgan_linear_wgrad(float* dw, const float* g, const float* x, int M, int N, int K, float scale,
+                                  void* stream) {
+  SPGAN_CHECK_ARG(M >= 0 && N >= 0 && K >= 0, "spgan_linear_wgrad: negative size");
+  if (N == 0 || K == 0) return 0;
+  SPGAN_CHECK_ARG(dw && (M == 0 || (g && x)), "spgan_linear_wgrad: null pointer");
+  SPGAN_CHECK_ARG((N + 7) / 8 <= 65535, "spgan_linear_wgrad: N=%d too large", N);
+  dim3 grid((K + 255) / 256, (N + 7) / 8);
+  linear_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dw, g, x, M, N, K, scale);
+  SPGAN_CHECK_LAUNCH("spgan_linear_wgrad");
+  return 0;
+}
 
 extern "C" int spgan_linear(float* y, const float* x, const float* w, const float* bias, int M, int N, int K,
                             float w_scale, float b_scale, int act, float alpha, float gain, void* stream) {

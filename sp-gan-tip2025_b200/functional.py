@@ -324,10 +324,37 @@ class _LinearFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             gx = _LinearFn.apply(g, w.t(), None, ctx.w_scale, 1.0)
         if ctx.needs_input_grad[1]:
-            gw = _LinearFn.apply(g.t(), x.t(), None, ctx.w_scale, 1.0)
+            gw = _LinearWgradFn.apply(g, x, ctx.w_scale)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = g.sum(0) * ctx.b_scale
         return gx, gw, gb, None, None
+
+
+class _LinearWgradFn(torch.autograd.Function):
+    """dw = scale * g^T x (bilinear in g and x, so its own backward is two more linear maps: second-order through the
+    discriminator's and the mapping network's linear layers, models/losses.py:36-41, 60-78)."""
+
+    @staticmethod
+    def forward(ctx, g, x, scale):
+        gc, xc = _f32c(g, "equal_linear wgrad"), _f32c(x, "equal_linear wgrad")
+        ctx.save_for_backward(gc, xc)
+        ctx.scale = scale
+        M, N = gc.shape
+        K = xc.shape[1]
+        dw = torch.empty((N, K), device=gc.device, dtype=torch.float32)
+        with torch.cuda.device(gc.device):
+            lib.call("spgan_linear_wgrad", _ptr(dw), _ptr(gc), _ptr(xc), M, N, K, float(scale), _stream(gc))
+        return dw
+
+    @staticmethod
+    def backward(ctx, ggw):
+        g, x = ctx.saved_tensors
+        gg = gx = None
+        if ctx.needs_input_grad[0]:  # d/dg: scale * x ggw^T  -> (M, N)
+            gg = _LinearFn.apply(x, ggw, None, ctx.scale, 1.0)
+        if ctx.needs_input_grad[1]:  # d/dx: scale * g ggw    -> (M, K)
+            gx = _LinearFn.apply(g, ggw.t(), None, ctx.scale, 1.0)
+        return gg, gx, None
 
 
 def _linear_raw(x, w, bias, w_scale, b_scale, act, alpha, gain):

@@ -51,6 +51,7 @@ SIGNATURES = {
     "spgan_sphere_gather_bwd": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_vp]),
     "spgan_sphere_grid_assemble": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, ctypes.c_double, c_vp]),
     "spgan_linear": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_f32, c_f32, c_int, c_f32, c_f32, c_vp]),
+    "spgan_linear_wgrad": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_f32, c_vp]),
     "spgan_conv_pass": (c_int, [_PASS_P] + [c_vp] * 10),
     "spgan_demod": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_f32, c_f32, c_vp]),
     "spgan_conv_wgrad": (c_int, [_PASS_P, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp]),

@@ -507,3 +507,24 @@ def test_equal_linear_vs_oracle(dev):
     rx, rw, rb = torch.autograd.grad(O.equal_linear(xr, wr, br, lr_mul=0.01, activation=True), [xr, wr, br], go)
     assert K.rel_err(K.t2n(gx), K.t2n(rx)) < 1e-5 and K.rel_err(K.t2n(gw), K.t2n(rw)) < 1e-5
     assert K.rel_err(K.t2n(gb), K.t2n(rb)) < 1e-5
+
+
+def test_linear_second_order_vs_torch(dev):
+    """Gradient-of-gradient through EqualLinear (R1 through the discriminator heads, path length through the mapping
+    network): the dedicated weight-gradient kernel and its two adjoint maps against torch autograd of F.linear."""
+    x = synth.randn_t(21, "l2x", (6, 40)).to(dev).requires_grad_(True)
+    w = synth.randn_t(21, "l2w", (24, 40)).to(dev).requires_grad_(True)
+    b = synth.randn_t(21, "l2b", (24,)).to(dev).requires_grad_(True)
+    go = synth.randn_t(21, "l2g", (6, 24)).to(dev)
+    def second(fn):
+        y = fn(x, w, b)
+        gx, gw = torch.autograd.grad((y * go).sum() + (y ** 2).sum(), [x, w], create_graph=True)
+        loss = (gx ** 2).sum() + (gw ** 3).sum()
+        return [gx, gw] + list(torch.autograd.grad(loss, [x, w, b], allow_unused=True))
+    ours = second(lambda x, w, b: SF().equal_linear(x, w, b, 0.3, 1.0, False))
+    ref = second(lambda x, w, b: F.linear(x, w * 0.3, b))
+    for a, r in zip(ours, ref):
+        if r is None:
+            assert a is None or float(a.abs().max()) == 0.0
+        else:
+            assert K.rel_err(K.t2n(a), K.t2n(r)) < 2e-5
