@@ -493,6 +493,22 @@ def clear_weight_cache():
     _WEIGHT_CACHE.clear()
 
 
+_EPOCH = 0
+
+
+def epoch():
+    return _EPOCH
+
+
+def bump_epoch():
+    """Invalidate everything memoised on parameter versions (packed weights here, the (s, d) modulation pairs of
+    ModulatedConv2d).  A CUDA-graph replay updates parameters on the device without bumping their Python `_version`, so
+    the training step calls this after every replay and before every capture."""
+    global _EPOCH
+    _EPOCH += 1
+    _WEIGHT_CACHE.clear()
+
+
 # --------------------------------------------------------------------------------------------------- conv driver
 def _tensor_path_ok(passes, Cin, Cout, precision):
     return precision != 0 and Cin >= 16 and Cout >= 16 and len({p["in_stride"] for p in passes}) == 1
@@ -520,7 +536,7 @@ def _phase_taps(passes):
 
 
 def conv_apply(x, w, geom, adjoint=False, out_hw=None, in_mul=None, out_mul=None, out_scale=1.0, noise=None,
-               noise_w=None, bias=None, act=None, residual=None, precision=None, polyphase=False):
+               noise_w=None, bias=None, act=None, residual=None, precision=None, polyphase=False, k_round=64):
     """y = [act]( out_scale * out_mul[b,o] * L_w(in_mul[b,c] * x) + noise_w*noise + bias ) + residual, no autograd.
 
     L_w is the conv described by `geom` (adjoint=False) or its adjoint / data gradient (adjoint=True, `out_hw`
@@ -588,7 +604,7 @@ def conv_apply(x, w, geom, adjoint=False, out_hw=None, in_mul=None, out_mul=None
             # K per tap padded to whole 64-wide blocks.  The kernel accepts any multiple of 16 (partial last block), but
             # measured on the 259-channel 7x7 layers a 16-wide last block is slower than padding to 320: it saves 15 % of
             # the MMAs yet leaves a pipeline bubble per tap (its stage holds 3 MMAs, not enough to cover the next TMA load)
-            Cp = _round_up(Cin, 64)
+            Cp = _round_up(Cin, k_round)
             rows = B * Hl * Wl
             a_packed = torch.empty((2, step * step * rows, Cp), device=x.device, dtype=torch.bfloat16)
             lib.call("spgan_pack_act", _ptr(a_packed), _ptr(x), _ptr(im), B, Cin, H, W, Cp, pt, pl, Hl, Wl, step, st)

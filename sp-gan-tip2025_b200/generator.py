@@ -203,9 +203,15 @@ class TextureSynthesizer(nn.Module):
     def get_style(self, global_latent):
         return self.mapping(global_latent)
 
-    def styles_for(self, global_latent, inject_index=None):
+    def styles_for(self, global_latent, inject_index=None, inject_mask=None):
         """global_latent (B, 2, 512) -> (B, n_latent, 512) w-space styles with style mixing at `inject_index`
-        (models/spgan/spgan.py:843-876)."""
+        (models/spgan/spgan.py:843-876).  `inject_mask` (n_latent,) is the same choice as a device tensor (1 = first
+        latent, 0 = second): lets a captured CUDA graph mix at a different index on every replay."""
+        if inject_mask is not None:
+            w0 = self.mapping(global_latent[:, 0])
+            w1 = self.mapping(global_latent[:, 1])
+            m = inject_mask.view(1, self.n_latent, 1)
+            return w0.unsqueeze(1) * m + w1.unsqueeze(1) * (1 - m)
         w0 = self.mapping(global_latent[:, 0])
         if inject_index is None or inject_index >= self.n_latent:
             return w0.unsqueeze(1).repeat(1, self.n_latent, 1)
@@ -250,7 +256,7 @@ class Generator(nn.Module):
         if global_latent.dim() == 2:
             global_latent = torch.stack([global_latent, global_latent], 1)
         ts = self.texture_synthesizer
-        if inject_index is None and self.training and self.config.train_params.mixing > 0:
+        if styles is None and inject_index is None and self.training and self.config.train_params.mixing > 0:
             if random.random() < self.config.train_params.mixing:  # models/spgan/spgan.py:865-869
                 inject_index = random.randint(1, ts.n_latent - 1)
         structure, _ = self.structure_synthesizer(global_latent[:, 0], local_latent, coords, coords_partial,

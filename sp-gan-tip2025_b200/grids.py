@@ -175,6 +175,64 @@ class _FactorTable:
         return s
 
 
+class WindowTables:
+    """Factor tables of a FIXED family of training windows (every x start and every y start of the coordinate grid the
+    sampler draws from), resident on the device: row slot = x-window index, column slot = y-window index.  With these,
+    the grid of a batch is a pure device computation on two int32 index tensors (CUDA-graph capturable: no host work)."""
+
+    def __init__(self, row_cps, col_cps, device):
+        self.row_cps, self.col_cps, self.device = list(row_cps), list(col_cps), torch.device(device)
+        self.y_total = float(self.row_cps[0]["y_total"])
+        self._rows, self._cols = {}, {}
+
+    def _row_tables(self, h):
+        t = self._rows.get(h)
+        if t is None:
+            lat_n = np.empty((len(self.row_cps), h, 9), np.float32)
+            lon = np.empty((len(self.row_cps), h, 9), np.float64)
+            for i, cp in enumerate(self.row_cps):
+                lat_g, lo = row_factor(h, cp)
+                lat_n[i] = ((lat_g / cp["x_total"]) * 2 - 1).astype(np.float32).reshape(h, 9)
+                lon[i] = lo.reshape(h, 9)
+            t = self._rows[h] = (torch.from_numpy(lat_n).to(self.device), torch.from_numpy(lon).to(self.device))
+        return t
+
+    def _col_table(self, w):
+        t = self._cols.get(w)
+        if t is None:
+            t = self._cols[w] = torch.from_numpy(np.stack([col_factor(w, cp) for cp in self.col_cps])).to(self.device)
+        return t
+
+    def prepare(self, sizes):
+        for h in sizes:
+            self._row_tables(h)
+            self._col_table(h)
+
+    def assemble(self, h, w, ix, iy):
+        from . import lib
+        import ctypes
+        lat_n, lon = self._row_tables(h)
+        nlon = self._col_table(w)
+        B = ix.numel()
+        out = torch.empty((B, 3 * h, 3 * w, 2), device=self.device, dtype=torch.float32)
+        vp = lambda t: ctypes.c_void_p(t.data_ptr())
+        with torch.cuda.device(self.device):
+            lib.call("spgan_sphere_grid_assemble", vp(out), vp(lat_n), vp(lon), vp(nlon), vp(ix), vp(iy), B, h, w,
+                     self.y_total, ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+        return out
+
+
+class DeviceWindows(list):
+    """A training `coords_partial` (list of per-sample dicts, coord_handler.py:1027-1038) that also carries the windows'
+    slot indices as device tensors: modules see the reference's list; GridCache builds the grids from `ix`, `iy` without
+    touching the host.  The dicts describe the windows at construction time; after `ix` / `iy` are updated in place
+    (CUDA-graph replay) only the device indices are authoritative."""
+
+    def __init__(self, cps, tables, ix, iy):
+        super().__init__(cps)
+        self.tables, self.ix, self.iy = tables, ix, iy
+
+
 class GridCache:
     """Device-resident sampling grids.
 
@@ -258,6 +316,8 @@ class GridCache:
         if isinstance(coords_partial, (list, tuple)):
             if len(coords_partial) != batch:
                 raise RuntimeError("coords_partial has %d entries for a batch of %d" % (len(coords_partial), batch))
+            if isinstance(coords_partial, DeviceWindows):
+                return coords_partial.tables.assemble(h, w, coords_partial.ix, coords_partial.iy)
             if torch.device(device).type != "cuda":
                 return torch.cat([self.get(h, w, cp, device) for cp in coords_partial], 0)
             return self.assemble(h, w, list(coords_partial), device)

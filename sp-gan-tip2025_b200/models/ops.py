@@ -386,7 +386,7 @@ class ModulatedConv2d(nn.Module):
                 wsq = (w * w).sum(dim=(2, 3))
                 d = torch.rsqrt(SF._LinearFn.apply(s * s, wsq, None, self.scale * self.scale, 1.0) + 1e-8)
             return s, w, d
-        key = (style.data_ptr(), style._version, tuple(style.shape), tuple(style.stride()), str(style.device),
+        key = (SF.epoch(), style.data_ptr(), style._version, tuple(style.shape), tuple(style.stride()), str(style.device),
                self.weight._version, self.modulation.weight._version,
                self.modulation.bias._version if self.modulation.bias is not None else -1,
                self.weight.data_ptr(), self.modulation.weight.data_ptr())

@@ -63,46 +63,94 @@ def diversity_z_loss(local_latent, structure_latent, eps=1e-5):
 
 # ------------------------------------------------------------------------------------------------ synthetic inputs
 class SyntheticSampler:
-    """Latents, real patches and training coordinate windows (coord_handler.py:907-921, 1027-1038)."""
+    """Latents, real patches and training coordinate windows (coord_handler.py:907-921, 1027-1038).
+
+    Every sampled tensor lives in a STATIC device buffer that is refilled in place, and the coordinate windows are handed
+    to the model as `grids.DeviceWindows` (the reference's list of dicts + device slot indices into pre-built factor
+    tables).  Sampling therefore never blocks the host behind queued kernels, and the training step bodies can be
+    captured in CUDA graphs: a replay reads whatever the buffers hold."""
 
     GRID_X, GRID_Y, SIZE = 45, 140, 35
+    NOISE_SIZES = (19, 17, 31, 29, 55, 53, 103, 101)
 
     def __init__(self, batch, device, seed=9000):
-        self.batch, self.device = batch, device
+        from . import grids
+        self.batch, self.device = batch, torch.device(device)
         self.rng = np.random.RandomState(seed)
         self.gen = torch.Generator(device=device).manual_seed(seed)
-        self.coord_canvas = panorama.meta_coords(self.GRID_X + self.SIZE, self.GRID_Y + self.SIZE, device)
+        S = self.SIZE
+        self.coord_canvas = panorama.meta_coords(self.GRID_X + S, self.GRID_Y + S, device)
+        self._bufs = {}
+        self.tables = None
+        if self.device.type == "cuda":
+            rows = [self._cp(x, 0) for x in range(10)]
+            cols = [self._cp(0, y) for y in range(self.GRID_Y)]
+            self.tables = grids.WindowTables(rows, cols, device)
+            self.tables.prepare((35, 29, 23, 17, 53))
+        self._ar = torch.arange(S, device=device)
 
-    def latents(self, batch=None):
+    def _cp(self, x, y):
+        S = self.SIZE
+        return {"p_x_st": x / self.GRID_X, "p_x_ed": (x + S - 1) / self.GRID_X, "p_y_st": y / self.GRID_Y,
+                "p_y_ed": (y + S - 1) / self.GRID_Y, "circular_flag": bool(y + S > self.GRID_Y), "x_total": self.GRID_X,
+                "y_total": self.GRID_Y, "y_st": int(y), "y_ed": int(y + S), "partial": 0.6667}
+
+    def _buf(self, name, shape, dtype=torch.float32):
+        key = (name, tuple(shape))
+        t = self._bufs.get(key)
+        if t is None:
+            t = self._bufs[key] = torch.zeros(shape, device=self.device, dtype=dtype)
+        return t
+
+    def _upload(self, dst, host):
+        if self.device.type == "cuda":
+            host = host.pin_memory()  # non-blocking: a pageable copy would stall the host behind the queued kernels
+        dst.copy_(host, non_blocking=True)
+        return dst
+
+    def latents(self, batch=None, tag="a"):
         b = batch or self.batch
-        gl = torch.randn(b, 2, 512, device=self.device, generator=self.gen)
-        lat = torch.randn(b, 256, self.SIZE, self.SIZE, device=self.device, generator=self.gen)
+        gl = self._buf(tag + "_gl", (b, 2, 512)).normal_(generator=self.gen)
+        lat = self._buf(tag + "_lat", (b, 256, self.SIZE, self.SIZE)).normal_(generator=self.gen)
         return gl, lat
 
-    def coords(self, batch=None):
+    def coords(self, batch=None, tag="a"):
         b = batch or self.batch
+        S = self.SIZE
         x_st = self.rng.randint(0, 10, b)
         y_st = self.rng.randint(0, self.GRID_Y, b)
-        S = self.SIZE
-        coords = torch.stack([self.coord_canvas[:, x:x + S, y:y + S] for x, y in zip(x_st, y_st)]).contiguous()
-        cps = [{"p_x_st": x / self.GRID_X, "p_x_ed": (x + S - 1) / self.GRID_X, "p_y_st": y / self.GRID_Y,
-                "p_y_ed": (y + S - 1) / self.GRID_Y, "circular_flag": bool(y + S > self.GRID_Y), "x_total": self.GRID_X,
-                "y_total": self.GRID_Y, "y_st": int(y), "y_ed": int(y + S), "partial": 0.6667} for x, y in zip(x_st, y_st)]
+        idx = self._upload(self._buf(tag + "_idx", (2, b), torch.int32), torch.from_numpy(np.stack([x_st, y_st]).astype(np.int32)))
+        xs = idx[0].long()[:, None, None] + self._ar[None, :, None]
+        ys = idx[1].long()[:, None, None] + self._ar[None, None, :]
+        coords = self._buf(tag + "_coords", (b, 3, S, S))
+        coords.copy_(self.coord_canvas[:, xs, ys].permute(1, 0, 2, 3))
+        cps = [self._cp(int(x), int(y)) for x, y in zip(x_st, y_st)]
+        if self.tables is not None:
+            from . import grids
+            cps = grids.DeviceWindows(cps, self.tables, idx[0], idx[1])
         ac = np.stack([(x_st / 9.0) * 2 - 1, np.cos(((y_st / (self.GRID_Y - 1)) * 2 - 1) * np.pi),
                        np.sin(((y_st / (self.GRID_Y - 1)) * 2 - 1) * np.pi)], 1)
-        ac = torch.from_numpy(ac).float()
-        if torch.device(self.device).type == "cuda":
-            ac = ac.pin_memory()  # non-blocking upload: a pageable copy would stall the host behind the queued kernels
-        return coords, cps, ac.to(self.device, non_blocking=True)
+        ac = self._upload(self._buf(tag + "_ac", (b, 3)), torch.from_numpy(ac).float())
+        return coords, cps, ac
 
-    def noises(self, batch=None):
+    def noises(self, batch=None, tag="a"):
         b = batch or self.batch
-        return [torch.randn(b, 1, s, s, device=self.device, generator=self.gen) for s in (19, 17, 31, 29, 55, 53, 103, 101)]
+        return [self._buf(tag + "_nz%d" % i, (b, 1, s, s)).normal_(generator=self.gen) for i, s in enumerate(self.NOISE_SIZES)]
 
-    def real(self):
-        img = torch.randn(self.batch, 3, 101, 101, device=self.device, generator=self.gen).clamp_(-1, 1)
-        ac = torch.rand(self.batch, 3, device=self.device, generator=self.gen) * 2 - 1
+    def real(self, tag="a"):
+        img = self._buf(tag + "_real", (self.batch, 3, 101, 101)).normal_(generator=self.gen).clamp_(-1, 1)
+        ac = self._buf(tag + "_real_ac", (self.batch, 3)).uniform_(-1, 1, generator=self.gen)
         return img, ac
+
+    def inject_mask(self, n_latent, mixing, tag="a"):
+        """Style-mixing choice of spgan.py:865-869 as a device mask: 1 for the first latent, 0 for the second."""
+        import random
+        idx = n_latent
+        if mixing > 0 and random.random() < mixing:
+            idx = random.randint(1, n_latent - 1)
+        m = torch.zeros(n_latent)
+        m[:idx] = 1
+        return self._upload(self._buf(tag + "_mask", (n_latent,)), m)
 
 
 # ------------------------------------------------------------------------------------------------ gradient exchange
@@ -145,17 +193,25 @@ def requires_grad(model, flag):
 def accumulate(ema, model, decay=0.999):
     """utils.py:86-94."""
     pe, pm = dict(ema.named_parameters()), dict(model.named_parameters())
-    for k in pe:
-        pe[k].mul_(decay).add_(pm[k], alpha=1 - decay)
+    dst = [pe[k] for k in pe]
+    src = [pm[k].detach() for k in pe]
+    torch._foreach_mul_(dst, decay)  # two multi-tensor launches instead of 2 x 115 tiny ones
+    torch._foreach_add_(dst, src, alpha=1 - decay)
 
 
 # ------------------------------------------------------------------------------------------------ the step
 class TrainStep:
-    def __init__(self, batch, device, world=1, seed=9000, config=None, with_ema=True):
+    """One training iteration (train.py:200-415) over the B200 hot path.  Each part is split into `prepare_*` (sampling
+    into static buffers, host-side) and a body that touches only device state; with `use_graphs=True` every body is
+    captured in a CUDA graph after two eager runs and replayed afterwards — the B = 8 iteration is launch-bound
+    (~6500 kernel launches for ~90 ms of kernels), a replay removes the Python / launch overhead."""
+
+    def __init__(self, batch, device, world=1, seed=9000, config=None, with_ema=True, use_graphs=False):
         self.config = config if config is not None else default_config()
         tp = self.config.train_params
         tp.batch_size = batch
         self.batch, self.device, self.world = batch, device, world
+        self.use_graphs = use_graphs
         torch.manual_seed(seed)
         self.G = Generator(self.config).to(device).train()
         self.D = Discriminator(self.config).to(device).train()
@@ -165,83 +221,136 @@ class TrainStep:
             self.G_ema.load_state_dict(self.G.state_dict())
         g_ratio = tp.g_reg_every / (tp.g_reg_every + 1)
         d_ratio = tp.d_reg_every / (tp.d_reg_every + 1)
-        self.g_optim = torch.optim.Adam(self.G.parameters(), lr=tp.lr * g_ratio, betas=(0 ** g_ratio, 0.99 ** g_ratio))
-        self.d_optim = torch.optim.Adam(self.D.parameters(), lr=tp.lr * d_ratio, betas=(0 ** d_ratio, 0.99 ** d_ratio))
+        cap = bool(use_graphs)
+        self.g_optim = torch.optim.Adam(self.G.parameters(), lr=tp.lr * g_ratio, betas=(0 ** g_ratio, 0.99 ** g_ratio), capturable=cap)
+        self.d_optim = torch.optim.Adam(self.D.parameters(), lr=tp.lr * d_ratio, betas=(0 ** d_ratio, 0.99 ** d_ratio), capturable=cap)
         self.sampler = SyntheticSampler(batch, device, seed)
         self.mean_path_length = torch.zeros((), device=device)
         self.iter = 0
+        self._graphs, self._eager_runs, self._inputs = {}, {}, {}
 
-    def _fake(self, batch=None, need_latents=False):
-        gl, lat = self.sampler.latents(batch)
-        coords, cps, ac = self.sampler.coords(batch)
-        noises = self.sampler.noises(batch)
-        img, styles, structure = self.G(gl, lat, coords, cps, noises=noises, return_latents=True)
-        return img, ac, styles, structure, lat
+    # ---- sampling (host side, outside any graph) ----
+    def _prepare_fake(self, tag, batch=None):
+        ts = self.G.texture_synthesizer
+        gl, lat = self.sampler.latents(batch, tag)
+        coords, cps, ac = self.sampler.coords(batch, tag)
+        noises = self.sampler.noises(batch, tag)
+        mask = self.sampler.inject_mask(ts.n_latent, self.config.train_params.mixing, tag)
+        return dict(gl=gl, lat=lat, coords=coords, cps=cps, ac=ac, noises=noises, mask=mask)
 
+    def _real(self, tag, real):
+        img, ac = self.sampler.real(tag)
+        if real is not None:  # the caller's data loader: copied into the static buffers (H2D when it is host memory)
+            img.copy_(real[0], non_blocking=True)
+            ac.copy_(real[1], non_blocking=True)
+        return img, ac
+
+    def _fake(self, inp):
+        styles = self.G.texture_synthesizer.styles_for(inp["gl"], inject_mask=inp["mask"])
+        img, styles, structure = self.G(inp["gl"], inp["lat"], inp["coords"], inp["cps"], noises=inp["noises"],
+                                        return_latents=True, styles=styles)
+        return img, styles, structure
+
+    # ---- graph plumbing ----
+    def _run(self, name, body):
+        if not self.use_graphs:
+            return body()
+        hit = self._graphs.get(name)
+        if hit is None:
+            n = self._eager_runs.get(name, 0)
+            if n < 2:  # allocator, autotuned attributes and optimizer state settle in eager mode first
+                self._eager_runs[name] = n + 1
+                return body()
+            from . import functional as SF
+            SF.bump_epoch()  # every memoised pack / modulation must be recomputed INSIDE the capture
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = body()
+            hit = self._graphs[name] = (graph, out)
+        hit[0].replay()
+        from . import functional as SF
+        SF.bump_epoch()  # parameters changed on the device without a Python version bump
+        return hit[1]
+
+    # ---- the four parts ----
     def d_step(self, real=None):
         """`real` = (images (B,3,101,101), ac_coords (B,3)) from the caller's data loader, or None for synthetic."""
         requires_grad(self.G, False)
         requires_grad(self.D, True)
-        with torch.no_grad():
-            fake, fake_ac, _, _, _ = self._fake()
-        real, real_ac = real if real is not None else self.sampler.real()
-        fp, rp = self.D(fake), self.D(real)
-        loss = d_logistic_loss(rp["d_patch"], fp["d_patch"])
-        loss = loss + (coord_ac_loss(rp["ac_coords_pred"], real_ac) + coord_ac_loss(fp["ac_coords_pred"], fake_ac)) * \
-            self.config.train_params.coord_ac_w
-        self.D.zero_grad(set_to_none=True)
-        loss.backward()
-        allreduce_gradients(self.D.parameters(), self.world)
-        self.d_optim.step()
-        return loss.detach()
+        inp = self._prepare_fake("d")
+        real_img, real_ac = self._real("d", real)
+
+        def body():
+            with torch.no_grad():
+                fake, _, _ = self._fake(inp)
+            fp, rp = self.D(fake), self.D(real_img)
+            loss = d_logistic_loss(rp["d_patch"], fp["d_patch"])
+            loss = loss + (coord_ac_loss(rp["ac_coords_pred"], real_ac) + coord_ac_loss(fp["ac_coords_pred"], inp["ac"])) * \
+                self.config.train_params.coord_ac_w
+            self.D.zero_grad(set_to_none=True)
+            loss.backward()
+            allreduce_gradients(self.D.parameters(), self.world)
+            self.d_optim.step()
+            return loss.detach()
+        return self._run("d", body)
 
     def d_r1_step(self, real=None):
         tp = self.config.train_params
+        requires_grad(self.G, False)
         requires_grad(self.D, True)
-        real = real[0].detach().clone() if real is not None else self.sampler.real()[0]
-        real.requires_grad_(True)
-        rp = self.D(real)
-        r1 = d_r1_loss(rp["d_patch"], real)
-        self.D.zero_grad(set_to_none=True)
-        (tp.r1 / 2 * r1 * tp.d_reg_every + 0 * rp["d_patch"][0]).sum().backward()
-        allreduce_gradients(self.D.parameters(), self.world)
-        self.d_optim.step()
-        return r1.detach()
+        real_img, _ = self._real("r1", real)
+
+        def body():
+            x = real_img.detach().clone().requires_grad_(True)
+            rp = self.D(x)
+            r1 = d_r1_loss(rp["d_patch"], x)
+            self.D.zero_grad(set_to_none=True)
+            (tp.r1 / 2 * r1 * tp.d_reg_every + 0 * rp["d_patch"][0]).sum().backward()
+            allreduce_gradients(self.D.parameters(), self.world)
+            self.d_optim.step()
+            return r1.detach()
+        return self._run("r1", body)
 
     def g_step(self):
         tp = self.config.train_params
         requires_grad(self.G, True)
         requires_grad(self.D, False)
-        fake, fake_ac, _, structure, lat = self._fake()
-        fp = self.D(fake)
-        loss = g_nonsaturating_loss(fp["d_patch"]) + coord_ac_loss(fp["ac_coords_pred"], fake_ac) * tp.coord_ac_w
-        if tp.diversity_z_w and self.batch % 2 == 0:
-            loss = loss + diversity_z_loss(lat, structure) * tp.diversity_z_w
-        self.G.zero_grad(set_to_none=True)
-        loss.backward()
-        allreduce_gradients(self.G.parameters(), self.world)
-        self.g_optim.step()
-        return loss.detach()
+        inp = self._prepare_fake("g")
+
+        def body():
+            fake, _, structure = self._fake(inp)
+            fp = self.D(fake)
+            loss = g_nonsaturating_loss(fp["d_patch"]) + coord_ac_loss(fp["ac_coords_pred"], inp["ac"]) * tp.coord_ac_w
+            if tp.diversity_z_w and self.batch % 2 == 0:
+                loss = loss + diversity_z_loss(inp["lat"], structure) * tp.diversity_z_w
+            self.G.zero_grad(set_to_none=True)
+            loss.backward()
+            allreduce_gradients(self.G.parameters(), self.world)
+            self.g_optim.step()
+            return loss.detach()
+        return self._run("g", body)
 
     def g_path_step(self):
         tp = self.config.train_params
         requires_grad(self.G, True)
         requires_grad(self.D, False)
         pb = max(1, self.batch // tp.path_batch_shrink)
-        gl, lat = self.sampler.latents(pb)
-        coords, cps, _ = self.sampler.coords(pb)
-        noises = self.sampler.noises(pb)
-        styles = self.G.texture_synthesizer.styles_for(gl, None)
-        img = self.G(gl, lat, coords, cps, noises=noises, styles=styles)
-        pl = path_lengths(img, styles)
-        mean = self.mean_path_length + 0.01 * (pl.mean() - self.mean_path_length)
-        penalty = (pl - mean).pow(2).mean()
-        self.mean_path_length = mean.detach()
-        self.G.zero_grad(set_to_none=True)
-        (tp.path_regularize * tp.g_reg_every * penalty).backward()
-        allreduce_gradients(self.G.parameters(), self.world)
-        self.g_optim.step()
-        return penalty.detach()
+        inp = self._prepare_fake("p", pb)
+
+        def body():
+            styles = self.G.texture_synthesizer.styles_for(inp["gl"], inject_mask=inp["mask"])
+            img = self.G(inp["gl"], inp["lat"], inp["coords"], inp["cps"], noises=inp["noises"], styles=styles)
+            pl = path_lengths(img, styles)
+            mean = self.mean_path_length + 0.01 * (pl.mean() - self.mean_path_length)
+            penalty = (pl - mean).pow(2).mean()
+            self.G.zero_grad(set_to_none=True)
+            (tp.path_regularize * tp.g_reg_every * penalty).backward()
+            self.mean_path_length.copy_(mean.detach())  # in place: the running mean is state a graph replay must see
+            allreduce_gradients(self.G.parameters(), self.world)
+            self.g_optim.step()
+            return penalty.detach()
+        return self._run("path", body)
 
     def ema_step(self):
         if self.G_ema is not None:

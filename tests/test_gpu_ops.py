@@ -283,6 +283,21 @@ def test_conv_tcgen05_matches_simt_at_layer_size_and_is_linear(dev):
     assert K.rel_err(K.t2n(y1[:1]), K.t2n(ys)) < 1e-4
 
 
+def test_conv_tcgen05_partial_last_k_block(dev):
+    """K per tap = 80 (a multiple of 16, not of 64): the last K block of every tap is partial (TMA zero fill, the MMAs of
+    the empty K steps are skipped)."""
+    from spgan_b200.functional import ConvGeom
+    name, geom, H = "k3", ConvGeom(3, 3), 19
+    B, C, Oc = 3, 70, 40
+    x = synth.randn_t(7, "cx" + name, (B, C, H, H))
+    w = synth.randn_t(7, "cw" + name, (Oc, C, 3, 3), 0.2)
+    im = synth.randn_t(7, "cim" + name, (B, C), 0.3, 1.0)
+    om = synth.randn_t(7, "com" + name, (B, Oc), 0.3, 1.0)
+    want = _ref_conv(x, w, geom, False, None, im, om, 0.37)
+    got = SF().conv_apply(x.to(dev), w.to(dev), geom, False, None, im.to(dev), om.to(dev), 0.37, precision=1, k_round=16)
+    assert K.rel_err(K.t2n(got), want.numpy()) < TOL[1]
+
+
 def test_wgrad_tcgen05_layer_size_split_k_vs_simt(dev):
     """Weight gradient at a real layer size (512 -> 259-like ragged Cin, several K chunks, two N tiles with a 3-column
     second tile) against the exact-fp32 SIMT kernel; the result is deterministic (fixed K-chunk summation order)."""
