@@ -41,6 +41,7 @@ def parse():
                     help="panorama = BASELINE configs[1] (default, the headline); train = configs[2], full G+D step; "
                          "pano768 = configs[3], one batch of 768x1536 panoramas with the patch lattice sharded over the ranks")
     ap.add_argument("--train-batch", type=int, default=8)
+    ap.add_argument("--no-train", action="store_true", help="panorama workload: do not append the train workload's object")
     ap.add_argument("--no-graphs", action="store_true", help="train workload: launch every kernel eagerly (no CUDA graphs)")
     return ap.parse_args()
 
@@ -252,6 +253,11 @@ def run_ours(args):
         ms_e2e = timed(step_e2e, args.steps) / args.steps
     e2e_value = jobs / (ms_e2e / 1000.0)
 
+    # second half of BASELINE.json's metric ("... & train img/s"): the train workload, same process, same ranks
+    train = None
+    if not sharded and not args.no_train and not args.skip_e2e:
+        train = measure_train(args, dev, world, rank, local)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -297,6 +303,8 @@ def run_ours(args):
     }
     if call_ms is not None:
         out["call_ms"] = call_ms
+    if train is not None:
+        out["train"] = train
     if not args.no_cpu_baseline and not sharded:
         rate, threads, dt, total = cpu_reference_rate(args.cpu_sample_patches)
         out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
@@ -346,7 +354,6 @@ def run_train(args):
     import torch.distributed as dist
     import spgan_b200.functional as SF
     import spgan_b200.lib as lib
-    from spgan_b200.training import TrainStep
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -357,6 +364,22 @@ def run_train(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     SF.set_precision(args.precision)
+    out = measure_train(args, dev, world, rank, local)
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def measure_train(args, dev, world, rank, local):
+    """The train workload (BASELINE configs[2]); returns the JSON object on rank 0, None elsewhere.  The process group
+    (world > 1) is the caller's."""
+    import torch
+    import torch.distributed as dist
+    import spgan_b200.functional as SF
+    import spgan_b200.lib as lib
+    from spgan_b200.training import TrainStep
+
     B = args.train_batch
     ts = TrainStep(batch=B, device=dev, world=world, seed=9000 + rank, use_graphs=not args.no_graphs)
     graphs_on = ts.use_graphs
@@ -443,9 +466,7 @@ def run_train(args):
         call_ms["_all_parts_ms"] = sum(ms_prof.values())
         ts.use_graphs = graphs_on
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return None
     ms_step = amortised(ms)
     value = world * B / (ms_step / 1000.0)
     e2e_value = world * B / (amortised(ms_e2e) / 1000.0)
@@ -489,9 +510,7 @@ def run_train(args):
         rate, threads, dt = cpu_train_rate(2)
         out["cpu_baseline"] = {"value": rate, "unit": TRAIN_UNIT, "cores": threads, "kind": "port",
                                "sample": "one D step + one G step (forward + backward, no regularisers) at batch 2 (%.1f s), oracle port on CPU" % dt}
-    print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+    return out
 
 
 if __name__ == "__main__":
