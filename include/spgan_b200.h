@@ -189,7 +189,10 @@ int spgan_sphere_pack(uint16_t* out, const float* x_nhwc, const float* coords, c
  *   activation, Cin is ignored (K per tap = kp, a multiple of 16), in_stride must be 1, tap_w is ignored (the packed
  *   weight is already in tap order) and precision must be 1 or 2.  a_packed [2][a_rows][kp], w_packed
  *   [2][ntaps][Cout][kp].  a_rows = phases * B*H*W; a tap reads phase plane f by carrying f * B*H in its tap_dy (the row
- *   offset of a tap is tap_dy*W + tap_dx).  Epilogue terms as in spgan_conv_pass. */
+ *   offset of a tap is tap_dy*W + tap_dx).  When the pass has lattice points that are not outputs (My < H or Mx < W, e.g.
+ *   every unpadded 3x3 / 7x7 conv) the A tiles are fetched with TMA im2col loads over the (kp, W, H, 2*phases*B) view of
+ *   a_packed: M then runs over the B*My*Mx outputs only, no MMA is spent on wrap-around points.  Epilogue terms as in
+ *   spgan_conv_pass. */
 int spgan_conv_gemm(const SpganConvPass* p, float* y, const uint16_t* a_packed, int64_t a_rows, int kp,
                     const uint16_t* w_packed, const float* out_mul, const float* noise, const float* noise_w,
                     const float* bias, const float* residual, void* stream);

@@ -23,9 +23,12 @@ namespace {
 constexpr int FWD_THREADS = 320;  // warp 0 producer, warp 1 MMA issuer, warps 2..9 epilogue
 
 struct GemmParams {
-  int32_t rows;        // B * Hl * Wl lattice points
-  int32_t Hl, Wl;      // lattice dims
+  int32_t rows;        // M extent: B * Hl * Wl lattice points (tiled A loads) or B * My * Mx outputs (im2col A loads)
+  int32_t Hl, Wl;      // row decode: points per sample = Hl * Wl, Wl per row (= My, Mx in im2col mode)
   int32_t My, Mx;      // valid lattice extent
+  int32_t im2col;      // 1: the A tile is fetched with TMA im2col loads (no lattice waste), 0: flat row offsets
+  int32_t img_lo;      // im2col: image offset of the lo plane (phases * B)
+  int32_t tap_ox[SPGAN_MAX_TAPS], tap_oy[SPGAN_MAX_TAPS], tap_img[SPGAN_MAX_TAPS];  // im2col: offsets, phase * B
   int32_t Cout, out_H, out_W;
   int32_t out_stride, out_off_y, out_off_x;
   int64_t out_cstride;     // elements between output channels
@@ -106,13 +109,34 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m0 = (tile / gp.n_tiles) * GEMM_BLOCK_M;
         const int n0 = (tile % gp.n_tiles) * kBlockN;
+        // im2col mode: the tile's first output pixel (sample b0, row i0, column j0); TMA walks 128 base pixels from there
+        // inside the (My, Mx) bounding box, across rows and samples, and adds the tap offset to each
+        int b0 = 0, i0 = 0, j0 = 0;
+        if (gp.im2col) {
+          const int plane = gp.Hl * gp.Wl;
+          b0 = m0 / plane;
+          const int r = m0 - b0 * plane;
+          i0 = r / gp.Wl;
+          j0 = r - i0 * gp.Wl;
+        }
         for (int t = 0; t < gp.ntaps; ++t) {
           const int row = m0 + gp.tap_off[t];
           for (int kb = 0; kb < gp.kblocks; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             const uint32_t sa = smem_base + stage * S::kStageBytes;
             mbar_arrive_expect_tx(full_bar(stage), S::kStageBytes);
-            if (kPasses == 3) {
+            if (gp.im2col) {
+              const int img = b0 + gp.tap_img[t];
+              tma_load_im2col(sa, &tmA, full_bar(stage), kb * GEMM_BLOCK_K, j0, i0, img, gp.tap_ox[t], gp.tap_oy[t]);
+              if (kPasses == 3) {
+                tma_load_im2col(sa + A_TILE_BYTES, &tmA, full_bar(stage), kb * GEMM_BLOCK_K, j0, i0, img + gp.img_lo,
+                                gp.tap_ox[t], gp.tap_oy[t]);
+                tma_load_4d(sa + 2 * A_TILE_BYTES, &tmB, full_bar(stage), kb * GEMM_BLOCK_K, n0, t, 0);
+                tma_load_4d(sa + 2 * A_TILE_BYTES + kBTile, &tmB, full_bar(stage), kb * GEMM_BLOCK_K, n0, t, 1);
+              } else {
+                tma_load_4d(sa + A_TILE_BYTES, &tmB, full_bar(stage), kb * GEMM_BLOCK_K, n0, t, 0);
+              }
+            } else if (kPasses == 3) {
               tma_load_3d(sa, &tmA, full_bar(stage), kb * GEMM_BLOCK_K, row, 0);
               tma_load_3d(sa + A_TILE_BYTES, &tmA, full_bar(stage), kb * GEMM_BLOCK_K, row, 1);
               tma_load_4d(sa + 2 * A_TILE_BYTES, &tmB, full_bar(stage), kb * GEMM_BLOCK_K, n0, t, 0);
@@ -752,12 +776,32 @@ extern "C" int spgan_conv_gemm(const SpganConvPass* p, float* y, const uint16_t*
   SPGAN_CHECK_ARG(y && a_packed && w_packed, "spgan_conv_gemm: null pointer");
   SPGAN_CHECK_ARG(((((uintptr_t)a_packed) | ((uintptr_t)w_packed)) & 15) == 0, "spgan_conv_gemm: packed operands must be 16-byte aligned");
 
+  // im2col A loads whenever the pass has lattice points that are not outputs (unpadded 3x3 / 7x7 convs, padded convs on
+  // their bordered lattice, parity passes): M then runs over the B*My*Mx outputs only.  The bounding-box corner of a
+  // rank-4 map is an 8-bit field, hence the 128 limit; passes outside it keep the flat row-offset loads.
+  const int phases = (int)(a_rows / rows);
+  const bool im2col = (p->My < p->H || p->Mx < p->W) && p->My <= p->H && p->Mx <= p->W && p->H - p->My <= 128 &&
+                      p->W - p->Mx <= 128 && (int64_t)2 * phases * p->B < (1LL << 31);
   GemmParams gp;
-  gp.rows = (int32_t)rows;
-  gp.Hl = p->H;
-  gp.Wl = p->W;
+  gp.im2col = im2col ? 1 : 0;
+  gp.img_lo = phases * p->B;
+  gp.rows = im2col ? (int32_t)((int64_t)p->B * p->My * p->Mx) : (int32_t)rows;
+  gp.Hl = im2col ? p->My : p->H;
+  gp.Wl = im2col ? p->Mx : p->W;
   gp.My = p->My;
   gp.Mx = p->Mx;
+  for (int t = 0; t < SPGAN_MAX_TAPS; ++t) gp.tap_ox[t] = gp.tap_oy[t] = gp.tap_img[t] = 0;
+  for (int t = 0; t < p->ntaps; ++t) {
+    // tap_dy carries the phase plane of the tap as phase * (B*H) (see the header): split it back
+    const int bh = p->B * p->H;
+    const int ph = p->tap_dy[t] / bh;
+    gp.tap_oy[t] = p->tap_dy[t] - ph * bh;
+    gp.tap_ox[t] = p->tap_dx[t];
+    gp.tap_img[t] = ph * p->B;
+    if (im2col)
+      SPGAN_CHECK_ARG(p->tap_dy[t] >= 0 && p->tap_dx[t] >= 0 && gp.tap_oy[t] < 256 && gp.tap_ox[t] < 256 && ph < phases,
+                      "spgan_conv_gemm: tap %d (%d, %d) outside the im2col offset range", t, p->tap_dy[t], p->tap_dx[t]);
+  }
   gp.Cout = p->Cout;
   gp.out_H = p->out_H;
   gp.out_W = p->out_W;
@@ -770,7 +814,7 @@ extern "C" int spgan_conv_gemm(const SpganConvPass* p, float* y, const uint16_t*
   gp.last_ksteps = (kp - (gp.kblocks - 1) * GEMM_BLOCK_K) / GEMM_UMMA_K;
   for (int t = 0; t < p->ntaps; ++t) gp.tap_off[t] = p->tap_dy[t] * p->W + p->tap_dx[t];
   for (int t = p->ntaps; t < SPGAN_MAX_TAPS; ++t) gp.tap_off[t] = 0;
-  gp.m_tiles = (int32_t)((rows + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M);
+  gp.m_tiles = (int32_t)(((int64_t)gp.rows + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M);
   const int block_n = pick_block_n(gp.m_tiles, p->Cout);
   gp.n_tiles = (p->Cout + block_n - 1) / block_n;
   gp.out_scale = p->out_scale;
@@ -779,7 +823,13 @@ extern "C" int spgan_conv_gemm(const SpganConvPass* p, float* y, const uint16_t*
   gp.act_gain = p->act_gain;
 
   CUtensorMap tmA, tmB;
-  {
+  if (im2col) {
+    // (kp channels, W, H, 2 * phases * B images): hi planes first, then the lo planes
+    if (int e = encode_bf16_im2col_map(&tmA, a_packed, (cuuint64_t)kp, (cuuint64_t)p->W, (cuuint64_t)p->H,
+                                       (cuuint64_t)2 * phases * p->B, p->Mx - p->W, p->My - p->H, GEMM_BLOCK_K, GEMM_BLOCK_M,
+                                       "spgan_conv_gemm (A im2col map)"))
+      return e;
+  } else {
     cuuint64_t dims[3] = {(cuuint64_t)kp, (cuuint64_t)a_rows, 2};
     cuuint64_t strides[2] = {(cuuint64_t)kp * 2, (cuuint64_t)a_rows * kp * 2};
     cuuint32_t box[3] = {GEMM_BLOCK_K, GEMM_BLOCK_M, 1};

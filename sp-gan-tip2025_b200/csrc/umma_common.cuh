@@ -71,6 +71,17 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// im2col-mode tile load from a rank-4 (C, W, H, N) tensor map: `pixelsPerColumn` base pixels starting at (w, h, n),
+// walking w, then h, then n inside the map's bounding box, each displaced by the filter offset (w_off, h_off).
+// Verified on a B200 by tools/probes/tma_im2col.cu (row / image crossing, channel offsets, zero fill past the tensor).
+__device__ __forceinline__ void tma_load_im2col(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c, int w, int h,
+                                                int n, int w_off, int h_off) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], "
+      "{%7, %8};" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"((uint16_t)w_off), "h"((uint16_t)h_off)
+      : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -136,6 +147,40 @@ EncodeTiledFn get_encode_fn() {
     return nullptr;
   fn = (EncodeTiledFn)sym;
   return fn;
+}
+
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*,
+                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                   CUtensorMapFloatOOBfill);
+
+inline EncodeIm2colFn get_encode_im2col_fn() {
+  static EncodeIm2colFn fn = nullptr;
+  if (fn) return fn;
+  void* sym = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess || sym == nullptr)
+    return nullptr;
+  fn = (EncodeIm2colFn)sym;
+  return fn;
+}
+
+// NHWC bf16 tensor (C, W, H, N) with base pixels restricted to [0, W + upper_w) x [0, H + upper_h) (upper_* <= 0).
+inline int encode_bf16_im2col_map(CUtensorMap* map, const void* base, cuuint64_t C, cuuint64_t W, cuuint64_t H, cuuint64_t N,
+                                  int upper_w, int upper_h, cuuint32_t channels, cuuint32_t pixels, const char* who) {
+  EncodeIm2colFn fn = get_encode_im2col_fn();
+  SPGAN_CHECK_ARG(fn != nullptr, "%s: cuTensorMapEncodeIm2col is not available from the CUDA driver", who);
+  cuuint64_t dims[4] = {C, W, H, N};
+  cuuint64_t strides[3] = {C * 2, W * C * 2, H * W * C * 2};
+  int lower[2] = {0, 0};
+  int upper[2] = {upper_w, upper_h};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, lower, upper, channels,
+                  pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SPGAN_CHECK_ARG(r == CUDA_SUCCESS, "%s: cuTensorMapEncodeIm2col failed with CUresult %d", who, (int)r);
+  return 0;
 }
 
 int encode_bf16_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
