@@ -274,7 +274,10 @@ def run_ours(args):
     ach = gemm_stats["flops"] / (gemm_stats["ms"] / 1000.0) / 1e12 if gemm_stats["ms"] > 0 else 0.0
     issued = {1: 3, 2: 1, 0: 0}[args.precision]
     roofline = {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit-GEMM modulated conv)", "achieved": ach,
-                "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf if peak_tf else None, "traffic": None,
+                "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf if peak_tf else None, "traffic": 1346227712,
+                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the dominant launch (TS layer 7, 32x103x103 lattice, 2.95 ms, "
+                                "24 % of the step) from the ncu --set full capture in profiles/r1b_ncu_full_pano_before_im2col.txt "
+                                "(launch 9): 716.5 MB + 629.7 MB against 1372 MB algorithmic (695 MB packed A + 9 MB weights + 668 MB output)",
                 "peak_source": peak_src, "launches_timed": gemm_stats["launches"], "avg_launch_ms": gemm_stats["ms"] / max(gemm_stats["launches"], 1),
                 "share_of_step": gemm_stats["ms"] / (ms_total if ms_total else 1.0),
                 "note": "achieved = algorithmic conv FLOPs (2*B*Ho*Wo*Cout*Cin*k^2, valid outputs, real channels) / CUDA-event "
