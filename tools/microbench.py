@@ -1,0 +1,187 @@
+"""Isolated-kernel microbenchmarks (BASELINE.json configs[4]): bias-act, upfirdn2d, the spherical gather, the fused FIR tail,
+the operand packers and the fused spherical modulated conv, each timed with CUDA events on inputs larger than L2 and
+reported against its roofline (HBM: MEASURED_PEAKS.json hbm_gbs; tensor: bf16_tflops_sustained).
+
+    python tools/microbench.py [--budget-s 45]
+
+Prints one JSON object per case.  Every case is wrapped so that a failure is reported and the sweep continues.
+"""
+import argparse
+import json
+import math
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+import spgan_b200.functional as SF
+import spgan_b200.lib as lib
+from spgan_b200 import grids, panorama
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--budget-s", type=float, default=45.0)
+    args = ap.parse_args()
+    torch.cuda.set_device(0)
+    lib.require_device()
+    dev = torch.device("cuda:0")
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    hbm = float(peaks.get("hbm_gbs", 6549.8))
+    tf_peak = float(peaks.get("bf16_tflops_sustained", 1388.5))
+    t_start = time.time()
+
+    def timed(fn, iters=5, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    def report(name, ms, bytes_=None, flops=None, **kw):
+        out = {"case": name, "ms": round(ms, 4)}
+        if bytes_ is not None:
+            gbs = bytes_ / (ms / 1e3) / 1e9
+            out.update(bound="hbm", algorithmic_MB=round(bytes_ / 1e6, 1), achieved_GBs=round(gbs, 1), peak_GBs=hbm,
+                       frac=round(gbs / hbm, 3))
+        if flops is not None:
+            tfs = flops / (ms / 1e3) / 1e12
+            out.update(bound="tensor", algorithmic_GFLOP=round(flops / 1e9, 2), achieved_TFs=round(tfs, 1), peak_TFs=tf_peak,
+                       frac=round(tfs / tf_peak, 3))
+        out.update(kw)
+        print(json.dumps(out), flush=True)
+
+    def case(name, build):
+        if time.time() - t_start > args.budget_s:
+            print(json.dumps({"case": name, "skipped": "time budget"}), flush=True)
+            return
+        try:
+            with torch.no_grad():
+                build()
+        except Exception as e:  # keep sweeping
+            print(json.dumps({"case": name, "error": "%s: %s" % (type(e).__name__, str(e)[:200])}), flush=True)
+        torch.cuda.empty_cache()
+
+    g = torch.Generator(device=dev).manual_seed(1)
+    rn = lambda *s: torch.randn(*s, device=dev, generator=g)
+    SQ2 = 2 ** 0.5
+    k3 = torch.tensor([[1., 2., 1.], [2., 4., 2.], [1., 2., 1.]], device=dev) / 16 * 4
+    k4 = torch.tensor([1., 3., 3., 1.], device=dev)
+    k4 = (k4[None, :] * k4[:, None]) / 64
+
+    # ---- K1 bias + activation (models/custom_ops/fused_bias_act_kernel.cu) ----
+    def bias_act_fwd():
+        x, b = rn(32, 512, 101, 101), rn(512)
+        ms = timed(lambda: SF.bias_act(x, b, None, 3, 0, 0.2, SQ2))
+        report("bias_act fwd (32,512,101,101)", ms, bytes_=2 * 4 * x.numel())
+    case("bias_act fwd", bias_act_fwd)
+
+    def bias_act_bwd():
+        go, out = rn(32, 512, 101, 101), rn(32, 512, 101, 101)
+        ms = timed(lambda: SF.FusedLeakyReLUFunctionBackward.apply(go, out, 0.2, SQ2))
+        report("bias_act bwd + bias reduction (32,512,101,101)", ms, bytes_=3 * 4 * go.numel())
+    case("bias_act bwd", bias_act_bwd)
+
+    def noise_bias_act():
+        x, nz, nw, b = rn(32, 512, 101, 101), rn(32, 1, 101, 101), torch.tensor([0.3], device=dev), rn(512)
+        ms = timed(lambda: SF.noise_bias_act(x, nz, nw, b))
+        report("noise + bias + act (32,512,101,101)", ms, bytes_=2 * 4 * x.numel())
+    case("noise_bias_act", noise_bias_act)
+
+    # ---- K2 upfirdn2d (models/custom_ops/upfirdn2d_kernel.cu) ----
+    def fir_g():
+        x = rn(32, 512, 105, 105)
+        ms = timed(lambda: SF.upfirdn2d(x, k3, pad=(0, 0)))
+        report("upfirdn2d 3x3 pad 0 (G blur) (32,512,105,105)", ms, bytes_=4 * 32 * 512 * (105 * 105 + 103 * 103))
+    case("upfirdn2d G blur", fir_g)
+
+    def fir_d():
+        x = rn(32, 256, 101, 101)
+        ms = timed(lambda: SF.upfirdn2d(x, k4, pad=(2, 2)))
+        report("upfirdn2d 4x4 pad 2 (D blur) (32,256,101,101)", ms, bytes_=4 * 32 * 256 * (101 * 101 + 102 * 102))
+    case("upfirdn2d D blur", fir_d)
+
+    def fir_up():
+        x = rn(32, 64, 53, 53)
+        ms = timed(lambda: SF.upfirdn2d(x, k3, up=2, down=1, pad=(1, 0)))
+        oh = 53 * 2 + 1 - 3 + 1
+        report("upfirdn2d up=2 3x3 (generic kernel) (32,64,53,53)", ms, bytes_=4 * 32 * 64 * (53 * 53 + oh * oh))
+    case("upfirdn2d up2", fir_up)
+
+    def upblur():
+        pp, nz, nw, b = rn(32, 512, 4, 53, 53), rn(32, 1, 103, 103), torch.tensor([0.3], device=dev), rn(512)
+        ms = timed(lambda: SF.upblur_act(pp, k3, (105, 105), nz, nw, b))
+        report("upblur_act (interleave + FIR + noise + bias + act) -> (32,512,103,103)", ms,
+               bytes_=4 * 32 * 512 * (4 * 53 * 53 + 103 * 103))
+    case("upblur_act", upblur)
+
+    # ---- L1 spherical gather (F.grid_sample in the reference) ----
+    pl = panorama.plan(384, 768)
+    cp, _ = panorama.patch_inputs(pl, 2, 7, 27, pl["lat_h"], pl["lat_w"])
+
+    def gather():
+        z = rn(32, 256, 35, 35)
+        grid = torch.from_numpy(grids.sampling_grid(35, 35, cp)).to(dev)
+        ms = timed(lambda: SF.sphere_gather_raw(z, grid))
+        report("sphere_gather (32,256,35,35) -> 9x", ms, bytes_=4 * z.numel() * 10 + grid.numel() * 4)
+    case("sphere_gather", gather)
+
+    # ---- operand packer ----
+    def pack():
+        x, s = rn(32, 512, 103, 103), rn(32, 512)
+        out = torch.empty((2, 32 * 103 * 103, 512), device=dev, dtype=torch.bfloat16)
+        import ctypes
+        p = lambda t: ctypes.c_void_p(t.data_ptr())
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        ms = timed(lambda: lib.call("spgan_pack_act", p(out), p(x), p(s), 32, 512, 103, 103, 512, 0, 0, 103, 103, 1, st))
+        report("pack_act (32,512,103,103) -> bf16 hi/lo channels-last", ms, bytes_=4 * x.numel() + out.numel() * 2)
+    case("pack_act", pack)
+
+    # ---- fused spherical modulated conv sweep (gather + encode + modulate + tcgen05 GEMM) ----
+    for C in (64, 128, 256, 512):
+        for H in (32, 64, 128):
+            B = 8
+
+            def sph(C=C, H=H, B=B):
+                x, c = rn(B, C, H, H), rn(B, 3, H, H)
+                w = rn(C, C + 3, 3, 3)
+                s, d = rn(B, C + 3), rn(B, C).abs() + 0.5
+                cpm = dict(cp)
+                grid = torch.from_numpy(grids.sampling_grid(H, H, cpm)).to(dev)
+                ms = timed(lambda: SF.sphere_modconv_fused(x, c, grid, w, s, d, 0.05, act=(0.01, 1.0), precision=1), iters=3, warm=1)
+                report("sphere_modconv fused fwd B=%d C=%d H=%d" % (B, C, H), ms, flops=2.0 * B * H * H * C * (C + 3) * 9)
+            case("sphere_modconv C=%d H=%d" % (C, H), sph)
+
+    # ---- plain modulated 3x3 conv fwd / data gradient / weight gradient at the largest layer ----
+    def conv_big():
+        geom = SF.ConvGeom(3, 3)
+        x, w = rn(32, 512, 103, 103), rn(512, 512, 3, 3)
+        s, d = rn(32, 512), rn(32, 512).abs() + 0.5
+        fl = 2.0 * 32 * 101 * 101 * 512 * 512 * 9
+        ms = timed(lambda: SF.conv_apply(x, w, geom, in_mul=s, out_mul=d, out_scale=0.02, precision=1), iters=3, warm=1)
+        report("modconv 3x3 512->512 fwd (pack + GEMM) (32,512,103,103)", ms, flops=fl)
+        gy = rn(32, 512, 101, 101)
+        ms = timed(lambda: SF.conv_apply(gy, w, geom, True, (103, 103), d, s, 0.02, precision=1), iters=3, warm=1)
+        report("modconv 3x3 512->512 data gradient (pack + GEMM)", ms, flops=fl)
+        ms = timed(lambda: SF.conv_wgrad(gy[:8], x[:8], (512, 512, 3, 3), geom, s[:8], d[:8], 0.02, precision=1), iters=3, warm=1)
+        report("modconv 3x3 512->512 weight gradient B=8 (2 packs + GEMM + reduce)", ms, flops=fl / 4)
+    case("modconv big", conv_big)
+
+
+if __name__ == "__main__":
+    main()
