@@ -15,20 +15,46 @@ __device__ __forceinline__ float act_fn(float v, float r, int code, float alpha)
   }
 }
 
+// 128-bit path for any channel extent >= 4: a float4 may straddle one channel boundary (odd planes such as 101 x 101), so
+// each element picks its own bias; the channel of the first element comes from two exact 32-bit fast divisions (the
+// hardware-emulated 64-bit division of the scalar path costs more than the memory traffic).  Two independent 128-bit
+// loads per thread and iteration are in flight before the first store.
 __global__ void __launch_bounds__(256) bias_act_vec4(float4* __restrict__ out, const float4* __restrict__ x,
                                                     const float* __restrict__ bias, const float4* __restrict__ ref,
-                                                    int64_t n4, int64_t step_b4, int64_t size_b, int code, float alpha,
-                                                    float scale) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-    float4 v = __ldcs(x + i);
-    float b = bias ? __ldg(bias + (i / step_b4) % size_b) : 0.f;
-    float4 r = ref ? __ldcs(ref + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 o;
-    o.x = act_fn(v.x + b, r.x, code, alpha) * scale;
-    o.y = act_fn(v.y + b, r.y, code, alpha) * scale;
-    o.z = act_fn(v.z + b, r.z, code, alpha) * scale;
-    o.w = act_fn(v.w + b, r.w, code, alpha) * scale;
-    __stcs(out + i, o);
+                                                    uint32_t n4, uint32_t step_b, uint32_t size_b, FastDiv dstep,
+                                                    FastDiv dsize, int code, float alpha, float scale) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += 2 * stride) {
+    float4 v[2], r[2];
+    bool ok[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const uint32_t i = i0 + u * stride;
+      ok[u] = i < n4;
+      v[u] = ok[u] ? __ldcs(x + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      r[u] = (ok[u] && ref) ? __ldcs(ref + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (!ok[u]) continue;
+      const uint32_t i = i0 + u * stride;
+      float b0 = 0.f, b1 = 0.f;
+      uint32_t left = 4;  // elements of this float4 that still belong to the first channel
+      if (bias) {
+        const uint32_t e = 4u * i;
+        const uint32_t c = fdiv(e, dstep);
+        left = (c + 1) * step_b - e;
+        const uint32_t cm = c - fdiv(c, dsize) * size_b;
+        b0 = __ldg(bias + cm);
+        b1 = __ldg(bias + (cm + 1 == size_b ? 0 : cm + 1));
+      }
+      float4 o;
+      o.x = act_fn(v[u].x + b0, r[u].x, code, alpha) * scale;
+      o.y = act_fn(v[u].y + (left > 1 ? b0 : b1), r[u].y, code, alpha) * scale;
+      o.z = act_fn(v[u].z + (left > 2 ? b0 : b1), r[u].z, code, alpha) * scale;
+      o.w = act_fn(v[u].w + (left > 3 ? b0 : b1), r[u].w, code, alpha) * scale;
+      __stcs(out + i, o);
+    }
   }
 }
 
@@ -63,23 +89,39 @@ __global__ void __launch_bounds__(256) bias_act_scalar(float* __restrict__ out, 
 // Writes grad_in and reduces grad_bias with one atomicAdd per CTA.
 __global__ void __launch_bounds__(256) bias_act_bwd_kernel(float* __restrict__ gi, float* __restrict__ gb,
                                                           const float* __restrict__ go, const float* __restrict__ ref,
-                                                          int64_t batch, int64_t channels, int64_t inner, float alpha,
-                                                          float scale) {
+                                                          int64_t batch, int64_t channels, int64_t inner, FastDiv dinner,
+                                                          float alpha, float scale) {
   const int64_t c = blockIdx.x;
   const int64_t total = batch * inner;
   const int64_t per = (total + gridDim.y - 1) / gridDim.y;
   const int64_t begin = (int64_t)blockIdx.y * per;
   const int64_t end = begin + per < total ? begin + per : total;
   float acc = 0.f;
-  for (int64_t e = begin + threadIdx.x; e < end; e += blockDim.x) {
-    const int64_t b = e / inner;
-    const int64_t k = e - b * inner;
-    const int64_t idx = (b * channels + c) * inner + k;
-    const float g = __ldcs(go + idx);
-    const float r = __ldcs(ref + idx);
-    const float v = (r > 0.f ? g : g * alpha) * scale;
-    __stcs(gi + idx, v);
-    acc += v;
+  // batches of 4 independent (grad, ref) load pairs per thread; the sample index of an element comes from one exact
+  // 32-bit fast division (total = batch * inner < 2^31 is checked by the launcher)
+  for (int64_t e0 = begin + threadIdx.x; e0 < end; e0 += 4 * (int64_t)blockDim.x) {
+    float g[4], r[4];
+    int64_t idx[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t e = e0 + u * (int64_t)blockDim.x;
+      idx[u] = -1;
+      g[u] = r[u] = 0.f;
+      if (e < end) {
+        const uint32_t b = fdiv((uint32_t)e, dinner);
+        const uint32_t k = (uint32_t)e - b * (uint32_t)inner;
+        idx[u] = ((int64_t)b * channels + c) * inner + k;
+        g[u] = __ldcs(go + idx[u]);
+        r[u] = __ldcs(ref + idx[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (idx[u] < 0) continue;
+      const float v = (r[u] > 0.f ? g[u] : g[u] * alpha) * scale;
+      __stcs(gi + idx[u], v);
+      acc += v;
+    }
   }
   __shared__ float warp_sums[8];
 #pragma unroll
@@ -107,10 +149,23 @@ __global__ void __launch_bounds__(256) noise_bias_act_kernel(float* __restrict__
   const float* xp = x + plane * inner;
   const float* np = noise ? noise + b * inner : nullptr;
   float* op = out + plane * inner;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < inner; i += (int64_t)gridDim.x * blockDim.x) {
-    float v = __ldcs(xp + i) + bv;
-    if (np) v += nw * __ldg(np + i);
-    __stcs(op + i, (v > 0.f ? v : v * alpha) * scale);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < inner; i0 += 4 * stride) {
+    float v[4], z[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {  // all loads of the batch before the first store
+      const int64_t i = i0 + u * stride;
+      v[u] = i < inner ? __ldcs(xp + i) : 0.f;
+      z[u] = (np && i < inner) ? __ldg(np + i) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i >= inner) continue;
+      float t = v[u] + bv;
+      if (np) t += nw * z[u];
+      __stcs(op + i, (t > 0.f ? t : t * alpha) * scale);
+    }
   }
 }
 
@@ -146,10 +201,11 @@ extern "C" int spgan_bias_act(float* out, const float* x, const float* bias, con
   const int code = act * 10 + grad;
   cudaStream_t st = (cudaStream_t)stream;
   const bool aligned = ((((uintptr_t)out) | ((uintptr_t)x) | ((uintptr_t)ref)) & 15) == 0;
-  if (aligned && n % 4 == 0 && (!bias || step_b % 4 == 0)) {
+  if (aligned && n % 4 == 0 && n < (1LL << 31) && (!bias || (step_b >= 4 && step_b < (1LL << 31) && size_b < (1LL << 31)))) {
     const int64_t n4 = n / 4;
-    bias_act_vec4<<<grid_for(n4, 256, 8), 256, 0, st>>>((float4*)out, (const float4*)x, bias, (const float4*)ref, n4,
-                                                        bias ? step_b / 4 : 1, bias ? size_b : 1, code, alpha, scale);
+    const uint32_t sb = bias ? (uint32_t)step_b : 4u, zb = bias ? (uint32_t)size_b : 1u;
+    bias_act_vec4<<<grid_for(n4, 512, 8), 256, 0, st>>>((float4*)out, (const float4*)x, bias, (const float4*)ref, (uint32_t)n4,
+                                                        sb, zb, make_fastdiv(sb), make_fastdiv(zb), code, alpha, scale);
   } else {
     bias_act_scalar<<<grid_for(n, 1024, 8), 256, 0, st>>>(out, x, bias, ref, n, bias ? step_b : 1, bias ? size_b : 1,
                                                           code, alpha, scale);
@@ -167,6 +223,7 @@ extern "C" int spgan_bias_act_bwd(float* grad_in, float* grad_bias, const float*
   if (batch * channels * inner == 0) return 0;
   SPGAN_CHECK_ARG(grad_in && grad_bias && grad_out && out_ref, "spgan_bias_act_bwd: null pointer");
   SPGAN_CHECK_ARG(channels <= 2147483647, "spgan_bias_act_bwd: too many channels");
+  SPGAN_CHECK_ARG(batch * inner < (1LL << 31), "spgan_bias_act_bwd: batch * inner = %lld exceeds 2^31", (long long)(batch * inner));
   // enough slices that channels*slices covers >= 4 waves of 148 SMs x 8 CTAs, each slice >= 2048 elements
   int64_t slices = ceil_div64((int64_t)SPGAN_NUM_SMS * 8 * 4, channels);
   const int64_t max_slices = ceil_div64(batch * inner, 2048);
@@ -174,7 +231,8 @@ extern "C" int spgan_bias_act_bwd(float* grad_in, float* grad_bias, const float*
   if (slices > 65535) slices = 65535;
   if (slices < 1) slices = 1;
   dim3 grid((unsigned)channels, (unsigned)slices);
-  bias_act_bwd_kernel<<<grid, 256, 0, st>>>(grad_in, grad_bias, grad_out, out_ref, batch, channels, inner, alpha, scale);
+  bias_act_bwd_kernel<<<grid, 256, 0, st>>>(grad_in, grad_bias, grad_out, out_ref, batch, channels, inner,
+                                            make_fastdiv((uint32_t)inner), alpha, scale);
   SPGAN_CHECK_LAUNCH("spgan_bias_act_bwd");
   return 0;
 }
