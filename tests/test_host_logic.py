@@ -1,6 +1,5 @@
 """CPU: host-side product logic (sampling tables, panorama lattice, module bookkeeping) against the oracle and the
 golden fixtures."""
-import json
 
 import numpy as np
 import torch

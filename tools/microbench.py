@@ -8,7 +8,6 @@ Prints one JSON object per case.  Every case is wrapped so that a failure is rep
 """
 import argparse
 import json
-import math
 import os
 import sys
 import time
@@ -16,7 +15,6 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-import numpy as np
 import torch
 
 import spgan_b200.functional as SF
