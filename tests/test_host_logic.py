@@ -128,3 +128,26 @@ def test_grid_factorisation_equals_dense_grid_bitwise():
             want = grids.sampling_grid(h, h, cp)
             got = grids.assemble_reference(h, h, cp)
             assert np.array_equal(want.view(np.uint32), got.view(np.uint32)), (h, cp)
+
+
+def test_bench_reference_arm_prints_contract_line():
+    """`bench.py --impl reference` (the arm the driver runs first, CPU only) prints one JSON line with the contract keys."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--cpu-sample-patches", "2"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    # other ranks of a torchrun launch exit 0 without work
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference"], capture_output=True, text=True,
+                         timeout=120, cwd=root, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""
