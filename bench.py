@@ -32,7 +32,13 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32)
-    ap.add_argument("--precision", type=int, default=1, choices=[0, 1, 2])
+    ap.add_argument("--precision", type=int, default=1, choices=[0, 1, 2, 3])
+    ap.add_argument("--streams", type=int, default=2, help="concurrent lattice-position branches of the panorama graph")
+    ap.add_argument("--ts-precision", default="", help="8 comma-separated per-layer modes for the texture chain")
+    ap.add_argument("--fast-tail", action="store_true", help="also measure the fp16x2 tail policy (reported beside the headline)")
+    ap.add_argument("--no-pano768", action="store_true", help="do not append the 768x1536 lattice-sharded object")
+    ap.add_argument("--pano768-batch", type=int, default=8)
+    ap.add_argument("--skip-profile", action="store_true", help="skip the eager per-launch profiling step")
     ap.add_argument("--cpu-sample-patches", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs under ncu only: skip the end-to-end leg")
@@ -73,28 +79,52 @@ def cpu_reference_rate(n_patches, threads=None):
     return (n_patches / total) / dt, threads, dt, total
 
 
+def reference_rate(steps, warmup):
+    """(panoramas/s, seconds per step list, threads, kind, sample) of the reference's CPU path.  The REAL reference (staged
+    under oracle/_ref by oracle/build_ref.py, or /root/reference in the build container) driven by its own close-loop
+    manager over all 60 lattice positions of one B = 1 panorama; the oracle port on a 12-position sample only when the
+    reference cannot be imported."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    try:
+        import refrun
+        if not refrun.available():
+            raise RuntimeError("reference tree not staged")
+        times, threads, total = refrun.time_reference_panorama(steps=steps, warmup=warmup)
+        rate = len(times) / sum(times)
+        return rate, times, threads, "reference", ("B=1, one full 384x768 panorama per step (all %d lattice positions), the reference's own "
+                                                  "InfinityGanGenerator + close-loop manager on CPU (native PyTorch ops)" % total)
+    except Exception as e:  # noqa: BLE001 - any import problem of the staged reference falls back to the port
+        sys.stderr.write("reference arm: real reference unavailable (%s: %s); timing the oracle port\n" % (type(e).__name__, str(e)[:200]))
+        per_step, times, threads, total = 12, [], None, 60
+        for i in range(warmup + steps):
+            _, threads, dt, total = cpu_reference_rate(per_step)
+            if i >= warmup:
+                times.append(dt)
+        rate = (per_step / total) * len(times) / sum(times)
+        return rate, times, threads, "port", ("B=1, %d of %d patch positions of one 384x768 panorama per step, oracle port of the "
+                                              "reference on CPU" % (per_step, total))
+
+
+def cpu_baseline_object(args):
+    rate, times, threads, kind, sample = reference_rate(1, 0)
+    return {"value": rate, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample + " (%.1f s)" % sum(times)}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    per_step = max(2, min(args.cpu_sample_patches, 12))
-    rates, dts = [], []
-    for i in range(args.warmup + args.steps):
-        r, threads, dt, total = cpu_reference_rate(per_step)
-        if i >= args.warmup:
-            rates.append(r)
-            dts.append(dt)
-    ms = 1000.0 * sum(dts) / len(dts)
-    value = (per_step / total) * len(dts) / sum(dts)
-    sample = "B=1, %d of %d patch positions of one 384x768 panorama per step, oracle port of the reference on CPU" % (per_step, total)
+    value, times, threads, kind, sample = reference_rate(args.steps, args.warmup)
+    ms = 1000.0 * sum(times) / len(times)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "fp32", "data": "synthetic",
-        "config": {"workload": "SP-GAN generator forward, 384x768 close-loop panorama, random-init configs/model/spgan.yaml",
-                   "batch": 1, "patches_per_panorama": total},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "config": {"workload": "SP-GAN generator forward at 384x768 (close-loop, 60 patch positions), random-init configs/model/spgan.yaml, "
+                               "synthetic latents; reference CPU path at batch 1 (BASELINE configs[0])", "batch_per_gpu": 1},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
     }))
 
 
@@ -146,7 +176,23 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
-def run_ours(args):
+DTYPES = {0: "fp32 (SIMT)", 1: "fp32-equivalent (bf16x3 split on tcgen05, fp32 accumulate)",
+          2: "bf16 (tcgen05, fp32 accumulate)", 3: "fp16x2 split on tcgen05 (fp16 hi+lo activations x fp16 weights, fp32 accumulate)"}
+ISSUED = {0: 0, 1: 3, 2: 1, 3: 2}  # tensor-core MMAs issued per algorithmic MMA
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+def measure_panorama(args, dev, world, rank, local, th, tw, B, sharded, steps, warmup, layer_precision=None,
+                     profile=True, e2e=True):
+    """Times `steps` panorama steps (one step = every lattice position of a batch of B panoramas) through
+    spgan_b200.panorama.PanoramaEngine.  Returns a dict of raw measurements (all ranks)."""
     import torch
     import torch.distributed as dist
     import spgan_b200.functional as SF
@@ -154,24 +200,11 @@ def run_ours(args):
     from spgan_b200 import panorama
     from spgan_b200.generator import Generator
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    lib.require_device()  # no fallback: fail loudly if the extension or a B200 is missing
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    SF.set_precision(args.precision)
-
     torch.manual_seed(9000)
     gen = Generator().to(dev).eval()
-    B = args.batch
-    sharded = args.workload == "pano768"
-    th, tw = (768, 1536) if sharded else (384, 768)
+    gen.texture_synthesizer.layer_precision = layer_precision
     pl = panorama.plan(th, tw)
     n_pos = len(panorama.positions(pl))
-
     # sharded: every rank holds the SAME canvases (same seed) and runs its share of the lattice (strong scaling)
     g = torch.Generator(device="cpu").manual_seed(9000 + (0 if sharded else rank))
     host = {
@@ -183,37 +216,30 @@ def run_ours(args):
     host_out = torch.empty(B, 3, pl["meta_h"], pl["meta_w"]).pin_memory()
     h2d = host["gl"].numel() * 4 + host["canvas"].numel() * 4 + sum(n.numel() * 4 for n in host["noises"])
     d2h = host_out.numel() * 4
-
-    def upload():
-        return (host["gl"].to(dev, non_blocking=True), host["canvas"].to(dev, non_blocking=True),
-                [n.to(dev, non_blocking=True) for n in host["noises"]])
-
-    resident = upload()
-    meta = torch.zeros(B, 3, pl["meta_h"], pl["meta_w"], device=dev)
-
-    def run(gl, canvas, noises):
-        if sharded:
-            return panorama.generate_sharded(gen, pl, gl, canvas, noises, rank, world, meta=meta)
-        return panorama.generate(gen, pl, gl, canvas, noises, meta=meta)
+    graphs = not args.no_graphs
+    if sharded:
+        eng = panorama.ShardedPanoramaEngine(gen, pl, B, dev, rank, world, streams=args.streams, use_graph=graphs)
+    else:
+        eng = panorama.PanoramaEngine(gen, pl, B, dev, streams=args.streams, use_graph=graphs)
+    eng.load(host["gl"], host["canvas"], host["noises"])
 
     def step_resident():
-        return run(*resident)
+        return eng.run()
 
     def step_e2e():
-        out = run(*upload())
-        host_out.copy_(out, non_blocking=True)
-        return out
+        eng.load(host["gl"], host["canvas"], host["noises"])
+        host_out.copy_(eng.run(), non_blocking=True)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, n):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(steps):
+        for _ in range(n):
             fn()
         e1.record()
         barrier()
@@ -224,34 +250,107 @@ def run_ours(args):
             ms = float(t.item())
         return ms
 
-    for _ in range(args.warmup if args.skip_e2e else max(args.warmup, 3)):
+    # warm-up: two eager passes (they also count the launches of a step), the capture, then graph replays
+    l0, g0 = lib.launches(), lib.load().spgan_gemm_launch_count()
+    step_resident()
+    l1, g1 = lib.launches(), lib.load().spgan_gemm_launch_count()
+    for _ in range(max(warmup, 3) + 2):
         step_resident()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    SF.profile_gemm(True)
-    l0, g0 = lib.launches(), lib.load().spgan_gemm_launch_count()
-    ms_total = timed(step_resident, args.steps)
-    l1, g1 = lib.launches(), lib.load().spgan_gemm_launch_count()
-    gemm_stats = SF.profile_gemm(False)
+    ms_total = timed(step_resident, steps)
     clocks = sampler.stop() if sampler else None
-    ms_step = ms_total / args.steps
+    out = {"ms_step": ms_total / steps, "ms_total": ms_total, "launches": l1 - l0, "gemm_launches": int(g1 - g0),
+           "clocks": clocks, "h2d": h2d, "d2h": d2h, "n_pos": n_pos, "plan": pl, "graphs": graphs,
+           "canvas_mb": host["canvas"].numel() * 4 // 2 ** 20}
+    if e2e:
+        step_e2e()
+        out["ms_e2e"] = timed(step_e2e, steps) / steps
+    if profile:
+        # per-launch CUDA-event times need eager launches on one stream (events cannot be recorded inside a graph replay,
+        # and concurrent branches would overlap the brackets): one extra eager step of the same work after the timed region
+        prof = (panorama.ShardedPanoramaEngine(gen, pl, B, dev, rank, world, streams=1, use_graph=False) if sharded
+                else panorama.PanoramaEngine(gen, pl, B, dev, streams=1, use_graph=False))
+        prof.load(host["gl"], host["canvas"], host["noises"])
+        prof.run()
+        SF.profile_gemm(True)
+        ms_prof = timed(prof.run, 1)
+        out["gemm_stats"] = SF.profile_gemm(False)
+        out["ms_eager_1stream"] = ms_prof
+        if args.profile_calls:
+            SF.profile_calls(True)
+            ms_calls = timed(prof.run, 1)
+            cm = {k: [round(v[0], 3), v[1]] for k, v in sorted(SF.profile_calls(False).items(), key=lambda kv: -kv[1][0])}
+            cm["_step_total_ms"] = ms_calls
+            out["call_ms"] = cm
+        del prof
+    del eng
+    torch.cuda.empty_cache()
+    return out
+
+
+def parse_modes(text):
+    if not text:
+        return None
+    m = [int(v) for v in text.split(",")]
+    if len(m) != 8:
+        raise SystemExit("--ts-precision needs 8 comma-separated modes")
+    return m
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import spgan_b200.functional as SF
+    import spgan_b200.lib as lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    lib.require_device()  # no fallback: fail loudly if the extension or a B200 is missing
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    SF.set_precision(args.precision)
+
+    B = args.batch
+    sharded = args.workload == "pano768"
+    th, tw = (768, 1536) if sharded else (384, 768)
+    modes = parse_modes(args.ts_precision)
+    warm = args.warmup if args.skip_e2e else max(args.warmup, 3)
+    m = measure_panorama(args, dev, world, rank, local, th, tw, B, sharded, args.steps, warm, layer_precision=modes,
+                         profile=not args.skip_profile, e2e=not args.skip_e2e)
+    pl, n_pos = m["plan"], m["n_pos"]
+    ms_step = m["ms_step"]
     jobs = B if sharded else world * B  # sharded: the ranks share ONE batch of panoramas
     value = jobs / (ms_step / 1000.0)
-
-    call_ms = None
-    if args.profile_calls:
-        SF.profile_calls(True)
-        ms_prof = timed(step_resident, 1)
-        call_ms = {k: [round(v[0], 3), v[1]] for k, v in sorted(SF.profile_calls(False).items(), key=lambda kv: -kv[1][0])}
-        call_ms["_step_total_ms"] = ms_prof
-
-    if args.skip_e2e:
-        ms_e2e = float("nan")
-    else:
-        step_e2e()
-        ms_e2e = timed(step_e2e, args.steps) / args.steps
+    ms_e2e = m.get("ms_e2e", float("nan"))
     e2e_value = jobs / (ms_e2e / 1000.0)
+
+    # optional second point: the 2-MMA fp16 split on the last texture layers (stated looser bound, tests/test_gpu_generator.py)
+    fast = None
+    if args.fast_tail and not sharded and modes is None and args.precision == 1 and not args.skip_e2e:
+        fm = [1, 1, 1, 1, 1, 3, 3, 3]
+        f = measure_panorama(args, dev, world, rank, local, th, tw, B, False, args.steps, 3, layer_precision=fm, profile=True,
+                             e2e=False)
+        gs = f.get("gemm_stats")
+        fast = {"layer_precision": fm, "value": jobs / (f["ms_step"] / 1000.0), "unit": UNIT, "ms_per_step": f["ms_step"],
+                "gemm_algorithmic_tflops": gs["flops"] / (gs["ms"] / 1000.0) / 1e12 if gs and gs["ms"] > 0 else None,
+                "note": "texture layers 5-7 (73 % of the FLOPs) issue 2 MMAs per product instead of 3; generator output within "
+                        "7e-4 of the reference (max-abs over peak) instead of 5e-4 — reported beside the headline, not as it"}
+
+    # strong-scaling point of BASELINE configs[3] in the same line: one batch of 768x1536 panoramas, lattice sharded
+    pano768 = None
+    if not sharded and not args.no_pano768 and not args.skip_e2e:
+        p7 = measure_panorama(args, dev, world, rank, local, 768, 1536, args.pano768_batch, True, max(1, args.steps // 2 + 1), 1,
+                              layer_precision=modes, profile=False, e2e=False)
+        pano768 = {"metric": "panoramas_per_sec_768x1536_generator_forward_lattice_sharded",
+                   "value": args.pano768_batch / (p7["ms_step"] / 1000.0), "unit": UNIT, "n_gpus": world,
+                   "ms_per_step": p7["ms_step"], "scaling": "strong", "batch": args.pano768_batch,
+                   "positions": p7["n_pos"], "collective": "one all-gather of the finished patches per step" if world > 1 else "none (1 rank)",
+                   "clocks": p7["clocks"]}
 
     # second half of BASELINE.json's metric ("... & train img/s"): the train workload, same process, same ranks
     train = None
@@ -263,58 +362,73 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    peaks = {}
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            peaks = json.load(f)
-    except Exception:
-        pass
+    peaks = load_peaks()
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)"
-    ach = gemm_stats["flops"] / (gemm_stats["ms"] / 1000.0) / 1e12 if gemm_stats["ms"] > 0 else 0.0
-    issued = {1: 3, 2: 1, 0: 0}[args.precision]
-    roofline = {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit-GEMM modulated conv)", "achieved": ach,
-                "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf if peak_tf else None, "traffic": 1346227712,
-                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the dominant launch (TS layer 7, 32x103x103 lattice, 2.95 ms, "
-                                "24 % of the step) from the ncu --set full capture in profiles/r1b_ncu_full_pano_before_im2col.txt "
-                                "(launch 9): 716.5 MB + 629.7 MB against 1372 MB algorithmic (695 MB packed A + 9 MB weights + 668 MB output)",
-                "peak_source": peak_src, "launches_timed": gemm_stats["launches"], "avg_launch_ms": gemm_stats["ms"] / max(gemm_stats["launches"], 1),
-                "share_of_step": gemm_stats["ms"] / (ms_total if ms_total else 1.0),
-                "note": "achieved = algorithmic conv FLOPs (2*B*Ho*Wo*Cout*Cin*k^2, valid outputs, real channels) / CUDA-event "
-                        "time of the launches; bf16x3 mode issues %dx that many tensor-core FLOPs" % issued}
-
-    shapes = sorted(gemm_stats.get("shapes", {}).items(), key=lambda kv: -kv[1][0])
-    roofline["by_shape"] = [{"shape": k, "ms_per_step": round(v[0] / args.steps, 3), "launches_per_step": v[2] // args.steps,
-                             "algorithmic_tflops": round(v[1] / (v[0] / 1000.0) / 1e12, 1) if v[0] > 0 else None}
-                            for k, v in shapes[:24]]
+    gemm_stats = m.get("gemm_stats")
+    roofline = None
+    if gemm_stats:
+        ach = gemm_stats["flops"] / (gemm_stats["ms"] / 1000.0) / 1e12 if gemm_stats["ms"] > 0 else 0.0
+        traffic, traffic_note = ncu_traffic()
+        roofline = {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit-GEMM modulated conv)", "achieved": ach,
+                    "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf if peak_tf else None, "traffic": traffic,
+                    "traffic_note": traffic_note, "peak_source": peak_src, "launches_timed": gemm_stats["launches"],
+                    "avg_launch_ms": gemm_stats["ms"] / max(gemm_stats["launches"], 1),
+                    "share_of_step": gemm_stats["ms"] / (m["ms_eager_1stream"] if m.get("ms_eager_1stream") else 1.0),
+                    "note": "achieved = algorithmic conv FLOPs (2*B*Ho*Wo*Cout*Cin*k^2, valid outputs, real channels) / CUDA-event "
+                            "time of the launches, taken from ONE eager single-stream step run right after the timed region (the timed "
+                            "steps are CUDA-graph replays with concurrent branches, which cannot be bracketed per launch); mode %d "
+                            "issues %dx that many tensor-core FLOPs" % (args.precision, ISSUED[args.precision])}
+        shapes = sorted(gemm_stats.get("shapes", {}).items(), key=lambda kv: -kv[1][0])
+        roofline["by_shape"] = [{"shape": k, "ms_per_step": round(v[0], 3), "launches_per_step": v[2],
+                                 "algorithmic_tflops": round(v[1] / (v[0] / 1000.0) / 1e12, 1) if v[0] > 0 else None}
+                                for k, v in shapes[:24]]
+    per_gpu_patches = B * (-(-n_pos // world) if sharded else n_pos)
     out = {
         "metric": METRIC.replace("384x768", "%dx%d" % (th, tw)) + ("_lattice_sharded" if sharded else ""), "value": value,
         "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None,
-        "dtype": {0: "fp32 (SIMT)", 1: "fp32-equivalent (bf16x3 split on tcgen05, fp32 accumulate)", 2: "bf16 (tcgen05, fp32 accumulate)"}[args.precision],
+        "dtype": DTYPES[args.precision] if modes is None else "per-layer modes %s" % modes,
         "data": "synthetic",
         "config": {"workload": "SP-GAN generator forward batch %d at %dx%d (close-loop, %d patch positions x %d patches of 101x101 per step%s), "
                                "random-init configs/model/spgan.yaml, synthetic latents" % (
                                    B, th, tw, n_pos, B, ", lattice positions sharded over the ranks + one all-gather of the patches" if sharded else ""),
-                   "batch_per_gpu": B, "patches_per_step_per_gpu": B * (-(-n_pos // world) if sharded else n_pos), "l2": "inputs and activations larger than L2 (latent canvas %d MB, activations > 1 GB per patch batch)" % (host["canvas"].numel() * 4 // 2 ** 20),
-                   "precision_mode": args.precision,
-                   "algorithmic_tflop_per_step_per_gpu": B * (-(-n_pos // world) if sharded else n_pos) * PATCH_GFLOP / 1000.0},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
-        "gpu_launches": l1 - l0, "tcgen05_gemm_launches": int(g1 - g0),
+                   "batch_per_gpu": B, "patches_per_step_per_gpu": per_gpu_patches,
+                   "l2": "inputs and activations larger than L2 (latent canvas %d MB, > 1 GB of operands per patch batch)" % m["canvas_mb"],
+                   "precision_mode": args.precision, "ts_layer_precision": modes,
+                   "execution": "one CUDA graph per step, lattice positions on %d concurrent branches" % args.streams if m["graphs"]
+                                else "eager launches, %d streams" % args.streams,
+                   "algorithmic_tflop_per_step_per_gpu": per_gpu_patches * PATCH_GFLOP / 1000.0},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": m["d2h"], "ms_per_step": ms_e2e},
+        "gpu_launches": m["launches"] * args.steps, "tcgen05_gemm_launches": m["gemm_launches"] * args.steps,
         "achieved_model_tflops": jobs * n_pos * PATCH_GFLOP / 1000.0 / (ms_step / 1000.0),
-        "clocks": clocks, "roofline": roofline,
+        "clocks": m["clocks"], "roofline": roofline,
     }
-    if call_ms is not None:
-        out["call_ms"] = call_ms
+    if "call_ms" in m:
+        out["call_ms"] = m["call_ms"]
+    if fast is not None:
+        out["fast_tail"] = fast
+    if pano768 is not None:
+        out["pano768"] = pano768
     if train is not None:
         out["train"] = train
     if not args.no_cpu_baseline and not sharded:
-        rate, threads, dt, total = cpu_reference_rate(args.cpu_sample_patches)
-        out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-                               "sample": "B=1, first %d of %d patch positions of one 384x768 panorama (%.1f s), oracle port of the reference's PyTorch CPU path" % (args.cpu_sample_patches, total, dt)}
+        out["cpu_baseline"] = cpu_baseline_object(args)
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def ncu_traffic():
+    """dram bytes per launch of the dominant GEMM launch, read from the committed ncu --set full summary of the final
+    kernels (profiles/r2_ncu_full_pano.json, written by tools/ncu_summary.py from the capture)."""
+    path = os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")
+    try:
+        with open(path) as f:
+            t = json.load(f)
+        return t["dram_bytes_per_launch"], "dram__bytes_read.sum + dram__bytes_write.sum of %s from %s" % (t["launch"], t["source"])
+    except Exception:
+        return None, "no ncu --set full capture of the final kernels is committed yet"
 
 
 # ------------------------------------------------------------------------------------------------ train workload

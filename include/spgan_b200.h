@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SPGAN_ABI_VERSION 1
+#define SPGAN_ABI_VERSION 2
 #define SPGAN_MAX_TAPS 49
 
 int spgan_abi_version(void);
@@ -128,7 +128,8 @@ typedef struct SpganConvPass {
   float out_scale;
   int32_t act;                    /* 0 = none, 1 = leaky relu */
   float act_alpha, act_gain;
-  int32_t precision;              /* 0 = fp32 SIMT, 1 = bf16x3 split on tcgen05 (fp32-equivalent), 2 = bf16 on tcgen05 */
+  int32_t precision;              /* 0 = fp32 SIMT, 1 = bf16x3 split on tcgen05 (fp32-equivalent), 2 = bf16 on tcgen05,
+                                     3 = fp16x2 on tcgen05 (fp16 hi+lo activations x fp16 weights, relative error ~2^-12) */
   int64_t out_cstride;            /* elements between output channels; 0 = out_H*out_W (dense NCHW).  A larger stride
                                      lets the parity passes of a transposed conv write polyphase planes
                                      (B, Cout, s*s, Hq, Wq) instead of scattering with stride s (see spgan_upblur_act) */
@@ -164,13 +165,15 @@ int spgan_conv_wgrad(const SpganConvPass* p, float* dw, const float* g, const fl
  *   step s > 1 writes s*s polyphase planes, out [2][s*s][B*Hl*Wl][Cp]: lattice point (i, j) of phase py*s + px holds image
  *   pixel (i*s + py - pad_y0, j*s + px - pad_x0).  A strided conv (the discriminator's stride-2 convs, models/ops.py:175;
  *   the stride-3 conv behind the spherical gather, models/spgan_ops_gs.py:814) is then a stride-1 conv whose taps pick
- *   their phase plane. */
+ *   their phase plane.
+ *   fmt selects the 16-bit planes: 0 = bf16 hi/lo (precision 1 and 2), 1 = fp16 hi/lo (precision 3; values saturate at
+ *   +-65504). */
 int spgan_pack_act(uint16_t* out, const float* x, const float* in_mul, int B, int C, int H, int W, int Cp, int pad_y0,
-                   int pad_x0, int Hl, int Wl, int step, void* stream);
+                   int pad_x0, int Hl, int Wl, int step, int fmt, void* stream);
 /* spgan_pack_weight: w[o*ws_o + c*ws_c + tap_w[t]] fp32 -> out [2][ntaps][Cout][Cp] bf16 (merged == 0) or
  *   [2][1][Cout][ntaps*Cp] (merged != 0, k = t*Cp + c: the layout that pairs with spgan_sphere_pack). */
 int spgan_pack_weight(uint16_t* out, const float* w, int Cout, int Cin, int64_t ws_o, int64_t ws_c, int ntaps,
-                      const int32_t* tap_w, int Cp, int merged, void* stream);
+                      const int32_t* tap_w, int Cp, int merged, int fmt, void* stream);
 /* spgan_nchw_to_nhwc: (B, C, H, W) fp32 -> (B, H, W, C) fp32; staging copy that makes the spherical gather coalesced. */
 int spgan_nchw_to_nhwc(float* out, const float* x, int B, int C, int H, int W, void* stream);
 /* spgan_sphere_pack: the fused A-operand producer of the spherical modulated conv
@@ -184,7 +187,7 @@ int spgan_nchw_to_nhwc(float* out, const float* x, int B, int C, int H, int W, v
  *   with groups = B, so group g reads flat channels [g*(C+nc), (g+1)*(C+nc)) (for B > 1 that mixes samples); the host
  *   encodes exactly that mapping (or the per-sample concatenation) in the table. */
 int spgan_sphere_pack(uint16_t* out, const float* x_nhwc, const float* coords, const float* grid, const float* in_mul,
-                      const uint32_t* chan_map, int B, int C, int H, int W, int grid_batch, int Cp, void* stream);
+                      const uint32_t* chan_map, int B, int C, int H, int W, int grid_batch, int Cp, int fmt, void* stream);
 /* spgan_conv_gemm: the tcgen05 kernel.  `p` is a conv pass whose (H, W) are the LATTICE dims (Hl, Wl) of the packed
  *   activation, Cin is ignored (K per tap = kp, a multiple of 16), in_stride must be 1, tap_w is ignored (the packed
  *   weight is already in tap order) and precision must be 1 or 2.  a_packed [2][a_rows][kp], w_packed
@@ -196,6 +199,57 @@ int spgan_sphere_pack(uint16_t* out, const float* x_nhwc, const float* coords, c
 int spgan_conv_gemm(const SpganConvPass* p, float* y, const uint16_t* a_packed, int64_t a_rows, int kp,
                     const uint16_t* w_packed, const float* out_mul, const float* noise, const float* noise_w,
                     const float* bias, const float* residual, void* stream);
+/* spgan_conv_gemm_ex: the same kernel with every epilogue sink exposed.  Besides (or instead of) the NCHW fp32 tensor the
+ *   epilogue can write, from the accumulator it already holds channels-last (TMEM lane = pixel, column = channel):
+ *     - y with y_layout = 1: channels-last fp32, element (b, Y, X, o) at y[b*y_bstride + (Y*out_W + X)*Cout + o] (the
+ *       parity passes of the transposed conv write their polyphase planes this way for spgan_upblur_pack);
+ *     - y_packed: the NEXT conv's packed operand [2][y_packed_rows][y_packed_cols] (16-bit hi/lo planes in y_packed_fmt),
+ *       row (b*out_H + Y)*out_W + X, already multiplied by that conv's style modulation next_mul (B, Cout): what
+ *       spgan_pack_act would compute from the fp32 tensor, bit for bit, without the tensor or the pass;
+ *     - rgb_w / rgb_part: ToRGB (1x1 modulated conv without demodulation, models/spgan_ops.py:1563-1586) folded in: rgb_w
+ *       (B, rgb_n, Cout) = scale * w_rgb[j][o] * s_rgb[b][o]; every (N tile, epilogue half) writes its partial sum over
+ *       its columns to slot 2*tile_n + half of rgb_part (slots, B, rgb_n, out_H*out_W), slots =
+ *       spgan_conv_gemm_rgb_slots(p, a_rows); spgan_rgb_tail adds the slots in a fixed order (deterministic).
+ *   y may be NULL when another sink is present (the last texture layer is consumed by ToRGB alone).  The extra sinks need
+ *   Cout % 32 == 0 and exclude `residual`.  fmt is the operand format of a_packed / w_packed and must match
+ *   p->precision (0 for 1 and 2, 1 for 3). */
+typedef struct SpganGemmIO {
+  const uint16_t* a_packed;
+  int64_t a_rows;
+  int32_t kp;
+  int32_t fmt;
+  const uint16_t* w_packed;
+  const float* out_mul;
+  const float* noise;
+  const float* noise_w;
+  const float* bias;
+  const float* residual;
+  float* y;
+  int32_t y_layout;
+  int32_t rgb_n;
+  int64_t y_bstride;
+  uint16_t* y_packed;
+  const float* next_mul;
+  int64_t y_packed_rows;
+  int32_t y_packed_cols;
+  int32_t y_packed_fmt;
+  const float* rgb_w;
+  float* rgb_part;
+} SpganGemmIO;
+int spgan_conv_gemm_ex(const SpganConvPass* p, const SpganGemmIO* io, void* stream);
+int spgan_conv_gemm_rgb_slots(const SpganConvPass* p, int64_t a_rows);
+
+/* Channels-last tail of the upsampling StyledConv (same arithmetic as spgan_upblur_act): pp (batch, 4, Hq, Wq, channels)
+ * fp32 polyphase planes in channels-last order -> interleave + 3x3 FIR + noise + bias + leaky-ReLU * scale, multiplied by the
+ * next conv's style modulation next_mul (batch, channels) (may be NULL) and split into that conv's packed operand
+ * out [2][out_rows][Cp] (Cp == channels, row (b*oh + oy)*ow + ox, fmt as in spgan_pack_act). */
+int spgan_upblur_pack(uint16_t* out, const float* pp, const float* kernel, const float* noise, const float* noise_w,
+                      const float* bias, const float* next_mul, int64_t batch, int channels, int zh, int zw, int Hq, int Wq,
+                      int Cp, int64_t out_rows, int fmt, float alpha, float scale, void* stream);
+/* out (batch, rgb_n, plane) = sum_s part[s] + bias[j] + skip (ToRGB's bias and upsampled skip, models/spgan_ops.py:1576-1585);
+ * part (slots, batch, rgb_n, plane) from spgan_conv_gemm_ex; bias (rgb_n) and skip (batch, rgb_n, plane) may be NULL. */
+int spgan_rgb_tail(float* out, const float* part, int slots, const float* bias, const float* skip, int64_t batch, int rgb_n,
+                   int64_t plane, void* stream);
 /* Number of tcgen05 GEMM launches since load (the bench's gpu_launches evidence for the tensor path). */
 int64_t spgan_gemm_launch_count(void);
 

@@ -1,15 +1,27 @@
-"""TEST INFRASTRUCTURE ONLY (oracle/): import the real reference in THIS container.
+"""TEST INFRASTRUCTURE ONLY (oracle/): import the real reference.
 
-Installs the five in-process stubs of SURVEY.md §A.4 so that /root/reference (read-only,
-Python/PyTorch) can be imported and run on CPU without CUDA, easydict, lmdb or matplotlib.
-Nothing here is copied from the reference; nothing here travels to the GPU box except as
-the committed golden vectors that `oracle/make_golden.py` writes under tests/golden/.
+Installs the five in-process stubs of SURVEY.md §A.4 so that the reference (read-only, Python/PyTorch) can be
+imported and run on CPU without CUDA, easydict, lmdb or matplotlib.  The reference tree is looked up at
+$SPGAN_REFERENCE_ROOT, /root/reference (the build container) or oracle/_ref/reference (a staged copy made by
+`oracle/build_ref.py`: git-ignored, so no reference source enters the history, but it travels to the GPU box with the
+snapshot, where the parity tests and bench.py's reference arm run the real reference as the checker / CPU baseline).
 """
 import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("SPGAN_REFERENCE_ROOT", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+STAGED_ROOT = os.path.join(HERE, "_ref", "reference")
+
+
+def _find_root():
+    for cand in (os.environ.get("SPGAN_REFERENCE_ROOT"), "/root/reference", STAGED_ROOT):
+        if cand and os.path.isdir(os.path.join(cand, "models")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 
 
 class _AttrDict(dict):
@@ -46,8 +58,10 @@ def available():
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "models"))
 
 
-def install():
-    """Make `import models...`, `import coord_handler`, `import test_managers...` resolve to the reference."""
+def install(real_cuda=False):
+    """Make `import models...`, `import coord_handler`, `import test_managers...` resolve to the reference.
+    real_cuda=True keeps torch's CUDA entry points (the drop-in tests run the reference's generator and manager on the
+    GPU over the mirrored op modules); the default replaces them so that everything stays on the CPU."""
     import torch
     import torch.utils.cpp_extension as cpp_ext
 
@@ -73,15 +87,16 @@ def install():
             __import__(name)
         except Exception:
             sys.modules[name] = types.ModuleType(name)
-    torch.cuda.get_device_name = lambda *a, **k: "cpu-stub"
     cpp_ext.load = lambda *a, **k: types.SimpleNamespace()
-    torch.Tensor.cuda = lambda self, *a, **k: self
+    if not real_cuda:
+        torch.cuda.get_device_name = lambda *a, **k: "cpu-stub"
+        torch.Tensor.cuda = lambda self, *a, **k: self
     return _AttrDict
 
 
-def load_config():
+def load_config(real_cuda=False):
     import yaml
-    EasyDict = install()
+    EasyDict = install(real_cuda)
     with open(os.path.join(REFERENCE_ROOT, "configs/model/spgan.yaml")) as f:
         config = EasyDict(yaml.safe_load(f))
     config.var = EasyDict()

@@ -23,6 +23,7 @@ namespace {
 constexpr int FWD_THREADS = 320;  // warp 0 producer, warp 1 MMA issuer, warps 2..9 epilogue
 
 struct GemmParams {
+  int32_t B;           // samples
   int32_t rows;        // M extent: B * Hl * Wl lattice points (tiled A loads) or B * My * Mx outputs (im2col A loads)
   int32_t Hl, Wl;      // row decode: points per sample = Hl * Wl, Wl per row (= My, Mx in im2col mode)
   int32_t My, Mx;      // valid lattice extent
@@ -39,6 +40,28 @@ struct GemmParams {
   float out_scale;
   int32_t act;
   float act_alpha, act_gain;
+  int32_t f16;             // operand format: 0 = bf16 planes, 1 = fp16 planes (instruction descriptor A/B format)
+  // ---- output sinks (any combination; y may be null)
+  int32_t y_nhwc;          // 0: y is NCHW fp32 (out_cstride between channels), 1: y is NHWC fp32 (channel fastest)
+  int64_t y_bstride;       // NHWC: elements between samples
+  int64_t pk_rows;         // packed sink: rows per 16-bit plane (the lo plane starts pk_rows * pk_cols elements later)
+  int32_t pk_cols;         // packed sink: leading dimension (the next conv's Cp)
+  int32_t pk_f16;          // packed sink: 0 = bf16 hi/lo, 1 = fp16 hi/lo
+  int32_t rgb_n;           // ToRGB sink: number of RGB channels (3) or 0
+};
+
+// Everything the epilogue may read or write besides the accumulator.
+struct GemmSinks {
+  float* y;                 // fp32 output (NCHW or NHWC), may be null
+  const float* out_mul;     // (B, Cout) demodulation
+  const float* noise;       // (B, out_H, out_W)
+  const float* noise_w;     // (1)
+  const float* bias;        // (Cout)
+  const float* residual;    // same layout as an NCHW y
+  uint16_t* y_packed;       // the next conv's A operand [2][pk_rows][pk_cols], row (b*out_H + Y)*out_W + X; may be null
+  const float* next_mul;    // (B, Cout) style modulation of the next conv, folded into y_packed; may be null
+  const float* rgb_w;       // (B, rgb_n, Cout) per-sample modulated ToRGB weights; null = sink off
+  float* rgb_part;          // (2 * n_tiles, B, rgb_n, out_H*out_W) partial sums, one slot per (N tile, epilogue half)
 };
 
 // ------------------------------------------------------------------------------------------------ GEMM kernel
@@ -48,7 +71,9 @@ struct GemmParams {
 template <int kPasses, int kBlockN>
 struct GemmSmem {
   static constexpr int kBTileBytes = kBlockN * GEMM_BLOCK_K * 2;
-  static constexpr int kStageBytes = (kPasses == 3 ? 2 : 1) * (A_TILE_BYTES + kBTileBytes);
+  static constexpr int kAPlanes = kPasses >= 2 ? 2 : 1;  // 2 passes: (A_hi + A_lo) * B_hi; 3 passes add A_hi * B_lo
+  static constexpr int kBPlanes = kPasses == 3 ? 2 : 1;
+  static constexpr int kStageBytes = kAPlanes * A_TILE_BYTES + kBPlanes * kBTileBytes;
   static constexpr int kStages = (196608 / kStageBytes) < 4 ? (196608 / kStageBytes) : 4;
   static constexpr int kTileBytes = kStageBytes * kStages;
   static constexpr int kBarrierBytes = 256;
@@ -58,8 +83,13 @@ struct GemmSmem {
 template <int kPasses, int kBlockN>
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams gp,
-                 float* __restrict__ y, const float* __restrict__ out_mul, const float* __restrict__ noise,
-                 const float* __restrict__ noise_w, const float* __restrict__ bias, const float* __restrict__ residual) {
+                 const GemmSinks sk) {
+  float* __restrict__ y = sk.y;
+  const float* __restrict__ out_mul = sk.out_mul;
+  const float* __restrict__ noise = sk.noise;
+  const float* __restrict__ noise_w = sk.noise_w;
+  const float* __restrict__ bias = sk.bias;
+  const float* __restrict__ residual = sk.residual;
   using S = GemmSmem<kPasses, kBlockN>;
   constexpr int kStages = S::kStages;
   constexpr int kBTile = S::kBTileBytes;
@@ -125,26 +155,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_wait(empty_bar(stage), phase ^ 1u);
             const uint32_t sa = smem_base + stage * S::kStageBytes;
             mbar_arrive_expect_tx(full_bar(stage), S::kStageBytes);
+            const uint32_t sb = sa + S::kAPlanes * A_TILE_BYTES;
             if (gp.im2col) {
               const int img = b0 + gp.tap_img[t];
               tma_load_im2col(sa, &tmA, full_bar(stage), kb * GEMM_BLOCK_K, j0, i0, img, gp.tap_ox[t], gp.tap_oy[t]);
-              if (kPasses == 3) {
+              if (S::kAPlanes == 2)
                 tma_load_im2col(sa + A_TILE_BYTES, &tmA, full_bar(stage), kb * GEMM_BLOCK_K, j0, i0, img + gp.img_lo,
                                 gp.tap_ox[t], gp.tap_oy[t]);
-                tma_load_4d(sa + 2 * A_TILE_BYTES, &tmB, full_bar(stage), kb * GEMM_BLOCK_K, n0, t, 0);
-                tma_load_4d(sa + 2 * A_TILE_BYTES + kBTile, &tmB, full_bar(stage), kb * GEMM_BLOCK_K, n0, t, 1);
-              } else {
-                tma_load_4d(sa + A_TILE_BYTES, &tmB, full_bar(stage), kb * GEMM_BLOCK_K, n0, t, 0);
-              }
-            } else if (kPasses == 3) {
-              tma_load_3d(sa, &tmA, full_bar(stage), kb * GEMM_BLOCK_K, row, 0);
-              tma_load_3d(sa + A_TILE_BYTES, &tmA, full_bar(stage), kb * GEMM_BLOCK_K, row, 1);
-              tma_load_4d(sa + 2 * A_TILE_BYTES, &tmB, full_bar(stage), kb * GEMM_BLOCK_K, n0, t, 0);
-              tma_load_4d(sa + 2 * A_TILE_BYTES + kBTile, &tmB, full_bar(stage), kb * GEMM_BLOCK_K, n0, t, 1);
             } else {
               tma_load_3d(sa, &tmA, full_bar(stage), kb * GEMM_BLOCK_K, row, 0);
-              tma_load_4d(sa + A_TILE_BYTES, &tmB, full_bar(stage), kb * GEMM_BLOCK_K, n0, t, 0);
+              if (S::kAPlanes == 2) tma_load_3d(sa + A_TILE_BYTES, &tmA, full_bar(stage), kb * GEMM_BLOCK_K, row, 1);
             }
+            tma_load_4d(sb, &tmB, full_bar(stage), kb * GEMM_BLOCK_K, n0, t, 0);
+            if (S::kBPlanes == 2) tma_load_4d(sb + kBTile, &tmB, full_bar(stage), kb * GEMM_BLOCK_K, n0, t, 1);
             if (++stage == kStages) {
               stage = 0;
               phase ^= 1u;
@@ -164,7 +187,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int n0 = (tile % gp.n_tiles) * kBlockN;
         int n_eff = gp.Cout - n0;
         n_eff = n_eff > kBlockN ? kBlockN : ((n_eff + 15) & ~15);
-        const uint32_t idesc = umma_idesc_bf16(n_eff);
+        const uint32_t idesc = umma_idesc_16(n_eff, gp.f16 != 0);
         const int as = titer & 1;
         const uint32_t aphase = (uint32_t)(titer >> 1) & 1u;
         mbar_wait(tempty_bar(as), aphase ^ 1u);
@@ -176,7 +199,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t sa = smem_base + stage * S::kStageBytes;
           const uint32_t a_hi = sa;
           const uint32_t a_lo = sa + A_TILE_BYTES;
-          const uint32_t b_hi = sa + (kPasses == 3 ? 2 : 1) * A_TILE_BYTES;
+          const uint32_t b_hi = sa + S::kAPlanes * A_TILE_BYTES;
           const uint32_t b_lo = b_hi + kBTile;
           // the last K block of a tap may be partial (kp a multiple of 16, not of 64): TMA zero-fills the box, the MMAs
           // of the all-zero K steps are simply not issued
@@ -188,12 +211,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint64_t da_hi = umma_desc_sw128(a_hi + koff);
             const uint64_t db_hi = umma_desc_sw128(b_hi + koff);
             tc_mma_f16(d_tmem, da_hi, db_hi, idesc, (it > 0 || k > 0) ? 1u : 0u);
-            if (kPasses == 3) {
-              const uint64_t da_lo = umma_desc_sw128(a_lo + koff);
-              const uint64_t db_lo = umma_desc_sw128(b_lo + koff);
-              tc_mma_f16(d_tmem, da_hi, db_lo, idesc, 1u);
-              tc_mma_f16(d_tmem, da_lo, db_hi, idesc, 1u);
-            }
+            if (kPasses == 3) tc_mma_f16(d_tmem, da_hi, umma_desc_sw128(b_lo + koff), idesc, 1u);
+            if (kPasses >= 2) tc_mma_f16(d_tmem, umma_desc_sw128(a_lo + koff), db_hi, idesc, 1u);
           }
           tc_commit(empty_bar(stage));  // frees the smem stage once these MMAs have read it
           if (++stage == kStages) {
@@ -221,6 +240,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const float nw = has_noise ? __ldg(noise_w) : 0.f;
     const bool plain = !has_noise && bias == nullptr && residual == nullptr && !gp.act;
     const bool vec_ok = (gp.Cout & 3) == 0;  // per-channel rows start 16-byte aligned
+    // legacy sink: one NCHW fp32 tensor.  Anything else (channels-last fp32, the next conv's packed operand, ToRGB
+    // partial sums) goes through the general path below, which the host only selects when Cout is a multiple of 32.
+    const bool nchw_only = y != nullptr && !gp.y_nhwc && sk.y_packed == nullptr && sk.rgb_w == nullptr;
     int titer = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++titer) {
       const int m0 = (tile / gp.n_tiles) * GEMM_BLOCK_M;
@@ -246,6 +268,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int64_t ybase = (int64_t)b * gp.Cout * ostride_c + pix;
       const float nz = (valid && has_noise) ? nw * __ldg(noise + (int64_t)b * oplane + pix) : 0.f;
       const float* om = out_mul ? out_mul + (int64_t)b * gp.Cout : nullptr;
+      float rgb[3] = {0.f, 0.f, 0.f};
 
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
@@ -275,35 +298,130 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               f[k] = (om ? __ldg(om + oc) : 1.f) * gp.out_scale;
             }
           }
-          float* yp = y + ybase + (int64_t)o0 * ostride_c;
-          if (plain && full) {
+          if (nchw_only) {
+            float* yp = y + ybase + (int64_t)o0 * ostride_c;
+            if (plain && full) {
 #pragma unroll
-            for (int k = 0; k < 32; ++k) {
-              *yp = v[k] * f[k];
-              yp += ostride_c;
+              for (int k = 0; k < 32; ++k) {
+                *yp = v[k] * f[k];
+                yp += ostride_c;
+              }
+            } else {
+              // rare terms: all loads of a 16-column half are issued before the first dependent use
+              const float* rp = residual ? residual + ybase + (int64_t)o0 * ostride_c : nullptr;
+#pragma unroll
+              for (int h0 = 0; h0 < 32; h0 += 16) {
+                float bv[16], rv[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                  const int o = o0 + h0 + k;
+                  const int oc = o < gp.Cout ? o : gp.Cout - 1;
+                  bv[k] = bias ? __ldg(bias + oc) : 0.f;
+                  rv[k] = (rp && o < gp.Cout) ? __ldg(rp + (int64_t)(h0 + k) * ostride_c) : 0.f;
+                }
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                  float r = v[h0 + k] * f[h0 + k] + nz + bv[k];
+                  if (gp.act) r = (r > 0.f ? r : r * gp.act_alpha) * gp.act_gain;
+                  if (o0 + h0 + k < gp.Cout) yp[(int64_t)(h0 + k) * ostride_c] = r + rv[k];
+                }
+              }
             }
           } else {
-            // rare terms: all loads of a 16-column half are issued before the first dependent use
-            const float* rp = residual ? residual + ybase + (int64_t)o0 * ostride_c : nullptr;
+            // ---- general sinks (host guarantees Cout % 32 == 0, so every block is full and 16-byte aligned)
+            if (bias) {
+              const float4* bp = reinterpret_cast<const float4*>(bias + o0);
 #pragma unroll
-            for (int h0 = 0; h0 < 32; h0 += 16) {
-              float bv[16], rv[16];
-#pragma unroll
-              for (int k = 0; k < 16; ++k) {
-                const int o = o0 + h0 + k;
-                const int oc = o < gp.Cout ? o : gp.Cout - 1;
-                bv[k] = bias ? __ldg(bias + oc) : 0.f;
-                rv[k] = (rp && o < gp.Cout) ? __ldg(rp + (int64_t)(h0 + k) * ostride_c) : 0.f;
+              for (int k = 0; k < 8; ++k) {
+                const float4 t4 = __ldg(bp + k);
+                v[4 * k] = v[4 * k] * f[4 * k] + nz + t4.x;  // same association as the NCHW path: bit-identical values
+                v[4 * k + 1] = v[4 * k + 1] * f[4 * k + 1] + nz + t4.y;
+                v[4 * k + 2] = v[4 * k + 2] * f[4 * k + 2] + nz + t4.z;
+                v[4 * k + 3] = v[4 * k + 3] * f[4 * k + 3] + nz + t4.w;
               }
+            } else {
 #pragma unroll
-              for (int k = 0; k < 16; ++k) {
-                float r = v[h0 + k] * f[h0 + k] + nz + bv[k];
-                if (gp.act) r = (r > 0.f ? r : r * gp.act_alpha) * gp.act_gain;
-                if (o0 + h0 + k < gp.Cout) yp[(int64_t)(h0 + k) * ostride_c] = r + rv[k];
+              for (int k = 0; k < 32; ++k) v[k] = v[k] * f[k] + nz + 0.f;
+            }
+            if (gp.act) {
+#pragma unroll
+              for (int k = 0; k < 32; ++k) v[k] = (v[k] > 0.f ? v[k] : v[k] * gp.act_alpha) * gp.act_gain;
+            }
+            if (y != nullptr) {
+              if (gp.y_nhwc) {
+                float4* yp4 = reinterpret_cast<float4*>(y + (int64_t)b * gp.y_bstride + pix * gp.Cout + o0);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) yp4[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+              } else {
+                float* yp = y + ybase + (int64_t)o0 * ostride_c;
+#pragma unroll
+                for (int k = 0; k < 32; ++k) yp[(int64_t)k * ostride_c] = v[k];
+              }
+            }
+            if (sk.rgb_w != nullptr) {
+              // ToRGB (1x1 modulated conv without demodulation, models/spgan_ops.py:1563-1586) folded into the producer
+#pragma unroll
+              for (int j = 0; j < 3; ++j) {
+                if (j < gp.rgb_n) {
+                  const float4* wp = reinterpret_cast<const float4*>(sk.rgb_w + ((int64_t)b * gp.rgb_n + j) * gp.Cout + o0);
+                  float a = 0.f;
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) {
+                    const float4 t4 = __ldg(wp + k);
+                    a += v[4 * k] * t4.x + v[4 * k + 1] * t4.y + v[4 * k + 2] * t4.z + v[4 * k + 3] * t4.w;
+                  }
+                  rgb[j] += a;
+                }
+              }
+            }
+            if (sk.y_packed != nullptr) {
+              // the next conv's A operand: style modulation of THAT conv, then the 16-bit hi/lo split (what spgan_pack_act
+              // would compute from the fp32 tensor, bit for bit)
+              if (sk.next_mul) {
+                const float4* mp = reinterpret_cast<const float4*>(sk.next_mul + (int64_t)b * gp.Cout + o0);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                  const float4 t4 = __ldg(mp + k);
+                  v[4 * k] *= t4.x;
+                  v[4 * k + 1] *= t4.y;
+                  v[4 * k + 2] *= t4.z;
+                  v[4 * k + 3] *= t4.w;
+                }
+              }
+              const int64_t prow = (int64_t)b * oplane + pix;
+              uint16_t* ph = sk.y_packed + prow * gp.pk_cols + o0;
+              uint16_t* pl = ph + gp.pk_rows * (int64_t)gp.pk_cols;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                uint32_t hw[4], lw[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  uint16_t h0, l0, h1, l1;
+                  if (gp.pk_f16) {
+                    split16<true>(v[8 * q + 2 * u], h0, l0);
+                    split16<true>(v[8 * q + 2 * u + 1], h1, l1);
+                  } else {
+                    split16<false>(v[8 * q + 2 * u], h0, l0);
+                    split16<false>(v[8 * q + 2 * u + 1], h1, l1);
+                  }
+                  hw[u] = pack2x16(h0, h1);
+                  lw[u] = pack2x16(l0, l1);
+                }
+                reinterpret_cast<uint4*>(ph)[q] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                reinterpret_cast<uint4*>(pl)[q] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
               }
             }
           }
         }
+      }
+      if (sk.rgb_w != nullptr && valid) {
+        // one slot per (N tile, epilogue half): every (slot, b, channel, pixel) is written exactly once, and
+        // spgan_rgb_tail sums the slots in a fixed order (deterministic, unlike atomics)
+        const int slot = (tile % gp.n_tiles) * 2 + half;
+        float* rp = sk.rgb_part + (((int64_t)slot * gp.B + b) * gp.rgb_n) * oplane + pix;
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+          if (j < gp.rgb_n) rp[(int64_t)j * oplane] = rgb[j];
       }
       tc_fence_before();
       __syncwarp();
@@ -324,7 +442,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // pixels, writes coalesced along channels (bf16x2 per lane, 128 bytes per warp).  With step s > 1 the lattice point
 // (i, j) of phase (py, px) holds source pixel (i*s + py - pad_y, j*s + px - pad_x): a strided conv becomes a stride-1
 // conv whose taps pick their phase plane (rows [ph * B*Hl*Wl, (ph+1) * B*Hl*Wl) of the packed matrix).
-__global__ void __launch_bounds__(256) pack_act_kernel(__nv_bfloat16* __restrict__ out, const float* __restrict__ x,
+template <bool kF16>
+__global__ void __launch_bounds__(256) pack_act_kernel(uint16_t* __restrict__ out, const float* __restrict__ x,
                                                       const float* __restrict__ in_mul, int B, int C, int H, int W,
                                                       int Cp, int pad_y, int pad_x, int Hl, int Wl, int step) {
   // (pad_y, pad_x) = top/left offset of the image inside the (Hl, Wl) lattice
@@ -362,19 +481,19 @@ __global__ void __launch_bounds__(256) pack_act_kernel(__nv_bfloat16* __restrict
   __syncthreads();
   const int cpair = threadIdx.x & 31, prow = threadIdx.x >> 5;
   const int64_t rows_total = (int64_t)step * step * B * plane_l;
-  __nv_bfloat16* out_lo = out + rows_total * Cp;
+  uint16_t* out_lo = out + rows_total * Cp;
 #pragma unroll
   for (int pp = prow; pp < 64; pp += 8) {
     const int q = q0 + pp;
     if (q >= plane_l) break;
     const float v0 = tile[2 * cpair][pp], v1 = tile[2 * cpair + 1][pp];
-    __nv_bfloat16 h0, l0, h1, l1;
-    split_bf16(v0, h0, l0);
-    split_bf16(v1, h1, l1);
+    uint16_t h0, l0, h1, l1;
+    split16<kF16>(v0, h0, l0);
+    split16<kF16>(v1, h1, l1);
     if (c0 + 2 * cpair >= Cp) continue;  // Cp is a multiple of 16: the last channel tile may be partial
     const int64_t off = (((int64_t)ph * B + b) * plane_l + q) * Cp + c0 + 2 * cpair;
-    *reinterpret_cast<__nv_bfloat162*>(out + off) = __halves2bfloat162(h0, h1);
-    *reinterpret_cast<__nv_bfloat162*>(out_lo + off) = __halves2bfloat162(l0, l1);
+    *reinterpret_cast<uint32_t*>(out + off) = pack2x16(h0, h1);
+    *reinterpret_cast<uint32_t*>(out_lo + off) = pack2x16(l0, l1);
   }
 }
 
@@ -383,7 +502,8 @@ struct TapList {
 };
 
 // out[plane][t][o][c] (or [plane][o][t*Cp + c] when merged); one thread per (t, o, c) element, c fastest.
-__global__ void __launch_bounds__(256) pack_weight_kernel(__nv_bfloat16* __restrict__ out, const float* __restrict__ w,
+template <bool kF16>
+__global__ void __launch_bounds__(256) pack_weight_kernel(uint16_t* __restrict__ out, const float* __restrict__ w,
                                                          int Cout, int Cin, int64_t ws_o, int64_t ws_c, int ntaps,
                                                          TapList taps, int Cp, int merged) {
   const int64_t total = (int64_t)ntaps * Cout * Cp;
@@ -395,8 +515,8 @@ __global__ void __launch_bounds__(256) pack_weight_kernel(__nv_bfloat16* __restr
     const int t = (int)(r / Cout);
     float v = 0.f;
     if (c < Cin) v = __ldg(w + (int64_t)o * ws_o + (int64_t)c * ws_c + taps.w[t]);
-    __nv_bfloat16 hi, lo;
-    split_bf16(v, hi, lo);
+    uint16_t hi, lo;
+    split16<kF16>(v, hi, lo);
     const int64_t dst = merged ? ((int64_t)o * ntaps + t) * Cp + c : idx;
     out[dst] = hi;
     out[total + dst] = lo;
@@ -458,7 +578,8 @@ __device__ __forceinline__ TapCorners tap_corners(const float* __restrict__ grid
 // quirk lives there), so the inner loop has no integer divisions.  The corner indices and weights are computed once
 // per source sample; corner reads are coalesced over channels in the NHWC staging copy and each lane writes one bf16x2
 // to the hi plane and one to the lo plane (128 B per warp and plane).
-__global__ void __launch_bounds__(256) sphere_pack_kernel(__nv_bfloat16* __restrict__ out, const float* __restrict__ xh,
+template <bool kF16>
+__global__ void __launch_bounds__(256) sphere_pack_kernel(uint16_t* __restrict__ out, const float* __restrict__ xh,
                                                          const float* __restrict__ coords, const float* __restrict__ grid,
                                                          const float* __restrict__ in_mul,
                                                          const uint32_t* __restrict__ chan_map, int B, int C, int nc,
@@ -481,7 +602,7 @@ __global__ void __launch_bounds__(256) sphere_pack_kernel(__nv_bfloat16* __restr
     TapCorners cn;
     cn.o_nw = cn.o_ne = cn.o_sw = cn.o_se = 0;
     cn.w_nw = cn.w_ne = cn.w_sw = cn.w_se = 0.f;
-    __nv_bfloat16* orow = out + wid * Cp;  // row (g, p), columns [t*Cp, (t+1)*Cp): wid = (g*HW + p)*9 + t
+    uint16_t* orow = out + wid * Cp;  // row (g, p), columns [t*Cp, (t+1)*Cp): wid = (g*HW + p)*9 + t
     const uint32_t* mrow = chan_map + (int64_t)g * Cp;
     const float* mulrow = in_mul ? in_mul + (int64_t)g * Ct : nullptr;
     for (int k0 = 2 * lane; k0 < Cp; k0 += 64) {
@@ -523,11 +644,11 @@ __global__ void __launch_bounds__(256) sphere_pack_kernel(__nv_bfloat16* __restr
         }
         v[u] = val;
       }
-      __nv_bfloat16 h0, l0, h1, l1;
-      split_bf16(v[0], h0, l0);
-      split_bf16(v[1], h1, l1);
-      *reinterpret_cast<__nv_bfloat162*>(orow + k0) = __halves2bfloat162(h0, h1);
-      *reinterpret_cast<__nv_bfloat162*>(orow + plane_elems + k0) = __halves2bfloat162(l0, l1);
+      uint16_t h0, l0, h1, l1;
+      split16<kF16>(v[0], h0, l0);
+      split16<kF16>(v[1], h1, l1);
+      *reinterpret_cast<uint32_t*>(orow + k0) = pack2x16(h0, h1);
+      *reinterpret_cast<uint32_t*>(orow + plane_elems + k0) = pack2x16(l0, l1);
     }
   }
 }
@@ -538,8 +659,8 @@ __global__ void __launch_bounds__(256) sphere_pack_kernel(__nv_bfloat16* __restr
 // shuffle), the channel map and the modulation are decoded once per pixel, and per tap all 8 * KITER corner loads of a
 // lane are issued before the first use.  The general kernel above pays three dependent global latencies per
 // (pixel, tap) with 16 warps per SM and sat at ~15 % of the HBM write roofline.
-template <int KITER>
-__global__ void __launch_bounds__(256, 2) sphere_pack_shared_kernel(__nv_bfloat16* __restrict__ out,
+template <int KITER, bool kF16>
+__global__ void __launch_bounds__(256, 2) sphere_pack_shared_kernel(uint16_t* __restrict__ out,
                                                                 const float* __restrict__ xh,
                                                                 const float* __restrict__ coords,
                                                                 const float* __restrict__ grid,
@@ -582,7 +703,7 @@ __global__ void __launch_bounds__(256, 2) sphere_pack_shared_kernel(__nv_bfloat1
         mv[j][u] = (valid && mulrow) ? __ldg(mulrow + 2 * lane + 64 * j + u) : 1.f;
       }
     }
-    __nv_bfloat16* obase = out + wid * 9 * Cp;  // row (g, p): 9 taps x Cp columns
+    uint16_t* obase = out + wid * 9 * Cp;  // row (g, p): 9 taps x Cp columns
 #pragma unroll 1
     for (int t = 0; t < 9; ++t) {
       TapCorners cn;
@@ -609,7 +730,7 @@ __global__ void __launch_bounds__(256, 2) sphere_pack_shared_kernel(__nv_bfloat1
           cv[j][u][2] = valid ? __ldg(sp + cn.o_sw * st) : 0.f;
           cv[j][u][3] = valid ? __ldg(sp + cn.o_se * st) : 0.f;
         }
-      __nv_bfloat16* orow = obase + t * Cp;
+      uint16_t* orow = obase + t * Cp;
 #pragma unroll
       for (int j = 0; j < KITER; ++j) {
         float v[2];
@@ -625,12 +746,12 @@ __global__ void __launch_bounds__(256, 2) sphere_pack_shared_kernel(__nv_bfloat1
           }
           v[u] = val * mv[j][u];
         }
-        __nv_bfloat16 h0, l0, h1, l1;
-        split_bf16(v[0], h0, l0);
-        split_bf16(v[1], h1, l1);
+        uint16_t h0, l0, h1, l1;
+        split16<kF16>(v[0], h0, l0);
+        split16<kF16>(v[1], h1, l1);
         const int k0 = 2 * lane + 64 * j;
-        *reinterpret_cast<__nv_bfloat162*>(orow + k0) = __halves2bfloat162(h0, h1);
-        *reinterpret_cast<__nv_bfloat162*>(orow + plane_elems + k0) = __halves2bfloat162(l0, l1);
+        *reinterpret_cast<uint32_t*>(orow + k0) = pack2x16(h0, h1);
+        *reinterpret_cast<uint32_t*>(orow + plane_elems + k0) = pack2x16(l0, l1);
       }
     }
   }
@@ -643,8 +764,7 @@ std::atomic<long long>* launch_counter() {
 }
 
 template <int kPasses, int kBlockN>
-int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& gp, float* y, const float* out_mul,
-                const float* noise, const float* noise_w, const float* bias, const float* residual, cudaStream_t st) {
+int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& gp, const GemmSinks& sk, cudaStream_t st) {
   using S = GemmSmem<kPasses, kBlockN>;
   static bool attr_set[64] = {false};
   int dev = 0;
@@ -656,7 +776,7 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams
   }
   const int tiles = gp.m_tiles * gp.n_tiles;
   const int grid = tiles < SPGAN_NUM_SMS ? tiles : SPGAN_NUM_SMS;
-  conv_gemm_kernel<kPasses, kBlockN><<<grid, FWD_THREADS, S::kTotal, st>>>(tmA, tmB, gp, y, out_mul, noise, noise_w, bias, residual);
+  conv_gemm_kernel<kPasses, kBlockN><<<grid, FWD_THREADS, S::kTotal, st>>>(tmA, tmB, gp, sk);
   SPGAN_CHECK_LAUNCH("spgan_conv_gemm");
   launch_counter()->fetch_add(1);
   return 0;
@@ -676,38 +796,68 @@ int pick_block_n(int64_t m_tiles, int cout) {
   return (2 * tiles256 <= 3 * SPGAN_NUM_SMS && eff(128) > 1.33 * eff(256)) ? 128 : 256;
 }
 
+// M extent and N tile of a pass: shared by the launcher and by spgan_conv_gemm_rgb_slots.
+struct GemmShape {
+  bool im2col;
+  int phases;
+  int64_t rows_m;
+  int m_tiles, block_n, n_tiles;
+};
+
+GemmShape gemm_shape(const SpganConvPass* p, int64_t a_rows) {
+  GemmShape g;
+  const int64_t rows = (int64_t)p->B * p->H * p->W;
+  g.phases = rows > 0 ? (int)(a_rows / rows) : 1;
+  // im2col A loads whenever the pass has lattice points that are not outputs (unpadded 3x3 / 7x7 convs, padded convs on
+  // their bordered lattice, parity passes): M then runs over the B*My*Mx outputs only.  The bounding-box corner of a
+  // rank-4 map is an 8-bit field, hence the 128 limit; passes outside it keep the flat row-offset loads.
+  g.im2col = (p->My < p->H || p->Mx < p->W) && p->My <= p->H && p->Mx <= p->W && p->H - p->My <= 128 &&
+             p->W - p->Mx <= 128 && (int64_t)2 * g.phases * p->B < (1LL << 31);
+  g.rows_m = g.im2col ? (int64_t)p->B * p->My * p->Mx : rows;
+  g.m_tiles = (int)((g.rows_m + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M);
+  g.block_n = pick_block_n(g.m_tiles, p->Cout);
+  g.n_tiles = (p->Cout + g.block_n - 1) / g.block_n;
+  return g;
+}
+
 }  // namespace
 
 extern "C" int64_t spgan_gemm_launch_count(void) { return (int64_t)launch_counter()->load(); }
 
 extern "C" int spgan_pack_act(uint16_t* out, const float* x, const float* in_mul, int B, int C, int H, int W, int Cp,
-                              int pad_y, int pad_x, int Hl, int Wl, int step, void* stream) {
+                              int pad_y, int pad_x, int Hl, int Wl, int step, int fmt, void* stream) {
   SPGAN_CHECK_ARG(B >= 0 && C >= 0 && H >= 0 && W >= 0 && pad_y >= 0 && pad_x >= 0, "spgan_pack_act: negative size");
   SPGAN_CHECK_ARG(step >= 1 && step <= 8, "spgan_pack_act: step %d unsupported", step);
   SPGAN_CHECK_ARG(step > 1 || (Hl >= H + pad_y && Wl >= W + pad_x), "spgan_pack_act: lattice %dx%d smaller than the padded image", Hl, Wl);
   SPGAN_CHECK_ARG(Cp >= C && Cp % 16 == 0, "spgan_pack_act: Cp=%d must be a multiple of 16 and >= C=%d", Cp, C);
+  SPGAN_CHECK_ARG(fmt == 0 || fmt == 1, "spgan_pack_act: fmt must be 0 (bf16 hi/lo) or 1 (fp16 hi/lo), got %d", fmt);
   if (B == 0 || Cp == 0 || H == 0 || W == 0) return 0;
   SPGAN_CHECK_ARG(out && x, "spgan_pack_act: null pointer");
   SPGAN_CHECK_ARG(B * step * step <= 65535, "spgan_pack_act: batch %d x %d phases > 65535", B, step * step);
   dim3 grid((Hl * Wl + 63) / 64, (Cp + 63) / 64, B * step * step);
-  pack_act_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)out, x, in_mul, B, C, H, W, Cp, pad_y, pad_x,
-                                                          Hl, Wl, step);
+  if (fmt)
+    pack_act_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(out, x, in_mul, B, C, H, W, Cp, pad_y, pad_x, Hl, Wl, step);
+  else
+    pack_act_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(out, x, in_mul, B, C, H, W, Cp, pad_y, pad_x, Hl, Wl, step);
   SPGAN_CHECK_LAUNCH("spgan_pack_act");
   return 0;
 }
 
 extern "C" int spgan_pack_weight(uint16_t* out, const float* w, int Cout, int Cin, int64_t ws_o, int64_t ws_c, int ntaps,
-                                 const int32_t* tap_w, int Cp, int merged, void* stream) {
+                                 const int32_t* tap_w, int Cp, int merged, int fmt, void* stream) {
   SPGAN_CHECK_ARG(Cout >= 0 && Cin >= 0, "spgan_pack_weight: negative size");
   SPGAN_CHECK_ARG(ntaps >= 1 && ntaps <= SPGAN_MAX_TAPS, "spgan_pack_weight: %d taps unsupported", ntaps);
   SPGAN_CHECK_ARG(Cp >= Cin && Cp % 16 == 0, "spgan_pack_weight: Cp=%d must be a multiple of 16 and >= Cin=%d", Cp, Cin);
+  SPGAN_CHECK_ARG(fmt == 0 || fmt == 1, "spgan_pack_weight: fmt must be 0 (bf16 hi/lo) or 1 (fp16 hi/lo), got %d", fmt);
   if (Cout == 0 || Cp == 0) return 0;
   SPGAN_CHECK_ARG(out && w && tap_w, "spgan_pack_weight: null pointer");
   TapList taps;
   for (int t = 0; t < ntaps; ++t) taps.w[t] = tap_w[t];
   const int64_t total = (int64_t)ntaps * Cout * Cp;
-  pack_weight_kernel<<<grid_for(total, 256, 8), 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)out, w, Cout, Cin, ws_o,
-                                                                                ws_c, ntaps, taps, Cp, merged);
+  if (fmt)
+    pack_weight_kernel<true><<<grid_for(total, 256, 8), 256, 0, (cudaStream_t)stream>>>(out, w, Cout, Cin, ws_o, ws_c, ntaps, taps, Cp, merged);
+  else
+    pack_weight_kernel<false><<<grid_for(total, 256, 8), 256, 0, (cudaStream_t)stream>>>(out, w, Cout, Cin, ws_o, ws_c, ntaps, taps, Cp, merged);
   SPGAN_CHECK_LAUNCH("spgan_pack_weight");
   return 0;
 }
@@ -725,10 +875,11 @@ extern "C" int spgan_nchw_to_nhwc(float* out, const float* x, int B, int C, int 
 
 extern "C" int spgan_sphere_pack(uint16_t* out, const float* x_nhwc, const float* coords, const float* grid,
                                  const float* in_mul, const uint32_t* chan_map, int B, int C, int H, int W,
-                                 int grid_batch, int Cp, void* stream) {
+                                 int grid_batch, int Cp, int fmt, void* stream) {
   SPGAN_CHECK_ARG(B >= 0 && C >= 0 && H >= 0 && W >= 0, "spgan_sphere_pack: negative size");
   const int nc = coords ? 3 : 0;
   SPGAN_CHECK_ARG(Cp >= C + nc && Cp % 64 == 0, "spgan_sphere_pack: Cp=%d must be a multiple of 64 and >= %d", Cp, C + nc);
+  SPGAN_CHECK_ARG(fmt == 0 || fmt == 1, "spgan_sphere_pack: fmt must be 0 (bf16 hi/lo) or 1 (fp16 hi/lo), got %d", fmt);
   if (B == 0 || H == 0 || W == 0) return 0;
   SPGAN_CHECK_ARG(out && x_nhwc && grid && chan_map, "spgan_sphere_pack: null pointer");
   SPGAN_CHECK_ARG(B <= 65535 && C <= 32767, "spgan_sphere_pack: B=%d / C=%d exceed the channel-map encoding", B, C);
@@ -738,31 +889,41 @@ extern "C" int spgan_sphere_pack(uint16_t* out, const float* x_nhwc, const float
                   "spgan_sphere_pack: grid and chan_map must be 8-byte aligned");
   const int64_t warps = (int64_t)B * H * W * 9;
   cudaStream_t st = (cudaStream_t)stream;
-  __nv_bfloat16* o = (__nv_bfloat16*)out;
   const int nblk = grid_for((int64_t)B * H * W, 8, 2, 16);
-#define SPGAN_SPHERE_SHARED(KI)                                                                                       \
-  sphere_pack_shared_kernel<KI><<<nblk, 256, 0, st>>>(o, x_nhwc, coords, grid, in_mul, chan_map, B, C, nc, H, W)
+#define SPGAN_SPHERE_SHARED(KI)                                                                                        \
+  do {                                                                                                                 \
+    if (fmt) sphere_pack_shared_kernel<KI, true><<<nblk, 256, 0, st>>>(out, x_nhwc, coords, grid, in_mul, chan_map, B, C, nc, H, W); \
+    else sphere_pack_shared_kernel<KI, false><<<nblk, 256, 0, st>>>(out, x_nhwc, coords, grid, in_mul, chan_map, B, C, nc, H, W);    \
+  } while (0)
   if (grid_batch == 1 && Cp == 64) SPGAN_SPHERE_SHARED(1);
   else if (grid_batch == 1 && Cp == 128) SPGAN_SPHERE_SHARED(2);
   else if (grid_batch == 1 && Cp == 192) SPGAN_SPHERE_SHARED(3);
   else if (grid_batch == 1 && Cp == 256) SPGAN_SPHERE_SHARED(4);
   else if (grid_batch == 1 && Cp == 320) SPGAN_SPHERE_SHARED(5);
+  else if (fmt)
+    sphere_pack_kernel<true><<<grid_for(warps, 8, 8, 8), 256, 0, st>>>(out, x_nhwc, coords, grid, in_mul, chan_map, B, C, nc, H, W, grid_batch, Cp);
   else
-    sphere_pack_kernel<<<grid_for(warps, 8, 8, 8), 256, 0, st>>>(o, x_nhwc, coords, grid, in_mul, chan_map, B, C, nc, H, W,
-                                                                grid_batch, Cp);
+    sphere_pack_kernel<false><<<grid_for(warps, 8, 8, 8), 256, 0, st>>>(out, x_nhwc, coords, grid, in_mul, chan_map, B, C, nc, H, W, grid_batch, Cp);
 #undef SPGAN_SPHERE_SHARED
   SPGAN_CHECK_LAUNCH("spgan_sphere_pack");
   return 0;
 }
 
-extern "C" int spgan_conv_gemm(const SpganConvPass* p, float* y, const uint16_t* a_packed, int64_t a_rows, int kp,
-                               const uint16_t* w_packed, const float* out_mul, const float* noise, const float* noise_w,
-                               const float* bias, const float* residual, void* stream) {
-  SPGAN_CHECK_ARG(p != nullptr, "spgan_conv_gemm: null pass descriptor");
-  SPGAN_CHECK_ARG(p->precision == 1 || p->precision == 2, "spgan_conv_gemm: precision must be 1 (bf16x3) or 2 (bf16), got %d",
-                  p->precision);
+extern "C" int spgan_conv_gemm_rgb_slots(const SpganConvPass* p, int64_t a_rows) {
+  if (p == nullptr || p->Cout <= 0) return 0;
+  return 2 * gemm_shape(p, a_rows).n_tiles;
+}
+
+extern "C" int spgan_conv_gemm_ex(const SpganConvPass* p, const SpganGemmIO* io, void* stream) {
+  SPGAN_CHECK_ARG(p != nullptr && io != nullptr, "spgan_conv_gemm: null descriptor");
+  SPGAN_CHECK_ARG(p->precision >= 1 && p->precision <= 3,
+                  "spgan_conv_gemm: precision must be 1 (bf16x3), 2 (bf16) or 3 (fp16x2), got %d", p->precision);
+  SPGAN_CHECK_ARG(io->fmt == (p->precision == 3 ? 1 : 0), "spgan_conv_gemm: operand format %d does not match precision %d "
+                  "(bf16 planes for 1 and 2, fp16 planes for 3)", io->fmt, p->precision);
   SPGAN_CHECK_ARG(p->ntaps >= 1 && p->ntaps <= SPGAN_MAX_TAPS, "spgan_conv_gemm: %d taps unsupported", p->ntaps);
   SPGAN_CHECK_ARG(p->in_stride == 1, "spgan_conv_gemm: in_stride %d unsupported on the tcgen05 path", p->in_stride);
+  const int kp = io->kp;
+  const int64_t a_rows = io->a_rows;
   SPGAN_CHECK_ARG(kp > 0 && kp % GEMM_UMMA_K == 0, "spgan_conv_gemm: kp=%d must be a positive multiple of 16", kp);
   SPGAN_CHECK_ARG(p->B >= 0 && p->H >= 0 && p->W >= 0 && p->Cout >= 0, "spgan_conv_gemm: negative size");
   SPGAN_CHECK_ARG(p->out_stride >= 1, "spgan_conv_gemm: out_stride must be >= 1");
@@ -773,19 +934,34 @@ extern "C" int spgan_conv_gemm(const SpganConvPass* p, float* y, const uint16_t*
   SPGAN_CHECK_ARG(rows < 2147483647LL - 65536, "spgan_conv_gemm: too many lattice points");
   if (rows == 0 || p->Cout == 0 || p->My == 0 || p->Mx == 0) return 0;
   SPGAN_CHECK_ARG(p->Cout >= 16, "spgan_conv_gemm: Cout=%d < 16 belongs on the SIMT path", p->Cout);
-  SPGAN_CHECK_ARG(y && a_packed && w_packed, "spgan_conv_gemm: null pointer");
-  SPGAN_CHECK_ARG(((((uintptr_t)a_packed) | ((uintptr_t)w_packed)) & 15) == 0, "spgan_conv_gemm: packed operands must be 16-byte aligned");
+  SPGAN_CHECK_ARG(io->a_packed && io->w_packed, "spgan_conv_gemm: null operand pointer");
+  SPGAN_CHECK_ARG(io->y || io->y_packed || io->rgb_w, "spgan_conv_gemm: no output sink");
+  SPGAN_CHECK_ARG(((((uintptr_t)io->a_packed) | ((uintptr_t)io->w_packed)) & 15) == 0, "spgan_conv_gemm: packed operands must be 16-byte aligned");
+  const bool general = io->y == nullptr || io->y_layout != 0 || io->y_packed != nullptr || io->rgb_w != nullptr;
+  if (general) {
+    SPGAN_CHECK_ARG(p->Cout % 32 == 0, "spgan_conv_gemm: channels-last / packed / ToRGB sinks need Cout %% 32 == 0, got %d", p->Cout);
+    SPGAN_CHECK_ARG(io->residual == nullptr, "spgan_conv_gemm: residual is only supported with a plain NCHW output");
+    SPGAN_CHECK_ARG(io->y == nullptr || io->y_layout == 0 || (((uintptr_t)io->y) & 15) == 0, "spgan_conv_gemm: NHWC output must be 16-byte aligned");
+  }
+  if (io->y_packed) {
+    SPGAN_CHECK_ARG(io->y_packed_cols >= p->Cout && io->y_packed_cols % 8 == 0 && (((uintptr_t)io->y_packed) & 15) == 0,
+                    "spgan_conv_gemm: packed sink needs cols %% 8 == 0, cols >= Cout and a 16-byte aligned pointer");
+    SPGAN_CHECK_ARG(io->y_packed_rows >= (int64_t)p->B * p->out_H * p->out_W, "spgan_conv_gemm: packed sink has too few rows");
+    SPGAN_CHECK_ARG(io->y_packed_fmt == 0 || io->y_packed_fmt == 1, "spgan_conv_gemm: packed sink format must be 0 or 1");
+  }
+  if (io->rgb_w) {
+    SPGAN_CHECK_ARG(io->rgb_part != nullptr && io->rgb_n >= 1 && io->rgb_n <= 3, "spgan_conv_gemm: ToRGB sink needs rgb_part and 1..3 channels");
+    SPGAN_CHECK_ARG((((uintptr_t)io->rgb_w) & 15) == 0, "spgan_conv_gemm: rgb_w must be 16-byte aligned");
+  }
 
-  // im2col A loads whenever the pass has lattice points that are not outputs (unpadded 3x3 / 7x7 convs, padded convs on
-  // their bordered lattice, parity passes): M then runs over the B*My*Mx outputs only.  The bounding-box corner of a
-  // rank-4 map is an 8-bit field, hence the 128 limit; passes outside it keep the flat row-offset loads.
-  const int phases = (int)(a_rows / rows);
-  const bool im2col = (p->My < p->H || p->Mx < p->W) && p->My <= p->H && p->Mx <= p->W && p->H - p->My <= 128 &&
-                      p->W - p->Mx <= 128 && (int64_t)2 * phases * p->B < (1LL << 31);
+  const GemmShape gs = gemm_shape(p, a_rows);
+  const int phases = gs.phases;
+  const bool im2col = gs.im2col;
   GemmParams gp;
+  gp.B = p->B;
   gp.im2col = im2col ? 1 : 0;
   gp.img_lo = phases * p->B;
-  gp.rows = im2col ? (int32_t)((int64_t)p->B * p->My * p->Mx) : (int32_t)rows;
+  gp.rows = (int32_t)gs.rows_m;
   gp.Hl = im2col ? p->My : p->H;
   gp.Wl = im2col ? p->Mx : p->W;
   gp.My = p->My;
@@ -814,18 +990,36 @@ extern "C" int spgan_conv_gemm(const SpganConvPass* p, float* y, const uint16_t*
   gp.last_ksteps = (kp - (gp.kblocks - 1) * GEMM_BLOCK_K) / GEMM_UMMA_K;
   for (int t = 0; t < p->ntaps; ++t) gp.tap_off[t] = p->tap_dy[t] * p->W + p->tap_dx[t];
   for (int t = p->ntaps; t < SPGAN_MAX_TAPS; ++t) gp.tap_off[t] = 0;
-  gp.m_tiles = (int32_t)(((int64_t)gp.rows + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M);
-  const int block_n = pick_block_n(gp.m_tiles, p->Cout);
-  gp.n_tiles = (p->Cout + block_n - 1) / block_n;
+  gp.m_tiles = gs.m_tiles;
+  const int block_n = gs.block_n;
+  gp.n_tiles = gs.n_tiles;
   gp.out_scale = p->out_scale;
   gp.act = p->act;
   gp.act_alpha = p->act_alpha;
   gp.act_gain = p->act_gain;
+  gp.f16 = io->fmt;
+  gp.y_nhwc = io->y_layout != 0 ? 1 : 0;
+  gp.y_bstride = io->y_bstride ? io->y_bstride : (int64_t)p->out_H * p->out_W * p->Cout;
+  gp.pk_rows = io->y_packed_rows;
+  gp.pk_cols = io->y_packed_cols;
+  gp.pk_f16 = io->y_packed_fmt;
+  gp.rgb_n = io->rgb_w ? io->rgb_n : 0;
+  GemmSinks sk;
+  sk.y = io->y;
+  sk.out_mul = io->out_mul;
+  sk.noise = io->noise;
+  sk.noise_w = io->noise_w;
+  sk.bias = io->bias;
+  sk.residual = io->residual;
+  sk.y_packed = io->y_packed;
+  sk.next_mul = io->next_mul;
+  sk.rgb_w = io->rgb_w;
+  sk.rgb_part = io->rgb_part;
 
   CUtensorMap tmA, tmB;
   if (im2col) {
     // (kp channels, W, H, 2 * phases * B images): hi planes first, then the lo planes
-    if (int e = encode_bf16_im2col_map(&tmA, a_packed, (cuuint64_t)kp, (cuuint64_t)p->W, (cuuint64_t)p->H,
+    if (int e = encode_bf16_im2col_map(&tmA, io->a_packed, (cuuint64_t)kp, (cuuint64_t)p->W, (cuuint64_t)p->H,
                                        (cuuint64_t)2 * phases * p->B, p->Mx - p->W, p->My - p->H, GEMM_BLOCK_K, GEMM_BLOCK_M,
                                        "spgan_conv_gemm (A im2col map)"))
       return e;
@@ -833,18 +1027,38 @@ extern "C" int spgan_conv_gemm(const SpganConvPass* p, float* y, const uint16_t*
     cuuint64_t dims[3] = {(cuuint64_t)kp, (cuuint64_t)a_rows, 2};
     cuuint64_t strides[2] = {(cuuint64_t)kp * 2, (cuuint64_t)a_rows * kp * 2};
     cuuint32_t box[3] = {GEMM_BLOCK_K, GEMM_BLOCK_M, 1};
-    if (int e = encode_bf16_map(&tmA, a_packed, 3, dims, strides, box, "spgan_conv_gemm (A map)")) return e;
+    if (int e = encode_bf16_map(&tmA, io->a_packed, 3, dims, strides, box, "spgan_conv_gemm (A map)")) return e;
   }
   {
     cuuint64_t dims[4] = {(cuuint64_t)kp, (cuuint64_t)p->Cout, (cuuint64_t)p->ntaps, 2};
     cuuint64_t strides[3] = {(cuuint64_t)kp * 2, (cuuint64_t)p->Cout * kp * 2, (cuuint64_t)p->ntaps * p->Cout * kp * 2};
     cuuint32_t box[4] = {GEMM_BLOCK_K, (cuuint32_t)block_n, 1, 1};
-    if (int e = encode_bf16_map(&tmB, w_packed, 4, dims, strides, box, "spgan_conv_gemm (B map)")) return e;
+    if (int e = encode_bf16_map(&tmB, io->w_packed, 4, dims, strides, box, "spgan_conv_gemm (B map)")) return e;
   }
   cudaStream_t st = (cudaStream_t)stream;
   if (p->precision == 1)
-    return block_n == 256 ? launch_gemm<3, 256>(tmA, tmB, gp, y, out_mul, noise, noise_w, bias, residual, st)
-                          : launch_gemm<3, 128>(tmA, tmB, gp, y, out_mul, noise, noise_w, bias, residual, st);
-  return block_n == 256 ? launch_gemm<1, 256>(tmA, tmB, gp, y, out_mul, noise, noise_w, bias, residual, st)
-                        : launch_gemm<1, 128>(tmA, tmB, gp, y, out_mul, noise, noise_w, bias, residual, st);
+    return block_n == 256 ? launch_gemm<3, 256>(tmA, tmB, gp, sk, st) : launch_gemm<3, 128>(tmA, tmB, gp, sk, st);
+  if (p->precision == 3)
+    return block_n == 256 ? launch_gemm<2, 256>(tmA, tmB, gp, sk, st) : launch_gemm<2, 128>(tmA, tmB, gp, sk, st);
+  return block_n == 256 ? launch_gemm<1, 256>(tmA, tmB, gp, sk, st) : launch_gemm<1, 128>(tmA, tmB, gp, sk, st);
+}
+
+extern "C" int spgan_conv_gemm(const SpganConvPass* p, float* y, const uint16_t* a_packed, int64_t a_rows, int kp,
+                               const uint16_t* w_packed, const float* out_mul, const float* noise, const float* noise_w,
+                               const float* bias, const float* residual, void* stream) {
+  SPGAN_CHECK_ARG(p != nullptr, "spgan_conv_gemm: null pass descriptor");
+  SpganGemmIO io = {};
+  io.a_packed = a_packed;
+  io.a_rows = a_rows;
+  io.kp = kp;
+  io.fmt = p->precision == 3 ? 1 : 0;
+  io.w_packed = w_packed;
+  io.out_mul = out_mul;
+  io.noise = noise;
+  io.noise_w = noise_w;
+  io.bias = bias;
+  io.residual = residual;
+  io.y = y;
+  SPGAN_CHECK_ARG(y != nullptr, "spgan_conv_gemm: null output pointer");
+  return spgan_conv_gemm_ex(p, &io, stream);
 }

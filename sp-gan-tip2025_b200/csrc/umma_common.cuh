@@ -6,6 +6,7 @@
 
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace {
 
@@ -113,6 +114,11 @@ __device__ __forceinline__ uint32_t umma_idesc_bf16(int n) {
          | ((uint32_t)(n >> 3) << 17)
          | ((uint32_t)(GEMM_BLOCK_M >> 4) << 24);  // A, B K-major: bits 15, 16 stay 0
 }
+// kind::f16 descriptor with both operands fp16 (format code 0) or both bf16 (format code 1).
+__device__ __forceinline__ uint32_t umma_idesc_16(int n, bool f16) {
+  const uint32_t fmt = f16 ? 0u : 1u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(GEMM_BLOCK_M >> 4) << 24);
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
   asm volatile(
@@ -131,6 +137,25 @@ __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bflo
   hi = __float2bfloat16_rn(v);
   lo = __float2bfloat16_rn(v - __bfloat162float(hi));
 }
+
+// 16-bit operand split, raw bits: kF16 = false -> bf16 hi/lo (8 + 8 mantissa bits, fp32 range), kF16 = true -> fp16 hi/lo
+// (11 + 11 bits; values beyond +-65504 saturate, which no activation or weight of this network approaches).
+template <bool kF16>
+__device__ __forceinline__ void split16(float v, uint16_t& hi, uint16_t& lo) {
+  if (kF16) {
+    v = fminf(fmaxf(v, -65504.f), 65504.f);
+    const __half h = __float2half_rn(v);
+    const __half l = __float2half_rn(v - __half2float(h));
+    hi = __half_as_ushort(h);
+    lo = __half_as_ushort(l);
+  } else {
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+    hi = __bfloat16_as_ushort(h);
+    lo = __bfloat16_as_ushort(l);
+  }
+}
+__device__ __forceinline__ uint32_t pack2x16(uint16_t a, uint16_t b) { return (uint32_t)a | ((uint32_t)b << 16); }
 
 // ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

@@ -17,15 +17,22 @@ import torch
 from . import lib
 from .lib import ConvPass
 
-# 0 = exact fp32 SIMT, 1 = bf16x3 split on tcgen05 (fp32-equivalent, default), 2 = plain bf16 on tcgen05
+# 0 = exact fp32 SIMT, 1 = bf16x3 split on tcgen05 (fp32-equivalent, default), 2 = plain bf16 on tcgen05,
+# 3 = fp16x2 on tcgen05 (fp16 hi+lo activations x fp16 weights: 2 MMAs per product, relative error ~2^-12; forward only —
+# gradients keep the bf16x3 split because their range does not fit fp16)
 _PRECISION = 1
 
 
 def set_precision(p):
     global _PRECISION
-    if p not in (0, 1, 2):
-        raise ValueError("precision must be 0 (fp32 SIMT), 1 (bf16x3 tcgen05) or 2 (bf16 tcgen05)")
+    if p not in (0, 1, 2, 3):
+        raise ValueError("precision must be 0 (fp32 SIMT), 1 (bf16x3 tcgen05), 2 (bf16 tcgen05) or 3 (fp16x2 tcgen05)")
     _PRECISION = p
+
+
+def _fmt(precision):
+    """Operand format of a precision mode: 0 = bf16 hi/lo planes, 1 = fp16 hi/lo planes."""
+    return 1 if precision == 3 else 0
 
 
 def get_precision():
@@ -471,9 +478,9 @@ def _round_up(a, b):
     return _ceil_div(a, b) * b
 
 
-def _packed_weight(w, Cout, Cin, ws_o, ws_c, tap_w, Cp, merged):
-    """bf16 hi/lo copy of the weight in [2][ntaps][Cout][Cp] (or merged-K) order, cached per weight version."""
-    key = (w.data_ptr(), w._version, tuple(w.shape), Cout, Cin, ws_o, ws_c, tuple(tap_w), Cp, merged, w.device.index)
+def _packed_weight(w, Cout, Cin, ws_o, ws_c, tap_w, Cp, merged, fmt=0):
+    """16-bit hi/lo copy of the weight in [2][ntaps][Cout][Cp] (or merged-K) order, cached per weight version."""
+    key = (w.data_ptr(), w._version, tuple(w.shape), Cout, Cin, ws_o, ws_c, tuple(tap_w), Cp, merged, fmt, w.device.index)
     hit = _WEIGHT_CACHE.get(key)
     if hit is not None:
         _WEIGHT_CACHE.move_to_end(key)
@@ -482,7 +489,7 @@ def _packed_weight(w, Cout, Cin, ws_o, ws_c, tap_w, Cp, merged):
     out = torch.empty((2, ntaps, Cout, Cp), device=w.device, dtype=torch.bfloat16)
     arr = (ctypes.c_int32 * ntaps)(*tap_w)
     with torch.cuda.device(w.device):
-        lib.call("spgan_pack_weight", _ptr(out), _ptr(w), Cout, Cin, ws_o, ws_c, ntaps, arr, Cp, int(merged), _stream(w))
+        lib.call("spgan_pack_weight", _ptr(out), _ptr(w), Cout, Cin, ws_o, ws_c, ntaps, arr, Cp, int(merged), int(fmt), _stream(w))
     _WEIGHT_CACHE[key] = (out, w)  # keep `w` alive so the data_ptr cannot be recycled while the entry exists
     if len(_WEIGHT_CACHE) > _WEIGHT_CACHE_MAX:
         _WEIGHT_CACHE.popitem(last=False)
@@ -494,10 +501,18 @@ def clear_weight_cache():
 
 
 _EPOCH = 0
+_STYLE_EPOCH = 0
 
 
 def epoch():
-    return _EPOCH
+    return (_EPOCH, _STYLE_EPOCH)
+
+
+def bump_style_epoch():
+    """Invalidate only the memoised (modulation, demodulation) pairs: a CUDA-graph capture must contain the kernels that
+    compute them (a memo hit during capture would freeze the styles of the capture-time latent into every replay)."""
+    global _STYLE_EPOCH
+    _STYLE_EPOCH += 1
 
 
 def bump_epoch():
@@ -559,6 +574,9 @@ def conv_apply(x, w, geom, adjoint=False, out_hw=None, in_mul=None, out_mul=None
         Cin, Cout, ws_o, ws_c = O, C, kk, C * kk
         oh, ow = out_hw
     precision = _PRECISION if precision is None else precision
+    if precision == 3 and adjoint:
+        precision = 1  # data gradients: fp16 has too little range
+    fmt = _fmt(precision)
     passes, covers = plan_passes(geom, adjoint, (H, W), (oh, ow))
     if polyphase:
         # parity passes write dense planes (B, Cout, s*s, Hq, Wq), plane (off_y * s + off_x), instead of scattering
@@ -607,12 +625,12 @@ def conv_apply(x, w, geom, adjoint=False, out_hw=None, in_mul=None, out_mul=None
             Cp = _round_up(Cin, k_round)
             rows = B * Hl * Wl
             a_packed = torch.empty((2, step * step * rows, Cp), device=x.device, dtype=torch.bfloat16)
-            lib.call("spgan_pack_act", _ptr(a_packed), _ptr(x), _ptr(im), B, Cin, H, W, Cp, pt, pl, Hl, Wl, step, st)
+            lib.call("spgan_pack_act", _ptr(a_packed), _ptr(x), _ptr(im), B, Cin, H, W, Cp, pt, pl, Hl, Wl, step, fmt, st)
             for p, taps in zip(passes, mapped):
                 q, yptr, o_h, o_w, cst = target(p)
                 shifted = dict(q, in_stride=1, taps=[(ph * B * Hl + oy, ox, wi) for ph, oy, ox, wi in taps])
                 cp = _fill_pass(shifted, B, Cin, Hl, Wl, Cout, o_h, o_w, ws_o, ws_c, out_scale, act_on, a, g, precision, cst)
-                wp = _packed_weight(w, Cout, Cin, ws_o, ws_c, [t[2] for t in p["taps"]], Cp, False)
+                wp = _packed_weight(w, Cout, Cin, ws_o, ws_c, [t[2] for t in p["taps"]], Cp, False, fmt)
                 valid = min(p["My"], _ceil_div(oh - p["off_y"], p["out_stride"])) * min(p["Mx"], _ceil_div(ow - p["off_x"], p["out_stride"]))
                 _gemm_call(2.0 * B * valid * Cout * Cin * len(p["taps"]), ctypes.byref(cp), yptr, _ptr(a_packed),
                            step * step * rows, Cp, _ptr(wp), _ptr(om), _ptr(nz), _ptr(nwt), _ptr(bs), _ptr(rs), st)
@@ -641,6 +659,8 @@ def conv_wgrad(g, x, w_shape, geom, in_mul=None, out_mul=None, out_scale=1.0, pr
     im = _f32c(in_mul, "conv wgrad") if in_mul is not None else None
     om = _f32c(out_mul, "conv wgrad") if out_mul is not None else None
     precision = _PRECISION if precision is None else precision
+    if precision == 3:
+        precision = 1  # weight gradients: fp16 has too little range
     if passes and _tensor_path_ok(passes, C, O, precision) and len({p["out_stride"] for p in passes}) == 1:
         # tcgen05: contraction over the flattened lattice rows of the same channels-last packs the forward GEMM reads
         s_in, pt, pl, Hl, Wl, mapped = _phase_taps(passes)
@@ -653,8 +673,8 @@ def conv_wgrad(g, x, w_shape, geom, in_mul=None, out_mul=None, out_scale=1.0, pr
         with torch.cuda.device(x.device):
             gp = torch.empty((2, s_out * s_out * Q, Op), device=x.device, dtype=torch.bfloat16)
             xp = torch.empty((2, s_in * s_in * Q, Cp), device=x.device, dtype=torch.bfloat16)
-            lib.call("spgan_pack_act", _ptr(gp), _ptr(g), _ptr(om), B, O, oh, ow, Op, 0, 0, Hl, Wl, s_out, st)
-            lib.call("spgan_pack_act", _ptr(xp), _ptr(x), _ptr(im), B, C, H, W, Cp, pt, pl, Hl, Wl, s_in, st)
+            lib.call("spgan_pack_act", _ptr(gp), _ptr(g), _ptr(om), B, O, oh, ow, Op, 0, 0, Hl, Wl, s_out, 0, st)
+            lib.call("spgan_pack_act", _ptr(xp), _ptr(x), _ptr(im), B, C, H, W, Cp, pt, pl, Hl, Wl, s_in, 0, st)
             for p, taps in zip(passes, mapped):
                 q = dict(p, in_stride=1, out_stride=1, off_y=0, off_x=0, taps=[(oy, ox, wi) for _, oy, ox, wi in taps])
                 cp = _fill_pass(q, B, C, Hl, Wl, O, Hl, Wl, C * kk, kk, out_scale, 0, 0.0, 1.0, precision)
@@ -836,8 +856,8 @@ def sphere_modconv_fused(x, coords, grid, w, in_mul, out_mul, out_scale, act=Non
         im = _f32c(in_mul, "sphere_modconv") if in_mul is not None else None
         cmap = _sphere_chan_map(B, C, nc, Cp, bool(flat_concat), x.device)
         lib.call("spgan_sphere_pack", _ptr(a_packed), _ptr(xh), _ptr(cc), _ptr(grid), _ptr(im), _ptr(cmap), B, C, H, W,
-                 grid.shape[0], Cp, st)
-        wp = _packed_weight(w, O, Ct, Ct * 9, 9, list(range(9)), Cp, True)
+                 grid.shape[0], Cp, _fmt(precision), st)
+        wp = _packed_weight(w, O, Ct, Ct * 9, 9, list(range(9)), Cp, True, _fmt(precision))
         p = dict(My=H, Mx=W, in_stride=1, out_stride=1, off_y=0, off_x=0, taps=[(0, 0, 0)])
         cp = _fill_pass(p, B, Ct, H, W, O, H, W, Ct * 9, 9, out_scale, 1 if act is not None else 0, a, g, precision)
         om = _f32c(out_mul, "sphere_modconv") if out_mul is not None else None
@@ -927,3 +947,128 @@ def sphere_modconv(x, coords, grid, w, in_mul, out_mul, out_scale, flat_concat=T
     else:
         inp = gx
     return _ConvFn.apply(inp, w, in_mul, out_mul, _SPHERE_GEOM, False, None, out_scale)
+
+
+# =================================================================================================== channels-last chain
+# Inference path of the texture synthesiser (models/spgan/spgan.py:924-978) without the NCHW fp32 tensors between its
+# convs: every GEMM epilogue / FIR tail writes the NEXT conv's packed operand, ToRGB is folded into the epilogue of the
+# conv it reads.  See csrc/chain.cu and the sinks of spgan_conv_gemm_ex.
+_UP_GEOM = ConvGeom(3, 3, stride=2, transposed=True, crop=1)
+_C3_GEOM = ConvGeom(3, 3)
+
+
+def _gemm_ex(cp, flops, st, **kw):
+    io = lib.GemmIO()
+    for k, v in kw.items():
+        if isinstance(v, torch.Tensor) or v is None:
+            v = v.data_ptr() if v is not None else None
+        setattr(io, k, v)
+    _timed_call(flops, "spgan_conv_gemm_ex", ctypes.byref(cp), ctypes.byref(io), st)
+
+
+def packed_to_float(packed, fmt):
+    """(2, rows, cols) 16-bit hi/lo planes -> fp32 (tests, diagnostics)."""
+    v = packed.view(torch.float16 if fmt else torch.bfloat16)
+    return v[0].float() + v[1].float()
+
+
+def chain_pack_input(x, in_mul, precision):
+    """NCHW fp32 -> packed operand (2, B*H*W, Cp) of a conv whose lattice is the image itself."""
+    x = _f32c(x, "chain")
+    B, C, H, W = x.shape
+    Cp = _round_up(C, 64)
+    a = torch.empty((2, B * H * W, Cp), device=x.device, dtype=torch.bfloat16)
+    with torch.cuda.device(x.device):
+        lib.call("spgan_pack_act", _ptr(a), _ptr(x), _ptr(in_mul), B, C, H, W, Cp, 0, 0, H, W, 1, _fmt(precision), _stream(x))
+    return a
+
+
+def chain_upconv(a, B, H, W, w, out_mul, out_scale, precision):
+    """Transposed 3x3 stride-2 conv cropped by 1 (models/ops.py:617-619) from the packed input `a` (2, B*H*W, Cp) to
+    channels-last polyphase planes (B, 4, H, W, Cout) fp32: four parity GEMMs, each writing its plane."""
+    O, C = w.shape[0], w.shape[1]
+    Cp = a.shape[2]
+    oh, ow = _UP_GEOM.out_size(H, W)
+    passes, _ = plan_passes(_UP_GEOM, False, (H, W), (oh, ow))
+    step, pt, pl, Hl, Wl, mapped = _phase_taps(passes)
+    assert step == 1 and pt == 0 and pl == 0 and Hl <= H and Wl <= W
+    pp = torch.empty((B, 4, H, W, O), device=a.device, dtype=torch.float32)
+    fmt = _fmt(precision)
+    st = _stream(a)
+    with torch.cuda.device(a.device):
+        for p, taps in zip(passes, mapped):
+            q = dict(p, in_stride=1, out_stride=1, off_y=0, off_x=0, taps=[(oy, ox, wi) for _, oy, ox, wi in taps])
+            cp = _fill_pass(q, B, C, H, W, O, H, W, C * 9, 9, out_scale, 0, 0.0, 1.0, precision)
+            wp = _packed_weight(w, O, C, C * 9, 9, [t[2] for t in p["taps"]], Cp, False, fmt)
+            plane = p["off_y"] * 2 + p["off_x"]
+            _gemm_ex(cp, 2.0 * B * p["My"] * p["Mx"] * O * C * len(taps), st, a_packed=a, a_rows=B * H * W, kp=Cp, fmt=fmt,
+                     w_packed=wp, out_mul=out_mul, y=pp.data_ptr() + 4 * plane * H * W * O, y_layout=1,
+                     y_bstride=4 * H * W * O)
+    return pp, (oh, ow)
+
+
+def chain_upblur_pack(pp, out_hw, kernel, noise, noise_w, bias, next_mul, next_precision, negative_slope=0.2,
+                      scale=2 ** 0.5):
+    """pp (B, 4, Hq, Wq, C) channels-last planes -> the next conv's packed operand (2, B*oh*ow, C)."""
+    B, _, Hq, Wq, C = pp.shape
+    zh, zw = out_hw
+    oh, ow = zh - 2, zw - 2
+    out = torch.empty((2, B * oh * ow, C), device=pp.device, dtype=torch.bfloat16)
+    nz = _f32c(noise, "upblur_pack") if noise is not None else None
+    if nz is not None and nz.numel() != B * oh * ow:
+        raise RuntimeError("upblur_pack: noise must have shape (B, 1, %d, %d)" % (oh, ow))
+    with torch.cuda.device(pp.device):
+        lib.call("spgan_upblur_pack", _ptr(out), _ptr(pp), _ptr(_f32c(kernel, "upblur_pack")), _ptr(nz),
+                 _ptr(noise_w) if nz is not None else _ptr(None), _ptr(bias), _ptr(next_mul), B, C, zh, zw, Hq, Wq, C,
+                 B * oh * ow, _fmt(next_precision), float(negative_slope), float(scale), _stream(pp))
+    return out, (oh, ow)
+
+
+def chain_conv3(a, B, H, W, w, out_mul, out_scale, noise, noise_w, bias, act, precision, next_mul=None,
+                next_precision=None, rgb_w=None, want_nchw=False):
+    """Unpadded 3x3 conv + noise + bias + leaky-ReLU from the packed input `a` (2, B*H*W, Cp).  Sinks: the next conv's
+    packed operand (when next_precision is given), ToRGB partial sums (when rgb_w (B, 3, Cout) is given), an NCHW fp32
+    tensor (want_nchw).  Returns (packed or None, (rgb_part, slots) or None, nchw or None, (oh, ow))."""
+    O, C = w.shape[0], w.shape[1]
+    Cp = a.shape[2]
+    oh, ow = H - 2, W - 2
+    fmt = _fmt(precision)
+    taps = [(ky, kx, ky * 3 + kx) for ky in range(3) for kx in range(3)]
+    p = dict(My=oh, Mx=ow, in_stride=1, out_stride=1, off_y=0, off_x=0, taps=taps)
+    alpha, gain = act if act is not None else (0.0, 1.0)
+    cp = _fill_pass(p, B, C, H, W, O, oh, ow, C * 9, 9, out_scale, 1 if act is not None else 0, alpha, gain, precision)
+    st = _stream(a)
+    nz = _f32c(noise, "chain_conv3") if noise is not None else None
+    if nz is not None and nz.numel() != B * oh * ow:
+        raise RuntimeError("chain_conv3: noise must have shape (B, 1, %d, %d)" % (oh, ow))
+    kw = {}
+    packed = rgb = y = None
+    with torch.cuda.device(a.device):
+        wp = _packed_weight(w, O, C, C * 9, 9, list(range(9)), Cp, False, fmt)
+        if next_precision is not None:
+            packed = torch.empty((2, B * oh * ow, O), device=a.device, dtype=torch.bfloat16)
+            kw.update(y_packed=packed, next_mul=next_mul, y_packed_rows=B * oh * ow, y_packed_cols=O,
+                      y_packed_fmt=_fmt(next_precision))
+        if rgb_w is not None:
+            slots = int(lib.load().spgan_conv_gemm_rgb_slots(ctypes.byref(cp), B * H * W))
+            part = torch.empty((slots, B, rgb_w.shape[1], oh * ow), device=a.device, dtype=torch.float32)
+            kw.update(rgb_w=rgb_w, rgb_part=part, rgb_n=rgb_w.shape[1])
+            rgb = (part, slots)
+        if want_nchw:
+            y = torch.empty((B, O, oh, ow), device=a.device, dtype=torch.float32)
+            kw.update(y=y)
+        _gemm_ex(cp, 2.0 * B * oh * ow * O * C * 9, st, a_packed=a, a_rows=B * H * W, kp=Cp, fmt=fmt, w_packed=wp,
+                 out_mul=out_mul, noise=nz, noise_w=noise_w if nz is not None else None, bias=bias, **kw)
+    return packed, rgb, y, (oh, ow)
+
+
+def rgb_tail(part, slots, bias, skip, B, oh, ow):
+    """ToRGB tail: fixed-order sum of the epilogue's partial sums + bias + upsampled skip -> (B, 3, oh, ow)."""
+    n = part.shape[2]
+    out = torch.empty((B, n, oh, ow), device=part.device, dtype=torch.float32)
+    sk = _f32c(skip, "rgb_tail") if skip is not None else None
+    if sk is not None and tuple(sk.shape) != tuple(out.shape):
+        raise RuntimeError("rgb_tail: skip shape %s != %s" % (tuple(sk.shape), tuple(out.shape)))
+    with torch.cuda.device(part.device):
+        lib.call("spgan_rgb_tail", _ptr(out), _ptr(part), slots, _ptr(bias), _ptr(sk), B, n, oh * ow, _stream(part))
+    return out

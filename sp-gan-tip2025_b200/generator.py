@@ -219,8 +219,79 @@ class TextureSynthesizer(nn.Module):
         return torch.cat([w0.unsqueeze(1).repeat(1, inject_index, 1),
                           w1.unsqueeze(1).repeat(1, self.n_latent - inject_index, 1)], 1)
 
+    # Per-layer precision of the fused inference chain: None = the global mode for every layer; a list of 8 modes lets the
+    # layers nearest the output (whose rounding error is not amplified by later layers) run the 2-MMA fp16 split.
+    layer_precision = None
+    use_chain = True
+
+    def _chain_modes(self):
+        g = SF.get_precision()
+        modes = list(self.layer_precision) if self.layer_precision is not None else [g] * self.num_layers
+        if len(modes) != self.num_layers or any(m not in (1, 2, 3) for m in modes):
+            return None
+        return modes
+
+    def _chain_ok(self, styles, structure_latent, noises, test_ids, calc_flops):
+        if not self.use_chain or calc_flops or test_ids is not None or noises is None or not structure_latent.is_cuda:
+            return False
+        if SF.get_precision() == 0 or self._chain_modes() is None:
+            return False
+        if ops._grad_needed(styles, structure_latent, *self.parameters()):
+            return False
+        for i, conv in enumerate(self.convs):
+            c = conv.conv
+            if conv.noise is None or not c.demodulate or c.out_channel % 32 or c.kernel_size != 3 or not c.no_zero_pad:
+                return False
+            if c.upsample and (tuple(c.blur.kernel.shape) != (3, 3) or c.blur.zero_pad != (0, 0) or c.blur.use_replicate_pad):
+                return False
+            if c.upsample != (i % 2 == 0):
+                return False
+        return all(n is not None for n in noises)
+
+    def _forward_chain(self, styles, structure_latent, coords_partial, noises):
+        """The synthesis loop with channels-last operands between the convs (csrc/chain.cu): per (upsampling conv, conv)
+        pair 4 parity GEMMs -> FIR tail writing the conv's packed operand -> GEMM writing the next pair's packed operand
+        and the ToRGB partial sums -> rgb tail.  No fp32 activation of the texture synthesiser is written to HBM."""
+        B = structure_latent.shape[0]
+        modes = self._chain_modes()
+        sd = [conv.conv._mod_demod(styles[:, i], B) for i, conv in enumerate(self.convs)]
+        H, W = structure_latent.shape[2], structure_latent.shape[3]
+        a = SF.chain_pack_input(structure_latent, sd[0][0], modes[0])
+        skip = None
+        for k in range(self.num_layers // 2):
+            up, cv = self.convs[2 * k], self.convs[2 * k + 1]
+            (s_u, w_u, d_u), (s_c, w_c, d_c) = sd[2 * k], sd[2 * k + 1]
+            pp, zhw = SF.chain_upconv(a, B, H, W, w_u, d_u, up.conv.scale, modes[2 * k])
+            a, (H, W) = SF.chain_upblur_pack(pp, zhw, up.conv.blur.kernel, noises[2 * k], up.noise.weight, up.activate.bias,
+                                             s_c, modes[2 * k + 1], up.activate.negative_slope, up.activate.scale)
+            last = 2 * k + 2 >= self.num_layers
+            rgb_mod = self.to_rgbs[k]
+            s_r, w_r, _ = rgb_mod.conv._mod_demod(styles[:, self.TO_RGBS[k][1]], B)
+            cached = getattr(rgb_mod, "_rgbw_cache", None)
+            if cached is None or cached[0] is not s_r or cached[1] != w_r._version:
+                rgb_w = (w_r.reshape(1, w_r.shape[0], w_r.shape[1]) * s_r.unsqueeze(1) * rgb_mod.conv.scale).contiguous()
+                object.__setattr__(rgb_mod, "_rgbw_cache", (s_r, w_r._version, rgb_w))
+            else:
+                rgb_w = cached[2]
+            a, rgb, _, (H, W) = SF.chain_conv3(a, B, H, W, w_c, d_c, cv.conv.scale, noises[2 * k + 1], cv.noise.weight,
+                                               cv.activate.bias, (cv.activate.negative_slope, cv.activate.scale),
+                                               modes[2 * k + 1], next_mul=None if last else sd[2 * k + 2][0],
+                                               next_precision=None if last else modes[2 * k + 2], rgb_w=rgb_w)
+            i = 2 * k + 1
+            if i in self.I2J:
+                skip = self.sp_convs[self.I2J[i]](skip, coords_partial)
+            res = None
+            if skip is not None:
+                res = rgb_mod.upsample(skip)
+                if rgb_mod.no_zero_pad:
+                    res = rgb_mod.align_spatial_size(res, target=torch.empty(1, 1, H, W, device="meta"))
+            skip = SF.rgb_tail(rgb[0], rgb[1], rgb_mod.bias.view(-1), res, B, H, W)
+        return skip
+
     def forward(self, styles, structure_latent, coords_partial, noises=None, test_ids=None, calc_flops=False):
         """Synthesis loop (models/spgan/spgan.py:924-978).  styles (B, 9, 512); noises: list of 8 (B, 1, h, w) or None."""
+        if self._chain_ok(styles, structure_latent, noises, test_ids, calc_flops):
+            return self._forward_chain(styles, structure_latent, coords_partial, noises), 0
         h = structure_latent
         skip = None
         flops = 0

@@ -34,6 +34,17 @@ class ConvPass(ctypes.Structure):
     ]
 
 
+class GemmIO(ctypes.Structure):
+    """Mirror of `SpganGemmIO` (include/spgan_b200.h)."""
+    _fields_ = [
+        ("a_packed", c_vp), ("a_rows", ctypes.c_int64), ("kp", ctypes.c_int32), ("fmt", ctypes.c_int32),
+        ("w_packed", c_vp), ("out_mul", c_vp), ("noise", c_vp), ("noise_w", c_vp), ("bias", c_vp), ("residual", c_vp),
+        ("y", c_vp), ("y_layout", ctypes.c_int32), ("rgb_n", ctypes.c_int32), ("y_bstride", ctypes.c_int64),
+        ("y_packed", c_vp), ("next_mul", c_vp), ("y_packed_rows", ctypes.c_int64), ("y_packed_cols", ctypes.c_int32),
+        ("y_packed_fmt", ctypes.c_int32), ("rgb_w", c_vp), ("rgb_part", c_vp),
+    ]
+
+
 _PASS_P = ctypes.POINTER(ConvPass)
 
 # name -> (restype, argtypes).  tests/test_abi.py checks this table against the header, symbol by symbol.
@@ -56,14 +67,18 @@ SIGNATURES = {
     "spgan_demod": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_f32, c_f32, c_vp]),
     "spgan_conv_wgrad": (c_int, [_PASS_P, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp]),
     "spgan_plane_dot": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp]),
-    "spgan_pack_act": (c_int, [c_vp, c_vp, c_vp] + [c_int] * 10 + [c_vp]),
+    "spgan_pack_act": (c_int, [c_vp, c_vp, c_vp] + [c_int] * 11 + [c_vp]),
     "spgan_conv_wgrad_gemm_workspace": (c_i64, [_PASS_P]),
     "spgan_conv_wgrad_gemm": (c_int, [_PASS_P, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_int, ctypes.POINTER(ctypes.c_int32),
                                       c_int, c_vp, c_i64, c_int, c_vp]),
-    "spgan_pack_weight": (c_int, [c_vp, c_vp, c_int, c_int, c_i64, c_i64, c_int, ctypes.POINTER(ctypes.c_int32), c_int, c_int, c_vp]),
+    "spgan_pack_weight": (c_int, [c_vp, c_vp, c_int, c_int, c_i64, c_i64, c_int, ctypes.POINTER(ctypes.c_int32), c_int, c_int, c_int, c_vp]),
     "spgan_nchw_to_nhwc": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp]),
-    "spgan_sphere_pack": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
+    "spgan_sphere_pack": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
     "spgan_conv_gemm": (c_int, [_PASS_P, c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "spgan_conv_gemm_ex": (c_int, [_PASS_P, ctypes.c_void_p, c_vp]),
+    "spgan_conv_gemm_rgb_slots": (c_int, [_PASS_P, c_i64]),
+    "spgan_upblur_pack": (c_int, [c_vp] * 7 + [c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_i64, c_int, c_f32, c_f32, c_vp]),
+    "spgan_rgb_tail": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp, c_i64, c_int, c_i64, c_vp]),
     "spgan_gemm_launch_count": (c_i64, []),
 }
 
@@ -89,8 +104,8 @@ def load():
             fn = getattr(lib, name)  # AttributeError here = header/library mismatch
             fn.restype = res
             fn.argtypes = args
-        if lib.spgan_abi_version() != 1:
-            raise RuntimeError("libspgan_b200.so ABI version %d, expected 1" % lib.spgan_abi_version())
+        if lib.spgan_abi_version() != 2:
+            raise RuntimeError("libspgan_b200.so ABI version %d, expected 2" % lib.spgan_abi_version())
         _lib = lib
     return _lib
 

@@ -202,3 +202,140 @@ def crop_to_target(meta, pl):
     ph = (meta.shape[2] - pl["target_h"]) // 2
     pw = (meta.shape[3] - pl["target_w"]) // 2
     return meta[:, :, ph:ph + pl["target_h"], pw:pw + pl["target_w"]]
+
+
+class PanoramaEngine:
+    """Steady-state panorama generation: static device buffers + ONE CUDA graph of the whole lattice loop.
+
+    The reference's manager issues one generator call per lattice position from Python and copies every patch to the
+    host (test_managers/base_test_manager.py:219-325).  Here the canvases live in fixed device buffers, the whole loop
+    (mapping network, per-layer modulation, `len(positions)` patch batches, assembly) is captured once and replayed,
+    and the lattice positions are spread over `streams` concurrent branches of the graph: the positions are independent
+    (SURVEY.md §8e), so the tail wave of one position's GEMM overlaps the head of another's, and the HBM-bound packers
+    / FIR kernels of one branch run under the tensor-bound GEMMs of the other.  Patches are parked in a per-position
+    buffer and written into the meta image after the join in the reference's row-major order, so the 5-pixel overlaps
+    resolve exactly as in the sequential loop.
+
+    load(gl, canvas, noises) copies new inputs (device or pinned host tensors) into the static buffers; run() returns
+    the static (B, 3, meta_h, meta_w) meta image.  `only` restricts the engine to a set of lattice positions (rank
+    sharding); `assemble=False` leaves the patches in `self.patches` (the sharded path exchanges them first)."""
+
+    def __init__(self, gen, pl, batch, device, streams=2, only=None, use_graph=True, assemble=True):
+        self.gen, self.pl, self.B, self.device = gen, pl, batch, torch.device(device)
+        self.pos = [(it, ix, iy) for it, (ix, iy) in enumerate(positions(pl)) if only is None or (ix, iy) in only]
+        self.n_streams = max(1, min(int(streams), len(self.pos)))
+        self.use_graph, self.assemble = use_graph, assemble
+        d = self.device
+        self.gl = torch.zeros(batch, 2, 512, device=d)
+        self.canvas = torch.zeros(batch, 256, pl["lat_h"], pl["lat_w"], device=d)
+        self.noises = [torch.zeros(batch, 1, pl["noise_h"][l], pl["noise_w"][l], device=d) for l in range(8)]
+        self.meta = torch.zeros(batch, 3, pl["meta_h"], pl["meta_w"], device=d)
+        self.patches = torch.zeros(len(self.pos), batch, 3, pl["patch"], pl["patch"], device=d)
+        self.coords_full = meta_coords(pl["lat_h"], pl["lat_w"], d).unsqueeze(0).expand(batch, -1, -1, -1)
+        self.graph = None
+        self._eager_runs = 0
+        self._side = [torch.cuda.Stream(device=d) for _ in range(self.n_streams - 1)]
+
+    def load(self, global_latent, local_latent, noises):
+        if global_latent.dim() == 2:
+            global_latent = torch.stack([global_latent, global_latent], 1)
+        self.gl.copy_(global_latent, non_blocking=True)
+        self.canvas.copy_(local_latent, non_blocking=True)
+        for dst, src in zip(self.noises, noises):
+            dst.copy_(src, non_blocking=True)
+
+    def _position(self, slot, styles):
+        it, ix, iy = self.pos[slot]
+        self.patches[slot].copy_(_run_position(self.gen, self.pl, self.gl, self.canvas, self.coords_full, self.noises,
+                                               styles, it, ix, iy))
+
+    def _body(self):
+        main = torch.cuda.current_stream(self.device)
+        styles = self.gen.texture_synthesizer.styles_for(self.gl)
+        # the first position runs alone on the launching stream: it computes every layer's memoised (modulation,
+        # demodulation) pair, which the concurrent branches then only read
+        self._position(0, styles)
+        if self.n_streams > 1 and len(self.pos) > 1:
+            fork = torch.cuda.Event()
+            fork.record(main)
+            lanes = [main] + self._side
+            for s in self._side:
+                s.wait_event(fork)
+            for slot in range(1, len(self.pos)):
+                with torch.cuda.stream(lanes[slot % len(lanes)]):
+                    self._position(slot, styles)
+            for s in self._side:
+                join = torch.cuda.Event()
+                join.record(s)
+                main.wait_event(join)
+        else:
+            for slot in range(1, len(self.pos)):
+                self._position(slot, styles)
+        if self.assemble:
+            P = self.pl["patch"]
+            for slot, (it, ix, iy) in enumerate(self.pos):
+                px, py = ix * self.pl["pix_step"], iy * self.pl["pix_step"]
+                circular_assign(self.meta, self.pl["meta_w"], px, px + P, py, py + P, self.patches[slot])
+
+    @torch.no_grad()
+    def run(self):
+        """Two eager passes first (they fill the sampling-grid, packed-weight and channel-map caches, whose uploads
+        cannot be captured), then capture, then replays."""
+        if not self.use_graph:
+            self._body()
+            return self.meta
+        if self.graph is None:
+            if self._eager_runs < 2:
+                self._eager_runs += 1
+                self._body()
+                return self.meta
+            from . import functional as SF
+            torch.cuda.synchronize(self.device)
+            SF.bump_style_epoch()  # the capture must contain the mapping / modulation kernels, not a memo hit
+            g = torch.cuda.CUDAGraph()
+            cap = torch.cuda.Stream(device=self.device)
+            cap.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.graph(g, stream=cap):
+                self._body()
+            torch.cuda.current_stream(self.device).wait_stream(cap)
+            self.graph = g
+        self.graph.replay()
+        return self.meta
+
+
+class ShardedPanoramaEngine:
+    """Multi-GPU generation of ONE batch of panoramas (BASELINE configs[3]): rank r owns lattice positions r, r + world,
+    ... (a PanoramaEngine over that subset, same graph + concurrent-branch machinery), the finished patches are exchanged
+    with ONE all-gather, and every rank assembles in the reference's row-major order (see generate_sharded)."""
+
+    def __init__(self, gen, pl, batch, device, rank, world, streams=2, use_graph=True):
+        self.pl, self.B, self.rank, self.world = pl, batch, rank, world
+        self.all_pos = positions(pl)
+        mine = self.all_pos[rank::world]
+        self.engine = PanoramaEngine(gen, pl, batch, device, streams=streams, only=set(mine), use_graph=use_graph,
+                                     assemble=False)
+        self.per_rank = -(-len(self.all_pos) // world)
+        P = pl["patch"]
+        self.mine = torch.zeros(self.per_rank, batch, 3, P, P, device=self.engine.device)
+        self.allp = torch.zeros(world, self.per_rank, batch, 3, P, P, device=self.engine.device) if world > 1 else None
+        self.meta = self.engine.meta
+
+    def load(self, global_latent, local_latent, noises):
+        self.engine.load(global_latent, local_latent, noises)
+
+    @torch.no_grad()
+    def run(self):
+        import torch.distributed as dist
+        self.engine.run()
+        n = self.engine.patches.shape[0]
+        self.mine[:n].copy_(self.engine.patches)
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.allp.view(self.world * self.per_rank, *self.mine.shape[1:]), self.mine)
+            allp = self.allp
+        else:
+            allp = self.mine.unsqueeze(0)
+        P = self.pl["patch"]
+        for it, (ix, iy) in enumerate(self.all_pos):
+            px, py = ix * self.pl["pix_step"], iy * self.pl["pix_step"]
+            circular_assign(self.meta, self.pl["meta_w"], px, px + P, py, py + P, allp[it % self.world, it // self.world])
+        return self.meta

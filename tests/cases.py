@@ -184,3 +184,28 @@ def generator_train_case():
     noises = [synth.randn_t(SEED, "tr_noise%d" % l, (B, 1, s, s)) for l, s in enumerate(O.TS_FEATURE_SIZES)]
     go = synth.randn_t(SEED, "tr_go", (B, 3, 101, 101))
     return gl, lat, coords, cps, noises, go
+
+
+def reference_gradient_sensitivity(net, key, fwd_err):
+    """How far the REFERENCE's own gradient `key` of `net` ("generator" / "discriminator") moves (relative L2) when its
+    forward output moves by `fwd_err` (relative L2), read off tests/golden/sensitivity.json: the reference was re-run
+    with its input perturbed by eps = 1e-6 .. 1e-3 and both changes were recorded (oracle/make_golden_r2.py).  Log-log
+    interpolation on the (forward change, gradient change) curve; keys that were not recorded use the largest recorded
+    curve of the same network.  Below the smallest recorded forward change the curve is held flat: that first point is
+    the reference's own noise floor under an fp32-rounding-sized perturbation."""
+    sens = load_json("sensitivity.json")[net]
+    fwd = np.asarray(sens["fwd"], dtype=np.float64)
+    names = [key] if key in sens else [k for k in sens if k != "fwd"]
+    best = 0.0
+    for k in names:
+        g = np.asarray(sens[k], dtype=np.float64)
+        order = np.argsort(fwd)
+        v = float(np.exp(np.interp(np.log(max(fwd_err, 1e-30)), np.log(fwd[order]), np.log(g[order]))))
+        best = max(best, v)
+    return best
+
+
+def rel_l2(a, b):
+    a = np.asarray(a, dtype=np.float64).reshape(-1)
+    b = np.asarray(b, dtype=np.float64).reshape(-1)
+    return float(np.sqrt(((a - b) ** 2).sum()) / max(np.sqrt((b ** 2).sum()), 1e-300))

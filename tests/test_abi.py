@@ -31,7 +31,7 @@ def test_binding_table_matches_header():
 def test_load_and_version_without_gpu():
     import spgan_b200.lib as lib
     h = lib.load()
-    assert h.spgan_abi_version() == 1
+    assert h.spgan_abi_version() == 2
     assert isinstance(lib.last_error(), str)
 
 

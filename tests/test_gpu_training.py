@@ -12,13 +12,21 @@ import synth
 
 pytestmark = pytest.mark.gpu
 
-# Network-level gradient bounds (relative L2 / relative norm).  Per-op gradients are held to 1e-4..1e-5 in
-# test_gpu_ops.py and in test_second_order_through_styled_conv below; through a whole network the leaky-ReLU gates turn
-# forward rounding noise e into a gradient change of ~sqrt(0.4 e) per layer (cases.compact_l2), which is what these
-# bounds allow for the bf16x3 forward error of ~2e-4 (measured: 2e-3 in exact-fp32 mode, 9e-3 in bf16x3 mode; the same
-# size as the change of OUR gradient under a 1e-6 relative perturbation of the input, see test_gradient_sensitivity).
-NET_GRAD_L2 = 3e-2
-NET_GRAD_NORM = 3e-3
+# Network-level gradient bounds.  Per-op gradients are held to 1e-4..1e-5 in test_gpu_ops.py and in
+# test_second_order_through_styled_conv below.  Through a whole network the leaky-ReLU gates make the gradient a
+# discontinuous function of the activations, and the REFERENCE ITSELF shows it: re-run with its input perturbed by a
+# relative 1e-6 (forward output moves by 6e-7 / 2e-6), its own discriminator input gradient moves by 2.1e-3 and its own
+# generator latent gradient by 1.3e-3 in relative L2; at a forward change of 9e-5 they move by 8.9e-3 / 1.8e-2
+# (tests/golden/sensitivity.json, written by oracle/make_golden_r2.py from the real reference).  The bound for each
+# gradient is therefore SENS_FACTOR x the reference's own movement at the forward error this implementation has on the
+# same case (cases.reference_gradient_sensitivity), not a constant.
+SENS_FACTOR = 2.0
+NET_GRAD_NORM = 3e-3  # gradient norms (not gated element-wise) agree far better than the element-wise L2
+
+
+def _net_bounds(net, key, fwd_err):
+    s = K.reference_gradient_sensitivity(net, key, fwd_err)
+    return SENS_FACTOR * s, NET_GRAD_NORM
 
 
 @pytest.fixture(scope="module")
@@ -43,19 +51,25 @@ def test_discriminator_golden_forward_grads_and_r1(dev):
     out = disc(img)
     d, ac = out["d_patch"], out["ac_coords_pred"]
     assert K.rel_err(K.t2n(d), g["d"]) < 5e-4 and K.rel_err(K.t2n(ac), g["ac"]) < 5e-4
+    fwd_err = max(K.rel_l2(K.t2n(d), g["d"]), 6e-7)
     params = dict(disc.named_parameters())
     loss = F.softplus(-d).mean() + (ac * synth.randn_t(K.SEED, "d_acw", ac.shape).to(dev)).sum()
     grads = torch.autograd.grad(loss, [img] + [params[n] for n in K.D_GRAD_KEYS], retain_graph=True)
+    report = {}
     for n, got in zip(["img"] + K.D_GRAD_KEYS, grads):
         l2, dn = K.compact_l2(g, "g_" + n, K.t2n(got))
-        assert l2 < NET_GRAD_L2 and dn < NET_GRAD_NORM, (n, l2, dn)
+        b_l2, b_n = _net_bounds("discriminator", "g_" + n, fwd_err)
+        report[n] = (l2, b_l2)
+        assert l2 < b_l2 and dn < b_n, (n, l2, dn, b_l2, b_n, fwd_err)
+    print("D forward rel-L2 %.2e; gradient rel-L2 (got, bound):" % fwd_err, {k: "%.1e/%.1e" % v for k, v in report.items()})
     from spgan_b200.training import d_r1_loss
     r1 = d_r1_loss(d, img)
     assert abs(float(r1) - float(g["r1"])) < 1e-3 * abs(float(g["r1"]))
     g2 = torch.autograd.grad(r1, [params[n] for n in K.D_GRAD_KEYS[:6]], allow_unused=True)
     for n, got in zip(K.D_GRAD_KEYS[:6], g2):
         l2, dn = K.compact_l2(g, "r1g_" + n, K.t2n(got))
-        assert l2 < 2 * NET_GRAD_L2 and dn < 2 * NET_GRAD_NORM, ("r1 " + n, l2, dn)
+        b_l2, b_n = _net_bounds("discriminator", "r1g_" + n, fwd_err)
+        assert l2 < 2 * b_l2 and dn < 2 * b_n, ("r1 " + n, l2, dn, b_l2, b_n)
 
 
 def test_gradient_sensitivity_explains_network_level_bound(dev):
@@ -85,9 +99,12 @@ def test_gradient_sensitivity_explains_network_level_bound(dev):
         SF.set_precision(prev)
     sens = float((g1 - g0).norm() / g0.norm())
     l2, _ = K.compact_l2(g, "g_img", K.t2n(g0))
-    print("self-sensitivity to a 1e-6 input perturbation: %.2e; distance to golden: %.2e" % (sens, l2))
+    ref_sens = K.load_json("sensitivity.json")["discriminator"]["g_img"][0]
+    print("self-sensitivity to a 1e-6 input perturbation: %.2e (the reference's own: %.2e); distance to golden: %.2e"
+          % (sens, ref_sens, l2))
     assert sens > 1e-4
-    assert l2 < 20 * sens
+    assert 0.2 * ref_sens < sens < 5 * ref_sens  # this implementation is as ill-conditioned as the reference, not more
+    assert l2 < SENS_FACTOR * ref_sens
 
 
 def _styled(kind, dev):
@@ -142,11 +159,16 @@ def test_generator_train_mode_golden_forward_and_grads(dev):
     lat = lat.to(dev).requires_grad_(True)
     img = gen(gl.to(dev), lat, coords.to(dev), cps, noises=[n.to(dev) for n in noises], inject_index=5)
     assert K.compact_check(g, "img", K.t2n(img), 5e-4)
+    fwd_err = max(K.compact_l2(g, "img", K.t2n(img))[0], 1.7e-6)
     params = dict(gen.named_parameters())
     grads = torch.autograd.grad((img * go.to(dev)).sum(), [lat] + [params[k] for k in K.TRAIN_GRAD_KEYS])
+    report = {}
     for k, got in zip(["lat"] + K.TRAIN_GRAD_KEYS, grads):
         l2, dn = K.compact_l2(g, "g_" + k, K.t2n(got))
-        assert l2 < NET_GRAD_L2 and dn < NET_GRAD_NORM, (k, l2, dn)
+        b_l2, b_n = _net_bounds("generator", "g_" + k, fwd_err)
+        report[k.split(".")[-3] + "." + k.split(".")[-1] if "." in k else k] = (l2, b_l2)
+        assert l2 < b_l2 and dn < b_n, (k, l2, dn, b_l2, b_n, fwd_err)
+    print("G forward rel-L2 %.2e; gradient rel-L2 (got, bound):" % fwd_err, {k: "%.1e/%.1e" % v for k, v in report.items()})
 
 
 def test_one_training_iteration_runs_and_updates(dev):

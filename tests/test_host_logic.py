@@ -144,7 +144,12 @@ def test_bench_reference_arm_prints_contract_line():
     for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
                 "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert key in line, key
-    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    assert line["impl"] == "reference" and line["value"] > 0
+    # the real reference when it is present (/root/reference here, oracle/_ref on the GPU box), else the oracle port
+    sys.path.insert(0, os.path.join(root, "oracle"))
+    import refimport
+    assert line["cpu_baseline"]["kind"] == ("reference" if refimport.available() else "port")
+    assert len(out.stdout.strip().splitlines()) == 1, "the arm must print exactly one line on stdout"
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     # other ranks of a torchrun launch exit 0 without work
     env = dict(os.environ, RANK="1", WORLD_SIZE="2")

@@ -146,7 +146,7 @@ def main():
         import ctypes
         p = lambda t: ctypes.c_void_p(t.data_ptr())
         st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-        ms = timed(lambda: lib.call("spgan_pack_act", p(out), p(x), p(s), 32, 512, 103, 103, 512, 0, 0, 103, 103, 1, st))
+        ms = timed(lambda: lib.call("spgan_pack_act", p(out), p(x), p(s), 32, 512, 103, 103, 512, 0, 0, 103, 103, 1, 0, st))
         report("pack_act (32,512,103,103) -> bf16 hi/lo channels-last", ms, bytes_=4 * x.numel() + out.numel() * 2)
     case("pack_act", pack)
 
