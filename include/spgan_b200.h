@@ -129,7 +129,8 @@ typedef struct SpganConvPass {
   int32_t act;                    /* 0 = none, 1 = leaky relu */
   float act_alpha, act_gain;
   int32_t precision;              /* 0 = fp32 SIMT, 1 = bf16x3 split on tcgen05 (fp32-equivalent), 2 = bf16 on tcgen05,
-                                     3 = fp16x2 on tcgen05 (fp16 hi+lo activations x fp16 weights, relative error ~2^-12) */
+                                     3 = fp16x2 on tcgen05 (fp16 hi+lo activations x fp16 weights, relative error ~2^-12;
+                                     activations beyond +-65504 saturate: the host pre-scales them by a power of two) */
   int64_t out_cstride;            /* elements between output channels; 0 = out_H*out_W (dense NCHW).  A larger stride
                                      lets the parity passes of a transposed conv write polyphase planes
                                      (B, Cout, s*s, Hq, Wq) instead of scattering with stride s (see spgan_upblur_act) */
@@ -211,14 +212,16 @@ int spgan_conv_gemm(const SpganConvPass* p, float* y, const uint16_t* a_packed, 
  *       its columns to slot 2*tile_n + half of rgb_part (slots, B, rgb_n, out_H*out_W), slots =
  *       spgan_conv_gemm_rgb_slots(p, a_rows); spgan_rgb_tail adds the slots in a fixed order (deterministic).
  *   y may be NULL when another sink is present (the last texture layer is consumed by ToRGB alone).  The extra sinks need
- *   Cout % 32 == 0 and exclude `residual`.  fmt is the operand format of a_packed / w_packed and must match
- *   p->precision (0 for 1 and 2, 1 for 3). */
+ *   Cout % 32 == 0 and exclude `residual`.  fmt / w_fmt are the 16-bit formats of a_packed / w_packed (0 = bf16 planes,
+ *   1 = fp16 planes) and must match p->precision: (0, 0) for 1 and 2, (1, 1) for 3.  Mixed formats inside one MMA are
+ *   rejected by the hardware (illegal instruction, measured), hence no bf16-activation x fp16-weight mode. */
 typedef struct SpganGemmIO {
   const uint16_t* a_packed;
   int64_t a_rows;
   int32_t kp;
   int32_t fmt;
   const uint16_t* w_packed;
+  int64_t w_fmt;
   const float* out_mul;
   const float* noise;
   const float* noise_w;

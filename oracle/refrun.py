@@ -53,7 +53,7 @@ def manager(gen, config, device, H, W, batch=1):
     return mgr
 
 
-def testing_vars(mgr, plan, tag, batch=1, seed=SEED):
+def testing_vars(mgr, plan, tag, batch=1, seed=SEED, device="cpu"):
     """Inputs named `<tag>_gl`, `<tag>_canvas`, `<tag>_noise<l>` (the names tests/ regenerate), held on the CPU as the
     reference manager expects (close_loop_infinite_generation.py:84-168)."""
     import torch
@@ -63,8 +63,10 @@ def testing_vars(mgr, plan, tag, batch=1, seed=SEED):
     canvas = synth.randn_t(seed, tag + "_canvas", (batch, 256, plan["lat_h"], plan["lat_w"]))
     noises = [synth.randn_t(seed, "%s_noise%d" % (tag, l), (batch, 1, plan["noise_h"][l], plan["noise_w"][l])) for l in range(8)]
     meta_coords = mgr.coord_handler.sample_coord_grid(canvas, is_training=False)
-    tv = TestingVars(meta_img=torch.zeros(batch, 3, plan["meta_h"], plan["meta_w"]), global_latent=gl, local_latent=canvas,
-                     meta_coords=meta_coords, noises=noises, device="cpu")
+    # the canvases stay on the CPU (the manager moves every slice, close_loop_infinite_generation.py:204-230); the global
+    # latent is created on the model's device, as create_vars does (:84-102)
+    tv = TestingVars(meta_img=torch.zeros(batch, 3, plan["meta_h"], plan["meta_w"]), global_latent=gl.to(device),
+                     local_latent=canvas, meta_coords=meta_coords, noises=noises, device=device)
     return tv, gl, canvas, noises
 
 

@@ -40,7 +40,7 @@ struct GemmParams {
   float out_scale;
   int32_t act;
   float act_alpha, act_gain;
-  int32_t f16;             // operand format: 0 = bf16 planes, 1 = fp16 planes (instruction descriptor A/B format)
+  int32_t a_f16, b_f16;    // operand formats: 0 = bf16 planes, 1 = fp16 planes (instruction descriptor A / B format)
   // ---- output sinks (any combination; y may be null)
   int32_t y_nhwc;          // 0: y is NCHW fp32 (out_cstride between channels), 1: y is NHWC fp32 (channel fastest)
   int64_t y_bstride;       // NHWC: elements between samples
@@ -187,7 +187,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int n0 = (tile % gp.n_tiles) * kBlockN;
         int n_eff = gp.Cout - n0;
         n_eff = n_eff > kBlockN ? kBlockN : ((n_eff + 15) & ~15);
-        const uint32_t idesc = umma_idesc_16(n_eff, gp.f16 != 0);
+        const uint32_t idesc = umma_idesc_16(n_eff, gp.a_f16 != 0, gp.b_f16 != 0);
         const int as = titer & 1;
         const uint32_t aphase = (uint32_t)(titer >> 1) & 1u;
         mbar_wait(tempty_bar(as), aphase ^ 1u);
@@ -918,8 +918,11 @@ extern "C" int spgan_conv_gemm_ex(const SpganConvPass* p, const SpganGemmIO* io,
   SPGAN_CHECK_ARG(p != nullptr && io != nullptr, "spgan_conv_gemm: null descriptor");
   SPGAN_CHECK_ARG(p->precision >= 1 && p->precision <= 3,
                   "spgan_conv_gemm: precision must be 1 (bf16x3), 2 (bf16) or 3 (fp16x2), got %d", p->precision);
-  SPGAN_CHECK_ARG(io->fmt == (p->precision == 3 ? 1 : 0), "spgan_conv_gemm: operand format %d does not match precision %d "
-                  "(bf16 planes for 1 and 2, fp16 planes for 3)", io->fmt, p->precision);
+  // both operands of one kind::f16 MMA must share a format: a bf16 A with an fp16 B raises an illegal-instruction fault
+  // on the B200 (tools/probes/mixed_fmt.py), so there is no "bf16 hi/lo activations x fp16 weights" mode
+  SPGAN_CHECK_ARG(io->fmt == (p->precision == 3 ? 1 : 0) && io->w_fmt == io->fmt,
+                  "spgan_conv_gemm: operand formats (A %d, W %d) do not match precision %d (bf16 planes for 1 and 2, fp16 planes "
+                  "for 3)", io->fmt, (int)io->w_fmt, p->precision);
   SPGAN_CHECK_ARG(p->ntaps >= 1 && p->ntaps <= SPGAN_MAX_TAPS, "spgan_conv_gemm: %d taps unsupported", p->ntaps);
   SPGAN_CHECK_ARG(p->in_stride == 1, "spgan_conv_gemm: in_stride %d unsupported on the tcgen05 path", p->in_stride);
   const int kp = io->kp;
@@ -997,7 +1000,8 @@ extern "C" int spgan_conv_gemm_ex(const SpganConvPass* p, const SpganGemmIO* io,
   gp.act = p->act;
   gp.act_alpha = p->act_alpha;
   gp.act_gain = p->act_gain;
-  gp.f16 = io->fmt;
+  gp.a_f16 = io->fmt;
+  gp.b_f16 = io->w_fmt;
   gp.y_nhwc = io->y_layout != 0 ? 1 : 0;
   gp.y_bstride = io->y_bstride ? io->y_bstride : (int64_t)p->out_H * p->out_W * p->Cout;
   gp.pk_rows = io->y_packed_rows;
@@ -1052,6 +1056,7 @@ extern "C" int spgan_conv_gemm(const SpganConvPass* p, float* y, const uint16_t*
   io.a_rows = a_rows;
   io.kp = kp;
   io.fmt = p->precision == 3 ? 1 : 0;
+  io.w_fmt = io.fmt;
   io.w_packed = w_packed;
   io.out_mul = out_mul;
   io.noise = noise;

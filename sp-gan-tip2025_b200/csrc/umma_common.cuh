@@ -114,10 +114,10 @@ __device__ __forceinline__ uint32_t umma_idesc_bf16(int n) {
          | ((uint32_t)(n >> 3) << 17)
          | ((uint32_t)(GEMM_BLOCK_M >> 4) << 24);  // A, B K-major: bits 15, 16 stay 0
 }
-// kind::f16 descriptor with both operands fp16 (format code 0) or both bf16 (format code 1).
-__device__ __forceinline__ uint32_t umma_idesc_16(int n, bool f16) {
-  const uint32_t fmt = f16 ? 0u : 1u;
-  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(GEMM_BLOCK_M >> 4) << 24);
+// kind::f16 descriptor; each operand is fp16 (format code 0) or bf16 (format code 1), independently.
+__device__ __forceinline__ uint32_t umma_idesc_16(int n, bool a_f16, bool b_f16) {
+  return (1u << 4) | ((a_f16 ? 0u : 1u) << 7) | ((b_f16 ? 0u : 1u) << 10) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(GEMM_BLOCK_M >> 4) << 24);
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);

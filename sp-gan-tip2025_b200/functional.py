@@ -19,7 +19,8 @@ from .lib import ConvPass
 
 # 0 = exact fp32 SIMT, 1 = bf16x3 split on tcgen05 (fp32-equivalent, default), 2 = plain bf16 on tcgen05,
 # 3 = fp16x2 on tcgen05 (fp16 hi+lo activations x fp16 weights: 2 MMAs per product, relative error ~2^-12; forward only —
-# gradients keep the bf16x3 split because their range does not fit fp16)
+# gradients keep the bf16x3 split because their range does not fit fp16; activations beyond 65504 saturate, so callers
+# pre-scale by a power of two, see TextureSynthesizer.act_scale)
 _PRECISION = 1
 
 
@@ -31,7 +32,12 @@ def set_precision(p):
 
 
 def _fmt(precision):
-    """Operand format of a precision mode: 0 = bf16 hi/lo planes, 1 = fp16 hi/lo planes."""
+    """Activation operand format of a precision mode: 0 = bf16 hi/lo planes, 1 = fp16 hi/lo planes."""
+    return 1 if precision == 3 else 0
+
+
+def _wfmt(precision):
+    """Weight operand format of a precision mode."""
     return 1 if precision == 3 else 0
 
 
@@ -574,7 +580,7 @@ def conv_apply(x, w, geom, adjoint=False, out_hw=None, in_mul=None, out_mul=None
         Cin, Cout, ws_o, ws_c = O, C, kk, C * kk
         oh, ow = out_hw
     precision = _PRECISION if precision is None else precision
-    if precision == 3 and adjoint:
+    if precision >= 3 and adjoint:
         precision = 1  # data gradients: fp16 has too little range
     fmt = _fmt(precision)
     passes, covers = plan_passes(geom, adjoint, (H, W), (oh, ow))
@@ -630,7 +636,7 @@ def conv_apply(x, w, geom, adjoint=False, out_hw=None, in_mul=None, out_mul=None
                 q, yptr, o_h, o_w, cst = target(p)
                 shifted = dict(q, in_stride=1, taps=[(ph * B * Hl + oy, ox, wi) for ph, oy, ox, wi in taps])
                 cp = _fill_pass(shifted, B, Cin, Hl, Wl, Cout, o_h, o_w, ws_o, ws_c, out_scale, act_on, a, g, precision, cst)
-                wp = _packed_weight(w, Cout, Cin, ws_o, ws_c, [t[2] for t in p["taps"]], Cp, False, fmt)
+                wp = _packed_weight(w, Cout, Cin, ws_o, ws_c, [t[2] for t in p["taps"]], Cp, False, _wfmt(precision))
                 valid = min(p["My"], _ceil_div(oh - p["off_y"], p["out_stride"])) * min(p["Mx"], _ceil_div(ow - p["off_x"], p["out_stride"]))
                 _gemm_call(2.0 * B * valid * Cout * Cin * len(p["taps"]), ctypes.byref(cp), yptr, _ptr(a_packed),
                            step * step * rows, Cp, _ptr(wp), _ptr(om), _ptr(nz), _ptr(nwt), _ptr(bs), _ptr(rs), st)
@@ -659,7 +665,7 @@ def conv_wgrad(g, x, w_shape, geom, in_mul=None, out_mul=None, out_scale=1.0, pr
     im = _f32c(in_mul, "conv wgrad") if in_mul is not None else None
     om = _f32c(out_mul, "conv wgrad") if out_mul is not None else None
     precision = _PRECISION if precision is None else precision
-    if precision == 3:
+    if precision >= 3:
         precision = 1  # weight gradients: fp16 has too little range
     if passes and _tensor_path_ok(passes, C, O, precision) and len({p["out_stride"] for p in passes}) == 1:
         # tcgen05: contraction over the flattened lattice rows of the same channels-last packs the forward GEMM reads
@@ -857,7 +863,7 @@ def sphere_modconv_fused(x, coords, grid, w, in_mul, out_mul, out_scale, act=Non
         cmap = _sphere_chan_map(B, C, nc, Cp, bool(flat_concat), x.device)
         lib.call("spgan_sphere_pack", _ptr(a_packed), _ptr(xh), _ptr(cc), _ptr(grid), _ptr(im), _ptr(cmap), B, C, H, W,
                  grid.shape[0], Cp, _fmt(precision), st)
-        wp = _packed_weight(w, O, Ct, Ct * 9, 9, list(range(9)), Cp, True, _fmt(precision))
+        wp = _packed_weight(w, O, Ct, Ct * 9, 9, list(range(9)), Cp, True, _wfmt(precision))
         p = dict(My=H, Mx=W, in_stride=1, out_stride=1, off_y=0, off_x=0, taps=[(0, 0, 0)])
         cp = _fill_pass(p, B, Ct, H, W, O, H, W, Ct * 9, 9, out_scale, 1 if act is not None else 0, a, g, precision)
         om = _f32c(out_mul, "sphere_modconv") if out_mul is not None else None
@@ -999,10 +1005,10 @@ def chain_upconv(a, B, H, W, w, out_mul, out_scale, precision):
         for p, taps in zip(passes, mapped):
             q = dict(p, in_stride=1, out_stride=1, off_y=0, off_x=0, taps=[(oy, ox, wi) for _, oy, ox, wi in taps])
             cp = _fill_pass(q, B, C, H, W, O, H, W, C * 9, 9, out_scale, 0, 0.0, 1.0, precision)
-            wp = _packed_weight(w, O, C, C * 9, 9, [t[2] for t in p["taps"]], Cp, False, fmt)
+            wp = _packed_weight(w, O, C, C * 9, 9, [t[2] for t in p["taps"]], Cp, False, _wfmt(precision))
             plane = p["off_y"] * 2 + p["off_x"]
             _gemm_ex(cp, 2.0 * B * p["My"] * p["Mx"] * O * C * len(taps), st, a_packed=a, a_rows=B * H * W, kp=Cp, fmt=fmt,
-                     w_packed=wp, out_mul=out_mul, y=pp.data_ptr() + 4 * plane * H * W * O, y_layout=1,
+                     w_fmt=_wfmt(precision), w_packed=wp, out_mul=out_mul, y=pp.data_ptr() + 4 * plane * H * W * O, y_layout=1,
                      y_bstride=4 * H * W * O)
     return pp, (oh, ow)
 
@@ -1044,7 +1050,7 @@ def chain_conv3(a, B, H, W, w, out_mul, out_scale, noise, noise_w, bias, act, pr
     kw = {}
     packed = rgb = y = None
     with torch.cuda.device(a.device):
-        wp = _packed_weight(w, O, C, C * 9, 9, list(range(9)), Cp, False, fmt)
+        wp = _packed_weight(w, O, C, C * 9, 9, list(range(9)), Cp, False, _wfmt(precision))
         if next_precision is not None:
             packed = torch.empty((2, B * oh * ow, O), device=a.device, dtype=torch.bfloat16)
             kw.update(y_packed=packed, next_mul=next_mul, y_packed_rows=B * oh * ow, y_packed_cols=O,
@@ -1057,7 +1063,8 @@ def chain_conv3(a, B, H, W, w, out_mul, out_scale, noise, noise_w, bias, act, pr
         if want_nchw:
             y = torch.empty((B, O, oh, ow), device=a.device, dtype=torch.float32)
             kw.update(y=y)
-        _gemm_ex(cp, 2.0 * B * oh * ow * O * C * 9, st, a_packed=a, a_rows=B * H * W, kp=Cp, fmt=fmt, w_packed=wp,
+        _gemm_ex(cp, 2.0 * B * oh * ow * O * C * 9, st, a_packed=a, a_rows=B * H * W, kp=Cp, fmt=fmt, w_fmt=_wfmt(precision),
+                 w_packed=wp,
                  out_mul=out_mul, noise=nz, noise_w=noise_w if nz is not None else None, bias=bias, **kw)
     return packed, rgb, y, (oh, ow)
 

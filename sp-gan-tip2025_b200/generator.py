@@ -223,6 +223,25 @@ class TextureSynthesizer(nn.Module):
     # layers nearest the output (whose rounding error is not amplified by later layers) run the 2-MMA fp16 split.
     layer_precision = None
     use_chain = True
+    # Power-of-two divisors of each layer's INPUT operand, used only where that layer runs mode 3 (fp16 planes saturate at
+    # 65504, and nothing bounds the activations of a GAN): the producer folds 1 / act_scale[i] into the style modulation it
+    # already applies, the consumer folds act_scale[i] into its output scale — both exact.  calibrate_act_scales() sets
+    # them from one forward so that the largest operand value maps to ~2^8 (256x headroom).
+    act_scale = None
+
+    def calibrate_act_scales(self, styles, structure_latent, coords_partial, noises):
+        """One bf16x3 pass of the chain that records max |operand| of every layer -> power-of-two act_scale."""
+        import math
+        saved, self.layer_precision = self.layer_precision, None
+        rec = []
+        try:
+            with torch.no_grad():
+                self._forward_chain(styles, structure_latent, coords_partial, noises, record=rec)
+        finally:
+            self.layer_precision = saved
+        amax = torch.stack(rec).tolist()  # one host sync: calibration is not on the hot path
+        self.act_scale = [2.0 ** math.ceil(math.log2(max(a, 1e-30) / 256.0)) for a in amax]
+        return self.act_scale
 
     def _chain_modes(self):
         g = SF.get_precision()
@@ -248,7 +267,17 @@ class TextureSynthesizer(nn.Module):
                 return False
         return all(n is not None for n in noises)
 
-    def _forward_chain(self, styles, structure_latent, coords_partial, noises):
+    def _scaled_mul(self, i, s, modes):
+        """Style modulation of layer i with 1 / act_scale[i] folded in when the layer runs mode 3."""
+        if modes[i] != 3 or self.act_scale is None or self.act_scale[i] == 1.0:
+            return s, 1.0
+        cache = self.__dict__.setdefault("_scaled_mul_cache", {})
+        hit = cache.get(i)
+        if hit is None or hit[0] is not s or hit[1] != self.act_scale[i]:
+            hit = cache[i] = (s, self.act_scale[i], s * (1.0 / self.act_scale[i]))
+        return hit[2], self.act_scale[i]
+
+    def _forward_chain(self, styles, structure_latent, coords_partial, noises, record=None):
         """The synthesis loop with channels-last operands between the convs (csrc/chain.cu): per (upsampling conv, conv)
         pair 4 parity GEMMs -> FIR tail writing the conv's packed operand -> GEMM writing the next pair's packed operand
         and the ToRGB partial sums -> rgb tail.  No fp32 activation of the texture synthesiser is written to HBM."""
@@ -256,14 +285,22 @@ class TextureSynthesizer(nn.Module):
         modes = self._chain_modes()
         sd = [conv.conv._mod_demod(styles[:, i], B) for i, conv in enumerate(self.convs)]
         H, W = structure_latent.shape[2], structure_latent.shape[3]
-        a = SF.chain_pack_input(structure_latent, sd[0][0], modes[0])
+        mul0, k_in = self._scaled_mul(0, sd[0][0], modes)
+        a = SF.chain_pack_input(structure_latent, mul0, modes[0])
         skip = None
+
+        def note(t):
+            if record is not None:
+                record.append(t.view(torch.bfloat16)[0].abs().max().float())
+        note(a)
         for k in range(self.num_layers // 2):
             up, cv = self.convs[2 * k], self.convs[2 * k + 1]
             (s_u, w_u, d_u), (s_c, w_c, d_c) = sd[2 * k], sd[2 * k + 1]
-            pp, zhw = SF.chain_upconv(a, B, H, W, w_u, d_u, up.conv.scale, modes[2 * k])
+            pp, zhw = SF.chain_upconv(a, B, H, W, w_u, d_u, up.conv.scale * k_in, modes[2 * k])
+            mul_c, k_in = self._scaled_mul(2 * k + 1, s_c, modes)
             a, (H, W) = SF.chain_upblur_pack(pp, zhw, up.conv.blur.kernel, noises[2 * k], up.noise.weight, up.activate.bias,
-                                             s_c, modes[2 * k + 1], up.activate.negative_slope, up.activate.scale)
+                                             mul_c, modes[2 * k + 1], up.activate.negative_slope, up.activate.scale)
+            note(a)
             last = 2 * k + 2 >= self.num_layers
             rgb_mod = self.to_rgbs[k]
             s_r, w_r, _ = rgb_mod.conv._mod_demod(styles[:, self.TO_RGBS[k][1]], B)
@@ -273,10 +310,14 @@ class TextureSynthesizer(nn.Module):
                 object.__setattr__(rgb_mod, "_rgbw_cache", (s_r, w_r._version, rgb_w))
             else:
                 rgb_w = cached[2]
-            a, rgb, _, (H, W) = SF.chain_conv3(a, B, H, W, w_c, d_c, cv.conv.scale, noises[2 * k + 1], cv.noise.weight,
+            mul_n, k_next = (None, 1.0) if last else self._scaled_mul(2 * k + 2, sd[2 * k + 2][0], modes)
+            a, rgb, _, (H, W) = SF.chain_conv3(a, B, H, W, w_c, d_c, cv.conv.scale * k_in, noises[2 * k + 1], cv.noise.weight,
                                                cv.activate.bias, (cv.activate.negative_slope, cv.activate.scale),
-                                               modes[2 * k + 1], next_mul=None if last else sd[2 * k + 2][0],
+                                               modes[2 * k + 1], next_mul=mul_n,
                                                next_precision=None if last else modes[2 * k + 2], rgb_w=rgb_w)
+            k_in = k_next
+            if not last:
+                note(a)
             i = 2 * k + 1
             if i in self.I2J:
                 skip = self.sp_convs[self.I2J[i]](skip, coords_partial)

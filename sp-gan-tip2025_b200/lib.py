@@ -38,7 +38,7 @@ class GemmIO(ctypes.Structure):
     """Mirror of `SpganGemmIO` (include/spgan_b200.h)."""
     _fields_ = [
         ("a_packed", c_vp), ("a_rows", ctypes.c_int64), ("kp", ctypes.c_int32), ("fmt", ctypes.c_int32),
-        ("w_packed", c_vp), ("out_mul", c_vp), ("noise", c_vp), ("noise_w", c_vp), ("bias", c_vp), ("residual", c_vp),
+        ("w_packed", c_vp), ("w_fmt", ctypes.c_int64), ("out_mul", c_vp), ("noise", c_vp), ("noise_w", c_vp), ("bias", c_vp), ("residual", c_vp),
         ("y", c_vp), ("y_layout", ctypes.c_int32), ("rgb_n", ctypes.c_int32), ("y_bstride", ctypes.c_int64),
         ("y_packed", c_vp), ("next_mul", c_vp), ("y_packed_rows", ctypes.c_int64), ("y_packed_cols", ctypes.c_int32),
         ("y_packed_fmt", ctypes.c_int32), ("rgb_w", c_vp), ("rgb_part", c_vp),

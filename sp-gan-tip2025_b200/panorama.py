@@ -233,6 +233,7 @@ class PanoramaEngine:
         self.patches = torch.zeros(len(self.pos), batch, 3, pl["patch"], pl["patch"], device=d)
         self.coords_full = meta_coords(pl["lat_h"], pl["lat_w"], d).unsqueeze(0).expand(batch, -1, -1, -1)
         self.graph = None
+        self._calibrated = False
         self._eager_runs = 0
         self._side = [torch.cuda.Stream(device=d) for _ in range(self.n_streams - 1)]
 
@@ -277,10 +278,35 @@ class PanoramaEngine:
                 px, py = ix * self.pl["pix_step"], iy * self.pl["pix_step"]
                 circular_assign(self.meta, self.pl["meta_w"], px, px + P, py, py + P, self.patches[slot])
 
+    def _calibrate(self):
+        """Mode-3 (fp16) layers of the texture chain need power-of-two operand scales: taken from the first lattice
+        position of the current inputs (TextureSynthesizer.calibrate_act_scales), once, before the capture."""
+        ts = getattr(self.gen, "texture_synthesizer", None)
+        modes = getattr(ts, "layer_precision", None)
+        if ts is None or modes is None or 3 not in modes or ts.act_scale is not None:
+            return
+        it, ix, iy = self.pos[0]
+        holder = {}
+        orig = ts._forward_chain
+
+        def spy(styles, structure, cp, noises, record=None):
+            holder["args"] = (styles, structure, cp, noises)
+            return orig(styles, structure, cp, noises, record=record)
+        ts._forward_chain = spy
+        try:
+            styles = ts.styles_for(self.gl)
+            _run_position(self.gen, self.pl, self.gl, self.canvas, self.coords_full, self.noises, styles, it, ix, iy)
+        finally:
+            del ts._forward_chain
+        ts.calibrate_act_scales(*holder["args"])
+
     @torch.no_grad()
     def run(self):
         """Two eager passes first (they fill the sampling-grid, packed-weight and channel-map caches, whose uploads
         cannot be captured), then capture, then replays."""
+        if not self._calibrated:
+            self._calibrate()
+            self._calibrated = True
         if not self.use_graph:
             self._body()
             return self.meta

@@ -34,6 +34,10 @@ import cases as K
 import spgan_oracle as O
 torch.cuda.set_device(0)
 lib.require_device()
+# SphereConditionalBlock.sc is a plain nn.Conv2d of the reference (models/spgan/spgan.py:141), not a mirrored module: keep
+# cuDNN in true fp32 (torch's default lets it use TF32, error ~1e-3) so the comparison with the CPU fixtures is fp32 vs fp32
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
 gen = refrun.synthetic_generator(config, Gen, K.load_json("generator_manifest.json")).cuda().eval()
 assert type(gen.texture_synthesizer.convs[0]) is mirror_ops.StyledConv
 out = {}
@@ -47,7 +51,7 @@ with torch.no_grad():
         out["patch_" + name] = K.rel_err(K.t2n(img), g["img_" + name])
     mgr = refrun.manager(gen, config, "cuda", 384, 768)
     plan = O.close_loop_plan(384, 768)
-    tv, _, _, _ = refrun.testing_vars(mgr, plan, "pano")
+    tv, _, _, _ = refrun.testing_vars(mgr, plan, "pano", device="cuda")
     import contextlib
     with contextlib.redirect_stdout(sys.stderr):
         mgr.generate(tv, disable_pbar=True)

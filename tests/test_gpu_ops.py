@@ -2,8 +2,9 @@
 
 Tolerances: bit-exact for sampling indices; <= 1e-5 relative-to-peak for the HBM-bound fp32 kernels and the exact
 fp32 SIMT conv; <= 1e-4 for the bf16x3 tcgen05 conv (fp32-equivalent, north_star bound 1e-3); <= 3e-2 for the
-plain-bf16 tcgen05 mode (the stated looser bound for bf16 paths); <= 4e-4 for the 2-MMA fp16 split (mode 3: one operand
-carries 11 significant bits, per-op error ~2^-12; forward only, gradients fall back to bf16x3)."""
+plain-bf16 tcgen05 mode (the stated looser bound for bf16 paths); <= 4e-4 for the 2-MMA fp16 split (mode 3: fp16 hi+lo
+activations x fp16 weights — one operand carries 11 significant bits, per-op error ~2^-12; forward only, gradients fall
+back to bf16x3)."""
 import numpy as np
 import pytest
 import torch
@@ -16,6 +17,7 @@ import synth
 pytestmark = pytest.mark.gpu
 
 TOL = {0: 1e-5, 1: 1e-4, 2: 3e-2, 3: 4e-4}
+MODES_16 = [1, 2, 3]
 
 
 @pytest.fixture(scope="module")
@@ -214,7 +216,7 @@ def test_conv_simt_forward_adjoint_wgrad_vs_torch(dev, gi):
 
 
 @pytest.mark.parametrize("gi", range(9))
-@pytest.mark.parametrize("precision", [1, 2, 3])
+@pytest.mark.parametrize("precision", MODES_16)
 def test_conv_tcgen05_forward_adjoint_vs_torch(dev, gi, precision):
     _conv_case(dev, gi, precision)
 
@@ -242,7 +244,7 @@ def _conv_case(dev, gi, precision):
     assert K.rel_err(K.t2n(got_w), want_w.numpy()) < (1e-5 if precision == 0 else TOL[precision]), "wgrad"
 
 
-@pytest.mark.parametrize("precision", [1, 2, 3])
+@pytest.mark.parametrize("precision", MODES_16)
 def test_conv_tcgen05_tiles_and_epilogue(dev, precision):
     """Two N tiles with a ragged second tile, several M tiles, K padding, and every epilogue term at once."""
     from spgan_b200.functional import ConvGeom
@@ -375,7 +377,7 @@ def test_chain_links_vs_module_path(dev, precision, next_precision):
     packed sink == pack(conv), its ToRGB partial sums + rgb_tail == the 1x1 modulated conv + bias + skip."""
     f = SF()
     from spgan_b200.functional import ConvGeom
-    B, C, Oc, H = 3, 64, 96, 9
+    B, C, Oc, H = 3, 64, 128, 9
     x = synth.randn_t(21, "chx", (B, C, H, H)).to(dev)
     w_up = synth.randn_t(21, "chwu", (Oc, C, 3, 3), 0.2).to(dev)
     w_cv = synth.randn_t(21, "chwc", (Oc, Oc, 3, 3), 0.1).to(dev)
@@ -416,13 +418,13 @@ def test_chain_links_vs_module_path(dev, precision, next_precision):
     a1, (oh, ow) = f.chain_upblur_pack(pp, zhw, k, nz1, nw, b1, s_cv, next_precision)
     assert (oh, ow) == (zh - 2, zh - 2)
     want_a1 = f.chain_pack_input(h1, s_cv, next_precision)
-    tol16 = 2e-6
+    tol16 = 2e-5  # a 1-ulp fp32 difference of the FIR sum can move the lo plane by one 2^-17 step
     assert K.rel_err(K.t2n(f.packed_to_float(a1, f._fmt(next_precision))), K.t2n(f.packed_to_float(want_a1, f._fmt(next_precision)))) < tol16
     rgb_w = (w_rgb.reshape(1, 3, Oc) * s_rgb.unsqueeze(1) * 0.21).contiguous()
     packed, rgb, y, (oh2, ow2) = f.chain_conv3(a1, B, oh, ow, w_cv, d_cv, 0.07, nz2, nw, b2, (0.2, 2 ** 0.5), next_precision,
                                               next_mul=s_nx, next_precision=precision, rgb_w=rgb_w, want_nchw=True)
     assert (oh2, ow2) == (zh - 4, zh - 4)
-    assert K.rel_err(K.t2n(y), K.t2n(h2)) < 2e-6
+    assert K.rel_err(K.t2n(y), K.t2n(h2)) < 2e-5
     want_packed = f.chain_pack_input(y, s_nx, precision)
     assert torch.equal(packed.view(torch.int16), want_packed.view(torch.int16))
     got_rgb = f.rgb_tail(rgb[0], rgb[1], b_rgb, skip, B, oh2, ow2)
@@ -518,7 +520,7 @@ def test_sphere_modconv_module_golden_forward_and_grads(dev, case):
     assert K.rel_err(K.t2n(gw), g["gw_" + name]) < 2e-5
 
 
-@pytest.mark.parametrize("precision", [1, 2, 3])
+@pytest.mark.parametrize("precision", MODES_16)
 def test_sphere_tcgen05_fused_vs_oracle(dev, precision):
     """The fused producer + tcgen05 GEMM at tensor-path channel counts, train (per-sample grids) and test (shared)."""
     for B, C, Oc, h, cps in ((2, 61, 32, 17, [K.train_cp(7, 139, 17), K.train_cp(1, 20, 17)]),
