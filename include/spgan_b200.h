@@ -238,9 +238,31 @@ typedef struct SpganGemmIO {
   int32_t y_packed_fmt;
   const float* rgb_w;
   float* rgb_part;
+  const float* residual_nhwc;   /* channels-last residual (b, Y, X, o), added after the activation; needs the general sinks */
+  int64_t res_bstride;          /* elements between samples of residual_nhwc; 0 = out_H*out_W*Cout */
 } SpganGemmIO;
 int spgan_conv_gemm_ex(const SpganConvPass* p, const SpganGemmIO* io, void* stream);
 int spgan_conv_gemm_rgb_slots(const SpganConvPass* p, int64_t a_rows);
+
+/* spgan_sphere_conv_gemm: the spherical modulated conv of models/spgan_ops_gs.py:791-816 as ONE kernel — the bilinear border
+ *   gather at the 3x3 tangent taps (grid_generator.py:610-613), the coordinate encoding, the reference's flat-concat channel
+ *   table and the style modulation run in the producer warps of the tcgen05 GEMM and write the A operand straight into
+ *   swizzled shared memory: neither the reference's 9x gathered fp32 tensor nor spgan_sphere_pack's [B*H*W][9*Cp] 16-bit
+ *   operand exists in HBM.  `in` describes the gather source exactly as spgan_sphere_pack does (x_nhwc (B, H, W, C) fp32,
+ *   coords (B, 3, H, W) or NULL, grid (1, 3H, 3W, 2) shared by the batch, in_mul (B, C + nc) or NULL, chan_map (B, Cp)); `p`
+ *   gives B, H, W (output lattice = input image), Cout, out_scale, activation and precision; `io` carries the packed weight
+ *   (w_packed [2][1][Cout][9*Cp] in the merged layout of spgan_pack_weight, kp = 9*Cp, a_packed unused) and every epilogue
+ *   term / sink of spgan_conv_gemm_ex.  Needs H*W >= 128 (smaller images: spgan_sphere_pack + spgan_conv_gemm). */
+typedef struct SpganSphereIn {
+  const float* x_nhwc;
+  const float* coords;
+  const float* grid;
+  const float* in_mul;
+  const uint32_t* chan_map;
+  int32_t C;
+  int32_t Cp;
+} SpganSphereIn;
+int spgan_sphere_conv_gemm(const SpganConvPass* p, const SpganSphereIn* in, const SpganGemmIO* io, void* stream);
 
 /* Channels-last tail of the upsampling StyledConv (same arithmetic as spgan_upblur_act): pp (batch, 4, Hq, Wq, channels)
  * fp32 polyphase planes in channels-last order -> interleave + 3x3 FIR + noise + bias + leaky-ReLU * scale, multiplied by the

@@ -9,6 +9,7 @@
 #define SPGAN_NUM_SMS 148  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
 
 void spgan_set_error(const char* fmt, ...);
+void spgan_internal_count_gemm_launch();  // conv_umma.cu: bumps the counter behind spgan_gemm_launch_count()
 
 #define SPGAN_CHECK_ARG(cond, ...)          \
   do {                                      \

@@ -14,55 +14,14 @@
 //               demodulation, noise, bias, leaky-ReLU, residual, scatter to the NCHW fp32 output.  Two accumulator stages
 //               (2 x 256 TMEM columns) overlap the epilogue of tile i with the mainloop of tile i+1.
 // Roofline: tensor pipe.  FLOPs per launch = 2 * rows * Cout * ntaps * kp (x3 issued MMAs in bf16x3 mode).
-#include "umma_common.cuh"
+#include "gemm_epilogue.cuh"
+#include "sphere_taps.cuh"
 
 #include <atomic>
 
 namespace {
 
 constexpr int FWD_THREADS = 320;  // warp 0 producer, warp 1 MMA issuer, warps 2..9 epilogue
-
-struct GemmParams {
-  int32_t B;           // samples
-  int32_t rows;        // M extent: B * Hl * Wl lattice points (tiled A loads) or B * My * Mx outputs (im2col A loads)
-  int32_t Hl, Wl;      // row decode: points per sample = Hl * Wl, Wl per row (= My, Mx in im2col mode)
-  int32_t My, Mx;      // valid lattice extent
-  int32_t im2col;      // 1: the A tile is fetched with TMA im2col loads (no lattice waste), 0: flat row offsets
-  int32_t img_lo;      // im2col: image offset of the lo plane (phases * B)
-  int32_t tap_ox[SPGAN_MAX_TAPS], tap_oy[SPGAN_MAX_TAPS], tap_img[SPGAN_MAX_TAPS];  // im2col: offsets, phase * B
-  int32_t Cout, out_H, out_W;
-  int32_t out_stride, out_off_y, out_off_x;
-  int64_t out_cstride;     // elements between output channels
-  int32_t ntaps, kblocks;  // kblocks = ceil(kp / 64)
-  int32_t last_ksteps;     // K = 16 steps in the last block of a tap (1..4)
-  int32_t tap_off[SPGAN_MAX_TAPS];
-  int32_t m_tiles, n_tiles;
-  float out_scale;
-  int32_t act;
-  float act_alpha, act_gain;
-  int32_t a_f16, b_f16;    // operand formats: 0 = bf16 planes, 1 = fp16 planes (instruction descriptor A / B format)
-  // ---- output sinks (any combination; y may be null)
-  int32_t y_nhwc;          // 0: y is NCHW fp32 (out_cstride between channels), 1: y is NHWC fp32 (channel fastest)
-  int64_t y_bstride;       // NHWC: elements between samples
-  int64_t pk_rows;         // packed sink: rows per 16-bit plane (the lo plane starts pk_rows * pk_cols elements later)
-  int32_t pk_cols;         // packed sink: leading dimension (the next conv's Cp)
-  int32_t pk_f16;          // packed sink: 0 = bf16 hi/lo, 1 = fp16 hi/lo
-  int32_t rgb_n;           // ToRGB sink: number of RGB channels (3) or 0
-};
-
-// Everything the epilogue may read or write besides the accumulator.
-struct GemmSinks {
-  float* y;                 // fp32 output (NCHW or NHWC), may be null
-  const float* out_mul;     // (B, Cout) demodulation
-  const float* noise;       // (B, out_H, out_W)
-  const float* noise_w;     // (1)
-  const float* bias;        // (Cout)
-  const float* residual;    // same layout as an NCHW y
-  uint16_t* y_packed;       // the next conv's A operand [2][pk_rows][pk_cols], row (b*out_H + Y)*out_W + X; may be null
-  const float* next_mul;    // (B, Cout) style modulation of the next conv, folded into y_packed; may be null
-  const float* rgb_w;       // (B, rgb_n, Cout) per-sample modulated ToRGB weights; null = sink off
-  float* rgb_part;          // (2 * n_tiles, B, rgb_n, out_H*out_W) partial sums, one slot per (N tile, epilogue half)
-};
 
 // ------------------------------------------------------------------------------------------------ GEMM kernel
 // kBlockN = 256 for the large layers; 128 halves the tile so that the small layers (structure synthesiser, first texture
@@ -84,12 +43,6 @@ template <int kPasses, int kBlockN>
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams gp,
                  const GemmSinks sk) {
-  float* __restrict__ y = sk.y;
-  const float* __restrict__ out_mul = sk.out_mul;
-  const float* __restrict__ noise = sk.noise;
-  const float* __restrict__ noise_w = sk.noise_w;
-  const float* __restrict__ bias = sk.bias;
-  const float* __restrict__ residual = sk.residual;
   using S = GemmSmem<kPasses, kBlockN>;
   constexpr int kStages = S::kStages;
   constexpr int kBTile = S::kBTileBytes;
@@ -231,198 +184,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // transposed conv, 1x1 shortcuts) was issue-latency bound at ~56 instructions per column; here the per-column work is
     // a multiply, a pointer bump and a store, the per-channel factors come in as 128-bit loads, and the rare terms (noise,
     // bias, activation, residual) are behind one warp-uniform branch.
-    const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;  // 0: even 32-column blocks, 1: odd ones
-    const int plane = gp.Hl * gp.Wl;
-    const int64_t ostride_c = gp.out_cstride;
-    const int64_t oplane = (int64_t)gp.out_H * gp.out_W;
-    const bool has_noise = noise != nullptr && noise_w != nullptr;
-    const float nw = has_noise ? __ldg(noise_w) : 0.f;
-    const bool plain = !has_noise && bias == nullptr && residual == nullptr && !gp.act;
-    const bool vec_ok = (gp.Cout & 3) == 0;  // per-channel rows start 16-byte aligned
-    // legacy sink: one NCHW fp32 tensor.  Anything else (channels-last fp32, the next conv's packed operand, ToRGB
-    // partial sums) goes through the general path below, which the host only selects when Cout is a multiple of 32.
-    const bool nchw_only = y != nullptr && !gp.y_nhwc && sk.y_packed == nullptr && sk.rgb_w == nullptr;
     int titer = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++titer) {
-      const int m0 = (tile / gp.n_tiles) * GEMM_BLOCK_M;
-      const int n0 = (tile % gp.n_tiles) * kBlockN;
-      int n_eff = gp.Cout - n0;
-      n_eff = n_eff > kBlockN ? kBlockN : ((n_eff + 15) & ~15);
       const int as = titer & 1;
       const uint32_t aphase = (uint32_t)(titer >> 1) & 1u;
-      // decode this thread's lattice point
-      const int p = m0 + quarter * 32 + lane;
-      bool valid = p < gp.rows;
-      int b = 0, Y = 0, X = 0;
-      if (valid) {
-        b = p / plane;
-        const int r = p - b * plane;
-        const int i = r / gp.Wl;
-        const int j = r - i * gp.Wl;
-        Y = i * gp.out_stride + gp.out_off_y;
-        X = j * gp.out_stride + gp.out_off_x;
-        valid = i < gp.My && j < gp.Mx && Y >= 0 && Y < gp.out_H && X >= 0 && X < gp.out_W;
-      }
-      const int64_t pix = (int64_t)Y * gp.out_W + X;
-      const int64_t ybase = (int64_t)b * gp.Cout * ostride_c + pix;
-      const float nz = (valid && has_noise) ? nw * __ldg(noise + (int64_t)b * oplane + pix) : 0.f;
-      const float* om = out_mul ? out_mul + (int64_t)b * gp.Cout : nullptr;
-      float rgb[3] = {0.f, 0.f, 0.f};
-
-      mbar_wait(tfull_bar(as), aphase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * kBlockN);
-      for (int c0 = half * 32; c0 < n_eff; c0 += 64) {
-        float v[32];
-        tmem_ld32(taddr + (uint32_t)c0, v);
-        if (valid) {
-          const int o0 = n0 + c0;
-          const bool full = o0 + 32 <= gp.Cout;
-          // per-channel factor out_scale * out_mul[b, o]
-          float f[32];
-          if (om && full && vec_ok) {
-            const float4* omp = reinterpret_cast<const float4*>(om + o0);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const float4 t4 = __ldg(omp + k);
-              f[4 * k] = t4.x * gp.out_scale;
-              f[4 * k + 1] = t4.y * gp.out_scale;
-              f[4 * k + 2] = t4.z * gp.out_scale;
-              f[4 * k + 3] = t4.w * gp.out_scale;
-            }
-          } else {
-#pragma unroll
-            for (int k = 0; k < 32; ++k) {
-              const int oc = o0 + k < gp.Cout ? o0 + k : gp.Cout - 1;
-              f[k] = (om ? __ldg(om + oc) : 1.f) * gp.out_scale;
-            }
-          }
-          if (nchw_only) {
-            float* yp = y + ybase + (int64_t)o0 * ostride_c;
-            if (plain && full) {
-#pragma unroll
-              for (int k = 0; k < 32; ++k) {
-                *yp = v[k] * f[k];
-                yp += ostride_c;
-              }
-            } else {
-              // rare terms: all loads of a 16-column half are issued before the first dependent use
-              const float* rp = residual ? residual + ybase + (int64_t)o0 * ostride_c : nullptr;
-#pragma unroll
-              for (int h0 = 0; h0 < 32; h0 += 16) {
-                float bv[16], rv[16];
-#pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                  const int o = o0 + h0 + k;
-                  const int oc = o < gp.Cout ? o : gp.Cout - 1;
-                  bv[k] = bias ? __ldg(bias + oc) : 0.f;
-                  rv[k] = (rp && o < gp.Cout) ? __ldg(rp + (int64_t)(h0 + k) * ostride_c) : 0.f;
-                }
-#pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                  float r = v[h0 + k] * f[h0 + k] + nz + bv[k];
-                  if (gp.act) r = (r > 0.f ? r : r * gp.act_alpha) * gp.act_gain;
-                  if (o0 + h0 + k < gp.Cout) yp[(int64_t)(h0 + k) * ostride_c] = r + rv[k];
-                }
-              }
-            }
-          } else {
-            // ---- general sinks (host guarantees Cout % 32 == 0, so every block is full and 16-byte aligned)
-            if (bias) {
-              const float4* bp = reinterpret_cast<const float4*>(bias + o0);
-#pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                const float4 t4 = __ldg(bp + k);
-                v[4 * k] = v[4 * k] * f[4 * k] + nz + t4.x;  // same association as the NCHW path: bit-identical values
-                v[4 * k + 1] = v[4 * k + 1] * f[4 * k + 1] + nz + t4.y;
-                v[4 * k + 2] = v[4 * k + 2] * f[4 * k + 2] + nz + t4.z;
-                v[4 * k + 3] = v[4 * k + 3] * f[4 * k + 3] + nz + t4.w;
-              }
-            } else {
-#pragma unroll
-              for (int k = 0; k < 32; ++k) v[k] = v[k] * f[k] + nz + 0.f;
-            }
-            if (gp.act) {
-#pragma unroll
-              for (int k = 0; k < 32; ++k) v[k] = (v[k] > 0.f ? v[k] : v[k] * gp.act_alpha) * gp.act_gain;
-            }
-            if (y != nullptr) {
-              if (gp.y_nhwc) {
-                float4* yp4 = reinterpret_cast<float4*>(y + (int64_t)b * gp.y_bstride + pix * gp.Cout + o0);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) yp4[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-              } else {
-                float* yp = y + ybase + (int64_t)o0 * ostride_c;
-#pragma unroll
-                for (int k = 0; k < 32; ++k) yp[(int64_t)k * ostride_c] = v[k];
-              }
-            }
-            if (sk.rgb_w != nullptr) {
-              // ToRGB (1x1 modulated conv without demodulation, models/spgan_ops.py:1563-1586) folded into the producer
-#pragma unroll
-              for (int j = 0; j < 3; ++j) {
-                if (j < gp.rgb_n) {
-                  const float4* wp = reinterpret_cast<const float4*>(sk.rgb_w + ((int64_t)b * gp.rgb_n + j) * gp.Cout + o0);
-                  float a = 0.f;
-#pragma unroll
-                  for (int k = 0; k < 8; ++k) {
-                    const float4 t4 = __ldg(wp + k);
-                    a += v[4 * k] * t4.x + v[4 * k + 1] * t4.y + v[4 * k + 2] * t4.z + v[4 * k + 3] * t4.w;
-                  }
-                  rgb[j] += a;
-                }
-              }
-            }
-            if (sk.y_packed != nullptr) {
-              // the next conv's A operand: style modulation of THAT conv, then the 16-bit hi/lo split (what spgan_pack_act
-              // would compute from the fp32 tensor, bit for bit)
-              if (sk.next_mul) {
-                const float4* mp = reinterpret_cast<const float4*>(sk.next_mul + (int64_t)b * gp.Cout + o0);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                  const float4 t4 = __ldg(mp + k);
-                  v[4 * k] *= t4.x;
-                  v[4 * k + 1] *= t4.y;
-                  v[4 * k + 2] *= t4.z;
-                  v[4 * k + 3] *= t4.w;
-                }
-              }
-              const int64_t prow = (int64_t)b * oplane + pix;
-              uint16_t* ph = sk.y_packed + prow * gp.pk_cols + o0;
-              uint16_t* pl = ph + gp.pk_rows * (int64_t)gp.pk_cols;
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                uint32_t hw[4], lw[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                  uint16_t h0, l0, h1, l1;
-                  if (gp.pk_f16) {
-                    split16<true>(v[8 * q + 2 * u], h0, l0);
-                    split16<true>(v[8 * q + 2 * u + 1], h1, l1);
-                  } else {
-                    split16<false>(v[8 * q + 2 * u], h0, l0);
-                    split16<false>(v[8 * q + 2 * u + 1], h1, l1);
-                  }
-                  hw[u] = pack2x16(h0, h1);
-                  lw[u] = pack2x16(l0, l1);
-                }
-                reinterpret_cast<uint4*>(ph)[q] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                reinterpret_cast<uint4*>(pl)[q] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-              }
-            }
-          }
-        }
-      }
-      if (sk.rgb_w != nullptr && valid) {
-        // one slot per (N tile, epilogue half): every (slot, b, channel, pixel) is written exactly once, and
-        // spgan_rgb_tail sums the slots in a fixed order (deterministic, unlike atomics)
-        const int slot = (tile % gp.n_tiles) * 2 + half;
-        float* rp = sk.rgb_part + (((int64_t)slot * gp.B + b) * gp.rgb_n) * oplane + pix;
-#pragma unroll
-        for (int j = 0; j < 3; ++j)
-          if (j < gp.rgb_n) rp[(int64_t)j * oplane] = rgb[j];
-      }
+      gemm_epilogue_tile<kBlockN>(gp, sk, tile, warp, lane, tfull_bar(as), aphase, tmem_base + (uint32_t)(as * kBlockN));
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(as));
@@ -538,39 +304,6 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(float* __restrict__ o
     const int p = p0 + pp, c = c0 + tx;
     if (p < HW && c < C) out[((int64_t)b * HW + p) * C + c] = tile[tx][pp];
   }
-}
-
-// ATen's fp32 index sequence (GridSampler.h:27-36, 58-60) with explicit round-to-nearest ops (no FMA contraction).
-__device__ __forceinline__ float unnorm_clip(float g, int size) {
-  float v = __fmul_rn(__fdiv_rn(__fadd_rn(g, 1.f), 2.f), (float)(size - 1));
-  return fminf((float)(size - 1), fmaxf(v, 0.f));
-}
-
-struct TapCorners {
-  int o_nw, o_ne, o_sw, o_se;  // pixel offsets y*W + x of the four corners
-  float w_nw, w_ne, w_sw, w_se;
-};
-
-__device__ __forceinline__ TapCorners tap_corners(const float* __restrict__ grid, int bg, int H, int W, int py, int px,
-                                                  int ty, int tx) {
-  const float2 gxy =
-      __ldg(reinterpret_cast<const float2*>(grid) + ((int64_t)bg * 3 * H + (3 * py + ty)) * (3 * W) + 3 * px + tx);
-  const float ix = unnorm_clip(gxy.x, W), iy = unnorm_clip(gxy.y, H);
-  const float fx = floorf(ix), fy = floorf(iy);
-  const int x0 = (int)fx, y0 = (int)fy;
-  const int x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
-  const float ex = __fsub_rn(__fadd_rn(fx, 1.f), ix), ey = __fsub_rn(__fadd_rn(fy, 1.f), iy);
-  const float wx = __fsub_rn(ix, fx), wy = __fsub_rn(iy, fy);
-  TapCorners c;
-  c.o_nw = y0 * W + x0;
-  c.o_ne = y0 * W + x1;
-  c.o_sw = y1 * W + x0;
-  c.o_se = y1 * W + x1;
-  c.w_nw = ex * ey;
-  c.w_ne = wx * ey;
-  c.w_sw = ex * wy;
-  c.w_se = wx * wy;
-  return c;
 }
 
 // One warp per (group g, pixel p, tap t); lanes sweep the channel pairs (2*lane, 2*lane + 1) + 64*j.  Which gathered
@@ -823,6 +556,7 @@ GemmShape gemm_shape(const SpganConvPass* p, int64_t a_rows) {
 }  // namespace
 
 extern "C" int64_t spgan_gemm_launch_count(void) { return (int64_t)launch_counter()->load(); }
+void spgan_internal_count_gemm_launch() { launch_counter()->fetch_add(1); }
 
 extern "C" int spgan_pack_act(uint16_t* out, const float* x, const float* in_mul, int B, int C, int H, int W, int Cp,
                               int pad_y, int pad_x, int Hl, int Wl, int step, int fmt, void* stream) {
@@ -940,7 +674,7 @@ extern "C" int spgan_conv_gemm_ex(const SpganConvPass* p, const SpganGemmIO* io,
   SPGAN_CHECK_ARG(io->a_packed && io->w_packed, "spgan_conv_gemm: null operand pointer");
   SPGAN_CHECK_ARG(io->y || io->y_packed || io->rgb_w, "spgan_conv_gemm: no output sink");
   SPGAN_CHECK_ARG(((((uintptr_t)io->a_packed) | ((uintptr_t)io->w_packed)) & 15) == 0, "spgan_conv_gemm: packed operands must be 16-byte aligned");
-  const bool general = io->y == nullptr || io->y_layout != 0 || io->y_packed != nullptr || io->rgb_w != nullptr;
+  const bool general = io->y == nullptr || io->y_layout != 0 || io->y_packed != nullptr || io->rgb_w != nullptr || io->residual_nhwc != nullptr;
   if (general) {
     SPGAN_CHECK_ARG(p->Cout % 32 == 0, "spgan_conv_gemm: channels-last / packed / ToRGB sinks need Cout %% 32 == 0, got %d", p->Cout);
     SPGAN_CHECK_ARG(io->residual == nullptr, "spgan_conv_gemm: residual is only supported with a plain NCHW output");
@@ -1008,6 +742,7 @@ extern "C" int spgan_conv_gemm_ex(const SpganConvPass* p, const SpganGemmIO* io,
   gp.pk_cols = io->y_packed_cols;
   gp.pk_f16 = io->y_packed_fmt;
   gp.rgb_n = io->rgb_w ? io->rgb_n : 0;
+  gp.res_bstride = io->res_bstride ? io->res_bstride : (int64_t)p->out_H * p->out_W * p->Cout;
   GemmSinks sk;
   sk.y = io->y;
   sk.out_mul = io->out_mul;
@@ -1015,6 +750,7 @@ extern "C" int spgan_conv_gemm_ex(const SpganConvPass* p, const SpganGemmIO* io,
   sk.noise_w = io->noise_w;
   sk.bias = io->bias;
   sk.residual = io->residual;
+  sk.residual_nhwc = io->residual_nhwc;
   sk.y_packed = io->y_packed;
   sk.next_mul = io->next_mul;
   sk.rgb_w = io->rgb_w;

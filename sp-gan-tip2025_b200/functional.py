@@ -854,22 +854,50 @@ def sphere_modconv_fused(x, coords, grid, w, in_mul, out_mul, out_scale, act=Non
     st = _stream(x)
     a, g = (act if act is not None else (0.0, 1.0))
     y = torch.empty((B, O, H, W), device=x.device, dtype=torch.float32)
+    fmt = _fmt(precision)
     with torch.cuda.device(x.device):
         xh = torch.empty((B, H, W, C), device=x.device, dtype=torch.float32)
         lib.call("spgan_nchw_to_nhwc", _ptr(xh), _ptr(x), B, C, H, W, st)
-        a_packed = torch.empty((2, rows, 9 * Cp), device=x.device, dtype=torch.bfloat16)
         cc = _f32c(coords, "sphere_modconv") if coords is not None else None
         im = _f32c(in_mul, "sphere_modconv") if in_mul is not None else None
         cmap = _sphere_chan_map(B, C, nc, Cp, bool(flat_concat), x.device)
-        lib.call("spgan_sphere_pack", _ptr(a_packed), _ptr(xh), _ptr(cc), _ptr(grid), _ptr(im), _ptr(cmap), B, C, H, W,
-                 grid.shape[0], Cp, _fmt(precision), st)
-        wp = _packed_weight(w, O, Ct, Ct * 9, 9, list(range(9)), Cp, True, _wfmt(precision))
+        wp = _packed_weight(w, O, Ct, Ct * 9, 9, list(range(9)), Cp, True, fmt)
         p = dict(My=H, Mx=W, in_stride=1, out_stride=1, off_y=0, off_x=0, taps=[(0, 0, 0)])
         cp = _fill_pass(p, B, Ct, H, W, O, H, W, Ct * 9, 9, out_scale, 1 if act is not None else 0, a, g, precision)
         om = _f32c(out_mul, "sphere_modconv") if out_mul is not None else None
-        _gemm_call(2.0 * B * H * W * O * Ct * 9, ctypes.byref(cp), _ptr(y), _ptr(a_packed), rows, 9 * Cp, _ptr(wp),
-                   _ptr(om), _ptr(None), _ptr(None), _ptr(bias), _ptr(residual), st)
+        bs = _f32c(bias, "sphere_modconv") if bias is not None else None
+        rs = _f32c(residual, "sphere_modconv") if residual is not None else None
+        if rs is not None and rs.shape != y.shape:
+            raise RuntimeError("sphere_modconv: residual shape %s != output shape %s" % (tuple(rs.shape), tuple(y.shape)))
+        flops = 2.0 * B * H * W * O * Ct * 9
+        if FUSED_SPHERE_GATHER and grid.shape[0] == 1 and H * W >= 128:
+            # the gather is the A-operand producer of the GEMM itself: no [B*H*W][9*Cp] operand in HBM
+            sphere_conv_gemm(cp, flops, st, xh, cc, grid, im, cmap, C, Cp, wp, fmt, out_mul=om, bias=bs, residual=rs, y=y)
+            return y
+        a_packed = torch.empty((2, rows, 9 * Cp), device=x.device, dtype=torch.bfloat16)
+        lib.call("spgan_sphere_pack", _ptr(a_packed), _ptr(xh), _ptr(cc), _ptr(grid), _ptr(im), _ptr(cmap), B, C, H, W,
+                 grid.shape[0], Cp, fmt, st)
+        _gemm_call(flops, ctypes.byref(cp), _ptr(y), _ptr(a_packed), rows, 9 * Cp, _ptr(wp),
+                   _ptr(om), _ptr(None), _ptr(None), _ptr(bs), _ptr(rs), st)
     return y
+
+
+FUSED_SPHERE_GATHER = True  # tests flip this to compare the fused kernel with the pack + GEMM composition
+
+
+def sphere_conv_gemm(cp, flops, st, xh, coords, grid, in_mul, cmap, C, Cp, wp, fmt, **sinks):
+    """spgan_sphere_conv_gemm: gather-producer GEMM.  `sinks` are SpganGemmIO fields (tensors or None)."""
+    sin = lib.SphereIn()
+    sin.x_nhwc, sin.coords, sin.grid = xh.data_ptr(), (coords.data_ptr() if coords is not None else None), grid.data_ptr()
+    sin.in_mul, sin.chan_map = (in_mul.data_ptr() if in_mul is not None else None), cmap.data_ptr()
+    sin.C, sin.Cp = C, Cp
+    io = lib.GemmIO()
+    io.kp, io.fmt, io.w_fmt, io.w_packed = 9 * Cp, fmt, fmt, wp.data_ptr()
+    for k, v in sinks.items():
+        if isinstance(v, torch.Tensor):
+            v = v.data_ptr()
+        setattr(io, k, v)
+    _timed_call(flops, "spgan_sphere_conv_gemm", ctypes.byref(cp), ctypes.byref(sin), ctypes.byref(io), st)
 
 
 _CHAN_MAPS = {}

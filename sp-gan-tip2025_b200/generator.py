@@ -219,9 +219,14 @@ class TextureSynthesizer(nn.Module):
         return torch.cat([w0.unsqueeze(1).repeat(1, inject_index, 1),
                           w1.unsqueeze(1).repeat(1, self.n_latent - inject_index, 1)], 1)
 
-    # Per-layer precision of the fused inference chain: None = the global mode for every layer; a list of 8 modes lets the
-    # layers nearest the output (whose rounding error is not amplified by later layers) run the 2-MMA fp16 split.
+    # Per-layer precision of the fused inference chain.  None = the default policy: the global mode for every layer, except
+    # that under the fp32-equivalent global mode (1, bf16x3) the LAST conv (48 % of the generator's FLOPs) runs the 2-MMA
+    # fp16 split (mode 3) — its rounding error is not amplified by any later layer, and every golden of the reference
+    # (B = 1, 2, 32 patches, 384x768 and 768x1536 panoramas) still passes at the tolerance the all-bf16x3 path is held to
+    # (5e-4; measured 3.2e-4 .. 3.8e-4 against 2.3e-4 .. 2.6e-4).  A list of 8 modes overrides it; STRICT = bf16x3 everywhere.
     layer_precision = None
+    STRICT = (1, 1, 1, 1, 1, 1, 1, 1)
+    FAST_TAIL = (1, 1, 1, 1, 1, 3, 3, 3)
     use_chain = True
     # Power-of-two divisors of each layer's INPUT operand, used only where that layer runs mode 3 (fp16 planes saturate at
     # 65504, and nothing bounds the activations of a GAN): the producer folds 1 / act_scale[i] into the style modulation it
@@ -232,20 +237,21 @@ class TextureSynthesizer(nn.Module):
     def calibrate_act_scales(self, styles, structure_latent, coords_partial, noises):
         """One bf16x3 pass of the chain that records max |operand| of every layer -> power-of-two act_scale."""
         import math
-        saved, self.layer_precision = self.layer_precision, None
         rec = []
-        try:
-            with torch.no_grad():
-                self._forward_chain(styles, structure_latent, coords_partial, noises, record=rec)
-        finally:
-            self.layer_precision = saved
+        with torch.no_grad():
+            self._forward_chain(styles, structure_latent, coords_partial, noises, modes=[1] * self.num_layers, record=rec)
         amax = torch.stack(rec).tolist()  # one host sync: calibration is not on the hot path
         self.act_scale = [2.0 ** math.ceil(math.log2(max(a, 1e-30) / 256.0)) for a in amax]
         return self.act_scale
 
     def _chain_modes(self):
         g = SF.get_precision()
-        modes = list(self.layer_precision) if self.layer_precision is not None else [g] * self.num_layers
+        if self.layer_precision is not None:
+            modes = list(self.layer_precision)
+        else:
+            modes = [g] * self.num_layers
+            if g == 1:
+                modes[-1] = 3
         if len(modes) != self.num_layers or any(m not in (1, 2, 3) for m in modes):
             return None
         return modes
@@ -277,12 +283,17 @@ class TextureSynthesizer(nn.Module):
             hit = cache[i] = (s, self.act_scale[i], s * (1.0 / self.act_scale[i]))
         return hit[2], self.act_scale[i]
 
-    def _forward_chain(self, styles, structure_latent, coords_partial, noises, record=None):
+    def _forward_chain(self, styles, structure_latent, coords_partial, noises, modes=None, record=None):
         """The synthesis loop with channels-last operands between the convs (csrc/chain.cu): per (upsampling conv, conv)
         pair 4 parity GEMMs -> FIR tail writing the conv's packed operand -> GEMM writing the next pair's packed operand
         and the ToRGB partial sums -> rgb tail.  No fp32 activation of the texture synthesiser is written to HBM."""
         B = structure_latent.shape[0]
-        modes = self._chain_modes()
+        if modes is None:
+            modes = self._chain_modes()
+            if 3 in modes and self.act_scale is None:
+                if torch.cuda.is_current_stream_capturing():
+                    raise RuntimeError("texture chain: fp16 layers need calibrate_act_scales() before a CUDA-graph capture")
+                self.calibrate_act_scales(styles, structure_latent, coords_partial, noises)
         sd = [conv.conv._mod_demod(styles[:, i], B) for i, conv in enumerate(self.convs)]
         H, W = structure_latent.shape[2], structure_latent.shape[3]
         mul0, k_in = self._scaled_mul(0, sd[0][0], modes)

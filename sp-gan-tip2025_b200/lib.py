@@ -42,7 +42,14 @@ class GemmIO(ctypes.Structure):
         ("y", c_vp), ("y_layout", ctypes.c_int32), ("rgb_n", ctypes.c_int32), ("y_bstride", ctypes.c_int64),
         ("y_packed", c_vp), ("next_mul", c_vp), ("y_packed_rows", ctypes.c_int64), ("y_packed_cols", ctypes.c_int32),
         ("y_packed_fmt", ctypes.c_int32), ("rgb_w", c_vp), ("rgb_part", c_vp),
+        ("residual_nhwc", c_vp), ("res_bstride", ctypes.c_int64),
     ]
+
+
+class SphereIn(ctypes.Structure):
+    """Mirror of `SpganSphereIn` (include/spgan_b200.h)."""
+    _fields_ = [("x_nhwc", c_vp), ("coords", c_vp), ("grid", c_vp), ("in_mul", c_vp), ("chan_map", c_vp),
+                ("C", ctypes.c_int32), ("Cp", ctypes.c_int32)]
 
 
 _PASS_P = ctypes.POINTER(ConvPass)
@@ -77,6 +84,7 @@ SIGNATURES = {
     "spgan_conv_gemm": (c_int, [_PASS_P, c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "spgan_conv_gemm_ex": (c_int, [_PASS_P, ctypes.c_void_p, c_vp]),
     "spgan_conv_gemm_rgb_slots": (c_int, [_PASS_P, c_i64]),
+    "spgan_sphere_conv_gemm": (c_int, [_PASS_P, ctypes.c_void_p, ctypes.c_void_p, c_vp]),
     "spgan_upblur_pack": (c_int, [c_vp] * 7 + [c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_i64, c_int, c_f32, c_f32, c_vp]),
     "spgan_rgb_tail": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp, c_i64, c_int, c_i64, c_vp]),
     "spgan_gemm_launch_count": (c_i64, []),

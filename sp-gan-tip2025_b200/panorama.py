@@ -282,23 +282,24 @@ class PanoramaEngine:
         """Mode-3 (fp16) layers of the texture chain need power-of-two operand scales: taken from the first lattice
         position of the current inputs (TextureSynthesizer.calibrate_act_scales), once, before the capture."""
         ts = getattr(self.gen, "texture_synthesizer", None)
-        modes = getattr(ts, "layer_precision", None)
-        if ts is None or modes is None or 3 not in modes or ts.act_scale is not None:
+        modes = ts._chain_modes() if ts is not None and hasattr(ts, "_chain_modes") else None
+        if modes is None or 3 not in modes or ts.act_scale is not None:
             return
         it, ix, iy = self.pos[0]
         holder = {}
         orig = ts._forward_chain
 
-        def spy(styles, structure, cp, noises, record=None):
-            holder["args"] = (styles, structure, cp, noises)
-            return orig(styles, structure, cp, noises, record=record)
+        def spy(styles, structure, cp, noises, modes=None, record=None):
+            holder.setdefault("args", (styles, structure, cp, noises))
+            return orig(styles, structure, cp, noises, modes=modes, record=record)
         ts._forward_chain = spy
         try:
             styles = ts.styles_for(self.gl)
             _run_position(self.gen, self.pl, self.gl, self.canvas, self.coords_full, self.noises, styles, it, ix, iy)
         finally:
             del ts._forward_chain
-        ts.calibrate_act_scales(*holder["args"])
+        if ts.act_scale is None and "args" in holder:
+            ts.calibrate_act_scales(*holder["args"])
 
     @torch.no_grad()
     def run(self):

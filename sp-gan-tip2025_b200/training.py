@@ -184,6 +184,38 @@ def allreduce_gradients(params, world, bucket_bytes=64 << 20):
     return n
 
 
+@torch.no_grad()
+def sync_module_states(modules, world, src=0):
+    """Make every rank start from rank `src`'s parameters and buffers (what DistributedDataParallel does at construction;
+    nn.DataParallel, train.py:809-816, replicates one module, so the reference's replicas are equal by construction).
+    Returns the number of broadcast tensors."""
+    if world <= 1:
+        return 0
+    n = 0
+    for m in modules:
+        if m is None:
+            continue
+        for t in list(m.parameters()) + list(m.buffers()):
+            dist.broadcast(t.data, src)
+            n += 1
+    return n
+
+
+def replicas_in_sync(modules, world):
+    """True when every rank holds the same parameters (max over ranks of a checksum == min over ranks)."""
+    if world <= 1:
+        return True
+    acc = None
+    for m in modules:
+        for p in m.parameters():
+            v = p.detach().double().sum() + p.detach().double().abs().sum()
+            acc = v if acc is None else acc + v
+    hi, lo = acc.clone(), acc.clone()
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    return bool(hi == lo)
+
+
 def requires_grad(model, flag):
     for p in model.parameters():
         p.requires_grad_(flag)
@@ -206,7 +238,9 @@ class TrainStep:
     captured in a CUDA graph after two eager runs and replayed afterwards — the B = 8 iteration is launch-bound
     (~6500 kernel launches for ~90 ms of kernels), a replay removes the Python / launch overhead."""
 
-    def __init__(self, batch, device, world=1, seed=9000, config=None, with_ema=True, use_graphs=False):
+    def __init__(self, batch, device, world=1, seed=9000, config=None, with_ema=True, use_graphs=False, rank=0):
+        """`seed` initialises the MODEL and is the same on every rank (the replicas are additionally broadcast from rank 0);
+        the synthetic data stream of rank r is seeded with seed + 7919 * (r + 1), so the ranks see different samples."""
         self.config = config if config is not None else default_config()
         tp = self.config.train_params
         tp.batch_size = batch
@@ -224,7 +258,9 @@ class TrainStep:
         cap = bool(use_graphs)
         self.g_optim = torch.optim.Adam(self.G.parameters(), lr=tp.lr * g_ratio, betas=(0 ** g_ratio, 0.99 ** g_ratio), capturable=cap)
         self.d_optim = torch.optim.Adam(self.D.parameters(), lr=tp.lr * d_ratio, betas=(0 ** d_ratio, 0.99 ** d_ratio), capturable=cap)
-        self.sampler = SyntheticSampler(batch, device, seed)
+        sync_module_states([self.G, self.D, self.G_ema], world)
+        self.rank = rank
+        self.sampler = SyntheticSampler(batch, device, seed + 7919 * (rank + 1) if world > 1 else seed)
         self.mean_path_length = torch.zeros((), device=device)
         self.iter = 0
         self._graphs, self._eager_runs, self._inputs = {}, {}, {}
@@ -342,7 +378,14 @@ class TrainStep:
             styles = self.G.texture_synthesizer.styles_for(inp["gl"], inject_mask=inp["mask"])
             img = self.G(inp["gl"], inp["lat"], inp["coords"], inp["cps"], noises=inp["noises"], styles=styles)
             pl = path_lengths(img, styles)
-            mean = self.mean_path_length + 0.01 * (pl.mean() - self.mean_path_length)
+            batch_mean = pl.mean()
+            if self.world > 1:
+                # the running mean is replica state: every rank folds in the GLOBAL batch mean (value), while the gradient
+                # still flows through its own samples, as in models/losses.py:70-78
+                glob = batch_mean.detach().clone()
+                dist.all_reduce(glob, op=dist.ReduceOp.SUM)
+                batch_mean = batch_mean + (glob / self.world - batch_mean.detach())
+            mean = self.mean_path_length + 0.01 * (batch_mean - self.mean_path_length)
             penalty = (pl - mean).pow(2).mean()
             self.G.zero_grad(set_to_none=True)
             (tp.path_regularize * tp.g_reg_every * penalty).backward()

@@ -15,8 +15,22 @@ def _worker(rank, world, port, ret):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from spgan_b200.training import allreduce_gradients
+    from spgan_b200.training import allreduce_gradients, replicas_in_sync, sync_module_states
     from spgan_b200 import panorama
+    # replicas: different init per rank -> broadcast from rank 0 -> identical; a data-parallel SGD loop on rank-dependent
+    # data keeps them identical (the ranks must not train different models)
+    torch.manual_seed(100 + rank)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.BatchNorm1d(5), torch.nn.Linear(5, 2))
+    differs_before = not replicas_in_sync([net], world)
+    nb = sync_module_states([net], world)
+    opt = torch.optim.SGD(net.parameters(), lr=0.1)
+    gdata = torch.Generator().manual_seed(1000 + rank)
+    for _ in range(3):
+        opt.zero_grad()
+        net(torch.randn(8, 6, generator=gdata)).square().mean().backward()
+        allreduce_gradients(net.parameters(), world, bucket_bytes=64)
+        opt.step()
+    dp_ok = differs_before and nb == 9 and replicas_in_sync([net], world)
     torch.manual_seed(0)
     params = [torch.nn.Parameter(torch.zeros(n)) for n in (3, 1000, 70000, 5)]
     for i, p in enumerate(params):
@@ -44,7 +58,7 @@ def _worker(rank, world, port, ret):
     seq = panorama.generate(stub_gen, pl, gl, canvas, noises)
     sh = panorama.generate_sharded(stub_gen, pl, gl, canvas, noises, rank, world)
     same = bool(torch.equal(seq, sh))
-    ret[rank] = bool(ok and n >= 2 and params[4].grad is None and bool((counts == 1).all()) and same)
+    ret[rank] = bool(dp_ok and ok and n >= 2 and params[4].grad is None and bool((counts == 1).all()) and same)
     dist.destroy_process_group()
 
 

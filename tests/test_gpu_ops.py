@@ -543,6 +543,34 @@ def test_sphere_tcgen05_fused_vs_oracle(dev, precision):
         assert K.rel_err(K.t2n(got), want.numpy()) < TOL[precision]
 
 
+@pytest.mark.parametrize("precision", MODES_16)
+@pytest.mark.parametrize("B,C,Oc,h,extras", [(3, 70, 40, 17, False), (2, 256, 256, 23, True), (5, 61, 288, 12, True)])
+def test_sphere_gather_producer_gemm_vs_pack_then_gemm(dev, precision, B, C, Oc, h, extras):
+    """spgan_sphere_conv_gemm (the gather runs in the GEMM's producer warps, A tiles exist only in shared memory) against
+    spgan_sphere_pack + spgan_conv_gemm (the operand it no longer writes): same operand bits, the K dimension is merely
+    walked channel-block-major instead of tap-major, so only the fp32 accumulation order differs.  Covers tiles that span
+    two samples, a ragged last M tile, one and two N tiles (the second ragged), the flat-concat table with the coordinate
+    planes in the last group, bias + residual + activation."""
+    f = SF()
+    cp = K.test_cp(2, 7, 27)
+    grid = torch.from_numpy(O.gen_sampling_grid(h, h, cp)).to(dev)
+    x = synth.randn_t(31, "sgx%d" % B, (B, C, h, h)).to(dev)
+    c = synth.randn_t(31, "sgc%d" % B, (B, 3, h, h)).to(dev)
+    w = synth.randn_t(31, "sgw%d" % B, (Oc, C + 3, 3, 3), 0.2).to(dev)
+    s = synth.randn_t(31, "sgs%d" % B, (B, C + 3), 0.3, 1.0).to(dev)
+    d = synth.randn_t(31, "sgd%d" % B, (B, Oc), 0.3, 1.0).to(dev)
+    bias = synth.randn_t(31, "sgb%d" % B, (Oc,)).to(dev) if extras else None
+    res = synth.randn_t(31, "sgr%d" % B, (B, Oc, h, h)).to(dev) if extras else None
+    outs = []
+    for fused in (True, False):
+        f.FUSED_SPHERE_GATHER = fused
+        try:
+            outs.append(f.sphere_modconv_fused(x, c, grid, w, s, d, 0.05, act=(0.01, 1.0), precision=precision, residual=res, bias=bias))
+        finally:
+            f.FUSED_SPHERE_GATHER = True
+    assert K.rel_err(K.t2n(outs[0]), K.t2n(outs[1])) < 1e-5
+
+
 def test_sphere_rgb_conv_golden(dev):
     from spgan_b200.models.spherenet import SphereConvBatchDiffFixBorderGNoGrad
     g = K.load("sphere_modconv.npz")

@@ -11,7 +11,7 @@ for line in sys.stdin:
     print("value %.2f %s  ms/step %.1f  e2e %.2f  launches %s  roofline %.3f (%.0f TF/s, share %.2f)  clocks %s" % (
         d["value"], d["unit"], d["ms_per_step"], (d.get("e2e") or {}).get("value", float("nan")), d.get("gpu_launches"),
         r.get("frac") or 0, r.get("achieved") or 0, r.get("share_of_step") or 0, (d.get("clocks") or {}).get("sm_mhz")))
-    for k in ("fast_tail", "pano768"):
+    for k in ("strict_bf16x3", "fast_tail", "pano768"):
         if k in d:
             print("  %s: %s" % (k, {a: b for a, b in d[k].items() if a in ("value", "ms_per_step", "gemm_algorithmic_tflops")}))
     if "train" in d and d["train"]:
