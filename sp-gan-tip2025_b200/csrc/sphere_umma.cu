@@ -32,6 +32,7 @@ namespace {
 
 constexpr int SPH_THREADS = 320;
 constexpr int SPH_PROD_WARPS = 8;
+constexpr int SPH_BATCH = 8;  // rows gathered per load batch of a producer warp
 constexpr int SPH_TABLE_ENTRIES = GEMM_BLOCK_M * 9;
 constexpr int SPH_TABLE_BYTES = SPH_TABLE_ENTRIES * 5 * 4;  // int base + 4 float weights, structure of arrays
 
@@ -66,6 +67,7 @@ sphere_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const GemmParams gp,
   using S = SphereSmem<kPasses, kBlockN>;
   constexpr int kStages = S::kStages;
   constexpr int kBTile = S::kBTileBytes;
+  constexpr bool kF16 = kPasses == 2;  // the 2-MMA mode is the fp16 split (precision 3); 1 and 3 passes use bf16 planes
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));  // generic-address view of the aligned region
@@ -236,11 +238,72 @@ sphere_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const GemmParams gp,
             mulv[sidx][u] = (valid && si.in_mul && k < Ct) ? __ldg(si.in_mul + (int64_t)g * Ct + k) : 1.f;
           }
         }
+        // Fast path (every k-block except the one that holds the coordinate planes, i.e. one block of the LAST group under
+        // the reference's flat concat): all 64 columns of both samples are feature planes or zero padding (modulation 0), so
+        // the gather is branch-free: 32-bit element offsets against the uniform base pointer, 8 loads in flight per row.
+        const bool fast = __all_sync(0xffffffffu, kind[0][0] <= 1 && kind[0][1] <= 1 && kind[1][0] <= 1 && kind[1][1] <= 1);
+        const uint32_t soA0 = soff[0][0], soA1 = soff[0][1], soB0 = soff[1][0], soB1 = soff[1][1];
+        const float mA0 = kind[0][0] ? mulv[0][0] : 0.f, mA1 = kind[0][1] ? mulv[0][1] : 0.f;
+        const float mB0 = kind[1][0] ? mulv[1][0] : 0.f, mB1 = kind[1][1] ? mulv[1][1] : 0.f;
+        const uint32_t lane_col = (uint32_t)(((lane >> 3) << 4) | ((lane & 7) << 1));  // byte offset of column `lane` in a 128 B row
         for (int t = 0; t < 9; ++t) {
           if (lane == 0) mbar_wait(empty_bar(stage), phase ^ 1u);
           __syncwarp();
           uint8_t* a_hi = smem_gen + stage * S::kStageBytes;
           uint8_t* a_lo = a_hi + A_TILE_BYTES;
+          if (fast) {
+            const uint32_t uC = (uint32_t)si.C, uWC = (uint32_t)si.W * (uint32_t)si.C;
+            // 8 rows per batch: 64 independent loads in flight per lane (the producers are 8 warps on an SM that could hold
+            // 64: memory-level parallelism has to come from the batch, not from occupancy); the bilinear weights are re-read
+            // from the shared table when they are used instead of being held across the loads
+#pragma unroll 1
+            for (int i0 = 0; i0 < GEMM_BLOCK_M / SPH_PROD_WARPS; i0 += SPH_BATCH) {
+              float cv[SPH_BATCH][2][4];
+#pragma unroll
+              for (int ii = 0; ii < SPH_BATCH; ++ii) {
+                const int r = w2 * (GEMM_BLOCK_M / SPH_PROD_WARPS) + i0 + ii;
+                const uint32_t base = (uint32_t)tbl_base[r * 9 + t];
+                const uint32_t c0 = (base >> 2) * uC;
+                const uint32_t c1 = c0 + ((base & 1u) ? uC : 0u);
+                const uint32_t c2 = c0 + ((base & 2u) ? uWC : 0u);
+                const uint32_t c3 = c2 + (c1 - c0);
+                const bool sb = r >= rb;
+                const uint32_t s0 = sb ? soB0 : soA0, s1 = sb ? soB1 : soA1;
+                cv[ii][0][0] = __ldg(xh + (s0 + c0));
+                cv[ii][0][1] = __ldg(xh + (s0 + c1));
+                cv[ii][0][2] = __ldg(xh + (s0 + c2));
+                cv[ii][0][3] = __ldg(xh + (s0 + c3));
+                cv[ii][1][0] = __ldg(xh + (s1 + c0));
+                cv[ii][1][1] = __ldg(xh + (s1 + c1));
+                cv[ii][1][2] = __ldg(xh + (s1 + c2));
+                cv[ii][1][3] = __ldg(xh + (s1 + c3));
+              }
+#pragma unroll
+              for (int ii = 0; ii < SPH_BATCH; ++ii) {
+                const int r = w2 * (GEMM_BLOCK_M / SPH_PROD_WARPS) + i0 + ii;
+                const int e = r * 9 + t;
+                const float w0 = tbl_w[e], w1 = tbl_w[SPH_TABLE_ENTRIES + e], w2v = tbl_w[2 * SPH_TABLE_ENTRIES + e],
+                            w3 = tbl_w[3 * SPH_TABLE_ENTRIES + e];
+                const bool sb = r >= rb;
+                // same association as spgan_sphere_pack: ((a*w_nw + b*w_ne) + c*w_sw) + d*w_se
+                float v0 = cv[ii][0][0] * w0 + cv[ii][0][1] * w1 + cv[ii][0][2] * w2v + cv[ii][0][3] * w3;
+                float v1 = cv[ii][1][0] * w0 + cv[ii][1][1] * w1 + cv[ii][1][2] * w2v + cv[ii][1][3] * w3;
+                v0 *= sb ? mB0 : mA0;
+                v1 *= sb ? mB1 : mA1;
+                uint16_t h0, l0, h1, l1;
+                split16<kF16>(v0, h0, l0);
+                split16<kF16>(v1, h1, l1);
+                const uint32_t off0 = (uint32_t)r * 128u + (lane_col ^ ((uint32_t)(r & 7) << 4));
+                const uint32_t off1 = off0 ^ 64u;  // column lane + 32: chunk index + 4
+                *reinterpret_cast<uint16_t*>(a_hi + off0) = h0;
+                *reinterpret_cast<uint16_t*>(a_hi + off1) = h1;
+                if (S::kAPlanes == 2) {
+                  *reinterpret_cast<uint16_t*>(a_lo + off0) = l0;
+                  *reinterpret_cast<uint16_t*>(a_lo + off1) = l1;
+                }
+              }
+            }
+          } else {
 #pragma unroll 1
           for (int i0 = 0; i0 < GEMM_BLOCK_M / SPH_PROD_WARPS; i0 += 4) {
             float cv[4][2][4];
@@ -295,14 +358,14 @@ sphere_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const GemmParams gp,
                 }
                 val *= sel[ii] ? mulv[1][u] : mulv[0][u];
                 uint16_t hi, lo;
-                if (gp.a_f16) split16<true>(val, hi, lo);
-                else split16<false>(val, hi, lo);
+                split16<kF16>(val, hi, lo);
                 const int c = lane + 32 * u;
                 const int off = r * 128 + ((((c >> 3) ^ (r & 7))) << 4) + ((c & 7) << 1);
                 *reinterpret_cast<uint16_t*>(a_hi + off) = hi;
                 if (S::kAPlanes == 2) *reinterpret_cast<uint16_t*>(a_lo + off) = lo;
               }
             }
+          }
           }
           // generic-proxy writes -> visible to the tensor core's async proxy, then one arrive per warp
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -882,7 +882,13 @@ def sphere_modconv_fused(x, coords, grid, w, in_mul, out_mul, out_scale, act=Non
     return y
 
 
-FUSED_SPHERE_GATHER = True  # tests flip this to compare the fused kernel with the pack + GEMM composition
+# Which spherical-conv implementation the no_grad path uses.  False (default): spgan_sphere_pack -> spgan_conv_gemm (the
+# packer runs at full occupancy, the [B*H*W][9*Cp] operand takes a round trip through HBM).  True: spgan_sphere_conv_gemm,
+# the gather inside the GEMM's producer warps (no operand in HBM).  Measured on the B200 at B = 32, 256 + 3 -> 256 channels,
+# bf16x3: 35x35 0.48 ms vs 0.84 ms, 17x17 0.14 vs 0.47 ms — the eight producer warps of the persistent one-CTA-per-SM GEMM
+# issue ~96 instructions per (pixel, tap, 64 channels) at 41 % issue utilisation against a 1573-cycle MMA stage, so the
+# in-kernel producer is the bottleneck (profiles/r2_ncu_sphere_gemm.txt); it stays selectable and tested.
+FUSED_SPHERE_GATHER = False
 
 
 def sphere_conv_gemm(cp, flops, st, xh, coords, grid, in_mul, cmap, C, Cp, wp, fmt, **sinks):

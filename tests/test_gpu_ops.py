@@ -567,7 +567,7 @@ def test_sphere_gather_producer_gemm_vs_pack_then_gemm(dev, precision, B, C, Oc,
         try:
             outs.append(f.sphere_modconv_fused(x, c, grid, w, s, d, 0.05, act=(0.01, 1.0), precision=precision, residual=res, bias=bias))
         finally:
-            f.FUSED_SPHERE_GATHER = True
+            f.FUSED_SPHERE_GATHER = False
     assert K.rel_err(K.t2n(outs[0]), K.t2n(outs[1])) < 1e-5
 
 
