@@ -84,6 +84,19 @@ int spgan_sphere_gather_indices(int32_t* x0, int32_t* y0, float* wx, float* wy, 
  * grad_out (planes, 3H, 3W) → grad_in (planes, H, W).  The guarded all_reduce of :621-622 is deliberately absent. */
 int spgan_sphere_gather_bwd(float* grad_in, const float* grad_out, int64_t planes, int H, int W, void* stream);
 
+/* General 2-D grid samplers with their true input gradients (samplers the spgan.yaml generator does not instantiate but
+ * whose signatures the drop-in keeps): mode 0 = F.grid_sample(bilinear, border, align_corners=True) (GridSamplerNew,
+ * models/spherenet/grid_generator.py:588-592); mode 1 = grid_sample_github, bilinear weights from the unclipped coordinate
+ * and clamped corner indices (GridSamplerNewTexture, models/spherenet/grid_sample_ops.py:5-55); mode 2 =
+ * F.grid_sample(nearest, zeros, align_corners=True) (GridSampler, models/spherenet/grid_sample_grad_fix.py:29-48).
+ * z (B, C, IH, IW), grid (Bg, OH, OW, 2) with Bg in {1, B}, out (B, C, OH, OW).  spgan_grid_sample_bwd overwrites grad_z
+ * (B, C, IH, IW) with the transposed scatter of grad_out (aten::grid_sampler_2d_backward's grad_input / autograd of
+ * torch.gather); the op is linear in z, so its double backward is spgan_grid_sample itself. */
+int spgan_grid_sample(float* out, const float* z, const float* grid, int B, int C, int IH, int IW, int OH, int OW,
+                      int grid_batch, int mode, void* stream);
+int spgan_grid_sample_bwd(float* grad_z, const float* grad_out, const float* grid, int B, int C, int IH, int IW, int OH,
+                          int OW, int grid_batch, int mode, void* stream);
+
 /* Per-sample training grids assembled on the device (replaces the per-sample, per-layer host rebuild of
  * models/spgan_ops_gs.py:767-781 -> models/spherenet/grid_generator.py:137-283).  The grid separates into a row factor
  * (lat_n (slots_x, H, 9) fp32 final latitude coordinate; lon (slots_x, H, 9) fp64 tangent-plane longitude offset) and a

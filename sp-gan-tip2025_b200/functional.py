@@ -832,6 +832,70 @@ def sphere_gather(z, grid):
     return GridSamplerFuncNoGrad.apply(z, grid)
 
 
+GRID_SAMPLE_MODES = {"bilinear_border": 0, "texture": 1, "nearest_zeros": 2}
+
+
+def _grid_sample_raw(z, grid, mode, backward_to=None):
+    """Forward (backward_to=None): (B, C, IH, IW) sampled at grid (Bg, OH, OW, 2) -> (B, C, OH, OW).  Backward:
+    z = grad_out (B, C, OH, OW), backward_to = (IH, IW) -> grad wrt the sampled image."""
+    z = _f32c(z, "grid_sample")
+    grid = _f32c(grid, "grid_sample")
+    B, C = z.shape[0], z.shape[1]
+    OH, OW = grid.shape[1], grid.shape[2]
+    if grid.dim() != 4 or grid.shape[3] != 2 or grid.shape[0] not in (1, B):
+        raise RuntimeError("grid_sample: grid %s does not match input %s" % (tuple(grid.shape), tuple(z.shape)))
+    with torch.cuda.device(z.device):
+        if backward_to is None:
+            IH, IW = z.shape[2], z.shape[3]
+            out = torch.empty((B, C, OH, OW), device=z.device, dtype=torch.float32)
+            lib.call("spgan_grid_sample", _ptr(out), _ptr(z), _ptr(grid), B, C, IH, IW, OH, OW, grid.shape[0], mode, _stream(z))
+        else:
+            IH, IW = backward_to
+            if tuple(z.shape[2:]) != (OH, OW):
+                raise RuntimeError("grid_sample backward: gradient %s does not match grid %s" % (tuple(z.shape), tuple(grid.shape)))
+            out = torch.empty((B, C, IH, IW), device=z.device, dtype=torch.float32)
+            lib.call("spgan_grid_sample_bwd", _ptr(out), _ptr(z), _ptr(grid), B, C, IH, IW, OH, OW, grid.shape[0], mode, _stream(z))
+    return out
+
+
+class _GridSampleFn(torch.autograd.Function):
+    """Linear in z: backward = transposed scatter, double backward = the forward again (what the reference gets from
+    autograd through torch.gather, grid_sample_ops.py:43-53, and from _GridSample2dBackward, grid_sample_grad_fix.py:54-88).
+    The grid is a constant of the model (built from coords_partial on the host): no gradient flows to it."""
+
+    @staticmethod
+    def forward(ctx, z, grid, mode):
+        ctx.save_for_backward(grid)
+        ctx.mode, ctx.in_hw = mode, (z.shape[2], z.shape[3])
+        return _grid_sample_raw(z, grid, mode)
+
+    @staticmethod
+    def backward(ctx, go):
+        grid, = ctx.saved_tensors
+        return _GridSampleBwdFn.apply(go, grid, ctx.mode, ctx.in_hw), None, None
+
+
+class _GridSampleBwdFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, go, grid, mode, in_hw):
+        ctx.save_for_backward(grid)
+        ctx.mode = mode
+        return _grid_sample_raw(go, grid, mode, backward_to=in_hw)
+
+    @staticmethod
+    def backward(ctx, gg):
+        grid, = ctx.saved_tensors
+        return _GridSampleFn.apply(gg, grid, ctx.mode), None, None, None
+
+
+def grid_sample(z, grid, mode="bilinear_border"):
+    """The reference's other samplers with TRUE input gradients: "bilinear_border" = F.grid_sample(bilinear, border,
+    align_corners=True); "texture" = grid_sample_github (grid_sample_ops.py:5-55); "nearest_zeros" = the 'nearest' sampler of
+    the full-sphere convs (grid_sample_grad_fix.py:29-48)."""
+    _check_cuda(z, "grid_sample")
+    return _GridSampleFn.apply(z, grid, GRID_SAMPLE_MODES[mode])
+
+
 # =================================================================================================== spherical conv
 def sphere_modconv_fused(x, coords, grid, w, in_mul, out_mul, out_scale, act=None, flat_concat=True, precision=None,
                          residual=None, bias=None):
@@ -969,16 +1033,19 @@ def encode_coords(c):
     return torch.stack([torch.tanh(c[:, 0]), torch.cos(c[:, 1] * math.pi), torch.sin(c[:, 2] * math.pi)], 1)
 
 
-def sphere_modconv(x, coords, grid, w, in_mul, out_mul, out_scale, flat_concat=True):
-    """Differentiable spherical modulated conv: gather (surrogate backward) -> flat concat -> stride-3 conv."""
+def sphere_modconv(x, coords, grid, w, in_mul, out_mul, out_scale, flat_concat=True, sampler="surrogate"):
+    """Differentiable spherical modulated conv: gather -> flat concat -> stride-3 conv.  sampler = "surrogate": the live
+    GridSamplerNewTextureNoGrad (bilinear/border forward, 3x3 block-mean * 0.1 backward); "texture": GridSamplerNewTexture
+    of models/spgan_ops.py's SphereModulatedConv2d (grid_sample_github forward, true gradient)."""
     needs = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (x, w, in_mul, out_mul))
-    if not needs:
+    if not needs and sampler == "surrogate":
         return sphere_modconv_fused(x, coords, grid, w, in_mul, out_mul, out_scale, None, flat_concat)
     B, C, H, W = x.shape
     Ct = w.shape[1]
-    gx = sphere_gather(x, grid)
+    sample = sphere_gather if sampler == "surrogate" else (lambda t, g: grid_sample(t, g, "texture"))
+    gx = sample(x, grid)
     if coords is not None:
-        gc = encode_coords(sphere_gather(coords, grid))
+        gc = encode_coords(sample(coords, grid))
         if flat_concat:
             inp = torch.cat([gx.reshape(1, B * C, 3 * H, 3 * W), gc.reshape(1, B * coords.shape[1], 3 * H, 3 * W)], 1)
             inp = inp.view(B, Ct, 3 * H, 3 * W)
@@ -986,6 +1053,8 @@ def sphere_modconv(x, coords, grid, w, in_mul, out_mul, out_scale, flat_concat=T
             inp = torch.cat([gx, gc], 1)
     else:
         inp = gx
+    if not needs:
+        return conv_apply(inp, w, _SPHERE_GEOM, False, None, in_mul, out_mul, out_scale)
     return _ConvFn.apply(inp, w, in_mul, out_mul, _SPHERE_GEOM, False, None, out_scale)
 
 

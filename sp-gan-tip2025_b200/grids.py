@@ -146,6 +146,83 @@ def full_sphere_pattern(height, width, kernel_size=(3, 3), stride=(1, 1)):
     return out.reshape(1, H * kh, W * kw, 2)
 
 
+def _tangent_kernel_full(height, width, kernel_size):
+    """createKernel of the full-sphere generators (grid_generator.py:86-108, 562-582) and the derived rho / nu terms."""
+    kh, kw = kernel_size
+    d_lat = np.pi / height
+    d_lon = 2 * np.pi / width
+    rx = np.arange(-(kw // 2), kw // 2 + 1)
+    if not kw % 2:
+        rx = np.delete(rx, kw // 2)
+    ry = np.arange(-(kh // 2), kh // 2 + 1)
+    if not kh % 2:
+        ry = np.delete(ry, kh // 2)
+    ker_x, ker_y = np.meshgrid(np.tan(rx * d_lon), np.tan(ry * d_lat) / np.cos(ry * d_lon))
+    rho = np.sqrt(ker_x ** 2 + ker_y ** 2)
+    if kh % 2 and kw % 2:
+        rho[kh // 2][kw // 2] = 1e-8
+    nu = np.arctan(rho)
+    return ker_x, ker_y, rho, np.cos(nu), np.sin(nu)
+
+
+def _incre_range(n, k, stride):
+    """Row / column centres of IncreIntervalGridGenerator (grid_generator.py:464-521): arange(0, n, stride) trimmed by the
+    kernel half-width, then re-spread with linspace over [0, n]."""
+    if k == 1:
+        return np.arange(0, n, stride)
+    d = k // 2
+    base = np.arange(0, n, stride)
+    if stride not in (1, 2):
+        raise NotImplementedError
+    if k % 2 == 0:
+        r = base[d - 1: -d]
+    elif stride == 1:
+        r = base[d: -d]
+    elif d == 1:
+        r = base
+    else:
+        r = base[d - 1: -d + 1]
+    return np.linspace(0, n, len(r))
+
+
+def incre_interval_pattern(height, width, kernel_size=(3, 3), stride=(1, 1), upsample=False):
+    """IncreIntervalGridGenerator.createSamplingPattern (grid_generator.py:385-560): (1, H'*Kh, W'*Kw, 2) float64
+    (lat, lon) pixel positions; same tangent-plane formulas as the full-sphere pattern on re-spread row / column centres."""
+    kh, kw = kernel_size
+    sh, sw = stride
+    ker_x, ker_y, rho, cos_nu, sin_nu = _tangent_kernel_full(height, width, kernel_size)
+    if upsample:
+        out_h = sh * (height - kh * sh * 2 - 1) + (1 + sh * 2) * kh
+        out_w = sw * (width - kw * sw * 2 - 1) + (1 + sw * 2) * kw
+        h_range, w_range = np.linspace(0, height, out_h), np.linspace(0, width, out_w)
+    else:
+        if kernel_size[0] == 1:
+            h_range, w_range = np.arange(0, height, sh), np.arange(0, width, sw)
+        else:
+            h_range, w_range = _incre_range(height, kh, sh), _incre_range(width, kw, sw)
+    lat_c = ((h_range / height) - 0.5) * np.pi
+    lon_c = ((w_range / width) - 0.5) * (2 * np.pi)
+    t = lat_c[:, None, None]
+    lat = np.arcsin(cos_nu * np.sin(t) + ker_y * sin_nu * np.cos(t) / rho)
+    lon = np.arctan(ker_x * sin_nu / (rho * np.cos(t) * cos_nu - ker_y * np.sin(t) * sin_nu))
+    lon = lon[:, None, :, :] + lon_c[None, :, None, None]
+    lat = (lat / np.pi + 0.5) * height
+    lon = ((lon / (2 * np.pi) + 0.5) * width) % width
+    H, W = len(lat_c), len(lon_c)
+    out = np.empty((H, kh, W, kw, 2), dtype=np.float64)
+    out[..., 0] = lat[:, :, None, :]
+    out[..., 1] = lon.transpose(0, 2, 1, 3)
+    return out.reshape(1, H * kh, W * kw, 2)
+
+
+def full_sphere_grid(pattern, h, w):
+    """SphereConv2d.genSamplingPattern (sphere_conv2d.py:35-47): (lat, lon) pixel positions -> (1, H*Kh, W*Kw, 2) float32
+    grid in F.grid_sample convention (x = lon, y = lat)."""
+    lat = (pattern[:, :, :, 0] / h) * 2 - 1
+    lon = (pattern[:, :, :, 1] / w) * 2 - 1
+    return np.stack((lon, lat), axis=-1).astype(np.float32)
+
+
 _KEYS_ROW = ("p_x_st", "p_x_ed", "x_total", "y_total", "test_flag", "partial")
 _KEYS_COL = ("p_y_st", "p_y_ed", "circular_flag")
 

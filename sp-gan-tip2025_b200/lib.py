@@ -67,6 +67,8 @@ SIGNATURES = {
     "spgan_sphere_gather": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_i64, c_i64, c_int, c_vp]),
     "spgan_sphere_gather_indices": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_vp]),
     "spgan_sphere_gather_bwd": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_vp]),
+    "spgan_grid_sample": (c_int, [c_vp, c_vp, c_vp] + [c_int] * 8 + [c_vp]),
+    "spgan_grid_sample_bwd": (c_int, [c_vp, c_vp, c_vp] + [c_int] * 8 + [c_vp]),
     "spgan_sphere_grid_assemble": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, ctypes.c_double, c_vp]),
     "spgan_linear": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_f32, c_f32, c_int, c_f32, c_f32, c_vp]),
     "spgan_linear_wgrad": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_f32, c_vp]),

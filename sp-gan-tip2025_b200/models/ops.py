@@ -406,13 +406,48 @@ class ModulatedConv2d(nn.Module):
             if ((style - mean_style) < 1e-8).all():
                 style = mean_style.squeeze()
         if style.ndim != 2:
-            raise NotImplementedError(
-                "spatially-shaped styles (test-time style fusion, models/ops.py:640-729) are outside the B200 hot path")
+            return self._forward_spatial_style(input, style), flops
         s, w, d = self._mod_demod(style, batch)
         out = SF.conv2d(input, w, self._geom(), in_mul=s, out_mul=d, out_scale=self.scale)
         if self.upsample:
             out = self.blur(out)
         return out, flops
+
+    def _forward_spatial_style(self, input, style):
+        """Spatially-shaped styles, test-time style fusion (models/ops.py:637-729): the style modulates the ACTIVATIONS per
+        pixel, the conv runs with the un-modulated weight, and the demodulation is the per-pixel estimate
+        rsqrt(sum_c (sum_t (scale W)^2)[o, c] * s[b, c, y, x]^2 + 1e-8), bilinearly resized for the upsampling conv and — a
+        quirk of the reference kept here — applied to the plain conv only when it is unpadded (:721-723)."""
+        assert not self.training, "Only accepts spatially-shaped global-latent for testing-time manipulation!"
+        assert style.ndim == 4, "Only considered BxCxHxW case, but got shape {}".format(style.shape)
+        assert style.shape[2] >= input.shape[2] and style.shape[3] >= input.shape[3]
+        assert (style.shape[2] - input.shape[2]) % 2 == 0 and (style.shape[3] - input.shape[3]) % 2 == 0
+        ph, pw = (style.shape[2] - input.shape[2]) // 2, (style.shape[3] - input.shape[3]) // 2
+        style = style[:, :, ph:ph + input.shape[2], pw:pw + input.shape[3]]
+        sb, sc, sh, sw = style.shape
+        flat = style.permute(0, 2, 3, 1).reshape(-1, sc)
+        smod_flat = self.modulation(flat)                                    # (B*H*W, Cin) through the linear kernel
+        style_mod = smod_flat.view(sb, sh, sw, self.in_channel).permute(0, 3, 1, 2)
+        input_st = style_mod * input
+        w = self.weight[0]
+        demod = None
+        if self.demodulate:
+            wsq = (w * w).sum(dim=(2, 3))                                       # (Cout, Cin)
+            dflat = torch.rsqrt(SF._LinearFn.apply(smod_flat * smod_flat, wsq, None, self.scale * self.scale, 1.0) + 1e-8)
+            demod = dflat.view(sb, sh, sw, self.out_channel).permute(0, 3, 1, 2)
+        # the reference's spatial branch crops the transposed conv by one pixel whatever no_zero_pad says (:708)
+        geom = ConvGeom(self.kernel_size, self.kernel_size, stride=2, transposed=True, crop=1) if self.upsample else self._geom()
+        out = SF.conv2d(input_st, w, geom, out_scale=self.scale)
+        if self.upsample:
+            if demod is not None:
+                out = out * F.interpolate(demod, size=(out.shape[2], out.shape[3]), mode="bilinear", align_corners=True)
+            out = self.blur(out)
+        elif self.downsample:
+            raise NotImplementedError("Never used.")
+        elif demod is not None and self.padding == 0:
+            d0, d1 = self.dirty_rm_size
+            out = out * demod[:, :, d0:-d0, d1:-d1]
+        return out.contiguous()
 
     def forward_fused(self, input, style, noise, noise_weight, act_bias, act=(0.2, 2 ** 0.5)):
         """no_grad fast path for StyledConv: conv + noise + bias + leaky-ReLU in the GEMM epilogue (plain conv), or

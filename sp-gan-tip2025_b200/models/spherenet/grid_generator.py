@@ -25,6 +25,20 @@ class GridGenerator:
         return grids.full_sphere_pattern(self.height, self.width, self.kernel_size, self.stride)
 
 
+class IncreIntervalGridGenerator:
+    """grid_generator.py:385-582: full-sphere pattern on re-spread row / column centres (optionally the upsampling variant)."""
+
+    def __init__(self, height, width, kernel_size, stride=1, upsample=False):
+        if isinstance(height, torch.Tensor):
+            height, width = int(height), int(width)
+        self.height, self.width, self.upsample = height, width, upsample
+        self.kernel_size = _as_pair(kernel_size)
+        self.stride = _as_pair(stride)
+
+    def createSamplingPattern(self):
+        return grids.incre_interval_pattern(self.height, self.width, self.kernel_size, self.stride, self.upsample)
+
+
 class GridGeneratorPatchCoordsFixBorder:
     """Patch pattern parameterised by `coords_partial` (grid_generator.py:111-352)."""
 
@@ -55,20 +69,23 @@ class GridSamplerNewTextureNoGrad(nn.Module):
 
 
 class GridSamplerNew(nn.Module):
-    """grid_generator.py:588-592: plain F.grid_sample(bilinear, border, align_corners=True); forward only here."""
+    """grid_generator.py:588-592: F.grid_sample(bilinear, border, align_corners=True) with its true input gradient."""
 
     def forward(self, z, grid):
-        if torch.is_grad_enabled() and z.requires_grad:
-            raise NotImplementedError("GridSamplerNew: the true grid-sample gradient is not on the spgan.yaml path")
-        return SF.sphere_gather_raw(z, grid)
+        return SF.grid_sample(z, grid, "bilinear_border")
 
 
-class GridSamplerNewTexture(GridSamplerNew):
-    """grid_generator.py:595-599 (pure-torch gather in the reference; same values to 4.8e-7)."""
+class GridSamplerNewTexture(nn.Module):
+    """grid_generator.py:595-599 -> grid_sample_github (grid_sample_ops.py:5-55): bilinear weights from the unclipped
+    coordinate, corner indices clamped, true gradient (autograd through torch.gather in the reference)."""
+
+    def forward(self, z, grid):
+        return SF.grid_sample(z, grid, "texture")
 
 
 class GridSampler(nn.Module):
-    """grid_generator.py:580-585 ('nearest' sampler of the full-sphere variants).  Not reached by spgan.yaml."""
+    """grid_generator.py:580-585 -> grid_sample_grad_fix.grid_sample: F.grid_sample(nearest, zeros, align_corners=True) with
+    aten::grid_sampler_2d_backward's input gradient and a double backward (grid_sample_grad_fix.py:29-88)."""
 
     def forward(self, z, grid):
-        raise NotImplementedError("the 'nearest' sampler of SphereConv2d is not part of the spgan.yaml hot path")
+        return SF.grid_sample(z, grid, "nearest_zeros")

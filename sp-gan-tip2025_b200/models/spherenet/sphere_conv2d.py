@@ -6,6 +6,7 @@ from torch import nn
 
 from ... import functional as SF
 from ...functional import ConvGeom
+from ... import grids
 from ...grids import GRID_CACHE
 from ..ops import leaky_relu
 from .grid_generator import GridSampler, GridSamplerNewTextureNoGrad
@@ -53,8 +54,10 @@ class SphereConvBatchDiffFixBorderGNoGrad(nn.Conv2d):
 
 
 class SphereConv2d(nn.Conv2d):
-    """sphere_conv2d.py:16-67 (full-sphere variant with the 'nearest' sampler).  Signature kept; not reached by
-    spgan.yaml, so the forward is not implemented on the B200 path."""
+    """sphere_conv2d.py:16-67: SphereNet's full-sphere conv — sample the whole equirectangular feature at the tangent-plane
+    taps of every pixel ('nearest' sampler), then a Kh x Kw conv with stride = kernel size."""
+
+    _pattern = staticmethod(grids.full_sphere_pattern)
 
     def __init__(self, in_channels, out_channels, kernel_size=(3, 3), stride=1, padding=0, dilation=1, scale=None,
                  groups=1, bias=True, padding_mode='zeros'):
@@ -64,9 +67,30 @@ class SphereConv2d(nn.Conv2d):
         self.scale = scale
         self.sampler = GridSampler()
 
+    def genSamplingPattern(self, h, w):
+        pattern = self._pattern(h, w, tuple(self.kernel_size), tuple(self.stride))
+        self.grid = torch.from_numpy(grids.full_sphere_grid(pattern, h, w))
+
     def forward(self, x):
-        raise NotImplementedError("SphereConv2d (full-sphere 'nearest' variant) is not part of the spgan.yaml hot path")
+        B, C, H, W = x.shape
+        if self.grid_shape is None or self.grid_shape != (H, W):
+            self.grid_shape = (H, W)
+            self.genSamplingPattern(H, W)
+        if self.grid.device != x.device:
+            self.grid = self.grid.to(x.device)
+        if self.groups != 1 or tuple(self.dilation) != (1, 1) or self.kernel_size[0] != self.kernel_size[1] or \
+                self.padding[0] != self.padding[1]:
+            raise NotImplementedError("SphereConv2d: groups / dilation / rectangular kernels are not used by the reference")
+        g = self.sampler(x, self.grid)  # one grid shared by the batch (the reference repeats it B times)
+        k = self.kernel_size[0]
+        geom = ConvGeom(k, k, stride=k, pad=self.padding[0])
+        y = SF.conv2d(g, self.weight, geom, out_scale=self.scale if self.scale else 1.0)
+        if self.bias is not None:
+            y = y + self.bias.view(1, -1, 1, 1)
+        return y
 
 
 class IncreIntervalSphereConv2d(SphereConv2d):
-    """sphere_conv2d.py:70-121.  Signature kept; not reached by spgan.yaml."""
+    """sphere_conv2d.py:70-121: same op on IncreIntervalGridGenerator's pattern."""
+
+    _pattern = staticmethod(grids.incre_interval_pattern)
