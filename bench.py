@@ -34,6 +34,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--precision", type=int, default=1, choices=[0, 1, 2, 3])
     ap.add_argument("--streams", type=int, default=2, help="concurrent lattice-position branches of the panorama graph")
+    ap.add_argument("--group", type=int, default=2, help="lattice positions per generator call (panorama.PanoramaEngine group)")
     ap.add_argument("--ts-precision", default="", help="8 comma-separated per-layer modes for the texture chain")
     ap.add_argument("--fast-tail", action="store_true", help="also measure the fp16x2 tail policy (reported beside the headline)")
     ap.add_argument("--no-strict", action="store_true", help="do not also measure bf16x3-everywhere (reported beside the headline)")
@@ -219,9 +220,9 @@ def measure_panorama(args, dev, world, rank, local, th, tw, B, sharded, steps, w
     d2h = host_out.numel() * 4
     graphs = not args.no_graphs
     if sharded:
-        eng = panorama.ShardedPanoramaEngine(gen, pl, B, dev, rank, world, streams=args.streams, use_graph=graphs)
+        eng = panorama.ShardedPanoramaEngine(gen, pl, B, dev, rank, world, streams=args.streams, use_graph=graphs, group=args.group)
     else:
-        eng = panorama.PanoramaEngine(gen, pl, B, dev, streams=args.streams, use_graph=graphs)
+        eng = panorama.PanoramaEngine(gen, pl, B, dev, streams=args.streams, use_graph=graphs, group=args.group)
     eng.load(host["gl"], host["canvas"], host["noises"])
 
     def step_resident():
@@ -271,8 +272,8 @@ def measure_panorama(args, dev, world, rank, local, th, tw, B, sharded, steps, w
     if profile:
         # per-launch CUDA-event times need eager launches on one stream (events cannot be recorded inside a graph replay,
         # and concurrent branches would overlap the brackets): one extra eager step of the same work after the timed region
-        prof = (panorama.ShardedPanoramaEngine(gen, pl, B, dev, rank, world, streams=1, use_graph=False) if sharded
-                else panorama.PanoramaEngine(gen, pl, B, dev, streams=1, use_graph=False))
+        prof = (panorama.ShardedPanoramaEngine(gen, pl, B, dev, rank, world, streams=1, use_graph=False, group=args.group) if sharded
+                else panorama.PanoramaEngine(gen, pl, B, dev, streams=1, use_graph=False, group=args.group))
         prof.load(host["gl"], host["canvas"], host["noises"])
         prof.run()
         SF.profile_gemm(True)
@@ -407,8 +408,8 @@ def run_ours(args):
                    "batch_per_gpu": B, "patches_per_step_per_gpu": per_gpu_patches,
                    "l2": "inputs and activations larger than L2 (latent canvas %d MB, > 1 GB of operands per patch batch)" % m["canvas_mb"],
                    "precision_mode": args.precision, "ts_layer_precision": modes,
-                   "execution": "one CUDA graph per step, lattice positions on %d concurrent branches" % args.streams if m["graphs"]
-                                else "eager launches, %d streams" % args.streams,
+                   "execution": ("one CUDA graph per step, lattice positions on %d concurrent branches" % args.streams if m["graphs"]
+                                 else "eager launches, %d streams" % args.streams) + ", %d lattice positions per generator call" % args.group,
                    "algorithmic_tflop_per_step_per_gpu": per_gpu_patches * PATCH_GFLOP / 1000.0},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": m["d2h"], "ms_per_step": ms_e2e},
         "gpu_launches": m["launches"] * args.steps, "tcgen05_gemm_launches": m["gemm_launches"] * args.steps,

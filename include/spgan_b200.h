@@ -202,6 +202,23 @@ int spgan_nchw_to_nhwc(float* out, const float* x, int B, int C, int H, int W, v
  *   encodes exactly that mapping (or the per-sample concatenation) in the table. */
 int spgan_sphere_pack(uint16_t* out, const float* x_nhwc, const float* coords, const float* grid, const float* in_mul,
                       const uint32_t* chan_map, int B, int C, int H, int W, int grid_batch, int Cp, int fmt, void* stream);
+/* spgan_sphere_pack_seg: spgan_sphere_pack with the K layout of the structure synthesiser's chain: the first Cm channels of
+ *   every group (Cm a multiple of 64, 256 for spgan.yaml) go to out [2][B*H*W][9*Cm], k = tap*Cm + channel, and the trailing
+ *   Cx = C + nc - Cm channels (the coordinate planes, or the reference's flat-concat spill-over) of ALL nine taps go to the
+ *   dense tail operand out2 [2][B*H*W][kp2], k2 = tap*Cx + j (columns 9*Cx..kp2-1 zero), which spgan_conv_gemm_ex consumes as
+ *   its second K segment.  grid is (B / grid_group, 3H, 3W, 2): samples [i*grid_group, (i+1)*grid_group) share grid i, so
+ *   several lattice positions of a panorama (close_loop_infinite_generation.py:185-261) run as one batch; chan_map rows are
+ *   cmap_ld entries apart. */
+int spgan_sphere_pack_seg(uint16_t* out, uint16_t* out2, const float* x_nhwc, const float* coords, const float* grid,
+                          const float* in_mul, const uint32_t* chan_map, int B, int C, int H, int W, int grid_group, int Cm,
+                          int cmap_ld, int kp2, int fmt, void* stream);
+/* spgan_coord_taps_pack: the tail operand of an unpadded kh x kw conv whose last nc input channels are the encoded coordinate
+ *   planes (ConditionalBlock, models/spgan/spgan.py:100-101: torch.cat([x, encode(coords)]) -> 7x7 StyledConv):
+ *   out2 [2][B*My*Mx][kp2], row (b, y, x) of the My x Mx = (H-kh+1) x (W-kw+1) outputs, k2 = tap*nc + j,
+ *   value = enc_j(coords[b, j, y+ty, x+tx]) * in_mul[b*mul_ld + mul_off + j]  (enc = tanh, cos(pi.), sin(pi.);
+ *   coord_handler.py:696-711), 16-bit hi/lo split as in spgan_pack_act. */
+int spgan_coord_taps_pack(uint16_t* out2, const float* coords, const float* in_mul, int B, int nc, int H, int W, int kh,
+                          int kw, int mul_ld, int mul_off, int kp2, int fmt, void* stream);
 /* spgan_conv_gemm: the tcgen05 kernel.  `p` is a conv pass whose (H, W) are the LATTICE dims (Hl, Wl) of the packed
  *   activation, Cin is ignored (K per tap = kp, a multiple of 16), in_stride must be 1, tap_w is ignored (the packed
  *   weight is already in tap order) and precision must be 1 or 2.  a_packed [2][a_rows][kp], w_packed
@@ -253,6 +270,17 @@ typedef struct SpganGemmIO {
   float* rgb_part;
   const float* residual_nhwc;   /* channels-last residual (b, Y, X, o), added after the activation; needs the general sinks */
   int64_t res_bstride;          /* elements between samples of residual_nhwc; 0 = out_H*out_W*Cout */
+  /* optional second K segment, Y[p, o] += sum_k a2_packed[p, k] * w2_packed[o, k]: a2_packed [2][a2_rows][kp2] is indexed by
+   * the pass's own M row p (a lattice point in flat mode, the p-th output (b, i, j) in im2col mode), w2_packed [2][Cout][kp2],
+   * kp2 a multiple of 64, same 16-bit formats as the main operands.  It carries the channels that do not fill a 64-wide K block
+   * per tap (the 3 coordinate planes behind the 256 features of the structure synthesiser's 259-channel convs,
+   * models/spgan/spgan.py:100, models/spgan_ops_gs.py:812) for ALL taps in one dense slab, so the main operand keeps
+   * kp = 256 instead of padding every tap to 320. */
+  const uint16_t* a2_packed;
+  int64_t a2_rows;
+  const uint16_t* w2_packed;
+  int32_t kp2;
+  int32_t reserved0;
 } SpganGemmIO;
 int spgan_conv_gemm_ex(const SpganConvPass* p, const SpganGemmIO* io, void* stream);
 int spgan_conv_gemm_rgb_slots(const SpganConvPass* p, int64_t a_rows);

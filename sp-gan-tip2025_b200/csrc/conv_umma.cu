@@ -41,7 +41,8 @@ struct GemmSmem {
 
 template <int kPasses, int kBlockN>
 __global__ void __launch_bounds__(FWD_THREADS, 1)
-conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams gp,
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, const GemmParams gp,
                  const GemmSinks sk) {
   using S = GemmSmem<kPasses, kBlockN>;
   constexpr int kStages = S::kStages;
@@ -60,7 +61,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_tiles = gp.m_tiles * gp.n_tiles;
-  const int kiters = gp.ntaps * gp.kblocks;
+  const int kmain = gp.ntaps * gp.kblocks;
+  const int kiters = kmain + gp.k2blocks;  // + the blocks of the second K segment (A2 x W2), if any
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -87,6 +89,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+      if (gp.k2blocks > 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA2) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB2) : "memory");
+      }
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -127,6 +133,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
         }
+        // second K segment: rows of A2 are the tile's M rows themselves (no tap displacement), one weight slab
+        for (int kb = 0; kb < gp.k2blocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = smem_base + stage * S::kStageBytes;
+          mbar_arrive_expect_tx(full_bar(stage), S::kStageBytes);
+          const uint32_t sb = sa + S::kAPlanes * A_TILE_BYTES;
+          tma_load_3d(sa, &tmA2, full_bar(stage), kb * GEMM_BLOCK_K, m0, 0);
+          if (S::kAPlanes == 2) tma_load_3d(sa + A_TILE_BYTES, &tmA2, full_bar(stage), kb * GEMM_BLOCK_K, m0, 1);
+          tma_load_4d(sb, &tmB2, full_bar(stage), kb * GEMM_BLOCK_K, n0, 0, 0);
+          if (S::kBPlanes == 2) tma_load_4d(sb + kBTile, &tmB2, full_bar(stage), kb * GEMM_BLOCK_K, n0, 0, 1);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
       }
     }
     __syncwarp();
@@ -156,7 +177,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t b_lo = b_hi + kBTile;
           // the last K block of a tap may be partial (kp a multiple of 16, not of 64): TMA zero-fills the box, the MMAs
           // of the all-zero K steps are simply not issued
-          const int ksteps = ((it + 1) % gp.kblocks == 0) ? gp.last_ksteps : GEMM_BLOCK_K / GEMM_UMMA_K;
+          const int ksteps = (it < kmain && (it + 1) % gp.kblocks == 0) ? gp.last_ksteps : GEMM_BLOCK_K / GEMM_UMMA_K;
 #pragma unroll
           for (int k = 0; k < GEMM_BLOCK_K / GEMM_UMMA_K; ++k) {
             if (k >= ksteps) break;
@@ -497,7 +518,8 @@ std::atomic<long long>* launch_counter() {
 }
 
 template <int kPasses, int kBlockN>
-int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& gp, const GemmSinks& sk, cudaStream_t st) {
+int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmA2, const CUtensorMap& tmB2,
+                const GemmParams& gp, const GemmSinks& sk, cudaStream_t st) {
   using S = GemmSmem<kPasses, kBlockN>;
   static bool attr_set[64] = {false};
   int dev = 0;
@@ -509,7 +531,7 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams
   }
   const int tiles = gp.m_tiles * gp.n_tiles;
   const int grid = tiles < SPGAN_NUM_SMS ? tiles : SPGAN_NUM_SMS;
-  conv_gemm_kernel<kPasses, kBlockN><<<grid, FWD_THREADS, S::kTotal, st>>>(tmA, tmB, gp, sk);
+  conv_gemm_kernel<kPasses, kBlockN><<<grid, FWD_THREADS, S::kTotal, st>>>(tmA, tmB, tmA2, tmB2, gp, sk);
   SPGAN_CHECK_LAUNCH("spgan_conv_gemm");
   launch_counter()->fetch_add(1);
   return 0;
@@ -775,12 +797,36 @@ extern "C" int spgan_conv_gemm_ex(const SpganConvPass* p, const SpganGemmIO* io,
     cuuint32_t box[4] = {GEMM_BLOCK_K, (cuuint32_t)block_n, 1, 1};
     if (int e = encode_bf16_map(&tmB, io->w_packed, 4, dims, strides, box, "spgan_conv_gemm (B map)")) return e;
   }
+  // optional second K segment: Y += A2[p, :] * W2[o, :] over kp2 more columns (the few channels that do not fill a
+  // 64-wide block per tap, gathered over all taps into one dense slab instead of padding every tap)
+  CUtensorMap tmA2 = tmA, tmB2 = tmB;
+  gp.k2blocks = 0;
+  if (io->kp2 > 0) {
+    SPGAN_CHECK_ARG(io->a2_packed && io->w2_packed, "spgan_conv_gemm: kp2 > 0 needs a2_packed and w2_packed");
+    SPGAN_CHECK_ARG(io->kp2 % GEMM_BLOCK_K == 0, "spgan_conv_gemm: kp2=%d must be a multiple of 64", io->kp2);
+    SPGAN_CHECK_ARG(io->a2_rows >= gs.rows_m, "spgan_conv_gemm: a2_packed has %lld rows, the pass has %lld M rows",
+                    (long long)io->a2_rows, (long long)gs.rows_m);
+    SPGAN_CHECK_ARG(((((uintptr_t)io->a2_packed) | ((uintptr_t)io->w2_packed)) & 15) == 0, "spgan_conv_gemm: second-segment operands must be 16-byte aligned");
+    gp.k2blocks = io->kp2 / GEMM_BLOCK_K;
+    {
+      cuuint64_t dims[3] = {(cuuint64_t)io->kp2, (cuuint64_t)io->a2_rows, 2};
+      cuuint64_t strides[2] = {(cuuint64_t)io->kp2 * 2, (cuuint64_t)io->a2_rows * io->kp2 * 2};
+      cuuint32_t box[3] = {GEMM_BLOCK_K, GEMM_BLOCK_M, 1};
+      if (int e = encode_bf16_map(&tmA2, io->a2_packed, 3, dims, strides, box, "spgan_conv_gemm (A2 map)")) return e;
+    }
+    {
+      cuuint64_t dims[4] = {(cuuint64_t)io->kp2, (cuuint64_t)p->Cout, 1, 2};
+      cuuint64_t strides[3] = {(cuuint64_t)io->kp2 * 2, (cuuint64_t)p->Cout * io->kp2 * 2, (cuuint64_t)p->Cout * io->kp2 * 2};
+      cuuint32_t box[4] = {GEMM_BLOCK_K, (cuuint32_t)block_n, 1, 1};
+      if (int e = encode_bf16_map(&tmB2, io->w2_packed, 4, dims, strides, box, "spgan_conv_gemm (W2 map)")) return e;
+    }
+  }
   cudaStream_t st = (cudaStream_t)stream;
   if (p->precision == 1)
-    return block_n == 256 ? launch_gemm<3, 256>(tmA, tmB, gp, sk, st) : launch_gemm<3, 128>(tmA, tmB, gp, sk, st);
+    return block_n == 256 ? launch_gemm<3, 256>(tmA, tmB, tmA2, tmB2, gp, sk, st) : launch_gemm<3, 128>(tmA, tmB, tmA2, tmB2, gp, sk, st);
   if (p->precision == 3)
-    return block_n == 256 ? launch_gemm<2, 256>(tmA, tmB, gp, sk, st) : launch_gemm<2, 128>(tmA, tmB, gp, sk, st);
-  return block_n == 256 ? launch_gemm<1, 256>(tmA, tmB, gp, sk, st) : launch_gemm<1, 128>(tmA, tmB, gp, sk, st);
+    return block_n == 256 ? launch_gemm<2, 256>(tmA, tmB, tmA2, tmB2, gp, sk, st) : launch_gemm<2, 128>(tmA, tmB, tmA2, tmB2, gp, sk, st);
+  return block_n == 256 ? launch_gemm<1, 256>(tmA, tmB, tmA2, tmB2, gp, sk, st) : launch_gemm<1, 128>(tmA, tmB, tmA2, tmB2, gp, sk, st);
 }
 
 extern "C" int spgan_conv_gemm(const SpganConvPass* p, float* y, const uint16_t* a_packed, int64_t a_rows, int kp,

@@ -18,6 +18,7 @@ struct GemmParams {
   int64_t out_cstride;     // elements between output channels
   int32_t ntaps, kblocks;  // kblocks = ceil(kp / 64)
   int32_t last_ksteps;     // K = 16 steps in the last block of a tap (1..4)
+  int32_t k2blocks;        // 64-wide blocks of the second K segment (A2 x W2, rows = the tile's M rows), 0 = none
   int32_t tap_off[SPGAN_MAX_TAPS];
   int32_t m_tiles, n_tiles;
   float out_scale;

@@ -510,6 +510,22 @@ _EPOCH = 0
 _STYLE_EPOCH = 0
 
 
+def memo_by_tensor(store, slot, t, build, extra=None):
+    """build() memoised in the dict `store` per (slot, identity of tensor `t`, extra).  The entry keeps `t` alive, so its id
+    cannot be recycled.  Several entries per slot: a panorama engine that runs lattice positions in groups of different sizes
+    presents one style tensor per size, alternately (a single-entry memo would be recomputed on whichever stream comes next,
+    and its readers on other streams would race with that)."""
+    key = (slot, id(t), extra)
+    hit = store.get(key)
+    if hit is not None and hit[0] is t:
+        return hit[1]
+    while len(store) >= 64:
+        del store[next(iter(store))]  # oldest first: never the entries of the run in flight
+    val = build()
+    store[key] = (t, val)
+    return val
+
+
 def epoch():
     return (_EPOCH, _STYLE_EPOCH)
 
@@ -973,30 +989,39 @@ def sphere_conv_gemm(cp, flops, st, xh, coords, grid, in_mul, cmap, C, Cp, wp, f
 _CHAN_MAPS = {}
 
 
-def _sphere_chan_map(B, C, nc, Cp, flat_concat, device):
+def _sphere_chan_map(B, C, nc, Cp, flat_concat, device, group=None):
     """(B, Cp) uint32 table for spgan_sphere_pack: which gathered plane feeds channel k of group g.  With flat_concat
     the reference's (1, B*C) ++ (1, B*nc) concatenation under groups=B is reproduced (models/spgan_ops_gs.py:792-814):
-    group g reads flat channels [g*Ct, (g+1)*Ct)."""
-    key = (B, C, nc, Cp, flat_concat, str(device))
+    group g reads flat channels [g*Ct, (g+1)*Ct).  `group` (a divisor of B): the batch is a stack of independent generator
+    calls of `group` samples each (grids.PositionGroup); the table is then block-diagonal, every block the table of one
+    call."""
+    group = B if group is None else int(group)
+    key = (B, C, nc, Cp, flat_concat, str(device), group)
     t = _CHAN_MAPS.get(key)
     if t is not None:
         return t
     import numpy as np
+    if group <= 0 or B % group:
+        raise RuntimeError("sphere channel map: group %d does not divide the batch %d" % (group, B))
     Ct = C + nc
-    m = np.full((B, Cp), 0xFFFFFFFF, dtype=np.uint64)
-    g = np.arange(B)[:, None]
+    m = np.full((group, Cp), 0xFFFFFFFF, dtype=np.uint64)
+    g = np.arange(group)[:, None]
     k = np.arange(Ct)[None, :]
     if flat_concat:
         flat = g * Ct + k
-        feat = flat < B * C
-        bs = np.where(feat, flat // max(C, 1), (flat - B * C) // max(nc, 1))
-        cs = np.where(feat, flat % max(C, 1), (flat - B * C) % max(nc, 1))
+        feat = flat < group * C
+        bs = np.where(feat, flat // max(C, 1), (flat - group * C) // max(nc, 1))
+        cs = np.where(feat, flat % max(C, 1), (flat - group * C) % max(nc, 1))
     else:
-        feat = np.broadcast_to(k < C, (B, Ct))
-        bs = np.broadcast_to(g, (B, Ct))
+        feat = np.broadcast_to(k < C, (group, Ct))
+        bs = np.broadcast_to(g, (group, Ct))
         cs = np.where(feat, k, k - C)
-    m[:, :Ct] = (np.where(feat, 0, 1).astype(np.uint64) << 31) | (bs.astype(np.uint64) << 15) | cs.astype(np.uint64)
-    t = torch.from_numpy(m.astype(np.uint32).view(np.int32)).to(device)
+    blocks = []
+    for i in range(B // group):
+        blk = m.copy()
+        blk[:, :Ct] = (np.where(feat, 0, 1).astype(np.uint64) << 31) | ((bs + i * group).astype(np.uint64) << 15) | cs.astype(np.uint64)
+        blocks.append(blk)
+    t = torch.from_numpy(np.concatenate(blocks, 0).astype(np.uint32).view(np.int32)).to(device)
     _CHAN_MAPS[key] = t
     return t
 
@@ -1182,3 +1207,139 @@ def rgb_tail(part, slots, bias, skip, B, oh, ow):
     with torch.cuda.device(part.device):
         lib.call("spgan_rgb_tail", _ptr(out), _ptr(part), slots, _ptr(bias), _ptr(sk), B, n, oh * ow, _stream(part))
     return out
+
+
+# =================================================================================================== structure chain
+# Inference path of the structure synthesiser (models/spgan/spgan.py:79-254) with channels-last operands between its convs
+# and the 256 + 3 channel split of csrc/structure.cu: per block
+#   shortcut 1x1 GEMM (packed x -> NHWC fp32)  ->  spherical gather producer (NHWC x -> main + tail operand)  ->  spherical
+#   GEMM (+ LeakyReLU + shortcut residual, writes the 7x7 conv's packed operand)  ->  coordinate tail operand  ->  7x7 GEMM
+#   (+ bias + leaky-ReLU, writes the next block's NHWC gather source and packed shortcut operand, or the final NCHW tensor).
+def _packed_weight_tail(w, c0, tap_w, kp2, fmt):
+    """Second-segment weight [2][Cout][kp2], k2 = t*Cx + j <-> w[o, c0 + j, tap_w[t]]: the channels past c0 of every tap in
+    one dense slab (pairs with spgan_sphere_pack_seg / spgan_coord_taps_pack).  Cached per weight version like
+    _packed_weight; built with torch ops (a few KB, once per weight version)."""
+    key = ("tail", w.data_ptr(), w._version, tuple(w.shape), c0, tuple(tap_w), kp2, fmt, w.device.index)
+    hit = _WEIGHT_CACHE.get(key)
+    if hit is not None:
+        _WEIGHT_CACHE.move_to_end(key)
+        return hit[0]
+    O, C = w.shape[0], w.shape[1]
+    wt = w.detach().reshape(O, C, -1)[:, c0:, :][:, :, list(tap_w)]  # (O, Cx, T)
+    flat = wt.permute(0, 2, 1).reshape(O, -1)
+    if flat.shape[1] > kp2:
+        raise RuntimeError("weight tail: %d columns do not fit kp2=%d" % (flat.shape[1], kp2))
+    v = torch.zeros((O, kp2), device=w.device, dtype=torch.float32)
+    v[:, :flat.shape[1]] = flat
+    if fmt:
+        v = v.clamp(-65504.0, 65504.0)
+        hi = v.half()
+        lo = (v - hi.float()).half()
+    else:
+        hi = v.bfloat16()
+        lo = (v - hi.float()).bfloat16()
+    out = torch.stack([hi, lo]).contiguous().view(torch.bfloat16)
+    _WEIGHT_CACHE[key] = (out, w)
+    if len(_WEIGHT_CACHE) > _WEIGHT_CACHE_MAX:
+        _WEIGHT_CACHE.popitem(last=False)
+    return out
+
+
+SS_MAIN = 256  # feature channels per tap of the main K segment
+
+
+def ss_input(x, precision):
+    """NCHW fp32 local latent -> (NHWC fp32 gather source, packed un-modulated operand of the first shortcut conv)."""
+    x = _f32c(x, "structure chain")
+    B, C, H, W = x.shape
+    xh = torch.empty((B, H, W, C), device=x.device, dtype=torch.float32)
+    xp = torch.empty((2, B * H * W, C), device=x.device, dtype=torch.bfloat16)
+    with torch.cuda.device(x.device):
+        lib.call("spgan_nchw_to_nhwc", _ptr(xh), _ptr(x), B, C, H, W, _stream(x))
+        lib.call("spgan_pack_act", _ptr(xp), _ptr(x), _ptr(None), B, C, H, W, C, 0, 0, H, W, 1, _fmt(precision), _stream(x))
+    return xh, xp
+
+
+def ss_shortcut(xp, B, H, W, w, bias, precision):
+    """1x1 conv + bias (nn.Conv2d(256, 256, 1), models/spgan/spgan.py:141) from the packed operand -> NHWC fp32."""
+    O, C = w.shape[0], w.shape[1]
+    y = torch.empty((B, H, W, O), device=xp.device, dtype=torch.float32)
+    p = dict(My=H, Mx=W, in_stride=1, out_stride=1, off_y=0, off_x=0, taps=[(0, 0, 0)])
+    cp = _fill_pass(p, B, C, H, W, O, H, W, C, 1, 1.0, 0, 0.0, 1.0, precision)
+    with torch.cuda.device(xp.device):
+        wp = _packed_weight(w, O, C, C, 1, [0], xp.shape[2], False, _wfmt(precision))
+        _gemm_ex(cp, 2.0 * B * H * W * O * C, _stream(xp), a_packed=xp, a_rows=B * H * W, kp=xp.shape[2], fmt=_fmt(precision),
+                 w_fmt=_wfmt(precision), w_packed=wp, bias=bias, y=y, y_layout=1)
+    return y
+
+
+def ss_sphere(xh, coords, grid, grid_group, w, in_mul, out_mul, out_scale, act, residual_nhwc, next_mul, precision):
+    """Spherical modulated conv + LeakyReLU + shortcut residual (models/spgan_ops_gs.py:791-816, models/spgan/spgan.py:169)
+    from the NHWC gather source; writes the NEXT (7x7) conv's packed operand (2, B*H*W, Cout), modulated by next_mul."""
+    B, H, W, C = xh.shape
+    O, Ct = w.shape[0], w.shape[1]
+    nc = 0 if coords is None else coords.shape[1]
+    Cm = SS_MAIN
+    Cx = Ct - Cm
+    if Ct != C + nc or Cx < 0 or Cx >= 32 or C % 64:
+        raise RuntimeError("structure chain: %d + %d channels do not split as %d + tail" % (C, nc, Cm))
+    kp2 = _round_up(9 * Cx, 64) if Cx else 0
+    rows = B * H * W
+    fmt = _fmt(precision)
+    st = _stream(xh)
+    G = grid.shape[0]
+    if B % G or (B // G) != grid_group:
+        raise RuntimeError("structure chain: %d grids for a batch of %d in groups of %d" % (G, B, grid_group))
+    a = torch.empty((2, rows, 9 * Cm), device=xh.device, dtype=torch.bfloat16)
+    a2 = torch.empty((2, rows, kp2), device=xh.device, dtype=torch.bfloat16) if kp2 else None
+    out = torch.empty((2, rows, O), device=xh.device, dtype=torch.bfloat16)
+    alpha, gain = act
+    with torch.cuda.device(xh.device):
+        cmap = _sphere_chan_map(B, C, nc, _round_up(Ct, 64), True, xh.device, group=grid_group)
+        lib.call("spgan_sphere_pack_seg", _ptr(a), _ptr(a2), _ptr(xh), _ptr(coords), _ptr(grid), _ptr(in_mul), _ptr(cmap), B, C,
+                 H, W, grid_group, Cm, cmap.shape[1], kp2, fmt, st)
+        wp = _packed_weight(w, O, Cm, Ct * 9, 9, list(range(9)), Cm, True, _wfmt(precision))
+        w2 = _packed_weight_tail(w, Cm, list(range(9)), kp2, _wfmt(precision)) if kp2 else None
+        p = dict(My=H, Mx=W, in_stride=1, out_stride=1, off_y=0, off_x=0, taps=[(0, 0, 0)])
+        cp = _fill_pass(p, B, Ct, H, W, O, H, W, Ct * 9, 9, out_scale, 1, alpha, gain, precision)
+        _gemm_ex(cp, 2.0 * rows * O * Ct * 9, st, a_packed=a, a_rows=rows, kp=9 * Cm, fmt=fmt, w_fmt=_wfmt(precision), w_packed=wp,
+                 a2_packed=a2, a2_rows=rows if kp2 else 0, w2_packed=w2, kp2=kp2, out_mul=out_mul, residual_nhwc=residual_nhwc,
+                 y_packed=out, next_mul=next_mul, y_packed_rows=rows, y_packed_cols=O, y_packed_fmt=fmt)
+    return out
+
+
+def ss_conv_k(a, coords, B, H, W, w, in_mul, out_mul, out_scale, bias, act, precision, last):
+    """Unpadded k x k modulated conv + bias + leaky-ReLU (ConditionalBlock, models/spgan/spgan.py:100-101 + models/ops.py:853)
+    whose input is [256 features (packed operand `a`, already modulated), 3 encoded coordinate planes (tail operand built
+    here from the raw planes)].  Sinks: last=False -> (NHWC fp32, packed un-modulated operand) for the next block;
+    last=True -> the NCHW fp32 structure latent."""
+    O, Ct, kh, kw = w.shape
+    Cm = a.shape[2]
+    nc = Ct - Cm
+    oh, ow = H - kh + 1, W - kw + 1
+    T = kh * kw
+    kp2 = _round_up(T * nc, 64)
+    rows_out = B * oh * ow
+    fmt = _fmt(precision)
+    st = _stream(a)
+    alpha, gain = act
+    taps = [(ky, kx, ky * kw + kx) for ky in range(kh) for kx in range(kw)]
+    p = dict(My=oh, Mx=ow, in_stride=1, out_stride=1, off_y=0, off_x=0, taps=taps)
+    cp = _fill_pass(p, B, Ct, H, W, O, oh, ow, Ct * T, T, out_scale, 1, alpha, gain, precision)
+    a2 = torch.empty((2, rows_out, kp2), device=a.device, dtype=torch.bfloat16)
+    kw_sinks = {}
+    y = packed = None
+    if last:
+        y = torch.empty((B, O, oh, ow), device=a.device, dtype=torch.float32)
+        kw_sinks.update(y=y)
+    else:
+        y = torch.empty((B, oh, ow, O), device=a.device, dtype=torch.float32)
+        packed = torch.empty((2, rows_out, O), device=a.device, dtype=torch.bfloat16)
+        kw_sinks.update(y=y, y_layout=1, y_packed=packed, y_packed_rows=rows_out, y_packed_cols=O, y_packed_fmt=fmt)
+    with torch.cuda.device(a.device):
+        lib.call("spgan_coord_taps_pack", _ptr(a2), _ptr(coords), _ptr(in_mul), B, nc, H, W, kh, kw, Ct, Cm, kp2, fmt, st)
+        wp = _packed_weight(w, O, Cm, Ct * T, T, list(range(T)), Cm, False, _wfmt(precision))
+        w2 = _packed_weight_tail(w, Cm, list(range(T)), kp2, _wfmt(precision))
+        _gemm_ex(cp, 2.0 * rows_out * O * Ct * T, st, a_packed=a, a_rows=B * H * W, kp=Cm, fmt=fmt, w_fmt=_wfmt(precision),
+                 w_packed=wp, a2_packed=a2, a2_rows=rows_out, w2_packed=w2, kp2=kp2, out_mul=out_mul, bias=bias, **kw_sinks)
+    return y, packed, (oh, ow)

@@ -113,7 +113,72 @@ class ImplicitFunction(nn.Module):
         self.conv_stack = nn.Sequential(*convs)
         self.global_mapping = None  # spgan.yaml has no ss_mapping
 
+    use_chain = True
+
+    def _chain_ok(self, global_latent, local_latent, coords, coords_partial, noises, test_ids, calc_flops):
+        """The channels-last structure chain covers spgan.yaml's inference configuration: test-mode sampling grids (one
+        dict, or a grids.PositionGroup of several lattice positions), 256 features + 3 coordinate planes on every layer,
+        no noise in the structure convs, bf16 operand planes (precision 1 or 2)."""
+        from .grids import PositionGroup
+        if not self.use_chain or calc_flops or test_ids is not None or coords is None or not local_latent.is_cuda:
+            return False
+        if SF.get_precision() not in (1, 2) or self.global_mapping is not None:
+            return False
+        if not (isinstance(coords_partial, dict) or isinstance(coords_partial, PositionGroup)):
+            return False
+        if ops._grad_needed(global_latent, local_latent, coords, *self.parameters()):
+            return False
+        if len(self.conv_stack) % 2 or local_latent.shape[1] != SF.SS_MAIN:
+            return False
+        for i, blk in enumerate(self.conv_stack):
+            sc = blk.conv
+            if i % 2 == 0:
+                if not (isinstance(blk, SphereConditionalBlock) and blk.deal_coords and sc.noise is None and sc.conv.deal_coords
+                        and isinstance(sc.activate, nn.LeakyReLU) and not sc.upsample and sc.conv.padding == 0
+                        and sc.conv.demodulate and sc.conv.out_channel == SF.SS_MAIN and sc.conv.in_channel == SF.SS_MAIN + 3):
+                    return False
+            else:
+                c = sc.conv
+                if not (isinstance(blk, ConditionalBlock) and sc.noise is None and not c.upsample and c.padding == 0 and c.demodulate
+                        and c.out_channel == SF.SS_MAIN and c.in_channel == SF.SS_MAIN + 3
+                        and blk.config.train_params.ss_coord_all_layers):
+                    return False
+        return True
+
+    def _forward_chain(self, global_latent, local_latent, coords, coords_partial):
+        from .grids import GRID_CACHE, PositionGroup
+        B, _, H, W = local_latent.shape
+        prec = SF.get_precision()
+        if isinstance(coords_partial, PositionGroup):
+            cps, group = list(coords_partial), coords_partial.group
+        else:
+            cps, group = [coords_partial], B
+        if len(cps) * group != B:
+            raise RuntimeError("structure chain: %d positions x %d samples for a batch of %d" % (len(cps), group, B))
+        xh, xp = SF.ss_input(local_latent, prec)
+        memo = self.__dict__.setdefault("_next_mul_cache", {})
+        out = None
+        n = len(self.conv_stack)
+        for i in range(0, n, 2):
+            sph, cnd = self.conv_stack[i], self.conv_stack[i + 1]
+            cc = center_crop(coords, H, W).contiguous()
+            s_s, w_s, d_s = sph.conv.conv._mod_demod(global_latent, B)
+            s_c, w_c, d_c = cnd.conv.conv._mod_demod(global_latent, B)
+            mul7 = SF.memo_by_tensor(memo, i, s_c, lambda: s_c[:, :SF.SS_MAIN].contiguous())
+            grid = GRID_CACHE.group_grid(H, W, cps, local_latent.device)
+            y_sc = SF.ss_shortcut(xp, B, H, W, sph.sc.weight, sph.sc.bias, prec)
+            a = SF.ss_sphere(xh, cc, grid, group, w_s, s_s, d_s, sph.conv.conv.scale, (sph.conv.activate.negative_slope, 1.0),
+                             y_sc, mul7, prec)
+            act = cnd.conv.activate
+            last = i + 2 >= n
+            xh, xp, (H, W) = SF.ss_conv_k(a, cc, B, H, W, w_c, s_c, d_c, cnd.conv.conv.scale, act.bias,
+                                          (act.negative_slope, act.scale), prec, last)
+            out = xh
+        return out
+
     def forward(self, global_latent, local_latent, coords, coords_partial, noises=None, test_ids=None, calc_flops=False):
+        if self._chain_ok(global_latent, local_latent, coords, coords_partial, noises, test_ids, calc_flops):
+            return self._forward_chain(global_latent, local_latent, coords, coords_partial), 0
         h = local_latent
         flops = 0
         for conv in self.conv_stack:
@@ -278,10 +343,8 @@ class TextureSynthesizer(nn.Module):
         if modes[i] != 3 or self.act_scale is None or self.act_scale[i] == 1.0:
             return s, 1.0
         cache = self.__dict__.setdefault("_scaled_mul_cache", {})
-        hit = cache.get(i)
-        if hit is None or hit[0] is not s or hit[1] != self.act_scale[i]:
-            hit = cache[i] = (s, self.act_scale[i], s * (1.0 / self.act_scale[i]))
-        return hit[2], self.act_scale[i]
+        k = self.act_scale[i]
+        return SF.memo_by_tensor(cache, i, s, lambda: s * (1.0 / k), extra=k), k
 
     def _forward_chain(self, styles, structure_latent, coords_partial, noises, modes=None, record=None):
         """The synthesis loop with channels-last operands between the convs (csrc/chain.cu): per (upsampling conv, conv)
@@ -315,12 +378,10 @@ class TextureSynthesizer(nn.Module):
             last = 2 * k + 2 >= self.num_layers
             rgb_mod = self.to_rgbs[k]
             s_r, w_r, _ = rgb_mod.conv._mod_demod(styles[:, self.TO_RGBS[k][1]], B)
-            cached = getattr(rgb_mod, "_rgbw_cache", None)
-            if cached is None or cached[0] is not s_r or cached[1] != w_r._version:
-                rgb_w = (w_r.reshape(1, w_r.shape[0], w_r.shape[1]) * s_r.unsqueeze(1) * rgb_mod.conv.scale).contiguous()
-                object.__setattr__(rgb_mod, "_rgbw_cache", (s_r, w_r._version, rgb_w))
-            else:
-                rgb_w = cached[2]
+            rgb_cache = rgb_mod.__dict__.setdefault("_rgbw_cache", {})
+            rgb_w = SF.memo_by_tensor(
+                rgb_cache, 0, s_r, lambda: (w_r.reshape(1, w_r.shape[0], w_r.shape[1]) * s_r.unsqueeze(1) * rgb_mod.conv.scale).contiguous(),
+                extra=(w_r._version, SF.epoch()))
             mul_n, k_next = (None, 1.0) if last else self._scaled_mul(2 * k + 2, sd[2 * k + 2][0], modes)
             a, rgb, _, (H, W) = SF.chain_conv3(a, B, H, W, w_c, d_c, cv.conv.scale * k_in, noises[2 * k + 1], cv.noise.weight,
                                                cv.activate.bias, (cv.activate.negative_slope, cv.activate.scale),

@@ -310,6 +310,18 @@ class DeviceWindows(list):
         self.tables, self.ix, self.iy = tables, ix, iy
 
 
+class PositionGroup(list):
+    """Test-mode `coords_partial` of SEVERAL lattice positions run as ONE batch (the reference's manager issues one
+    generator call per position, test_managers/close_loop_infinite_generation.py:185-261): entry i is the dict of position
+    i, whose `group` samples are rows [i*group, (i+1)*group) of the batch.  Every per-sample quantity of the generator is
+    independent across the batch except the spherical conv's flat-concat channel table, which the reference builds per
+    call — the table is therefore block-diagonal over the groups (functional._sphere_chan_map)."""
+
+    def __init__(self, cps, group):
+        super().__init__(cps)
+        self.group = int(group)
+
+
 class GridCache:
     """Device-resident sampling grids.
 
@@ -387,9 +399,27 @@ class GridCache:
                      vp(idx[1]), B, h, w, float(y_total), ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream))
         return out
 
+    def group_grid(self, h, w, cps, device):
+        """(G, 3h, 3w, 2): one test-mode grid per lattice position of a PositionGroup (memoised per tuple of positions)."""
+        key = ("group", h, w, str(device)) + tuple(self._key(h, w, cp, device) for cp in cps)
+        g = self._store.get(key)
+        if g is None:
+            g = self._store[key] = torch.cat([self.get(h, w, cp, device) for cp in cps], 0).contiguous()
+        return g
+
     def batch(self, h, w, coords_partial, batch, device):
         """Training: a list of per-sample dicts -> (B, 3h, 3w, 2); test: one dict -> (1, 3h, 3w, 2) shared by the
         batch (models/spgan_ops_gs.py:760-789)."""
+        if isinstance(coords_partial, PositionGroup):
+            if len(coords_partial) * coords_partial.group != batch:
+                raise RuntimeError("PositionGroup of %d x %d samples for a batch of %d" % (len(coords_partial), coords_partial.group, batch))
+            if len(coords_partial) == 1:
+                return self.get(h, w, coords_partial[0], device)
+            key = ("expanded", coords_partial.group, h, w, str(device)) + tuple(self._key(h, w, cp, device) for cp in coords_partial)
+            g = self._store.get(key)
+            if g is None:  # per-sample copy for the consumers that know only "one grid" or "one grid per sample"
+                g = self._store[key] = self.group_grid(h, w, coords_partial, device).repeat_interleave(coords_partial.group, dim=0).contiguous()
+            return g
         if isinstance(coords_partial, (list, tuple)):
             if len(coords_partial) != batch:
                 raise RuntimeError("coords_partial has %d entries for a batch of %d" % (len(coords_partial), batch))

@@ -43,6 +43,7 @@ class GemmIO(ctypes.Structure):
         ("y_packed", c_vp), ("next_mul", c_vp), ("y_packed_rows", ctypes.c_int64), ("y_packed_cols", ctypes.c_int32),
         ("y_packed_fmt", ctypes.c_int32), ("rgb_w", c_vp), ("rgb_part", c_vp),
         ("residual_nhwc", c_vp), ("res_bstride", ctypes.c_int64),
+        ("a2_packed", c_vp), ("a2_rows", ctypes.c_int64), ("w2_packed", c_vp), ("kp2", ctypes.c_int32), ("reserved0", ctypes.c_int32),
     ]
 
 
@@ -83,6 +84,8 @@ SIGNATURES = {
     "spgan_pack_weight": (c_int, [c_vp, c_vp, c_int, c_int, c_i64, c_i64, c_int, ctypes.POINTER(ctypes.c_int32), c_int, c_int, c_int, c_vp]),
     "spgan_nchw_to_nhwc": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp]),
     "spgan_sphere_pack": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
+    "spgan_sphere_pack_seg": (c_int, [c_vp] * 7 + [c_int] * 9 + [c_vp]),
+    "spgan_coord_taps_pack": (c_int, [c_vp, c_vp, c_vp] + [c_int] * 10 + [c_vp]),
     "spgan_conv_gemm": (c_int, [_PASS_P, c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "spgan_conv_gemm_ex": (c_int, [_PASS_P, ctypes.c_void_p, c_vp]),
     "spgan_conv_gemm_rgb_slots": (c_int, [_PASS_P, c_i64]),

@@ -390,12 +390,20 @@ class ModulatedConv2d(nn.Module):
                self.weight._version, self.modulation.weight._version,
                self.modulation.bias._version if self.modulation.bias is not None else -1,
                self.weight.data_ptr(), self.modulation.weight.data_ptr())
-        cached = getattr(self, "_md_cache", None)
-        if cached is not None and cached[0] == key:
-            return cached[2], w, cached[3]
+        cache = self.__dict__.setdefault("_md_cache", {})
+        cached = cache.get(key)
+        if cached is not None:
+            return cached[1], w, cached[2]
         s = self.modulation(style).view(batch, self.in_channel)
         d = SF.demod_coefficients(w, s, self.scale, 1e-8) if self.demodulate else None
-        object.__setattr__(self, "_md_cache", (key, style, s, d))
+        # several live styles per module (one per position-group size of a panorama engine); entries of an older epoch are
+        # dead.  Never evict a live entry: a concurrent branch of a captured graph may only READ what the launching stream
+        # computed before the fork (panorama.PanoramaEngine._body)
+        for k in [k for k in cache if k[0] != key[0]]:
+            del cache[k]
+        while len(cache) >= 16:
+            del cache[next(iter(cache))]  # oldest first
+        cache[key] = (style, s, d)
         return s, w, d
 
     def forward(self, input, style, coords=None, calc_flops=False):

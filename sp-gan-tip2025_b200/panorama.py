@@ -135,6 +135,31 @@ def _run_position(gen, pl, global_latent, local_latent, coords_full, noises, sty
     return gen(global_latent, cur_lat, cur_coords, cp, noises=cur_noises, styles=styles)
 
 
+def _run_positions(gen, pl, global_latent, local_latent, coords_full, noises, styles, items):
+    """Several lattice positions as ONE generator call: their patch batches are stacked along the batch axis
+    (position-major) and the per-position sampling grids travel as a grids.PositionGroup.  `items` = [(it, ix, iy)];
+    `global_latent` / `styles` are already repeated len(items) times.  Returns (len(items) * B, 3, P, P)."""
+    from .grids import PositionGroup
+    if len(items) == 1:
+        it, ix, iy = items[0]
+        return _run_position(gen, pl, global_latent, local_latent, coords_full, noises, styles, it, ix, iy)
+    B = local_latent.shape[0]
+    lat_h, lat_w = local_latent.shape[2], local_latent.shape[3]
+    cps, lats, crds = [], [], []
+    nzs = [[] for _ in range(8)]
+    for it, ix, iy in items:
+        cp, (zx_st, zx_ed, zy_st, zy_ed) = patch_inputs(pl, ix, iy, it, lat_h, lat_w)
+        cps.append(cp)
+        lats.append(circular_slice(local_latent, lat_w, zx_st, zx_ed, zy_st, zy_ed))
+        crds.append(circular_slice(coords_full, lat_w, zx_st, zx_ed, zy_st, zy_ed))
+        for l in range(8):
+            fx, fy = ix * pl["outfeat_step"][l], iy * pl["outfeat_step"][l]
+            s = pl["out_sizes"][l]
+            nzs[l].append(circular_slice(noises[l], pl["noise_w"][l], fx, fx + s, fy, fy + s))
+    return gen(global_latent, torch.cat(lats, 0), torch.cat(crds, 0), PositionGroup(cps, B),
+               noises=[torch.cat(n, 0) for n in nzs], styles=styles)
+
+
 def _prepare(gen, global_latent, local_latent):
     B = local_latent.shape[0]
     coords_full = meta_coords(local_latent.shape[2], local_latent.shape[3], local_latent.device).unsqueeze(0).expand(B, -1, -1, -1)
@@ -220,10 +245,15 @@ class PanoramaEngine:
     the static (B, 3, meta_h, meta_w) meta image.  `only` restricts the engine to a set of lattice positions (rank
     sharding); `assemble=False` leaves the patches in `self.patches` (the sharded path exchanges them first)."""
 
-    def __init__(self, gen, pl, batch, device, streams=2, only=None, use_graph=True, assemble=True):
+    def __init__(self, gen, pl, batch, device, streams=2, only=None, use_graph=True, assemble=True, group=1):
         self.gen, self.pl, self.B, self.device = gen, pl, batch, torch.device(device)
         self.pos = [(it, ix, iy) for it, (ix, iy) in enumerate(positions(pl)) if only is None or (ix, iy) in only]
-        self.n_streams = max(1, min(int(streams), len(self.pos)))
+        # `group` consecutive lattice positions run as ONE generator call of group * batch patches (SURVEY.md §8 f2 / fact 12:
+        # the reference issues one call per position): the small layers of the structure synthesiser and the first texture
+        # layers then fill whole waves of the 148 SMs, and the launch count per panorama drops by the same factor
+        self.group = max(1, int(group))
+        self.items = [list(range(i, min(i + self.group, len(self.pos)))) for i in range(0, len(self.pos), self.group)]
+        self.n_streams = max(1, min(int(streams), len(self.items)))
         self.use_graph, self.assemble = use_graph, assemble
         d = self.device
         self.gl = torch.zeros(batch, 2, 512, device=d)
@@ -245,33 +275,48 @@ class PanoramaEngine:
         for dst, src in zip(self.noises, noises):
             dst.copy_(src, non_blocking=True)
 
-    def _position(self, slot, styles):
-        it, ix, iy = self.pos[slot]
-        self.patches[slot].copy_(_run_position(self.gen, self.pl, self.gl, self.canvas, self.coords_full, self.noises,
-                                               styles, it, ix, iy))
+    def _position(self, item, rep):
+        """Run one group of lattice positions; rep[n] = (global latent, styles) repeated n times."""
+        slots = self.items[item]
+        gl, styles = rep[len(slots)]
+        out = _run_positions(self.gen, self.pl, gl, self.canvas, self.coords_full, self.noises, styles,
+                             [self.pos[s] for s in slots])
+        if slots[-1] - slots[0] + 1 == len(slots):
+            self.patches[slots[0]:slots[-1] + 1].copy_(out.view(len(slots), self.B, *out.shape[1:]))
+        else:
+            for i, s in enumerate(slots):
+                self.patches[s].copy_(out[i * self.B:(i + 1) * self.B])
 
     def _body(self):
         main = torch.cuda.current_stream(self.device)
         styles = self.gen.texture_synthesizer.styles_for(self.gl)
-        # the first position runs alone on the launching stream: it computes every layer's memoised (modulation,
-        # demodulation) pair, which the concurrent branches then only read
-        self._position(0, styles)
-        if self.n_streams > 1 and len(self.pos) > 1:
+        rep = {n: (self.gl if n == 1 else self.gl.repeat(n, 1, 1), styles if n == 1 else styles.repeat(n, 1, 1))
+               for n in {len(g) for g in self.items}}
+        # the first group OF EACH SIZE runs alone on the launching stream: it computes every layer's memoised (modulation,
+        # demodulation) pair for that batch size, which the concurrent branches then only read
+        first = {}
+        for idx, g in enumerate(self.items):
+            first.setdefault(len(g), idx)
+        pre = sorted(first.values())
+        rest = [i for i in range(len(self.items)) if i not in pre]
+        for idx in pre:
+            self._position(idx, rep)
+        if self.n_streams > 1 and len(rest) > 1:
             fork = torch.cuda.Event()
             fork.record(main)
             lanes = [main] + self._side
             for s in self._side:
                 s.wait_event(fork)
-            for slot in range(1, len(self.pos)):
-                with torch.cuda.stream(lanes[slot % len(lanes)]):
-                    self._position(slot, styles)
+            for k, item in enumerate(rest):
+                with torch.cuda.stream(lanes[(k + 1) % len(lanes)]):
+                    self._position(item, rep)
             for s in self._side:
                 join = torch.cuda.Event()
                 join.record(s)
                 main.wait_event(join)
         else:
-            for slot in range(1, len(self.pos)):
-                self._position(slot, styles)
+            for item in rest:
+                self._position(item, rep)
         if self.assemble:
             P = self.pl["patch"]
             for slot, (it, ix, iy) in enumerate(self.pos):
@@ -335,12 +380,12 @@ class ShardedPanoramaEngine:
     ... (a PanoramaEngine over that subset, same graph + concurrent-branch machinery), the finished patches are exchanged
     with ONE all-gather, and every rank assembles in the reference's row-major order (see generate_sharded)."""
 
-    def __init__(self, gen, pl, batch, device, rank, world, streams=2, use_graph=True):
+    def __init__(self, gen, pl, batch, device, rank, world, streams=2, use_graph=True, group=1):
         self.pl, self.B, self.rank, self.world = pl, batch, rank, world
         self.all_pos = positions(pl)
         mine = self.all_pos[rank::world]
         self.engine = PanoramaEngine(gen, pl, batch, device, streams=streams, only=set(mine), use_graph=use_graph,
-                                     assemble=False)
+                                     assemble=False, group=group)
         self.per_rank = -(-len(self.all_pos) // world)
         P = pl["patch"]
         self.mine = torch.zeros(self.per_rank, batch, 3, P, P, device=self.engine.device)

@@ -233,3 +233,49 @@ def test_panorama_768_golden_strip_and_seam(gen):
     assert max(errs) < 5e-4
     assert abs(img.mean() - float(ref["mean"])) < 1e-3 * float(ref["std"])
     assert abs(img.std() - float(ref["std"])) < 1e-3 * float(ref["std"])
+
+
+def test_structure_chain_matches_module_path(gen):
+    """The channels-last structure chain (256-channel main K segment + dense coordinate tail segment, shortcut as the
+    residual of the spherical GEMM, packed / NHWC sinks between the convs) computes what the module-by-module path computes
+    (259 channels padded to 320 per tap, NCHW fp32 tensors between the convs): same products, different summation order."""
+    from spgan_b200.generator import ImplicitFunction
+    for name, B, pos in [("b1_p27", 1, (2, 7)), ("b2_p59", 2, (5, 9))]:
+        gl, lat, coords, cp, _ = K.generator_case(name, B, *pos)
+        ss = gen.structure_synthesizer
+        with torch.no_grad():
+            a, _ = ss(gl.cuda()[:, 0], lat.cuda(), coords.cuda(), cp)
+            ImplicitFunction.use_chain = False
+            try:
+                b, _ = ss(gl.cuda()[:, 0], lat.cuda(), coords.cuda(), cp)
+            finally:
+                ImplicitFunction.use_chain = True
+        assert a.shape == b.shape == (B, 256, 11, 11)
+        err = K.rel_err(K.t2n(a), K.t2n(b))
+        print("structure chain vs module path, %s: %.2e" % (name, err))
+        assert err < 5e-5
+
+
+@pytest.mark.parametrize("group,streams,graph", [(3, 1, False), (2, 2, True)])
+def test_panorama_engine_position_groups(gen, group, streams, graph):
+    """Several lattice positions per generator call (grids.PositionGroup: stacked patch batches, one sampling grid per
+    position, block-diagonal flat-concat table) give the patches of the one-position-per-call loop; 7 positions in groups of
+    3 / 2 leave a ragged last group."""
+    from spgan_b200 import panorama
+    pl = panorama.plan(384, 768)
+    B = 2
+    only = set(panorama.positions(pl)[8:15])  # crosses a lattice row: two different latitude windows in one group
+    eng = panorama.PanoramaEngine(gen, pl, B, "cuda:0", streams=streams, only=only, use_graph=graph, group=group)
+    for seed in (1, 2, 3, 4):
+        g = torch.Generator(device="cpu").manual_seed(seed)
+        gl = torch.randn(B, 512, generator=g).cuda()
+        canvas = torch.randn(B, 256, pl["lat_h"], pl["lat_w"], generator=g).cuda()
+        noises = [torch.randn(B, 1, pl["noise_h"][l], pl["noise_w"][l], generator=g).cuda() for l in range(8)]
+        want = panorama.generate(gen, pl, gl, canvas, noises, only=only)
+        eng.load(gl, canvas, noises)
+        got = eng.run()
+        err = K.rel_err(K.t2n(got), K.t2n(want))
+        print("position groups of %d, seed %d: %.2e" % (group, seed, err))
+        # the GEMM rows are bit-identical; only the ToRGB partial sums are added in a different order (N-tile count)
+        assert err < 2e-6, seed
+    assert (eng.graph is not None) == graph

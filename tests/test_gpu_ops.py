@@ -638,3 +638,59 @@ def test_linear_second_order_vs_torch(dev):
             assert a is None or float(a.abs().max()) == 0.0
         else:
             assert K.rel_err(K.t2n(a), K.t2n(r)) < 2e-5
+
+
+@pytest.mark.parametrize("precision,tol", [(1, 1e-4), (2, 3e-2)])
+def test_structure_chain_ops_vs_padded_path(precision, tol):
+    """K-segment operands of the structure chain (spgan_sphere_pack_seg / spgan_coord_taps_pack feeding the second K segment
+    of spgan_conv_gemm_ex) against the same convs computed with every tap padded to 320 channels (sphere_modconv_fused,
+    conv_apply), two position groups with different sampling grids."""
+    import spgan_b200.functional as SF  # noqa: F811 (module, not the helper above)
+    from spgan_b200 import grids
+    dev = torch.device("cuda:0")
+    G, Bg, C, H = 2, 3, 256, 17
+    B = G * Bg
+    cps = [{"p_x_st": 6 / 65, "p_x_ed": 42 / 65, "p_y_st": 12 / 48, "p_y_ed": 48 / 48, "circular_flag": False, "x_total": 65,
+            "y_total": 48, "test_flag": True, "partial": 0.6667},
+           {"p_x_st": 12 / 65, "p_x_ed": 48 / 65, "p_y_st": 30 / 48, "p_y_ed": 66 / 48, "circular_flag": True, "x_total": 65,
+            "y_total": 48, "test_flag": True, "partial": 0.6667}]
+    x = synth.randn_t(3, "ssc_x", (B, C, H, H)).to(dev)
+    coords = synth.randn_t(3, "ssc_c", (B, 3, H, H)).to(dev)
+    w_s = synth.randn_t(3, "ssc_ws", (256, C + 3, 3, 3)).to(dev)
+    w_7 = synth.randn_t(3, "ssc_w7", (256, C + 3, 7, 7)).to(dev)
+    w_sc = synth.randn_t(3, "ssc_wsc", (256, C, 1, 1), 0.05).to(dev)
+    b_sc = synth.randn_t(3, "ssc_bsc", (256,), 0.1).to(dev)
+    b_7 = synth.randn_t(3, "ssc_b7", (256,), 0.1).to(dev)
+    s_s = synth.randn_t(3, "ssc_ss", (B, C + 3), 0.3, 1.0).to(dev)
+    s_7 = synth.randn_t(3, "ssc_s7", (B, C + 3), 0.3, 1.0).to(dev)
+    sc_s, sc_7 = 1 / np.sqrt((C + 3) * 9), 1 / np.sqrt((C + 3) * 49)
+    d_s = SF.demod_coefficients(w_s, s_s, sc_s)
+    d_7 = SF.demod_coefficients(w_7, s_7, sc_7)
+    with torch.no_grad():
+        # reference composition, one position group at a time (the flat-concat table is per call)
+        want = []
+        for i, cp in enumerate(cps):
+            sl = slice(i * Bg, (i + 1) * Bg)
+            grid = grids.GRID_CACHE.get(H, H, cp, dev)
+            sph = SF.sphere_modconv_fused(x[sl], coords[sl], grid, w_s, s_s[sl].contiguous(), d_s[sl].contiguous(), sc_s,
+                                          act=(0.01, 1.0), precision=precision)
+            h = SF.conv_apply(x[sl].contiguous(), w_sc, SF.ConvGeom(1, 1), bias=b_sc, residual=sph, precision=precision)
+            inp = torch.cat([h, SF.encode_coords(coords[sl])], 1)
+            want.append(SF.conv_apply(inp, w_7, SF.ConvGeom(7, 7), in_mul=s_7[sl].contiguous(), out_mul=d_7[sl].contiguous(),
+                                      out_scale=sc_7, bias=b_7, act=(0.2, 2 ** 0.5), precision=precision))
+        want = torch.cat(want, 0)
+        # chain
+        xh, xp = SF.ss_input(x, precision)
+        grid = grids.GRID_CACHE.group_grid(H, H, cps, dev)
+        y_sc = SF.ss_shortcut(xp, B, H, H, w_sc, b_sc, precision)
+        a = SF.ss_sphere(xh, coords, grid, Bg, w_s, s_s, d_s, sc_s, (0.01, 1.0), y_sc, s_7[:, :C].contiguous(), precision)
+        got, _, hw = SF.ss_conv_k(a, coords, B, H, H, w_7, s_7, d_7, sc_7, b_7, (0.2, 2 ** 0.5), precision, True)
+        nh, pk, _ = SF.ss_conv_k(a, coords, B, H, H, w_7, s_7, d_7, sc_7, b_7, (0.2, 2 ** 0.5), precision, False)
+    assert hw == (11, 11) and got.shape == want.shape
+    err = K.rel_err(K.t2n(got), K.t2n(want))
+    print("structure chain ops, precision %d: %.2e" % (precision, err))
+    assert err < tol
+    # the two sink sets of the 7x7 GEMM carry the same values: NHWC fp32 and the packed hi/lo planes
+    assert torch.equal(nh.permute(0, 3, 1, 2), got)
+    back = SF.packed_to_float(pk, 0).view(B, 11, 11, 256).permute(0, 3, 1, 2)
+    assert K.rel_err(K.t2n(back), K.t2n(got)) < (2e-5 if precision == 1 else 1e-2)
