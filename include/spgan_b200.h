@@ -316,6 +316,21 @@ int spgan_upblur_pack(uint16_t* out, const float* pp, const float* kernel, const
  * part (slots, batch, rgb_n, plane) from spgan_conv_gemm_ex; bias (rgb_n) and skip (batch, rgb_n, plane) may be NULL. */
 int spgan_rgb_tail(float* out, const float* part, int slots, const float* bias, const float* skip, int64_t batch, int rgb_n,
                    int64_t plane, void* stream);
+/* ---- training-loop tails ------------------------------------------------------------------------------
+ * spgan_ema_multi: the EMA `accumulate` of utils.py:86-94 over ALL parameters in one launch: table is a DEVICE array of
+ *   nchunks records {float* dst; const float* src; int64_t n} (24 bytes each, n <= spgan_ema_chunk_elems()), one CTA per
+ *   record: dst[i] = fma(1 - decay, src[i], dst[i] * decay) — the arithmetic of torch's mul_(decay).add_(src, alpha=1-decay). */
+int spgan_ema_chunk_elems(void);
+int spgan_ema_multi(const void* table, int nchunks, float decay, void* stream);
+/* spgan_minibatch_stddev: models/stylegan2discriminator.py:205-212 fused with its torch.cat: h (B, C, HW) -> out (B, C+1, HW),
+ *   out[:, :C] = h, out[b, C, :] = mean over (c, p) of sqrt(var over the `group` samples {n*M + b % M} + eps), M = B / group
+ *   (stddev_feat = 1).  partial: fp32 scratch of M * 8 elements.  Forward only; the host composes the gradient. */
+int spgan_minibatch_stddev(float* out, float* partial, const float* h, int B, int C, int HW, int group, float eps, void* stream);
+
+/* Tuning switches (process-wide).  key 1: use of the CTA-pair (tcgen05 cta_group::2, 256 x 256 tiles over two SMs) variant of
+ * the GEMM kernel for Cout % 256 == 0: 0 = never, 1 = where its tiling fills the 148 SMs at least as well as the single-CTA
+ * tiling (default), 2 = wherever legal.  Results do not depend on it (same products, same K order). */
+int spgan_set_option(int key, int value);
 /* Number of tcgen05 GEMM launches since load (the bench's gpu_launches evidence for the tensor path). */
 int64_t spgan_gemm_launch_count(void);
 

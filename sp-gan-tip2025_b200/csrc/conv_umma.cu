@@ -209,7 +209,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++titer) {
       const int as = titer & 1;
       const uint32_t aphase = (uint32_t)(titer >> 1) & 1u;
-      gemm_epilogue_tile<kBlockN>(gp, sk, tile, warp, lane, tfull_bar(as), aphase, tmem_base + (uint32_t)(as * kBlockN));
+      gemm_epilogue_tile<kBlockN>(gp, sk, (tile / gp.n_tiles) * GEMM_BLOCK_M, tile % gp.n_tiles, warp, lane, tfull_bar(as), aphase, tmem_base + (uint32_t)(as * kBlockN));
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(as));
@@ -221,6 +221,256 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ CTA-pair GEMM kernel
+// cta_group::2: the two CTAs of a cluster (one TPC) compute ONE 256 x 256 tile.  CTA r holds rows [128 r, 128 r + 128) of the
+// A tile and rows [128 r, 128 r + 128) of the 256-row weight tile; the leader (rank 0) issues tcgen05.mma.cta_group::2 with
+// M = 256, which reads both CTAs' shared memory and writes both CTAs' TMEM.  Per CTA and K block that is 32 KiB of weights less
+// than the single-CTA kernel fetches from L2 (a third of the bf16x3 stage), so the ring holds 3 / 4 / 6 stages instead of
+// 2 / 3 / 4 and the operand traffic — which is what the power-limited part pays for — drops by a third.
+//   both CTAs   warp 0: TMA for its own A rows and its own half of the weight tile, completing on the LEADER's full barrier
+//   leader      warp 1: waits the full barrier (bytes of both CTAs), issues the MMAs, commits (multicast) to both CTAs' empty /
+//                       accumulator-full barriers
+//   both CTAs   warps 2..9: epilogue of their own 128 accumulator rows; accumulator-empty arrives go to the leader's barrier
+template <int kPasses>
+struct Gemm2Smem {
+  static constexpr int kBHalfBytes = 128 * GEMM_BLOCK_K * 2;  // this CTA's half of the 256-row weight tile
+  static constexpr int kAPlanes = kPasses >= 2 ? 2 : 1;
+  static constexpr int kBPlanes = kPasses == 3 ? 2 : 1;
+  static constexpr int kStageBytes = kAPlanes * A_TILE_BYTES + kBPlanes * kBHalfBytes;
+  static constexpr int kStages = (196608 / kStageBytes) < 6 ? (196608 / kStageBytes) : 6;
+  static constexpr int kTileBytes = kStageBytes * kStages;
+  static constexpr int kBarrierBytes = 256;
+  static constexpr int kTotal = kTileBytes + kBarrierBytes + 1024;
+};
+
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma2_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_im2col(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c, int w, int h, int n,
+                                                 int w_off, int h_off) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+      "[%2], {%7, %8};" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"((uint16_t)w_off), "h"((uint16_t)h_off)
+      : "memory");
+}
+__device__ __forceinline__ void tc2_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void tc2_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+template <int kPasses>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FWD_THREADS, 1)
+conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, const GemmParams gp,
+                  const GemmSinks sk) {
+  using S = Gemm2Smem<kPasses>;
+  constexpr int kStages = S::kStages;
+  constexpr int kBHalf = S::kBHalfBytes;
+  constexpr int kPairN = 256;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + S::kTileBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_rank();
+  const bool leader = rank == 0;
+  const int m_pairs = (gp.m_tiles + 1) / 2;
+  const int n_tiles = gp.Cout / kPairN;  // the host launches this kernel only for Cout % 256 == 0
+  const int num_tiles = m_pairs * n_tiles;
+  const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
+  const int kmain = gp.ntaps * gp.kblocks;
+  const int kiters = kmain + gp.k2blocks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), 1);   // leader: its own arrive.expect_tx; the bytes of both CTAs complete on it
+      mbar_init(empty_bar(s), 1);  // one multicast commit per phase
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 16);  // leader: 8 epilogue warps of each CTA
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer's barriers are initialised before anything signals them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer (both CTAs)
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+      if (gp.k2blocks > 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA2) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB2) : "memory");
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cid; tile < num_tiles; tile += ncl) {
+        const int m0 = (tile / n_tiles) * (2 * GEMM_BLOCK_M) + (int)rank * GEMM_BLOCK_M;
+        const int n0 = (tile % n_tiles) * kPairN + (int)rank * 128;  // this CTA's half of the weight rows
+        int b0 = 0, i0 = 0, j0 = 0;
+        if (gp.im2col) {
+          const int plane = gp.Hl * gp.Wl;
+          b0 = m0 / plane;
+          const int r = m0 - b0 * plane;
+          i0 = r / gp.Wl;
+          j0 = r - i0 * gp.Wl;
+        }
+        for (int it = 0; it < kiters; ++it) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = smem_base + stage * S::kStageBytes;
+          const uint32_t sb = sa + S::kAPlanes * A_TILE_BYTES;
+          const uint32_t fb = map_to_cta(full_bar(stage), 0);
+          if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * S::kStageBytes);
+          if (it < kmain) {
+            const int t = it / gp.kblocks, kb = it - t * gp.kblocks;
+            if (gp.im2col) {
+              const int img = b0 + gp.tap_img[t];
+              tma2_load_im2col(sa, &tmA, fb, kb * GEMM_BLOCK_K, j0, i0, img, gp.tap_ox[t], gp.tap_oy[t]);
+              if (S::kAPlanes == 2)
+                tma2_load_im2col(sa + A_TILE_BYTES, &tmA, fb, kb * GEMM_BLOCK_K, j0, i0, img + gp.img_lo, gp.tap_ox[t], gp.tap_oy[t]);
+            } else {
+              const int row = m0 + gp.tap_off[t];
+              tma2_load_3d(sa, &tmA, fb, kb * GEMM_BLOCK_K, row, 0);
+              if (S::kAPlanes == 2) tma2_load_3d(sa + A_TILE_BYTES, &tmA, fb, kb * GEMM_BLOCK_K, row, 1);
+            }
+            tma2_load_4d(sb, &tmB, fb, kb * GEMM_BLOCK_K, n0, t, 0);
+            if (S::kBPlanes == 2) tma2_load_4d(sb + kBHalf, &tmB, fb, kb * GEMM_BLOCK_K, n0, t, 1);
+          } else {
+            const int kb = it - kmain;
+            tma2_load_3d(sa, &tmA2, fb, kb * GEMM_BLOCK_K, m0, 0);
+            if (S::kAPlanes == 2) tma2_load_3d(sa + A_TILE_BYTES, &tmA2, fb, kb * GEMM_BLOCK_K, m0, 1);
+            tma2_load_4d(sb, &tmB2, fb, kb * GEMM_BLOCK_K, n0, 0, 0);
+            if (S::kBPlanes == 2) tma2_load_4d(sb + kBHalf, &tmB2, fb, kb * GEMM_BLOCK_K, n0, 0, 1);
+          }
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer (leader only)
+    if (leader && lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int titer = 0;
+      // M = 256 (both CTAs' 128 rows), N = 256
+      const uint32_t idesc = (1u << 4) | ((gp.a_f16 ? 0u : 1u) << 7) | ((gp.b_f16 ? 0u : 1u) << 10) | ((uint32_t)(kPairN >> 3) << 17) |
+                             ((uint32_t)(256 >> 4) << 24);
+      for (int tile = cid; tile < num_tiles; tile += ncl, ++titer) {
+        const int as = titer & 1;
+        const uint32_t aphase = (uint32_t)(titer >> 1) & 1u;
+        mbar_wait(tempty_bar(as), aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * kPairN);
+        for (int it = 0; it < kiters; ++it) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * S::kStageBytes;
+          const uint32_t a_hi = sa;
+          const uint32_t a_lo = sa + A_TILE_BYTES;
+          const uint32_t b_hi = sa + S::kAPlanes * A_TILE_BYTES;
+          const uint32_t b_lo = b_hi + kBHalf;
+          const int ksteps = (it < kmain && (it + 1) % gp.kblocks == 0) ? gp.last_ksteps : GEMM_BLOCK_K / GEMM_UMMA_K;
+#pragma unroll
+          for (int k = 0; k < GEMM_BLOCK_K / GEMM_UMMA_K; ++k) {
+            if (k >= ksteps) break;
+            const uint32_t koff = k * GEMM_UMMA_K * 2;
+            const uint64_t da_hi = umma_desc_sw128(a_hi + koff);
+            const uint64_t db_hi = umma_desc_sw128(b_hi + koff);
+            tc2_mma_f16(d_tmem, da_hi, db_hi, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            if (kPasses == 3) tc2_mma_f16(d_tmem, da_hi, umma_desc_sw128(b_lo + koff), idesc, 1u);
+            if (kPasses >= 2) tc2_mma_f16(d_tmem, umma_desc_sw128(a_lo + koff), db_hi, idesc, 1u);
+          }
+          tc2_commit(empty_bar(stage));  // both CTAs' stage `stage` is free once these MMAs have read it
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        tc2_commit(tfull_bar(as));  // both CTAs' accumulator halves are complete
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================================================================== epilogue (both CTAs, their own 128 rows)
+    int titer = 0;
+    for (int tile = cid; tile < num_tiles; tile += ncl, ++titer) {
+      const int as = titer & 1;
+      const uint32_t aphase = (uint32_t)(titer >> 1) & 1u;
+      const int m0 = (tile / n_tiles) * (2 * GEMM_BLOCK_M) + (int)rank * GEMM_BLOCK_M;
+      gemm_epilogue_tile<kPairN>(gp, sk, m0, tile % n_tiles, warp, lane, tfull_bar(as), aphase, tmem_base + (uint32_t)(as * kPairN));
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(tempty_bar(as));
+        else mbar_arrive_cluster(map_to_cta(tempty_bar(as), 0));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // neither CTA leaves (or frees TMEM) while the other may still signal it or read its shared memory
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -537,6 +787,32 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
   return 0;
 }
 
+template <int kPasses>
+int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmA2, const CUtensorMap& tmB2,
+                 const GemmParams& gp, const GemmSinks& sk, cudaStream_t st) {
+  using S = Gemm2Smem<kPasses>;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  SPGAN_CUDA(cudaGetDevice(&dev), "spgan_conv_gemm");
+  if (dev < 64 && !attr_set[dev]) {
+    SPGAN_CUDA(cudaFuncSetAttribute(conv_gemm2_kernel<kPasses>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal),
+               "spgan_conv_gemm (shared memory opt-in, CTA-pair kernel)");
+    attr_set[dev] = true;
+  }
+  const int ptiles = ((gp.m_tiles + 1) / 2) * (gp.Cout / 256);
+  const int clusters = ptiles < SPGAN_NUM_SMS / 2 ? ptiles : SPGAN_NUM_SMS / 2;
+  conv_gemm2_kernel<kPasses><<<2 * clusters, FWD_THREADS, S::kTotal, st>>>(tmA, tmB, tmA2, tmB2, gp, sk);
+  SPGAN_CHECK_LAUNCH("spgan_conv_gemm (CTA-pair kernel)");
+  launch_counter()->fetch_add(1);
+  return 0;
+}
+
+// 0 = never use the CTA-pair kernel, 1 = where its tiling fills the machine at least as well (default), 2 = wherever legal
+std::atomic<int>* pair_mode() {
+  static std::atomic<int> m{1};
+  return &m;
+}
+
 // N tile choice.  N = 128 costs ~25 % more time per FLOP than N = 256 (measured on the 55x55 layer: the A tile is fetched
 // twice as often and the chip is power-limited), so it is used only where N = 256 leaves the machine badly under-filled:
 // at most 1.5 waves of tiles and a wave efficiency gain of more than a third.
@@ -554,6 +830,7 @@ int pick_block_n(int64_t m_tiles, int cout) {
 // M extent and N tile of a pass: shared by the launcher and by spgan_conv_gemm_rgb_slots.
 struct GemmShape {
   bool im2col;
+  bool pair;  // cta_group::2 kernel: 256 x 256 tiles over CTA pairs
   int phases;
   int64_t rows_m;
   int m_tiles, block_n, n_tiles;
@@ -572,12 +849,33 @@ GemmShape gemm_shape(const SpganConvPass* p, int64_t a_rows) {
   g.m_tiles = (int)((g.rows_m + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M);
   g.block_n = pick_block_n(g.m_tiles, p->Cout);
   g.n_tiles = (p->Cout + g.block_n - 1) / g.block_n;
+  g.pair = false;
+  const int mode = pair_mode()->load();
+  if (mode != 0 && p->Cout % 256 == 0 && g.m_tiles >= 2) {
+    const int64_t ptiles = (int64_t)((g.m_tiles + 1) / 2) * (p->Cout / 256);
+    const int64_t tiles = (int64_t)g.m_tiles * g.n_tiles;
+    const int half = SPGAN_NUM_SMS / 2;
+    const double eff_pair = (double)ptiles / (double)(((ptiles + half - 1) / half) * half) * (2.0 * g.m_tiles / (2.0 * ((g.m_tiles + 1) / 2)));
+    const double eff_one = (double)tiles / (double)(((tiles + SPGAN_NUM_SMS - 1) / SPGAN_NUM_SMS) * SPGAN_NUM_SMS);
+    g.pair = mode == 2 || eff_pair >= 0.95 * eff_one;
+    if (g.pair) {
+      g.block_n = 256;
+      g.n_tiles = p->Cout / 256;
+    }
+  }
   return g;
 }
 
 }  // namespace
 
 extern "C" int64_t spgan_gemm_launch_count(void) { return (int64_t)launch_counter()->load(); }
+
+extern "C" int spgan_set_option(int key, int value) {
+  SPGAN_CHECK_ARG(key == 1, "spgan_set_option: unknown key %d", key);
+  SPGAN_CHECK_ARG(value >= 0 && value <= 2, "spgan_set_option: CTA-pair mode must be 0 (off), 1 (auto) or 2 (wherever legal), got %d", value);
+  pair_mode()->store(value);
+  return 0;
+}
 void spgan_internal_count_gemm_launch() { launch_counter()->fetch_add(1); }
 
 extern "C" int spgan_pack_act(uint16_t* out, const float* x, const float* in_mul, int B, int C, int H, int W, int Cp,
@@ -794,7 +1092,7 @@ extern "C" int spgan_conv_gemm_ex(const SpganConvPass* p, const SpganGemmIO* io,
   {
     cuuint64_t dims[4] = {(cuuint64_t)kp, (cuuint64_t)p->Cout, (cuuint64_t)p->ntaps, 2};
     cuuint64_t strides[3] = {(cuuint64_t)kp * 2, (cuuint64_t)p->Cout * kp * 2, (cuuint64_t)p->ntaps * p->Cout * kp * 2};
-    cuuint32_t box[4] = {GEMM_BLOCK_K, (cuuint32_t)block_n, 1, 1};
+    cuuint32_t box[4] = {GEMM_BLOCK_K, (cuuint32_t)(gs.pair ? 128 : block_n), 1, 1};
     if (int e = encode_bf16_map(&tmB, io->w_packed, 4, dims, strides, box, "spgan_conv_gemm (B map)")) return e;
   }
   // optional second K segment: Y += A2[p, :] * W2[o, :] over kp2 more columns (the few channels that do not fill a
@@ -817,11 +1115,16 @@ extern "C" int spgan_conv_gemm_ex(const SpganConvPass* p, const SpganGemmIO* io,
     {
       cuuint64_t dims[4] = {(cuuint64_t)io->kp2, (cuuint64_t)p->Cout, 1, 2};
       cuuint64_t strides[3] = {(cuuint64_t)io->kp2 * 2, (cuuint64_t)p->Cout * io->kp2 * 2, (cuuint64_t)p->Cout * io->kp2 * 2};
-      cuuint32_t box[4] = {GEMM_BLOCK_K, (cuuint32_t)block_n, 1, 1};
+      cuuint32_t box[4] = {GEMM_BLOCK_K, (cuuint32_t)(gs.pair ? 128 : block_n), 1, 1};
       if (int e = encode_bf16_map(&tmB2, io->w2_packed, 4, dims, strides, box, "spgan_conv_gemm (W2 map)")) return e;
     }
   }
   cudaStream_t st = (cudaStream_t)stream;
+  if (gs.pair) {
+    if (p->precision == 1) return launch_gemm2<3>(tmA, tmB, tmA2, tmB2, gp, sk, st);
+    if (p->precision == 3) return launch_gemm2<2>(tmA, tmB, tmA2, tmB2, gp, sk, st);
+    return launch_gemm2<1>(tmA, tmB, tmA2, tmB2, gp, sk, st);
+  }
   if (p->precision == 1)
     return block_n == 256 ? launch_gemm<3, 256>(tmA, tmB, tmA2, tmB2, gp, sk, st) : launch_gemm<3, 128>(tmA, tmB, tmA2, tmB2, gp, sk, st);
   if (p->precision == 3)

@@ -56,10 +56,11 @@ struct GemmSinks {
 // the few-tap passes (parity passes of the transposed conv, 1x1 shortcuts) was issue-latency bound at ~56 instructions
 // per column; here the per-column work is a multiply, a pointer bump and a store, the per-channel factors come in as
 // 128-bit loads, and the rare terms (noise, bias, activation, residual) are behind one warp-uniform branch.
+// m0: first M row of this CTA's 128-row accumulator; n_tile: index of the kBlockN-wide column tile.
 // tfull_bar / aphase: the accumulator-complete barrier of this TMEM stage and its parity; tmem_acc: column base of the stage.
 template <int kBlockN>
-__device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& gp, const GemmSinks& sk, int tile, int warp, int lane,
-                                                   uint32_t tfull_bar, uint32_t aphase, uint32_t tmem_acc) {
+__device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& gp, const GemmSinks& sk, int m0, int n_tile, int warp,
+                                                   int lane, uint32_t tfull_bar, uint32_t aphase, uint32_t tmem_acc) {
   float* __restrict__ y = sk.y;
   const float* __restrict__ out_mul = sk.out_mul;
   const float* __restrict__ noise = sk.noise;
@@ -80,8 +81,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& gp, const G
     // partial sums) goes through the general path below, which the host only selects when Cout is a multiple of 32.
     const bool nchw_only = y != nullptr && !gp.y_nhwc && sk.y_packed == nullptr && sk.rgb_w == nullptr && sk.residual_nhwc == nullptr;
     {
-      const int m0 = (tile / gp.n_tiles) * GEMM_BLOCK_M;
-      const int n0 = (tile % gp.n_tiles) * kBlockN;
+      const int n0 = n_tile * kBlockN;
       int n_eff = gp.Cout - n0;
       n_eff = n_eff > kBlockN ? kBlockN : ((n_eff + 15) & ~15);
       // decode this thread's lattice point
@@ -261,7 +261,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& gp, const G
       if (sk.rgb_w != nullptr && valid) {
         // one slot per (N tile, epilogue half): every (slot, b, channel, pixel) is written exactly once, and
         // spgan_rgb_tail sums the slots in a fixed order (deterministic, unlike atomics)
-        const int slot = (tile % gp.n_tiles) * 2 + half;
+        const int slot = n_tile * 2 + half;
         float* rp = sk.rgb_part + (((int64_t)slot * gp.B + b) * gp.rgb_n) * oplane + pix;
 #pragma unroll
         for (int j = 0; j < 3; ++j)

@@ -381,7 +381,7 @@ sphere_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const GemmParams gp,
       if (prev_tile >= 0) {
         const int pt = titer - 1;
         const int as = pt & 1;
-        gemm_epilogue_tile<kBlockN>(gp, sk, prev_tile, warp, lane, tfull_bar(as), (uint32_t)(pt >> 1) & 1u,
+        gemm_epilogue_tile<kBlockN>(gp, sk, (prev_tile / gp.n_tiles) * GEMM_BLOCK_M, prev_tile % gp.n_tiles, warp, lane, tfull_bar(as), (uint32_t)(pt >> 1) & 1u,
                                     tmem_base + (uint32_t)(as * kBlockN));
         tc_fence_before();
         __syncwarp();
@@ -392,7 +392,7 @@ sphere_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const GemmParams gp,
     if (prev_tile >= 0) {
       const int pt = titer - 1;
       const int as = pt & 1;
-      gemm_epilogue_tile<kBlockN>(gp, sk, prev_tile, warp, lane, tfull_bar(as), (uint32_t)(pt >> 1) & 1u,
+      gemm_epilogue_tile<kBlockN>(gp, sk, (prev_tile / gp.n_tiles) * GEMM_BLOCK_M, prev_tile % gp.n_tiles, warp, lane, tfull_bar(as), (uint32_t)(pt >> 1) & 1u,
                                   tmem_base + (uint32_t)(as * kBlockN));
       tc_fence_before();
       __syncwarp();

@@ -14,6 +14,8 @@
 #include "sphere_taps.cuh"
 #include "umma_common.cuh"
 
+#include <stdlib.h>
+
 namespace {
 
 template <int KITER, bool kF16>
@@ -155,6 +157,236 @@ __global__ void __launch_bounds__(256, 2) sphere_pack_seg_kernel(uint16_t* __res
   }
 }
 
+// ---- vectorised producer for the 256-feature configuration -----------------------------------------------------------------
+// sphere_pack_seg_kernel above is instruction-issue bound (~210 warp instructions per (pixel, tap): 32 scalar gathers, 32
+// address computations, scalar blends and 2-byte splits), 19 % of the HBM write roofline.  Here one warp handles one (pixel,
+// tap) with lane = one run of 8 consecutive K columns: when those 8 columns are 8 consecutive feature channels of one sample
+// (every lane of every group except the few at the reference's flat-concat sample / coordinate boundaries, decided from
+// chan_map once per CTA) the four corners are fetched with 2-3 aligned 128-bit loads each, blended with packed FFMA2, and
+// stored as one 16-byte hi and one 16-byte lo vector (512 contiguous bytes per warp and plane).  A CTA owns SP2_PX pixels of
+// ONE group, so the corner table of its 9 * SP2_PX (pixel, tap) pairs and the group's modulation row live in shared memory.
+constexpr int SP2_PX = 16;
+constexpr int SP2_TASKS = SP2_PX * 9;
+
+__device__ __forceinline__ unsigned long long pack_f2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f2(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+// 8 consecutive floats starting M elements (0..3) past the 16-byte aligned pointer p, as four packed pairs.
+template <int M>
+__device__ __forceinline__ void load8(const float* __restrict__ p, unsigned long long (&x)[4]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  float w[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, 0.f, 0.f, 0.f, 0.f};
+  if (M > 0) {
+    const float4 c = __ldg(reinterpret_cast<const float4*>(p) + 2);
+    w[8] = c.x;
+    w[9] = c.y;
+    w[10] = c.z;
+    w[11] = c.w;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) x[j] = pack_f2(w[2 * j + M], w[2 * j + 1 + M]);
+}
+
+// ((a*w_nw + b*w_ne) + c*w_sw) + d*w_se per channel, the association of the scalar kernels (their compiler-contracted form).
+template <int M>
+__device__ __forceinline__ void blend8(const float* __restrict__ base, const int (&o)[4], const float (&wt)[4],
+                                       unsigned long long (&acc)[4]) {
+  unsigned long long x0[4], x1[4], x2[4], x3[4];
+  load8<M>(base + o[0], x0);
+  load8<M>(base + o[1], x1);
+  load8<M>(base + o[2], x2);
+  load8<M>(base + o[3], x3);
+  const unsigned long long w0 = pack_f2(wt[0], wt[0]), w1 = pack_f2(wt[1], wt[1]), w2 = pack_f2(wt[2], wt[2]),
+                           w3 = pack_f2(wt[3], wt[3]);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) acc[j] = fma2(x3[j], w3, fma2(x2[j], w2, fma2(x1[j], w1, mul2(x0[j], w0))));
+}
+
+template <bool kF16>
+__device__ __forceinline__ void split_store8(uint16_t* __restrict__ hi_p, uint16_t* __restrict__ lo_p, const float (&v)[8]) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint16_t h0, l0, h1, l1;
+    split16<kF16>(v[2 * j], h0, l0);
+    split16<kF16>(v[2 * j + 1], h1, l1);
+    h[j] = pack2x16(h0, h1);
+    l[j] = pack2x16(l0, l1);
+  }
+  *reinterpret_cast<uint4*>(hi_p) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(lo_p) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+template <bool kF16>
+__global__ void __launch_bounds__(256) sphere_pack_v2_kernel(uint16_t* __restrict__ out, uint16_t* __restrict__ out2,
+                                                            const float* __restrict__ xh, const float* __restrict__ coords,
+                                                            const float* __restrict__ grid, const float* __restrict__ in_mul,
+                                                            const uint32_t* __restrict__ chan_map, int B, int nc, int H, int W,
+                                                            int grid_group, int cmap_ld, int kp2, int blocks_per_group) {
+  constexpr int C = 256;  // features per sample = main K columns per tap
+  __shared__ int s_off[4][SP2_TASKS];
+  __shared__ float s_wt[4][SP2_TASKS];
+  __shared__ __align__(16) float s_mul[C + 32];
+  __shared__ uint32_t s_map[C];
+  const int Ct = C + nc;
+  const int Cx = Ct - C;
+  const int HW = H * W;
+  const int g = blockIdx.x / blocks_per_group;
+  const int p0 = (blockIdx.x - g * blocks_per_group) * SP2_PX;
+  const int npx = min(SP2_PX, HW - p0);
+  const int ntask = npx * 9;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // ---- corner table and modulation row
+  for (int e = threadIdx.x; e < ntask; e += blockDim.x) {
+    const int r = e / 9, t = e - r * 9;
+    const int p = p0 + r;
+    const int py = p / W, px = p - py * W;
+    const TapCorners cn = tap_corners(grid, g / grid_group, H, W, py, px, t / 3, t - (t / 3) * 3);
+    s_off[0][e] = cn.o_nw;
+    s_off[1][e] = cn.o_ne;
+    s_off[2][e] = cn.o_sw;
+    s_off[3][e] = cn.o_se;
+    s_wt[0][e] = cn.w_nw;
+    s_wt[1][e] = cn.w_ne;
+    s_wt[2][e] = cn.w_sw;
+    s_wt[3][e] = cn.w_se;
+  }
+  for (int k = threadIdx.x; k < C + 32; k += blockDim.x) s_mul[k] = (k < Ct && in_mul) ? __ldg(in_mul + (int64_t)g * Ct + k) : (k < Ct ? 1.f : 0.f);
+  // ---- this lane's 8 columns: one run of consecutive feature channels of one sample?
+  const uint32_t* mrow = chan_map + (int64_t)g * cmap_ld;
+  const int k0 = 8 * lane;
+  uint32_t mw[8];
+  {
+    const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(mrow + k0));
+    const uint4 q1 = __ldg(reinterpret_cast<const uint4*>(mrow + k0) + 1);
+    mw[0] = q0.x; mw[1] = q0.y; mw[2] = q0.z; mw[3] = q0.w;
+    mw[4] = q1.x; mw[5] = q1.y; mw[6] = q1.z; mw[7] = q1.w;
+  }
+  bool run = (mw[0] >> 31) == 0;  // a feature (an all-ones padding entry has bit 31 set)
+#pragma unroll
+  for (int j = 1; j < 8; ++j) run = run && mw[j] == mw[0] + (uint32_t)j;  // same sample (bits 15..30), channel + j (no carry below)
+  const int cs0 = (int)(mw[0] & 0x7FFFu);
+  const int mis = cs0 & 3;
+  run = run && (cs0 - mis + (mis ? 12 : 8) <= C);
+  const float* fbase = xh + ((int64_t)((mw[0] >> 15) & 0xFFFFu) * HW) * C + (cs0 - mis);
+  const unsigned slowmask = __ballot_sync(0xffffffffu, !run);
+  if (warp == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s_map[k0 + j] = mw[j];
+  }
+  __syncthreads();
+  const int64_t plane_elems = (int64_t)B * HW * 9 * C;
+  for (int e = warp; e < ntask; e += 8) {
+    int o[4];
+    float wt[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      o[c] = s_off[c][e];
+      wt[c] = s_wt[c][e];
+    }
+    const int r = e / 9, t = e - r * 9;
+    uint16_t* dst = out + (((int64_t)g * HW + p0 + r) * 9 + t) * C;
+    if (run) {
+      int oc[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) oc[c] = o[c] * C;
+      unsigned long long acc[4];
+      switch (mis) {
+        case 0: blend8<0>(fbase, oc, wt, acc); break;
+        case 1: blend8<1>(fbase, oc, wt, acc); break;
+        case 2: blend8<2>(fbase, oc, wt, acc); break;
+        default: blend8<3>(fbase, oc, wt, acc); break;
+      }
+      const float4 m0 = *reinterpret_cast<const float4*>(&s_mul[k0]);
+      const float4 m1 = *reinterpret_cast<const float4*>(&s_mul[k0 + 4]);
+      acc[0] = mul2(acc[0], pack_f2(m0.x, m0.y));
+      acc[1] = mul2(acc[1], pack_f2(m0.z, m0.w));
+      acc[2] = mul2(acc[2], pack_f2(m1.x, m1.y));
+      acc[3] = mul2(acc[3], pack_f2(m1.z, m1.w));
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) unpack_f2(acc[j], v[2 * j], v[2 * j + 1]);
+      split_store8<kF16>(dst + k0, dst + k0 + plane_elems, v);
+    }
+    // boundary runs (sample change of the flat concat, coordinate planes, padding): one COLUMN per lane, 8 lanes per run,
+    // so that the one such run nearly every group has costs ~30 instructions per task instead of a serial 8-column loop
+    for (unsigned sm = slowmask; sm; sm &= sm - 1) {
+      const int k = 8 * (__ffs(sm) - 1) + (lane & 7);
+      if (lane < 8) {
+        const uint32_t m = s_map[k];
+        float val = 0.f;
+        if (m != 0xFFFFFFFFu) {
+          const uint32_t bs = (m >> 15) & 0xFFFFu, cs = m & 0x7FFFu;
+          const bool is_coord = (m >> 31) != 0;
+          const float* sp = is_coord ? coords + ((int64_t)bs * nc + cs) * HW : xh + (int64_t)bs * HW * C + cs;
+          const int st = is_coord ? 1 : C;
+          val = __ldg(sp + o[0] * st) * wt[0] + __ldg(sp + o[1] * st) * wt[1] + __ldg(sp + o[2] * st) * wt[2] +
+                __ldg(sp + o[3] * st) * wt[3];
+          if (is_coord) {
+            if (cs == 0) val = tanhf(val);
+            else if (cs == 1) val = cosf(val * 3.14159274101257324f);
+            else if (cs == 2) val = sinf(val * 3.14159274101257324f);
+          }
+          val *= s_mul[k];
+        }
+        uint16_t h, l;
+        split16<kF16>(val, h, l);
+        dst[k] = h;
+        dst[k + plane_elems] = l;
+      }
+    }
+  }
+  // ---- tail columns (channels C .. Ct-1 of the group, all taps) and their zero padding
+  if (Cx > 0) {
+    const int64_t plane2_elems = (int64_t)B * HW * kp2;
+    for (int idx = threadIdx.x; idx < npx * kp2; idx += blockDim.x) {
+      const int r = idx / kp2, col = idx - r * kp2;
+      uint16_t h = 0, l = 0;
+      if (col < 9 * Cx) {
+        const int t = col / Cx, j = col - t * Cx;
+        const int e = r * 9 + t;
+        const uint32_t m = __ldg(mrow + C + j);
+        float val = 0.f;
+        if (m != 0xFFFFFFFFu) {
+          const uint32_t bs = (m >> 15) & 0xFFFFu, cs = m & 0x7FFFu;
+          const bool is_coord = (m >> 31) != 0;
+          const float* sp = is_coord ? coords + ((int64_t)bs * nc + cs) * HW : xh + (int64_t)bs * HW * C + cs;
+          const int st = is_coord ? 1 : C;
+          val = __ldg(sp + s_off[0][e] * st) * s_wt[0][e] + __ldg(sp + s_off[1][e] * st) * s_wt[1][e] +
+                __ldg(sp + s_off[2][e] * st) * s_wt[2][e] + __ldg(sp + s_off[3][e] * st) * s_wt[3][e];
+          if (is_coord) {
+            if (cs == 0) val = tanhf(val);
+            else if (cs == 1) val = cosf(val * 3.14159274101257324f);
+            else if (cs == 2) val = sinf(val * 3.14159274101257324f);
+          }
+          val *= s_mul[C + j];
+        }
+        split16<kF16>(val, h, l);
+      }
+      const int64_t off = ((int64_t)g * HW + p0 + r) * kp2 + col;
+      out2[off] = h;
+      out2[plane2_elems + off] = l;
+    }
+  }
+}
+
 // One thread per (output row, column of the tail operand).
 template <bool kF16>
 __global__ void __launch_bounds__(256) coord_taps_pack_kernel(uint16_t* __restrict__ out2, const float* __restrict__ coords,
@@ -207,6 +439,18 @@ extern "C" int spgan_sphere_pack_seg(uint16_t* out, uint16_t* out2, const float*
   SPGAN_CHECK_ARG((((uintptr_t)grid) & 7) == 0 && (((uintptr_t)chan_map) & 7) == 0,
                   "spgan_sphere_pack_seg: grid and chan_map must be 8-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
+  static const bool force_v1 = getenv("SPGAN_SPHERE_PACK_V1") != nullptr;  // diagnostics: A/B against the scalar producer
+  if (!force_v1 && C == 256 && Cm == 256 && cmap_ld % 4 == 0 && (((uintptr_t)chan_map) & 15) == 0 && (((uintptr_t)x_nhwc) & 15) == 0 &&
+      (((uintptr_t)out) & 15) == 0) {
+    const int bpg = (H * W + SP2_PX - 1) / SP2_PX;
+    SPGAN_CHECK_ARG((int64_t)B * bpg < (1LL << 31), "spgan_sphere_pack_seg: grid too large");
+    if (fmt)
+      sphere_pack_v2_kernel<true><<<B * bpg, 256, 0, st>>>(out, out2, x_nhwc, coords, grid, in_mul, chan_map, B, nc, H, W, grid_group, cmap_ld, kp2, bpg);
+    else
+      sphere_pack_v2_kernel<false><<<B * bpg, 256, 0, st>>>(out, out2, x_nhwc, coords, grid, in_mul, chan_map, B, nc, H, W, grid_group, cmap_ld, kp2, bpg);
+    SPGAN_CHECK_LAUNCH("spgan_sphere_pack_seg");
+    return 0;
+  }
   const int nblk = grid_for((int64_t)B * H * W, 8, 2, 16);
 #define SPGAN_SEG(KI)                                                                                                          \
   do {                                                                                                                         \

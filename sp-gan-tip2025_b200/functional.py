@@ -45,6 +45,13 @@ def get_precision():
     return _PRECISION
 
 
+def set_gemm_pair_mode(mode):
+    """0 = never use the CTA-pair (cta_group::2) GEMM kernel, 1 = where its tiling fills the SMs as well (default), 2 = wherever
+    legal (Cout % 256 == 0).  Results are bit-identical either way (same products, same K order)."""
+    if lib.load().spgan_set_option(1, int(mode)) != 0:  # not a kernel launch: bypass lib.call's launch counter
+        raise RuntimeError("spgan_set_option failed: " + lib.last_error())
+
+
 _PROFILE = None  # list of (start event, end event, algorithmic flops) while bench.py profiles the tcgen05 launches
 
 

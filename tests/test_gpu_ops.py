@@ -694,3 +694,40 @@ def test_structure_chain_ops_vs_padded_path(precision, tol):
     assert torch.equal(nh.permute(0, 3, 1, 2), got)
     back = SF.packed_to_float(pk, 0).view(B, 11, 11, 256).permute(0, 3, 1, 2)
     assert K.rel_err(K.t2n(back), K.t2n(got)) < (2e-5 if precision == 1 else 1e-2)
+
+
+@pytest.mark.parametrize("precision", [1, 2, 3])
+@pytest.mark.parametrize("shape", [(3, 128, 256, 23, 3), (2, 64, 512, 31, 3), (5, 256, 256, 17, 7), (2, 96, 512, 19, 1)])
+def test_gemm_cta_pair_kernel_bit_identical(precision, shape):
+    """The cta_group::2 kernel (256 x 256 tiles over two SMs, weight tile split between the CTAs, multicast commits) issues the
+    same products in the same K order as the single-CTA kernel: bit-identical outputs, im2col and flat A loads, odd numbers of
+    M tiles (a half-empty last pair), epilogue terms included."""
+    import spgan_b200.functional as SF  # noqa: F811
+    dev = torch.device("cuda:0")
+    B, C, O, H, k = shape
+    x = synth.randn_t(5, "pair_x", (B, C, H, H)).to(dev)
+    w = synth.randn_t(5, "pair_w", (O, C, k, k)).to(dev)
+    s = synth.randn_t(5, "pair_s", (B, C), 0.3, 1.0).to(dev)
+    if precision == 3:
+        x = x.clamp(-8, 8)
+    oh = H - k + 1
+    nz = synth.randn_t(5, "pair_nz", (B, 1, oh, oh)).to(dev)
+    nw = torch.tensor([0.3], device=dev)
+    bias = synth.randn_t(5, "pair_b", (O,), 0.1).to(dev)
+    d = SF.demod_coefficients(w, s, 0.05)
+    outs = []
+    try:
+        for mode in (0, 2):
+            SF.set_gemm_pair_mode(mode)
+            before = SF.lib.load().spgan_gemm_launch_count()
+            with torch.no_grad():
+                outs.append(SF.conv_apply(x, w, SF.ConvGeom(k, k), in_mul=s, out_mul=d, out_scale=0.05, noise=nz, noise_w=nw, bias=bias,
+                                          act=(0.2, 2 ** 0.5), precision=precision))
+            assert SF.lib.load().spgan_gemm_launch_count() == before + 1
+    finally:
+        SF.set_gemm_pair_mode(1)
+    assert torch.isfinite(outs[0]).all()
+    assert torch.equal(outs[0], outs[1])
+    want = F.conv2d((x * s[:, :, None, None]).double(), w.double()) * 0.05 * d.double()[:, :, None, None]
+    want = F.leaky_relu(want + 0.3 * nz.double() + bias.double().view(1, -1, 1, 1), 0.2) * 2 ** 0.5
+    assert K.rel_err(K.t2n(outs[1]), K.t2n(want)) < TOL[precision]

@@ -16,6 +16,19 @@ WANT = [
     ("smsp__inst_executed.sum", "warp instructions"),
     ("sm__cycles_elapsed.max", "SM cycles"),
     ("smsp__cycles_active.avg", "SMSP active cycles"),
+    ("sm__inst_executed.avg.per_cycle_active", "IPC (active)"),
+    ("sm__inst_issued.avg.pct_of_peak_sustained_active", "issue slots busy %"),
+    ("l1tex__t_sector_hit_rate.pct", "L1 hit rate %"),
+    ("lts__t_sector_hit_rate.pct", "L2 hit rate %"),
+    ("smsp__average_warp_latency_issue_stalled_long_scoreboard_per_warp_active.pct", "stall long scoreboard %"),
+    ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "stall long_scoreboard / issue"),
+    ("smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "stall short_scoreboard / issue"),
+    ("smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio", "stall lg_throttle / issue"),
+    ("smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio", "stall mio_throttle / issue"),
+    ("smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "stall math_pipe / issue"),
+    ("smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "stall wait / issue"),
+    ("smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "stall barrier / issue"),
+    ("smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio", "stall not_selected / issue"),
     ("launch__registers_per_thread", "registers/thread"),
     ("launch__grid_size", "grid"),
     ("launch__block_size", "block"),
