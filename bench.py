@@ -35,6 +35,7 @@ def parse():
     ap.add_argument("--precision", type=int, default=1, choices=[0, 1, 2, 3])
     ap.add_argument("--streams", type=int, default=2, help="concurrent lattice-position branches of the panorama graph")
     ap.add_argument("--group", type=int, default=2, help="lattice positions per generator call (panorama.PanoramaEngine group)")
+    ap.add_argument("--pair-mode", type=int, default=1, choices=[0, 1, 2], help="CTA-pair GEMM kernel: 0 never, 1 auto, 2 wherever legal")
     ap.add_argument("--ts-precision", default="", help="8 comma-separated per-layer modes for the texture chain")
     ap.add_argument("--fast-tail", action="store_true", help="also measure the fp16x2 tail policy (reported beside the headline)")
     ap.add_argument("--no-strict", action="store_true", help="do not also measure bf16x3-everywhere (reported beside the headline)")
@@ -316,6 +317,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     SF.set_precision(args.precision)
+    SF.set_gemm_pair_mode(args.pair_mode)
 
     B = args.batch
     sharded = args.workload == "pano768"

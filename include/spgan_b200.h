@@ -208,10 +208,13 @@ int spgan_sphere_pack(uint16_t* out, const float* x_nhwc, const float* coords, c
  *   dense tail operand out2 [2][B*H*W][kp2], k2 = tap*Cx + j (columns 9*Cx..kp2-1 zero), which spgan_conv_gemm_ex consumes as
  *   its second K segment.  grid is (B / grid_group, 3H, 3W, 2): samples [i*grid_group, (i+1)*grid_group) share grid i, so
  *   several lattice positions of a panorama (close_loop_infinite_generation.py:185-261) run as one batch; chan_map rows are
- *   cmap_ld entries apart. */
+ *   cmap_ld entries apart.  scratch: fp32 workspace of spgan_sphere_pack_seg_scratch(B, C, H, W) elements (may be NULL: slower
+ *   scalar producer) that receives the flat-concat channels of every group as 16-byte aligned rows, so that the gather itself
+ *   runs on 128-bit loads. */
+int64_t spgan_sphere_pack_seg_scratch(int B, int C, int H, int W);
 int spgan_sphere_pack_seg(uint16_t* out, uint16_t* out2, const float* x_nhwc, const float* coords, const float* grid,
                           const float* in_mul, const uint32_t* chan_map, int B, int C, int H, int W, int grid_group, int Cm,
-                          int cmap_ld, int kp2, int fmt, void* stream);
+                          int cmap_ld, int kp2, int fmt, float* scratch, void* stream);
 /* spgan_coord_taps_pack: the tail operand of an unpadded kh x kw conv whose last nc input channels are the encoded coordinate
  *   planes (ConditionalBlock, models/spgan/spgan.py:100-101: torch.cat([x, encode(coords)]) -> 7x7 StyledConv):
  *   out2 [2][B*My*Mx][kp2], row (b, y, x) of the My x Mx = (H-kh+1) x (W-kw+1) outputs, k2 = tap*nc + j,

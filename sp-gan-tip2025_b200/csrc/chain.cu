@@ -35,85 +35,162 @@ __device__ __forceinline__ void fma4(float4& a, float w, const float4& v) {
   a.w += w * v.w;
 }
 
-// Thread = 4 channels x 2 adjacent output columns, sliding down a band of UP_ROWS output rows with a 3-row window in
-// registers: 4 float4 loads per 2 outputs (the L1 serves the column overlap between neighbouring threads), all accesses
-// 512 B contiguous per warp.
+// (v0, v1) -> packed 16-bit hi pair and lo pair (lo = round(v - hi)), two values per conversion instruction.
 template <bool kF16>
-__global__ void __launch_bounds__(UP_THREADS) upblur_pack_kernel(uint16_t* __restrict__ out, const float* __restrict__ pp,
-                                                                const float* __restrict__ kernel,
-                                                                const float* __restrict__ noise,
-                                                                const float* __restrict__ noise_w,
-                                                                const float* __restrict__ bias,
-                                                                const float* __restrict__ next_mul, UpPackParams P) {
+__device__ __forceinline__ void split_pair16(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+  if (kF16) {
+    v0 = fminf(fmaxf(v0, -65504.f), 65504.f);
+    v1 = fminf(fmaxf(v1, -65504.f), 65504.f);
+    const __half2 h = __floats2half2_rn(v0, v1);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+  } else {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+    const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h);
+    const float h0 = __uint_as_float(hb << 16), h1 = __uint_as_float(hb & 0xFFFF0000u);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(v0 - h0, v1 - h1);
+    hi = hb;
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+  }
+}
+
+__device__ __forceinline__ unsigned long long pk2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void fma2_acc(unsigned long long& acc, unsigned long long w, float a, float b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(pk2(a, b)), "l"(w));
+}
+
+// Thread = 4 channels x 2 adjacent output columns, sliding down a band of UP_ROWS output rows with a FOUR-row window in
+// registers: the row needed by the NEXT output row is requested before the current one is computed (the three-row version
+// had 32 KB in flight per SM at 16 resident warps and sat at ~45 % of the HBM roofline, ncu long-scoreboard 3.4 per issue);
+// 4 float4 loads per 2 outputs (the L1 serves the column overlap between neighbouring threads), all accesses 512 B
+// contiguous per warp; the 3x3 FIR runs on packed FFMA2.
+template <bool kF16>
+__global__ void __launch_bounds__(UP_THREADS, 2) upblur_pack_kernel(uint16_t* __restrict__ out, const float* __restrict__ pp,
+                                                                   const float* __restrict__ kernel,
+                                                                   const float* __restrict__ noise,
+                                                                   const float* __restrict__ noise_w,
+                                                                   const float* __restrict__ bias,
+                                                                   const float* __restrict__ next_mul, UpPackParams P) {
   const int c4 = threadIdx.x % P.C4;
   const int sub = threadIdx.x / P.C4;
   const int ox0 = (blockIdx.x * P.nsub + sub) * 2;
   const int oy0 = blockIdx.y * UP_ROWS;
   const int b = blockIdx.z;
   if (sub >= P.nsub || ox0 >= P.ow) return;
-  float kf[9];
+  unsigned long long kf[9];
 #pragma unroll
-  for (int i = 0; i < 9; ++i) kf[i] = __ldg(kernel + (2 - i / 3) * 3 + (2 - i % 3));  // upfirdn2d flips the kernel
+  for (int i = 0; i < 9; ++i) {
+    const float k = __ldg(kernel + (2 - i / 3) * 3 + (2 - i % 3));  // upfirdn2d flips the kernel
+    kf[i] = pk2(k, k);
+  }
   const int c = 4 * c4;
   const float4 bv = bias ? ld4(bias + c) : make_float4(0.f, 0.f, 0.f, 0.f);
   const float4 mv = next_mul ? ld4(next_mul + (int64_t)b * P.C + c) : make_float4(1.f, 1.f, 1.f, 1.f);
   const float nw = noise ? __ldg(noise_w) : 0.f;
   const int64_t Q = (int64_t)P.Hq * P.Wq;
   const float* base = pp + (int64_t)b * 4 * Q * P.C + c;
-  // interleaved pixel (Y, X) lives in plane (Y & 1) * 2 + (X & 1) at (Y >> 1, X >> 1)
-  auto load_row = [&](int Y, float4* r) {
+  // interleaved pixel (Y, X) lives in plane (Y & 1) * 2 + (X & 1) at (Y >> 1, X >> 1).  All addresses are running pointers:
+  // the column part is fixed per thread, even rows walk planes 0/1 and odd rows planes 2/3 with one pointer each (the band
+  // starts on an even row), outputs and noise advance by one image row per step.  (Recomputing the 64-bit addresses per row
+  // cost ~60 of the ~280 instructions per step and made the kernel issue-bound at 60 % of the HBM roofline.)
+  int col_off[4];
+  bool col_ok[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int X = ox0 + j;
-      if (Y < P.zh && X < P.zw)
-        r[j] = ld4(base + ((int64_t)((Y & 1) * 2 + (X & 1)) * Q + (int64_t)(Y >> 1) * P.Wq + (X >> 1)) * P.C);
-      else
-        r[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+  for (int j = 0; j < 4; ++j) {
+    const int X = ox0 + j;
+    col_ok[j] = X < P.zw;
+    col_off[j] = (int)(((int64_t)(X & 1) * Q + (X >> 1)) * P.C);  // < 2 * Q * C elements: the host checks it fits 31 bits
+  }
+  const int64_t rstep = (int64_t)P.Wq * P.C;
+  const float* pe = base + (int64_t)(oy0 >> 1) * rstep;  // next even row to load
+  const float* po = pe + 2 * Q * P.C;                    // next odd row to load
+  int Yn = oy0;                                          // index of the next row to load
+  auto load_next = [&](bool odd, float4* r) {
+    const float* rp = odd ? po : pe;
+    const bool row_ok = Yn < P.zh;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) r[j] = (row_ok && col_ok[j]) ? ld4(rp + col_off[j]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (odd) po += rstep;
+    else pe += rstep;
+    ++Yn;
   };
-  float4 win[3][4];
-  load_row(oy0, win[0]);
-  load_row(oy0 + 1, win[1]);
+  float4 win[4][4];
+  load_next(false, win[0]);
+  load_next(true, win[1]);
+  load_next(false, win[2]);
   const int rows = min(UP_ROWS, P.oh - oy0);
   const bool two = ox0 + 1 < P.ow;
-  uint16_t* out_lo = out + P.pk_rows * (int64_t)P.Cp;
-  // one output row: (w0, w1, w2) are the window rows oy, oy + 1, oy + 2; the three call sites below rotate the roles so
-  // that the window stays in registers (compile-time indices)
-  auto step = [&](int r, float4* w0, float4* w1, float4* w2) {
-    const int oy = oy0 + r;
-    load_row(oy + 2, w2);
-    float4 acc[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+  const int64_t prow0 = ((int64_t)b * P.oh + oy0) * P.ow + ox0;
+  const float* nzp = noise ? noise + prow0 : nullptr;
+  uint16_t* op = out + prow0 * P.Cp + c;
+  uint16_t* op_lo = op + P.pk_rows * (int64_t)P.Cp;
+  const int64_t ostep = (int64_t)P.ow * P.Cp;
+  // epilogue constants as packed pairs: bias, alpha, scale * next-layer modulation.  leaky-ReLU(v) = max(v, alpha v) for
+  // alpha <= 1 (min otherwise): a multiply and a min/max instead of compare + select + multiply
+  const unsigned long long b01 = pk2(bv.x, bv.y), b23 = pk2(bv.z, bv.w);
+  const unsigned long long al2 = pk2(P.alpha, P.alpha);
+  const unsigned long long sm01 = pk2(P.scale * mv.x, P.scale * mv.y), sm23 = pk2(P.scale * mv.z, P.scale * mv.w);
+  const bool use_max = P.alpha <= 1.f;
+  auto act_pair = [&](unsigned long long v2, unsigned long long bias2, unsigned long long nz2, unsigned long long sm2, uint32_t& h,
+                      uint32_t& l) {
+    unsigned long long t;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(t) : "l"(v2), "l"(bias2));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(t) : "l"(t), "l"(nz2));
+    unsigned long long ta;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(ta) : "l"(t), "l"(al2));
+    float x0, x1, y0, y1;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(t));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(y0), "=f"(y1) : "l"(ta));
+    x0 = use_max ? fmaxf(x0, y0) : fminf(x0, y0);
+    x1 = use_max ? fmaxf(x1, y1) : fminf(x1, y1);
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(x0, x1)), "l"(sm2));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(r));
+    split_pair16<kF16>(x0, x1, h, l);
+  };
+  // one output row: (w0, w1, w2) are the window rows oy, oy + 1, oy + 2, wn receives row oy + 3 (odd for even r: the band
+  // starts on an even row); the four call sites below rotate the roles so that the window stays in registers
+  auto step = [&](int r, bool next_odd, float4* w0, float4* w1, float4* w2, float4* wn) {
+    if (r + 1 < rows) load_next(next_odd, wn);
+    unsigned long long acc[2][2] = {{0ull, 0ull}, {0ull, 0ull}};  // [column][channel pair], +0.0f bit patterns
 #pragma unroll
     for (int kx = 0; kx < 3; ++kx) {
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        fma4(acc[j], kf[kx], w0[kx + j]);
-        fma4(acc[j], kf[3 + kx], w1[kx + j]);
-        fma4(acc[j], kf[6 + kx], w2[kx + j]);
+        fma2_acc(acc[j][0], kf[kx], w0[kx + j].x, w0[kx + j].y);
+        fma2_acc(acc[j][1], kf[kx], w0[kx + j].z, w0[kx + j].w);
+        fma2_acc(acc[j][0], kf[3 + kx], w1[kx + j].x, w1[kx + j].y);
+        fma2_acc(acc[j][1], kf[3 + kx], w1[kx + j].z, w1[kx + j].w);
+        fma2_acc(acc[j][0], kf[6 + kx], w2[kx + j].x, w2[kx + j].y);
+        fma2_acc(acc[j][1], kf[6 + kx], w2[kx + j].z, w2[kx + j].w);
       }
     }
-    const int64_t prow = ((int64_t)b * P.oh + oy) * P.ow + ox0;
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       if (j == 1 && !two) break;
-      const float nz = noise ? nw * __ldg(noise + prow + j) : 0.f;
-      float v[4] = {acc[j].x + bv.x + nz, acc[j].y + bv.y + nz, acc[j].z + bv.z + nz, acc[j].w + bv.w + nz};
-      const float m[4] = {mv.x, mv.y, mv.z, mv.w};
-      uint16_t h[4], l[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        v[k] = (v[k] > 0.f ? v[k] : v[k] * P.alpha) * P.scale;
-        split16<kF16>(v[k] * m[k], h[k], l[k]);
-      }
-      const int64_t off = (prow + j) * P.Cp + c;
-      *reinterpret_cast<uint2*>(out + off) = make_uint2(pack2x16(h[0], h[1]), pack2x16(h[2], h[3]));
-      *reinterpret_cast<uint2*>(out_lo + off) = make_uint2(pack2x16(l[0], l[1]), pack2x16(l[2], l[3]));
+      const float nz = nzp ? nw * __ldg(nzp + j) : 0.f;
+      const unsigned long long nz2 = pk2(nz, nz);
+      uint32_t h0, l0, h1, l1;
+      act_pair(acc[j][0], b01, nz2, sm01, h0, l0);
+      act_pair(acc[j][1], b23, nz2, sm23, h1, l1);
+      *reinterpret_cast<uint2*>(op + (int64_t)j * P.Cp) = make_uint2(h0, h1);
+      *reinterpret_cast<uint2*>(op_lo + (int64_t)j * P.Cp) = make_uint2(l0, l1);
     }
+    if (nzp) nzp += P.ow;
+    op += ostep;
+    op_lo += ostep;
   };
-  for (int r = 0; r < rows; r += 3) {
-    step(r, win[0], win[1], win[2]);
-    if (r + 1 < rows) step(r + 1, win[1], win[2], win[0]);
-    if (r + 2 < rows) step(r + 2, win[2], win[0], win[1]);
+  for (int r = 0; r < rows; r += 4) {
+    step(r, true, win[0], win[1], win[2], win[3]);
+    if (r + 1 < rows) step(r + 1, false, win[1], win[2], win[3], win[0]);
+    if (r + 2 < rows) step(r + 2, true, win[2], win[3], win[0], win[1]);
+    if (r + 3 < rows) step(r + 3, false, win[3], win[0], win[1], win[2]);
   }
 }
 
@@ -149,6 +226,7 @@ extern "C" int spgan_upblur_pack(uint16_t* out, const float* pp, const float* ke
   SPGAN_CHECK_ARG(out_rows >= batch * oh * ow, "spgan_upblur_pack: packed operand has too few rows");
   SPGAN_CHECK_ARG(batch <= 65535, "spgan_upblur_pack: batch %lld > 65535", (long long)batch);
   SPGAN_CHECK_ARG(((((uintptr_t)out) | ((uintptr_t)pp)) & 15) == 0, "spgan_upblur_pack: pointers must be 16-byte aligned");
+  SPGAN_CHECK_ARG((int64_t)2 * Hq * Wq * channels < (1LL << 31), "spgan_upblur_pack: polyphase planes too large for 32-bit column offsets");
   UpPackParams P;
   P.C = channels;
   P.C4 = channels / 4;

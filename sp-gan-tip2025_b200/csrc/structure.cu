@@ -158,15 +158,22 @@ __global__ void __launch_bounds__(256, 2) sphere_pack_seg_kernel(uint16_t* __res
 }
 
 // ---- vectorised producer for the 256-feature configuration -----------------------------------------------------------------
-// sphere_pack_seg_kernel above is instruction-issue bound (~210 warp instructions per (pixel, tap): 32 scalar gathers, 32
-// address computations, scalar blends and 2-byte splits), 19 % of the HBM write roofline.  Here one warp handles one (pixel,
-// tap) with lane = one run of 8 consecutive K columns: when those 8 columns are 8 consecutive feature channels of one sample
-// (every lane of every group except the few at the reference's flat-concat sample / coordinate boundaries, decided from
-// chan_map once per CTA) the four corners are fetched with 2-3 aligned 128-bit loads each, blended with packed FFMA2, and
-// stored as one 16-byte hi and one 16-byte lo vector (512 contiguous bytes per warp and plane).  A CTA owns SP2_PX pixels of
-// ONE group, so the corner table of its 9 * SP2_PX (pixel, tap) pairs and the group's modulation row live in shared memory.
-constexpr int SP2_PX = 16;
-constexpr int SP2_TASKS = SP2_PX * 9;
+// sphere_pack_seg_kernel above is instruction-issue bound (ncu: ~210 warp instructions per (pixel, tap), IPC 1.9, 19 % of the
+// HBM write roofline): 32 scalar gathers with 32 address computations, scalar blends and 2-byte splits per lane and tap.  The
+// reference's flat (1,B*C)++(1,B*3) concatenation makes group g read channels [259 g, 259 g + 259) of the flat list, so its K
+// columns are neither aligned to 16 bytes in the NHWC source nor confined to one sample; a first vectorised version that
+// realigned in registers (3 loads per corner, per-lane boundary paths) was SLOWER (347 instructions per task).  Hence two steps:
+//   concat_repack : xg[g][pixel][k] = the k-th flat-concat channel of group g, raw (features and raw coordinate planes), rows
+//                   of SPV_LD floats (16-byte aligned) — the reference's concat made explicit once per layer (2 x 80 MB at
+//                   35 x 35, B = 64, against 742 MB of operand written);
+//   sphere_pack_v3: one warp per (pixel, tap), lane = 8 consecutive K columns: two aligned 128-bit loads per corner, packed
+//                   FFMA2 blend, coordinate encoding only in the lanes of the one group per call that holds coordinate
+//                   planes, packed bf16x2 / f16x2 conversions, one 16-byte store per plane.  A CTA owns SP_PX pixels of ONE
+//                   group: the corner table of its 9 * SP_PX (pixel, tap) pairs and the group's modulation row sit in smem.
+constexpr int SP_PX = 16;
+constexpr int SP_TASKS = SP_PX * 9;
+constexpr int SPV_C = 256;   // main K columns per tap
+constexpr int SPV_LD = 264;  // floats per (group, pixel) row of the repacked source: 259 flat-concat channels + padding
 
 __device__ __forceinline__ unsigned long long pack_f2(float lo, float hi) {
   unsigned long long r;
@@ -187,111 +194,107 @@ __device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigne
   return d;
 }
 
-// 8 consecutive floats starting M elements (0..3) past the 16-byte aligned pointer p, as four packed pairs.
-template <int M>
-__device__ __forceinline__ void load8(const float* __restrict__ p, unsigned long long (&x)[4]) {
-  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
-  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
-  float w[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, 0.f, 0.f, 0.f, 0.f};
-  if (M > 0) {
-    const float4 c = __ldg(reinterpret_cast<const float4*>(p) + 2);
-    w[8] = c.x;
-    w[9] = c.y;
-    w[10] = c.z;
-    w[11] = c.w;
-  }
-#pragma unroll
-  for (int j = 0; j < 4; ++j) x[j] = pack_f2(w[2 * j + M], w[2 * j + 1 + M]);
-}
-
-// ((a*w_nw + b*w_ne) + c*w_sw) + d*w_se per channel, the association of the scalar kernels (their compiler-contracted form).
-template <int M>
-__device__ __forceinline__ void blend8(const float* __restrict__ base, const int (&o)[4], const float (&wt)[4],
-                                       unsigned long long (&acc)[4]) {
-  unsigned long long x0[4], x1[4], x2[4], x3[4];
-  load8<M>(base + o[0], x0);
-  load8<M>(base + o[1], x1);
-  load8<M>(base + o[2], x2);
-  load8<M>(base + o[3], x3);
-  const unsigned long long w0 = pack_f2(wt[0], wt[0]), w1 = pack_f2(wt[1], wt[1]), w2 = pack_f2(wt[2], wt[2]),
-                           w3 = pack_f2(wt[3], wt[3]);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) acc[j] = fma2(x3[j], w3, fma2(x2[j], w2, fma2(x1[j], w1, mul2(x0[j], w0))));
-}
-
+// (v0, v1) -> packed 16-bit hi pair and lo pair (lo = round(v - hi)), two values per conversion instruction.
 template <bool kF16>
-__device__ __forceinline__ void split_store8(uint16_t* __restrict__ hi_p, uint16_t* __restrict__ lo_p, const float (&v)[8]) {
-  uint32_t h[4], l[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    uint16_t h0, l0, h1, l1;
-    split16<kF16>(v[2 * j], h0, l0);
-    split16<kF16>(v[2 * j + 1], h1, l1);
-    h[j] = pack2x16(h0, h1);
-    l[j] = pack2x16(l0, l1);
+__device__ __forceinline__ void split_pair(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+  if (kF16) {
+    v0 = fminf(fmaxf(v0, -65504.f), 65504.f);
+    v1 = fminf(fmaxf(v1, -65504.f), 65504.f);
+    const __half2 h = __floats2half2_rn(v0, v1);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+  } else {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+    const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h);
+    const float h0 = __uint_as_float(hb << 16), h1 = __uint_as_float(hb & 0xFFFF0000u);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(v0 - h0, v1 - h1);
+    hi = hb;
+    lo = *reinterpret_cast<const uint32_t*>(&l);
   }
-  *reinterpret_cast<uint4*>(hi_p) = make_uint4(h[0], h[1], h[2], h[3]);
-  *reinterpret_cast<uint4*>(lo_p) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-template <bool kF16>
-__global__ void __launch_bounds__(256) sphere_pack_v2_kernel(uint16_t* __restrict__ out, uint16_t* __restrict__ out2,
-                                                            const float* __restrict__ xh, const float* __restrict__ coords,
-                                                            const float* __restrict__ grid, const float* __restrict__ in_mul,
-                                                            const uint32_t* __restrict__ chan_map, int B, int nc, int H, int W,
-                                                            int grid_group, int cmap_ld, int kp2, int blocks_per_group) {
-  constexpr int C = 256;  // features per sample = main K columns per tap
-  __shared__ int s_off[4][SP2_TASKS];
-  __shared__ float s_wt[4][SP2_TASKS];
-  __shared__ __align__(16) float s_mul[C + 32];
-  __shared__ uint32_t s_map[C];
+// not inlined: the trigonometric slow paths would sit nine times inside the hot loop, which takes them for one group in 32
+__device__ __noinline__ float encode_coord(float v, int kind) {
+  if (kind == 1) return tanhf(v);
+  if (kind == 2) return cosf(v * 3.14159274101257324f);
+  if (kind == 3) return sinf(v * 3.14159274101257324f);
+  return v;
+}
+
+// xg[(g*HW + p)*SPV_LD + k] for k < SPV_LD; one thread per element, k fastest (coalesced writes, near-coalesced reads).
+__global__ void __launch_bounds__(256) concat_repack_kernel(float* __restrict__ xg, const float* __restrict__ xh,
+                                                           const float* __restrict__ coords,
+                                                           const uint32_t* __restrict__ chan_map, int C, int nc, int HW,
+                                                           int cmap_ld, int px_per_cta) {
+  __shared__ uint32_t s_map[SPV_LD];
+  const int g = blockIdx.y;
   const int Ct = C + nc;
+  for (int k = threadIdx.x; k < SPV_LD; k += blockDim.x) s_map[k] = k < Ct ? __ldg(chan_map + (int64_t)g * cmap_ld + k) : 0xFFFFFFFFu;
+  __syncthreads();
+  const int p0 = blockIdx.x * px_per_cta;
+  const int npx = min(px_per_cta, HW - p0);
+  for (int idx = threadIdx.x; idx < npx * SPV_LD; idx += blockDim.x) {
+    const int r = idx / SPV_LD, k = idx - r * SPV_LD;
+    const uint32_t m = s_map[k];
+    float v = 0.f;
+    if (m != 0xFFFFFFFFu) {
+      const uint32_t bs = (m >> 15) & 0xFFFFu, cs = m & 0x7FFFu;
+      v = (m >> 31) ? __ldg(coords + ((int64_t)bs * nc + cs) * HW + p0 + r) : __ldg(xh + ((int64_t)bs * HW + p0 + r) * C + cs);
+    }
+    xg[((int64_t)g * HW + p0 + r) * SPV_LD + k] = v;
+  }
+}
+
+template <bool kF16>
+__global__ void __launch_bounds__(256) sphere_pack_v3_kernel(uint16_t* __restrict__ out, uint16_t* __restrict__ out2,
+                                                            const float* __restrict__ xg, const float* __restrict__ grid,
+                                                            const float* __restrict__ in_mul,
+                                                            const uint32_t* __restrict__ chan_map, int B, int Ct, int H, int W,
+                                                            int grid_group, int cmap_ld, int kp2, int blocks_per_group) {
+  constexpr int C = SPV_C;
+  __shared__ int s_off[4][SP_TASKS];
+  __shared__ float s_wt[4][SP_TASKS];
+  __shared__ __align__(16) float s_mul[SPV_LD];
   const int Cx = Ct - C;
   const int HW = H * W;
   const int g = blockIdx.x / blocks_per_group;
-  const int p0 = (blockIdx.x - g * blocks_per_group) * SP2_PX;
-  const int npx = min(SP2_PX, HW - p0);
+  const int p0 = (blockIdx.x - g * blocks_per_group) * SP_PX;
+  const int npx = min(SP_PX, HW - p0);
   const int ntask = npx * 9;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // ---- corner table and modulation row
   for (int e = threadIdx.x; e < ntask; e += blockDim.x) {
     const int r = e / 9, t = e - r * 9;
     const int p = p0 + r;
     const int py = p / W, px = p - py * W;
     const TapCorners cn = tap_corners(grid, g / grid_group, H, W, py, px, t / 3, t - (t / 3) * 3);
-    s_off[0][e] = cn.o_nw;
-    s_off[1][e] = cn.o_ne;
-    s_off[2][e] = cn.o_sw;
-    s_off[3][e] = cn.o_se;
+    s_off[0][e] = cn.o_nw * SPV_LD;
+    s_off[1][e] = cn.o_ne * SPV_LD;
+    s_off[2][e] = cn.o_sw * SPV_LD;
+    s_off[3][e] = cn.o_se * SPV_LD;
     s_wt[0][e] = cn.w_nw;
     s_wt[1][e] = cn.w_ne;
     s_wt[2][e] = cn.w_sw;
     s_wt[3][e] = cn.w_se;
   }
-  for (int k = threadIdx.x; k < C + 32; k += blockDim.x) s_mul[k] = (k < Ct && in_mul) ? __ldg(in_mul + (int64_t)g * Ct + k) : (k < Ct ? 1.f : 0.f);
-  // ---- this lane's 8 columns: one run of consecutive feature channels of one sample?
+  for (int k = threadIdx.x; k < SPV_LD; k += blockDim.x) s_mul[k] = k < Ct ? (in_mul ? __ldg(in_mul + (int64_t)g * Ct + k) : 1.f) : 0.f;
+  // this lane's K columns: [4 lane, 4 lane + 4) and [128 + 4 lane, 128 + 4 lane + 4), so that every warp-wide 128-bit load
+  // covers 512 contiguous bytes of a source row (8-column runs per lane touched every 32-byte sector twice: ncu L1 77 %).
+  // Coordinate-plane columns among them: 2 bits each (0 feature, 1 tanh, 2 cos pi, 3 sin pi).
   const uint32_t* mrow = chan_map + (int64_t)g * cmap_ld;
-  const int k0 = 8 * lane;
-  uint32_t mw[8];
-  {
-    const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(mrow + k0));
-    const uint4 q1 = __ldg(reinterpret_cast<const uint4*>(mrow + k0) + 1);
-    mw[0] = q0.x; mw[1] = q0.y; mw[2] = q0.z; mw[3] = q0.w;
-    mw[4] = q1.x; mw[5] = q1.y; mw[6] = q1.z; mw[7] = q1.w;
-  }
-  bool run = (mw[0] >> 31) == 0;  // a feature (an all-ones padding entry has bit 31 set)
+  const int ka = 4 * lane, kb = C / 2 + 4 * lane;
+  uint32_t kinds = 0;
 #pragma unroll
-  for (int j = 1; j < 8; ++j) run = run && mw[j] == mw[0] + (uint32_t)j;  // same sample (bits 15..30), channel + j (no carry below)
-  const int cs0 = (int)(mw[0] & 0x7FFFu);
-  const int mis = cs0 & 3;
-  run = run && (cs0 - mis + (mis ? 12 : 8) <= C);
-  const float* fbase = xh + ((int64_t)((mw[0] >> 15) & 0xFFFFu) * HW) * C + (cs0 - mis);
-  const unsigned slowmask = __ballot_sync(0xffffffffu, !run);
-  if (warp == 0) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) s_map[k0 + j] = mw[j];
+  for (int j = 0; j < 8; ++j) {
+    const uint32_t m = __ldg(mrow + (j < 4 ? ka + j : kb + j - 4));
+    if (m != 0xFFFFFFFFu && (m >> 31)) kinds |= (1u + (m & 3u)) << (2 * j);
   }
   __syncthreads();
+  const float4 m0 = *reinterpret_cast<const float4*>(&s_mul[ka]);
+  const float4 m1 = *reinterpret_cast<const float4*>(&s_mul[kb]);
+  const unsigned long long mm[4] = {pack_f2(m0.x, m0.y), pack_f2(m0.z, m0.w), pack_f2(m1.x, m1.y), pack_f2(m1.z, m1.w)};
+  const float* gbase = xg + (int64_t)g * HW * SPV_LD;
   const int64_t plane_elems = (int64_t)B * HW * 9 * C;
   for (int e = warp; e < ntask; e += 8) {
     int o[4];
@@ -301,127 +304,121 @@ __global__ void __launch_bounds__(256) sphere_pack_v2_kernel(uint16_t* __restric
       o[c] = s_off[c][e];
       wt[c] = s_wt[c][e];
     }
-    const int r = e / 9, t = e - r * 9;
-    uint16_t* dst = out + (((int64_t)g * HW + p0 + r) * 9 + t) * C;
-    if (run) {
-      int oc[4];
+    float4 xa[4], xb[4];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) oc[c] = o[c] * C;
-      unsigned long long acc[4];
-      switch (mis) {
-        case 0: blend8<0>(fbase, oc, wt, acc); break;
-        case 1: blend8<1>(fbase, oc, wt, acc); break;
-        case 2: blend8<2>(fbase, oc, wt, acc); break;
-        default: blend8<3>(fbase, oc, wt, acc); break;
-      }
-      const float4 m0 = *reinterpret_cast<const float4*>(&s_mul[k0]);
-      const float4 m1 = *reinterpret_cast<const float4*>(&s_mul[k0 + 4]);
-      acc[0] = mul2(acc[0], pack_f2(m0.x, m0.y));
-      acc[1] = mul2(acc[1], pack_f2(m0.z, m0.w));
-      acc[2] = mul2(acc[2], pack_f2(m1.x, m1.y));
-      acc[3] = mul2(acc[3], pack_f2(m1.z, m1.w));
-      float v[8];
+    for (int c = 0; c < 4; ++c) {
+      xa[c] = __ldg(reinterpret_cast<const float4*>(gbase + o[c] + ka));
+      xb[c] = __ldg(reinterpret_cast<const float4*>(gbase + o[c] + kb));
+    }
+    const unsigned long long w0 = pack_f2(wt[0], wt[0]), w1 = pack_f2(wt[1], wt[1]), w2 = pack_f2(wt[2], wt[2]),
+                             w3 = pack_f2(wt[3], wt[3]);
+    unsigned long long acc[4];
+    // ((a*w_nw + b*w_ne) + c*w_sw) + d*w_se per channel: the association of the scalar kernels in their contracted form
+    acc[0] = fma2(pack_f2(xa[3].x, xa[3].y), w3, fma2(pack_f2(xa[2].x, xa[2].y), w2, fma2(pack_f2(xa[1].x, xa[1].y), w1, mul2(pack_f2(xa[0].x, xa[0].y), w0))));
+    acc[1] = fma2(pack_f2(xa[3].z, xa[3].w), w3, fma2(pack_f2(xa[2].z, xa[2].w), w2, fma2(pack_f2(xa[1].z, xa[1].w), w1, mul2(pack_f2(xa[0].z, xa[0].w), w0))));
+    acc[2] = fma2(pack_f2(xb[3].x, xb[3].y), w3, fma2(pack_f2(xb[2].x, xb[2].y), w2, fma2(pack_f2(xb[1].x, xb[1].y), w1, mul2(pack_f2(xb[0].x, xb[0].y), w0))));
+    acc[3] = fma2(pack_f2(xb[3].z, xb[3].w), w3, fma2(pack_f2(xb[2].z, xb[2].w), w2, fma2(pack_f2(xb[1].z, xb[1].w), w1, mul2(pack_f2(xb[0].z, xb[0].w), w0))));
+    float v[8];
+    if (kinds != 0) {  // only the lanes of the group that holds the coordinate planes
 #pragma unroll
       for (int j = 0; j < 4; ++j) unpack_f2(acc[j], v[2 * j], v[2 * j + 1]);
-      split_store8<kF16>(dst + k0, dst + k0 + plane_elems, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = encode_coord(v[j], (int)((kinds >> (2 * j)) & 3u));
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j] = pack_f2(v[2 * j], v[2 * j + 1]);
     }
-    // boundary runs (sample change of the flat concat, coordinate planes, padding): one COLUMN per lane, 8 lanes per run,
-    // so that the one such run nearly every group has costs ~30 instructions per task instead of a serial 8-column loop
-    for (unsigned sm = slowmask; sm; sm &= sm - 1) {
-      const int k = 8 * (__ffs(sm) - 1) + (lane & 7);
-      if (lane < 8) {
-        const uint32_t m = s_map[k];
-        float val = 0.f;
-        if (m != 0xFFFFFFFFu) {
-          const uint32_t bs = (m >> 15) & 0xFFFFu, cs = m & 0x7FFFu;
-          const bool is_coord = (m >> 31) != 0;
-          const float* sp = is_coord ? coords + ((int64_t)bs * nc + cs) * HW : xh + (int64_t)bs * HW * C + cs;
-          const int st = is_coord ? 1 : C;
-          val = __ldg(sp + o[0] * st) * wt[0] + __ldg(sp + o[1] * st) * wt[1] + __ldg(sp + o[2] * st) * wt[2] +
-                __ldg(sp + o[3] * st) * wt[3];
-          if (is_coord) {
-            if (cs == 0) val = tanhf(val);
-            else if (cs == 1) val = cosf(val * 3.14159274101257324f);
-            else if (cs == 2) val = sinf(val * 3.14159274101257324f);
-          }
-          val *= s_mul[k];
-        }
-        uint16_t h, l;
-        split16<kF16>(val, h, l);
-        dst[k] = h;
-        dst[k + plane_elems] = l;
-      }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      acc[j] = mul2(acc[j], mm[j]);
+      unpack_f2(acc[j], v[2 * j], v[2 * j + 1]);
     }
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) split_pair<kF16>(v[2 * j], v[2 * j + 1], h[j], l[j]);
+    const int r = e / 9, t = e - r * 9;
+    uint16_t* dst = out + (((int64_t)g * HW + p0 + r) * 9 + t) * C;
+    *reinterpret_cast<uint2*>(dst + ka) = make_uint2(h[0], h[1]);
+    *reinterpret_cast<uint2*>(dst + kb) = make_uint2(h[2], h[3]);
+    *reinterpret_cast<uint2*>(dst + plane_elems + ka) = make_uint2(l[0], l[1]);
+    *reinterpret_cast<uint2*>(dst + plane_elems + kb) = make_uint2(l[2], l[3]);
   }
-  // ---- tail columns (channels C .. Ct-1 of the group, all taps) and their zero padding
+  // ---- tail operand: columns C .. Ct-1 of every (pixel, tap) of this CTA and the zero padding, one element per thread
+  // (inside the warp loop above the three tail lanes cost every task ~70 instructions)
   if (Cx > 0) {
     const int64_t plane2_elems = (int64_t)B * HW * kp2;
     for (int idx = threadIdx.x; idx < npx * kp2; idx += blockDim.x) {
       const int r = idx / kp2, col = idx - r * kp2;
-      uint16_t h = 0, l = 0;
+      uint16_t hh = 0, ll = 0;
       if (col < 9 * Cx) {
         const int t = col / Cx, j = col - t * Cx;
         const int e = r * 9 + t;
         const uint32_t m = __ldg(mrow + C + j);
-        float val = 0.f;
-        if (m != 0xFFFFFFFFu) {
-          const uint32_t bs = (m >> 15) & 0xFFFFu, cs = m & 0x7FFFu;
-          const bool is_coord = (m >> 31) != 0;
-          const float* sp = is_coord ? coords + ((int64_t)bs * nc + cs) * HW : xh + (int64_t)bs * HW * C + cs;
-          const int st = is_coord ? 1 : C;
-          val = __ldg(sp + s_off[0][e] * st) * s_wt[0][e] + __ldg(sp + s_off[1][e] * st) * s_wt[1][e] +
-                __ldg(sp + s_off[2][e] * st) * s_wt[2][e] + __ldg(sp + s_off[3][e] * st) * s_wt[3][e];
-          if (is_coord) {
-            if (cs == 0) val = tanhf(val);
-            else if (cs == 1) val = cosf(val * 3.14159274101257324f);
-            else if (cs == 2) val = sinf(val * 3.14159274101257324f);
-          }
-          val *= s_mul[C + j];
-        }
-        split16<kF16>(val, h, l);
+        const float* sp = gbase + C + j;
+        float val = __ldg(sp + s_off[3][e]) * s_wt[3][e] +
+                    (__ldg(sp + s_off[2][e]) * s_wt[2][e] + (__ldg(sp + s_off[1][e]) * s_wt[1][e] + __ldg(sp + s_off[0][e]) * s_wt[0][e]));
+        if (m != 0xFFFFFFFFu && (m >> 31)) val = encode_coord(val, 1 + (int)(m & 3u));
+        val *= s_mul[C + j];
+        split16<kF16>(val, hh, ll);
       }
       const int64_t off = ((int64_t)g * HW + p0 + r) * kp2 + col;
-      out2[off] = h;
-      out2[plane2_elems + off] = l;
+      out2[off] = hh;
+      out2[plane2_elems + off] = ll;
     }
   }
 }
 
-// One thread per (output row, column of the tail operand).
+// One CTA per (sample, output row): the kh input rows of encoded, modulated coordinate values are computed ONCE into shared
+// memory (kh * W * nc values; the first version evaluated tanh / cos / sin per output element, 49 times per value, and was
+// issue-bound at 96 us for a 20 MB operand), then the im2col copy pairs them up and splits them, two columns per thread.
 template <bool kF16>
 __global__ void __launch_bounds__(256) coord_taps_pack_kernel(uint16_t* __restrict__ out2, const float* __restrict__ coords,
                                                              const float* __restrict__ in_mul, int64_t rows, int nc, int H,
-                                                             int W, int kw, int ntaps, int My, int Mx, int mul_ld, int mul_off,
+                                                             int W, int kh, int kw, int My, int Mx, int mul_ld, int mul_off,
                                                              int kp2) {
-  const int64_t total = rows * kp2;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int col = (int)(idx % kp2);
-    const int64_t row = idx / kp2;
-    uint16_t h = 0, l = 0;
-    if (col < ntaps * nc) {
-      const int t = col / nc, j = col - t * nc;
-      const int ty = t / kw, tx = t - ty * kw;
-      const int x = (int)(row % Mx);
-      const int64_t r = row / Mx;
-      const int y = (int)(r % My);
-      const int b = (int)(r / My);
-      float v = __ldg(coords + (((int64_t)b * nc + j) * H + (y + ty)) * W + (x + tx));
-      if (j == 0) v = tanhf(v);
-      else if (j == 1) v = cosf(v * 3.14159274101257324f);
-      else if (j == 2) v = sinf(v * 3.14159274101257324f);
-      if (in_mul) v *= __ldg(in_mul + (int64_t)b * mul_ld + mul_off + j);
-      split16<kF16>(v, h, l);
+  extern __shared__ float s_enc[];  // [kh][W][nc]
+  const int b = blockIdx.x / My, y = blockIdx.x - b * My;
+  for (int idx = threadIdx.x; idx < kh * W * nc; idx += blockDim.x) {
+    const int j = idx % nc;
+    const int q = idx / nc;
+    const int ty = q / W, x = q - ty * W;
+    float v = __ldg(coords + (((int64_t)b * nc + j) * H + (y + ty)) * W + x);
+    v = encode_coord(v, j + 1);
+    if (in_mul) v *= __ldg(in_mul + (int64_t)b * mul_ld + mul_off + j);
+    s_enc[idx] = v;
+  }
+  __syncthreads();
+  const int used = kh * kw * nc;
+  const int half = kp2 >> 1;
+  const int64_t plane = rows * kp2;
+  uint16_t* orow = out2 + ((int64_t)b * My + y) * Mx * kp2;
+  for (int idx = threadIdx.x; idx < Mx * half; idx += blockDim.x) {
+    const int x = idx / half, col = (idx - x * half) * 2;
+    float v[2] = {0.f, 0.f};
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int c = col + u;
+      if (c < used) {
+        const int t = c / nc, j = c - t * nc;
+        const int ty = t / kw, tx = t - ty * kw;
+        v[u] = s_enc[(ty * W + x + tx) * nc + j];
+      }
     }
-    out2[idx] = h;
-    out2[total + idx] = l;
+    uint32_t h, l;
+    split_pair<kF16>(v[0], v[1], h, l);
+    *reinterpret_cast<uint32_t*>(orow + (int64_t)x * kp2 + col) = h;
+    *reinterpret_cast<uint32_t*>(orow + plane + (int64_t)x * kp2 + col) = l;
   }
 }
 
 }  // namespace
 
+extern "C" int64_t spgan_sphere_pack_seg_scratch(int B, int C, int H, int W) {
+  return C == SPV_C ? (int64_t)B * H * W * SPV_LD : 0;
+}
+
 extern "C" int spgan_sphere_pack_seg(uint16_t* out, uint16_t* out2, const float* x_nhwc, const float* coords,
                                      const float* grid, const float* in_mul, const uint32_t* chan_map, int B, int C, int H,
-                                     int W, int grid_group, int Cm, int cmap_ld, int kp2, int fmt, void* stream) {
+                                     int W, int grid_group, int Cm, int cmap_ld, int kp2, int fmt, float* scratch, void* stream) {
   SPGAN_CHECK_ARG(B >= 0 && C >= 0 && H >= 0 && W >= 0, "spgan_sphere_pack_seg: negative size");
   const int nc = coords ? 3 : 0;
   const int Cx = C + nc - Cm;
@@ -440,14 +437,17 @@ extern "C" int spgan_sphere_pack_seg(uint16_t* out, uint16_t* out2, const float*
                   "spgan_sphere_pack_seg: grid and chan_map must be 8-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   static const bool force_v1 = getenv("SPGAN_SPHERE_PACK_V1") != nullptr;  // diagnostics: A/B against the scalar producer
-  if (!force_v1 && C == 256 && Cm == 256 && cmap_ld % 4 == 0 && (((uintptr_t)chan_map) & 15) == 0 && (((uintptr_t)x_nhwc) & 15) == 0 &&
-      (((uintptr_t)out) & 15) == 0) {
-    const int bpg = (H * W + SP2_PX - 1) / SP2_PX;
+  if (!force_v1 && scratch != nullptr && C == SPV_C && Cm == SPV_C && C + nc <= SPV_LD && (((uintptr_t)scratch) & 15) == 0 &&
+      (((uintptr_t)out) & 15) == 0 && (int64_t)H * W * SPV_LD < (1LL << 31)) {
+    const int bpg = (H * W + SP_PX - 1) / SP_PX;
     SPGAN_CHECK_ARG((int64_t)B * bpg < (1LL << 31), "spgan_sphere_pack_seg: grid too large");
+    const int rp_px = 8;
+    concat_repack_kernel<<<dim3((H * W + rp_px - 1) / rp_px, B), 256, 0, st>>>(scratch, x_nhwc, coords, chan_map, C, nc, H * W, cmap_ld, rp_px);
+    SPGAN_CHECK_LAUNCH("spgan_sphere_pack_seg (concat repack)");
     if (fmt)
-      sphere_pack_v2_kernel<true><<<B * bpg, 256, 0, st>>>(out, out2, x_nhwc, coords, grid, in_mul, chan_map, B, nc, H, W, grid_group, cmap_ld, kp2, bpg);
+      sphere_pack_v3_kernel<true><<<B * bpg, 256, 0, st>>>(out, out2, scratch, grid, in_mul, chan_map, B, C + nc, H, W, grid_group, cmap_ld, kp2, bpg);
     else
-      sphere_pack_v2_kernel<false><<<B * bpg, 256, 0, st>>>(out, out2, x_nhwc, coords, grid, in_mul, chan_map, B, nc, H, W, grid_group, cmap_ld, kp2, bpg);
+      sphere_pack_v3_kernel<false><<<B * bpg, 256, 0, st>>>(out, out2, scratch, grid, in_mul, chan_map, B, C + nc, H, W, grid_group, cmap_ld, kp2, bpg);
     SPGAN_CHECK_LAUNCH("spgan_sphere_pack_seg");
     return 0;
   }
@@ -481,11 +481,13 @@ extern "C" int spgan_coord_taps_pack(uint16_t* out2, const float* coords, const 
   SPGAN_CHECK_ARG(out2 && coords, "spgan_coord_taps_pack: null pointer");
   SPGAN_CHECK_ARG(in_mul == nullptr || (mul_ld >= mul_off + nc && mul_off >= 0), "spgan_coord_taps_pack: modulation slice out of range");
   cudaStream_t st = (cudaStream_t)stream;
-  const int nblk = grid_for(rows * kp2, 256, 4);
+  SPGAN_CHECK_ARG((int64_t)B * My < (1LL << 31) && (((uintptr_t)out2) & 3) == 0, "spgan_coord_taps_pack: grid too large / misaligned output");
+  const size_t smem = (size_t)kh * W * nc * sizeof(float);
+  SPGAN_CHECK_ARG(smem <= 48 * 1024, "spgan_coord_taps_pack: %d rows of %d pixels do not fit the staging buffer", kh, W);
   if (fmt)
-    coord_taps_pack_kernel<true><<<nblk, 256, 0, st>>>(out2, coords, in_mul, rows, nc, H, W, kw, kh * kw, My, Mx, mul_ld, mul_off, kp2);
+    coord_taps_pack_kernel<true><<<B * My, 256, smem, st>>>(out2, coords, in_mul, rows, nc, H, W, kh, kw, My, Mx, mul_ld, mul_off, kp2);
   else
-    coord_taps_pack_kernel<false><<<nblk, 256, 0, st>>>(out2, coords, in_mul, rows, nc, H, W, kw, kh * kw, My, Mx, mul_ld, mul_off, kp2);
+    coord_taps_pack_kernel<false><<<B * My, 256, smem, st>>>(out2, coords, in_mul, rows, nc, H, W, kh, kw, My, Mx, mul_ld, mul_off, kp2);
   SPGAN_CHECK_LAUNCH("spgan_coord_taps_pack");
   return 0;
 }

@@ -1303,8 +1303,10 @@ def ss_sphere(xh, coords, grid, grid_group, w, in_mul, out_mul, out_scale, act, 
     alpha, gain = act
     with torch.cuda.device(xh.device):
         cmap = _sphere_chan_map(B, C, nc, _round_up(Ct, 64), True, xh.device, group=grid_group)
+        need = int(lib.load().spgan_sphere_pack_seg_scratch(B, C, H, W))
+        scratch = torch.empty((need,), device=xh.device, dtype=torch.float32) if need else None
         lib.call("spgan_sphere_pack_seg", _ptr(a), _ptr(a2), _ptr(xh), _ptr(coords), _ptr(grid), _ptr(in_mul), _ptr(cmap), B, C,
-                 H, W, grid_group, Cm, cmap.shape[1], kp2, fmt, st)
+                 H, W, grid_group, Cm, cmap.shape[1], kp2, fmt, _ptr(scratch), st)
         wp = _packed_weight(w, O, Cm, Ct * 9, 9, list(range(9)), Cm, True, _wfmt(precision))
         w2 = _packed_weight_tail(w, Cm, list(range(9)), kp2, _wfmt(precision)) if kp2 else None
         p = dict(My=H, Mx=W, in_stride=1, out_stride=1, off_y=0, off_x=0, taps=[(0, 0, 0)])

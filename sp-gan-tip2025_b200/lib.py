@@ -84,7 +84,8 @@ SIGNATURES = {
     "spgan_pack_weight": (c_int, [c_vp, c_vp, c_int, c_int, c_i64, c_i64, c_int, ctypes.POINTER(ctypes.c_int32), c_int, c_int, c_int, c_vp]),
     "spgan_nchw_to_nhwc": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp]),
     "spgan_sphere_pack": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
-    "spgan_sphere_pack_seg": (c_int, [c_vp] * 7 + [c_int] * 9 + [c_vp]),
+    "spgan_sphere_pack_seg_scratch": (c_i64, [c_int, c_int, c_int, c_int]),
+    "spgan_sphere_pack_seg": (c_int, [c_vp] * 7 + [c_int] * 9 + [c_vp, c_vp]),
     "spgan_coord_taps_pack": (c_int, [c_vp, c_vp, c_vp] + [c_int] * 10 + [c_vp]),
     "spgan_conv_gemm": (c_int, [_PASS_P, c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "spgan_conv_gemm_ex": (c_int, [_PASS_P, ctypes.c_void_p, c_vp]),
