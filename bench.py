@@ -497,6 +497,7 @@ def run_train(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     SF.set_precision(args.precision)
+    SF.set_gemm_pair_mode(args.pair_mode)
     out = measure_train(args, dev, world, rank, local)
     if rank == 0:
         print(json.dumps(out))

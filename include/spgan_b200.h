@@ -212,6 +212,12 @@ int spgan_sphere_pack(uint16_t* out, const float* x_nhwc, const float* coords, c
  *   scalar producer) that receives the flat-concat channels of every group as 16-byte aligned rows, so that the gather itself
  *   runs on 128-bit loads. */
 int64_t spgan_sphere_pack_seg_scratch(int B, int C, int H, int W);
+/* spgan_sphere_concat_repack: the reference's flat (1,B*C) ++ (1,B*3) concatenation made explicit once per layer:
+ *   xg[(g*H*W + p)*264 + k] = the k-th channel group g reads (chan_map[g][k]: feature plane of some sample, or RAW coordinate
+ *   plane), zero for k >= C + nc; 16-byte aligned rows, so that the gather of spgan_sphere_pack_seg / spgan_sphere_conv_gemm
+ *   runs on aligned 128-bit loads.  C must be 256; xg holds spgan_sphere_pack_seg_scratch(B, C, H, W) floats. */
+int spgan_sphere_concat_repack(float* xg, const float* x_nhwc, const float* coords, const uint32_t* chan_map, int B, int C,
+                               int H, int W, int cmap_ld, void* stream);
 int spgan_sphere_pack_seg(uint16_t* out, uint16_t* out2, const float* x_nhwc, const float* coords, const float* grid,
                           const float* in_mul, const uint32_t* chan_map, int B, int C, int H, int W, int grid_group, int Cm,
                           int cmap_ld, int kp2, int fmt, float* scratch, void* stream);
@@ -305,6 +311,13 @@ typedef struct SpganSphereIn {
   const uint32_t* chan_map;
   int32_t C;
   int32_t Cp;
+  /* Optional: the REPACKED gather source of spgan_sphere_concat_repack (xg != NULL selects the vectorised producer: C = Cp = 256
+   * main columns per tap, io->kp = 9*256 in the merged weight layout, the trailing C + nc - 256 channels of all taps in the
+   * tail weight io->w2_packed with io->kp2 = 64, Cout <= 256).  x_nhwc is then unused; coords only says whether there are
+   * coordinate planes; samples [i*grid_group, (i+1)*grid_group) share grid i; chan_map rows are cmap_ld entries apart. */
+  const float* xg;
+  int32_t grid_group;
+  int32_t cmap_ld;
 } SpganSphereIn;
 int spgan_sphere_conv_gemm(const SpganConvPass* p, const SpganSphereIn* in, const SpganGemmIO* io, void* stream);
 
@@ -322,9 +335,10 @@ int spgan_rgb_tail(float* out, const float* part, int slots, const float* bias, 
 /* ---- training-loop tails ------------------------------------------------------------------------------
  * spgan_ema_multi: the EMA `accumulate` of utils.py:86-94 over ALL parameters in one launch: table is a DEVICE array of
  *   nchunks records {float* dst; const float* src; int64_t n} (24 bytes each, n <= spgan_ema_chunk_elems()), one CTA per
- *   record: dst[i] = fma(1 - decay, src[i], dst[i] * decay) — the arithmetic of torch's mul_(decay).add_(src, alpha=1-decay). */
+ *   record: dst[i] = fma(alpha, src[i], dst[i] * decay) — torch's mul_(decay).add_(src, alpha=1-decay); the caller passes
+ *   alpha = (float)(1 - decay) evaluated in double precision, as Python does for the reference. */
 int spgan_ema_chunk_elems(void);
-int spgan_ema_multi(const void* table, int nchunks, float decay, void* stream);
+int spgan_ema_multi(const void* table, int nchunks, float decay, float alpha, void* stream);
 /* spgan_minibatch_stddev: models/stylegan2discriminator.py:205-212 fused with its torch.cat: h (B, C, HW) -> out (B, C+1, HW),
  *   out[:, :C] = h, out[b, C, :] = mean over (c, p) of sqrt(var over the `group` samples {n*M + b % M} + eps), M = B / group
  *   (stddev_feat = 1).  partial: fp32 scratch of M * 8 elements.  Forward only; the host composes the gradient. */

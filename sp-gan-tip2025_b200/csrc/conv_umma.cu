@@ -836,7 +836,7 @@ struct GemmShape {
   int m_tiles, block_n, n_tiles;
 };
 
-GemmShape gemm_shape(const SpganConvPass* p, int64_t a_rows) {
+GemmShape gemm_shape(const SpganConvPass* p, int64_t a_rows, int kblocks) {
   GemmShape g;
   const int64_t rows = (int64_t)p->B * p->H * p->W;
   g.phases = rows > 0 ? (int)(a_rows / rows) : 1;
@@ -849,15 +849,13 @@ GemmShape gemm_shape(const SpganConvPass* p, int64_t a_rows) {
   g.m_tiles = (int)((g.rows_m + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M);
   g.block_n = pick_block_n(g.m_tiles, p->Cout);
   g.n_tiles = (p->Cout + g.block_n - 1) / g.block_n;
+  // CTA-pair kernel (cta_group::2).  Measured per shape on the B200 (tools/probes/pair_ab.py, bf16x3): 8-16 % faster from
+  // ~130 M tiles of 128 rows upwards (less weight traffic per SM, deeper ring), 15-30 % SLOWER below ~70 M tiles (half as many
+  // work items, cluster launch + two cluster barriers per launch), neutral for 1x1 convs (4 K blocks: epilogue-bound).
   g.pair = false;
   const int mode = pair_mode()->load();
   if (mode != 0 && p->Cout % 256 == 0 && g.m_tiles >= 2) {
-    const int64_t ptiles = (int64_t)((g.m_tiles + 1) / 2) * (p->Cout / 256);
-    const int64_t tiles = (int64_t)g.m_tiles * g.n_tiles;
-    const int half = SPGAN_NUM_SMS / 2;
-    const double eff_pair = (double)ptiles / (double)(((ptiles + half - 1) / half) * half) * (2.0 * g.m_tiles / (2.0 * ((g.m_tiles + 1) / 2)));
-    const double eff_one = (double)tiles / (double)(((tiles + SPGAN_NUM_SMS - 1) / SPGAN_NUM_SMS) * SPGAN_NUM_SMS);
-    g.pair = mode == 2 || eff_pair >= 0.95 * eff_one;
+    g.pair = mode == 2 || (g.m_tiles >= 128 && p->ntaps * kblocks >= 8);
     if (g.pair) {
       g.block_n = 256;
       g.n_tiles = p->Cout / 256;
@@ -965,7 +963,7 @@ extern "C" int spgan_sphere_pack(uint16_t* out, const float* x_nhwc, const float
 
 extern "C" int spgan_conv_gemm_rgb_slots(const SpganConvPass* p, int64_t a_rows) {
   if (p == nullptr || p->Cout <= 0) return 0;
-  return 2 * gemm_shape(p, a_rows).n_tiles;
+  return 2 * gemm_shape(p, a_rows, 8).n_tiles;  // the ToRGB sink rides on 512-channel convs: kp >= 512
 }
 
 extern "C" int spgan_conv_gemm_ex(const SpganConvPass* p, const SpganGemmIO* io, void* stream) {
@@ -1011,7 +1009,7 @@ extern "C" int spgan_conv_gemm_ex(const SpganConvPass* p, const SpganGemmIO* io,
     SPGAN_CHECK_ARG((((uintptr_t)io->rgb_w) & 15) == 0, "spgan_conv_gemm: rgb_w must be 16-byte aligned");
   }
 
-  const GemmShape gs = gemm_shape(p, a_rows);
+  const GemmShape gs = gemm_shape(p, a_rows, (kp + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K);
   const int phases = gs.phases;
   const bool im2col = gs.im2col;
   GemmParams gp;

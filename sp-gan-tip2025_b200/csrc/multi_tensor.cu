@@ -94,11 +94,11 @@ __global__ void __launch_bounds__(256) stddev_concat_kernel(float* __restrict__ 
 
 extern "C" int spgan_ema_chunk_elems(void) { return EMA_CHUNK; }
 
-extern "C" int spgan_ema_multi(const void* table, int nchunks, float decay, void* stream) {
+extern "C" int spgan_ema_multi(const void* table, int nchunks, float decay, float alpha, void* stream) {
   SPGAN_CHECK_ARG(nchunks >= 0, "spgan_ema_multi: negative chunk count");
   if (nchunks == 0) return 0;
   SPGAN_CHECK_ARG(table != nullptr && (((uintptr_t)table) & 7) == 0, "spgan_ema_multi: chunk table must be an 8-byte aligned device pointer");
-  ema_multi_kernel<<<nchunks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const EmaChunk*>(table), decay, 1.f - decay);
+  ema_multi_kernel<<<nchunks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const EmaChunk*>(table), decay, alpha);
   SPGAN_CHECK_LAUNCH("spgan_ema_multi");
   return 0;
 }

@@ -13,6 +13,7 @@
 // Roofline: HBM (sphere_pack_seg writes 4*9*Cm + 4*kp2 bytes per pixel and gathers 4x that from L2).
 #include "sphere_taps.cuh"
 #include "umma_common.cuh"
+#include "pack_math.cuh"
 
 #include <stdlib.h>
 
@@ -172,56 +173,6 @@ __global__ void __launch_bounds__(256, 2) sphere_pack_seg_kernel(uint16_t* __res
 //                   group: the corner table of its 9 * SP_PX (pixel, tap) pairs and the group's modulation row sit in smem.
 constexpr int SP_PX = 16;
 constexpr int SP_TASKS = SP_PX * 9;
-constexpr int SPV_C = 256;   // main K columns per tap
-constexpr int SPV_LD = 264;  // floats per (group, pixel) row of the repacked source: 259 flat-concat channels + padding
-
-__device__ __forceinline__ unsigned long long pack_f2(float lo, float hi) {
-  unsigned long long r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void unpack_f2(unsigned long long v, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
-  unsigned long long d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
-  unsigned long long d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-
-// (v0, v1) -> packed 16-bit hi pair and lo pair (lo = round(v - hi)), two values per conversion instruction.
-template <bool kF16>
-__device__ __forceinline__ void split_pair(float v0, float v1, uint32_t& hi, uint32_t& lo) {
-  if (kF16) {
-    v0 = fminf(fmaxf(v0, -65504.f), 65504.f);
-    v1 = fminf(fmaxf(v1, -65504.f), 65504.f);
-    const __half2 h = __floats2half2_rn(v0, v1);
-    const float2 hf = __half22float2(h);
-    const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
-    hi = *reinterpret_cast<const uint32_t*>(&h);
-    lo = *reinterpret_cast<const uint32_t*>(&l);
-  } else {
-    const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
-    const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h);
-    const float h0 = __uint_as_float(hb << 16), h1 = __uint_as_float(hb & 0xFFFF0000u);
-    const __nv_bfloat162 l = __floats2bfloat162_rn(v0 - h0, v1 - h1);
-    hi = hb;
-    lo = *reinterpret_cast<const uint32_t*>(&l);
-  }
-}
-
-// not inlined: the trigonometric slow paths would sit nine times inside the hot loop, which takes them for one group in 32
-__device__ __noinline__ float encode_coord(float v, int kind) {
-  if (kind == 1) return tanhf(v);
-  if (kind == 2) return cosf(v * 3.14159274101257324f);
-  if (kind == 3) return sinf(v * 3.14159274101257324f);
-  return v;
-}
 
 // xg[(g*HW + p)*SPV_LD + k] for k < SPV_LD; one thread per element, k fastest (coalesced writes, near-coalesced reads).
 __global__ void __launch_bounds__(256) concat_repack_kernel(float* __restrict__ xg, const float* __restrict__ xh,
@@ -411,6 +362,20 @@ __global__ void __launch_bounds__(256) coord_taps_pack_kernel(uint16_t* __restri
 }
 
 }  // namespace
+
+extern "C" int spgan_sphere_concat_repack(float* xg, const float* x_nhwc, const float* coords, const uint32_t* chan_map, int B,
+                                          int C, int H, int W, int cmap_ld, void* stream) {
+  SPGAN_CHECK_ARG(B >= 0 && H >= 0 && W >= 0 && C == SPV_C, "spgan_sphere_concat_repack: needs C = %d features, got %d", SPV_C, C);
+  const int nc = coords ? 3 : 0;
+  SPGAN_CHECK_ARG(C + nc <= SPV_LD && cmap_ld >= C + nc, "spgan_sphere_concat_repack: channel count / chan_map stride out of range");
+  if (B == 0 || H == 0 || W == 0) return 0;
+  SPGAN_CHECK_ARG(xg && x_nhwc && chan_map, "spgan_sphere_concat_repack: null pointer");
+  SPGAN_CHECK_ARG(B <= 65535, "spgan_sphere_concat_repack: batch %d > 65535", B);
+  const int rp_px = 8;
+  concat_repack_kernel<<<dim3((H * W + rp_px - 1) / rp_px, B), 256, 0, (cudaStream_t)stream>>>(xg, x_nhwc, coords, chan_map, C, nc, H * W, cmap_ld, rp_px);
+  SPGAN_CHECK_LAUNCH("spgan_sphere_concat_repack");
+  return 0;
+}
 
 extern "C" int64_t spgan_sphere_pack_seg_scratch(int B, int C, int H, int W) {
   return C == SPV_C ? (int64_t)B * H * W * SPV_LD : 0;

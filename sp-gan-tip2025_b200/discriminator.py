@@ -109,6 +109,13 @@ class Discriminator(nn.Module):
         h = self.convs(img)
         batch, channel, height, width = h.shape
         group = min(batch, self.stddev_group)
+        if h.is_cuda and self.stddev_feat == 1 and batch % group == 0:
+            h = SF.minibatch_stddev(h, group)  # fused stddev + concat (csrc/multi_tensor.cu)
+            out = self.final_conv(h).view(batch, -1)
+            ret = {"d_patch": self.final_linear(out)}
+            if self.use_coord_ac:
+                ret["ac_coords_pred"] = self.coord_linear(out)
+            return ret
         stddev = h.view(group, -1, self.stddev_feat, channel // self.stddev_feat, height, width)
         stddev = torch.sqrt(stddev.var(0, unbiased=False) + 1e-8)
         stddev = stddev.mean([2, 3, 4], keepdims=True).squeeze(2)

@@ -343,9 +343,9 @@ class _LinearFn(torch.autograd.Function):
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
             gx = _LinearFn.apply(g, w.t(), None, ctx.w_scale, 1.0)
-        if ctx.needs_input_grad[1]:
+        if ctx.needs_input_grad[1] and not _ONLY_DATA_GRADS:
             gw = _LinearWgradFn.apply(g, x, ctx.w_scale)
-        if ctx.has_bias and ctx.needs_input_grad[2]:
+        if ctx.has_bias and ctx.needs_input_grad[2] and not _ONLY_DATA_GRADS:
             gb = g.sum(0) * ctx.b_scale
         return gx, gw, gb, None, None
 
@@ -721,6 +721,26 @@ def conv_wgrad(g, x, w_shape, geom, in_mul=None, out_mul=None, out_scale=1.0, pr
     return dw
 
 
+_ONLY_DATA_GRADS = False
+
+
+class only_data_grads:
+    """Context manager for a `create_graph=True` backward whose caller consumes only DATA gradients (R1: d D(x) / dx,
+    models/losses.py:36-41; path length: d <G(w), noise> / dw, :60-68).  autograd evaluates every output of a custom
+    backward whose input `requires_grad`, so without it each conv / linear of the network would also compute — and record
+    for double backward — a weight gradient that is thrown away.  Inside the context the weight / bias gradient slots of
+    this package's Functions return None.  The second backward (through the recorded graph) is unaffected."""
+
+    def __enter__(self):
+        global _ONLY_DATA_GRADS
+        self.prev, _ONLY_DATA_GRADS = _ONLY_DATA_GRADS, True
+
+    def __exit__(self, *exc):
+        global _ONLY_DATA_GRADS
+        _ONLY_DATA_GRADS = self.prev
+        return False
+
+
 class _ConvFn(torch.autograd.Function):
     """y = out_scale * D(out_mul) L_w( D(in_mul) x ), differentiable to any order in x, w, in_mul, out_mul
     (the weight-gradient node itself is first-order only, which is all R1 / path-length need)."""
@@ -738,6 +758,7 @@ class _ConvFn(torch.autograd.Function):
     def backward(ctx, g):
         x, w, in_mul, out_mul, y = ctx.saved_tensors
         need_x, need_w, need_im, need_om = ctx.needs_input_grad[:4]
+        need_w = need_w and not _ONLY_DATA_GRADS
         gx = gw = gim = gom = None
         if need_x or need_im:
             # D(in_mul)^-1 applied lazily: the un-modulated data gradient serves both dx and d(in_mul)
@@ -1253,6 +1274,15 @@ def _packed_weight_tail(w, c0, tap_w, kp2, fmt):
 
 
 SS_MAIN = 256  # feature channels per tap of the main K segment
+# True: the spherical conv of the structure chain is ONE kernel (gather in the GEMM's producer warps, spgan_sphere_conv_gemm with
+# the repacked source: no [B*H*W][9*256] operand in HBM); False (default): spgan_sphere_pack_seg writes the operand to HBM and
+# spgan_conv_gemm_ex consumes it.  Measured on the B200 at B = 64, 256 + 3 -> 256 channels, bf16x3, in situ (bench.py
+# --profile-calls): fused 1.08 / 0.66 / 0.50 / 0.35 ms at 35 / 29 / 23 / 17 pixels against 0.30 + 0.25 / 0.22 + 0.16 / 0.15 + 0.12 /
+# 0.10 + 0.08 ms for producer + GEMM.  The persistent one-CTA-per-SM GEMM leaves the L1 ~30 KB (223 KB of the 256 KB are
+# operand stages and the corner table), so the 128 KB a stage gathers comes from L2 at 8 warps' worth of loads in flight:
+# ~5.8 us per stage against 0.9 us of MMAs.  The standalone producer runs 24 warps per SM with a full L1 (87 % hit rate).
+# Both paths are tested against each other and against the padded formulation (tests/test_gpu_ops.py).
+SS_FUSED_GATHER = False
 
 
 def ss_input(x, precision):
@@ -1297,10 +1327,33 @@ def ss_sphere(xh, coords, grid, grid_group, w, in_mul, out_mul, out_scale, act, 
     G = grid.shape[0]
     if B % G or (B // G) != grid_group:
         raise RuntimeError("structure chain: %d grids for a batch of %d in groups of %d" % (G, B, grid_group))
-    a = torch.empty((2, rows, 9 * Cm), device=xh.device, dtype=torch.bfloat16)
-    a2 = torch.empty((2, rows, kp2), device=xh.device, dtype=torch.bfloat16) if kp2 else None
     out = torch.empty((2, rows, O), device=xh.device, dtype=torch.bfloat16)
     alpha, gain = act
+    if SS_FUSED_GATHER and C == 256 and kp2 == 64 and O <= 256 and O % 32 == 0 and H * W >= 128:
+        # the gather runs in the producer warps of the GEMM itself (csrc/sphere_umma.cu, vectorised producer): neither the
+        # reference's 9x gathered fp32 tensor nor the [B*H*W][9*256] 16-bit operand exists in HBM
+        with torch.cuda.device(xh.device):
+            cmap = _sphere_chan_map(B, C, nc, _round_up(Ct, 64), True, xh.device, group=grid_group)
+            xg = torch.empty((int(lib.load().spgan_sphere_pack_seg_scratch(B, C, H, W)),), device=xh.device, dtype=torch.float32)
+            lib.call("spgan_sphere_concat_repack", _ptr(xg), _ptr(xh), _ptr(coords), _ptr(cmap), B, C, H, W, cmap.shape[1], st)
+            wp = _packed_weight(w, O, Cm, Ct * 9, 9, list(range(9)), Cm, True, _wfmt(precision))
+            w2 = _packed_weight_tail(w, Cm, list(range(9)), kp2, _wfmt(precision))
+            p = dict(My=H, Mx=W, in_stride=1, out_stride=1, off_y=0, off_x=0, taps=[(0, 0, 0)])
+            cp = _fill_pass(p, B, Ct, H, W, O, H, W, Ct * 9, 9, out_scale, 1, alpha, gain, precision)
+            sin = lib.SphereIn()
+            sin.coords = coords.data_ptr() if coords is not None else None
+            sin.grid, sin.in_mul, sin.chan_map = grid.data_ptr(), (in_mul.data_ptr() if in_mul is not None else None), cmap.data_ptr()
+            sin.C, sin.Cp, sin.xg, sin.grid_group, sin.cmap_ld = C, Cm, xg.data_ptr(), grid_group, cmap.shape[1]
+            io = lib.GemmIO()
+            io.kp, io.fmt, io.w_fmt, io.w_packed, io.w2_packed, io.kp2 = 9 * Cm, fmt, _wfmt(precision), wp.data_ptr(), w2.data_ptr(), kp2
+            io.out_mul = out_mul.data_ptr() if out_mul is not None else None
+            io.residual_nhwc = residual_nhwc.data_ptr() if residual_nhwc is not None else None
+            io.y_packed, io.next_mul = out.data_ptr(), (next_mul.data_ptr() if next_mul is not None else None)
+            io.y_packed_rows, io.y_packed_cols, io.y_packed_fmt = rows, O, fmt
+            _timed_call(2.0 * rows * O * Ct * 9, "spgan_sphere_conv_gemm", ctypes.byref(cp), ctypes.byref(sin), ctypes.byref(io), st)
+        return out
+    a = torch.empty((2, rows, 9 * Cm), device=xh.device, dtype=torch.bfloat16)
+    a2 = torch.empty((2, rows, kp2), device=xh.device, dtype=torch.bfloat16) if kp2 else None
     with torch.cuda.device(xh.device):
         cmap = _sphere_chan_map(B, C, nc, _round_up(Ct, 64), True, xh.device, group=grid_group)
         need = int(lib.load().spgan_sphere_pack_seg_scratch(B, C, H, W))
@@ -1352,3 +1405,72 @@ def ss_conv_k(a, coords, B, H, W, w, in_mul, out_mul, out_scale, bias, act, prec
         _gemm_ex(cp, 2.0 * rows_out * O * Ct * T, st, a_packed=a, a_rows=B * H * W, kp=Cm, fmt=fmt, w_fmt=_wfmt(precision),
                  w_packed=wp, a2_packed=a2, a2_rows=rows_out, w2_packed=w2, kp2=kp2, out_mul=out_mul, bias=bias, **kw_sinks)
     return y, packed, (oh, ow)
+
+
+# =================================================================================================== training-loop tails
+_EMA_TABLES = {}
+
+
+def ema_accumulate(dst_params, src_params, decay):
+    """utils.py:86-94 (`accumulate`): dst = dst * decay + src * (1 - decay) for every parameter pair in ONE launch
+    (spgan_ema_multi over a cached device table of (dst, src, count) chunks)."""
+    dst_params, src_params = list(dst_params), list(src_params)
+    if not dst_params:
+        return
+    dev = dst_params[0].device
+    ptrs = tuple(p.data_ptr() for p in dst_params) + tuple(p.data_ptr() for p in src_params)
+    hit = _EMA_TABLES.get(ptrs)
+    if hit is None:
+        chunk = int(lib.load().spgan_ema_chunk_elems())
+        rows = []
+        for d, s in zip(dst_params, src_params):
+            if d.shape != s.shape or d.dtype != torch.float32 or s.dtype != torch.float32 or not d.is_contiguous() or not s.is_contiguous():
+                raise RuntimeError("ema_accumulate: parameter pairs must be contiguous fp32 tensors of equal shape")
+            n = d.numel()
+            for off in range(0, n, chunk):
+                rows.append((d.data_ptr() + 4 * off, s.data_ptr() + 4 * off, min(chunk, n - off)))
+        table = torch.tensor(rows, dtype=torch.int64).to(dev)
+        _EMA_TABLES.clear()  # one live model pair at a time; parameter storage is stable across optimizer steps
+        hit = _EMA_TABLES[ptrs] = (table, len(rows))
+    with torch.cuda.device(dev):
+        lib.call("spgan_ema_multi", _ptr(hit[0]), hit[1], float(decay), float(1 - decay), _stream(dst_params[0]))
+
+
+class _MinibatchStddevFn(torch.autograd.Function):
+    """models/stylegan2discriminator.py:205-212 + the torch.cat: forward is one fused kernel pair (spgan_minibatch_stddev),
+    backward is written in differentiable torch ops (R1 differentiates through it a second time)."""
+
+    @staticmethod
+    def forward(ctx, h, group, eps):
+        hc = _f32c(h, "minibatch_stddev")
+        B, C, H, W = hc.shape
+        out = torch.empty((B, C + 1, H, W), device=hc.device, dtype=torch.float32)
+        partial = torch.empty(((B // group) * 8,), device=hc.device, dtype=torch.float32)
+        with torch.cuda.device(hc.device):
+            lib.call("spgan_minibatch_stddev", _ptr(out), _ptr(partial), _ptr(hc), B, C, H * W, int(group), float(eps), _stream(hc))
+        ctx.save_for_backward(h)
+        ctx.group, ctx.eps = int(group), float(eps)
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        h, = ctx.saved_tensors
+        B, C, H, W = h.shape
+        G = ctx.group
+        M = B // G
+        gh = go[:, :C]
+        if ctx.needs_input_grad[0]:
+            hv = h.view(G, M, C, H, W)
+            d = hv - hv.mean(0, keepdim=True)
+            sd = torch.sqrt((d * d).mean(0) + ctx.eps)
+            gs = go[:, C].reshape(G, M, H * W).sum((0, 2))  # d loss / d (the per-sub-batch scalar)
+            gh = gh + (gs.view(1, M, 1, 1, 1) / float(C * H * W * G) * d / sd.unsqueeze(0)).reshape(B, C, H, W)
+        return gh, None, None
+
+
+def minibatch_stddev(h, group, eps=1e-8):
+    """(B, C, H, W) -> (B, C + 1, H, W): the feature map with its minibatch-stddev channel appended (stddev_feat = 1)."""
+    _check_cuda(h, "minibatch_stddev")
+    if h.shape[0] % group:
+        raise RuntimeError("minibatch_stddev: batch %d is not a multiple of the group %d" % (h.shape[0], group))
+    return _MinibatchStddevFn.apply(h, int(group), float(eps))

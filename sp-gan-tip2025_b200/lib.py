@@ -50,7 +50,8 @@ class GemmIO(ctypes.Structure):
 class SphereIn(ctypes.Structure):
     """Mirror of `SpganSphereIn` (include/spgan_b200.h)."""
     _fields_ = [("x_nhwc", c_vp), ("coords", c_vp), ("grid", c_vp), ("in_mul", c_vp), ("chan_map", c_vp),
-                ("C", ctypes.c_int32), ("Cp", ctypes.c_int32)]
+                ("C", ctypes.c_int32), ("Cp", ctypes.c_int32), ("xg", c_vp), ("grid_group", ctypes.c_int32),
+                ("cmap_ld", ctypes.c_int32)]
 
 
 _PASS_P = ctypes.POINTER(ConvPass)
@@ -85,6 +86,7 @@ SIGNATURES = {
     "spgan_nchw_to_nhwc": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp]),
     "spgan_sphere_pack": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
     "spgan_sphere_pack_seg_scratch": (c_i64, [c_int, c_int, c_int, c_int]),
+    "spgan_sphere_concat_repack": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
     "spgan_sphere_pack_seg": (c_int, [c_vp] * 7 + [c_int] * 9 + [c_vp, c_vp]),
     "spgan_coord_taps_pack": (c_int, [c_vp, c_vp, c_vp] + [c_int] * 10 + [c_vp]),
     "spgan_conv_gemm": (c_int, [_PASS_P, c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
@@ -96,7 +98,7 @@ SIGNATURES = {
     "spgan_gemm_launch_count": (c_i64, []),
     "spgan_set_option": (c_int, [c_int, c_int]),
     "spgan_ema_chunk_elems": (c_int, []),
-    "spgan_ema_multi": (c_int, [c_vp, c_int, c_f32, c_vp]),
+    "spgan_ema_multi": (c_int, [c_vp, c_int, c_f32, c_f32, c_vp]),
     "spgan_minibatch_stddev": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_f32, c_vp]),
 }
 

@@ -30,7 +30,9 @@ def g_nonsaturating_loss(fake_pred):
 
 
 def d_r1_loss(real_pred, real_img):
-    grad_real, = torch.autograd.grad(outputs=real_pred.sum(), inputs=real_img, create_graph=True)
+    from . import functional as SF
+    with SF.only_data_grads():  # only d D(x) / dx is consumed here: no weight gradients in the create_graph pass
+        grad_real, = torch.autograd.grad(outputs=real_pred.sum(), inputs=real_img, create_graph=True)
     return grad_real.pow(2).reshape(grad_real.shape[0], -1).sum(1).mean()
 
 
@@ -39,7 +41,9 @@ def path_lengths(fake_img, styles, noise=None):
     if noise is None:
         noise = torch.randn_like(fake_img)
     noise = noise / math.sqrt(fake_img.shape[2] * fake_img.shape[3])
-    grad, = torch.autograd.grad(outputs=(fake_img * noise).sum(), inputs=styles, create_graph=True)
+    from . import functional as SF
+    with SF.only_data_grads():
+        grad, = torch.autograd.grad(outputs=(fake_img * noise).sum(), inputs=styles, create_graph=True)
     return torch.sqrt(grad.pow(2).mean([1, 2]))
 
 
@@ -227,7 +231,11 @@ def accumulate(ema, model, decay=0.999):
     pe, pm = dict(ema.named_parameters()), dict(model.named_parameters())
     dst = [pe[k] for k in pe]
     src = [pm[k].detach() for k in pe]
-    torch._foreach_mul_(dst, decay)  # two multi-tensor launches instead of 2 x 115 tiny ones
+    if dst and dst[0].is_cuda:
+        from . import functional as SF
+        SF.ema_accumulate(dst, src, decay)  # ONE launch over all 115 parameter pairs (csrc/multi_tensor.cu)
+        return
+    torch._foreach_mul_(dst, decay)  # host-side tests (gloo, CPU): the torch multi-tensor ops
     torch._foreach_add_(dst, src, alpha=1 - decay)
 
 

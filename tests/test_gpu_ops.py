@@ -640,8 +640,9 @@ def test_linear_second_order_vs_torch(dev):
             assert K.rel_err(K.t2n(a), K.t2n(r)) < 2e-5
 
 
+@pytest.mark.parametrize("fused", [True, False])
 @pytest.mark.parametrize("precision,tol", [(1, 1e-4), (2, 3e-2)])
-def test_structure_chain_ops_vs_padded_path(precision, tol):
+def test_structure_chain_ops_vs_padded_path(precision, tol, fused):
     """K-segment operands of the structure chain (spgan_sphere_pack_seg / spgan_coord_taps_pack feeding the second K segment
     of spgan_conv_gemm_ex) against the same convs computed with every tap padded to 320 channels (sphere_modconv_fused,
     conv_apply), two position groups with different sampling grids."""
@@ -679,16 +680,22 @@ def test_structure_chain_ops_vs_padded_path(precision, tol):
             want.append(SF.conv_apply(inp, w_7, SF.ConvGeom(7, 7), in_mul=s_7[sl].contiguous(), out_mul=d_7[sl].contiguous(),
                                       out_scale=sc_7, bias=b_7, act=(0.2, 2 ** 0.5), precision=precision))
         want = torch.cat(want, 0)
-        # chain
+        # chain: the spherical conv as ONE kernel (gather in the GEMM's producer warps) or as operand producer + GEMM
         xh, xp = SF.ss_input(x, precision)
         grid = grids.GRID_CACHE.group_grid(H, H, cps, dev)
         y_sc = SF.ss_shortcut(xp, B, H, H, w_sc, b_sc, precision)
-        a = SF.ss_sphere(xh, coords, grid, Bg, w_s, s_s, d_s, sc_s, (0.01, 1.0), y_sc, s_7[:, :C].contiguous(), precision)
+        prev, SF.SS_FUSED_GATHER = SF.SS_FUSED_GATHER, fused
+        try:
+            launches = SF.lib.load().spgan_gemm_launch_count()
+            a = SF.ss_sphere(xh, coords, grid, Bg, w_s, s_s, d_s, sc_s, (0.01, 1.0), y_sc, s_7[:, :C].contiguous(), precision)
+            assert SF.lib.load().spgan_gemm_launch_count() == launches + 1
+        finally:
+            SF.SS_FUSED_GATHER = prev
         got, _, hw = SF.ss_conv_k(a, coords, B, H, H, w_7, s_7, d_7, sc_7, b_7, (0.2, 2 ** 0.5), precision, True)
         nh, pk, _ = SF.ss_conv_k(a, coords, B, H, H, w_7, s_7, d_7, sc_7, b_7, (0.2, 2 ** 0.5), precision, False)
     assert hw == (11, 11) and got.shape == want.shape
     err = K.rel_err(K.t2n(got), K.t2n(want))
-    print("structure chain ops, precision %d: %.2e" % (precision, err))
+    print("structure chain ops, precision %d, fused gather %s: %.2e" % (precision, fused, err))
     assert err < tol
     # the two sink sets of the 7x7 GEMM carry the same values: NHWC fp32 and the packed hi/lo planes
     assert torch.equal(nh.permute(0, 3, 1, 2), got)

@@ -223,3 +223,78 @@ def test_cuda_graph_replay_matches_eager_step_from_same_state(dev):
         assert abs(lg - le) <= 1e-4 * abs(le) and abs(lg2 - le) <= 1e-4 * abs(le), (part, lg, le, lg2)
         cos = float((dg * de).sum() / (dg.norm() * de.norm()))
         assert cos > 0.9, (part, cos)
+
+
+def test_ema_multi_tensor_matches_torch_foreach():
+    """spgan_ema_multi (one launch over a chunk table) == torch's mul_(decay).add_(src, alpha = 1 - decay) on every parameter,
+    odd sizes and sizes beyond one chunk included."""
+    import spgan_b200.functional as SF
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(11)
+    shapes = [(1,), (3,), (512,), (7, 13), (256, 259, 3, 3), (512, 512, 3, 3), (16385,), (5, 4099)]
+    dst = [torch.randn(*s, generator=g).to(dev) for s in shapes]
+    src = [torch.randn(*s, generator=g).to(dev) for s in shapes]
+    want = [d.clone() for d in dst]
+    for _ in range(3):
+        torch._foreach_mul_(want, 0.999)
+        torch._foreach_add_(want, src, alpha=1 - 0.999)
+        SF.ema_accumulate(dst, src, 0.999)
+    for a, b in zip(dst, want):
+        assert torch.allclose(a, b, rtol=1e-6, atol=1e-9)  # fma(alpha, src, dst * decay) vs torch's separately rounded product
+
+
+def test_minibatch_stddev_forward_backward_double_backward():
+    """Fused minibatch-stddev + concat (models/stylegan2discriminator.py:205-212) against the reference's torch composition:
+    values, first-order gradient and the gradient of a gradient penalty (the R1 path)."""
+    import spgan_b200.functional as SF
+    dev = torch.device("cuda:0")
+    B, C, H, W, group = 8, 24, 3, 3, 4
+    h0 = synth.randn_t(7, "mbstd_h", (B, C, H, W)).to(dev)
+    wgt = synth.randn_t(7, "mbstd_w", (B, C + 1, H, W)).to(dev)
+
+    def reference(h):
+        sd = h.view(group, -1, 1, C, H, W)
+        sd = torch.sqrt(sd.var(0, unbiased=False) + 1e-8)
+        sd = sd.mean([2, 3, 4], keepdims=True).squeeze(2)
+        return torch.cat([h, sd.repeat(group, 1, H, W)], 1)
+
+    outs = []
+    for fn in (reference, lambda t: SF.minibatch_stddev(t, group)):
+        h = h0.clone().requires_grad_(True)
+        y = fn(h)
+        g1, = torch.autograd.grad((y * wgt).sum() + (y[:, C] ** 2).sum(), h, create_graph=True)
+        pen = g1.pow(2).sum()
+        g2, = torch.autograd.grad(pen, h)
+        outs.append((y.detach(), g1.detach(), g2.detach()))
+    for a, b, name in zip(outs[1], outs[0], ("forward", "gradient", "double backward")):
+        err = K.rel_err(K.t2n(a), K.t2n(b))
+        print("minibatch stddev %s: %.2e" % (name, err))
+        assert err < 1e-5, name
+
+
+def test_only_data_grads_context_leaves_r1_unchanged():
+    """R1 computed with the weight-gradient slots of the create_graph pass switched off (functional.only_data_grads) equals R1
+    computed with them: same penalty, same parameter gradients."""
+    import spgan_b200.functional as SF
+    from spgan_b200.discriminator import Discriminator
+    from spgan_b200 import training
+    torch.manual_seed(5)
+    D = Discriminator().cuda().train()
+    x0 = torch.randn(4, 3, 101, 101, device="cuda").clamp_(-1, 1)
+    res = []
+    for use_ctx in (True, False):
+        x = x0.clone().requires_grad_(True)
+        pred = D(x)["d_patch"]
+        if use_ctx:
+            r1 = training.d_r1_loss(pred, x)
+        else:
+            g, = torch.autograd.grad(outputs=pred.sum(), inputs=x, create_graph=True)
+            r1 = g.pow(2).reshape(g.shape[0], -1).sum(1).mean()
+        D.zero_grad(set_to_none=True)
+        r1.backward()
+        res.append((r1.detach().clone(), [p.grad.detach().clone() for p in D.parameters() if p.grad is not None]))
+    assert not SF._ONLY_DATA_GRADS
+    assert torch.equal(res[0][0], res[1][0])
+    assert len(res[0][1]) == len(res[1][1]) > 0
+    for a, b in zip(res[0][1], res[1][1]):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-6 * float(b.abs().max()))
