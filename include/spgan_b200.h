@@ -332,6 +332,24 @@ int spgan_upblur_pack(uint16_t* out, const float* pp, const float* kernel, const
  * part (slots, batch, rgb_n, plane) from spgan_conv_gemm_ex; bias (rgb_n) and skip (batch, rgb_n, plane) may be NULL. */
 int spgan_rgb_tail(float* out, const float* part, int slots, const float* bias, const float* skip, int64_t batch, int rgb_n,
                    int64_t plane, void* stream);
+/* ---- mapping network and modulation chain --------------------------------------------------------------
+ * spgan_mapping_chain: PixelNorm (models/ops.py:13-20) + n_layers x [EqualLinear 512 -> 512 + fused leaky-ReLU] (models/spgan/
+ *   spgan.py:405-412, models/ops.py:190-222) in ONE kernel: a cluster of 8 CTAs per 8 latent rows, activations exchanged through
+ *   distributed shared memory.  z (B rows, z_stride floats apart, 512 wide) -> out (B, 512).  weights / biases: HOST arrays of
+ *   n_layers device pointers ((512, 512) and (512) or NULL).  y = lrelu(x (W w_scale)^T + b b_scale, alpha) * gain per layer.
+ * spgan_modulation_batch: the modulation s = EqualLinear(style) and demodulation d = rsqrt(c_scale^2 sum_c s^2 sum_t W^2 + eps)
+ *   (models/ops.py:598-604) of EVERY modulated conv of the generator in one launch.  `layers`: DEVICE array of n_layers records
+ *   of spgan_modulation_layer_bytes() bytes: {const float* wm (Cin, 512); const float* bm (Cin) or NULL; const float* wsq
+ *   (Cout, Cin) = sum over taps of W^2, or NULL for no demodulation; int64 s_off, d_off (float offsets into out of s (B, Cin)
+ *   and d (B, Cout)); int32 Cin, Cout, style_sel, style_idx; float m_scale, m_lr_mul, c_scale, eps}.  style_sel 0 reads
+ *   styles[b*styles_bstride + style_idx*512 + k], style_sel 1 reads gl[b*gl_bstride + k].  Cin <= 520. */
+int spgan_mapping_chain(float* out, const float* z, int64_t z_stride, int B, const float* const* weights,
+                        const float* const* biases, int n_layers, float w_scale, float b_scale, float alpha, float gain,
+                        void* stream);
+int spgan_modulation_layer_bytes(void);
+int spgan_modulation_batch(float* out, const void* layers, int n_layers, const float* styles, int64_t styles_bstride,
+                           const float* gl, int64_t gl_bstride, int B, void* stream);
+
 /* ---- training-loop tails ------------------------------------------------------------------------------
  * spgan_ema_multi: the EMA `accumulate` of utils.py:86-94 over ALL parameters in one launch: table is a DEVICE array of
  *   nchunks records {float* dst; const float* src; int64_t n} (24 bytes each, n <= spgan_ema_chunk_elems()), one CTA per

@@ -4,7 +4,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["error.cu", "bias_act.cu", "upfirdn2d.cu", "sphere_gather.cu", "linear.cu", "conv_fp32.cu", "conv_umma.cu", "conv_wgrad_umma.cu", "chain.cu", "sphere_umma.cu", "grid_sample.cu", "structure.cu", "multi_tensor.cu"]
+SOURCES = ["error.cu", "bias_act.cu", "upfirdn2d.cu", "sphere_gather.cu", "linear.cu", "conv_fp32.cu", "conv_umma.cu", "conv_wgrad_umma.cu", "chain.cu", "sphere_umma.cu", "grid_sample.cu", "structure.cu", "multi_tensor.cu", "style_chain.cu"]
 OUT = os.path.join(HERE, "libspgan_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",

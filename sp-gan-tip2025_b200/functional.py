@@ -1474,3 +1474,48 @@ def minibatch_stddev(h, group, eps=1e-8):
     if h.shape[0] % group:
         raise RuntimeError("minibatch_stddev: batch %d is not a multiple of the group %d" % (h.shape[0], group))
     return _MinibatchStddevFn.apply(h, int(group), float(eps))
+
+
+# =================================================================================================== style chain (f3)
+def mapping_chain(z, weights, biases, w_scale, b_scale, alpha=0.2, gain=2 ** 0.5):
+    """PixelNorm + len(weights) x (EqualLinear 512 -> 512 + fused leaky-ReLU) in one launch (csrc/style_chain.cu).  z: (B, 512)
+    fp32, possibly a strided view (rows z.stride(0) floats apart, unit inner stride).  No autograd."""
+    _check_cuda(z, "mapping_chain")
+    if z.dim() != 2 or z.shape[1] != 512 or z.stride(1) != 1:
+        raise RuntimeError("mapping_chain: z must be (B, 512) with unit inner stride, got %s / %s" % (tuple(z.shape), z.stride()))
+    B = z.shape[0]
+    n = len(weights)
+    out = torch.empty((B, 512), device=z.device, dtype=torch.float32)
+    wp = (ctypes.c_void_p * n)(*[w.data_ptr() for w in weights])
+    bp = (ctypes.c_void_p * n)(*[(b.data_ptr() if b is not None else None) for b in biases])
+    with torch.cuda.device(z.device):
+        lib.call("spgan_mapping_chain", _ptr(out), _ptr(z), int(z.stride(0)), B, wp, bp, n, float(w_scale), float(b_scale),
+                 float(alpha), float(gain), _stream(z))
+    return out
+
+
+_MOD_RECORD = "<QQQqqiiiiffff"
+
+
+def modulation_table(records, device):
+    """Device table for spgan_modulation_batch from a list of dicts (wm, bm, wsq tensors or None; s_off, d_off, Cin, Cout,
+    style_sel, style_idx, m_scale, m_lr_mul, c_scale, eps)."""
+    import struct
+    size = int(lib.load().spgan_modulation_layer_bytes())
+    if struct.calcsize(_MOD_RECORD) != size:
+        raise RuntimeError("modulation_table: record layout mismatch (%d != %d bytes)" % (struct.calcsize(_MOD_RECORD), size))
+    blob = b"".join(struct.pack(_MOD_RECORD, r["wm"].data_ptr(), r["bm"].data_ptr() if r["bm"] is not None else 0,
+                                r["wsq"].data_ptr() if r["wsq"] is not None else 0, r["s_off"], r["d_off"], r["Cin"], r["Cout"],
+                                r["style_sel"], r["style_idx"], r["m_scale"], r["m_lr_mul"], r["c_scale"], r["eps"]) for r in records)
+    return torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(device)
+
+
+def modulation_batch(table, n_layers, total_floats, styles, gl, B):
+    """One launch for the (modulation, demodulation) pairs of every layer in `table`; returns the flat fp32 buffer."""
+    ref = styles if styles is not None else gl
+    out = torch.empty((int(total_floats),), device=ref.device, dtype=torch.float32)
+    with torch.cuda.device(ref.device):
+        lib.call("spgan_modulation_batch", _ptr(out), _ptr(table), int(n_layers), _ptr(styles),
+                 int(styles.stride(0)) if styles is not None else 0, _ptr(gl), int(gl.stride(0)) if gl is not None else 0, int(B),
+                 _stream(ref))
+    return out

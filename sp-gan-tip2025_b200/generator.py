@@ -265,22 +265,36 @@ class TextureSynthesizer(nn.Module):
             sizes.append(in_spatial_size)
         return sizes if return_list else sizes[-1]
 
+    use_fused_mapping = True
+
+    def _map(self, z):
+        """The mapping network on (B, 512) latents.  no_grad on the GPU: PixelNorm + the 8 EqualLinear / leaky-ReLU layers
+        as ONE cluster kernel (csrc/style_chain.cu); otherwise the module-by-module path (autograd)."""
+        lin = [m for m in self.mapping if isinstance(m, ops.EqualLinear)]
+        if (self.use_fused_mapping and z.is_cuda and z.dim() == 2 and z.shape[1] == 512 and z.stride(1) == 1 and len(lin) <= 16
+                and isinstance(self.mapping[0], ops.PixelNorm) and len(lin) == len(self.mapping) - 1
+                and all(m.activation and tuple(m.weight.shape) == (512, 512) and m.scale == lin[0].scale and m.lr_mul == lin[0].lr_mul
+                        for m in lin)
+                and not ops._grad_needed(z, *self.mapping.parameters())):
+            return SF.mapping_chain(z, [m.weight for m in lin], [m.bias for m in lin], lin[0].scale, lin[0].lr_mul)
+        return self.mapping(z)
+
     def get_style(self, global_latent):
-        return self.mapping(global_latent)
+        return self._map(global_latent)
 
     def styles_for(self, global_latent, inject_index=None, inject_mask=None):
         """global_latent (B, 2, 512) -> (B, n_latent, 512) w-space styles with style mixing at `inject_index`
         (models/spgan/spgan.py:843-876).  `inject_mask` (n_latent,) is the same choice as a device tensor (1 = first
         latent, 0 = second): lets a captured CUDA graph mix at a different index on every replay."""
         if inject_mask is not None:
-            w0 = self.mapping(global_latent[:, 0])
-            w1 = self.mapping(global_latent[:, 1])
+            w0 = self._map(global_latent[:, 0])
+            w1 = self._map(global_latent[:, 1])
             m = inject_mask.view(1, self.n_latent, 1)
             return w0.unsqueeze(1) * m + w1.unsqueeze(1) * (1 - m)
-        w0 = self.mapping(global_latent[:, 0])
+        w0 = self._map(global_latent[:, 0])
         if inject_index is None or inject_index >= self.n_latent:
             return w0.unsqueeze(1).repeat(1, self.n_latent, 1)
-        w1 = self.mapping(global_latent[:, 1])
+        w1 = self._map(global_latent[:, 1])
         return torch.cat([w0.unsqueeze(1).repeat(1, inject_index, 1),
                           w1.unsqueeze(1).repeat(1, self.n_latent - inject_index, 1)], 1)
 
@@ -433,6 +447,66 @@ class Generator(nn.Module):
         self.structure_synthesizer = StructureSynthesizer(self.config)
         self.texture_synthesizer = TextureSynthesizer(self.config)
 
+    use_fused_modulation = True
+
+    def _modulated_layers(self):
+        """(module, latent source, style index) of every modulated conv, in execution order: the structure synthesiser's convs
+        read the RAW global latent (column 0), texture conv i reads styles[:, i], ToRGB k reads styles[:, TO_RGBS[k][1]]."""
+        ts = self.texture_synthesizer
+        out = [(blk.conv.conv, 1, 0) for blk in self.structure_synthesizer.implicit_model.conv_stack]
+        out += [(conv.conv, 0, i) for i, conv in enumerate(ts.convs)]
+        out += [(rgb.conv, 0, ts.TO_RGBS[k][1]) for k, rgb in enumerate(ts.to_rgbs)]
+        return out
+
+    @torch.no_grad()
+    def prepare_modulation(self, global_latent, styles):
+        """Compute the (modulation, demodulation) pair of EVERY modulated conv for these latents in ONE launch
+        (spgan_modulation_batch) and seed each module's memo with it, so that the per-layer
+        `_mod_demod` calls of the following generator forwards are hits.  global_latent (B, 2, 512), styles (B, n_latent, 512).
+        Returns False (and does nothing) when the configuration is outside the fused kernel's reach."""
+        if not self.use_fused_modulation or not styles.is_cuda or global_latent.dim() != 3 or styles.dim() != 3:
+            return False
+        if styles.stride(2) != 1 or styles.stride(1) != 512 or global_latent.stride(2) != 1:
+            return False
+        layers = self._modulated_layers()
+        if any(m.in_channel > 520 or m.modulation is None or tuple(m.modulation.weight.shape) != (m.in_channel, 512)
+               for m, _, _ in layers):
+            return False
+        if ops._grad_needed(global_latent, styles, *self.parameters()):
+            return False
+        B = styles.shape[0]
+        views = [(global_latent[:, 0] if sel else styles[:, idx]) for _, sel, idx in layers]
+        keys = [m._md_key(v) for (m, _, _), v in zip(layers, views)]
+        if all(k in m.__dict__.get("_md_cache", {}) for (m, _, _), k in zip(layers, keys)):
+            return True
+        tkey = (B, SF.epoch()[0]) + tuple(k[6:] for k in keys)
+        tables = self.__dict__.setdefault("_mod_tables", {})  # one per batch size (position-group sizes of a panorama engine)
+        hit = tables.get(tkey)
+        if hit is None:
+            if torch.cuda.is_current_stream_capturing():
+                return False  # the table upload cannot be captured: the per-layer path computes the pairs instead
+            recs, off = [], 0
+            for m, sel, idx in layers:
+                r = dict(wm=m.modulation.weight, bm=m.modulation.bias, wsq=m.weight_sq() if m.demodulate else None, s_off=off,
+                         Cin=m.in_channel, Cout=m.out_channel, style_sel=sel, style_idx=idx, m_scale=m.modulation.scale,
+                         m_lr_mul=m.modulation.lr_mul, c_scale=m.scale, eps=1e-8)
+                off = -(-(off + B * m.in_channel) // 64) * 64  # every slice starts 256-byte aligned: consumers use 128-bit loads
+                r["d_off"] = off
+                if m.demodulate:
+                    off = -(-(off + B * m.out_channel) // 64) * 64
+                recs.append(r)
+            hit = (tkey, SF.modulation_table(recs, styles.device), recs, off)
+            while len(tables) >= 8:
+                del tables[next(iter(tables))]
+            tables[tkey] = hit
+        _, table, recs, total = hit
+        buf = SF.modulation_batch(table, len(recs), total, styles, global_latent, B)
+        for (m, _, _), v, k, r in zip(layers, views, keys, recs):
+            s_ = buf[r["s_off"]:r["s_off"] + B * r["Cin"]].view(B, r["Cin"])
+            d_ = buf[r["d_off"]:r["d_off"] + B * r["Cout"]].view(B, r["Cout"]) if m.demodulate else None
+            m._md_store(k, v, s_, d_)
+        return True
+
     def forward(self, global_latent, local_latent, coords, coords_partial, noises=None, inject_index=None,
                 test_ids=None, return_latents=False, styles=None):
         """`styles` (B, 9, 512): optional precomputed w-space styles (`texture_synthesizer.styles_for`); the panorama
@@ -443,10 +517,12 @@ class Generator(nn.Module):
         if styles is None and inject_index is None and self.training and self.config.train_params.mixing > 0:
             if random.random() < self.config.train_params.mixing:  # models/spgan/spgan.py:865-869
                 inject_index = random.randint(1, ts.n_latent - 1)
-        structure, _ = self.structure_synthesizer(global_latent[:, 0], local_latent, coords, coords_partial,
-                                                  test_ids=test_ids)
         if styles is None:
             styles = ts.styles_for(global_latent, inject_index)
+        if not torch.is_grad_enabled() and not self.training:
+            self.prepare_modulation(global_latent, styles)  # one launch; no-op when the memo already holds these latents
+        structure, _ = self.structure_synthesizer(global_latent[:, 0], local_latent, coords, coords_partial,
+                                                  test_ids=test_ids)
         img, _ = ts(styles, structure, coords_partial, noises=noises, test_ids=test_ids)
         if return_latents:
             return img, styles, structure

@@ -97,6 +97,9 @@ SIGNATURES = {
     "spgan_rgb_tail": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp, c_i64, c_int, c_i64, c_vp]),
     "spgan_gemm_launch_count": (c_i64, []),
     "spgan_set_option": (c_int, [c_int, c_int]),
+    "spgan_mapping_chain": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_int, c_f32, c_f32, c_f32, c_f32, c_vp]),
+    "spgan_modulation_layer_bytes": (c_int, []),
+    "spgan_modulation_batch": (c_int, [c_vp, c_vp, c_int, c_vp, c_i64, c_vp, c_i64, c_int, c_vp]),
     "spgan_ema_chunk_elems": (c_int, []),
     "spgan_ema_multi": (c_int, [c_vp, c_int, c_f32, c_f32, c_vp]),
     "spgan_minibatch_stddev": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_f32, c_vp]),

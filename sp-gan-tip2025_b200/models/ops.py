@@ -386,16 +386,26 @@ class ModulatedConv2d(nn.Module):
                 wsq = (w * w).sum(dim=(2, 3))
                 d = torch.rsqrt(SF._LinearFn.apply(s * s, wsq, None, self.scale * self.scale, 1.0) + 1e-8)
             return s, w, d
-        key = (SF.epoch(), style.data_ptr(), style._version, tuple(style.shape), tuple(style.stride()), str(style.device),
-               self.weight._version, self.modulation.weight._version,
-               self.modulation.bias._version if self.modulation.bias is not None else -1,
-               self.weight.data_ptr(), self.modulation.weight.data_ptr())
+        key = self._md_key(style)
         cache = self.__dict__.setdefault("_md_cache", {})
         cached = cache.get(key)
         if cached is not None:
             return cached[1], w, cached[2]
         s = self.modulation(style).view(batch, self.in_channel)
         d = SF.demod_coefficients(w, s, self.scale, 1e-8) if self.demodulate else None
+        self._md_store(key, style, s, d)
+        return s, w, d
+
+    def _md_key(self, style):
+        return (SF.epoch(), style.data_ptr(), style._version, tuple(style.shape), tuple(style.stride()), str(style.device),
+                self.weight._version, self.modulation.weight._version,
+                self.modulation.bias._version if self.modulation.bias is not None else -1,
+                self.weight.data_ptr(), self.modulation.weight.data_ptr())
+
+    def _md_store(self, key, style, s, d):
+        """Memoise a (modulation, demodulation) pair for `style` (also used by Generator.prepare_modulation, which computes the
+        pairs of all layers in one launch)."""
+        cache = self.__dict__.setdefault("_md_cache", {})
         # several live styles per module (one per position-group size of a panorama engine); entries of an older epoch are
         # dead.  Never evict a live entry: a concurrent branch of a captured graph may only READ what the launching stream
         # computed before the fork (panorama.PanoramaEngine._body)
@@ -404,7 +414,17 @@ class ModulatedConv2d(nn.Module):
         while len(cache) >= 16:
             del cache[next(iter(cache))]  # oldest first
         cache[key] = (style, s, d)
-        return s, w, d
+
+    def weight_sq(self):
+        """(Cout, Cin) sum over the taps of W^2 (the demodulation's weight factor, models/ops.py:603), cached per weight version."""
+        w = self.weight[0]
+        key = (SF.epoch()[0], self.weight._version, self.weight.data_ptr())
+        hit = self.__dict__.get("_wsq_cache")
+        if hit is None or hit[0] != key:
+            with torch.no_grad():
+                hit = (key, (w * w).sum(dim=(2, 3)).contiguous())
+            self.__dict__["_wsq_cache"] = hit
+        return hit[1]
 
     def forward(self, input, style, coords=None, calc_flops=False):
         batch = input.shape[0]

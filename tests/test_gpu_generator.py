@@ -279,3 +279,43 @@ def test_panorama_engine_position_groups(gen, group, streams, graph):
         # the GEMM rows are bit-identical; only the ToRGB partial sums are added in a different order (N-tile count)
         assert err < 2e-6, seed
     assert (eng.graph is not None) == graph
+
+
+def test_fused_mapping_and_modulation_match_per_layer_path(gen):
+    """the mapping network as one cluster kernel and the (modulation, demodulation) pairs of all 20 modulated
+    convs as one launch against the module-by-module path (8 + 40 launches): styles, every pair, and the generator output."""
+    from spgan_b200.generator import Generator, TextureSynthesizer
+    gl, lat, coords, cp, noises = K.generator_case("b2_p59", 2, 5, 9)
+    gl, lat, coords = gl.cuda(), lat.cuda(), coords.cuda()
+    nz = [n.cuda() for n in noises]
+    ts = gen.texture_synthesizer
+    with torch.no_grad():
+        TextureSynthesizer.use_fused_mapping = False
+        Generator.use_fused_modulation = False
+        try:
+            styles_ref = ts.styles_for(gl)
+            pairs_ref = [m._mod_demod(gl[:, 0] if sel else styles_ref[:, idx], 2) for m, sel, idx in gen._modulated_layers()]
+            img_ref = gen(gl, lat, coords, cp, noises=nz, styles=styles_ref)
+        finally:
+            TextureSynthesizer.use_fused_mapping = True
+            Generator.use_fused_modulation = True
+        styles = ts.styles_for(gl)
+        assert K.rel_err(K.t2n(styles), K.t2n(styles_ref)) < 2e-6
+        gl2 = gl.clone()  # fresh storage: no memo entry yet
+        launches = SF_launches()
+        assert gen.prepare_modulation(gl2, styles)
+        assert SF_launches() == launches + 1
+        for (m, sel, idx), (s_ref, _, d_ref) in zip(gen._modulated_layers(), pairs_ref):
+            s, _, d = m._mod_demod(gl2[:, 0] if sel else styles[:, idx], 2)
+            assert K.rel_err(K.t2n(s), K.t2n(s_ref)) < 5e-6
+            assert (d is None) == (d_ref is None)
+            if d is not None:
+                assert K.rel_err(K.t2n(d), K.t2n(d_ref)) < 5e-6
+        assert SF_launches() == launches + 1  # every pair came from the memo
+        img = gen(gl2, lat, coords, cp, noises=nz, styles=styles)
+    assert K.rel_err(K.t2n(img), K.t2n(img_ref)) < 2e-5
+
+
+def SF_launches():
+    import spgan_b200.lib as lib
+    return lib.launches()
