@@ -17,6 +17,7 @@ sys.path.insert(0, ROOT)
 
 import torch
 
+from bench import ClockSampler
 import spgan_b200.functional as SF
 import spgan_b200.lib as lib
 from spgan_b200 import grids, panorama
@@ -25,6 +26,8 @@ from spgan_b200 import grids, panorama
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--budget-s", type=float, default=45.0)
+    ap.add_argument("--sweep", action="store_true", help="run the configs[4] sweep (C x H x B, forward and backward)")
+    ap.add_argument("--max-gb", type=float, default=6.0, help="skip sweep cases whose tensors exceed this many GiB")
     args = ap.parse_args()
     torch.cuda.set_device(0)
     lib.require_device()
@@ -39,16 +42,30 @@ def main():
     tf_peak = float(peaks.get("bf16_tflops_sustained", 1388.5))
     t_start = time.time()
 
-    def timed(fn, iters=5, warm=2):
+    last_clocks = {}
+
+    def timed(fn, iters=5, warm=2, min_s=0.45):
+        """ms per call (CUDA events); the loop runs for at least `min_s` so that the nvidia-smi clock sampler (200 ms period)
+        sees the kernel under load — the record lands in the case's JSON line."""
         for _ in range(warm):
             fn()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        one = max(e0.elapsed_time(e1), 1e-3)
+        iters = max(iters, min(2000, int(min_s * 1e3 / one) + 1))
+        sampler = ClockSampler(0)
+        sampler.start()
+        e0.record()
         for _ in range(iters):
             fn()
         e1.record()
         torch.cuda.synchronize()
+        last_clocks.clear()
+        last_clocks.update(sampler.stop())
         return e0.elapsed_time(e1) / iters
 
     def report(name, ms, bytes_=None, flops=None, **kw):
@@ -62,6 +79,7 @@ def main():
             out.update(bound="tensor", algorithmic_GFLOP=round(flops / 1e9, 2), achieved_TFs=round(tfs, 1), peak_TFs=tf_peak,
                        frac=round(tfs / tf_peak, 3))
         out.update(kw)
+        out["clocks"] = dict(last_clocks)
         print(json.dumps(out), flush=True)
 
     def case(name, build):
@@ -72,7 +90,10 @@ def main():
             with torch.no_grad():
                 build()
         except Exception as e:  # keep sweeping
-            print(json.dumps({"case": name, "error": "%s: %s" % (type(e).__name__, str(e)[:200])}), flush=True)
+            if str(e).startswith("skipped:"):
+                print(json.dumps({"case": name, "skipped": str(e)[9:]}), flush=True)
+            else:
+                print(json.dumps({"case": name, "error": "%s: %s" % (type(e).__name__, str(e)[:200])}), flush=True)
         torch.cuda.empty_cache()
 
     g = torch.Generator(device=dev).manual_seed(1)
@@ -81,6 +102,9 @@ def main():
     k3 = torch.tensor([[1., 2., 1.], [2., 4., 2.], [1., 2., 1.]], device=dev) / 16 * 4
     k4 = torch.tensor([1., 3., 3., 1.], device=dev)
     k4 = (k4[None, :] * k4[:, None]) / 64
+
+    pl = panorama.plan(384, 768)
+    cp, _ = panorama.patch_inputs(pl, 2, 7, 27, pl["lat_h"], pl["lat_w"])
 
     # ---- K1 bias + activation (models/custom_ops/fused_bias_act_kernel.cu) ----
     def bias_act_fwd():
@@ -128,10 +152,35 @@ def main():
                bytes_=4 * 32 * 512 * (4 * 53 * 53 + 103 * 103))
     case("upblur_act", upblur)
 
-    # ---- L1 spherical gather (F.grid_sample in the reference) ----
-    pl = panorama.plan(384, 768)
-    cp, _ = panorama.patch_inputs(pl, 2, 7, 27, pl["lat_h"], pl["lat_w"])
+    def upblur_pack():
+        pp, nz, nw, b = rn(64, 4, 53, 53, 512), rn(64, 1, 103, 103), torch.tensor([0.3], device=dev), rn(512)
+        mul = rn(64, 512)
+        ms = timed(lambda: SF.chain_upblur_pack(pp, (105, 105), k3, nz, nw, b, mul, 1))
+        report("upblur_pack (channels-last planes -> FIR + noise + bias + act -> packed bf16 hi/lo) -> (64,103,103,512)", ms,
+               bytes_=4 * 64 * 512 * (105 * 105 + 103 * 103))
+    case("upblur_pack", upblur_pack)
 
+    def sphere_pack_seg():
+        B, Bg, C, H = 64, 32, 256, 35
+        x, c, s = rn(B, C, H, H), rn(B, 3, H, H), rn(B, C + 3)
+        w = rn(256, C + 3, 3, 3)
+        d = rn(B, 256).abs() + 0.5
+        cp2, _ = panorama.patch_inputs(pl, 2, 8, 28, pl["lat_h"], pl["lat_w"])
+        grid = grids.GRID_CACHE.group_grid(H, H, [cp, cp2], dev)
+        xh, _ = SF.ss_input(x, 1)
+        y_sc, nm = torch.zeros(B, H, H, 256, device=dev), torch.ones(B, 256, device=dev)
+        SF.profile_calls(True)
+        for _ in range(12):
+            SF.ss_sphere(xh, c, grid, Bg, w, s, d, 0.02, (0.01, 1.0), y_sc, nm, 1)
+        t = SF.profile_calls(False)
+        ms = t["spgan_sphere_pack_seg"][0] / t["spgan_sphere_pack_seg"][1]
+        report("sphere_pack_seg (concat repack + vectorised gather producer) (64,256+3,35,35) -> [9*256 | 64] bf16 hi/lo", ms,
+               bytes_=4.0 * B * H * H * (9 * 256 + 64) + 4.0 * B * H * H * 259)
+        ms = t["spgan_conv_gemm_ex"][0] / t["spgan_conv_gemm_ex"][1]
+        report("spherical GEMM K = 9*256 + 64 (64,35,35) -> 256", ms, flops=2.0 * B * H * H * 256 * 259 * 9)
+    case("sphere_pack_seg", sphere_pack_seg)
+
+    # ---- L1 spherical gather (F.grid_sample in the reference) ----
     def gather():
         z = rn(32, 256, 35, 35)
         grid = torch.from_numpy(grids.sampling_grid(35, 35, cp)).to(dev)
@@ -150,20 +199,74 @@ def main():
         report("pack_act (32,512,103,103) -> bf16 hi/lo channels-last", ms, bytes_=4 * x.numel() + out.numel() * 2)
     case("pack_act", pack)
 
-    # ---- fused spherical modulated conv sweep (gather + encode + modulate + tcgen05 GEMM) ----
-    for C in (64, 128, 256, 512):
-        for H in (32, 64, 128):
-            B = 8
+    # ---- BASELINE configs[4] / SURVEY §8(d)5: C in {64..512} x H in {32..384} x B in {1, 8, 32}, forward and backward, for the
+    # spherical modulated conv, upfirdn2d (G blur 3x3 / D blur 4x4 / up 2 / down 2) and bias-act.  Cases whose tensors exceed
+    # `--max-gb` are reported as skipped (the autograd path of the spherical conv holds the 9x gathered tensor, as the
+    # reference does); the time budget cuts the tail of the sweep, largest shapes first within each (C, B).
+    max_bytes = args.max_gb * 2 ** 30
 
-            def sph(C=C, H=H, B=B):
-                x, c = rn(B, C, H, H), rn(B, 3, H, H)
-                w = rn(C, C + 3, 3, 3)
-                s, d = rn(B, C + 3), rn(B, C).abs() + 0.5
-                cpm = dict(cp)
-                grid = torch.from_numpy(grids.sampling_grid(H, H, cpm)).to(dev)
-                ms = timed(lambda: SF.sphere_modconv_fused(x, c, grid, w, s, d, 0.05, act=(0.01, 1.0), precision=1), iters=3, warm=1)
-                report("sphere_modconv fused fwd B=%d C=%d H=%d" % (B, C, H), ms, flops=2.0 * B * H * H * C * (C + 3) * 9)
-            case("sphere_modconv C=%d H=%d" % (C, H), sph)
+    def sph_case(B, C, H):
+        def run():
+            if 4.0 * B * C * H * H * 9 * 3 > max_bytes:
+                raise RuntimeError("skipped: tensors exceed --max-gb")
+            x, c = rn(B, C, H, H), rn(B, 3, H, H)
+            w = rn(C, C + 3, 3, 3)
+            s, d = rn(B, C + 3), rn(B, C).abs() + 0.5
+            grid = torch.from_numpy(grids.sampling_grid(H, H, dict(cp))).to(dev)
+            fl = 2.0 * B * H * H * C * (C + 3) * 9
+            ms = timed(lambda: SF.sphere_modconv_fused(x, c, grid, w, s, d, 0.05, act=(0.01, 1.0), precision=1), iters=3, warm=1)
+            report("sphere_modconv fwd B=%d C=%d H=%d" % (B, C, H), ms, flops=fl)
+            with torch.enable_grad():
+                xg, wg = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+
+                def fb():
+                    y = SF.sphere_modconv(xg, c, grid, wg, s, d, 0.05)
+                    gx, gw = torch.autograd.grad(y.sum(), [xg, wg])
+                    return gx
+                ms = timed(fb, iters=2, warm=1, min_s=0.3)
+            report("sphere_modconv fwd+bwd (dX, dW) B=%d C=%d H=%d" % (B, C, H), ms, flops=3 * fl)
+        case("sphere_modconv B=%d C=%d H=%d" % (B, C, H), run)
+
+    def fir_case(B, C, H, name, kern, up, down, pad):
+        def run():
+            if 4.0 * B * C * H * H * (up * up + 1) * 2 > max_bytes:
+                raise RuntimeError("skipped: tensors exceed --max-gb")
+            x = rn(B, C, H, H)
+            y = SF.upfirdn2d(x, kern, up=up, down=down, pad=pad)
+            by = 4.0 * (x.numel() + y.numel())
+            ms = timed(lambda: SF.upfirdn2d(x, kern, up=up, down=down, pad=pad))
+            report("upfirdn2d %s fwd B=%d C=%d H=%d" % (name, B, C, H), ms, bytes_=by)
+            with torch.enable_grad():
+                xg = x.clone().requires_grad_(True)
+                yy = SF.upfirdn2d(xg, kern, up=up, down=down, pad=pad)
+                go = torch.ones_like(yy)
+                ms = timed(lambda: torch.autograd.grad(yy, xg, go, retain_graph=True))
+            report("upfirdn2d %s bwd B=%d C=%d H=%d" % (name, B, C, H), ms, bytes_=by)
+        case("upfirdn2d %s B=%d C=%d H=%d" % (name, B, C, H), run)
+
+    def act_case(B, C, H):
+        def run():
+            if 4.0 * B * C * H * H * 3 > max_bytes:
+                raise RuntimeError("skipped: tensors exceed --max-gb")
+            x, b = rn(B, C, H, H), rn(C)
+            ms = timed(lambda: SF.bias_act(x, b, None, 3, 0, 0.2, SQ2))
+            report("bias_act fwd B=%d C=%d H=%d" % (B, C, H), ms, bytes_=2 * 4.0 * x.numel())
+            go = rn(B, C, H, H)
+            ms = timed(lambda: SF.FusedLeakyReLUFunctionBackward.apply(go, x, 0.2, SQ2))
+            report("bias_act bwd + bias reduction B=%d C=%d H=%d" % (B, C, H), ms, bytes_=3 * 4.0 * x.numel())
+        case("bias_act B=%d C=%d H=%d" % (B, C, H), run)
+
+    for B in (32, 8, 1):
+        for C in (512, 256, 128, 64):
+            for H in (384, 256, 128, 64, 32):
+                if not args.sweep:
+                    continue
+                act_case(B, C, H)
+                fir_case(B, C, H, "3x3 pad0", k3, 1, 1, (0, 0))
+                fir_case(B, C, H, "4x4 pad2", k4, 1, 1, (2, 2))
+                fir_case(B, C, H, "up2 4x4", k4 * 4, 2, 1, (2, 1))
+                fir_case(B, C, H, "down2 4x4", k4, 1, 2, (1, 1))
+                sph_case(B, C, H)
 
     # ---- plain modulated 3x3 conv fwd / data gradient / weight gradient at the largest layer ----
     def conv_big():
