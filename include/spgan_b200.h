@@ -160,7 +160,9 @@ int spgan_demod(float* d, const float* s, const float* w, int B, int Cin, int Co
 
 /* Weight gradient of a conv pass: dw[o*ws_o + c*ws_c + tap_w[t]] (+)= sum_b sum_ij
  *   g[b,o,Y,X] * out_mul[b,o] * out_scale * in_mul[b,c] * x[b,c,i*in_stride+dy_t, j*in_stride+dx_t].
- * Replaces cuDNN wgrad of the same F.conv2d / F.conv_transpose2d calls.  accumulate != 0 adds into dw. */
+ * Replaces cuDNN wgrad of the same F.conv2d / F.conv_transpose2d calls.  accumulate != 0 adds into dw.  Partial sums over the
+ * batch and over pixel splits are combined with atomicAdd: results are reproducible to fp32 rounding, not bit for bit (the
+ * tcgen05 weight gradient below is deterministic). */
 int spgan_conv_wgrad(const SpganConvPass* p, float* dw, const float* g, const float* x, const float* in_mul,
                      const float* out_mul, int accumulate, void* stream);
 

@@ -6,7 +6,19 @@
 #include <stdarg.h>
 #include "../../include/spgan_b200.h"
 
-#define SPGAN_NUM_SMS 148  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+// SM count of the current device (B200: 2 dies x 74 = 148); grids are sized in multiples of this.  Queried once per device
+// (the library is used one process per GPU, but nothing here assumes device 0).
+static inline int spgan_num_sms() {
+  static int cache[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cache[dev] == 0) {
+    int n = 0;
+    cache[dev] = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) ? n : 148;
+  }
+  return cache[dev];
+}
+#define SPGAN_NUM_SMS spgan_num_sms()
 
 void spgan_set_error(const char* fmt, ...);
 void spgan_internal_count_gemm_launch();  // conv_umma.cu: bumps the counter behind spgan_gemm_launch_count()

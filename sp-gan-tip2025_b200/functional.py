@@ -485,32 +485,55 @@ def _fill_pass(p, B, Cin, H, W, Cout, out_H, out_W, ws_o, ws_c, out_scale, act, 
 # --------------------------------------------------------------------------------------------------- weight packing
 _WEIGHT_CACHE = OrderedDict()
 _WEIGHT_CACHE_MAX = 512
+_WEIGHT_CACHE_MAX_BYTES = 4 << 30
+_WEIGHT_CACHE_BYTES = 0
 
 
 def _round_up(a, b):
     return _ceil_div(a, b) * b
 
 
-def _packed_weight(w, Cout, Cin, ws_o, ws_c, tap_w, Cp, merged, fmt=0):
-    """16-bit hi/lo copy of the weight in [2][ntaps][Cout][Cp] (or merged-K) order, cached per weight version."""
-    key = (w.data_ptr(), w._version, tuple(w.shape), Cout, Cin, ws_o, ws_c, tuple(tap_w), Cp, merged, fmt, w.device.index)
+def _weight_cache_get(key, version):
     hit = _WEIGHT_CACHE.get(key)
-    if hit is not None:
+    if hit is not None and hit[2] == version:
         _WEIGHT_CACHE.move_to_end(key)
         return hit[0]
+    return None
+
+
+def _weight_cache_put(key, out, w):
+    """One entry per (weight storage, geometry): a new parameter version OVERWRITES the stale pack instead of sitting next to it
+    (eager training bumps the version every optimizer step).  Bounded by bytes as well as by entries."""
+    global _WEIGHT_CACHE_BYTES
+    old = _WEIGHT_CACHE.pop(key, None)
+    if old is not None:
+        _WEIGHT_CACHE_BYTES -= old[0].numel() * old[0].element_size()
+    _WEIGHT_CACHE[key] = (out, w, w._version)  # keep `w` alive so the data_ptr cannot be recycled while the entry exists
+    _WEIGHT_CACHE_BYTES += out.numel() * out.element_size()
+    while _WEIGHT_CACHE and (len(_WEIGHT_CACHE) > _WEIGHT_CACHE_MAX or _WEIGHT_CACHE_BYTES > _WEIGHT_CACHE_MAX_BYTES):
+        _, ev = _WEIGHT_CACHE.popitem(last=False)
+        _WEIGHT_CACHE_BYTES -= ev[0].numel() * ev[0].element_size()
+
+
+def _packed_weight(w, Cout, Cin, ws_o, ws_c, tap_w, Cp, merged, fmt=0):
+    """16-bit hi/lo copy of the weight in [2][ntaps][Cout][Cp] (or merged-K) order, cached per weight version."""
+    key = (w.data_ptr(), tuple(w.shape), Cout, Cin, ws_o, ws_c, tuple(tap_w), Cp, merged, fmt, w.device.index)
+    hit = _weight_cache_get(key, w._version)
+    if hit is not None:
+        return hit
     ntaps = len(tap_w)
     out = torch.empty((2, ntaps, Cout, Cp), device=w.device, dtype=torch.bfloat16)
     arr = (ctypes.c_int32 * ntaps)(*tap_w)
     with torch.cuda.device(w.device):
         lib.call("spgan_pack_weight", _ptr(out), _ptr(w), Cout, Cin, ws_o, ws_c, ntaps, arr, Cp, int(merged), int(fmt), _stream(w))
-    _WEIGHT_CACHE[key] = (out, w)  # keep `w` alive so the data_ptr cannot be recycled while the entry exists
-    if len(_WEIGHT_CACHE) > _WEIGHT_CACHE_MAX:
-        _WEIGHT_CACHE.popitem(last=False)
+    _weight_cache_put(key, out, w)
     return out
 
 
 def clear_weight_cache():
+    global _WEIGHT_CACHE_BYTES
     _WEIGHT_CACHE.clear()
+    _WEIGHT_CACHE_BYTES = 0
 
 
 _EPOCH = 0
@@ -550,7 +573,7 @@ def bump_epoch():
     the training step calls this after every replay and before every capture."""
     global _EPOCH
     _EPOCH += 1
-    _WEIGHT_CACHE.clear()
+    clear_weight_cache()
 
 
 # --------------------------------------------------------------------------------------------------- conv driver
@@ -626,6 +649,17 @@ def conv_apply(x, w, geom, adjoint=False, out_hw=None, in_mul=None, out_mul=None
     im = _f32c(in_mul, "conv") if in_mul is not None else None
     om = _f32c(out_mul, "conv") if out_mul is not None else None
     nz = _f32c(noise, "conv") if noise is not None else None
+    if nz is not None:
+        if noise_w is None:
+            raise RuntimeError("conv: noise needs noise_w")
+        want = (B, 1, max(oh, 0), max(ow, 0))
+        if tuple(nz.shape) != want:
+            # the reference's `image + weight * noise` broadcasts: accept what broadcasts to (B, 1, oh, ow), reject the rest
+            # (the kernel indexes noise[b*oh*ow + pixel]; a smaller tensor would be read out of bounds)
+            try:
+                nz = nz.expand(want).contiguous()
+            except RuntimeError:
+                raise RuntimeError("conv: noise of shape %s does not broadcast to %s" % (tuple(nz.shape), want))
     nwt = _f32c(noise_w, "conv") if (noise is not None) else None
     bs = _f32c(bias, "conv") if bias is not None else None
     rs = _f32c(residual, "conv") if residual is not None else None
@@ -1247,11 +1281,10 @@ def _packed_weight_tail(w, c0, tap_w, kp2, fmt):
     """Second-segment weight [2][Cout][kp2], k2 = t*Cx + j <-> w[o, c0 + j, tap_w[t]]: the channels past c0 of every tap in
     one dense slab (pairs with spgan_sphere_pack_seg / spgan_coord_taps_pack).  Cached per weight version like
     _packed_weight; built with torch ops (a few KB, once per weight version)."""
-    key = ("tail", w.data_ptr(), w._version, tuple(w.shape), c0, tuple(tap_w), kp2, fmt, w.device.index)
-    hit = _WEIGHT_CACHE.get(key)
+    key = ("tail", w.data_ptr(), tuple(w.shape), c0, tuple(tap_w), kp2, fmt, w.device.index)
+    hit = _weight_cache_get(key, w._version)
     if hit is not None:
-        _WEIGHT_CACHE.move_to_end(key)
-        return hit[0]
+        return hit
     O, C = w.shape[0], w.shape[1]
     wt = w.detach().reshape(O, C, -1)[:, c0:, :][:, :, list(tap_w)]  # (O, Cx, T)
     flat = wt.permute(0, 2, 1).reshape(O, -1)
@@ -1267,9 +1300,7 @@ def _packed_weight_tail(w, c0, tap_w, kp2, fmt):
         hi = v.bfloat16()
         lo = (v - hi.float()).bfloat16()
     out = torch.stack([hi, lo]).contiguous().view(torch.bfloat16)
-    _WEIGHT_CACHE[key] = (out, w)
-    if len(_WEIGHT_CACHE) > _WEIGHT_CACHE_MAX:
-        _WEIGHT_CACHE.popitem(last=False)
+    _weight_cache_put(key, out, w)
     return out
 
 

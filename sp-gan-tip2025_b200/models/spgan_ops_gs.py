@@ -81,16 +81,7 @@ class ModulatedConv2d(norm_ops.ModulatedConv2d):
         if self.upsample:
             out, _ = norm_ops.ModulatedConv2d.forward(self, input, style)
             return out, flops
-        if self.padding != 0:
-            raise NotImplementedError("the spherical conv is only used with no_zero_pad=True (padding 0) in spgan.yaml")
-        nc = 0
-        if self.deal_coords:
-            nc = self._coord_dim()
-            if nc != 3:
-                raise NotImplementedError("coord_num_dir == %d: only the 3-channel encoding of spgan.yaml is implemented" % nc)
-            tp = self.config.train_params
-            if (hasattr(tp, "no_coord_encode_all") and tp.no_coord_encode) or (hasattr(tp, "no_coord_encode") and tp.no_coord_encode):
-                raise NotImplementedError("no_coord_encode variants are not used by spgan.yaml")
+        self._check_config()
         s, w, d = self._mod_demod(style, batch)  # in_channel already counts the coordinate planes
         self.grid_shape = (H, W)
         grid = GRID_CACHE.batch(H, W, coords_partial, batch, input.device)
@@ -99,13 +90,34 @@ class ModulatedConv2d(norm_ops.ModulatedConv2d):
             out = out[:, :, 1:-1, 1:-1]
         return out, flops
 
+    def _check_config(self):
+        """The configurations the spherical conv supports; shared by the autograd path and the fused no_grad path so that eval
+        mode cannot silently differ from train mode (models/spgan_ops_gs.py:700-760)."""
+        if self.padding != 0:
+            raise NotImplementedError("the spherical conv is only used with no_zero_pad=True (padding 0) in spgan.yaml")
+        if self.deal_coords:
+            nc = self._coord_dim()
+            if nc != 3:
+                raise NotImplementedError("coord_num_dir == %d: only the 3-channel encoding of spgan.yaml is implemented" % nc)
+            tp = self.config.train_params
+            if (hasattr(tp, "no_coord_encode_all") and tp.no_coord_encode) or (hasattr(tp, "no_coord_encode") and tp.no_coord_encode):
+                raise NotImplementedError("no_coord_encode variants are not used by spgan.yaml")
+
     def forward_fused(self, input, style, coords, coords_partial, act, residual=None):
-        """no_grad fast path: gather + encode + modulate + conv + LeakyReLU (+ residual) in two kernels."""
+        """no_grad fast path: gather + encode + modulate + conv + LeakyReLU (+ residual) in two kernels.  Same guards and
+        the same `cut_size` crop as forward(); a residual cannot be folded in when the output is cropped afterwards."""
         batch, C, H, W = input.shape
+        self._check_config()
+        crop = (not self.deal_coords) and self.cut_size
         s, w, d = self._mod_demod(style, batch)
         grid = GRID_CACHE.batch(H, W, coords_partial, batch, input.device)
-        return SF.sphere_modconv_fused(input, coords if self.deal_coords else None, grid, w, s, d, self.scale, act=act,
-                                       flat_concat=True, residual=residual)
+        out = SF.sphere_modconv_fused(input, coords if self.deal_coords else None, grid, w, s, d, self.scale, act=act,
+                                      flat_concat=True, residual=None if crop else residual)
+        if crop:
+            out = out[:, :, 1:-1, 1:-1]
+            if residual is not None:
+                out = out + residual
+        return out
 
 
 class StyledConv(nn.Module):

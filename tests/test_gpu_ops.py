@@ -738,3 +738,23 @@ def test_gemm_cta_pair_kernel_bit_identical(precision, shape):
     want = F.conv2d((x * s[:, :, None, None]).double(), w.double()) * 0.05 * d.double()[:, :, None, None]
     want = F.leaky_relu(want + 0.3 * nz.double() + bias.double().view(1, -1, 1, 1), 0.2) * 2 ** 0.5
     assert K.rel_err(K.t2n(outs[1]), K.t2n(want)) < TOL[precision]
+
+
+@pytest.mark.parametrize("M,N,K", [(1, 512, 512), (8, 259, 512), (16, 3, 512), (33, 512, 4608), (64, 1, 512), (65, 512, 512), (8, 512, 500)])
+def test_linear_small_and_general_kernels_vs_fp64(M, N, K, dev):
+    """EqualLinear forward over both kernels (the small-batch kernel: M <= 64, K % 128 == 0; the general one otherwise),
+    with and without the fused bias + leaky-ReLU epilogue."""
+    x = synth.randn_t(9, "lin_x", (M, K)).to(dev)
+    w = synth.randn_t(9, "lin_w", (N, K)).to(dev)
+    b = synth.randn_t(9, "lin_b", (N,)).to(dev)
+    for act in (False, True):
+        with torch.no_grad():
+            got = SF().equal_linear(x, w, b, 0.04, 0.5, act)
+        want = x.double() @ (w.double() * 0.04).t() + b.double() * 0.5
+        if act:
+            want = F.leaky_relu(want, 0.2) * 2 ** 0.5
+        assert K_rel(got, want) < 2e-6
+
+
+def K_rel(a, b):
+    return K.rel_err(K.t2n(a), K.t2n(b))

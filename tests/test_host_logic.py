@@ -156,3 +156,59 @@ def test_bench_reference_arm_prints_contract_line():
     out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference"], capture_output=True, text=True,
                          timeout=120, cwd=root, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_position_group_channel_map_is_block_diagonal():
+    """Several lattice positions per generator call (grids.PositionGroup): the reference builds its flat (1,B*C)++(1,B*3)
+    concat table per call, so the table of a stacked batch is one copy of the per-call table per position, with the source
+    sample offset by the position's first row (models/spgan_ops_gs.py:792-814)."""
+    import numpy as np
+    import spgan_b200.functional as SF
+    Bg, G, C, nc, Cp = 4, 3, 256, 3, 320
+    one = SF._sphere_chan_map(Bg, C, nc, Cp, True, "cpu").numpy().view(np.uint32)
+    full = SF._sphere_chan_map(Bg * G, C, nc, Cp, True, "cpu", group=Bg).numpy().view(np.uint32)
+    assert full.shape == (Bg * G, Cp)
+    for i in range(G):
+        blk = full[i * Bg:(i + 1) * Bg]
+        valid = one != 0xFFFFFFFF
+        assert np.array_equal(blk != 0xFFFFFFFF, valid)
+        assert np.array_equal(blk[valid] & 0x80007FFF, one[valid] & 0x80007FFF)            # kind and source channel
+        assert np.array_equal((blk[valid] >> 15) & 0xFFFF, ((one[valid] >> 15) & 0xFFFF) + i * Bg)  # source sample
+    # the oracle's statement of the same quirk for one call: group g reads flat channels [g*Ct, (g+1)*Ct)
+    Ct = C + nc
+    for g in range(Bg):
+        for k in (0, 1, 255, 256, 258):
+            flat = g * Ct + k
+            m = int(one[g, k])
+            if flat < Bg * C:
+                assert (m >> 31) == 0 and ((m >> 15) & 0xFFFF) == flat // C and (m & 0x7FFF) == flat % C
+            else:
+                assert (m >> 31) == 1 and ((m >> 15) & 0xFFFF) == (flat - Bg * C) // nc and (m & 0x7FFF) == (flat - Bg * C) % nc
+
+
+def test_position_group_grids_and_engine_partition():
+    import torch
+    from spgan_b200 import grids, panorama
+    pl = panorama.plan(384, 768)
+    cps = [panorama.patch_inputs(pl, ix, iy, it, pl["lat_h"], pl["lat_w"])[0] for it, (ix, iy) in enumerate(panorama.positions(pl)[8:11])]
+    cache = grids.GridCache()
+    g = cache.group_grid(17, 17, cps, "cpu")
+    assert g.shape == (3, 51, 51, 2)
+    for i, cp in enumerate(cps):
+        assert torch.equal(g[i:i + 1], cache.get(17, 17, cp, "cpu"))
+    pg = grids.PositionGroup(cps, 2)
+    expanded = cache.batch(17, 17, pg, 6, "cpu")
+    assert expanded.shape == (6, 51, 51, 2) and torch.equal(expanded[2], g[1]) and torch.equal(expanded[5], g[2])
+    try:
+        cache.batch(17, 17, pg, 5, "cpu")
+        raise AssertionError("a PositionGroup of 3 x 2 samples must not accept a batch of 5")
+    except RuntimeError:
+        pass
+
+    class Stub:  # PanoramaEngine only partitions here: no generator call
+        pass
+    eng = panorama.PanoramaEngine.__new__(panorama.PanoramaEngine)
+    pos = [(it, ix, iy) for it, (ix, iy) in enumerate(panorama.positions(pl))][:7]
+    group = 3
+    items = [list(range(i, min(i + group, len(pos)))) for i in range(0, len(pos), group)]
+    assert items == [[0, 1, 2], [3, 4, 5], [6]]
