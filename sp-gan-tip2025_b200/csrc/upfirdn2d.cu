@@ -49,6 +49,57 @@ __global__ void __launch_bounds__(256) upfirdn2d_generic(float* __restrict__ out
   }
 }
 
+// Polyphase FIR for up, down in {1, 2} and kernels up to 4x4 (Upsample / Downsample of models/ops.py:32-79 and the gradients of
+// each other): the generic kernel below spends ~25 emulated-division instructions per tap on `% up` / `/ up` and decodes a
+// 64-bit flat index per output (0.03-0.08 of the HBM roofline in the configs[4] sweep).  Here up / down are template
+// parameters (parity tests and shifts), a CTA owns a 32 x 32 output tile of one plane, a thread four outputs of one column;
+// neighbouring outputs share their inputs through L1.
+template <int UP, int DOWN>
+__global__ void __launch_bounds__(256) upfirdn2d_poly(float* __restrict__ out, const float* __restrict__ x,
+                                                     const float* __restrict__ kernel, int64_t planes, int tiles_x, UfdParams p) {
+  __shared__ float kf[16];  // flipped kernel, row stride 4
+  if (threadIdx.x < 16) {
+    const int ky = threadIdx.x >> 2, kx = threadIdx.x & 3;
+    kf[threadIdx.x] = (ky < p.kh && kx < p.kw) ? __ldg(kernel + (p.kh - 1 - ky) * p.kw + (p.kw - 1 - kx)) : 0.f;
+  }
+  __syncthreads();
+  const int tile_y = blockIdx.x / tiles_x, tile_x = blockIdx.x - tile_y * tiles_x;
+  const int ox = tile_x * 32 + (threadIdx.x & 31);
+  const int oy0 = tile_y * 32 + (threadIdx.x >> 5);
+  if (ox >= p.out_w) return;
+  for (int64_t plane = blockIdx.y; plane < planes; plane += gridDim.y) {
+    const float* __restrict__ xp = x + plane * (int64_t)p.in_h * p.in_w;
+    float* __restrict__ op = out + plane * (int64_t)p.out_h * p.out_w;
+    // this column's taps: input column and validity per kx (the same for the four outputs)
+    int ixs[4];
+    bool okx[4];
+#pragma unroll
+    for (int kx = 0; kx < 4; ++kx) {
+      const int X = ox * DOWN + kx - p.pad_x0;
+      okx[kx] = kx < p.kw && X >= 0 && (UP == 1 || (X & 1) == 0) && (X / UP) < p.in_w;
+      ixs[kx] = X / UP;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int oy = oy0 + 8 * i;
+      if (oy >= p.out_h) break;
+      float acc = 0.f;
+#pragma unroll
+      for (int ky = 0; ky < 4; ++ky) {
+        const int Y = oy * DOWN + ky - p.pad_y0;
+        if (ky >= p.kh || Y < 0 || (UP == 2 && (Y & 1))) continue;
+        const int iy = Y / UP;
+        if (iy >= p.in_h) continue;
+        const float* row = xp + (int64_t)iy * p.in_w;
+#pragma unroll
+        for (int kx = 0; kx < 4; ++kx)
+          if (okx[kx]) acc += kf[ky * 4 + kx] * __ldg(row + ixs[kx]);
+      }
+      op[(int64_t)oy * p.out_w + ox] = acc;
+    }
+  }
+}
+
 // Tiled FIR kernels: 64x64 output tile per CTA (256 threads as 64 columns x 4 row groups, 16 rows per thread).
 // A CTA's lifetime is one global-load latency + one store; the tile size is what keeps enough bytes in flight per SM
 // (8 resident CTAs x ~17 KB) for the kernel to sit on the HBM roofline rather than on the load latency.
@@ -429,6 +480,13 @@ extern "C" int spgan_upfirdn2d(float* out, const float* x, const float* kernel, 
     if (kh == 2) upfirdn2d_tiled<2><<<(unsigned)blocks, 256, 0, st>>>(out, x, kernel, tiles_x, tiles_y, p);
     if (kh == 3) upfirdn2d_tiled<3><<<(unsigned)blocks, 256, 0, st>>>(out, x, kernel, tiles_x, tiles_y, p);
     if (kh == 4) upfirdn2d_tiled<4><<<(unsigned)blocks, 256, 0, st>>>(out, x, kernel, tiles_x, tiles_y, p);
+  } else if (up_x == up_y && down_x == down_y && up_x <= 2 && down_x <= 2 && kh <= 4 && kw <= 4) {
+    const int tx = (p.out_w + 31) / 32, ty = (p.out_h + 31) / 32;
+    dim3 grid((unsigned)(tx * ty), (unsigned)(planes < 65535 ? planes : 65535));
+    if (up_x == 1 && down_x == 1) upfirdn2d_poly<1, 1><<<grid, 256, 0, st>>>(out, x, kernel, planes, tx, p);
+    else if (up_x == 2 && down_x == 1) upfirdn2d_poly<2, 1><<<grid, 256, 0, st>>>(out, x, kernel, planes, tx, p);
+    else if (up_x == 1 && down_x == 2) upfirdn2d_poly<1, 2><<<grid, 256, 0, st>>>(out, x, kernel, planes, tx, p);
+    else upfirdn2d_poly<2, 2><<<grid, 256, 0, st>>>(out, x, kernel, planes, tx, p);
   } else {
     const int64_t total = planes * p.out_h * p.out_w;
     upfirdn2d_generic<<<grid_for(total, 256, 8, 8), 256, 0, st>>>(out, x, kernel, planes, p);

@@ -45,8 +45,11 @@ def main():
     last_clocks = {}
 
     def timed(fn, iters=5, warm=2, min_s=0.45):
-        """ms per call (CUDA events); the loop runs for at least `min_s` so that the nvidia-smi clock sampler (200 ms period)
-        sees the kernel under load — the record lands in the case's JSON line."""
+        """ms per call (CUDA events).  The call is captured in a CUDA graph of `reps` repetitions and the graph is replayed, so
+        that small kernels are timed on the device and not on the Python / autograd launch overhead (~0.1 ms per call, which
+        made every sub-0.1 ms case of the first sweep read as a fraction of its real bandwidth); eager loop if the capture
+        fails.  The loop runs for at least `min_s` so that the nvidia-smi clock sampler (200 ms period) sees the kernel under
+        load — the record lands in the case's JSON line."""
         for _ in range(warm):
             fn()
         torch.cuda.synchronize()
@@ -56,17 +59,39 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         one = max(e0.elapsed_time(e1), 1e-3)
-        iters = max(iters, min(2000, int(min_s * 1e3 / one) + 1))
+        reps = max(1, min(20, int(2.0 / one)))
+        graph = None
+        if reps > 1:
+            try:
+                g = torch.cuda.CUDAGraph()
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.graph(g, stream=side):
+                    for _ in range(reps):
+                        fn()
+                torch.cuda.current_stream().wait_stream(side)
+                g.replay()
+                torch.cuda.synchronize()
+                graph = g
+            except Exception:
+                torch.cuda.synchronize()
+                graph = None
+        if graph is None:
+            reps = 1
+        run = graph.replay if graph is not None else fn
+        iters = max(iters, min(4000, int(min_s * 1e3 / (one * reps)) + 1))
         sampler = ClockSampler(0)
         sampler.start()
         e0.record()
         for _ in range(iters):
-            fn()
+            run()
         e1.record()
         torch.cuda.synchronize()
         last_clocks.clear()
         last_clocks.update(sampler.stop())
-        return e0.elapsed_time(e1) / iters
+        last_clocks["graph_replay"] = graph is not None
+        del graph
+        return e0.elapsed_time(e1) / (iters * reps)
 
     def report(name, ms, bytes_=None, flops=None, **kw):
         out = {"case": name, "ms": round(ms, 4)}
