@@ -167,7 +167,7 @@ def main():
         x = rn(32, 64, 53, 53)
         ms = timed(lambda: SF.upfirdn2d(x, k3, up=2, down=1, pad=(1, 0)))
         oh = 53 * 2 + 1 - 3 + 1
-        report("upfirdn2d up=2 3x3 (generic kernel) (32,64,53,53)", ms, bytes_=4 * 32 * 64 * (53 * 53 + oh * oh))
+        report("upfirdn2d up=2 3x3 (polyphase kernel) (32,64,53,53)", ms, bytes_=4 * 32 * 64 * (53 * 53 + oh * oh))
     case("upfirdn2d up2", fir_up)
 
     def upblur():
@@ -219,8 +219,8 @@ def main():
         out = torch.empty((2, 32 * 103 * 103, 512), device=dev, dtype=torch.bfloat16)
         import ctypes
         p = lambda t: ctypes.c_void_p(t.data_ptr())
-        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-        ms = timed(lambda: lib.call("spgan_pack_act", p(out), p(x), p(s), 32, 512, 103, 103, 512, 0, 0, 103, 103, 1, 0, st))
+        st = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)  # the capture stream while a graph is recorded
+        ms = timed(lambda: lib.call("spgan_pack_act", p(out), p(x), p(s), 32, 512, 103, 103, 512, 0, 0, 103, 103, 1, 0, st()))
         report("pack_act (32,512,103,103) -> bf16 hi/lo channels-last", ms, bytes_=4 * x.numel() + out.numel() * 2)
     case("pack_act", pack)
 
