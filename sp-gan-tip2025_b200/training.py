@@ -158,6 +158,90 @@ class SyntheticSampler:
 
 
 # ------------------------------------------------------------------------------------------------ gradient exchange
+def _exchange_bucket(bucket, world):
+    """One bucket: flatten, NCCL / gloo all-reduce (SUM), average, and ONE multi-tensor copy back into the gradients."""
+    flat = torch.cat([g.reshape(-1) for g in bucket])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    flat.div_(world)
+    views, off = [], 0
+    for g in bucket:
+        views.append(flat[off:off + g.numel()].view_as(g))
+        off += g.numel()
+    torch._foreach_copy_(bucket, views)
+
+
+class OverlappedGradExchange:
+    """Gradient all-reduce overlapped with the backward pass (what DistributedDataParallel's bucket hooks do).
+
+    The parameters are assigned to ~`bucket_bytes` buckets in REVERSE registration order (backward reaches the last layers
+    first).  A post-accumulate-grad hook counts the bucket's gradients; when the last one has arrived the bucket is exchanged
+    on a SIDE stream (fork by event from the stream autograd runs on), while backward continues on the main stream; `finish()`
+    exchanges whatever did not fill up (parameters without a gradient in this pass) and joins the side stream.  Inside a
+    CUDA-graph capture the fork / join become graph edges, so the replayed step overlaps as well.  Before this the exchange
+    ran after the whole backward: +3.5 ms on a 47 ms step at N = 2 (0.93 weak-scaling efficiency)."""
+
+    def __init__(self, params, world, bucket_bytes=32 << 20):
+        self.world = world
+        self.params = [p for p in params]
+        self.bucket_of, self.buckets = {}, []
+        cur, size = [], 0
+        for p in reversed(self.params):
+            cur.append(p)
+            size += p.numel() * p.element_size()
+            if size >= bucket_bytes:
+                self.buckets.append(cur)
+                cur, size = [], 0
+        if cur:
+            self.buckets.append(cur)
+        for b, ps in enumerate(self.buckets):
+            for p in ps:
+                self.bucket_of[p] = b
+        self.active = False
+        self.side = None
+        self.pending, self.done = [], []
+        self._handles = [p.register_post_accumulate_grad_hook(self._hook) for p in self.params]
+
+    def begin(self):
+        """Arm the hooks for the backward pass that follows (call after zero_grad, before backward)."""
+        if self.world <= 1:
+            return
+        self.pending = [sum(1 for p in ps if p.requires_grad) for ps in self.buckets]
+        self.done = [False] * len(self.buckets)
+        if self.side is None:
+            self.side = torch.cuda.Stream(device=self.params[0].device)
+        self.active = True
+
+    def _launch(self, b):
+        grads = [p.grad for p in self.buckets[b] if p.grad is not None]
+        self.done[b] = True
+        if not grads:
+            return
+        main = torch.cuda.current_stream(grads[0].device)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self.side.wait_event(ev)
+        with torch.cuda.stream(self.side):
+            _exchange_bucket(grads, self.world)
+
+    def _hook(self, p):
+        if not self.active:
+            return
+        b = self.bucket_of[p]
+        self.pending[b] -= 1
+        if self.pending[b] == 0 and not self.done[b]:
+            self._launch(b)
+
+    def finish(self):
+        """Exchange the buckets that did not fill up and make the main stream wait for the side stream."""
+        if self.world <= 1 or not self.active:
+            return
+        self.active = False
+        for b in range(len(self.buckets)):
+            if not self.done[b]:
+                self._launch(b)
+        torch.cuda.current_stream(self.params[0].device).wait_stream(self.side)
+
+
 def allreduce_gradients(params, world, bucket_bytes=64 << 20):
     """Average parameter gradients over ranks: flatten into ~64 MB buckets (launch-latency sized, NVSwitch gives every
     rank full bandwidth), one NCCL all-reduce per bucket, unflatten.  No-op for world == 1."""
@@ -170,13 +254,7 @@ def allreduce_gradients(params, world, bucket_bytes=64 << 20):
         nonlocal bucket, size, n
         if not bucket:
             return
-        flat = torch.cat([g.reshape(-1) for g in bucket])
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-        flat.div_(world)
-        off = 0
-        for g in bucket:
-            g.copy_(flat[off:off + g.numel()].view_as(g))
-            off += g.numel()
+        _exchange_bucket(bucket, world)
         n += 1
         bucket, size = [], 0
     for g in grads:
@@ -267,6 +345,10 @@ class TrainStep:
         self.g_optim = torch.optim.Adam(self.G.parameters(), lr=tp.lr * g_ratio, betas=(0 ** g_ratio, 0.99 ** g_ratio), capturable=cap)
         self.d_optim = torch.optim.Adam(self.D.parameters(), lr=tp.lr * d_ratio, betas=(0 ** d_ratio, 0.99 ** d_ratio), capturable=cap)
         sync_module_states([self.G, self.D, self.G_ema], world)
+        # gradient exchange overlapped with backward (GPU, world > 1); the post-backward bucketed exchange otherwise
+        self.overlap = world > 1 and torch.device(device).type == "cuda"
+        self.g_xchg = OverlappedGradExchange(self.G.parameters(), world) if self.overlap else None
+        self.d_xchg = OverlappedGradExchange(self.D.parameters(), world) if self.overlap else None
         self.rank = rank
         self.sampler = SyntheticSampler(batch, device, seed + 7919 * (rank + 1) if world > 1 else seed)
         self.mean_path_length = torch.zeros((), device=device)
@@ -294,6 +376,18 @@ class TrainStep:
         img, styles, structure = self.G(inp["gl"], inp["lat"], inp["coords"], inp["cps"], noises=inp["noises"],
                                         return_latents=True, styles=styles)
         return img, styles, structure
+
+    def _backward(self, loss, model, xchg):
+        """backward + gradient exchange: overlapped per bucket on a side stream (GPU, world > 1), else after the pass."""
+        if xchg is None:
+            loss.backward()
+            allreduce_gradients(model.parameters(), self.world)
+            return
+        xchg.begin()
+        try:
+            loss.backward()
+        finally:
+            xchg.finish()
 
     # ---- graph plumbing ----
     def _run(self, name, body):
@@ -333,8 +427,7 @@ class TrainStep:
             loss = loss + (coord_ac_loss(rp["ac_coords_pred"], real_ac) + coord_ac_loss(fp["ac_coords_pred"], inp["ac"])) * \
                 self.config.train_params.coord_ac_w
             self.D.zero_grad(set_to_none=True)
-            loss.backward()
-            allreduce_gradients(self.D.parameters(), self.world)
+            self._backward(loss, self.D, self.d_xchg)
             self.d_optim.step()
             return loss.detach()
         return self._run("d", body)
@@ -350,8 +443,7 @@ class TrainStep:
             rp = self.D(x)
             r1 = d_r1_loss(rp["d_patch"], x)
             self.D.zero_grad(set_to_none=True)
-            (tp.r1 / 2 * r1 * tp.d_reg_every + 0 * rp["d_patch"][0]).sum().backward()
-            allreduce_gradients(self.D.parameters(), self.world)
+            self._backward((tp.r1 / 2 * r1 * tp.d_reg_every + 0 * rp["d_patch"][0]).sum(), self.D, self.d_xchg)
             self.d_optim.step()
             return r1.detach()
         return self._run("r1", body)
@@ -369,8 +461,7 @@ class TrainStep:
             if tp.diversity_z_w and self.batch % 2 == 0:
                 loss = loss + diversity_z_loss(inp["lat"], structure) * tp.diversity_z_w
             self.G.zero_grad(set_to_none=True)
-            loss.backward()
-            allreduce_gradients(self.G.parameters(), self.world)
+            self._backward(loss, self.G, self.g_xchg)
             self.g_optim.step()
             return loss.detach()
         return self._run("g", body)
@@ -396,9 +487,8 @@ class TrainStep:
             mean = self.mean_path_length + 0.01 * (batch_mean - self.mean_path_length)
             penalty = (pl - mean).pow(2).mean()
             self.G.zero_grad(set_to_none=True)
-            (tp.path_regularize * tp.g_reg_every * penalty).backward()
+            self._backward(tp.path_regularize * tp.g_reg_every * penalty, self.G, self.g_xchg)
             self.mean_path_length.copy_(mean.detach())  # in place: the running mean is state a graph replay must see
-            allreduce_gradients(self.G.parameters(), self.world)
             self.g_optim.step()
             return penalty.detach()
         return self._run("path", body)
