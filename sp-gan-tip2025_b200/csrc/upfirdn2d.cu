@@ -53,7 +53,10 @@ __global__ void __launch_bounds__(256) upfirdn2d_generic(float* __restrict__ out
 // each other): the generic kernel below spends ~25 emulated-division instructions per tap on `% up` / `/ up` and decodes a
 // 64-bit flat index per output (0.03-0.08 of the HBM roofline in the configs[4] sweep).  Here up / down are template
 // parameters (parity tests and shifts), a CTA owns a 32 x 32 output tile of one plane, a thread four outputs of one column;
-// neighbouring outputs share their inputs through L1.
+// neighbouring outputs share their inputs through L1.  Measured (tools/microbench.py sweep): 0.2-0.3 of the HBM roofline for
+// down = 2 and 0.09 for up = 2 (2-3x the generic kernel) — still instruction-bound on per-tap predicates (a predicate-first,
+// branch-free variant was 3x slower: 64 predicated loads per thread).  Off the hot path: spgan.yaml reaches up = 2 only through
+// ToRGB's 3-channel skip upsample (models/spgan_ops.py:36-65); a quad-per-thread phase decomposition is the next step.
 template <int UP, int DOWN>
 __global__ void __launch_bounds__(256) upfirdn2d_poly(float* __restrict__ out, const float* __restrict__ x,
                                                      const float* __restrict__ kernel, int64_t planes, int tiles_x, UfdParams p) {
@@ -79,31 +82,23 @@ __global__ void __launch_bounds__(256) upfirdn2d_poly(float* __restrict__ out, c
       okx[kx] = kx < p.kw && X >= 0 && (UP == 1 || (X & 1) == 0) && (X / UP) < p.in_w;
       ixs[kx] = X / UP;
     }
-    // branch-free: all predicates first, then every load of the four outputs in flight, then the FMAs (a `continue` per
-    // skipped tap row serialised the loads behind warp-uniform branches: one L2 latency per tap row, 0.09 of the roofline)
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int oy = oy0 + 8 * i;
-      float v[4][4];
+      if (oy >= p.out_h) break;
+      float acc = 0.f;
 #pragma unroll
       for (int ky = 0; ky < 4; ++ky) {
         const int Y = oy * DOWN + ky - p.pad_y0;
+        if (ky >= p.kh || Y < 0 || (UP == 2 && (Y & 1))) continue;  // warp-uniform: a warp is one output row
         const int iy = Y / UP;
-        const bool oky = oy < p.out_h && ky < p.kh && Y >= 0 && (UP == 1 || (Y & 1) == 0) && iy < p.in_h;
-        const float* row = xp + (int64_t)(oky ? iy : 0) * p.in_w;
+        if (iy >= p.in_h) continue;
+        const float* row = xp + (int64_t)iy * p.in_w;
 #pragma unroll
-        for (int kx = 0; kx < 4; ++kx) v[ky][kx] = (oky && okx[kx]) ? __ldg(row + ixs[kx]) : 0.f;
+        for (int kx = 0; kx < 4; ++kx)
+          if (okx[kx]) acc += kf[ky * 4 + kx] * __ldg(row + ixs[kx]);
       }
-#pragma unroll
-      for (int ky = 0; ky < 4; ++ky)
-#pragma unroll
-        for (int kx = 0; kx < 4; ++kx) acc[i] += kf[ky * 4 + kx] * v[ky][kx];
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int oy = oy0 + 8 * i;
-      if (oy < p.out_h) op[(int64_t)oy * p.out_w + ox] = acc[i];
+      op[(int64_t)oy * p.out_w + ox] = acc;
     }
   }
 }

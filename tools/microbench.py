@@ -167,7 +167,7 @@ def main():
         x = rn(32, 64, 53, 53)
         ms = timed(lambda: SF.upfirdn2d(x, k3, up=2, down=1, pad=(1, 0)))
         oh = 53 * 2 + 1 - 3 + 1
-        report("upfirdn2d up=2 3x3 (polyphase kernel) (32,64,53,53)", ms, bytes_=4 * 32 * 64 * (53 * 53 + oh * oh))
+        report("upfirdn2d up=2 3x3 (template up/down kernel) (32,64,53,53)", ms, bytes_=4 * 32 * 64 * (53 * 53 + oh * oh))
     case("upfirdn2d up2", fir_up)
 
     def upblur():
