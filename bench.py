@@ -241,12 +241,14 @@ def measure_panorama(args, dev, world, rank, local, th, tw, B, sharded, steps, w
     def timed(fn, n):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.nvtx.range_push("spgan_timed")  # ncu --nvtx --nvtx-include "spgan_timed/" lists exactly these launches
+        # a start/end range (process-wide, unlike push/pop): `ncu --nvtx --nvtx-include "spgan_timed"` lists exactly the
+        # launches of the timed region, including those issued by autograd's backward thread
+        rng = torch.cuda.nvtx.range_start("spgan_timed")
         e0.record()
         for _ in range(n):
             fn()
         e1.record()
-        torch.cuda.nvtx.range_pop()
+        torch.cuda.nvtx.range_end(rng)
         barrier()
         ms = e0.elapsed_time(e1)
         if world > 1:
@@ -552,13 +554,16 @@ def measure_train(args, dev, world, rank, local):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def measure(steps, e2e):
+    def measure(steps, e2e, mark=False):
         acc = []
         barrier()
-        torch.cuda.nvtx.range_push("spgan_timed")
+        # the timed region only: a process-wide NVTX range (backward kernels come from autograd's own thread)
+        rng = torch.cuda.nvtx.range_start("spgan_timed") if mark else None
         for _ in range(steps):
             one_iteration(acc, e2e)
-        torch.cuda.nvtx.range_pop()
+        if mark:
+            torch.cuda.synchronize()
+            torch.cuda.nvtx.range_end(rng)
         barrier()
         ms = {k: sum(ev[i].elapsed_time(ev[i + 1]) for ev in acc) / steps for i, k in enumerate(parts)}
         t = torch.tensor([ms[k] for k in parts], device=dev)
@@ -592,7 +597,7 @@ def measure_train(args, dev, world, rank, local):
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    ms = measure(args.steps, False)
+    ms = measure(args.steps, False, mark=True)
     clocks = sampler.stop() if sampler else None
     ms_e2e = measure(args.steps, True) if not args.skip_e2e else {k: float("nan") for k in parts}
     call_ms = None

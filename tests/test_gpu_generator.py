@@ -235,6 +235,26 @@ def test_panorama_768_golden_strip_and_seam(gen):
     assert abs(img.std() - float(ref["std"])) < 1e-3 * float(ref["std"])
 
 
+def test_position_group_at_bench_batch_32(gen):
+    """The benchmarked configuration: two lattice positions of B = 32 as ONE generator call of 64 (block-diagonal flat-concat
+    table of 2 x 32 groups, two sampling grids) against the two single-position calls."""
+    from spgan_b200 import panorama
+    pl = panorama.plan(384, 768)
+    B = 32
+    only = set(panorama.positions(pl)[9:11])
+    g = torch.Generator(device="cpu").manual_seed(32)
+    gl = torch.randn(B, 512, generator=g).cuda()
+    canvas = torch.randn(B, 256, pl["lat_h"], pl["lat_w"], generator=g).cuda()
+    noises = [torch.randn(B, 1, pl["noise_h"][l], pl["noise_w"][l], generator=g).cuda() for l in range(8)]
+    want = panorama.generate(gen, pl, gl, canvas, noises, only=only)
+    eng = panorama.PanoramaEngine(gen, pl, B, "cuda:0", streams=1, only=only, use_graph=False, group=2)
+    eng.load(gl, canvas, noises)
+    got = eng.run()
+    err = K.rel_err(K.t2n(got), K.t2n(want))
+    print("two positions x 32 patches as one call: %.2e" % err)
+    assert err < 2e-6
+
+
 def test_structure_chain_matches_module_path(gen):
     """The channels-last structure chain (256-channel main K segment + dense coordinate tail segment, shortcut as the
     residual of the spherical GEMM, packed / NHWC sinks between the convs) computes what the module-by-module path computes

@@ -10,11 +10,11 @@ timeout 420 python tools/microbench.py --budget-s 60 > $E/microbench_fixed.jsonl
 timeout 600 python tools/microbench.py --budget-s ${SWEEP_S:-240} --sweep > $E/microbench_sweep.jsonl 2> $E/microbench_sweep.err; echo "microbench sweep exit $?"
 PANO="python bench.py --steps 1 --warmup 1 --skip-e2e --skip-profile --no-cpu-baseline --no-strict --no-train --no-pano768 --no-graphs --streams 1"
 timeout 600 $PANO > $E/pano_plain.log 2>&1 && \
-timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none --nvtx --nvtx-include "spgan_timed/" --csv --log-file $E/launches_pano.csv $PANO > $E/ncu_launches_pano.log 2>&1
+timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none --nvtx --nvtx-include "spgan_timed" --csv --log-file $E/launches_pano.csv $PANO > $E/ncu_launches_pano.log 2>&1
 echo "pano launch list exit $?"; wc -l $E/launches_pano.csv
 TRAIN="python bench.py --workload train --steps 1 --warmup 1 --skip-e2e --no-cpu-baseline --no-graphs"
 timeout 600 $TRAIN > $E/train_plain.log 2>&1 && \
-timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none --nvtx --nvtx-include "spgan_timed/" --csv --log-file $E/launches_train.csv $TRAIN > $E/ncu_launches_train.log 2>&1
+timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none --nvtx --nvtx-include "spgan_timed" --csv --log-file $E/launches_train.csv $TRAIN > $E/ncu_launches_train.log 2>&1
 echo "train launch list exit $?"; wc -l $E/launches_train.csv
 timeout 300 python tools/probes/one_group.py > $E/group_plain.log 2>&1 && \
 timeout 900 ncu --set full --clock-control none --nvtx --nvtx-include "prof/" -k regex:"conv_gemm|sphere_pack_v3|upblur_pack|coord_taps|concat_repack" -o /tmp/ev_group python tools/probes/one_group.py > $E/ncu_group.log 2>&1
