@@ -385,7 +385,7 @@ def run_ours(args):
     if gemm_stats:
         ach = gemm_stats["flops"] / (gemm_stats["ms"] / 1000.0) / 1e12 if gemm_stats["ms"] > 0 else 0.0
         traffic, traffic_note = ncu_traffic()
-        roofline = {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit-GEMM modulated conv)", "achieved": ach,
+        roofline = {"bound": "tensor", "kernel": "conv_gemm2_kernel / conv_gemm_kernel (tcgen05 implicit-GEMM modulated conv: cta_group::2 CTA-pair and single-CTA variants)", "achieved": ach,
                     "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf if peak_tf else None, "traffic": traffic,
                     "traffic_note": traffic_note, "peak_source": peak_src, "launches_timed": gemm_stats["launches"],
                     "avg_launch_ms": gemm_stats["ms"] / max(gemm_stats["launches"], 1),
