@@ -775,6 +775,20 @@ class only_data_grads:
         return False
 
 
+def plane_dot(a, b):
+    """out[b, c] = sum over pixels of a[b, c] * b[b, c] in one pass (spgan_plane_dot): the style / demodulation gradients
+    d s[b,c] = <x[b,c], dxs[b,c]> without the (B, C, H, W) product tensor.  No autograd: first-order backward only."""
+    ac, bc = _f32c(a, "plane_dot"), _f32c(b, "plane_dot")
+    if ac.shape != bc.shape or ac.dim() != 4:
+        raise RuntimeError("plane_dot: operands must be two (B, C, H, W) tensors of equal shape")
+    B, C, H, W = ac.shape
+    out = torch.empty((B, C), device=ac.device, dtype=torch.float32)
+    if B * C:
+        with torch.cuda.device(ac.device):
+            lib.call("spgan_plane_dot", _ptr(out), _ptr(ac), _ptr(bc), B * C, H * W, _stream(ac))
+    return out
+
+
 class _ConvFn(torch.autograd.Function):
     """y = out_scale * D(out_mul) L_w( D(in_mul) x ), differentiable to any order in x, w, in_mul, out_mul
     (the weight-gradient node itself is first-order only, which is all R1 / path-length need)."""
@@ -798,7 +812,8 @@ class _ConvFn(torch.autograd.Function):
             # D(in_mul)^-1 applied lazily: the un-modulated data gradient serves both dx and d(in_mul)
             gx_un = _ConvFn.apply(g, w, out_mul, None, ctx.geom, not ctx.adjoint, ctx.in_hw, ctx.out_scale)
             if need_im:
-                gim = (x * gx_un).sum(dim=(2, 3))
+                # first-order backward (no create_graph): one fused pass instead of a (B, C, H, W) product + reduction
+                gim = plane_dot(x, gx_un) if not torch.is_grad_enabled() else (x * gx_un).sum(dim=(2, 3))
             if need_x:
                 gx = gx_un * in_mul[:, :, None, None] if ctx.has_im else gx_un
         if need_w:
@@ -807,7 +822,7 @@ class _ConvFn(torch.autograd.Function):
             else:  # z = L^T(g'): <z, gz> = <L(gz), g'>, so the base input is the incoming gradient
                 gw = _WgradFn.apply(x, g, out_mul, in_mul, tuple(w.shape), ctx.geom, ctx.out_scale)
         if need_om:
-            gom = (g * y).sum(dim=(2, 3)) / out_mul
+            gom = (plane_dot(g, y) if not torch.is_grad_enabled() else (g * y).sum(dim=(2, 3))) / out_mul
         return gx, gw, gim, gom, None, None, None, None
 
 
