@@ -76,10 +76,14 @@ def test_bias_act_empty_and_double_backward(dev):
     assert K.rel_err(K.t2n(ggo), want) < 1e-6
 
 
-def test_noise_bias_act_vs_oracle(dev):
-    x = synth.randn_t(2, "nx", (3, 6, 19, 19))
-    nz = synth.randn_t(2, "nn", (3, 1, 19, 19))
-    b = synth.randn_t(2, "nb", (6,))
+@pytest.mark.parametrize("shape", [(3, 6, 19, 19), (4, 6, 19, 19), (2, 4, 8, 8), (4, 3, 5, 5), (8, 5, 101, 101)])
+def test_noise_bias_act_vs_oracle(dev, shape):
+    """Scalar plane kernel (element count not a multiple of 4) and the 128-bit flat kernel, whose float4s straddle plane,
+    channel and sample boundaries on odd planes."""
+    B, C, H, W = shape
+    x = synth.randn_t(2, "nx", (B, C, H, W))
+    nz = synth.randn_t(2, "nn", (B, 1, H, W))
+    b = synth.randn_t(2, "nb", (C,))
     nw = torch.tensor([0.37])
     want = O.fused_leaky_relu(K.t2n(x + nw * nz), K.t2n(b))
     got = SF().noise_bias_act(x.to(dev), nz.to(dev), nw.to(dev), b.to(dev))
