@@ -762,3 +762,18 @@ def test_linear_small_and_general_kernels_vs_fp64(M, N, K, dev):
 
 def K_rel(a, b):
     return K.rel_err(K.t2n(a), K.t2n(b))
+
+
+@pytest.mark.parametrize("shape", [(3, 6, 19, 19), (4, 6, 19, 19), (2, 3, 8, 8), (8, 5, 101, 101), (16, 512, 9, 9)])
+def test_bias_act_backward_kernels_vs_torch(dev, shape):
+    """First-order backward of fused_leaky_relu (models/custom_ops/fused_act.py:24-44) over both kernels: per-channel scalar
+    kernel and the 128-bit flat kernel (float4s straddling plane / channel / sample boundaries, bias gradient through
+    shared-memory bins)."""
+    B, C, H, W = shape
+    go = synth.randn_t(4, "bab_go", shape).to(dev)
+    out = synth.randn_t(4, "bab_out", shape).to(dev)
+    with torch.no_grad():
+        gi, gb = SF().FusedLeakyReLUFunctionBackward.apply(go, out, 0.2, 2 ** 0.5)
+    want = go.double() * torch.where(out > 0, 1.0, 0.2).double() * 2 ** 0.5
+    assert K_rel(gi, want) < 1e-6
+    assert K_rel(gb, want.sum(dim=(0, 2, 3))) < 2e-6
