@@ -34,7 +34,8 @@ def parse():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--precision", type=int, default=1, choices=[0, 1, 2, 3])
     ap.add_argument("--streams", type=int, default=2, help="concurrent lattice-position branches of the panorama graph")
-    ap.add_argument("--group", type=int, default=2, help="lattice positions per generator call (panorama.PanoramaEngine group)")
+    ap.add_argument("--group", type=int, default=0, help="lattice positions per generator call (panorama.PanoramaEngine group); "
+                                                         "0 = automatic: ~64 patches per call, at most 8 positions")
     ap.add_argument("--pair-mode", type=int, default=1, choices=[0, 1, 2], help="CTA-pair GEMM kernel: 0 never, 1 auto, 2 wherever legal")
     ap.add_argument("--ts-precision", default="", help="8 comma-separated per-layer modes for the texture chain")
     ap.add_argument("--fast-tail", action="store_true", help="also measure the fp16x2 tail policy (reported beside the headline)")
@@ -221,9 +222,10 @@ def measure_panorama(args, dev, world, rank, local, th, tw, B, sharded, steps, w
     d2h = host_out.numel() * 4
     graphs = not args.no_graphs
     if sharded:
-        eng = panorama.ShardedPanoramaEngine(gen, pl, B, dev, rank, world, streams=args.streams, use_graph=graphs, group=args.group)
+        eng = panorama.ShardedPanoramaEngine(gen, pl, B, dev, rank, world, streams=args.streams, use_graph=graphs, group=args.group or None)
     else:
-        eng = panorama.PanoramaEngine(gen, pl, B, dev, streams=args.streams, use_graph=graphs, group=args.group)
+        eng = panorama.PanoramaEngine(gen, pl, B, dev, streams=args.streams, use_graph=graphs, group=args.group or None)
+    group_used = (eng.engine if sharded else eng).group
     eng.load(host["gl"], host["canvas"], host["noises"])
 
     def step_resident():
@@ -269,7 +271,7 @@ def measure_panorama(args, dev, world, rank, local, th, tw, B, sharded, steps, w
     ms_total = timed(step_resident, steps)
     clocks = sampler.stop() if sampler else None
     out = {"ms_step": ms_total / steps, "ms_total": ms_total, "launches": l1 - l0, "gemm_launches": int(g1 - g0),
-           "clocks": clocks, "h2d": h2d, "d2h": d2h, "n_pos": n_pos, "plan": pl, "graphs": graphs,
+           "clocks": clocks, "h2d": h2d, "d2h": d2h, "n_pos": n_pos, "plan": pl, "graphs": graphs, "group": group_used,
            "canvas_mb": host["canvas"].numel() * 4 // 2 ** 20}
     if e2e:
         step_e2e()
@@ -277,8 +279,8 @@ def measure_panorama(args, dev, world, rank, local, th, tw, B, sharded, steps, w
     if profile:
         # per-launch CUDA-event times need eager launches on one stream (events cannot be recorded inside a graph replay,
         # and concurrent branches would overlap the brackets): one extra eager step of the same work after the timed region
-        prof = (panorama.ShardedPanoramaEngine(gen, pl, B, dev, rank, world, streams=1, use_graph=False, group=args.group) if sharded
-                else panorama.PanoramaEngine(gen, pl, B, dev, streams=1, use_graph=False, group=args.group))
+        prof = (panorama.ShardedPanoramaEngine(gen, pl, B, dev, rank, world, streams=1, use_graph=False, group=args.group or None) if sharded
+                else panorama.PanoramaEngine(gen, pl, B, dev, streams=1, use_graph=False, group=args.group or None))
         prof.load(host["gl"], host["canvas"], host["noises"])
         prof.run()
         SF.profile_gemm(True)
@@ -415,7 +417,7 @@ def run_ours(args):
                    "l2": "inputs and activations larger than L2 (latent canvas %d MB, > 1 GB of operands per patch batch)" % m["canvas_mb"],
                    "precision_mode": args.precision, "ts_layer_precision": modes,
                    "execution": ("one CUDA graph per step, lattice positions on %d concurrent branches" % args.streams if m["graphs"]
-                                 else "eager launches, %d streams" % args.streams) + ", %d lattice positions per generator call" % args.group,
+                                 else "eager launches, %d streams" % args.streams) + ", %d lattice positions per generator call" % m["group"],
                    "algorithmic_tflop_per_step_per_gpu": per_gpu_patches * PATCH_GFLOP / 1000.0},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": m["d2h"], "ms_per_step": ms_e2e},
         "gpu_launches": m["launches"] * args.steps, "tcgen05_gemm_launches": m["gemm_launches"] * args.steps,

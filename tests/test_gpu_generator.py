@@ -180,7 +180,7 @@ def test_panorama_engine_graph_equals_eager_loop(gen, streams):
     pl = panorama.plan(384, 768)
     B = 2
     only = set(panorama.positions(pl)[:7])
-    eng = panorama.PanoramaEngine(gen, pl, B, "cuda:0", streams=streams, only=only)
+    eng = panorama.PanoramaEngine(gen, pl, B, "cuda:0", streams=streams, only=only, group=1)  # one position per call: bit-exact
     for seed in (1, 2, 3, 4):
         g = torch.Generator(device="cpu").manual_seed(seed)
         gl = torch.randn(B, 512, generator=g).cuda()
