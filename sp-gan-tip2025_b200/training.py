@@ -29,6 +29,21 @@ def g_nonsaturating_loss(fake_pred):
     return F.softplus(-fake_pred).mean()
 
 
+def discriminate_pair(D, fake, real):
+    """D(fake), D(real) (train.py:262-263) as ONE pass over the interleaved batch [f0, r0, f1, r1, ...]: every conv of D is
+    per-sample, and the minibatch-stddev feature groups samples {m, m + M, m + 2M, ...} (stylegan2discriminator.py:205-212:
+    view(group, -1, ...)), so with M = 2 sub-batches the interleaving puts all fakes into one statistics group and all reals
+    into the other — the same numbers as two separate calls, with half the launches and twice the rows per GEMM.  Falls back
+    to two calls when the stddev grouping would not separate the two halves."""
+    B = fake.shape[0]
+    group = min(2 * B, getattr(D, "stddev_group", 0))
+    if fake.shape != real.shape or group != B:
+        return D(fake), D(real)
+    both = torch.stack([fake, real], 1).reshape(2 * B, *fake.shape[1:])
+    out = D(both)
+    return {k: v[0::2] for k, v in out.items()}, {k: v[1::2] for k, v in out.items()}
+
+
 def d_r1_loss(real_pred, real_img):
     from . import functional as SF
     with SF.only_data_grads():  # only d D(x) / dx is consumed here: no weight gradients in the create_graph pass
@@ -422,7 +437,7 @@ class TrainStep:
         def body():
             with torch.no_grad():
                 fake, _, _ = self._fake(inp)
-            fp, rp = self.D(fake), self.D(real_img)
+            fp, rp = discriminate_pair(self.D, fake, real_img)
             loss = d_logistic_loss(rp["d_patch"], fp["d_patch"])
             loss = loss + (coord_ac_loss(rp["ac_coords_pred"], real_ac) + coord_ac_loss(fp["ac_coords_pred"], inp["ac"])) * \
                 self.config.train_params.coord_ac_w

@@ -301,3 +301,28 @@ def test_only_data_grads_context_leaves_r1_unchanged():
     scale = max(float(b.abs().max()) for b in res[1][1])
     for a, b in zip(res[0][1], res[1][1]):
         assert torch.allclose(a, b, rtol=1e-4, atol=1e-6 * scale)
+
+
+def test_discriminator_pair_pass_equals_two_passes():
+    """training.discriminate_pair: D over the interleaved (fake, real) batch == D(fake), D(real) — outputs and parameter
+    gradients of the D loss (the minibatch-stddev groups stay separate by construction)."""
+    from spgan_b200.discriminator import Discriminator
+    from spgan_b200 import training
+    torch.manual_seed(7)
+    D = Discriminator().cuda().train()
+    D.stddev_group = 8
+    fake = torch.randn(8, 3, 101, 101, device="cuda").clamp_(-1, 1)
+    real = torch.randn(8, 3, 101, 101, device="cuda").clamp_(-1, 1)
+    res = []
+    for pair in (False, True):
+        fp, rp = training.discriminate_pair(D, fake, real) if pair else (D(fake), D(real))
+        loss = training.d_logistic_loss(rp["d_patch"], fp["d_patch"]) + fp["ac_coords_pred"].square().mean() + rp["ac_coords_pred"].abs().mean()
+        D.zero_grad(set_to_none=True)
+        loss.backward()
+        res.append((loss.detach().clone(), fp["d_patch"].detach().clone(), rp["d_patch"].detach().clone(),
+                    [p.grad.detach().clone() for p in D.parameters() if p.grad is not None]))
+    assert K.rel_err(K.t2n(res[1][1]), K.t2n(res[0][1])) < 1e-5 and K.rel_err(K.t2n(res[1][2]), K.t2n(res[0][2])) < 1e-5
+    assert abs(float(res[1][0]) - float(res[0][0])) < 1e-5 * abs(float(res[0][0]))
+    scale = max(float(b.abs().max()) for b in res[0][3])
+    for a, b in zip(res[1][3], res[0][3]):
+        assert torch.allclose(a, b, rtol=2e-4, atol=2e-5 * scale)
