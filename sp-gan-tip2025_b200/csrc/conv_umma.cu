@@ -475,8 +475,29 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------------ operand packers
+// (v0, v1) -> packed 16-bit hi pair and lo pair (lo = round(v - hi)); same values as two split16 calls
+template <bool kF16>
+__device__ __forceinline__ void split_pair_k(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+  if (kF16) {
+    v0 = fminf(fmaxf(v0, -65504.f), 65504.f);
+    v1 = fminf(fmaxf(v1, -65504.f), 65504.f);
+    const __half2 h = __floats2half2_rn(v0, v1);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+  } else {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+    const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h);
+    const float h0 = __uint_as_float(hb << 16), h1 = __uint_as_float(hb & 0xFFFF0000u);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(v0 - h0, v1 - h1);
+    hi = hb;
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+  }
+}
+
 // One CTA: 64 channels x 64 consecutive lattice points of one sample (and one polyphase plane).  Reads coalesced along
-// pixels, writes coalesced along channels (bf16x2 per lane, 128 bytes per warp).  With step s > 1 the lattice point
+// pixels, writes coalesced along channels (8 channels = 16 bytes per lane and plane).  With step s > 1 the lattice point
 // (i, j) of phase (py, px) holds source pixel (i*s + py - pad_y, j*s + px - pad_x): a strided conv becomes a stride-1
 // conv whose taps pick their phase plane (rows [ph * B*Hl*Wl, (ph+1) * B*Hl*Wl) of the packed matrix).
 template <bool kF16>
@@ -516,21 +537,27 @@ __global__ void __launch_bounds__(256) pack_act_kernel(uint16_t* __restrict__ ou
     for (int u = 0; u < 16; ++u) tile[ty + 4 * u][tx] = v[u] * m[u];
   }
   __syncthreads();
-  const int cpair = threadIdx.x & 31, prow = threadIdx.x >> 5;
+  // write phase: one item = (lattice point, run of 8 channels) -> one 16-byte store per plane (a warp covers 4 points x 128
+  // contiguous bytes); pairwise 16-bit conversions.  (One bf16x2 per lane and eight 2-byte-pair splits per thread made this
+  // phase the issue bottleneck: 0.65 of the HBM roofline.)
   const int64_t rows_total = (int64_t)step * step * B * plane_l;
   uint16_t* out_lo = out + rows_total * Cp;
 #pragma unroll
-  for (int pp = prow; pp < 64; pp += 8) {
+  for (int k = 0; k < 2; ++k) {
+    const int item = threadIdx.x + 256 * k;
+    const int pp = item >> 3, chunk = item & 7;
     const int q = q0 + pp;
-    if (q >= plane_l) break;
-    const float v0 = tile[2 * cpair][pp], v1 = tile[2 * cpair + 1][pp];
-    uint16_t h0, l0, h1, l1;
-    split16<kF16>(v0, h0, l0);
-    split16<kF16>(v1, h1, l1);
-    if (c0 + 2 * cpair >= Cp) continue;  // Cp is a multiple of 16: the last channel tile may be partial
-    const int64_t off = (((int64_t)ph * B + b) * plane_l + q) * Cp + c0 + 2 * cpair;
-    *reinterpret_cast<uint32_t*>(out + off) = pack2x16(h0, h1);
-    *reinterpret_cast<uint32_t*>(out_lo + off) = pack2x16(l0, l1);
+    const int cbase = c0 + 8 * chunk;
+    if (q >= plane_l || cbase >= Cp) continue;  // Cp is a multiple of 16: whole 8-channel runs
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float v0 = tile[8 * chunk + 2 * j][pp], v1 = tile[8 * chunk + 2 * j + 1][pp];
+      split_pair_k<kF16>(v0, v1, h[j], l[j]);
+    }
+    const int64_t off = (((int64_t)ph * B + b) * plane_l + q) * Cp + cbase;
+    *reinterpret_cast<uint4*>(out + off) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(out_lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
   }
 }
 
@@ -885,6 +912,7 @@ extern "C" int spgan_pack_act(uint16_t* out, const float* x, const float* in_mul
   SPGAN_CHECK_ARG(fmt == 0 || fmt == 1, "spgan_pack_act: fmt must be 0 (bf16 hi/lo) or 1 (fp16 hi/lo), got %d", fmt);
   if (B == 0 || Cp == 0 || H == 0 || W == 0) return 0;
   SPGAN_CHECK_ARG(out && x, "spgan_pack_act: null pointer");
+  SPGAN_CHECK_ARG((((uintptr_t)out) & 15) == 0, "spgan_pack_act: the packed operand must be 16-byte aligned");
   SPGAN_CHECK_ARG(B * step * step <= 65535, "spgan_pack_act: batch %d x %d phases > 65535", B, step * step);
   dim3 grid((Hl * Wl + 63) / 64, (Cp + 63) / 64, B * step * step);
   if (fmt)
