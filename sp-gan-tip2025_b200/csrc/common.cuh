@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include "../../include/spgan_b200.h"
 
 // SM count of the current device (B200: 2 dies x 74 = 148); grids are sized in multiples of this.  Queried once per device
@@ -48,6 +49,13 @@ void spgan_internal_count_gemm_launch();  // conv_umma.cu: bumps the counter beh
       return 2;                                                           \
     }                                                                     \
   } while (0)
+
+// Diagnostics: SPGAN_LEGACY_HBM_KERNELS=1 routes the FIR / gather entry points to the pre-streaming kernels (A/B timing in
+// tools/microbench.py and cross-checks in the tests).  Read per call so a process can toggle it.
+static inline bool spgan_legacy_hbm() {
+  const char* e = getenv("SPGAN_LEGACY_HBM_KERNELS");
+  return e != nullptr && e[0] == '1';
+}
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

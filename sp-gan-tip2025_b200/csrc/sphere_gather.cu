@@ -6,6 +6,7 @@
 // HBM roofline: writes 9x the input (4*B*C*9*H*W bytes) + reads input once (the 36 corner reads per input pixel
 // hit L1/L2) + the grid.
 #include "common.cuh"
+#include "stream_stage.cuh"
 
 namespace {
 
@@ -15,7 +16,8 @@ struct Corner {
 };
 
 __device__ __forceinline__ float unnormalize_clip(float g, int size) {
-  float v = __fmul_rn(__fdiv_rn(__fadd_rn(g, 1.f), 2.f), (float)(size - 1));
+  // (g + 1) / 2: halving is exact, so the multiply is bit-identical to ATen's division and ~10 instructions shorter
+  float v = __fmul_rn(__fmul_rn(__fadd_rn(g, 1.f), 0.5f), (float)(size - 1));
   return fminf((float)(size - 1), fmaxf(v, 0.f));
 }
 
@@ -70,6 +72,188 @@ __global__ void __launch_bounds__(256) sphere_gather_kernel(float* __restrict__ 
       op += opix;
     }
   }
+}
+
+// Streamed gather (the default): persistent CTAs; a work item = CC (8 or 4) consecutive channel planes of one sample x a
+// slice of the output positions.  The planes are one contiguous run of CC*H*W floats, fetched by ONE bulk-async copy
+// (stream_stage.cuh) while the previous item is sampled; the CTA then transposes them inside shared memory to
+// [pixel][channel] (conflict-free 128-bit stores), so that a corner of a position is ONE 128-bit shared-memory read per four
+// channels at an immediate offset, and the blend of two channels is one packed FFMA2.  A thread owns output positions: it
+// evaluates the corner table of a position once and reuses it for the CC channels.  ~10 instructions per output instead of
+// ~17, and no scattered L1 requests (the L1-gather kernel above: 4 LDG x 2-4 wavefronts per 32 outputs, 0.26 of the HBM
+// peak).  Stores are 128-byte coalesced rows of the 3H x 3W output planes.  Same corner arithmetic and blend order as the
+// kernel above: bit-identical outputs (tests/test_gpu_ops.py).
+constexpr int GS_THREADS = 512;
+
+struct GatherStream {
+  int B, C, H, W, grid_batch, encode;
+  int chunks, psplit, pslice, raw_floats;
+  int64_t out_bstride, out_coff, nitems;
+  uintptr_t limit;
+};
+
+__device__ __forceinline__ unsigned long long gs_pack(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+
+template <int CCQ, bool ENC>  // channel quads per item: 2 (8 channels) or 1 (4 channels); ENC: coordinate encoding (C == 3)
+__global__ void __launch_bounds__(GS_THREADS, 2) sphere_gather_stream_kernel(float* __restrict__ out,
+                                                                            const float* __restrict__ z,
+                                                                            const float* __restrict__ grid, GatherStream q) {
+  constexpr int CC = 4 * CCQ;
+  constexpr int TS = CCQ == 1 ? 4 : 12;  // floats per pixel row of the transposed tile: an odd number of 16-byte units
+  extern __shared__ __align__(128) float gs_smem[];
+  __shared__ uint64_t bar;
+  float* raw = gs_smem;
+  float* tile = gs_smem + q.raw_floats;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    stream_stage::bar_init(stream_stage::smem_addr(&bar), 1);
+    stream_stage::fence_bar_init();
+  }
+  __syncthreads();
+  const int HW = q.H * q.W;
+  const int opix = 9 * HW;
+  const int per_sample = q.chunks * q.psplit;
+  auto issue = [&](int64_t item) {
+    const int b = (int)(item / per_sample);
+    const int c0 = ((int)(item - (int64_t)b * per_sample) / q.psplit) * CC;
+    const int nc = min(CC, q.C - c0);
+    stream_stage::issue_chunk(raw, z + ((int64_t)b * q.C + c0) * HW, nc * HW, q.limit, &bar);
+  };
+  int64_t item = blockIdx.x;
+  if (tid == 0 && item < q.nitems) issue(item);
+  const uint32_t tile_addr = stream_stage::smem_addr(tile);
+  for (uint32_t k = 0; item < q.nitems; item += gridDim.x, ++k) {
+    const int b = (int)(item / per_sample);
+    const int rem = (int)(item - (int64_t)b * per_sample);
+    const int c0 = (rem / q.psplit) * CC;
+    const int slice = rem - (rem / q.psplit) * q.psplit;
+    const int nc = min(CC, q.C - c0);
+    const float* src = z + ((int64_t)b * q.C + c0) * HW;
+    const float* st = raw + stream_stage::chunk_shift(src);
+    stream_stage::bar_wait(stream_stage::smem_addr(&bar), k & 1);
+    // transpose [channel][pixel] -> [pixel][channel]; channels beyond the tensor read as zero
+    for (int e = tid; e < HW * CCQ; e += GS_THREADS) {
+      const int qd = e / HW, pix = e - qd * HW;
+      float4 v;
+      v.x = 4 * qd + 0 < nc ? st[(4 * qd + 0) * HW + pix] : 0.f;
+      v.y = 4 * qd + 1 < nc ? st[(4 * qd + 1) * HW + pix] : 0.f;
+      v.z = 4 * qd + 2 < nc ? st[(4 * qd + 2) * HW + pix] : 0.f;
+      v.w = 4 * qd + 3 < nc ? st[(4 * qd + 3) * HW + pix] : 0.f;
+      *reinterpret_cast<float4*>(tile + pix * TS + 4 * qd) = v;
+    }
+    __syncthreads();  // tile complete, raw planes consumed
+    if (tid == 0 && item + gridDim.x < q.nitems) issue(item + gridDim.x);
+    const float2* gp = reinterpret_cast<const float2*>(grid) + (int64_t)(q.grid_batch == 1 ? 0 : b) * opix;
+    float* ob = out + ((int64_t)b * q.out_bstride + q.out_coff + c0) * opix;
+    const int p_end = min(opix, (slice + 1) * q.pslice);
+    // the tap grid comes from L2 (~1 us away): keep the loads of the next two positions in flight while one is blended
+    const int p_first = slice * q.pslice + tid;
+    float2 g_1 = p_first < p_end ? __ldg(gp + p_first) : make_float2(0.f, 0.f);
+    float2 g_2 = p_first + GS_THREADS < p_end ? __ldg(gp + p_first + GS_THREADS) : g_1;
+    for (int p = p_first; p < p_end; p += GS_THREADS) {
+      const float2 g = g_1;
+      g_1 = g_2;
+      if (p + 2 * GS_THREADS < p_end) g_2 = __ldg(gp + p + 2 * GS_THREADS);
+      const Corner cn = corners(g.x, g.y, q.H, q.W);
+      const uint32_t a_n = tile_addr + (uint32_t)(cn.y0 * q.W) * (TS * 4u), a_s = tile_addr + (uint32_t)(cn.y1 * q.W) * (TS * 4u);
+      const uint32_t a_nw = a_n + (uint32_t)cn.x0 * (TS * 4u), a_ne = a_n + (uint32_t)cn.x1 * (TS * 4u);
+      const uint32_t a_sw = a_s + (uint32_t)cn.x0 * (TS * 4u), a_se = a_s + (uint32_t)cn.x1 * (TS * 4u);
+      const unsigned long long w_nw = gs_pack(cn.nw, cn.nw), w_ne = gs_pack(cn.ne, cn.ne), w_sw = gs_pack(cn.sw, cn.sw),
+                               w_se = gs_pack(cn.se, cn.se);
+      float* o = ob + p;
+#pragma unroll
+      for (int qd = 0; qd < CCQ; ++qd) {
+        unsigned long long nw0, nw1, ne0, ne1, sw0, sw1, se0, se1;
+        asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(nw0), "=l"(nw1) : "r"(a_nw + 16u * qd));
+        asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(ne0), "=l"(ne1) : "r"(a_ne + 16u * qd));
+        asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(sw0), "=l"(sw1) : "r"(a_sw + 16u * qd));
+        asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(se0), "=l"(se1) : "r"(a_se + 16u * qd));
+        unsigned long long r0, r1;
+        asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r0) : "l"(nw0), "l"(w_nw));
+        asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r1) : "l"(nw1), "l"(w_nw));
+        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(r0) : "l"(ne0), "l"(w_ne));
+        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(r1) : "l"(ne1), "l"(w_ne));
+        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(r0) : "l"(sw0), "l"(w_sw));
+        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(r1) : "l"(sw1), "l"(w_sw));
+        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(r0) : "l"(se0), "l"(w_se));
+        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(r1) : "l"(se1), "l"(w_se));
+        float v[4];
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(v[0]), "=f"(v[1]) : "l"(r0));
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(v[2]), "=f"(v[3]) : "l"(r1));
+        if (ENC && qd == 0) {  // channels 0, 1, 2 of the coordinate tensor (C == 3: c0 == 0)
+          v[0] = tanhf(v[0]);
+          v[1] = cosf(v[1] * 3.14159274101257324f);
+          v[2] = sinf(v[2] * 3.14159274101257324f);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (4 * qd + j < nc) __stcs(o + (int64_t)(4 * qd + j) * opix, v[j]);
+      }
+    }
+    __syncthreads();  // every read of the tile is done before the next item overwrites it
+  }
+}
+
+bool launch_gather_stream(float* out, const float* z, const float* grid, int B, int C, int H, int W, int grid_batch,
+                          int64_t out_bstride, int64_t out_coff, int encode, cudaStream_t st) {
+  if ((((uintptr_t)z) & 15) != 0) return false;
+  const int64_t HW = (int64_t)H * W;
+  if (9 * HW >= (1LL << 26)) return false;
+  const int nsm = SPGAN_NUM_SMS;
+  constexpr int64_t SMEM_MAX = 220 * 1024;
+  auto bytes = [&](int cc) {
+    const int64_t raw = (cc * HW + 8 + 31) / 32 * 32;
+    return (raw + HW * (cc == 8 ? 12 : 4)) * 4;
+  };
+  int cc = (C >= 8 && !encode && bytes(8) <= SMEM_MAX) ? 8 : 4;
+  if (const char* e = getenv("SPGAN_GS_CC")) cc = atoi(e) == 4 ? 4 : cc;  // diagnostics
+  if (bytes(cc) > SMEM_MAX) return false;  // planes too large to stage: L1-gather kernel
+  const int resident = (2 * (bytes(cc) + 1024) <= SMEM_MAX + 4096) ? 2 : 1;
+  const int64_t ncta = (int64_t)nsm * resident;
+  const int chunks = (C + cc - 1) / cc;
+  // position slices per (sample, channel group): the smallest split that balances the items over the persistent CTAs
+  int psplit = 1;
+  double best = -1.0;
+  for (int ps = 1; ps <= 4; ++ps) {
+    const int64_t items = (int64_t)B * chunks * ps;
+    const double eff = (double)items / (double)(((items + ncta - 1) / ncta) * ncta);
+    const double score = eff * (1.0 - 0.02 * (ps - 1));  // each slice re-stages the planes
+    if (score > best + 1e-9) {
+      best = score;
+      psplit = ps;
+    }
+  }
+  if (const char* e = getenv("SPGAN_GS_PSPLIT")) psplit = atoi(e) >= 1 ? atoi(e) : psplit;  // diagnostics
+  GatherStream q;
+  q.B = B; q.C = C; q.H = H; q.W = W; q.grid_batch = grid_batch; q.encode = encode;
+  q.chunks = chunks;
+  q.psplit = psplit;
+  q.pslice = (int)((9 * HW + psplit - 1) / psplit);
+  q.raw_floats = (int)((cc * HW + 8 + 31) / 32 * 32);
+  q.out_bstride = out_bstride; q.out_coff = out_coff;
+  q.nitems = (int64_t)B * chunks * psplit;
+  q.limit = ((uintptr_t)(z + (int64_t)B * C * HW)) & ~(uintptr_t)15;
+  const size_t smem = (size_t)bytes(cc);
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(sphere_gather_stream_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)SMEM_MAX) != cudaSuccess ||
+        cudaFuncSetAttribute(sphere_gather_stream_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)SMEM_MAX) != cudaSuccess ||
+        cudaFuncSetAttribute(sphere_gather_stream_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)SMEM_MAX) != cudaSuccess)
+      return false;
+    attr_done = true;
+  }
+  const unsigned grid_n = (unsigned)(q.nitems < ncta ? q.nitems : ncta);
+  if (encode) sphere_gather_stream_kernel<1, true><<<grid_n, GS_THREADS, smem, st>>>(out, z, grid, q);
+  else if (cc == 8) sphere_gather_stream_kernel<2, false><<<grid_n, GS_THREADS, smem, st>>>(out, z, grid, q);
+  else sphere_gather_stream_kernel<1, false><<<grid_n, GS_THREADS, smem, st>>>(out, z, grid, q);
+  return true;
 }
 
 __global__ void __launch_bounds__(256) sphere_indices_kernel(int32_t* __restrict__ x0, int32_t* __restrict__ y0,
@@ -163,6 +347,11 @@ extern "C" int spgan_sphere_gather(float* out, const float* z, const float* grid
   SPGAN_CHECK_ARG(!encode || C == 3, "spgan_sphere_gather: coordinate encoding expects 3 channels, got %d", C);
   SPGAN_CHECK_ARG((((uintptr_t)grid) & 7) == 0, "spgan_sphere_gather: grid must be 8-byte aligned");
   const int64_t total = (int64_t)B * 9 * H * W;
+  if (!spgan_legacy_hbm() &&
+      launch_gather_stream(out, z, grid, B, C, H, W, grid_batch, out_bstride, out_coff, encode, (cudaStream_t)stream)) {
+    SPGAN_CHECK_LAUNCH("spgan_sphere_gather");
+    return 0;
+  }
   dim3 g(grid_for(total, 256, 8, 2), (C + GATHER_CCHUNK - 1) / GATHER_CCHUNK);
   sphere_gather_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(out, z, grid, B, C, H, W, grid_batch, out_bstride, out_coff,
                                                            encode);

@@ -5,6 +5,7 @@
 //   * tiled kernel (same filters, very wide images): one 64x64 output tile per CTA.
 //   * generic kernel: any up/down/pad/kernel up to 16x16 (reads through L1/L2).
 #include "common.cuh"
+#include "stream_stage.cuh"
 
 namespace {
 
@@ -297,6 +298,268 @@ bool launch_band(float* out, const float* x, const float* kernel, int64_t planes
   return true;
 }
 
+// Streamed FIR (up = down = 1, K x K, K <= 4, zero padding): the default for the generator's Blur (3x3, pad 0) and the
+// discriminator's Blur (4x4, pad 2 / 1) and for their gradients.  Persistent CTAs (two per SM); a work item is a group of
+// P whole planes (small images) or a band of R output rows of one plane (large images) — in both cases ONE contiguous run
+// of floats, fetched by one bulk-async copy into a two-stage ring (stream_stage.cuh) while the previous item is filtered.
+// The rows are staged exactly as they lie in memory (no zero borders): a thread owns one output column of a strip of S
+// rows, clamps its K tap columns once and folds the column validity into its own copy of the taps, so the inner loop is a
+// sliding window of K shared-memory reads and K*K FMAs per output with no bounds checks; staged rows outside the image are
+// skipped by a per-row predicate.
+constexpr int FS_THREADS = 256;
+constexpr int FS_STRIP = 8;
+
+struct FirStream {
+  int in_h, in_w, out_h, out_w, pad_x0, pad_y0;
+  int P;       // planes per item (bands == 1)
+  int bands;   // bands per plane (P == 1 when bands > 1)
+  int R;       // output rows per band
+  int strips;  // ceil(R / FS_STRIP)
+  int stage_floats;
+  int64_t planes, nitems;
+  uintptr_t limit;  // 16-byte floor of the end of x
+  FastDiv d_ow, d_strips;
+};
+
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ unsigned long long fs_pack(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+
+// One strip of FS_STRIP output rows of one column: sliding window over the staged rows.  The K taps of a row are held as
+// K/2 packed pairs (+ one scalar for K = 3), so a K x K stencil costs K * (K/2) FFMA2 (+ K FFMA) and one or two adds per
+// output instead of K*K FFMA.  CHECK = false: every window row is staged and every output row exists (interior strips):
+// K running shared-memory addresses, no predicates.  CHECK = true (first / last strips): rows outside the image are read
+// from a clamped row and multiplied by zero, missing output rows are not stored — still branch-free.
+template <int K>
+struct FirTaps {
+  unsigned long long w2[K][K / 2 > 0 ? K / 2 : 1];  // packed column pairs of every tap row
+  float ws[K];                                      // last column when K is odd
+};
+
+template <int K>
+__device__ __forceinline__ void fir_taps(FirTaps<K>& t, const float (&w)[K * K], const float (&m)[K]) {
+#pragma unroll
+  for (int ky = 0; ky < K; ++ky) {
+#pragma unroll
+    for (int pi = 0; pi < K / 2; ++pi)
+      t.w2[ky][pi] = fs_pack(w[ky * K + 2 * pi] * m[2 * pi], w[ky * K + 2 * pi + 1] * m[2 * pi + 1]);
+    t.ws[ky] = (K & 1) ? w[ky * K + K - 1] * m[K - 1] : 0.f;
+  }
+}
+
+template <int K, bool CHECK>
+__device__ __forceinline__ void fir_strip(const FirTaps<K>& t, const uint32_t (&pk)[K], uint32_t base, float* __restrict__ o,
+                                          int ybase, int iy_lo, int iy_hi, int in_w, int out_w, int rows_left) {
+  constexpr int NP = K / 2;
+  constexpr bool ODD = (K & 1) != 0;
+  const auto& w2 = t.w2;
+  const auto& ws = t.ws;
+  uint32_t a[K];
+  const uint32_t row_bytes = (uint32_t)in_w * 4u;
+#pragma unroll
+  for (int kx = 0; kx < K; ++kx) a[kx] = base + pk[kx] + (CHECK ? 0u : (uint32_t)(ybase - iy_lo) * row_bytes);
+  unsigned long long win2[K][NP > 0 ? NP : 1];
+  float wins[K];
+#pragma unroll
+  for (int r = 0; r < FS_STRIP + K - 1; ++r) {
+    float v[K];
+    if (CHECK) {
+      const int iy = ybase + r;
+      const float mr = (iy >= iy_lo && iy <= iy_hi) ? 1.f : 0.f;
+      const uint32_t ro = (uint32_t)(min(max(iy, iy_lo), iy_hi) - iy_lo) * row_bytes;
+#pragma unroll
+      for (int kx = 0; kx < K; ++kx) v[kx] = lds_f32(a[kx] + ro) * mr;
+    } else {
+#pragma unroll
+      for (int kx = 0; kx < K; ++kx) {
+        v[kx] = lds_f32(a[kx]);
+        a[kx] += row_bytes;
+      }
+    }
+#pragma unroll
+    for (int pi = 0; pi < NP; ++pi) win2[r % K][pi] = fs_pack(v[2 * pi], v[2 * pi + 1]);
+    if (ODD) wins[r % K] = v[K - 1];
+    if (r >= K - 1) {
+      const int i = r - (K - 1);
+      unsigned long long acc2 = 0ull;
+      float accs = 0.f;
+#pragma unroll
+      for (int ky = 0; ky < K; ++ky) {
+#pragma unroll
+        for (int pi = 0; pi < NP; ++pi)
+          asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2) : "l"(w2[ky][pi]), "l"(win2[(i + ky) % K][pi]));
+        if (ODD) accs = fmaf(ws[ky], wins[(i + ky) % K], accs);
+      }
+      float lo, hi;
+      asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc2));
+      const float res = ODD ? (lo + hi) + accs : lo + hi;
+      if (!CHECK || i < rows_left) __stcs(o + (int64_t)i * out_w, res);
+    }
+  }
+}
+
+template <int K, int NT>
+__global__ void __launch_bounds__(NT, 2) fir_stream_kernel(float* __restrict__ out, const float* __restrict__ x,
+                                                                  const float* __restrict__ kernel, FirStream q) {
+  extern __shared__ __align__(128) float fs_smem[];
+  __shared__ uint64_t bars[2];
+  __shared__ float kf[K * K];
+  const int tid = threadIdx.x;
+  if (tid < K * K) {
+    const int ky = tid / K, kx = tid - ky * K;
+    kf[tid] = kernel[(K - 1 - ky) * K + (K - 1 - kx)];
+  }
+  if (tid == 0) {
+    stream_stage::bar_init(stream_stage::smem_addr(&bars[0]), 1);
+    stream_stage::bar_init(stream_stage::smem_addr(&bars[1]), 1);
+    stream_stage::fence_bar_init();
+  }
+  __syncthreads();
+  const int64_t plane_floats = (int64_t)q.in_h * q.in_w;
+  // item -> (first plane, plane count, first output row, output rows, first / last staged input row)
+  auto decode = [&](int64_t item, int64_t& plane0, int& np, int& oy0, int& rows_out, int& iy_lo, int& iy_hi) {
+    if (q.bands == 1) {
+      plane0 = item * q.P;
+      np = (int)min((int64_t)q.P, q.planes - plane0);
+      oy0 = 0;
+      rows_out = q.out_h;
+      iy_lo = 0;
+      iy_hi = q.in_h - 1;
+    } else {
+      plane0 = item / q.bands;
+      const int band = (int)(item - plane0 * q.bands);
+      np = 1;
+      oy0 = band * q.R;
+      rows_out = min(q.R, q.out_h - oy0);
+      iy_lo = max(oy0 - q.pad_y0, 0);
+      iy_hi = min(oy0 + rows_out - 1 - q.pad_y0 + K - 1, q.in_h - 1);
+    }
+  };
+  auto issue = [&](int64_t item, int s) {
+    int64_t plane0;
+    int np, oy0, rows_out, iy_lo, iy_hi;
+    decode(item, plane0, np, oy0, rows_out, iy_lo, iy_hi);
+    const int n = (int)((np - 1) * plane_floats) + (iy_hi - iy_lo + 1) * q.in_w;
+    stream_stage::issue_chunk(fs_smem + s * q.stage_floats, x + plane0 * plane_floats + (int64_t)iy_lo * q.in_w, n, q.limit,
+                              &bars[s]);
+  };
+  float w[K * K];
+#pragma unroll
+  for (int i = 0; i < K * K; ++i) w[i] = kf[i];
+  FirTaps<K> taps_all;  // every tap column inside the image (all but the border columns)
+  {
+    float ones[K];
+#pragma unroll
+    for (int kx = 0; kx < K; ++kx) ones[kx] = 1.f;
+    fir_taps<K>(taps_all, w, ones);
+  }
+  int64_t item = blockIdx.x;
+  if (tid == 0 && item < q.nitems) issue(item, 0);
+  for (uint32_t k = 0; item < q.nitems; item += gridDim.x, ++k) {
+    const int s = k & 1;
+    if (tid == 0 && item + gridDim.x < q.nitems) issue(item + gridDim.x, s ^ 1);
+    int64_t plane0;
+    int np, oy0, rows_out, iy_lo, iy_hi;
+    decode(item, plane0, np, oy0, rows_out, iy_lo, iy_hi);
+    const float* src = x + plane0 * plane_floats + (int64_t)iy_lo * q.in_w;
+    const uint32_t st_addr = stream_stage::smem_addr(fs_smem + s * q.stage_floats + stream_stage::chunk_shift(src));
+    float* op = out + plane0 * (int64_t)q.out_h * q.out_w;
+    stream_stage::bar_wait(stream_stage::smem_addr(&bars[s]), (k >> 1) & 1);
+    const int units = np * q.strips * q.out_w;
+    for (int u = tid; u < units; u += NT) {
+      const uint32_t v = fdiv((uint32_t)u, q.d_ow);
+      const int ox = u - (int)v * q.out_w;
+      const uint32_t pl = fdiv(v, q.d_strips);
+      const int ly0 = ((int)v - (int)pl * q.strips) * FS_STRIP;  // first output row of the strip inside the band
+      if (ly0 >= rows_out) continue;
+      // tap columns: clamped address + validity folded into this thread's copy of the taps
+      uint32_t pk[K];
+      const int ix0 = ox - q.pad_x0;
+      FirTaps<K> taps = taps_all;
+      if (ix0 < 0 || ix0 + K > q.in_w) {  // border column: some taps fall outside the image
+        float m[K];
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx) m[kx] = (ix0 + kx >= 0 && ix0 + kx < q.in_w) ? 1.f : 0.f;
+        fir_taps<K>(taps, w, m);
+      }
+#pragma unroll
+      for (int kx = 0; kx < K; ++kx) pk[kx] = (uint32_t)min(max(ix0 + kx, 0), q.in_w - 1) * 4u;
+      const uint32_t base = st_addr + (uint32_t)pl * (uint32_t)plane_floats * 4u;
+      const int ybase = oy0 + ly0 - q.pad_y0;  // input row of window row 0
+      float* o = op + (int64_t)pl * q.out_h * q.out_w + (int64_t)(oy0 + ly0) * q.out_w + ox;
+      const int rows_left = rows_out - ly0;
+      if (ybase >= iy_lo && ybase + FS_STRIP + K - 2 <= iy_hi && rows_left >= FS_STRIP)
+        fir_strip<K, false>(taps, pk, base, o, ybase, iy_lo, iy_hi, q.in_w, q.out_w, rows_left);
+      else
+        fir_strip<K, true>(taps, pk, base, o, ybase, iy_lo, iy_hi, q.in_w, q.out_w, rows_left);
+    }
+    __syncthreads();  // every read of stage s is done before the copy of item k + 2 is issued into it
+  }
+}
+
+template <int K>
+bool launch_fir_stream(float* out, const float* x, const float* kernel, int64_t planes, const UfdParams& p,
+                       cudaStream_t st) {
+  if ((((uintptr_t)x) & 15) != 0) return false;
+  constexpr int MAX_STAGE = 11776;  // floats per stage: 46 KB, two stages and two CTAs per SM
+  const int64_t plane_floats = (int64_t)p.in_h * p.in_w;
+  const int ncta = 2 * SPGAN_NUM_SMS;
+  FirStream q;
+  q.in_h = p.in_h; q.in_w = p.in_w; q.out_h = p.out_h; q.out_w = p.out_w; q.pad_x0 = p.pad_x0; q.pad_y0 = p.pad_y0;
+  q.planes = planes;
+  if (plane_floats + 8 <= MAX_STAGE) {
+    // whole planes: as many per item as fit, but no more than spreads the planes over all CTAs
+    int64_t P = (MAX_STAGE - 8) / plane_floats;
+    const int64_t spread = (planes + ncta - 1) / ncta;
+    if (P > spread) P = spread;
+    if (P < 1) P = 1;
+    q.P = (int)P;
+    q.bands = 1;
+    q.R = p.out_h;
+    q.nitems = (planes + P - 1) / P;
+    q.stage_floats = (int)(P * plane_floats + 8 + 31) / 32 * 32;
+  } else {
+    int R = (MAX_STAGE - 8) / p.in_w - (K - 1);
+    if (R < 1) return false;  // a single row group does not fit: tiled kernel
+    if (R > p.out_h) R = p.out_h;
+    const int bands = (p.out_h + R - 1) / R;
+    R = (p.out_h + bands - 1) / bands;
+    q.P = 1;
+    q.bands = bands;
+    q.R = R;
+    q.nitems = planes * bands;
+    q.stage_floats = ((R + K - 1) * p.in_w + 8 + 31) / 32 * 32;
+  }
+  if ((int64_t)q.P * ((q.R + FS_STRIP - 1) / FS_STRIP) * p.out_w >= (1LL << 31)) return false;
+  q.strips = (q.R + FS_STRIP - 1) / FS_STRIP;
+  q.limit = ((uintptr_t)(x + planes * plane_floats)) & ~(uintptr_t)15;
+  q.d_ow = make_fastdiv((uint32_t)p.out_w);
+  q.d_strips = make_fastdiv((uint32_t)q.strips);
+  const size_t smem = (size_t)2 * q.stage_floats * sizeof(float);
+  static bool attr_done[3] = {false, false, false};
+  if (!attr_done[K - 2]) {
+    if (cudaFuncSetAttribute(fir_stream_kernel<K, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             2 * MAX_STAGE * 4 + 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(fir_stream_kernel<K, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             2 * MAX_STAGE * 4 + 1024) != cudaSuccess)
+      return false;
+    attr_done[K - 2] = true;
+  }
+  const unsigned grid = (unsigned)(q.nitems < ncta ? q.nitems : ncta);
+  int nt = FS_THREADS;
+  if (const char* e = getenv("SPGAN_FS_THREADS")) nt = atoi(e) == 512 ? 512 : 256;  // diagnostics
+  if (nt == 512) fir_stream_kernel<K, 512><<<grid, 512, smem, st>>>(out, x, kernel, q);
+  else fir_stream_kernel<K, 256><<<grid, 256, smem, st>>>(out, x, kernel, q);
+  return true;
+}
+
 // Fused tail of the upsampling StyledConv: interleave the four polyphase planes of the transposed conv on the fly,
 // 3x3 FIR, + noise + bias, leaky-ReLU * scale.  HBM traffic = one read of the planes (+ one halo row per band) and one
 // write of the result, instead of scatter-write + FIR read/write + activation read/write.
@@ -473,7 +736,13 @@ extern "C" int spgan_upfirdn2d(float* out, const float* x, const float* kernel, 
   const int tiles_x = (p.out_w + TILE - 1) / TILE, tiles_y = (p.out_h + TILE - 1) / TILE;
   const int64_t blocks = planes * tiles_x * tiles_y;
   bool done = false;
-  if (unit && kh >= 2 && kh <= 4 && pad_x0 <= kh - 1 && pad_y0 <= kh - 1 && p.in_w >= 1) {
+  if (unit && kh >= 2 && kh <= 4 && pad_x0 <= kh - 1 && pad_y0 <= kh - 1 && pad_x1 <= kh - 1 && pad_y1 <= kh - 1 &&
+      p.in_w >= 1 && !spgan_legacy_hbm()) {
+    if (kh == 2) done = launch_fir_stream<2>(out, x, kernel, planes, p, st);
+    if (kh == 3) done = launch_fir_stream<3>(out, x, kernel, planes, p, st);
+    if (kh == 4) done = launch_fir_stream<4>(out, x, kernel, planes, p, st);
+  }
+  if (!done && unit && kh >= 2 && kh <= 4 && pad_x0 <= kh - 1 && pad_y0 <= kh - 1 && p.in_w >= 1) {
     if (kh == 2) done = launch_band<2>(out, x, kernel, planes, p, pad_x1, st);
     if (kh == 3) done = launch_band<3>(out, x, kernel, planes, p, pad_x1, st);
     if (kh == 4) done = launch_band<4>(out, x, kernel, planes, p, pad_x1, st);

@@ -122,6 +122,49 @@ def test_upfirdn2d_large_and_double_backward(dev):
     assert torch.equal(SF().upfirdn2d(x.to(dev), d), x.to(dev))
 
 
+def _legacy(flag):
+    import os
+    if flag:
+        os.environ["SPGAN_LEGACY_HBM_KERNELS"] = "1"
+    else:
+        os.environ.pop("SPGAN_LEGACY_HBM_KERNELS", None)
+
+
+@pytest.mark.parametrize("shape,taps,pad", [
+    ((2, 3, 13, 13), [1, 2, 1], (0, 0)),        # whole planes, tensor end not a multiple of 16 bytes (scalar tail)
+    ((3, 5, 19, 19), [1, 3, 3, 1], (2, 2)),     # several planes per item, plane count not a multiple of the group
+    ((5, 67, 21, 23), [1, 3, 3, 1], (1, 1)),    # more items than resident CTAs, ring of two stages wraps
+    ((1, 2, 150, 131), [1, 3, 3, 1], (2, 1)),   # bands of one plane, asymmetric padding
+    ((1, 3, 384, 384), [1, 2, 1], (0, 0)),      # configs[4] largest resolution: bands
+    ((1, 2, 105, 105), [1, 2, 1], (2, 2)),      # gradient of the generator's blur
+    ((2, 2, 9, 40), [1, 1], (1, 0)),            # 2x2 taps
+    ((600, 1, 5, 7), [1, 3, 3, 1], (2, 2)),     # many tiny planes
+], ids=lambda v: "x".join(map(str, v)) if isinstance(v, tuple) and len(v) == 4 else None)
+def test_upfirdn2d_streamed_kernel_vs_torch_and_legacy(dev, shape, taps, pad):
+    """The bulk-copy staged FIR (csrc/upfirdn2d.cu: fir_stream_kernel) against an fp64 torch correlation and against the
+    band / tiled kernels it replaces."""
+    k = torch.from_numpy(O.make_kernel(taps)).to(dev)
+    x = synth.randn_t(11, "fs_%s" % (shape,), shape).to(dev)
+    _legacy(False)
+    y = SF().upfirdn2d(x, k, pad=pad)
+    _legacy(True)
+    try:
+        y_old = SF().upfirdn2d(x, k, pad=pad)
+    finally:
+        _legacy(False)
+    B, C, H, W = shape
+    xp = F.pad(x.double().reshape(B * C, 1, H, W), (pad[0], pad[1], pad[0], pad[1]))
+    want = F.conv2d(xp, torch.flip(k.double(), [0, 1])[None, None]).reshape(B, C, *y.shape[2:])
+    assert y.shape == want.shape
+    assert K.rel_err(K.t2n(y), want.cpu().numpy()) < 1e-6
+    assert K.rel_err(K.t2n(y), K.t2n(y_old)) < 1e-6
+    # a view whose data pointer is not 16-byte aligned takes the fallback and still agrees
+    flat = torch.zeros(x.numel() + 1, device=dev)
+    flat[1:] = x.reshape(-1)
+    y_off = SF().upfirdn2d(flat[1:].view(shape), k, pad=pad)
+    assert K.rel_err(K.t2n(y_off), want.cpu().numpy()) < 1e-6
+
+
 # ---------------------------------------------------------------------------------------------- gather
 def test_gather_indices_bit_exact(dev):
     g = K.load("grids.npz")
@@ -169,6 +212,37 @@ def test_gather_shared_grid_and_channel_chunks(dev):
     want = O.grid_sample_border(z, np.repeat(grid, 3, 0))
     got = SF().sphere_gather_raw(torch.from_numpy(z).to(dev), torch.from_numpy(grid).to(dev))
     assert K.rel_err(K.t2n(got), want) < 2e-6
+
+
+@pytest.mark.parametrize("B,C,h,w,shared", [(2, 5, 7, 9, False), (3, 37, 23, 23, True), (2, 3, 17, 17, False),
+                                            (9, 20, 35, 35, True), (1, 2, 130, 70, True), (2, 1, 11, 11, False)])
+def test_gather_streamed_kernel_vs_oracle_and_legacy(dev, B, C, h, w, shared):
+    """The bulk-copy staged gather (csrc/sphere_gather.cu: sphere_gather_stream_kernel) against the oracle and against the
+    L1-gather kernel it replaces (same corner arithmetic; the blend may contract its first product differently, so the
+    two agree to an ulp, not bit for bit); also the coordinate-encoding variant and the strided output of the flat-concat
+    buffer."""
+    cp = K.test_cp(2, 7, 27)
+    g1 = O.gen_sampling_grid(h, w, cp)
+    grid = g1 if shared else np.concatenate([g1 + np.float32(0.003 * i) for i in range(B)], 0)
+    z = synth.randn(5, "gsz%d" % C, (B, C, h, w))
+    want = O.grid_sample_border(z, np.repeat(g1, B, 0) if shared else grid)
+    zt, gt = torch.from_numpy(z).to(dev), torch.from_numpy(grid).to(dev)
+    _legacy(False)
+    got = SF().sphere_gather_raw(zt, gt)
+    buf = torch.zeros(B, C + 4, 3 * h, 3 * w, device=dev)
+    SF().sphere_gather_raw(zt, gt, out=buf, out_bstride=C + 4, out_coff=2)
+    enc = SF().sphere_gather_raw(zt[:, :3].contiguous(), gt, encode=True) if C >= 3 else None
+    _legacy(True)
+    try:
+        old = SF().sphere_gather_raw(zt, gt)
+        enc_old = SF().sphere_gather_raw(zt[:, :3].contiguous(), gt, encode=True) if C >= 3 else None
+    finally:
+        _legacy(False)
+    assert K.rel_err(K.t2n(got), want) < 2e-6
+    assert K.rel_err(K.t2n(got), K.t2n(old)) < 5e-7
+    assert torch.equal(buf[:, 2:2 + C], got) and float(buf[:, :2].abs().max()) == 0 and float(buf[:, 2 + C:].abs().max()) == 0
+    if enc is not None:
+        assert K.rel_err(K.t2n(enc), K.t2n(enc_old)) < 1e-6
 
 
 # ---------------------------------------------------------------------------------------------- conv passes

@@ -28,6 +28,9 @@ def main():
     ap.add_argument("--budget-s", type=float, default=45.0)
     ap.add_argument("--sweep", action="store_true", help="run the configs[4] sweep (C x H x B, forward and backward)")
     ap.add_argument("--max-gb", type=float, default=6.0, help="skip sweep cases whose tensors exceed this many GiB")
+    ap.add_argument("--only", default="", help="comma-separated substrings: run only the fixed cases whose name contains one")
+    ap.add_argument("--legacy-ab", action="store_true",
+                    help="also time the pre-streaming FIR / gather kernels (SPGAN_LEGACY_HBM_KERNELS=1) beside the defaults")
     args = ap.parse_args()
     torch.cuda.set_device(0)
     lib.require_device()
@@ -107,7 +110,21 @@ def main():
         out["clocks"] = dict(last_clocks)
         print(json.dumps(out), flush=True)
 
+    only = [t for t in args.only.split(",") if t]
+
+    def legacy_ab(name, fn, **kw):
+        """Time `fn` again with the pre-streaming kernels selected (the library reads the variable per call)."""
+        if not args.legacy_ab:
+            return
+        os.environ["SPGAN_LEGACY_HBM_KERNELS"] = "1"
+        try:
+            report(name + " [legacy kernel]", timed(fn), **kw)
+        finally:
+            os.environ.pop("SPGAN_LEGACY_HBM_KERNELS", None)
+
     def case(name, build):
+        if only and not any(t in name for t in only):
+            return
         if time.time() - t_start > args.budget_s:
             print(json.dumps({"case": name, "skipped": "time budget"}), flush=True)
             return
@@ -155,12 +172,22 @@ def main():
         x = rn(32, 512, 105, 105)
         ms = timed(lambda: SF.upfirdn2d(x, k3, pad=(0, 0)))
         report("upfirdn2d 3x3 pad 0 (G blur) (32,512,105,105)", ms, bytes_=4 * 32 * 512 * (105 * 105 + 103 * 103))
+        legacy_ab("upfirdn2d 3x3 pad 0 (G blur) (32,512,105,105)", lambda: SF.upfirdn2d(x, k3, pad=(0, 0)),
+                  bytes_=4 * 32 * 512 * (105 * 105 + 103 * 103))
+        x = rn(8, 512, 105, 105)
+        ms = timed(lambda: SF.upfirdn2d(x, k3, pad=(0, 0)))
+        report("upfirdn2d 3x3 pad 0 (G blur, training batch) (8,512,105,105)", ms, bytes_=4 * 8 * 512 * (105 * 105 + 103 * 103))
     case("upfirdn2d G blur", fir_g)
 
     def fir_d():
         x = rn(32, 256, 101, 101)
         ms = timed(lambda: SF.upfirdn2d(x, k4, pad=(2, 2)))
         report("upfirdn2d 4x4 pad 2 (D blur) (32,256,101,101)", ms, bytes_=4 * 32 * 256 * (101 * 101 + 102 * 102))
+        legacy_ab("upfirdn2d 4x4 pad 2 (D blur) (32,256,101,101)", lambda: SF.upfirdn2d(x, k4, pad=(2, 2)),
+                  bytes_=4 * 32 * 256 * (101 * 101 + 102 * 102))
+        x = rn(32, 512, 50, 50)
+        ms = timed(lambda: SF.upfirdn2d(x, k4, pad=(2, 2)))
+        report("upfirdn2d 4x4 pad 2 (D blur) (32,512,50,50)", ms, bytes_=4 * 32 * 512 * (50 * 50 + 51 * 51))
     case("upfirdn2d D blur", fir_d)
 
     def fir_up():
@@ -211,6 +238,12 @@ def main():
         grid = torch.from_numpy(grids.sampling_grid(35, 35, cp)).to(dev)
         ms = timed(lambda: SF.sphere_gather_raw(z, grid))
         report("sphere_gather (32,256,35,35) -> 9x", ms, bytes_=4 * z.numel() * 10 + grid.numel() * 4)
+        legacy_ab("sphere_gather (32,256,35,35) -> 9x", lambda: SF.sphere_gather_raw(z, grid),
+                  bytes_=4 * z.numel() * 10 + grid.numel() * 4)
+        z = rn(8, 256, 35, 35)
+        gb = grid.expand(8, -1, -1, -1).contiguous()
+        ms = timed(lambda: SF.sphere_gather_raw(z, gb))
+        report("sphere_gather, per-sample grids (training) (8,256,35,35) -> 9x", ms, bytes_=4 * z.numel() * 10 + gb.numel() * 4)
     case("sphere_gather", gather)
 
     # ---- operand packer ----
