@@ -189,9 +189,19 @@ __global__ void __launch_bounds__(GS_THREADS, 2) sphere_gather_stream_kernel(flo
           v[1] = cosf(v[1] * 3.14159274101257324f);
           v[2] = sinf(v[2] * 3.14159274101257324f);
         }
+        if (nc == CC) {  // running pointer: one 64-bit add per store instead of a multiply-add chain per channel
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (4 * qd + j < nc) __stcs(o + (int64_t)(4 * qd + j) * opix, v[j]);
+          for (int j = 0; j < 4; ++j) {
+            __stcs(o, v[j]);
+            o += opix;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (4 * qd + j < nc) __stcs(o, v[j]);
+            o += opix;
+          }
+        }
       }
     }
     __syncthreads();  // every read of the tile is done before the next item overwrites it

@@ -302,11 +302,17 @@ bool launch_band(float* out, const float* x, const float* kernel, int64_t planes
 // discriminator's Blur (4x4, pad 2 / 1) and for their gradients.  Persistent CTAs (two per SM); a work item is a group of
 // P whole planes (small images) or a band of R output rows of one plane (large images) — in both cases ONE contiguous run
 // of floats, fetched by one bulk-async copy into a two-stage ring (stream_stage.cuh) while the previous item is filtered.
-// The rows are staged exactly as they lie in memory (no zero borders): a thread owns one output column of a strip of S
-// rows, clamps its K tap columns once and folds the column validity into its own copy of the taps, so the inner loop is a
-// sliding window of K shared-memory reads and K*K FMAs per output with no bounds checks; staged rows outside the image are
-// skipped by a per-row predicate.
-constexpr int FS_THREADS = 256;
+//
+// The rows are staged exactly as they lie in memory (no zero borders).  A thread owns ONE output column for the whole
+// kernel (threads = G groups x out_w columns; the groups share the strips of an item), so everything that depends on the
+// column is set up once per item: each of its K taps is a running shared-memory address plus a row stride, and a tap that
+// falls outside the image points at a zero word with stride 0 — no column masks, no bounds checks.  The inner loop is a
+// sliding window over the staged rows: K shared-memory reads per row, taps held as packed pairs so that a K x K stencil is
+// K * (K/2) FFMA2 (+ K FFMA for K = 3) per output.  Only the first / last strips of an image (rows in the zero padding)
+// take a variant with a clamped row index and a zero multiplier.  ncu (profiles/r2_ncu_hbm_kernels.txt): the first
+// streamed version decoded (plane, strip, column) and rebuilt its column state for every 8 outputs — 33 / 44
+// instructions per output for K = 3 / 4 and 65-71 % of the issue slots busy at 0.85 / 0.61 of the HBM peak.
+constexpr int FS_MAX_THREADS = 320;
 constexpr int FS_STRIP = 8;
 
 struct FirStream {
@@ -315,6 +321,7 @@ struct FirStream {
   int bands;   // bands per plane (P == 1 when bands > 1)
   int R;       // output rows per band
   int strips;  // ceil(R / FS_STRIP)
+  int G;       // thread groups sharing the strips of an item (threads g * out_w + column)
   int stage_floats;
   int64_t planes, nitems;
   uintptr_t limit;  // 16-byte floor of the end of x
@@ -332,55 +339,40 @@ __device__ __forceinline__ unsigned long long fs_pack(float lo, float hi) {
   return r;
 }
 
-// One strip of FS_STRIP output rows of one column: sliding window over the staged rows.  The K taps of a row are held as
-// K/2 packed pairs (+ one scalar for K = 3), so a K x K stencil costs K * (K/2) FFMA2 (+ K FFMA) and one or two adds per
-// output instead of K*K FFMA.  CHECK = false: every window row is staged and every output row exists (interior strips):
-// K running shared-memory addresses, no predicates.  CHECK = true (first / last strips): rows outside the image are read
-// from a clamped row and multiplied by zero, missing output rows are not stored — still branch-free.
 template <int K>
 struct FirTaps {
   unsigned long long w2[K][K / 2 > 0 ? K / 2 : 1];  // packed column pairs of every tap row
   float ws[K];                                      // last column when K is odd
 };
 
-template <int K>
-__device__ __forceinline__ void fir_taps(FirTaps<K>& t, const float (&w)[K * K], const float (&m)[K]) {
-#pragma unroll
-  for (int ky = 0; ky < K; ++ky) {
-#pragma unroll
-    for (int pi = 0; pi < K / 2; ++pi)
-      t.w2[ky][pi] = fs_pack(w[ky * K + 2 * pi] * m[2 * pi], w[ky * K + 2 * pi + 1] * m[2 * pi + 1]);
-    t.ws[ky] = (K & 1) ? w[ky * K + K - 1] * m[K - 1] : 0.f;
-  }
-}
-
+// One strip of FS_STRIP output rows of one column.  a0[kx] = shared-memory address of tap column kx in staged row 0 of the
+// plane (or of the zero word), rs[kx] = its row stride in bytes (0 for the zero word).  CHECK = false: every window row is
+// staged and every output row exists (interior strips).  CHECK = true (first / last strips): rows outside the image are
+// read from a clamped row and multiplied by zero, missing output rows are not stored — still branch-free.
 template <int K, bool CHECK>
-__device__ __forceinline__ void fir_strip(const FirTaps<K>& t, const uint32_t (&pk)[K], uint32_t base, float* __restrict__ o,
-                                          int ybase, int iy_lo, int iy_hi, int in_w, int out_w, int rows_left) {
+__device__ __forceinline__ void fir_strip(const FirTaps<K>& t, const uint32_t (&a0)[K], const uint32_t (&rs)[K],
+                                          float* __restrict__ o, int row0, int nrows, int out_w, int rows_left) {
   constexpr int NP = K / 2;
   constexpr bool ODD = (K & 1) != 0;
-  const auto& w2 = t.w2;
-  const auto& ws = t.ws;
   uint32_t a[K];
-  const uint32_t row_bytes = (uint32_t)in_w * 4u;
 #pragma unroll
-  for (int kx = 0; kx < K; ++kx) a[kx] = base + pk[kx] + (CHECK ? 0u : (uint32_t)(ybase - iy_lo) * row_bytes);
+  for (int kx = 0; kx < K; ++kx) a[kx] = CHECK ? a0[kx] : a0[kx] + (uint32_t)row0 * rs[kx];
   unsigned long long win2[K][NP > 0 ? NP : 1];
   float wins[K];
 #pragma unroll
   for (int r = 0; r < FS_STRIP + K - 1; ++r) {
     float v[K];
     if (CHECK) {
-      const int iy = ybase + r;
-      const float mr = (iy >= iy_lo && iy <= iy_hi) ? 1.f : 0.f;
-      const uint32_t ro = (uint32_t)(min(max(iy, iy_lo), iy_hi) - iy_lo) * row_bytes;
+      const int ry = row0 + r;  // staged row index; outside [0, nrows) = zero padding
+      const float mr = (ry >= 0 && ry < nrows) ? 1.f : 0.f;
+      const uint32_t rc = (uint32_t)min(max(ry, 0), nrows - 1);
 #pragma unroll
-      for (int kx = 0; kx < K; ++kx) v[kx] = lds_f32(a[kx] + ro) * mr;
+      for (int kx = 0; kx < K; ++kx) v[kx] = lds_f32(a[kx] + rc * rs[kx]) * mr;
     } else {
 #pragma unroll
       for (int kx = 0; kx < K; ++kx) {
         v[kx] = lds_f32(a[kx]);
-        a[kx] += row_bytes;
+        a[kx] += rs[kx];
       }
     }
 #pragma unroll
@@ -394,29 +386,32 @@ __device__ __forceinline__ void fir_strip(const FirTaps<K>& t, const uint32_t (&
       for (int ky = 0; ky < K; ++ky) {
 #pragma unroll
         for (int pi = 0; pi < NP; ++pi)
-          asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2) : "l"(w2[ky][pi]), "l"(win2[(i + ky) % K][pi]));
-        if (ODD) accs = fmaf(ws[ky], wins[(i + ky) % K], accs);
+          asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2) : "l"(t.w2[ky][pi]), "l"(win2[(i + ky) % K][pi]));
+        if (ODD) accs = fmaf(t.ws[ky], wins[(i + ky) % K], accs);
       }
       float lo, hi;
       asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc2));
       const float res = ODD ? (lo + hi) + accs : lo + hi;
-      if (!CHECK || i < rows_left) __stcs(o + (int64_t)i * out_w, res);
+      if (!CHECK || i < rows_left) __stcs(o, res);
+      o += out_w;
     }
   }
 }
 
-template <int K, int NT>
-__global__ void __launch_bounds__(NT, 2) fir_stream_kernel(float* __restrict__ out, const float* __restrict__ x,
-                                                                  const float* __restrict__ kernel, FirStream q) {
+template <int K>
+__global__ void __launch_bounds__(FS_MAX_THREADS, 2) fir_stream_kernel(float* __restrict__ out, const float* __restrict__ x,
+                                                                      const float* __restrict__ kernel, FirStream q) {
   extern __shared__ __align__(128) float fs_smem[];
   __shared__ uint64_t bars[2];
   __shared__ float kf[K * K];
+  __shared__ float zero_word;
   const int tid = threadIdx.x;
   if (tid < K * K) {
     const int ky = tid / K, kx = tid - ky * K;
     kf[tid] = kernel[(K - 1 - ky) * K + (K - 1 - kx)];
   }
   if (tid == 0) {
+    zero_word = 0.f;
     stream_stage::bar_init(stream_stage::smem_addr(&bars[0]), 1);
     stream_stage::bar_init(stream_stage::smem_addr(&bars[1]), 1);
     stream_stage::fence_bar_init();
@@ -450,16 +445,19 @@ __global__ void __launch_bounds__(NT, 2) fir_stream_kernel(float* __restrict__ o
     stream_stage::issue_chunk(fs_smem + s * q.stage_floats, x + plane0 * plane_floats + (int64_t)iy_lo * q.in_w, n, q.limit,
                               &bars[s]);
   };
-  float w[K * K];
+  FirTaps<K> taps;
 #pragma unroll
-  for (int i = 0; i < K * K; ++i) w[i] = kf[i];
-  FirTaps<K> taps_all;  // every tap column inside the image (all but the border columns)
-  {
-    float ones[K];
+  for (int ky = 0; ky < K; ++ky) {
 #pragma unroll
-    for (int kx = 0; kx < K; ++kx) ones[kx] = 1.f;
-    fir_taps<K>(taps_all, w, ones);
+    for (int pi = 0; pi < K / 2; ++pi) taps.w2[ky][pi] = fs_pack(kf[ky * K + 2 * pi], kf[ky * K + 2 * pi + 1]);
+    taps.ws[ky] = (K & 1) ? kf[ky * K + K - 1] : 0.f;
   }
+  // thread -> (group, first column); wide images (out_w > threads) walk their columns with one group
+  const int nt = blockDim.x;
+  const int grp = (int)fdiv((uint32_t)tid, q.d_ow);
+  const int col0 = tid - grp * q.out_w;
+  const uint32_t zero_addr = stream_stage::smem_addr(&zero_word);
+  const uint32_t row_bytes = (uint32_t)q.in_w * 4u;
   int64_t item = blockIdx.x;
   if (tid == 0 && item < q.nitems) issue(item, 0);
   for (uint32_t k = 0; item < q.nitems; item += gridDim.x, ++k) {
@@ -470,35 +468,37 @@ __global__ void __launch_bounds__(NT, 2) fir_stream_kernel(float* __restrict__ o
     decode(item, plane0, np, oy0, rows_out, iy_lo, iy_hi);
     const float* src = x + plane0 * plane_floats + (int64_t)iy_lo * q.in_w;
     const uint32_t st_addr = stream_stage::smem_addr(fs_smem + s * q.stage_floats + stream_stage::chunk_shift(src));
-    float* op = out + plane0 * (int64_t)q.out_h * q.out_w;
+    float* op = out + plane0 * (int64_t)q.out_h * q.out_w + (int64_t)oy0 * q.out_w;
+    const int nrows = iy_hi - iy_lo + 1;  // staged rows of the (last) plane of the item
+    const int units = np * q.strips;
     stream_stage::bar_wait(stream_stage::smem_addr(&bars[s]), (k >> 1) & 1);
-    const int units = np * q.strips * q.out_w;
-    for (int u = tid; u < units; u += NT) {
-      const uint32_t v = fdiv((uint32_t)u, q.d_ow);
-      const int ox = u - (int)v * q.out_w;
-      const uint32_t pl = fdiv(v, q.d_strips);
-      const int ly0 = ((int)v - (int)pl * q.strips) * FS_STRIP;  // first output row of the strip inside the band
-      if (ly0 >= rows_out) continue;
-      // tap columns: clamped address + validity folded into this thread's copy of the taps
-      uint32_t pk[K];
-      const int ix0 = ox - q.pad_x0;
-      FirTaps<K> taps = taps_all;
-      if (ix0 < 0 || ix0 + K > q.in_w) {  // border column: some taps fall outside the image
-        float m[K];
+    if (grp < q.G) {
+      for (int ox = col0; ox < q.out_w; ox += nt) {
+        uint32_t a0[K], rs[K];
 #pragma unroll
-        for (int kx = 0; kx < K; ++kx) m[kx] = (ix0 + kx >= 0 && ix0 + kx < q.in_w) ? 1.f : 0.f;
-        fir_taps<K>(taps, w, m);
+        for (int kx = 0; kx < K; ++kx) {
+          const int ix = ox - q.pad_x0 + kx;
+          const bool ok = ix >= 0 && ix < q.in_w;
+          a0[kx] = ok ? st_addr + (uint32_t)ix * 4u : zero_addr;
+          rs[kx] = ok ? row_bytes : 0u;
+        }
+        for (int u = grp; u < units; u += q.G) {
+          const int pl = (int)fdiv((uint32_t)u, q.d_strips);
+          const int ly0 = (u - pl * q.strips) * FS_STRIP;  // first output row of the strip inside the band
+          const int rows_left = rows_out - ly0;
+          if (rows_left <= 0) continue;
+          uint32_t ap[K];
+          const uint32_t poff = (uint32_t)pl * (uint32_t)plane_floats * 4u;
+#pragma unroll
+          for (int kx = 0; kx < K; ++kx) ap[kx] = a0[kx] + (rs[kx] ? poff : 0u);
+          const int row0 = oy0 + ly0 - q.pad_y0 - iy_lo;  // staged row of window row 0
+          float* o = op + (int64_t)pl * q.out_h * q.out_w + (int64_t)ly0 * q.out_w + ox;
+          if (row0 >= 0 && row0 + FS_STRIP + K - 2 < nrows && rows_left >= FS_STRIP)
+            fir_strip<K, false>(taps, ap, rs, o, row0, nrows, q.out_w, rows_left);
+          else
+            fir_strip<K, true>(taps, ap, rs, o, row0, nrows, q.out_w, rows_left);
+        }
       }
-#pragma unroll
-      for (int kx = 0; kx < K; ++kx) pk[kx] = (uint32_t)min(max(ix0 + kx, 0), q.in_w - 1) * 4u;
-      const uint32_t base = st_addr + (uint32_t)pl * (uint32_t)plane_floats * 4u;
-      const int ybase = oy0 + ly0 - q.pad_y0;  // input row of window row 0
-      float* o = op + (int64_t)pl * q.out_h * q.out_w + (int64_t)(oy0 + ly0) * q.out_w + ox;
-      const int rows_left = rows_out - ly0;
-      if (ybase >= iy_lo && ybase + FS_STRIP + K - 2 <= iy_hi && rows_left >= FS_STRIP)
-        fir_strip<K, false>(taps, pk, base, o, ybase, iy_lo, iy_hi, q.in_w, q.out_w, rows_left);
-      else
-        fir_strip<K, true>(taps, pk, base, o, ybase, iy_lo, iy_hi, q.in_w, q.out_w, rows_left);
     }
     __syncthreads();  // every read of stage s is done before the copy of item k + 2 is issued into it
   }
@@ -537,26 +537,39 @@ bool launch_fir_stream(float* out, const float* x, const float* kernel, int64_t 
     q.nitems = planes * bands;
     q.stage_floats = ((R + K - 1) * p.in_w + 8 + 31) / 32 * 32;
   }
-  if ((int64_t)q.P * ((q.R + FS_STRIP - 1) / FS_STRIP) * p.out_w >= (1LL << 31)) return false;
   q.strips = (q.R + FS_STRIP - 1) / FS_STRIP;
+  // threads = G groups x out_w columns (rounded up to whole warps): the G that wastes the fewest lanes and strip rounds
+  const int units = q.P * q.strips;
+  int best_g = 1, best_nt = FS_MAX_THREADS;
+  if (p.out_w <= FS_MAX_THREADS) {
+    double best = -1.0;
+    for (int g = 1; g * p.out_w <= FS_MAX_THREADS && g <= units; ++g) {
+      const int nt = (g * p.out_w + 31) / 32 * 32;
+      if (nt < 96 && (g + 1) * p.out_w <= FS_MAX_THREADS && g + 1 <= units) continue;  // too few warps to hide latency
+      const double lanes = (double)(g * p.out_w) / nt;
+      const double rounds = (double)units / (double)(((units + g - 1) / g) * g);
+      const double score = lanes * rounds * (0.85 + 0.15 * nt / FS_MAX_THREADS);
+      if (score > best) {
+        best = score;
+        best_g = g;
+        best_nt = nt;
+      }
+    }
+  }
+  q.G = best_g;
   q.limit = ((uintptr_t)(x + planes * plane_floats)) & ~(uintptr_t)15;
   q.d_ow = make_fastdiv((uint32_t)p.out_w);
   q.d_strips = make_fastdiv((uint32_t)q.strips);
   const size_t smem = (size_t)2 * q.stage_floats * sizeof(float);
   static bool attr_done[3] = {false, false, false};
   if (!attr_done[K - 2]) {
-    if (cudaFuncSetAttribute(fir_stream_kernel<K, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             2 * MAX_STAGE * 4 + 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(fir_stream_kernel<K, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             2 * MAX_STAGE * 4 + 1024) != cudaSuccess)
+    if (cudaFuncSetAttribute(fir_stream_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * MAX_STAGE * 4 + 1024) !=
+        cudaSuccess)
       return false;
     attr_done[K - 2] = true;
   }
   const unsigned grid = (unsigned)(q.nitems < ncta ? q.nitems : ncta);
-  int nt = FS_THREADS;
-  if (const char* e = getenv("SPGAN_FS_THREADS")) nt = atoi(e) == 512 ? 512 : 256;  // diagnostics
-  if (nt == 512) fir_stream_kernel<K, 512><<<grid, 512, smem, st>>>(out, x, kernel, q);
-  else fir_stream_kernel<K, 256><<<grid, 256, smem, st>>>(out, x, kernel, q);
+  fir_stream_kernel<K><<<grid, best_nt, smem, st>>>(out, x, kernel, q);
   return true;
 }
 
