@@ -322,6 +322,7 @@ struct FirStream {
   int R;       // output rows per band
   int strips;  // ceil(R / FS_STRIP)
   int G;       // thread groups sharing the strips of an item (threads g * out_w + column)
+  int kh, kw;  // kernel size (<= K: smaller kernels are zero-padded)
   int stage_floats;
   int64_t planes, nitems;
   uintptr_t limit;  // 16-byte floor of the end of x
@@ -349,7 +350,7 @@ struct FirTaps {
 // plane (or of the zero word), rs[kx] = its row stride in bytes (0 for the zero word).  CHECK = false: every window row is
 // staged and every output row exists (interior strips).  CHECK = true (first / last strips): rows outside the image are
 // read from a clamped row and multiplied by zero, missing output rows are not stored — still branch-free.
-template <int K, bool CHECK>
+template <int K, int DOWN, bool CHECK>
 __device__ __forceinline__ void fir_strip(const FirTaps<K>& t, const uint32_t (&a0)[K], const uint32_t (&rs)[K],
                                           float* __restrict__ o, int row0, int nrows, int out_w, int rows_left) {
   constexpr int NP = K / 2;
@@ -360,7 +361,7 @@ __device__ __forceinline__ void fir_strip(const FirTaps<K>& t, const uint32_t (&
   unsigned long long win2[K][NP > 0 ? NP : 1];
   float wins[K];
 #pragma unroll
-  for (int r = 0; r < FS_STRIP + K - 1; ++r) {
+  for (int r = 0; r < (FS_STRIP - 1) * DOWN + K; ++r) {
     float v[K];
     if (CHECK) {
       const int ry = row0 + r;  // staged row index; outside [0, nrows) = zero padding
@@ -378,16 +379,16 @@ __device__ __forceinline__ void fir_strip(const FirTaps<K>& t, const uint32_t (&
 #pragma unroll
     for (int pi = 0; pi < NP; ++pi) win2[r % K][pi] = fs_pack(v[2 * pi], v[2 * pi + 1]);
     if (ODD) wins[r % K] = v[K - 1];
-    if (r >= K - 1) {
-      const int i = r - (K - 1);
+    if (r >= K - 1 && (r - (K - 1)) % DOWN == 0) {  // down-sampling keeps every DOWN-th window position
+      const int i = (r - (K - 1)) / DOWN;
       unsigned long long acc2 = 0ull;
       float accs = 0.f;
 #pragma unroll
       for (int ky = 0; ky < K; ++ky) {
 #pragma unroll
         for (int pi = 0; pi < NP; ++pi)
-          asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2) : "l"(t.w2[ky][pi]), "l"(win2[(i + ky) % K][pi]));
-        if (ODD) accs = fmaf(t.ws[ky], wins[(i + ky) % K], accs);
+          asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2) : "l"(t.w2[ky][pi]), "l"(win2[(i * DOWN + ky) % K][pi]));
+        if (ODD) accs = fmaf(t.ws[ky], wins[(i * DOWN + ky) % K], accs);
       }
       float lo, hi;
       asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc2));
@@ -398,7 +399,39 @@ __device__ __forceinline__ void fir_strip(const FirTaps<K>& t, const uint32_t (&
   }
 }
 
-template <int K>
+// Up-sampling by two (zero stuffing): an output sees only the taps whose parity matches its position — two columns and two
+// rows of a 4 x 4 kernel.  A thread owns one output column, so its column parity, its two input columns and its 4 x 2 taps
+// are fixed; consecutive output rows alternate between tap rows (0, 2) and (1, 3) and advance one input row every second
+// output.  ODD0 = parity of the first output row's tap origin (uniform over an item).  a0 / rs as in fir_strip.
+template <bool ODD0>
+__device__ __forceinline__ void fir_strip_up2(const float (&wc)[4][2], const uint32_t (&a0)[2], const uint32_t (&rs)[2],
+                                              float* __restrict__ o, int j0, int nrows, int out_w, int rows_left) {
+  constexpr int NR = ODD0 ? FS_STRIP / 2 + 1 : FS_STRIP / 2 + 2;
+  float v[NR][2];
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    const int ry = j0 + r;
+    const float mr = (ry >= 0 && ry < nrows) ? 1.f : 0.f;
+    const uint32_t rc = (uint32_t)min(max(ry, 0), nrows - 1);
+    v[r][0] = lds_f32(a0[0] + rc * rs[0]) * mr;
+    v[r][1] = lds_f32(a0[1] + rc * rs[1]) * mr;
+  }
+#pragma unroll
+  for (int i = 0; i < FS_STRIP; ++i) {
+    constexpr int dummy = 0;
+    (void)dummy;
+    const int A = ODD0 ? (i >> 1) : ((i + 1) >> 1);
+    const int par = ((ODD0 ? 1 : 0) + i) & 1;
+    float res = wc[par][0] * v[A][0];
+    res = fmaf(wc[par][1], v[A][1], res);
+    res = fmaf(wc[par + 2][0], v[A + 1][0], res);
+    res = fmaf(wc[par + 2][1], v[A + 1][1], res);
+    if (i < rows_left) __stcs(o, res);
+    o += out_w;
+  }
+}
+
+template <int K, int UP, int DOWN>
 __global__ void __launch_bounds__(FS_MAX_THREADS, 2) fir_stream_kernel(float* __restrict__ out, const float* __restrict__ x,
                                                                       const float* __restrict__ kernel, FirStream q) {
   extern __shared__ __align__(128) float fs_smem[];
@@ -406,9 +439,9 @@ __global__ void __launch_bounds__(FS_MAX_THREADS, 2) fir_stream_kernel(float* __
   __shared__ float kf[K * K];
   __shared__ float zero_word;
   const int tid = threadIdx.x;
-  if (tid < K * K) {
+  if (tid < K * K) {  // flipped taps, zero-padded to K x K when the kernel is smaller (up / down variants)
     const int ky = tid / K, kx = tid - ky * K;
-    kf[tid] = kernel[(K - 1 - ky) * K + (K - 1 - kx)];
+    kf[tid] = (ky < q.kh && kx < q.kw) ? kernel[(q.kh - 1 - ky) * q.kw + (q.kw - 1 - kx)] : 0.f;
   }
   if (tid == 0) {
     zero_word = 0.f;
@@ -433,8 +466,9 @@ __global__ void __launch_bounds__(FS_MAX_THREADS, 2) fir_stream_kernel(float* __
       np = 1;
       oy0 = band * q.R;
       rows_out = min(q.R, q.out_h - oy0);
-      iy_lo = max(oy0 - q.pad_y0, 0);
-      iy_hi = min(oy0 + rows_out - 1 - q.pad_y0 + K - 1, q.in_h - 1);
+      const int y_first = oy0 * DOWN - q.pad_y0, y_last = (oy0 + rows_out - 1) * DOWN - q.pad_y0 + K - 1;
+      iy_lo = max(UP == 2 ? (y_first + 1) >> 1 : y_first, 0);
+      iy_hi = min(UP == 2 ? y_last >> 1 : y_last, q.in_h - 1);
     }
   };
   auto issue = [&](int64_t item, int s) {
@@ -474,29 +508,62 @@ __global__ void __launch_bounds__(FS_MAX_THREADS, 2) fir_stream_kernel(float* __
     stream_stage::bar_wait(stream_stage::smem_addr(&bars[s]), (k >> 1) & 1);
     if (grp < q.G) {
       for (int ox = col0; ox < q.out_w; ox += nt) {
-        uint32_t a0[K], rs[K];
+        if (UP == 1) {
+          uint32_t a0[K], rs[K];
 #pragma unroll
-        for (int kx = 0; kx < K; ++kx) {
-          const int ix = ox - q.pad_x0 + kx;
-          const bool ok = ix >= 0 && ix < q.in_w;
-          a0[kx] = ok ? st_addr + (uint32_t)ix * 4u : zero_addr;
-          rs[kx] = ok ? row_bytes : 0u;
-        }
-        for (int u = grp; u < units; u += q.G) {
-          const int pl = (int)fdiv((uint32_t)u, q.d_strips);
-          const int ly0 = (u - pl * q.strips) * FS_STRIP;  // first output row of the strip inside the band
-          const int rows_left = rows_out - ly0;
-          if (rows_left <= 0) continue;
-          uint32_t ap[K];
-          const uint32_t poff = (uint32_t)pl * (uint32_t)plane_floats * 4u;
+          for (int kx = 0; kx < K; ++kx) {
+            const int ix = ox * DOWN - q.pad_x0 + kx;
+            const bool ok = ix >= 0 && ix < q.in_w;
+            a0[kx] = ok ? st_addr + (uint32_t)ix * 4u : zero_addr;
+            rs[kx] = ok ? row_bytes : 0u;
+          }
+          for (int u = grp; u < units; u += q.G) {
+            const int pl = (int)fdiv((uint32_t)u, q.d_strips);
+            const int ly0 = (u - pl * q.strips) * FS_STRIP;  // first output row of the strip inside the band
+            const int rows_left = rows_out - ly0;
+            if (rows_left <= 0) continue;
+            uint32_t ap[K];
+            const uint32_t poff = (uint32_t)pl * (uint32_t)plane_floats * 4u;
 #pragma unroll
-          for (int kx = 0; kx < K; ++kx) ap[kx] = a0[kx] + (rs[kx] ? poff : 0u);
-          const int row0 = oy0 + ly0 - q.pad_y0 - iy_lo;  // staged row of window row 0
-          float* o = op + (int64_t)pl * q.out_h * q.out_w + (int64_t)ly0 * q.out_w + ox;
-          if (row0 >= 0 && row0 + FS_STRIP + K - 2 < nrows && rows_left >= FS_STRIP)
-            fir_strip<K, false>(taps, ap, rs, o, row0, nrows, q.out_w, rows_left);
-          else
-            fir_strip<K, true>(taps, ap, rs, o, row0, nrows, q.out_w, rows_left);
+            for (int kx = 0; kx < K; ++kx) ap[kx] = a0[kx] + (rs[kx] ? poff : 0u);
+            const int row0 = (oy0 + ly0) * DOWN - q.pad_y0 - iy_lo;  // staged row of window row 0
+            float* o = op + (int64_t)pl * q.out_h * q.out_w + (int64_t)ly0 * q.out_w + ox;
+            if (row0 >= 0 && row0 + (FS_STRIP - 1) * DOWN + K - 1 < nrows && rows_left >= FS_STRIP)
+              fir_strip<K, DOWN, false>(taps, ap, rs, o, row0, nrows, q.out_w, rows_left);
+            else
+              fir_strip<K, DOWN, true>(taps, ap, rs, o, row0, nrows, q.out_w, rows_left);
+          }
+        } else {
+          // up 2: this column's tap parity, its two input columns and its 4 x 2 taps
+          const int c = ox - q.pad_x0;
+          const int kx0 = c & 1;
+          const int ix0 = (c + kx0) >> 1;
+          uint32_t a0[2], rs[2];
+          float wc[4][2];
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            const bool ok = ix0 + b >= 0 && ix0 + b < q.in_w;
+            a0[b] = ok ? st_addr + (uint32_t)(ix0 + b) * 4u : zero_addr;
+            rs[b] = ok ? row_bytes : 0u;
+#pragma unroll
+            for (int ky = 0; ky < 4; ++ky) wc[ky][b] = kx0 ? kf[ky * K + 1 + 2 * b] : kf[ky * K + 2 * b];
+          }
+          const int par0 = (oy0 - q.pad_y0) & 1;  // strips start at multiples of 8 rows: one parity per item
+          for (int u = grp; u < units; u += q.G) {
+            const int pl = (int)fdiv((uint32_t)u, q.d_strips);
+            const int ly0 = (u - pl * q.strips) * FS_STRIP;
+            const int rows_left = rows_out - ly0;
+            if (rows_left <= 0) continue;
+            uint32_t ap[2];
+            const uint32_t poff = (uint32_t)pl * (uint32_t)plane_floats * 4u;
+            ap[0] = a0[0] + (rs[0] ? poff : 0u);
+            ap[1] = a0[1] + (rs[1] ? poff : 0u);
+            const int t0 = oy0 + ly0 - q.pad_y0;
+            const int j0 = ((t0 + par0) >> 1) - iy_lo;  // staged row of the first output's upper input row
+            float* o = op + (int64_t)pl * q.out_h * q.out_w + (int64_t)ly0 * q.out_w + ox;
+            if (par0) fir_strip_up2<true>(wc, ap, rs, o, j0, nrows, q.out_w, rows_left);
+            else fir_strip_up2<false>(wc, ap, rs, o, j0, nrows, q.out_w, rows_left);
+          }
         }
       }
     }
@@ -504,15 +571,17 @@ __global__ void __launch_bounds__(FS_MAX_THREADS, 2) fir_stream_kernel(float* __
   }
 }
 
-template <int K>
+template <int K, int UP, int DOWN>
 bool launch_fir_stream(float* out, const float* x, const float* kernel, int64_t planes, const UfdParams& p,
                        cudaStream_t st) {
+  static_assert(UP == 1 || (K == 4 && DOWN == 1), "up 2 uses the zero-padded 4 x 4 form");
   if ((((uintptr_t)x) & 15) != 0) return false;
   constexpr int MAX_STAGE = 11776;  // floats per stage: 46 KB, two stages and two CTAs per SM
   const int64_t plane_floats = (int64_t)p.in_h * p.in_w;
   const int ncta = 2 * SPGAN_NUM_SMS;
   FirStream q;
   q.in_h = p.in_h; q.in_w = p.in_w; q.out_h = p.out_h; q.out_w = p.out_w; q.pad_x0 = p.pad_x0; q.pad_y0 = p.pad_y0;
+  q.kh = p.kh; q.kw = p.kw;
   q.planes = planes;
   if (plane_floats + 8 <= MAX_STAGE) {
     // whole planes: as many per item as fit, but no more than spreads the planes over all CTAs
@@ -526,16 +595,22 @@ bool launch_fir_stream(float* out, const float* x, const float* kernel, int64_t 
     q.nitems = (planes + P - 1) / P;
     q.stage_floats = (int)(P * plane_floats + 8 + 31) / 32 * 32;
   } else {
-    int R = (MAX_STAGE - 8) / p.in_w - (K - 1);
-    if (R < 1) return false;  // a single row group does not fit: tiled kernel
+    // bands: R output rows need ((R - 1) * DOWN + K - 1) / UP + 2 input rows at most
+    const int rows_fit = (MAX_STAGE - 8) / p.in_w;
+    int R = ((rows_fit - 2) * UP - (K - 1)) / DOWN + 1;
+    if (rows_fit < 3 || R < 1) return false;  // a single row group does not fit: tiled / polyphase kernel
+    R = R / FS_STRIP * FS_STRIP;              // whole strips, so that every band starts on the same tap parity
+    if (R < FS_STRIP) return false;
     if (R > p.out_h) R = p.out_h;
     const int bands = (p.out_h + R - 1) / R;
-    R = (p.out_h + bands - 1) / bands;
+    if (bands > 1) {
+      R = ((p.out_h + bands - 1) / bands + FS_STRIP - 1) / FS_STRIP * FS_STRIP;
+    }
     q.P = 1;
-    q.bands = bands;
+    q.bands = (p.out_h + R - 1) / R;
     q.R = R;
-    q.nitems = planes * bands;
-    q.stage_floats = ((R + K - 1) * p.in_w + 8 + 31) / 32 * 32;
+    q.nitems = planes * q.bands;
+    q.stage_floats = (rows_fit * p.in_w + 8 + 31) / 32 * 32;
   }
   q.strips = (q.R + FS_STRIP - 1) / FS_STRIP;
   // threads = G groups x out_w columns (rounded up to whole warps): the G that wastes the fewest lanes and strip rounds
@@ -561,15 +636,15 @@ bool launch_fir_stream(float* out, const float* x, const float* kernel, int64_t 
   q.d_ow = make_fastdiv((uint32_t)p.out_w);
   q.d_strips = make_fastdiv((uint32_t)q.strips);
   const size_t smem = (size_t)2 * q.stage_floats * sizeof(float);
-  static bool attr_done[3] = {false, false, false};
-  if (!attr_done[K - 2]) {
-    if (cudaFuncSetAttribute(fir_stream_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * MAX_STAGE * 4 + 1024) !=
-        cudaSuccess)
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(fir_stream_kernel<K, UP, DOWN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             2 * MAX_STAGE * 4 + 1024) != cudaSuccess)
       return false;
-    attr_done[K - 2] = true;
+    attr_done = true;
   }
   const unsigned grid = (unsigned)(q.nitems < ncta ? q.nitems : ncta);
-  fir_stream_kernel<K><<<grid, best_nt, smem, st>>>(out, x, kernel, q);
+  fir_stream_kernel<K, UP, DOWN><<<grid, best_nt, smem, st>>>(out, x, kernel, q);
   return true;
 }
 
@@ -751,10 +826,17 @@ extern "C" int spgan_upfirdn2d(float* out, const float* x, const float* kernel, 
   bool done = false;
   if (unit && kh >= 2 && kh <= 4 && pad_x0 <= kh - 1 && pad_y0 <= kh - 1 && pad_x1 <= kh - 1 && pad_y1 <= kh - 1 &&
       p.in_w >= 1 && !spgan_legacy_hbm()) {
-    if (kh == 2) done = launch_fir_stream<2>(out, x, kernel, planes, p, st);
-    if (kh == 3) done = launch_fir_stream<3>(out, x, kernel, planes, p, st);
-    if (kh == 4) done = launch_fir_stream<4>(out, x, kernel, planes, p, st);
+    if (kh == 2) done = launch_fir_stream<2, 1, 1>(out, x, kernel, planes, p, st);
+    if (kh == 3) done = launch_fir_stream<3, 1, 1>(out, x, kernel, planes, p, st);
+    if (kh == 4) done = launch_fir_stream<4, 1, 1>(out, x, kernel, planes, p, st);
   }
+  // Upsample / Downsample of models/ops.py:32-79 and each other's gradient: up or down by two, kernels up to 4 x 4
+  const bool small_k = kh >= 1 && kw >= 1 && kh <= 4 && kw <= 4 && pad_x0 >= 0 && pad_y0 >= 0 && pad_x0 <= 3 && pad_y0 <= 3 &&
+                       pad_x1 <= 3 && pad_y1 <= 3 && p.in_w >= 1 && !spgan_legacy_hbm();
+  if (!done && small_k && up_x == 2 && up_y == 2 && down_x == 1 && down_y == 1)
+    done = launch_fir_stream<4, 2, 1>(out, x, kernel, planes, p, st);
+  if (!done && small_k && up_x == 1 && up_y == 1 && down_x == 2 && down_y == 2)
+    done = launch_fir_stream<4, 1, 2>(out, x, kernel, planes, p, st);
   if (!done && unit && kh >= 2 && kh <= 4 && pad_x0 <= kh - 1 && pad_y0 <= kh - 1 && p.in_w >= 1) {
     if (kh == 2) done = launch_band<2>(out, x, kernel, planes, p, pad_x1, st);
     if (kh == 3) done = launch_band<3>(out, x, kernel, planes, p, pad_x1, st);

@@ -165,6 +165,37 @@ def test_upfirdn2d_streamed_kernel_vs_torch_and_legacy(dev, shape, taps, pad):
     assert K.rel_err(K.t2n(y_off), want.cpu().numpy()) < 1e-6
 
 
+@pytest.mark.parametrize("shape,taps,up,down,pad", [
+    ((2, 3, 53, 53), [1, 3, 3, 1], 2, 1, (2, 1)),     # Upsample of ToRGB's skip (models/ops.py:32-55)
+    ((2, 3, 17, 29), [1, 2, 1], 2, 1, (1, 0)),        # 3 taps, odd tap origin
+    ((1, 2, 150, 131), [1, 3, 3, 1], 2, 1, (2, 1)),   # bands
+    ((3, 4, 101, 101), [1, 3, 3, 1], 1, 2, (1, 1)),   # Downsample (models/ops.py:58-79)
+    ((1, 2, 384, 384), [1, 3, 3, 1], 1, 2, (1, 1)),   # bands
+    ((2, 2, 106, 106), [1, 3, 3, 1], 1, 2, (1, 2)),   # gradient of the up-sampling above
+    ((5, 40, 12, 12), [1, 3, 3, 1], 2, 1, (2, 1)),    # several planes per item
+], ids=lambda v: "x".join(map(str, v)) if isinstance(v, tuple) and len(v) == 4 else None)
+def test_upfirdn2d_streamed_up_down_vs_oracle_and_legacy(dev, shape, taps, up, down, pad):
+    """Up / down by two through the bulk-copy staged kernel (fir_stream_kernel<4, 2, 1> / <4, 1, 2>) against the oracle
+    and the polyphase kernel it replaces, forward and gradient."""
+    k = torch.from_numpy(O.make_kernel(taps) * np.float32(up * up)).to(dev)
+    x = synth.randn_t(12, "fsud_%s" % (shape,), shape).to(dev).requires_grad_(True)
+    _legacy(False)
+    y = SF().upfirdn2d(x, k, up=up, down=down, pad=pad)
+    go = synth.randn_t(12, "fsud_go_%s" % (shape,), y.shape).to(dev)
+    gx, = torch.autograd.grad(y, x, go)
+    _legacy(True)
+    try:
+        y_old = SF().upfirdn2d(x, k, up=up, down=down, pad=pad)
+        gx_old, = torch.autograd.grad(y_old, x, go)
+    finally:
+        _legacy(False)
+    want = O.upfirdn2d(K.t2n(x), K.t2n(k), up=(up, up), down=(down, down), pad=(pad[0], pad[1], pad[0], pad[1]))
+    assert y.shape == want.shape
+    assert K.rel_err(K.t2n(y), want) < 1e-6
+    assert K.rel_err(K.t2n(y), K.t2n(y_old)) < 1e-6
+    assert K.rel_err(K.t2n(gx), K.t2n(gx_old)) < 1e-6
+
+
 # ---------------------------------------------------------------------------------------------- gather
 def test_gather_indices_bit_exact(dev):
     g = K.load("grids.npz")

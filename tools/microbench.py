@@ -194,7 +194,17 @@ def main():
         x = rn(32, 64, 53, 53)
         ms = timed(lambda: SF.upfirdn2d(x, k3, up=2, down=1, pad=(1, 0)))
         oh = 53 * 2 + 1 - 3 + 1
-        report("upfirdn2d up=2 3x3 (template up/down kernel) (32,64,53,53)", ms, bytes_=4 * 32 * 64 * (53 * 53 + oh * oh))
+        report("upfirdn2d up=2 3x3 (32,64,53,53)", ms, bytes_=4 * 32 * 64 * (53 * 53 + oh * oh))
+        legacy_ab("upfirdn2d up=2 3x3 (32,64,53,53)", lambda: SF.upfirdn2d(x, k3, up=2, down=1, pad=(1, 0)),
+                  bytes_=4 * 32 * 64 * (53 * 53 + oh * oh))
+        x = rn(32, 256, 53, 53)
+        ms = timed(lambda: SF.upfirdn2d(x, k4 * 4, up=2, down=1, pad=(2, 1)))
+        report("upfirdn2d up=2 4x4 pad (2,1) (Upsample) (32,256,53,53)", ms, bytes_=4 * 32 * 256 * (53 * 53 + 106 * 106))
+        x = rn(32, 256, 101, 101)
+        ms = timed(lambda: SF.upfirdn2d(x, k4, up=1, down=2, pad=(1, 1)))
+        report("upfirdn2d down=2 4x4 pad (1,1) (Downsample) (32,256,101,101)", ms, bytes_=4 * 32 * 256 * (101 * 101 + 50 * 50))
+        legacy_ab("upfirdn2d down=2 4x4 pad (1,1) (Downsample) (32,256,101,101)",
+                  lambda: SF.upfirdn2d(x, k4, up=1, down=2, pad=(1, 1)), bytes_=4 * 32 * 256 * (101 * 101 + 50 * 50))
     case("upfirdn2d up2", fir_up)
 
     def upblur():
