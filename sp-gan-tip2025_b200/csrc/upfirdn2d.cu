@@ -631,6 +631,11 @@ bool launch_fir_stream(float* out, const float* x, const float* kernel, int64_t 
       }
     }
   }
+  if (p.out_w > FS_MAX_THREADS) {
+    // wide images: every thread walks `passes` columns; size the block so that the last pass is as full as the others
+    const int passes = (p.out_w + FS_MAX_THREADS - 1) / FS_MAX_THREADS;
+    best_nt = ((p.out_w + passes - 1) / passes + 31) / 32 * 32;
+  }
   q.G = best_g;
   q.limit = ((uintptr_t)(x + planes * plane_floats)) & ~(uintptr_t)15;
   q.d_ow = make_fastdiv((uint32_t)p.out_w);

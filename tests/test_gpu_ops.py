@@ -139,6 +139,8 @@ def _legacy(flag):
     ((1, 2, 105, 105), [1, 2, 1], (2, 2)),      # gradient of the generator's blur
     ((2, 2, 9, 40), [1, 1], (1, 0)),            # 2x2 taps
     ((600, 1, 5, 7), [1, 3, 3, 1], (2, 2)),     # many tiny planes
+    ((1, 2, 40, 400), [1, 3, 3, 1], (2, 2)),    # wider than a thread block: two balanced column passes
+    ((1, 1, 30, 700), [1, 2, 1], (1, 1)),       # three column passes
 ], ids=lambda v: "x".join(map(str, v)) if isinstance(v, tuple) and len(v) == 4 else None)
 def test_upfirdn2d_streamed_kernel_vs_torch_and_legacy(dev, shape, taps, pad):
     """The bulk-copy staged FIR (csrc/upfirdn2d.cu: fir_stream_kernel) against an fp64 torch correlation and against the
