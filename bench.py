@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--cpu-sample-patches", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs under ncu only: skip the end-to-end leg")
+    ap.add_argument("--no-hbm", action="store_true", help="skip the hbm_kernels side table (FIR / gather / bias-act timed alone)")
     ap.add_argument("--profile-calls", action="store_true", help="add per-entry-point CUDA-event times of one extra step")
     ap.add_argument("--workload", default="panorama", choices=["panorama", "train", "pano768"],
                     help="panorama = BASELINE configs[1] (default, the headline); train = configs[2], full G+D step; "
@@ -434,11 +435,79 @@ def run_ours(args):
         out["pano768"] = pano768
     if train is not None:
         out["train"] = train
+    if not sharded and not args.no_hbm and not args.skip_e2e and rank == 0 and world == 1:
+        try:
+            out["hbm_kernels"] = measure_hbm_kernels(dev, local)
+        except Exception as e:  # the headline line must not depend on the side table
+            out["hbm_kernels"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
     if not args.no_cpu_baseline and not sharded:
         out["cpu_baseline"] = cpu_baseline_object(args)
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_hbm_kernels(dev, local):
+    """The HBM-bound kernels of the path (north_star: gather / upfirdn2d / bias-act against the B200 HBM peak) timed alone in
+    this run: CUDA events around 40 back-to-back launches after 5 warm-up launches, inputs larger than L2, clocks sampled during
+    the loops.  `frac` = algorithmic bytes / time / MEASURED_PEAKS.json hbm_gbs (the copy peak; burst figure: each kernel runs
+    alone).  tools/microbench.py is the full version (graph replays, legacy A/B, configs[4] sweep)."""
+    import torch
+    import spgan_b200.functional as SF
+    from spgan_b200 import grids, panorama
+    hbm = float(load_peaks().get("hbm_gbs", 6549.8))
+    g = torch.Generator(device=dev).manual_seed(3)
+    rn = lambda *s: torch.randn(*s, device=dev, generator=g)
+    k3 = torch.tensor([[1., 2., 1.], [2., 4., 2.], [1., 2., 1.]], device=dev) / 4
+    k4 = torch.tensor([1., 3., 3., 1.], device=dev)
+    k4 = (k4[None, :] * k4[:, None]) / 64
+    pl = panorama.plan(384, 768)
+    cp, _ = panorama.patch_inputs(pl, 2, 7, 27, pl["lat_h"], pl["lat_w"])
+    cases = []
+    x = rn(32, 512, 101, 101)
+    b = rn(512)
+    cases.append(("bias_act fwd (32,512,101,101)", lambda: SF.bias_act(x, b, None, 3, 0, 0.2, 2 ** 0.5), 8.0 * x.numel()))
+    go = rn(32, 512, 101, 101)
+    cases.append(("bias_act bwd + bias reduction (32,512,101,101)",
+                  lambda: SF.FusedLeakyReLUFunctionBackward.apply(go, x, 0.2, 2 ** 0.5), 12.0 * x.numel()))
+    xg = rn(32, 512, 105, 105)
+    cases.append(("upfirdn2d 3x3 pad 0 (32,512,105,105)", lambda: SF.upfirdn2d(xg, k3, pad=(0, 0)),
+                  4.0 * 32 * 512 * (105 * 105 + 103 * 103)))
+    xd = rn(32, 256, 101, 101)
+    cases.append(("upfirdn2d 4x4 pad 2 (32,256,101,101)", lambda: SF.upfirdn2d(xd, k4, pad=(2, 2)),
+                  4.0 * 32 * 256 * (101 * 101 + 102 * 102)))
+    cases.append(("upfirdn2d down 2 4x4 (32,256,101,101)", lambda: SF.upfirdn2d(xd, k4, up=1, down=2, pad=(1, 1)),
+                  4.0 * 32 * 256 * (101 * 101 + 50 * 50)))
+    xu = rn(32, 256, 53, 53)
+    cases.append(("upfirdn2d up 2 4x4 (32,256,53,53)", lambda: SF.upfirdn2d(xu, k4 * 4, up=2, down=1, pad=(2, 1)),
+                  4.0 * 32 * 256 * (53 * 53 + 106 * 106)))
+    z = rn(32, 256, 35, 35)
+    grid = torch.from_numpy(grids.sampling_grid(35, 35, cp)).to(dev)
+    cases.append(("sphere_gather (32,256,35,35) -> 9x", lambda: SF.sphere_gather_raw(z, grid), 4.0 * z.numel() * 10 + grid.numel() * 4))
+    out = []
+    sampler = ClockSampler(local)
+    sampler.start()
+    with torch.no_grad():
+        for name, fn, nbytes in cases:
+            for _ in range(5):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n = 40
+            e0.record()
+            for _ in range(n):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / n
+            gbs = nbytes / (ms / 1e3) / 1e9
+            out.append({"case": name, "ms": round(ms, 4), "achieved_GBs": round(gbs, 1), "frac": round(gbs / hbm, 3)})
+    clocks = sampler.stop()
+    del cases, x, go, xg, xd, xu, z
+    torch.cuda.empty_cache()
+    return {"peak_GBs": hbm, "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy bandwidth)", "clocks": clocks, "cases": out,
+            "note": "each kernel timed alone (40 launches, CUDA events, eager: the Python launch overhead is inside the figure), "
+                    "inputs larger than L2"}
 
 
 def ncu_traffic():

@@ -57,6 +57,18 @@ static inline bool spgan_legacy_hbm() {
   return e != nullptr && e[0] == '1';
 }
 
+// Opt a kernel into more than 48 KB of dynamic shared memory, once per device (the attribute is per context; the library is
+// used one process per GPU, but nothing here assumes it).
+template <class Kernel>
+static inline bool spgan_allow_smem(Kernel kernel, int bytes, bool (&done)[64]) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
+  if (done[dev]) return true;
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return false;
+  done[dev] = true;
+  return true;
+}
+
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // Grid size for a grid-stride kernel: enough CTAs for `work` items at `per_block` each, capped at

@@ -248,17 +248,11 @@ bool launch_gather_stream(float* out, const float* z, const float* grid, int B, 
   q.nitems = (int64_t)B * chunks * psplit;
   q.limit = ((uintptr_t)(z + (int64_t)B * C * HW)) & ~(uintptr_t)15;
   const size_t smem = (size_t)bytes(cc);
-  static bool attr_done = false;
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(sphere_gather_stream_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)SMEM_MAX) != cudaSuccess ||
-        cudaFuncSetAttribute(sphere_gather_stream_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)SMEM_MAX) != cudaSuccess ||
-        cudaFuncSetAttribute(sphere_gather_stream_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)SMEM_MAX) != cudaSuccess)
-      return false;
-    attr_done = true;
-  }
+  static bool done_a[64] = {false}, done_b[64] = {false}, done_c[64] = {false};
+  if (!spgan_allow_smem(sphere_gather_stream_kernel<2, false>, (int)SMEM_MAX, done_a) ||
+      !spgan_allow_smem(sphere_gather_stream_kernel<1, false>, (int)SMEM_MAX, done_b) ||
+      !spgan_allow_smem(sphere_gather_stream_kernel<1, true>, (int)SMEM_MAX, done_c))
+    return false;
   const unsigned grid_n = (unsigned)(q.nitems < ncta ? q.nitems : ncta);
   if (encode) sphere_gather_stream_kernel<1, true><<<grid_n, GS_THREADS, smem, st>>>(out, z, grid, q);
   else if (cc == 8) sphere_gather_stream_kernel<2, false><<<grid_n, GS_THREADS, smem, st>>>(out, z, grid, q);

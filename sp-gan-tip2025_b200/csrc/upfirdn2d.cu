@@ -323,6 +323,9 @@ struct FirStream {
   int strips;  // ceil(R / FS_STRIP)
   int G;       // thread groups sharing the strips of an item (threads g * out_w + column)
   int kh, kw;  // kernel size (<= K: smaller kernels are zero-padded)
+  int n_int, int_lo;             // interior columns [int_lo, int_lo + n_int): all K taps inside the image (0 = uniform mapping)
+  int n_bord, Gb, border_base;   // border columns, their thread groups, first thread of the border warp
+  FastDiv d_int;
   int stage_floats;
   int64_t planes, nitems;
   uintptr_t limit;  // 16-byte floor of the end of x
@@ -350,11 +353,13 @@ struct FirTaps {
 // plane (or of the zero word), rs[kx] = its row stride in bytes (0 for the zero word).  CHECK = false: every window row is
 // staged and every output row exists (interior strips).  CHECK = true (first / last strips): rows outside the image are
 // read from a clamped row and multiplied by zero, missing output rows are not stored — still branch-free.
-template <int K, int DOWN, bool CHECK>
+template <int K, int DOWN, bool CHECK, bool INTERIOR>
 __device__ __forceinline__ void fir_strip(const FirTaps<K>& t, const uint32_t (&a0)[K], const uint32_t (&rs)[K],
                                           float* __restrict__ o, int row0, int nrows, int out_w, int rows_left) {
   constexpr int NP = K / 2;
   constexpr bool ODD = (K & 1) != 0;
+  // INTERIOR: all K taps of the column lie inside the image, so they sit at a0[0] + 4 * kx — ONE running address with
+  // immediate offsets (LDS takes register + immediate only) instead of K running addresses
   uint32_t a[K];
 #pragma unroll
   for (int kx = 0; kx < K; ++kx) a[kx] = CHECK ? a0[kx] : a0[kx] + (uint32_t)row0 * rs[kx];
@@ -367,8 +372,18 @@ __device__ __forceinline__ void fir_strip(const FirTaps<K>& t, const uint32_t (&
       const int ry = row0 + r;  // staged row index; outside [0, nrows) = zero padding
       const float mr = (ry >= 0 && ry < nrows) ? 1.f : 0.f;
       const uint32_t rc = (uint32_t)min(max(ry, 0), nrows - 1);
+      if (INTERIOR) {
+        const uint32_t ar = a[0] + rc * rs[0];
 #pragma unroll
-      for (int kx = 0; kx < K; ++kx) v[kx] = lds_f32(a[kx] + rc * rs[kx]) * mr;
+        for (int kx = 0; kx < K; ++kx) v[kx] = lds_f32(ar + 4u * kx) * mr;
+      } else {
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx) v[kx] = lds_f32(a[kx] + rc * rs[kx]) * mr;
+      }
+    } else if (INTERIOR) {
+#pragma unroll
+      for (int kx = 0; kx < K; ++kx) v[kx] = lds_f32(a[0] + 4u * kx);
+      a[0] += rs[0];
     } else {
 #pragma unroll
       for (int kx = 0; kx < K; ++kx) {
@@ -396,6 +411,38 @@ __device__ __forceinline__ void fir_strip(const FirTaps<K>& t, const uint32_t (&
       if (!CHECK || i < rows_left) __stcs(o, res);
       o += out_w;
     }
+  }
+}
+
+// All strips of one output column that fall to thread group `grp` of `groups` (UP == 1).
+template <int K, int DOWN, bool INTERIOR>
+__device__ __forceinline__ void fir_column(const FirTaps<K>& taps, const FirStream& q, int ox, int grp, int groups, int units,
+                                           uint32_t st_addr, uint32_t zero_addr, uint32_t plane_bytes, float* __restrict__ op,
+                                           int oy0, int rows_out, int iy_lo, int nrows) {
+  const uint32_t row_bytes = (uint32_t)q.in_w * 4u;
+  uint32_t a0[K], rs[K];
+#pragma unroll
+  for (int kx = 0; kx < K; ++kx) {
+    const int ix = ox * DOWN - q.pad_x0 + kx;
+    const bool ok = INTERIOR || (ix >= 0 && ix < q.in_w);
+    a0[kx] = ok ? st_addr + (uint32_t)ix * 4u : zero_addr;
+    rs[kx] = ok ? row_bytes : 0u;
+  }
+  for (int u = grp; u < units; u += groups) {
+    const int pl = (int)fdiv((uint32_t)u, q.d_strips);
+    const int ly0 = (u - pl * q.strips) * FS_STRIP;  // first output row of the strip inside the band
+    const int rows_left = rows_out - ly0;
+    if (rows_left <= 0) continue;
+    uint32_t ap[K];
+    const uint32_t poff = (uint32_t)pl * plane_bytes;
+#pragma unroll
+    for (int kx = 0; kx < K; ++kx) ap[kx] = a0[kx] + (rs[kx] ? poff : 0u);
+    const int row0 = (oy0 + ly0) * DOWN - q.pad_y0 - iy_lo;  // staged row of window row 0
+    float* o = op + (int64_t)pl * q.out_h * q.out_w + (int64_t)ly0 * q.out_w + ox;
+    if (row0 >= 0 && row0 + (FS_STRIP - 1) * DOWN + K - 1 < nrows && rows_left >= FS_STRIP)
+      fir_strip<K, DOWN, false, INTERIOR>(taps, ap, rs, o, row0, nrows, q.out_w, rows_left);
+    else
+      fir_strip<K, DOWN, true, INTERIOR>(taps, ap, rs, o, row0, nrows, q.out_w, rows_left);
   }
 }
 
@@ -506,33 +553,25 @@ __global__ void __launch_bounds__(FS_MAX_THREADS, 2) fir_stream_kernel(float* __
     const int nrows = iy_hi - iy_lo + 1;  // staged rows of the (last) plane of the item
     const int units = np * q.strips;
     stream_stage::bar_wait(stream_stage::smem_addr(&bars[s]), (k >> 1) & 1);
-    if (grp < q.G) {
+    if (UP == 1 && q.n_int > 0) {
+      // split mapping: interior columns (all taps inside the image) on the leading warps, the few border columns on one
+      // trailing warp, so that no warp runs both variants
+      if (tid < q.G * q.n_int) {
+        const int g2 = (int)fdiv((uint32_t)tid, q.d_int);
+        fir_column<K, DOWN, true>(taps, q, q.int_lo + tid - g2 * q.n_int, g2, q.G, units, st_addr, zero_addr,
+                                  (uint32_t)plane_floats * 4u, op, oy0, rows_out, iy_lo, nrows);
+      } else if (tid >= q.border_base && tid - q.border_base < q.Gb * q.n_bord) {
+        const int j = tid - q.border_base;
+        const int g2 = j / q.n_bord, b = j - g2 * q.n_bord;
+        const int ox = b < q.int_lo ? b : q.n_int + b;  // columns left of the interior, then right of it
+        fir_column<K, DOWN, false>(taps, q, ox, g2, q.Gb, units, st_addr, zero_addr, (uint32_t)plane_floats * 4u, op, oy0,
+                                   rows_out, iy_lo, nrows);
+      }
+    } else if (grp < q.G) {
       for (int ox = col0; ox < q.out_w; ox += nt) {
         if (UP == 1) {
-          uint32_t a0[K], rs[K];
-#pragma unroll
-          for (int kx = 0; kx < K; ++kx) {
-            const int ix = ox * DOWN - q.pad_x0 + kx;
-            const bool ok = ix >= 0 && ix < q.in_w;
-            a0[kx] = ok ? st_addr + (uint32_t)ix * 4u : zero_addr;
-            rs[kx] = ok ? row_bytes : 0u;
-          }
-          for (int u = grp; u < units; u += q.G) {
-            const int pl = (int)fdiv((uint32_t)u, q.d_strips);
-            const int ly0 = (u - pl * q.strips) * FS_STRIP;  // first output row of the strip inside the band
-            const int rows_left = rows_out - ly0;
-            if (rows_left <= 0) continue;
-            uint32_t ap[K];
-            const uint32_t poff = (uint32_t)pl * (uint32_t)plane_floats * 4u;
-#pragma unroll
-            for (int kx = 0; kx < K; ++kx) ap[kx] = a0[kx] + (rs[kx] ? poff : 0u);
-            const int row0 = (oy0 + ly0) * DOWN - q.pad_y0 - iy_lo;  // staged row of window row 0
-            float* o = op + (int64_t)pl * q.out_h * q.out_w + (int64_t)ly0 * q.out_w + ox;
-            if (row0 >= 0 && row0 + (FS_STRIP - 1) * DOWN + K - 1 < nrows && rows_left >= FS_STRIP)
-              fir_strip<K, DOWN, false>(taps, ap, rs, o, row0, nrows, q.out_w, rows_left);
-            else
-              fir_strip<K, DOWN, true>(taps, ap, rs, o, row0, nrows, q.out_w, rows_left);
-          }
+          fir_column<K, DOWN, false>(taps, q, ox, grp, q.G, units, st_addr, zero_addr, (uint32_t)plane_floats * 4u, op, oy0,
+                                     rows_out, iy_lo, nrows);
         } else {
           // up 2: this column's tap parity, its two input columns and its 4 x 2 taps
           const int c = ox - q.pad_x0;
@@ -631,6 +670,44 @@ bool launch_fir_stream(float* out, const float* x, const float* kernel, int64_t 
       }
     }
   }
+  q.n_int = 0; q.int_lo = 0; q.n_bord = 0; q.Gb = 1; q.border_base = 0;
+  q.d_int = make_fastdiv(1);
+  if (UP == 1 && DOWN == 1 && p.out_w + 32 <= FS_MAX_THREADS) {  // (down 2 is bound by its strided shared-memory reads)
+    // interior columns: 0 <= ox * DOWN - pad_x0 and ox * DOWN - pad_x0 + K - 1 <= in_w - 1
+    const int lo = (p.pad_x0 + DOWN - 1) / DOWN;
+    int hi = (p.in_w - K + p.pad_x0) >= 0 ? (p.in_w - K + p.pad_x0) / DOWN : -1;  // last interior column
+    if (hi > p.out_w - 1) hi = p.out_w - 1;
+    const int n_int = hi - lo + 1, n_bord = p.out_w - n_int;
+    if (n_int >= 8 && n_bord <= 32) {
+      double best = -1.0;
+      int g_best = 0, nt_best = 0;
+      const int bw = n_bord > 0 ? 32 : 0;  // one trailing warp for the border columns
+      for (int g = 1; g * n_int + bw <= FS_MAX_THREADS && g <= units; ++g) {
+        const int lead = (g * n_int + 31) / 32 * 32;
+        if (lead + bw > FS_MAX_THREADS) break;
+        if (lead + bw < 96 && (g + 1) * n_int + bw <= FS_MAX_THREADS && g + 1 <= units) continue;
+        const double lanes = (double)(g * n_int) / lead;
+        const double rounds = (double)units / (double)(((units + g - 1) / g) * g);
+        const double score = lanes * rounds * (0.85 + 0.15 * (lead + bw) / FS_MAX_THREADS);
+        if (score > best) {
+          best = score;
+          g_best = g;
+          nt_best = lead + bw;
+        }
+      }
+      if (g_best > 0) {
+        best_g = g_best;
+        best_nt = nt_best;
+        q.n_int = n_int;
+        q.int_lo = lo;
+        q.n_bord = n_bord;
+        q.border_base = nt_best - bw;
+        q.Gb = n_bord > 0 ? (32 / n_bord < units ? 32 / n_bord : units) : 1;
+        if (q.Gb < 1) q.Gb = 1;
+        q.d_int = make_fastdiv((uint32_t)n_int);
+      }
+    }
+  }
   if (p.out_w > FS_MAX_THREADS) {
     // wide images: every thread walks `passes` columns; size the block so that the last pass is as full as the others
     const int passes = (p.out_w + FS_MAX_THREADS - 1) / FS_MAX_THREADS;
@@ -641,13 +718,8 @@ bool launch_fir_stream(float* out, const float* x, const float* kernel, int64_t 
   q.d_ow = make_fastdiv((uint32_t)p.out_w);
   q.d_strips = make_fastdiv((uint32_t)q.strips);
   const size_t smem = (size_t)2 * q.stage_floats * sizeof(float);
-  static bool attr_done = false;
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(fir_stream_kernel<K, UP, DOWN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             2 * MAX_STAGE * 4 + 1024) != cudaSuccess)
-      return false;
-    attr_done = true;
-  }
+  static bool attr_done[64] = {false};
+  if (!spgan_allow_smem(fir_stream_kernel<K, UP, DOWN>, 2 * MAX_STAGE * 4 + 1024, attr_done)) return false;
   const unsigned grid = (unsigned)(q.nitems < ncta ? q.nitems : ncta);
   fir_stream_kernel<K, UP, DOWN><<<grid, best_nt, smem, st>>>(out, x, kernel, q);
   return true;
