@@ -10,7 +10,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "sp-gan-tip2025_b200", "csrc", "libspgan_b200.so")
 KEYS = ["UTCHMMA", "UTMALDG", "UTMALDG.IM2COL", "UTMALDG.2CTA", "LDTM", "UTCBAR", "UTCBAR.2CTA", "UCGABAR_ARV", "SYNCS", "FFMA2", "FMUL2",
-        "FADD2", "HMMA", "LDG.E.128", "STG.E.128", "STS.128", "MUFU"]
+        "FADD2", "HMMA", "LDG.E.128", "STG.E.128", "STS.128", "LDS.128", "UBLKCP", "MUFU"]
 
 
 def main():
