@@ -57,6 +57,14 @@ int spgan_upfirdn2d(float* out, const float* x, const float* kernel, int64_t pla
                     int up_x, int up_y, int down_x, int down_y, int pad_x0, int pad_x1, int pad_y0, int pad_y1,
                     void* stream);
 
+/* Host-only: the launch plan spgan_upfirdn2d would use for a 16-byte aligned input of these sizes (no device work; callable
+ * without a GPU).  plan[20] = { streamed variant K*100 + up*10 + down (0 = band / tiled / polyphase / generic kernel),
+ *   planes per item, bands per plane, output rows per band, 8-row strips per band, thread groups, threads, floats per
+ *   stage, interior columns, first interior column, border columns, border thread groups, first border thread, items, grid,
+ *   out_h, out_w, stage capacity (floats), thread limit, strip rows }. */
+int spgan_upfirdn2d_plan(int64_t planes, int in_h, int in_w, int kh, int kw, int up, int down, int pad_x0, int pad_x1,
+                         int pad_y0, int pad_y1, int32_t* plan);
+
 /* Fused tail of the upsampling StyledConv (models/ops.py:617-622 + 784 + fused_act.py:56-64): the cropped
  * conv_transpose2d(stride 2) output is held as four polyphase planes pp (planes, 4, Hq, Wq), plane index
  * (Y & 1) * 2 + (X & 1), element (Y >> 1, X >> 1); this kernel applies the 3x3 FIR of Blur (upfirdn2d, pad 0; `kernel`
@@ -76,6 +84,12 @@ int spgan_upblur_act(float* out, const float* pp, const float* kernel, const flo
  * 0/1/2 (tanh, cos(pi x), sin(pi x)) after sampling. */
 int spgan_sphere_gather(float* out, const float* z, const float* grid, int B, int C, int H, int W, int grid_batch,
                         int64_t out_bstride, int64_t out_coff, int encode, void* stream);
+
+/* Host-only: the launch plan spgan_sphere_gather would use for these sizes (no device work; callable without a GPU).
+ * plan[12] = { streamed (0 = L1-gather fallback), channels per item, channel groups per sample, position slices,
+ *   positions per slice, staged floats, dynamic shared-memory bytes, resident CTAs per SM, grid, items,
+ *   shared-memory limit, threads }. */
+int spgan_sphere_gather_plan(int B, int C, int H, int W, int encode, int32_t* plan);
 /* Corner indices and weights exactly as ATen computes them (GridSampler.h:27-36, 58-60); used by the
  * bit-exactness tests.  grid (n, 2); x0,y0 int32 (n); wx,wy fp32 (n) = weight of the +1 corner. */
 int spgan_sphere_gather_indices(int32_t* x0, int32_t* y0, float* wx, float* wy, const float* grid, int64_t n, int H,

@@ -208,21 +208,23 @@ __global__ void __launch_bounds__(GS_THREADS, 2) sphere_gather_stream_kernel(flo
   }
 }
 
-bool launch_gather_stream(float* out, const float* z, const float* grid, int B, int C, int H, int W, int grid_batch,
-                          int64_t out_bstride, int64_t out_coff, int encode, cudaStream_t st) {
-  if ((((uintptr_t)z) & 15) != 0) return false;
+constexpr int64_t GS_SMEM_MAX = 220 * 1024;
+
+// Host-side plan of a streamed gather: channels per item, position slices, shared-memory bytes, grid.  Pure arithmetic,
+// exported as spgan_sphere_gather_plan so that the CPU tests can sweep it for its invariants.
+bool plan_gather_stream(int B, int C, int H, int W, int encode, GatherStream& q, int& cc_out, size_t& smem, unsigned& grid_n,
+                        int& resident_out) {
   const int64_t HW = (int64_t)H * W;
   if (9 * HW >= (1LL << 26)) return false;
   const int nsm = SPGAN_NUM_SMS;
-  constexpr int64_t SMEM_MAX = 220 * 1024;
   auto bytes = [&](int cc) {
     const int64_t raw = (cc * HW + 8 + 31) / 32 * 32;
     return (raw + HW * (cc == 8 ? 12 : 4)) * 4;
   };
-  int cc = (C >= 8 && !encode && bytes(8) <= SMEM_MAX) ? 8 : 4;
+  int cc = (C >= 8 && !encode && bytes(8) <= GS_SMEM_MAX) ? 8 : 4;
   if (const char* e = getenv("SPGAN_GS_CC")) cc = atoi(e) == 4 ? 4 : cc;  // diagnostics
-  if (bytes(cc) > SMEM_MAX) return false;  // planes too large to stage: L1-gather kernel
-  const int resident = (2 * (bytes(cc) + 1024) <= SMEM_MAX + 4096) ? 2 : 1;
+  if (bytes(cc) > GS_SMEM_MAX) return false;  // planes too large to stage: L1-gather kernel
+  const int resident = (2 * (bytes(cc) + 1024) <= GS_SMEM_MAX + 4096) ? 2 : 1;
   const int64_t ncta = (int64_t)nsm * resident;
   const int chunks = (C + cc - 1) / cc;
   // position slices per (sample, channel group): the smallest split that balances the items over the persistent CTAs
@@ -238,22 +240,37 @@ bool launch_gather_stream(float* out, const float* z, const float* grid, int B, 
     }
   }
   if (const char* e = getenv("SPGAN_GS_PSPLIT")) psplit = atoi(e) >= 1 ? atoi(e) : psplit;  // diagnostics
-  GatherStream q;
-  q.B = B; q.C = C; q.H = H; q.W = W; q.grid_batch = grid_batch; q.encode = encode;
+  q.B = B; q.C = C; q.H = H; q.W = W; q.grid_batch = 1; q.encode = encode;
   q.chunks = chunks;
   q.psplit = psplit;
   q.pslice = (int)((9 * HW + psplit - 1) / psplit);
   q.raw_floats = (int)((cc * HW + 8 + 31) / 32 * 32);
-  q.out_bstride = out_bstride; q.out_coff = out_coff;
+  q.out_bstride = C; q.out_coff = 0;
   q.nitems = (int64_t)B * chunks * psplit;
-  q.limit = ((uintptr_t)(z + (int64_t)B * C * HW)) & ~(uintptr_t)15;
-  const size_t smem = (size_t)bytes(cc);
+  q.limit = 0;
+  cc_out = cc;
+  smem = (size_t)bytes(cc);
+  grid_n = (unsigned)(q.nitems < ncta ? q.nitems : ncta);
+  resident_out = resident;
+  return true;
+}
+
+bool launch_gather_stream(float* out, const float* z, const float* grid, int B, int C, int H, int W, int grid_batch,
+                          int64_t out_bstride, int64_t out_coff, int encode, cudaStream_t st) {
+  if ((((uintptr_t)z) & 15) != 0) return false;
+  GatherStream q;
+  int cc = 0, resident = 0;
+  size_t smem = 0;
+  unsigned grid_n = 0;
+  if (!plan_gather_stream(B, C, H, W, encode, q, cc, smem, grid_n, resident)) return false;
+  q.grid_batch = grid_batch;
+  q.out_bstride = out_bstride; q.out_coff = out_coff;
+  q.limit = ((uintptr_t)(z + (int64_t)B * C * H * W)) & ~(uintptr_t)15;
   static bool done_a[64] = {false}, done_b[64] = {false}, done_c[64] = {false};
-  if (!spgan_allow_smem(sphere_gather_stream_kernel<2, false>, (int)SMEM_MAX, done_a) ||
-      !spgan_allow_smem(sphere_gather_stream_kernel<1, false>, (int)SMEM_MAX, done_b) ||
-      !spgan_allow_smem(sphere_gather_stream_kernel<1, true>, (int)SMEM_MAX, done_c))
+  if (!spgan_allow_smem(sphere_gather_stream_kernel<2, false>, (int)GS_SMEM_MAX, done_a) ||
+      !spgan_allow_smem(sphere_gather_stream_kernel<1, false>, (int)GS_SMEM_MAX, done_b) ||
+      !spgan_allow_smem(sphere_gather_stream_kernel<1, true>, (int)GS_SMEM_MAX, done_c))
     return false;
-  const unsigned grid_n = (unsigned)(q.nitems < ncta ? q.nitems : ncta);
   if (encode) sphere_gather_stream_kernel<1, true><<<grid_n, GS_THREADS, smem, st>>>(out, z, grid, q);
   else if (cc == 8) sphere_gather_stream_kernel<2, false><<<grid_n, GS_THREADS, smem, st>>>(out, z, grid, q);
   else sphere_gather_stream_kernel<1, false><<<grid_n, GS_THREADS, smem, st>>>(out, z, grid, q);
@@ -379,5 +396,23 @@ extern "C" int spgan_sphere_gather_bwd(float* grad_in, const float* grad_out, in
   sphere_gather_bwd_kernel<<<grid_for(planes * H * W, 256, 8), 256, 0, (cudaStream_t)stream>>>(grad_in, grad_out, planes,
                                                                                             H, W);
   SPGAN_CHECK_LAUNCH("spgan_sphere_gather_bwd");
+  return 0;
+}
+
+extern "C" int spgan_sphere_gather_plan(int B, int C, int H, int W, int encode, int32_t* plan) {
+  SPGAN_CHECK_ARG(plan != nullptr, "spgan_sphere_gather_plan: null plan");
+  SPGAN_CHECK_ARG(B >= 1 && C >= 1 && H >= 1 && W >= 1, "spgan_sphere_gather_plan: sizes must be positive");
+  for (int i = 0; i < 12; ++i) plan[i] = 0;
+  GatherStream q;
+  int cc = 0, resident = 0;
+  size_t smem = 0;
+  unsigned grid_n = 0;
+  if (!plan_gather_stream(B, C, H, W, encode, q, cc, smem, grid_n, resident)) return 0;
+  plan[0] = 1;
+  plan[1] = cc; plan[2] = q.chunks; plan[3] = q.psplit; plan[4] = q.pslice; plan[5] = q.raw_floats; plan[6] = (int32_t)smem;
+  plan[7] = resident; plan[8] = (int32_t)grid_n;
+  plan[9] = (int32_t)(q.nitems < 2147483647LL ? q.nitems : 2147483647LL);
+  plan[10] = (int32_t)GS_SMEM_MAX;
+  plan[11] = GS_THREADS;
   return 0;
 }

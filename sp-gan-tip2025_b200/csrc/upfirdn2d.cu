@@ -610,15 +610,16 @@ __global__ void __launch_bounds__(FS_MAX_THREADS, 2) fir_stream_kernel(float* __
   }
 }
 
+constexpr int FS_MAX_STAGE = 11776;  // floats per stage: 46 KB, two stages and two CTAs per SM
+
+// Host-side plan of a streamed launch: work items, stage size, thread mapping.  Pure arithmetic (no CUDA calls besides the SM
+// count), exported as spgan_upfirdn2d_plan so that the CPU tests can sweep it for its invariants.
 template <int K, int UP, int DOWN>
-bool launch_fir_stream(float* out, const float* x, const float* kernel, int64_t planes, const UfdParams& p,
-                       cudaStream_t st) {
+bool plan_fir_stream(int64_t planes, const UfdParams& p, FirStream& q, int& block, unsigned& grid) {
   static_assert(UP == 1 || (K == 4 && DOWN == 1), "up 2 uses the zero-padded 4 x 4 form");
-  if ((((uintptr_t)x) & 15) != 0) return false;
-  constexpr int MAX_STAGE = 11776;  // floats per stage: 46 KB, two stages and two CTAs per SM
+  constexpr int MAX_STAGE = FS_MAX_STAGE;
   const int64_t plane_floats = (int64_t)p.in_h * p.in_w;
   const int ncta = 2 * SPGAN_NUM_SMS;
-  FirStream q;
   q.in_h = p.in_h; q.in_w = p.in_w; q.out_h = p.out_h; q.out_w = p.out_w; q.pad_x0 = p.pad_x0; q.pad_y0 = p.pad_y0;
   q.kh = p.kh; q.kw = p.kw;
   q.planes = planes;
@@ -714,15 +715,42 @@ bool launch_fir_stream(float* out, const float* x, const float* kernel, int64_t 
     best_nt = ((p.out_w + passes - 1) / passes + 31) / 32 * 32;
   }
   q.G = best_g;
-  q.limit = ((uintptr_t)(x + planes * plane_floats)) & ~(uintptr_t)15;
+  q.limit = 0;
   q.d_ow = make_fastdiv((uint32_t)p.out_w);
   q.d_strips = make_fastdiv((uint32_t)q.strips);
+  block = best_nt;
+  grid = (unsigned)(q.nitems < ncta ? q.nitems : ncta);
+  return true;
+}
+
+template <int K, int UP, int DOWN>
+bool launch_fir_stream(float* out, const float* x, const float* kernel, int64_t planes, const UfdParams& p,
+                       cudaStream_t st) {
+  if ((((uintptr_t)x) & 15) != 0) return false;
+  FirStream q;
+  int block = 0;
+  unsigned grid = 0;
+  if (!plan_fir_stream<K, UP, DOWN>(planes, p, q, block, grid)) return false;
+  q.limit = ((uintptr_t)(x + planes * (int64_t)p.in_h * p.in_w)) & ~(uintptr_t)15;
   const size_t smem = (size_t)2 * q.stage_floats * sizeof(float);
   static bool attr_done[64] = {false};
-  if (!spgan_allow_smem(fir_stream_kernel<K, UP, DOWN>, 2 * MAX_STAGE * 4 + 1024, attr_done)) return false;
-  const unsigned grid = (unsigned)(q.nitems < ncta ? q.nitems : ncta);
-  fir_stream_kernel<K, UP, DOWN><<<grid, best_nt, smem, st>>>(out, x, kernel, q);
+  if (!spgan_allow_smem(fir_stream_kernel<K, UP, DOWN>, 2 * FS_MAX_STAGE * 4 + 1024, attr_done)) return false;
+  fir_stream_kernel<K, UP, DOWN><<<grid, block, smem, st>>>(out, x, kernel, q);
   return true;
+}
+
+// Which streamed kernel serves a geometry: K * 100 + UP * 10 + DOWN, or 0 (tiled / band / polyphase / generic kernels).
+int fir_stream_variant(const UfdParams& p, int up_x, int up_y, int down_x, int down_y, int pad_x1, int pad_y1) {
+  const bool unit = up_x == 1 && up_y == 1 && down_x == 1 && down_y == 1 && p.kh == p.kw && p.pad_x0 >= 0 && p.pad_y0 >= 0;
+  if (unit && p.kh >= 2 && p.kh <= 4 && p.pad_x0 <= p.kh - 1 && p.pad_y0 <= p.kh - 1 && pad_x1 <= p.kh - 1 &&
+      pad_y1 <= p.kh - 1 && p.in_w >= 1)
+    return p.kh * 100 + 11;
+  // Upsample / Downsample of models/ops.py:32-79 and each other's gradient: up or down by two, kernels up to 4 x 4
+  const bool small_k = p.kh >= 1 && p.kw >= 1 && p.kh <= 4 && p.kw <= 4 && p.pad_x0 >= 0 && p.pad_y0 >= 0 && p.pad_x0 <= 3 &&
+                       p.pad_y0 <= 3 && pad_x1 <= 3 && pad_y1 <= 3 && p.in_w >= 1;
+  if (small_k && up_x == 2 && up_y == 2 && down_x == 1 && down_y == 1) return 421;
+  if (small_k && up_x == 1 && up_y == 1 && down_x == 2 && down_y == 2) return 412;
+  return 0;
 }
 
 // Fused tail of the upsampling StyledConv: interleave the four polyphase planes of the transposed conv on the fly,
@@ -901,19 +929,14 @@ extern "C" int spgan_upfirdn2d(float* out, const float* x, const float* kernel, 
   const int tiles_x = (p.out_w + TILE - 1) / TILE, tiles_y = (p.out_h + TILE - 1) / TILE;
   const int64_t blocks = planes * tiles_x * tiles_y;
   bool done = false;
-  if (unit && kh >= 2 && kh <= 4 && pad_x0 <= kh - 1 && pad_y0 <= kh - 1 && pad_x1 <= kh - 1 && pad_y1 <= kh - 1 &&
-      p.in_w >= 1 && !spgan_legacy_hbm()) {
-    if (kh == 2) done = launch_fir_stream<2, 1, 1>(out, x, kernel, planes, p, st);
-    if (kh == 3) done = launch_fir_stream<3, 1, 1>(out, x, kernel, planes, p, st);
-    if (kh == 4) done = launch_fir_stream<4, 1, 1>(out, x, kernel, planes, p, st);
+  switch (spgan_legacy_hbm() ? 0 : fir_stream_variant(p, up_x, up_y, down_x, down_y, pad_x1, pad_y1)) {
+    case 211: done = launch_fir_stream<2, 1, 1>(out, x, kernel, planes, p, st); break;
+    case 311: done = launch_fir_stream<3, 1, 1>(out, x, kernel, planes, p, st); break;
+    case 411: done = launch_fir_stream<4, 1, 1>(out, x, kernel, planes, p, st); break;
+    case 421: done = launch_fir_stream<4, 2, 1>(out, x, kernel, planes, p, st); break;
+    case 412: done = launch_fir_stream<4, 1, 2>(out, x, kernel, planes, p, st); break;
+    default: break;
   }
-  // Upsample / Downsample of models/ops.py:32-79 and each other's gradient: up or down by two, kernels up to 4 x 4
-  const bool small_k = kh >= 1 && kw >= 1 && kh <= 4 && kw <= 4 && pad_x0 >= 0 && pad_y0 >= 0 && pad_x0 <= 3 && pad_y0 <= 3 &&
-                       pad_x1 <= 3 && pad_y1 <= 3 && p.in_w >= 1 && !spgan_legacy_hbm();
-  if (!done && small_k && up_x == 2 && up_y == 2 && down_x == 1 && down_y == 1)
-    done = launch_fir_stream<4, 2, 1>(out, x, kernel, planes, p, st);
-  if (!done && small_k && up_x == 1 && up_y == 1 && down_x == 2 && down_y == 2)
-    done = launch_fir_stream<4, 1, 2>(out, x, kernel, planes, p, st);
   if (!done && unit && kh >= 2 && kh <= 4 && pad_x0 <= kh - 1 && pad_y0 <= kh - 1 && p.in_w >= 1) {
     if (kh == 2) done = launch_band<2>(out, x, kernel, planes, p, pad_x1, st);
     if (kh == 3) done = launch_band<3>(out, x, kernel, planes, p, pad_x1, st);
@@ -936,5 +959,47 @@ extern "C" int spgan_upfirdn2d(float* out, const float* x, const float* kernel, 
     upfirdn2d_generic<<<grid_for(total, 256, 8, 8), 256, 0, st>>>(out, x, kernel, planes, p);
   }
   SPGAN_CHECK_LAUNCH("spgan_upfirdn2d");
+  return 0;
+}
+
+extern "C" int spgan_upfirdn2d_plan(int64_t planes, int in_h, int in_w, int kh, int kw, int up, int down, int pad_x0, int pad_x1,
+                                    int pad_y0, int pad_y1, int32_t* plan) {
+  SPGAN_CHECK_ARG(plan != nullptr, "spgan_upfirdn2d_plan: null plan");
+  SPGAN_CHECK_ARG(planes >= 1 && in_h >= 1 && in_w >= 1 && kh >= 1 && kw >= 1 && up >= 1 && down >= 1,
+                  "spgan_upfirdn2d_plan: sizes must be positive");
+  for (int i = 0; i < 20; ++i) plan[i] = 0;
+  UfdParams p;
+  p.in_h = in_h; p.in_w = in_w; p.kh = kh; p.kw = kw;
+  p.up_x = up; p.up_y = up; p.down_x = down; p.down_y = down;
+  p.pad_x0 = pad_x0; p.pad_y0 = pad_y0;
+  const int full_h = in_h * up + pad_y0 + pad_y1 - kh, full_w = in_w * up + pad_x0 + pad_x1 - kw;
+  p.out_h = full_h >= 0 ? full_h / down + 1 : 0;
+  p.out_w = full_w >= 0 ? full_w / down + 1 : 0;
+  plan[15] = p.out_h;
+  plan[16] = p.out_w;
+  if (p.out_h <= 0 || p.out_w <= 0) return 0;
+  const int variant = fir_stream_variant(p, up, up, down, down, pad_x1, pad_y1);
+  FirStream q;
+  int block = 0;
+  unsigned grid = 0;
+  bool ok = false;
+  switch (variant) {
+    case 211: ok = plan_fir_stream<2, 1, 1>(planes, p, q, block, grid); break;
+    case 311: ok = plan_fir_stream<3, 1, 1>(planes, p, q, block, grid); break;
+    case 411: ok = plan_fir_stream<4, 1, 1>(planes, p, q, block, grid); break;
+    case 421: ok = plan_fir_stream<4, 2, 1>(planes, p, q, block, grid); break;
+    case 412: ok = plan_fir_stream<4, 1, 2>(planes, p, q, block, grid); break;
+    default: break;
+  }
+  if (!ok) return 0;
+  plan[0] = variant;
+  plan[1] = q.P; plan[2] = q.bands; plan[3] = q.R; plan[4] = q.strips; plan[5] = q.G; plan[6] = block;
+  plan[7] = q.stage_floats; plan[8] = q.n_int; plan[9] = q.int_lo; plan[10] = q.n_bord; plan[11] = q.Gb;
+  plan[12] = q.border_base;
+  plan[13] = (int32_t)(q.nitems < 2147483647LL ? q.nitems : 2147483647LL);
+  plan[14] = (int32_t)grid;
+  plan[17] = FS_MAX_STAGE;
+  plan[18] = FS_MAX_THREADS;
+  plan[19] = FS_STRIP;
   return 0;
 }

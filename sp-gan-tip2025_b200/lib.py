@@ -67,6 +67,8 @@ SIGNATURES = {
     "spgan_upblur_act": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_int, c_int, c_int, c_int, c_f32, c_f32, c_vp]),
     "spgan_upfirdn2d": (c_int, [c_vp, c_vp, c_vp, c_i64] + [c_int] * 12 + [c_vp]),
     "spgan_sphere_gather": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_i64, c_i64, c_int, c_vp]),
+    "spgan_sphere_gather_plan": (c_int, [c_int] * 5 + [c_vp]),
+    "spgan_upfirdn2d_plan": (c_int, [c_i64] + [c_int] * 10 + [c_vp]),
     "spgan_sphere_gather_indices": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_vp]),
     "spgan_sphere_gather_bwd": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_vp]),
     "spgan_grid_sample": (c_int, [c_vp, c_vp, c_vp] + [c_int] * 8 + [c_vp]),

@@ -1,0 +1,145 @@
+"""CPU: the host-side launch plans of the streamed FIR / gather kernels (csrc/upfirdn2d.cu plan_fir_stream,
+csrc/sphere_gather.cu plan_gather_stream), swept through the host-only C-ABI entry points for their invariants: every output
+row and column is covered exactly once, nothing staged exceeds the shared-memory stage, thread blocks stay within the
+register-limited size, interior columns really have all taps inside the image."""
+import ctypes
+import itertools
+
+import numpy as np
+import pytest
+
+
+def _lib():
+    import __graft_entry__ as ge
+    ge.build()
+    import spgan_b200.lib as lib
+    return lib.load()
+
+
+def fir_plan(planes, h, w, k, up, down, pad):
+    out = (ctypes.c_int32 * 20)()
+    rc = _lib().spgan_upfirdn2d_plan(planes, h, w, k, k, up, down, pad[0], pad[1], pad[0], pad[1], ctypes.cast(out, ctypes.c_void_p))
+    assert rc == 0
+    keys = ["variant", "P", "bands", "R", "strips", "G", "threads", "stage_floats", "n_int", "int_lo", "n_bord", "Gb",
+            "border_base", "items", "grid", "out_h", "out_w", "max_stage", "max_threads", "strip"]
+    return dict(zip(keys, list(out)))
+
+
+def _fir_cases():
+    geoms = [(3, 1, 1, (0, 0)), (3, 1, 1, (2, 2)), (4, 1, 1, (2, 2)), (4, 1, 1, (1, 1)), (4, 1, 1, (2, 1)), (2, 1, 1, (1, 0)),
+             (4, 2, 1, (2, 1)), (3, 2, 1, (1, 0)), (4, 1, 2, (1, 1)), (4, 1, 2, (1, 2))]
+    sizes = [(5, 7), (11, 11), (19, 19), (50, 50), (53, 53), (101, 101), (105, 105), (106, 106), (128, 128), (150, 131),
+             (30, 700), (40, 400), (256, 256), (384, 384), (9, 2900)]
+    planes = [1, 3, 600, 16384]
+    return list(itertools.product(geoms, sizes, planes))
+
+
+@pytest.mark.parametrize("chunk", range(4))
+def test_fir_stream_plan_invariants(chunk):
+    cases = _fir_cases()[chunk::4]
+    streamed = 0
+    for (k, up, down, pad), (h, w), planes in cases:
+        p = fir_plan(planes, h, w, k, up, down, pad)
+        oh = (h * up + pad[0] + pad[1] - k) // down + 1
+        ow = (w * up + pad[0] + pad[1] - k) // down + 1
+        assert (p["out_h"], p["out_w"]) == (max(oh, 0), max(ow, 0))
+        if p["variant"] == 0:
+            continue
+        streamed += 1
+        K = p["variant"] // 100
+        assert p["variant"] % 100 == up * 10 + down and K >= k
+        S = p["strip"]
+        # stage capacity
+        assert p["stage_floats"] <= p["max_stage"]
+        if p["bands"] == 1 and p["P"] >= 1 and h * w + 8 <= p["max_stage"]:
+            assert p["P"] * h * w + 8 <= p["stage_floats"]
+            assert p["R"] == oh
+            assert p["items"] == -(-planes // p["P"])
+        else:
+            assert p["P"] == 1
+            # every band's input rows fit the stage (restating the kernel's decode)
+            for band in range(p["bands"]):
+                oy0 = band * p["R"]
+                rows = min(p["R"], oh - oy0)
+                assert rows >= 1
+                y_first, y_last = oy0 * down - pad[0], (oy0 + rows - 1) * down - pad[0] + K - 1
+                lo = max((y_first + 1) >> 1 if up == 2 else y_first, 0)
+                hi = min(y_last >> 1 if up == 2 else y_last, h - 1)
+                assert (hi - lo + 1) * w + 8 <= p["stage_floats"], (h, w, k, up, down, pad, band)
+            assert p["items"] == min(planes * p["bands"], 2 ** 31 - 1)
+        # rows covered exactly: bands * R >= out_h, no empty band, whole strips
+        assert p["bands"] * p["R"] >= oh and (p["bands"] - 1) * p["R"] < oh
+        assert p["strips"] == -(-p["R"] // S)
+        if p["bands"] > 1:
+            assert p["R"] % S == 0  # every band starts on the same tap parity (up 2)
+        # threads
+        assert p["threads"] % 32 == 0 and 32 <= p["threads"] <= p["max_threads"]
+        assert 1 <= p["grid"] <= max(1, p["items"])
+        if p["n_int"] > 0:
+            assert up == 1 and down == 1
+            n_int, lo = p["n_int"], p["int_lo"]
+            assert n_int + p["n_bord"] == ow and lo >= 0
+            # interior columns have all K taps inside the image; the columns next to them do not
+            for ox in (lo, lo + n_int - 1):
+                assert 0 <= ox - pad[0] and ox - pad[0] + K - 1 <= w - 1
+            for ox in (lo - 1, lo + n_int):
+                if 0 <= ox < ow:
+                    assert ox - pad[0] < 0 or ox - pad[0] + K - 1 > w - 1
+            assert p["G"] * n_int <= p["border_base"] <= p["threads"]
+            assert p["border_base"] % 32 == 0
+            assert p["border_base"] + p["Gb"] * p["n_bord"] <= p["threads"]
+            assert p["Gb"] >= 1
+        elif ow <= p["max_threads"]:
+            assert p["G"] * ow <= p["threads"]
+        else:
+            assert p["G"] == 1
+            passes = -(-ow // p["max_threads"])
+            assert p["threads"] * passes >= ow
+    assert streamed > len(cases) // 2
+
+
+def test_fir_stream_plan_hot_path_shapes():
+    """The generator's and discriminator's blurs take the streamed kernel with whole planes and the split column mapping."""
+    g = fir_plan(32 * 512, 105, 105, 3, 1, 1, (0, 0))
+    assert g["variant"] == 311 and g["bands"] == 1 and g["P"] == 1 and g["n_bord"] == 0 and g["n_int"] == 103
+    d = fir_plan(32 * 256, 101, 101, 4, 1, 1, (2, 2))
+    assert d["variant"] == 411 and d["bands"] == 1 and d["n_int"] == 98 and d["n_bord"] == 4 and d["int_lo"] == 2
+    u = fir_plan(32 * 256, 53, 53, 4, 2, 1, (2, 1))
+    assert u["variant"] == 421 and u["P"] == 4  # four 53 x 53 planes per 46 KB stage
+    assert fir_plan(32 * 3, 53, 53, 4, 2, 1, (2, 1))["P"] == 1  # few planes: spread over the CTAs first
+    assert fir_plan(8, 64, 64, 5, 1, 1, (2, 2))["variant"] == 0      # 5 x 5: generic kernel
+    assert fir_plan(8, 64, 64, 4, 2, 2, (2, 2))["variant"] == 0      # up and down together: polyphase kernel
+
+
+def gather_plan(B, C, H, W, encode=0):
+    out = (ctypes.c_int32 * 12)()
+    rc = _lib().spgan_sphere_gather_plan(B, C, H, W, encode, ctypes.cast(out, ctypes.c_void_p))
+    assert rc == 0
+    keys = ["streamed", "cc", "chunks", "psplit", "pslice", "raw_floats", "smem", "resident", "grid", "items", "smem_max",
+            "threads"]
+    return dict(zip(keys, list(out)))
+
+
+def test_gather_stream_plan_invariants():
+    n = 0
+    for B, C, (H, W), enc in itertools.product([1, 2, 8, 32, 64], [1, 3, 5, 37, 256, 259], [(7, 9), (17, 17), (35, 35), (53, 53),
+                                                                                           (83, 83), (130, 70), (384, 384)], [0, 1]):
+        if enc and C != 3:
+            continue
+        p = gather_plan(B, C, H, W, enc)
+        if not p["streamed"]:
+            assert H * W * 32 > p["smem_max"] - 64  # only planes too large for one 4-channel stage fall back
+            continue
+        n += 1
+        cc = p["cc"]
+        assert cc in (4, 8) and (cc == 4 or (C >= 8 and not enc))
+        assert p["chunks"] == -(-C // cc)
+        assert p["raw_floats"] >= cc * H * W + 8 and p["raw_floats"] % 32 == 0
+        assert p["smem"] == 4 * (p["raw_floats"] + H * W * (12 if cc == 8 else 4)) <= p["smem_max"]
+        assert p["resident"] in (1, 2) and p["resident"] * (p["smem"] + 1024) <= 228 * 1024
+        assert 1 <= p["psplit"] <= 4 and p["psplit"] * p["pslice"] >= 9 * H * W > (p["psplit"] - 1) * p["pslice"]
+        assert p["items"] == B * p["chunks"] * p["psplit"]
+        assert 1 <= p["grid"] <= p["items"]
+    assert n > 100
+    hot = gather_plan(32, 256, 35, 35)
+    assert hot["cc"] == 8 and hot["resident"] == 2 and hot["psplit"] == 2
