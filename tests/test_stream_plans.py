@@ -143,3 +143,112 @@ def test_gather_stream_plan_invariants():
     assert n > 100
     hot = gather_plan(32, 256, 35, 35)
     assert hot["cc"] == 8 and hot["resident"] == 2 and hot["psplit"] == 2
+
+
+# ------------------------------------------------------------------------------------------------ index arithmetic
+def _emulate_fir_stream(p, x, kern, up, down, pad):
+    """numpy restatement of fir_stream_kernel's index arithmetic (csrc/upfirdn2d.cu: item decode, staged row window, strips,
+    zero-word taps, up-2 tap parity) driven by the exported plan.  Every output must be written exactly once."""
+    planes, h, w = x.shape
+    kh, kw = kern.shape
+    K, S = p["variant"] // 100, p["strip"]
+    px0 = py0 = pad[0]
+    oh, ow = p["out_h"], p["out_w"]
+    kf = np.zeros((K, K), x.dtype)
+    kf[:kh, :kw] = kern[::-1, ::-1]
+    out = np.full((planes, oh, ow), np.nan, x.dtype)
+    written = np.zeros((planes, oh, ow), np.int32)
+    ox = np.arange(ow)
+    for item in range(p["items"]):
+        if p["bands"] == 1:
+            plane0 = item * p["P"]
+            npl = min(p["P"], planes - plane0)
+            oy0, rows_out, iy_lo, iy_hi = 0, oh, 0, h - 1
+        else:
+            plane0, band = divmod(item, p["bands"])
+            npl = 1
+            oy0 = band * p["R"]
+            rows_out = min(p["R"], oh - oy0)
+            y_first, y_last = oy0 * down - py0, (oy0 + rows_out - 1) * down - py0 + K - 1
+            iy_lo = max((y_first + 1) >> 1 if up == 2 else y_first, 0)
+            iy_hi = min(y_last >> 1 if up == 2 else y_last, h - 1)
+        nrows = iy_hi - iy_lo + 1
+        assert npl * h * w + 8 <= p["stage_floats"] if p["bands"] == 1 else nrows * w + 8 <= p["stage_floats"]
+        for pl in range(npl):
+            staged = x[plane0 + pl, iy_lo:iy_hi + 1]  # what the bulk copy brings in
+            for strip in range(p["strips"]):
+                ly0 = strip * S
+                rows_left = rows_out - ly0
+                if rows_left <= 0:
+                    continue
+                for i in range(min(S, rows_left)):
+                    acc = np.zeros(ow, x.dtype)
+                    if up == 1:
+                        row0 = (oy0 + ly0) * down - py0 - iy_lo
+                        for ky in range(K):
+                            ry = row0 + i * down + ky
+                            if not 0 <= ry < nrows:
+                                continue  # CHECK variant: clamped row times zero
+                            for kx in range(K):
+                                ix = ox * down - px0 + kx
+                                ok = (ix >= 0) & (ix < w)  # else: the zero word
+                                acc += kf[ky, kx] * np.where(ok, staged[ry, np.clip(ix, 0, w - 1)], 0)
+                    else:
+                        c = ox - px0
+                        kx0 = c & 1
+                        ix0 = (c + kx0) >> 1
+                        par0 = (oy0 - py0) & 1
+                        t0 = oy0 + ly0 - py0
+                        j0 = ((t0 + par0) >> 1) - iy_lo
+                        A = (i >> 1) if par0 else ((i + 1) >> 1)
+                        par = (par0 + i) & 1
+                        for a, ky in ((0, par), (1, par + 2)):
+                            ry = j0 + A + a
+                            if not 0 <= ry < nrows:
+                                continue
+                            for b in range(2):
+                                ix = ix0 + b
+                                ok = (ix >= 0) & (ix < w)
+                                wcol = np.where(kx0 == 1, kf[ky, 1 + 2 * b] if 1 + 2 * b < K else 0, kf[ky, 2 * b])
+                                acc += wcol * np.where(ok, staged[ry, np.clip(ix, 0, w - 1)], 0)
+                    out[plane0 + pl, oy0 + ly0 + i] = acc
+                    written[plane0 + pl, oy0 + ly0 + i] += 1
+    assert (written == 1).all()
+    return out
+
+
+def test_fir_stream_index_arithmetic_vs_oracle():
+    """The kernel's decode / window / parity formulas, restated in numpy and driven by the real plan, reproduce the oracle's
+    upfirdn2d over geometries far beyond the GPU test list (all pads 0..K-1, non-square small kernels for up / down 2, bands)."""
+    import spgan_oracle as O
+    rng = np.random.default_rng(7)
+    cases = []
+    for k in (2, 3, 4):
+        for pad in itertools.product(range(k), range(k)):
+            cases.append((3, 13, 11, (k, k), 1, 1, pad))
+    for kh, kw in ((4, 4), (3, 3), (2, 4), (4, 1), (1, 3)):
+        for pad in ((0, 0), (1, 0), (2, 1), (3, 3), (1, 2), (0, 3)):
+            cases.append((2, 9, 12, (kh, kw), 2, 1, pad))
+            cases.append((2, 14, 11, (kh, kw), 1, 2, pad))
+    # bands: planes larger than a 46 KB stage
+    cases += [(1, 120, 131, (4, 4), 1, 1, (2, 1)), (1, 150, 100, (3, 3), 1, 1, (0, 0)), (1, 140, 110, (4, 4), 2, 1, (2, 1)),
+              (1, 141, 97, (3, 3), 2, 1, (1, 0)), (1, 260, 90, (4, 4), 1, 2, (1, 1)), (1, 301, 60, (4, 4), 1, 2, (3, 0)),
+              (2, 40, 400, (4, 4), 1, 1, (2, 2)), (5, 50, 50, (4, 4), 1, 1, (2, 2))]
+    streamed = 0
+    for planes, h, w, (kh, kw), up, down, pad in cases:
+        out = (ctypes.c_int32 * 20)()
+        assert _lib().spgan_upfirdn2d_plan(planes, h, w, kh, kw, up, down, pad[0], pad[1], pad[0], pad[1],
+                                           ctypes.cast(out, ctypes.c_void_p)) == 0
+        keys = ["variant", "P", "bands", "R", "strips", "G", "threads", "stage_floats", "n_int", "int_lo", "n_bord", "Gb",
+                "border_base", "items", "grid", "out_h", "out_w", "max_stage", "max_threads", "strip"]
+        p = dict(zip(keys, list(out)))
+        if p["variant"] == 0 or p["out_h"] <= 0 or p["out_w"] <= 0:
+            continue
+        streamed += 1
+        x = rng.standard_normal((planes, h, w))
+        kern = rng.standard_normal((kh, kw))
+        want = O.upfirdn2d(x[None], kern, up=(up, up), down=(down, down), pad=(pad[0], pad[1], pad[0], pad[1]))[0]
+        got = _emulate_fir_stream(p, x, kern, up, down, pad)
+        assert got.shape == want.shape, (h, w, kh, kw, up, down, pad)
+        assert np.allclose(got, want, rtol=1e-12, atol=1e-12), (h, w, kh, kw, up, down, pad)
+    assert streamed >= 60
