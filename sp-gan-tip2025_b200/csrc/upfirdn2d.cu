@@ -1,8 +1,13 @@
 // K2/K3: upfirdn2d over (planes, H, W) fp32 images — pad, zero-stuff by `up`, FIR with the flipped kernel,
 // keep every `down`-th sample.  HBM-bound stencil: algorithmic traffic 4*(in_h*in_w + out_h*out_w) bytes per plane.
-//   * band kernel (up = down = 1, K x K with K <= 4, rows that fit the staging buffer): the shapes the generator's Blur
-//     (3x3, pad 0) and the discriminator's Blur (4x4, pad 2/1) use; a CTA filters R full-width output rows.
+//   * streamed kernels (the default: fir_stream_kernel<K, UP, DOWN>, K <= 4, up or down by two or neither): persistent CTAs,
+//     whole planes / row bands staged by bulk-async copies into a two-stage ring (stream_stage.cuh), one output column per
+//     thread.  The Blur of the generator (3x3, pad 0) and of the discriminator (4x4, pad 2 / 1), Upsample, Downsample and
+//     their gradients.
+//   Fallbacks (input not 16-byte aligned, rows too long for a stage, other geometries; SPGAN_LEGACY_HBM_KERNELS=1):
+//   * band kernel (up = down = 1, K x K with K <= 4, rows that fit the staging buffer): a CTA filters R full-width output rows.
 //   * tiled kernel (same filters, very wide images): one 64x64 output tile per CTA.
+//   * polyphase kernel (up, down in {1, 2}, kernels up to 4x4).
 //   * generic kernel: any up/down/pad/kernel up to 16x16 (reads through L1/L2).
 #include "common.cuh"
 #include "stream_stage.cuh"
