@@ -356,9 +356,6 @@ extern "C" int spgan_sphere_grid_assemble(float* out, const float* lat_n, const 
   return 0;
 }
 
-namespace {
-}  // namespace
-
 extern "C" int spgan_sphere_gather(float* out, const float* z, const float* grid, int B, int C, int H, int W,
                                    int grid_batch, int64_t out_bstride, int64_t out_coff, int encode, void* stream) {
   SPGAN_CHECK_ARG(B >= 0 && C >= 0 && H >= 0 && W >= 0, "spgan_sphere_gather: negative size");

@@ -470,8 +470,6 @@ __device__ __forceinline__ void fir_strip_up2(const float (&wc)[4][2], const uin
   }
 #pragma unroll
   for (int i = 0; i < FS_STRIP; ++i) {
-    constexpr int dummy = 0;
-    (void)dummy;
     const int A = ODD0 ? (i >> 1) : ((i + 1) >> 1);
     const int par = ((ODD0 ? 1 : 0) + i) & 1;
     float res = wc[par][0] * v[A][0];
