@@ -303,20 +303,25 @@ bool launch_band(float* out, const float* x, const float* kernel, int64_t planes
   return true;
 }
 
-// Streamed FIR (up = down = 1, K x K, K <= 4, zero padding): the default for the generator's Blur (3x3, pad 0) and the
-// discriminator's Blur (4x4, pad 2 / 1) and for their gradients.  Persistent CTAs (two per SM); a work item is a group of
-// P whole planes (small images) or a band of R output rows of one plane (large images) — in both cases ONE contiguous run
-// of floats, fetched by one bulk-async copy into a two-stage ring (stream_stage.cuh) while the previous item is filtered.
+// Streamed FIR (K x K taps, K <= 4, zero padding; up = down = 1, or up 2, or down 2): the default for the generator's Blur
+// (3x3, pad 0), the discriminator's Blur (4x4, pad 2 / 1), Upsample / Downsample (models/ops.py:32-79) and their gradients.
+// Persistent CTAs (two per SM); a work item is a group of P whole planes (small images) or a band of R output rows of one
+// plane (large images) — in both cases ONE contiguous run of floats, fetched by one bulk-async copy into a two-stage ring
+// (stream_stage.cuh) while the previous item is filtered.
 //
 // The rows are staged exactly as they lie in memory (no zero borders).  A thread owns ONE output column for the whole
-// kernel (threads = G groups x out_w columns; the groups share the strips of an item), so everything that depends on the
-// column is set up once per item: each of its K taps is a running shared-memory address plus a row stride, and a tap that
-// falls outside the image points at a zero word with stride 0 — no column masks, no bounds checks.  The inner loop is a
-// sliding window over the staged rows: K shared-memory reads per row, taps held as packed pairs so that a K x K stencil is
+// kernel (threads = G groups x columns; the groups share the 8-row strips of an item), so everything that depends on the
+// column is set up once per item: each of its K taps is a shared-memory address plus a row stride, and a tap that falls
+// outside the image points at a zero word with stride 0 — no column masks, no bounds checks.  For up = down = 1 the columns
+// whose K taps all lie inside the image sit on the leading warps and use one running address with immediate tap offsets;
+// the few border columns run the general form on one trailing warp, so no warp executes both.  The inner loop is a sliding
+// window over the staged rows: K shared-memory reads per row, taps held as packed pairs so that a K x K stencil is
 // K * (K/2) FFMA2 (+ K FFMA for K = 3) per output.  Only the first / last strips of an image (rows in the zero padding)
-// take a variant with a clamped row index and a zero multiplier.  ncu (profiles/r2_ncu_hbm_kernels.txt): the first
-// streamed version decoded (plane, strip, column) and rebuilt its column state for every 8 outputs — 33 / 44
-// instructions per output for K = 3 / 4 and 65-71 % of the issue slots busy at 0.85 / 0.61 of the HBM peak.
+// take a variant with a clamped row index and a zero multiplier.  Up 2: see fir_strip_up2.  ncu
+// (profiles/r2_ncu_hbm_kernels.txt): the first streamed version decoded (plane, strip, column) and rebuilt its column state
+// for every 8 outputs — 33 / 44 instructions per output for K = 3 / 4 at 0.85 / 0.61 of the HBM peak; now 28 / 39 warp-level
+// (idle lanes included) at 0.88 / 0.65.  The launch plan is host arithmetic (plan_fir_stream), swept on the CPU by
+// tests/test_stream_plans.py together with a numpy restatement of the index arithmetic below.
 constexpr int FS_MAX_THREADS = 320;
 constexpr int FS_STRIP = 8;
 
