@@ -449,8 +449,8 @@ def run_ours(args):
 
 def measure_hbm_kernels(dev, local):
     """The HBM-bound kernels of the path (north_star: gather / upfirdn2d / bias-act against the B200 HBM peak) timed alone in
-    this run: CUDA events around 40 back-to-back launches after 5 warm-up launches, inputs larger than L2, clocks sampled during
-    the loops.  `frac` = algorithmic bytes / time / MEASURED_PEAKS.json hbm_gbs (the copy peak; burst figure: each kernel runs
+    this run: CUDA events around ~0.3 s of back-to-back launches after 5 warm-up launches, inputs larger than L2, clocks sampled
+    during the loops.  `frac` = algorithmic bytes / time / MEASURED_PEAKS.json hbm_gbs (the copy peak; burst figure: each kernel runs
     alone).  tools/microbench.py is the full version (graph replays, legacy A/B, configs[4] sweep)."""
     import torch
     import spgan_b200.functional as SF
@@ -489,11 +489,14 @@ def measure_hbm_kernels(dev, local):
     sampler.start()
     with torch.no_grad():
         for name, fn, nbytes in cases:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
             for _ in range(5):
                 fn()
+            e1.record()
             torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            n = 40
+            # ~0.3 s per case, so that the 200 ms clock sampler sees every kernel under load
+            n = max(40, min(4000, int(300.0 / max(e0.elapsed_time(e1) / 5, 0.02))))
             e0.record()
             for _ in range(n):
                 fn()
@@ -506,7 +509,7 @@ def measure_hbm_kernels(dev, local):
     del cases, x, go, xg, xd, xu, z
     torch.cuda.empty_cache()
     return {"peak_GBs": hbm, "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy bandwidth)", "clocks": clocks, "cases": out,
-            "note": "each kernel timed alone (40 launches, CUDA events, eager: the Python launch overhead is inside the figure), "
+            "note": "each kernel timed alone (~0.3 s of back-to-back launches, CUDA events, eager: the Python launch overhead is inside the figure), "
                     "inputs larger than L2"}
 
 
