@@ -252,3 +252,54 @@ def test_fir_stream_index_arithmetic_vs_oracle():
         assert got.shape == want.shape, (h, w, kh, kw, up, down, pad)
         assert np.allclose(got, want, rtol=1e-12, atol=1e-12), (h, w, kh, kw, up, down, pad)
     assert streamed >= 60
+
+
+def _emulate_gather_stream(p, z, grid):
+    """numpy restatement of sphere_gather_stream_kernel's item decode, [pixel][channel] tile and position slices
+    (csrc/sphere_gather.cu) driven by the exported plan; corners / weights come from the oracle's index arithmetic."""
+    import spgan_oracle as O
+    B, C, H, W = z.shape
+    cc, TS = p["cc"], (12 if p["cc"] == 8 else 4)
+    opix = 9 * H * W
+    x0, y0, wx1, wy1 = O.gather_indices(grid, H, W)
+    x0, y0, wx1, wy1 = (a.reshape(a.shape[0], -1) for a in (x0, y0, wx1, wy1))
+    out = np.full((B, C, opix), np.nan, np.float32)
+    written = np.zeros((B, C, opix), np.int32)
+    per_sample = p["chunks"] * p["psplit"]
+    for item in range(p["items"]):
+        b, rem = divmod(item, per_sample)
+        c0 = (rem // p["psplit"]) * cc
+        sl = rem % p["psplit"]
+        nc = min(cc, C - c0)
+        tile = np.zeros((H * W, TS), np.float32)  # channels beyond the tensor read as zero
+        tile[:, :nc] = z[b, c0:c0 + nc].reshape(nc, H * W).T
+        lo, hi = sl * p["pslice"], min(opix, (sl + 1) * p["pslice"])
+        pos = np.arange(lo, hi)
+        g = 0 if grid.shape[0] == 1 else b
+        xa, ya = x0[g, pos], y0[g, pos]
+        xb, yb = np.minimum(xa + 1, W - 1), np.minimum(ya + 1, H - 1)
+        fx, fy = wx1[g, pos], wy1[g, pos]
+        ex, ey = np.float32(1) - fx, np.float32(1) - fy
+        v = (tile[ya * W + xa, :nc] * (ex * ey)[:, None] + tile[ya * W + xb, :nc] * (fx * ey)[:, None] +
+             tile[yb * W + xa, :nc] * (ex * fy)[:, None] + tile[yb * W + xb, :nc] * (fx * fy)[:, None])
+        out[b, c0:c0 + nc, lo:hi] = v.T
+        written[b, c0:c0 + nc, lo:hi] += 1
+    assert (written == 1).all()
+    return out.reshape(B, C, 3 * H, 3 * W)
+
+
+def test_gather_stream_item_decode_vs_oracle():
+    import cases as K
+    import spgan_oracle as O
+    rng = np.random.default_rng(11)
+    cp = K.test_cp(2, 7, 27)
+    for B, C, H, W, shared in [(2, 5, 7, 9, False), (3, 37, 11, 11, True), (1, 3, 17, 17, True), (40, 8, 5, 6, True),
+                               (2, 9, 35, 35, False), (300, 4, 5, 5, True)]:
+        p = gather_plan(B, C, H, W)
+        assert p["streamed"]
+        g1 = O.gen_sampling_grid(H, W, cp)
+        grid = g1 if shared else np.concatenate([g1 + np.float32(0.004 * i) for i in range(B)], 0)
+        z = rng.standard_normal((B, C, H, W)).astype(np.float32)
+        want = O.grid_sample_border(z, np.repeat(g1, B, 0) if shared else grid)
+        got = _emulate_gather_stream(p, z, grid)
+        assert np.abs(got - want).max() <= 2e-6 * np.abs(want).max(), (B, C, H, W)
